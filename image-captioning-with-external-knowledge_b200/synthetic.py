@@ -1,0 +1,195 @@
+"""
+Synthetic workloads for the caption-decoder path: word maps, input batches and deterministic
+weights with the shapes and value ranges the reference's preprocessing produces.
+
+Shapes/ranges follow: word map layout G/create_input_files.py:311-315 (<pad>=0, <unk>,<start>,<end> last three);
+entity rows [row_idx, distance, azimuth, size, type_idx] with dummy ranges G/create_input_files.py:159-160
+(K: distance up to 10, K/create_input_files.py:174); fact rows [row_idx, subject_idx, predicate_idx], last row =
+<unk_fact> with subject <unk_ent> (K/create_input_files.py:186-187); news entity rows
+[idx, count, in_headline, in_first_par, type, 5 name-word ids] (N/create_input_files.py:173); captions
+<start> w.. <end> <pad>.. with pointer tokens V+e (mask 1) and V+E+f (mask 2) (K/create_input_files.py:287,333);
+K/N store caption_length == padded length (K/create_input_files.py:347), G stores the true length (:262).
+"""
+from __future__ import annotations
+
+import zlib
+from dataclasses import dataclass, replace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class Config:
+    variant: str  # "G" geo-aware | "K" knowledge-aware | "N" news-knowledge-aware
+    B: int
+    T: int
+    E: int
+    F: int
+    V: int
+    P: int = 196
+    D: int = 300
+    H: int = 10
+    L: int = 3
+    ff: int = 512
+
+    @property
+    def has_facts(self) -> bool:
+        return self.variant in ("K", "N")
+
+    @property
+    def M(self) -> int:
+        return self.P + self.E + (self.F if self.has_facts else 0)
+
+    @property
+    def W(self) -> int:
+        return self.V + self.E + (self.F if self.has_facts else 0)
+
+    @property
+    def num_predicates(self) -> int:
+        return {"G": 0, "K": 3000, "N": 3500}[self.variant]
+
+    @property
+    def num_types(self) -> int:
+        return {"G": 1000, "K": 1000, "N": 20}[self.variant]
+
+    @property
+    def num_feat(self) -> int:
+        return {"G": 4, "K": 6, "N": 5}[self.variant]
+
+    @property
+    def ent_cols(self) -> int:
+        return {"G": 5, "K": 5, "N": 10}[self.variant]
+
+    def with_batch(self, B: int) -> "Config":
+        return replace(self, B=B)
+
+
+# BASELINE.json configs; per-GPU batch for the DDP config.
+BASELINE_CONFIGS = {
+    "geo_b32": Config("G", B=32, T=32, E=301, F=0, V=10000),
+    "knowledge_b128": Config("K", B=128, T=102, E=301, F=51, V=10000),
+    "news_b8": Config("N", B=8, T=52, E=101, F=301, V=10000),
+}
+# small parity cases (oracle finishes in seconds; odd sizes on purpose)
+SMALL_CONFIGS = {
+    "G": Config("G", B=3, T=9, E=13, F=0, V=57, P=20),
+    "K": Config("K", B=3, T=11, E=13, F=7, V=57, P=20),
+    "N": Config("N", B=2, T=10, E=9, F=12, V=57, P=20),
+}
+
+
+def make_word_map(V: int) -> Dict[str, int]:
+    wm = {"<pad>": 0}
+    for i in range(1, V - 3):
+        wm[f"w{i}"] = i
+    wm["<unk>"] = V - 3
+    wm["<start>"] = V - 2
+    wm["<end>"] = V - 1
+    assert len(wm) == V
+    return wm
+
+
+def make_batch(cfg: Config, seed: int = 0, equal_lengths: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+    """All tensors on CPU, dtypes as the reference's dataset yields them (G/datasets.py:44-54)."""
+    g = np.random.default_rng(seed)
+    B, T, E, Fn, V = cfg.B, cfg.T, cfg.E, cfg.F, cfg.V
+    start, end, pad = V - 2, V - 1, 0
+    if equal_lengths is None:
+        equal_lengths = cfg.variant in ("K", "N")
+    out: Dict[str, torch.Tensor] = {}
+
+    # ---- contexts -------------------------------------------------------------------------------------------
+    if cfg.variant in ("G", "K"):
+        ent = np.zeros((B, E, 5), dtype=np.float32)
+        ent[:, :, 0] = np.arange(E)
+        ent[:, :, 1] = g.uniform(0.0, 1.0 if cfg.variant == "G" else 10.0, (B, E))
+        ent[:, :, 2] = g.uniform(-179.0, 179.0, (B, E))
+        ent[:, :, 3] = g.uniform(0.0, 0.1, (B, E))
+        ent[:, :, 4] = g.integers(0, 500, (B, E))
+    else:
+        ent = np.zeros((B, E, 10), dtype=np.float32)
+        ent[:, :, 0] = np.arange(E)
+        ent[:, :, 1] = g.integers(0, 21, (B, E))
+        ent[:, :, 2] = g.integers(0, 2, (B, E))
+        ent[:, :, 3] = g.integers(0, 2, (B, E))
+        ent[:, :, 4] = g.integers(0, 20, (B, E))
+        ent[:, :, 5:] = g.integers(0, V, (B, E, 5))
+    out["entities"] = torch.from_numpy(ent)
+    facts = None
+    if cfg.has_facts:
+        facts = np.zeros((B, Fn, 3), dtype=np.int64)
+        facts[:, :, 0] = np.arange(Fn)
+        facts[:, :, 1] = g.integers(0, E - 1, (B, Fn))
+        # few distinct predicates so that several facts share one (exercises the set semantics of the indicator)
+        facts[:, :, 2] = g.integers(0, max(2, min(cfg.num_predicates, 4 * Fn)), (B, Fn))
+        facts[:, Fn - 1, 1] = E - 1  # <unk_fact>: subject <unk_ent>, predicate 0
+        facts[:, Fn - 1, 2] = 0
+        out["facts"] = torch.from_numpy(facts)
+
+    # ---- captions -------------------------------------------------------------------------------------------
+    caps = np.full((B, T), pad, dtype=np.int64)
+    masks = np.zeros((B, T), dtype=np.int64)
+    lens = np.zeros((B, 1), dtype=np.int64)
+    max_content = T - 2
+    for b in range(B):
+        hi = max_content if cfg.variant == "G" else max(3, min(max_content, 40))
+        n = int(g.integers(min(3, hi), hi + 1))
+        toks, mk = [], []
+        last_ent = None
+        for i in range(n):
+            r = g.random()
+            if r < 0.2:
+                e = int(g.integers(0, E))  # may be <unk_ent> (E-1)
+                if cfg.has_facts and g.random() < 0.5:
+                    e = int(facts[b, int(g.integers(0, Fn)), 1])  # an entity that has facts
+                toks.append(V + e)
+                mk.append(1)
+                last_ent = e
+            elif cfg.has_facts and last_ent is not None and r < 0.35:
+                cand = np.nonzero(facts[b, :, 1] == last_ent)[0]
+                f = int(cand[0]) if len(cand) else Fn - 1
+                toks.append(V + E + f)
+                mk.append(2)
+            else:
+                toks.append(int(g.integers(1, V - 3)))
+                mk.append(0)
+        caps[b, 0] = start
+        caps[b, 1 : 1 + n] = toks
+        masks[b, 1 : 1 + n] = mk
+        caps[b, 1 + n] = end
+        lens[b, 0] = T if equal_lengths else n + 2
+    out["captions"] = torch.from_numpy(caps)
+    out["caption_masks"] = torch.from_numpy(masks)
+    out["caption_lengths"] = torch.from_numpy(lens)
+    out["encoder_out"] = torch.from_numpy(g.standard_normal((B, cfg.D, cfg.P)).astype(np.float32) * 0.5)
+    return out
+
+
+def det_weights(shapes: Dict[str, tuple], seed: int = 0, scale: float = 0.08) -> Dict[str, torch.Tensor]:
+    """
+    Deterministic, construction-order-independent weights: every tensor is drawn from a generator keyed by the
+    crc32 of its state_dict key.  LayerNorm scales are 1+noise, biases are non-zero (zero-init biases hide
+    bias/mask ordering bugs).  The positional table is left to the model (not returned).
+    """
+    out = {}
+    for k, shp in shapes.items():
+        if k.endswith("pos_encoder.pe"):
+            continue
+        # the predicate embedding is one module registered under two names (K/models.py:330-331)
+        canon = k.replace("fact_encoder.predicate_embedding", "predicate_embedding")
+        g = np.random.default_rng((zlib.crc32(canon.encode()) + 7919 * seed) & 0xFFFFFFFF)
+        a = g.uniform(-1.0, 1.0, size=shp).astype(np.float32)
+        if ".norm" in k and k.endswith("weight"):
+            a = 1.0 + 0.1 * a
+        elif "embedding" in k:
+            a = a * 0.1
+        elif k in ("fc_entity.weight", "fc_fact.weight"):
+            a = a * 1.5  # pointer scores must compete with vocabulary scores for predict() to emit pointer tokens
+        elif k.startswith("fc_predicate"):
+            a = a * 0.3 + (0.7 if k.endswith("bias") else 0.0)
+        else:
+            a = a * scale
+        out[k] = torch.from_numpy(a)
+    return out

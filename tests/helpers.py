@@ -1,0 +1,44 @@
+"""Shared test helpers: golden fixtures, oracle specs/params, error metrics."""
+import os
+
+import numpy as np
+import torch
+
+import ickb200  # noqa: F401  (import shim)
+from ickb200 import layout, synthetic as syn
+from oracle import decoder_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(variant):
+    return dict(np.load(os.path.join(GOLDEN_DIR, f"golden_{variant}.npz")))
+
+
+def spec_for(cfg):
+    return orc.Spec(cfg.variant, cfg.V, cfg.D, cfg.H, cfg.L, pad=0, start=cfg.V - 2, end=cfg.V - 1)
+
+
+def oracle_params(cfg, seed=0, requires_grad=False):
+    shapes = layout.param_shapes(cfg.variant, cfg.V, cfg.D, cfg.L, cfg.ff, cfg.ff)
+    p = syn.det_weights(shapes, seed=seed)
+    p["pos_encoder.pe"] = orc.positional_table(5000, cfg.D).unsqueeze(1)
+    if requires_grad:
+        for k, v in p.items():
+            if k != "pos_encoder.pe":
+                v.requires_grad_(True)
+    return p
+
+
+def batch_args(cfg, batch):
+    a = [batch["captions"], batch["encoder_out"], batch["caption_masks"], batch["caption_lengths"], batch["entities"]]
+    if cfg.has_facts:
+        a.append(batch["facts"])
+    return a
+
+
+def nmax_err(a, b):
+    """max |a-b| / max |b|  (normalised max error; an absolute floor is needed on near-zero logits)."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

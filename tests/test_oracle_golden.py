@@ -1,0 +1,84 @@
+"""
+CPU: the oracle restatement (oracle/decoder_oracle.py) against the golden vectors produced by the unmodified
+reference modules (tests/golden/make_golden.py) — forward scores, train.py loss, parameter gradients, greedy predict.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import batch_args, load_golden, nmax_err, oracle_params, spec_for
+from ickb200 import synthetic as syn
+from oracle import decoder_oracle as orc
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_inputs_and_weights_regenerate(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    batch = syn.make_batch(cfg, seed=1)
+    for k, v in batch.items():
+        assert np.array_equal(v.numpy(), g[f"in_{k}"]), k
+    p = oracle_params(cfg)
+    chk = sum(float(v.double().abs().sum()) for k, v in sorted(p.items()) if not k.endswith("pe"))
+    assert abs(chk - float(g["weights_checksum"])) <= 1e-9 * abs(chk)
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_forward_loss_grads(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    p = oracle_params(cfg, requires_grad=True)
+    batch = syn.make_batch(cfg, seed=1)
+    batch["encoder_out"].requires_grad_(True)
+    scores, caps, dl = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch))
+    assert np.array_equal(caps.numpy(), g["captions_sorted"])
+    assert dl == g["decode_lengths"].tolist()
+    # fp32, tolerance 1e-4 relative (north_star), measured ~1e-6
+    assert nmax_err(scores.detach(), g["scores"]) < 1e-4
+    loss = orc.caption_loss(scores, caps, dl)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    loss.backward()
+    assert nmax_err(batch["encoder_out"].grad, g["grad_encoder_out"]) < 1e-3
+    for k, v in p.items():
+        if k == "pos_encoder.pe":
+            continue
+        gr = v.grad if v.grad is not None else torch.zeros_like(v)
+        ref_norm = float(g[f"gnorm_{k}"])
+        assert abs(float(gr.double().norm()) - ref_norm) <= 1e-3 * max(ref_norm, 1e-6), k
+        if f"grad_{k}" in g:
+            assert nmax_err(gr, g[f"grad_{k}"]) < 1e-3 or ref_norm < 1e-12, k
+        else:
+            rows = gr.reshape(gr.shape[0], -1)[:: max(1, gr.shape[0] // 7)][:, :64]
+            ref = g[f"gradrows_{k}"]
+            assert float((rows.double() - torch.as_tensor(ref).double()).abs().max()) <= 1e-3 * max(
+                float(np.abs(ref).max()), 1e-6) + 1e-9, k
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_predict_tokens(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    p = oracle_params(cfg)
+    pb = syn.make_batch(cfg, seed=int(g["predict_seed"]))
+    T = int(g["predict_max_len"])
+    with torch.no_grad():
+        for i in range(min(2, cfg.B)):  # the rest of the golden images are covered by the GPU tests
+            out, margins = orc.predict(
+                spec_for(cfg), p, pb["encoder_out"][i : i + 1], T, pb["entities"][i : i + 1],
+                pb["facts"][i : i + 1] if cfg.has_facts else None, return_margins=True)
+            assert out.reshape(-1).tolist() == g["predict_tokens"][i].tolist(), (i, min(margins))
+
+
+def test_indicator_predict_mode_has_no_lag():
+    # K/models.py:406-409: with out_length == 1 every position counts, including the last one
+    cfg = syn.SMALL_CONFIGS["K"]
+    sp = spec_for(cfg)
+    facts = torch.zeros(1, cfg.F, 3, dtype=torch.long)
+    facts[0, :, 1] = torch.arange(cfg.F) % cfg.E
+    facts[0, :, 2] = torch.arange(cfg.F)
+    caps = torch.full((1, 5), cfg.V - 2)
+    caps[0, 4] = cfg.V + 3
+    eb1, pi1 = orc.context_indicators(sp, caps, facts, cfg.E, 1)
+    assert eb1[0, 0, 3] == 1 and pi1[0, 0, 3] == 1 and eb1.sum() == 1
+    ebT, _ = orc.context_indicators(sp, caps, facts, cfg.E, 5)
+    assert ebT.sum() == 0  # teacher-forced: only strictly later positions, and there are none

@@ -1,0 +1,413 @@
+// Multi-head scaled-dot-product attention, forward and backward, for head_dim <= 32 (the reference uses 10 heads of
+// 30, nn.TransformerEncoderLayer/DecoderLayer(300, 10, ...), G/models.py:241-244).  Four call sites: entity and fact
+// self-attention (no mask), decoder causal self-attention, decoder cross-attention over [pixels; entities; facts].
+//
+// Layout: Q/K/V/O rows are (batch, position); head h occupies columns [h*32, h*32+32) ("head layout": the 30 real
+// columns followed by 2 zero pads, produced by the packed projection weights), so a head row is one aligned
+// 64 B (bf16) / 128 B (fp32) vector.  Flash-style: one thread owns one query (fwd, dQ) or one key (dK/dV), the other
+// operand streams through shared memory in tiles and is read as warp-wide broadcasts; the softmax is online
+// (running max / sum in the exp2 domain) so the score matrix never exists in memory.  Attention-probability dropout
+// (torch applies it after the softmax) is regenerated from the counter hash in the backward pass.
+#include "common.cuh"
+#include "ickb200.h"
+
+namespace {
+
+constexpr int HD = 32;    // padded head dim
+constexpr int NT = 128;   // threads per CTA = queries (or keys) per CTA
+constexpr int KT = 64;    // keys per shared-memory tile (fwd / dQ)
+constexpr int QT = 32;    // queries per shared-memory tile (dK/dV)
+
+template <typename T>
+__device__ __forceinline__ void load_row32(const T* p, float* v) {
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) ld8(p + c, v + c);
+}
+template <typename T>
+__device__ __forceinline__ void store_row32(T* p, const float* v) {
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) st8(p + c, v + c);
+}
+
+// cooperative tile load: rows [r0, r0+nrows) of a (rows, ld) matrix, 32 columns starting at col0, into smem as floats
+template <typename T>
+__device__ __forceinline__ void load_tile(const T* base, size_t ld, int r0, int rmax, int nrows, float (*dst)[HD]) {
+    for (int idx = threadIdx.x; idx < nrows * 4; idx += NT) {
+        const int r = idx >> 2, c = (idx & 3) * 8;
+        float v[8];
+        if (r0 + r < rmax) ld8(base + (size_t)(r0 + r) * ld + c, v);
+        else
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        *reinterpret_cast<float4*>(&dst[r][c]) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(&dst[r][c + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__device__ __forceinline__ float dot32(const float* a, const float* b_smem) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(b_smem + c);
+        s = fmaf(a[c], b.x, s);
+        s = fmaf(a[c + 1], b.y, s);
+        s = fmaf(a[c + 2], b.z, s);
+        s = fmaf(a[c + 3], b.w, s);
+    }
+    return s;
+}
+__device__ __forceinline__ void axpy32(float* acc, float a, const float* x_smem) {
+#pragma unroll
+    for (int c = 0; c < HD; c += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(x_smem + c);
+        acc[c] = fmaf(a, x.x, acc[c]);
+        acc[c + 1] = fmaf(a, x.y, acc[c + 1]);
+        acc[c + 2] = fmaf(a, x.z, acc[c + 2]);
+        acc[c + 3] = fmaf(a, x.w, acc[c + 3]);
+    }
+}
+
+struct AttnDims {
+    int B, H, Sq, Sk, dh;
+    int ldq, ldk, ldv, ldo;
+    int causal;
+    float scale_log2;  // (1/sqrt(dh)) * log2(e)
+    float scale;       // 1/sqrt(dh)
+};
+
+// dropout index of probability (b,h,i,j)
+__device__ __forceinline__ uint64_t pidx(const AttnDims& d, int b, int h, int i, int j) {
+    return (((uint64_t)b * d.H + h) * (uint64_t)d.Sq + i) * (uint64_t)d.Sk + j;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, const T* __restrict__ K,
+                                                     const T* __restrict__ V, T* __restrict__ O, float* __restrict__ LSE,
+                                                     AttnDims d, DropCfg drop) {
+    __shared__ __align__(16) float Ks[KT][HD];
+    __shared__ __align__(16) float Vs[KT][HD];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i = blockIdx.x * NT + threadIdx.x;
+    const bool active = i < d.Sq;
+    const T* Kb = K + (size_t)b * d.Sk * d.ldk + h * HD;
+    const T* Vb = V + (size_t)b * d.Sk * d.ldv + h * HD;
+
+    float q[HD], acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) { q[c] = 0.f; acc[c] = 0.f; }
+    if (active) load_row32(Q + ((size_t)b * d.Sq + i) * d.ldq + h * HD, q);
+#pragma unroll
+    for (int c = 0; c < HD; ++c) q[c] = (c < d.dh) ? q[c] * d.scale_log2 : 0.f;  // pad lanes never contribute
+    float m = -INFINITY, l = 0.f;
+
+    // causal: no key beyond the last query of this CTA is visible
+    const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
+    for (int k0 = 0; k0 < kmax; k0 += KT) {
+        __syncthreads();
+        load_tile(Kb, d.ldk, k0, d.Sk, KT, Ks);
+        load_tile(Vb, d.ldv, k0, d.Sk, KT, Vs);
+        __syncthreads();
+        const int nk = min(KT, d.Sk - k0);
+        if (!active) continue;
+        for (int j0 = 0; j0 < nk; j0 += 8) {
+            float s[8];
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = k0 + j0 + jj;
+                const bool vis = (j0 + jj < nk) && (!d.causal || j <= i);
+                s[jj] = vis ? dot32(q, Ks[j0 + jj]) : -INFINITY;
+                cmax = fmaxf(cmax, s[jj]);
+            }
+            if (cmax == -INFINITY) continue;  // whole chunk masked
+            const float mnew = fmaxf(m, cmax);
+            const float corr = exp2f(m - mnew);  // m = -inf on the first visible chunk -> 0
+            l *= corr;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) acc[c] *= corr;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float p = exp2f(s[jj] - mnew);  // masked -> exp2(-inf) = 0
+                l += p;
+                const float pd = p * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, k0 + j0 + jj));
+                axpy32(acc, pd, Vs[j0 + jj]);
+            }
+            m = mnew;
+        }
+    }
+    if (active) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc[c] = (c < d.dh) ? acc[c] * inv : 0.f;
+        store_row32(O + ((size_t)b * d.Sq + i) * d.ldo + h * HD, acc);
+        LSE[((size_t)b * d.H + h) * d.Sq + i] = m + log2f(l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dQ: one thread per query.  Also writes Dsum[b,h,i] = sum_c dO*O for the dK/dV kernel.
+template <typename T>
+__global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q, const T* __restrict__ K,
+                                                        const T* __restrict__ V, const T* __restrict__ O,
+                                                        const T* __restrict__ dO, const float* __restrict__ LSE,
+                                                        float* __restrict__ Dsum, T* __restrict__ dQ, AttnDims d,
+                                                        int lddo, int lddq, DropCfg drop) {
+    __shared__ __align__(16) float Ks[KT][HD];
+    __shared__ __align__(16) float Vs[KT][HD];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i = blockIdx.x * NT + threadIdx.x;
+    const bool active = i < d.Sq;
+    const T* Kb = K + (size_t)b * d.Sk * d.ldk + h * HD;
+    const T* Vb = V + (size_t)b * d.Sk * d.ldv + h * HD;
+
+    float q[HD], go[HD], dq[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) { q[c] = 0.f; go[c] = 0.f; dq[c] = 0.f; }
+    float lse = 0.f, Di = 0.f;
+    if (active) {
+        load_row32(Q + ((size_t)b * d.Sq + i) * d.ldq + h * HD, q);
+        load_row32(dO + ((size_t)b * d.Sq + i) * lddo + h * HD, go);
+        float o[HD];
+        load_row32(O + ((size_t)b * d.Sq + i) * d.ldo + h * HD, o);
+#pragma unroll
+        for (int c = 0; c < HD; ++c) Di = fmaf(go[c], o[c], Di);
+        lse = LSE[((size_t)b * d.H + h) * d.Sq + i];
+        Dsum[((size_t)b * d.H + h) * d.Sq + i] = Di;
+    }
+#pragma unroll
+    for (int c = 0; c < HD; ++c) {
+        q[c] = (c < d.dh) ? q[c] * d.scale_log2 : 0.f;
+        go[c] = (c < d.dh) ? go[c] : 0.f;
+    }
+
+    const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
+    for (int k0 = 0; k0 < kmax; k0 += KT) {
+        __syncthreads();
+        load_tile(Kb, d.ldk, k0, d.Sk, KT, Ks);
+        load_tile(Vb, d.ldv, k0, d.Sk, KT, Vs);
+        __syncthreads();
+        const int nk = min(KT, d.Sk - k0);
+        if (!active) continue;
+        for (int jj = 0; jj < nk; ++jj) {
+            const int j = k0 + jj;
+            if (d.causal && j > i) break;
+            const float p = exp2f(dot32(q, Ks[jj]) - lse);
+            const float dp = dot32(go, Vs[jj]) * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, j));
+            const float ds = p * (dp - Di);
+            axpy32(dq, ds, Ks[jj]);
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < HD; ++c) dq[c] = (c < d.dh) ? dq[c] * d.scale : 0.f;
+        store_row32(dQ + ((size_t)b * d.Sq + i) * lddq + h * HD, dq);
+    }
+}
+
+// dK, dV: one thread per key; queries stream through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(NT) mha_bwd_dkv_kernel(const T* __restrict__ Q, const T* __restrict__ K,
+                                                         const T* __restrict__ V, const T* __restrict__ dO,
+                                                         const float* __restrict__ LSE, const float* __restrict__ Dsum,
+                                                         T* __restrict__ dK, T* __restrict__ dV, AttnDims d, int lddo,
+                                                         int lddk, int lddv, DropCfg drop) {
+    __shared__ __align__(16) float Qs[QT][HD];
+    __shared__ __align__(16) float Gs[QT][HD];
+    __shared__ float Ls[QT], Ds[QT];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int j = blockIdx.x * NT + threadIdx.x;
+    const bool active = j < d.Sk;
+    const T* Qb = Q + (size_t)b * d.Sq * d.ldq + h * HD;
+    const T* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
+    const float* Lb = LSE + ((size_t)b * d.H + h) * d.Sq;
+    const float* Db = Dsum + ((size_t)b * d.H + h) * d.Sq;
+
+    float k[HD], v[HD], dk[HD], dv[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) { k[c] = 0.f; v[c] = 0.f; dk[c] = 0.f; dv[c] = 0.f; }
+    if (active) {
+        load_row32(K + ((size_t)b * d.Sk + j) * d.ldk + h * HD, k);
+        load_row32(V + ((size_t)b * d.Sk + j) * d.ldv + h * HD, v);
+    }
+#pragma unroll
+    for (int c = 0; c < HD; ++c) {
+        k[c] = (c < d.dh) ? k[c] * d.scale_log2 : 0.f;
+        v[c] = (c < d.dh) ? v[c] : 0.f;
+    }
+
+    // causal: queries before the first key of this CTA see none of its keys
+    const int qbeg = d.causal ? (int)(blockIdx.x * NT) / QT * QT : 0;
+    for (int q0 = qbeg; q0 < d.Sq; q0 += QT) {
+        __syncthreads();
+        load_tile(Qb, d.ldq, q0, d.Sq, QT, Qs);
+        load_tile(Gb, lddo, q0, d.Sq, QT, Gs);
+        if (threadIdx.x < QT) {
+            const int i = q0 + threadIdx.x;
+            Ls[threadIdx.x] = i < d.Sq ? Lb[i] : 0.f;
+            Ds[threadIdx.x] = i < d.Sq ? Db[i] : 0.f;
+        }
+        __syncthreads();
+        const int nq = min(QT, d.Sq - q0);
+        if (!active) continue;
+        for (int ii = 0; ii < nq; ++ii) {
+            const int i = q0 + ii;
+            if (d.causal && j > i) continue;
+            const float p = exp2f(dot32(k, Qs[ii]) - Ls[ii]);
+            const float mul = ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, j));
+            axpy32(dv, p * mul, Gs[ii]);
+            const float dp = dot32(v, Gs[ii]) * mul;
+            const float ds = p * (dp - Ds[ii]);
+            axpy32(dk, ds, Qs[ii]);
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int c = 0; c < HD; ++c) {
+            dk[c] = (c < d.dh) ? dk[c] * d.scale : 0.f;
+            dv[c] = (c < d.dh) ? dv[c] : 0.f;
+        }
+        store_row32(dK + ((size_t)b * d.Sk + j) * lddk + h * HD, dk);
+        store_row32(dV + ((size_t)b * d.Sk + j) * lddv + h * HD, dv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental (KV-cached) decode attention: one query per (batch, head); a warp per (b,h), lanes split the keys.
+// K/V caches hold `klen[b]`-many valid rows (or `klen_all` if klen is null).
+template <typename T>
+__global__ void __launch_bounds__(128) mha_decode_kernel(const T* __restrict__ Q, const T* __restrict__ K,
+                                                         const T* __restrict__ V, T* __restrict__ O, int B, int H, int dh,
+                                                         int ldq, int ldk, int ldv, int ldo, long long kbatch_stride,
+                                                         long long vbatch_stride, int klen, float scale_log2) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B * H) return;
+    const int b = w / H, h = w % H;
+    float q[HD];
+    load_row32(Q + (size_t)b * ldq + h * HD, q);
+#pragma unroll
+    for (int c = 0; c < HD; ++c) q[c] = (c < dh) ? q[c] * scale_log2 : 0.f;
+    const T* Kb = K + (size_t)b * kbatch_stride + h * HD;
+    const T* Vb = V + (size_t)b * vbatch_stride + h * HD;
+    float m = -INFINITY, l = 0.f, acc[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+    for (int j = lane; j < klen; j += 32) {
+        float kv[HD];
+        load_row32(Kb + (size_t)j * ldk, kv);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) s = fmaf(q[c], kv[c], s);
+        const float mnew = fmaxf(m, s);
+        const float corr = exp2f(m - mnew);
+        const float p = exp2f(s - mnew);
+        l = l * corr + p;
+        load_row32(Vb + (size_t)j * ldv, kv);
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc[c] = fmaf(p, kv[c], acc[c] * corr);
+        m = mnew;
+    }
+    // merge the 32 partial softmaxes
+    const float mall = warp_max(m);
+    const float f = (m == -INFINITY) ? 0.f : exp2f(m - mall);
+    l = warp_sum(l * f);
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = warp_sum(acc[c] * f);
+    if (lane == 0) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc[c] = (c < dh) ? acc[c] * inv : 0.f;
+        store_row32(O + (size_t)b * ldo + h * HD, acc);
+    }
+}
+
+int check_dims(const char* what, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo) {
+    ICK_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0, "%s: bad sizes B=%d H=%d Sq=%d Sk=%d", what, B, H, Sq, Sk);
+    ICK_REQUIRE(dh > 0 && dh <= HD, "%s: head_dim %d not in (0, 32]", what, dh);
+    ICK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "%s: leading dims must be multiples of 8", what);
+    ICK_REQUIRE(ldq >= H * HD && ldk >= H * HD && ldv >= H * HD && ldo >= H * HD, "%s: leading dims smaller than H*32", what);
+    return ICK_OK;
+}
+
+AttnDims make_dims(int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int causal) {
+    AttnDims d;
+    d.B = B; d.H = H; d.Sq = Sq; d.Sk = Sk; d.dh = dh;
+    d.ldq = ldq; d.ldk = ldk; d.ldv = ldv; d.ldo = ldo;
+    d.causal = causal;
+    d.scale = 1.0f / sqrtf((float)dh);
+    d.scale_log2 = d.scale * 1.4426950408889634f;
+    return d;
+}
+
+}  // namespace
+
+extern "C" int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O, float* lse, int dt, int B, int H, int Sq,
+                           int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int causal, float drop_p, unsigned seed,
+                           unsigned site, cudaStream_t stream) {
+    int rc = check_dims("mha_fwd", B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo);
+    if (rc) return rc;
+    ICK_REQUIRE(!causal || Sq == Sk, "mha_fwd: causal needs Sq == Sk");
+    AttnDims d = make_dims(B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal);
+    DropCfg dc = make_drop(drop_p, seed, site);
+    dim3 grid((Sq + NT - 1) / NT, H, B);
+    if (dt == ICK_F32)
+        mha_fwd_kernel<float><<<grid, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (float*)O, lse, d, dc);
+    else if (dt == ICK_BF16)
+        mha_fwd_kernel<bf16><<<grid, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, lse, d, dc);
+    else {
+        ick_set_error("mha_fwd: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("mha_fwd");
+}
+
+extern "C" int ick_mha_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse,
+                           float* dsum, void* dQ, void* dK, void* dV, int dt, int B, int H, int Sq, int Sk, int dh, int ldq,
+                           int ldk, int ldv, int ldo, int lddo, int lddq, int lddk, int lddv, int causal, float drop_p,
+                           unsigned seed, unsigned site, cudaStream_t stream) {
+    int rc = check_dims("mha_bwd", B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo);
+    if (rc) return rc;
+    ICK_REQUIRE(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "mha_bwd: grad leading dims must be multiples of 8");
+    ICK_REQUIRE(!causal || Sq == Sk, "mha_bwd: causal needs Sq == Sk");
+    AttnDims d = make_dims(B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal);
+    DropCfg dc = make_drop(drop_p, seed, site);
+    dim3 gq((Sq + NT - 1) / NT, H, B), gk((Sk + NT - 1) / NT, H, B);
+    if (dt == ICK_F32) {
+        mha_bwd_dq_kernel<float><<<gq, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (const float*)O,
+                                                        (const float*)dO, lse, dsum, (float*)dQ, d, lddo, lddq, dc);
+        mha_bwd_dkv_kernel<float><<<gk, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (const float*)dO,
+                                                         lse, dsum, (float*)dK, (float*)dV, d, lddo, lddk, lddv, dc);
+    } else if (dt == ICK_BF16) {
+        mha_bwd_dq_kernel<bf16><<<gq, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)O,
+                                                       (const bf16*)dO, lse, dsum, (bf16*)dQ, d, lddo, lddq, dc);
+        mha_bwd_dkv_kernel<bf16><<<gk, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)dO, lse,
+                                                        dsum, (bf16*)dK, (bf16*)dV, d, lddo, lddk, lddv, dc);
+    } else {
+        ick_set_error("mha_bwd: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("mha_bwd");
+}
+
+extern "C" int ick_mha_decode(const void* Q, const void* K, const void* V, void* O, int dt, int B, int H, int dh, int ldq,
+                              int ldk, int ldv, int ldo, long long kbatch_stride, long long vbatch_stride, int klen,
+                              cudaStream_t stream) {
+    ICK_REQUIRE(B > 0 && H > 0 && klen > 0 && dh > 0 && dh <= HD, "mha_decode: bad sizes");
+    ICK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && kbatch_stride % 8 == 0 && vbatch_stride % 8 == 0,
+                "mha_decode: strides must be multiples of 8");
+    const float sl2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+    const int warps = B * H;
+    dim3 grid((warps * 32 + 127) / 128);
+    if (dt == ICK_F32)
+        mha_decode_kernel<float><<<grid, 128, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (float*)O, B, H, dh,
+                                                           ldq, ldk, ldv, ldo, kbatch_stride, vbatch_stride, klen, sl2);
+    else if (dt == ICK_BF16)
+        mha_decode_kernel<bf16><<<grid, 128, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, B, H, dh, ldq,
+                                                          ldk, ldv, ldo, kbatch_stride, vbatch_stride, klen, sl2);
+    else {
+        ick_set_error("mha_decode: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("mha_decode");
+}

@@ -1,0 +1,124 @@
+// Shared device helpers for the ickb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define ICK_OK 0
+#define ICK_ERR_ARG 1
+#define ICK_ERR_CUDA 2
+#define ICK_ERR_UNSUPPORTED 3
+
+// dtype codes of the C-ABI
+#define ICK_F32 0
+#define ICK_BF16 1
+
+void ick_set_error(const char* fmt, ...);
+int ick_check_launch(const char* what);
+
+#define ICK_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            ick_set_error(__VA_ARGS__); \
+            return ICK_ERR_ARG;         \
+        }                               \
+    } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+// ---- dtype conversion -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+// load / store 2 consecutive elements (address must be 2-element aligned)
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const bf16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// load 8 consecutive elements as floats (address must be 8-element aligned: 32 B for f32, 16 B for bf16)
+__device__ __forceinline__ void ld8(const float* p, float* v) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---- warp reductions ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- counter-based dropout hash -------------------------------------------------------------------------------------
+// keep(seed, site, idx) is a pure function so the backward pass regenerates the mask instead of storing it.
+// tests/dropout_ref.py holds the numpy port used to inject identical masks into the oracle.
+__host__ __device__ __forceinline__ uint32_t ick_hash(uint32_t seed, uint32_t site, uint64_t idx) {
+    uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
+    uint32_t h = (lo * 0x9E3779B1u) ^ ((hi + site * 0x7F4A7C15u) * 0x85EBCA77u) ^ seed;
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+// thr = p * 2^32 (0 disables dropout); returns the multiplier 0 or 1/(1-p)
+__device__ __forceinline__ float ick_drop_mul(uint32_t thr, float inv_keep, uint32_t seed, uint32_t site, uint64_t idx) {
+    if (thr == 0u) return 1.0f;
+    return ick_hash(seed, site, idx) >= thr ? inv_keep : 0.0f;
+}
+
+struct DropCfg {
+    uint32_t thr;    // p * 2^32, 0 = off
+    float inv_keep;  // 1 / (1 - p)
+    uint32_t seed;
+    uint32_t site;
+};
+static inline DropCfg make_drop(float p, unsigned seed, unsigned site) {
+    DropCfg d;
+    if (p <= 0.f) {
+        d.thr = 0u;
+        d.inv_keep = 1.f;
+    } else {
+        double t = (double)p * 4294967296.0;
+        d.thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+        d.inv_keep = 1.0f / (1.0f - p);
+    }
+    d.seed = seed;
+    d.site = site;
+    return d;
+}

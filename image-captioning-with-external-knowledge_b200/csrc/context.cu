@@ -1,0 +1,729 @@
+// Context-preparation and pointer-head kernels of the caption decoder (all HBM/latency-bound integer + gather work):
+//   entity encoder      G/models.py:82-104, K/models.py:82-133, N/models.py:79-134
+//   fact encoder        K/models.py:170-188
+//   caption embedder    G/models.py:143-181, K/models.py:209-259  (+ sqrt(d) scale and positional table, G:355-357)
+//   pixel hand-off      encoder_out.permute(2,0,1) + cat, G/models.py:347-349
+//   context indicators  K/models.py:380-418 as a first-mention scan (no B*T host syncs) + predicate gate K:436-437
+//   pointer heads       fc_entity / fc_fact as a bilinear form, K/models.py:440-452 (no (T,B,E,300) tensor)
+// Row layout everywhere: (batch, position) rows of `ld` elements, logical width D, pad columns [D, ld) zero.
+#include "common.cuh"
+#include "ickb200.h"
+
+namespace {
+
+constexpr int FIRST_NONE = 1 << 29;  // "never mentioned" sentinel for first_t / tmin
+
+__device__ __forceinline__ float east_dist(float az) {
+    // G/models.py:106-115
+    return (az >= -90.f ? fabsf(90.f - az) : 90.f + fabsf(az + 180.f)) / 180.f;
+}
+
+// number of facts whose subject is entity e (0 for the last slot <unk_ent>), computed by one warp
+__device__ __forceinline__ float fact_count_warp(const long long* facts_b, int F, int e, int E, int lane) {
+    if (e == E - 1) return 0.f;
+    int c = 0;
+    for (int f = lane; f < F; f += 32) c += (facts_b[3 * f + 1] == (long long)e);
+    return warp_sum((float)c);
+}
+
+// hand-made feature columns + type embedding (before the N-variant name multiply)
+__device__ __forceinline__ float ent_base(int variant, const float* er, float cnt, const float* type_row, int nf, int c) {
+    if (c >= nf) return type_row[c - nf];
+    if (variant == 2) {  // N
+        switch (c) {
+            case 0: return er[1];
+            case 1: return er[2];
+            case 2: return er[3];
+            case 3: return cnt;
+            default: return cnt > 0.f ? 1.f : 0.f;
+        }
+    }
+    switch (c) {
+        case 0: return er[1];
+        case 1: return fabsf(er[2]) / 180.f;
+        case 2: return east_dist(er[2]);
+        case 3: return er[3];
+        case 4: return cnt;
+        default: return cnt > 0.f ? 1.f : 0.f;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) entity_encode_fwd_kernel(const float* __restrict__ ent, const long long* __restrict__ facts,
+                                                                const float* __restrict__ type_emb, const T* __restrict__ wemb,
+                                                                T* __restrict__ out, int variant, int B, int E, int C, int F,
+                                                                int D, int ld, int ldw, int ntypes, int V) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * E) return;
+    const int b = row / E, e = row % E;
+    const float* er = ent + (size_t)row * C;
+    const int nf = variant == 0 ? 4 : (variant == 1 ? 6 : 5);
+    float cnt = 0.f;
+    if (variant != 0) cnt = fact_count_warp(facts + (size_t)b * F * 3, F, e, E, lane);
+    int ty = (int)er[4];
+    ty = min(max(ty, 0), ntypes - 1);
+    const float* trow = type_emb + (size_t)ty * (D - nf);
+    int nm[5] = {0, 0, 0, 0, 0};
+    if (variant == 2)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) nm[k] = min(max((int)er[5 + k], 0), V - 1);
+    T* o = out + (size_t)row * ld;
+    for (int c = lane; c < ld; c += 32) {
+        float v = 0.f;
+        if (c < D) {
+            v = ent_base(variant, er, cnt, trow, nf, c);
+            if (variant == 2) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) a += to_f(wemb[(size_t)nm[k] * ldw + c]);
+                v *= a / 5.f;
+            }
+        }
+        o[c] = from_f<T>(v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) entity_encode_bwd_kernel(const float* __restrict__ dEnt, const float* __restrict__ ent,
+                                                                const long long* __restrict__ facts,
+                                                                const float* __restrict__ type_emb, const T* __restrict__ wemb,
+                                                                float* __restrict__ gflat, int type_off, int word_off, int variant,
+                                                                int B, int E, int C, int F, int D, int ld, int ldw, int ntypes,
+                                                                int V) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * E) return;
+    const int b = row / E, e = row % E;
+    const float* er = ent + (size_t)row * C;
+    const int nf = variant == 0 ? 4 : (variant == 1 ? 6 : 5);
+    int ty = (int)er[4];
+    ty = min(max(ty, 0), ntypes - 1);
+    const float* g = dEnt + (size_t)row * ld;
+    float* dtype_row = gflat + type_off + (size_t)ty * (D - nf);
+    if (variant != 2) {
+        for (int c = nf + lane; c < D; c += 32) atomicAdd(dtype_row + (c - nf), g[c]);
+        return;
+    }
+    const float cnt = fact_count_warp(facts + (size_t)b * F * 3, F, e, E, lane);
+    const float* trow = type_emb + (size_t)ty * (D - nf);
+    int nm[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nm[k] = min(max((int)er[5 + k], 0), V - 1);
+    for (int c = lane; c < D; c += 32) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a += to_f(wemb[(size_t)nm[k] * ldw + c]);
+        a /= 5.f;
+        const float base = ent_base(2, er, cnt, trow, nf, c);
+        const float gv = g[c];
+        if (c >= nf) atomicAdd(dtype_row + (c - nf), gv * a);
+        const float dn = gv * base / 5.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(gflat + word_off + (size_t)nm[k] * D + c, dn);
+    }
+}
+
+// ---- fact encoder ----------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fact_encode_fwd_kernel(const long long* __restrict__ facts, const T* __restrict__ entenc,
+                                                              const float* __restrict__ pred_emb, T* __restrict__ out, int B, int E,
+                                                              int F, int D, int ld, int NP) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * F) return;
+    const int b = row / F;
+    const int subj = min(max((int)facts[(size_t)row * 3 + 1], 0), E - 1);
+    const int pred = min(max((int)facts[(size_t)row * 3 + 2], 0), NP - 1);
+    const T* er = entenc + ((size_t)b * E + subj) * ld;
+    const float* pr = pred_emb + (size_t)pred * D;
+    T* o = out + (size_t)row * ld;
+    for (int c = lane; c < ld; c += 32) o[c] = from_f<T>(c < D ? to_f(er[c]) + pr[c] : 0.f);
+}
+
+__global__ void __launch_bounds__(256) fact_encode_bwd_kernel(const float* __restrict__ dFact, const long long* __restrict__ facts,
+                                                              float* __restrict__ dEnt, float* __restrict__ gflat, int pred_off,
+                                                              int B, int E, int F, int D, int ld, int NP) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * F) return;
+    const int b = row / F;
+    const int subj = min(max((int)facts[(size_t)row * 3 + 1], 0), E - 1);
+    const int pred = min(max((int)facts[(size_t)row * 3 + 2], 0), NP - 1);
+    const float* g = dFact + (size_t)row * ld;
+    float* de = dEnt + ((size_t)b * E + subj) * ld;
+    float* dp = gflat + pred_off + (size_t)pred * D;
+    for (int c = lane; c < D; c += 32) {
+        const float v = g[c];
+        atomicAdd(de + c, v);
+        atomicAdd(dp + c, v);
+    }
+}
+
+// ---- caption embedder ------------------------------------------------------------------------------------------------
+struct TokSel {
+    int kind;  // 0 word, 1 entity, 2 fact
+    int idx;
+};
+__device__ __forceinline__ TokSel select_token(long long tok, long long mask, int V, int E, int F, int pad) {
+    TokSel s;
+    if (mask == 1) {
+        long long e = tok - V;
+        s.kind = 1;
+        s.idx = (e < 0 || e >= E) ? E - 1 : (int)e;  // out-of-range -> <unk_ent> (last slot), G/models.py:160
+    } else if (mask == 2 && F > 0) {
+        long long f = tok - V - E;
+        s.kind = 2;
+        s.idx = (f < 0 || f >= F) ? F - 1 : (int)f;  // K/models.py:232
+    } else {
+        s.kind = 0;
+        s.idx = (tok >= V || tok < 0) ? pad : (int)tok;  // pointer ids embed as <pad>, G/models.py:165-166
+    }
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) caption_embed_fwd_kernel(const long long* __restrict__ caps, const long long* __restrict__ masks,
+                                                                const T* __restrict__ wemb, const T* __restrict__ entenc,
+                                                                const T* __restrict__ factenc, const float* __restrict__ pe,
+                                                                T* __restrict__ out, int B, int Tstride, int t0, int Tn, int V, int E,
+                                                                int F, int D, int ld, int ldw, int pad, float scale, DropCfg drop) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * Tn) return;
+    const int b = row / Tn, t = t0 + row % Tn;
+    const TokSel s = select_token(caps[(size_t)b * Tstride + t], masks[(size_t)b * Tstride + t], V, E, F, pad);
+    const T* src = s.kind == 0 ? wemb + (size_t)s.idx * ldw
+                 : s.kind == 1 ? entenc + ((size_t)b * E + s.idx) * ld
+                               : factenc + ((size_t)b * F + s.idx) * ld;
+    const float* per = pe + (size_t)t * D;
+    T* o = out + (size_t)row * ld;
+    for (int c = lane; c < ld; c += 32) {
+        float v = 0.f;
+        if (c < D)
+            v = (to_f(src[c]) * scale + per[c]) *
+                ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, (uint64_t)row * (uint64_t)D + c);
+        o[c] = from_f<T>(v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restrict__ dX, const long long* __restrict__ caps,
+                                                                const long long* __restrict__ masks, float* __restrict__ dEnt,
+                                                                float* __restrict__ dFact, float* __restrict__ gflat, int word_off,
+                                                                int B, int T_, int V, int E, int F, int D, int ld, int pad, float scale,
+                                                                DropCfg drop) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= B * T_) return;
+    const int b = row / T_;
+    const TokSel s = select_token(caps[row], masks[row], V, E, F, pad);
+    float* dst = s.kind == 0 ? gflat + word_off + (size_t)s.idx * D
+               : s.kind == 1 ? dEnt + ((size_t)b * E + s.idx) * ld
+                             : dFact + ((size_t)b * F + s.idx) * ld;
+    const T* g = dX + (size_t)row * ld;
+    for (int c = lane; c < D; c += 32) {
+        const float v = to_f(g[c]) * scale *
+                        ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, (uint64_t)row * (uint64_t)D + c);
+        atomicAdd(dst + c, v);
+    }
+}
+
+// ---- pixels: (B, D, P) fp32 channel-major  <->  memory rows (b*M + p, c) ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pixels_fwd_kernel(const float* __restrict__ enc, T* __restrict__ mem, int D, int P, int M, int ld) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        tile[i][tx] = (c < D && p < P) ? enc[((size_t)b * D + c) * P + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + tx;
+        if (p < P && c < ld) mem[((size_t)b * M + p) * ld + c] = from_f<T>(c < D ? tile[tx][i] : 0.f);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pixels_bwd_kernel(const T* __restrict__ dmem, float* __restrict__ denc, int D, int P, int M, int ld) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + tx;
+        tile[i][tx] = (p < P && c < D) ? to_f(dmem[((size_t)b * M + p) * ld + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        if (c < D && p < P) denc[((size_t)b * D + c) * P + p] = tile[tx][i];
+    }
+}
+
+// ---- context indicators ----------------------------------------------------------------------------------------------
+// first_t[b,f]: first caption position holding an entity token (value in [V, V+E)) whose slot is the subject of fact f.
+// tmin[b,f]   : for the representative (lowest-index) fact of each distinct predicate, the earliest first_t over all
+//               facts sharing that predicate; FIRST_NONE for the others (the predicate indicator is a SET of predicates).
+__global__ void __launch_bounds__(256) fact_first_mention_kernel(const long long* __restrict__ caps, const long long* __restrict__ facts,
+                                                                 int* __restrict__ first_t, int* __restrict__ tmin, int T_, int F,
+                                                                 int V, int E) {
+    extern __shared__ int sm[];
+    int* sfirst = sm;
+    int* spred = sm + F;
+    const int b = blockIdx.x;
+    const long long* cb = caps + (size_t)b * T_;
+    const long long* fb = facts + (size_t)b * F * 3;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const long long subj = fb[3 * f + 1];
+        int first = FIRST_NONE;
+        for (int t = 0; t < T_; ++t) {
+            const long long tok = cb[t];
+            if (tok >= V && tok < (long long)V + E && tok - V == subj) { first = t; break; }
+        }
+        sfirst[f] = first;
+        spred[f] = (int)fb[3 * f + 2];
+        first_t[(size_t)b * F + f] = first;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const int p = spred[f];
+        int tm = FIRST_NONE;
+        bool rep = true;
+        for (int g = 0; g < F; ++g)
+            if (spred[g] == p) {
+                tm = min(tm, sfirst[g]);
+                if (g < f) rep = false;
+            }
+        tmin[(size_t)b * F + f] = rep ? tm : FIRST_NONE;
+    }
+}
+
+// gate[b,t,:] = bias + sum_{f representative, tmin[b,f] < t + lag} WpT[pred_f, :]   (= fc_predicate(predicate_indicator))
+// and, fused, hg = h * gate (the input of fc_vocab, K/models.py:437).  lag = 0 teacher-forced, 1 in predict mode.
+template <typename T>
+__global__ void __launch_bounds__(128) pred_gate_fwd_kernel(const int* __restrict__ tmin, const long long* __restrict__ facts,
+                                                            const float* __restrict__ WpT, const float* __restrict__ bias,
+                                                            const T* __restrict__ h, T* __restrict__ gate, T* __restrict__ hg, int Tn,
+                                                            int t0, int F, int D, int ld, int ldp, int NP, int lag) {
+    extern __shared__ int sact[];  // predicate ids of the active facts
+    __shared__ int nact;
+    const int b = blockIdx.y, tt = blockIdx.x, t = t0 + tt;
+    if (threadIdx.x == 0) nact = 0;
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x)
+        if (tmin[(size_t)b * F + f] < t + lag) {
+            const int p = min(max((int)facts[((size_t)b * F + f) * 3 + 2], 0), NP - 1);
+            sact[atomicAdd(&nact, 1)] = p;
+        }
+    __syncthreads();
+    const size_t row = (size_t)b * Tn + tt;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+        float g = 0.f;
+        if (c < D) {
+            g = bias[c];
+            for (int k = 0; k < nact; ++k) g += WpT[(size_t)sact[k] * ldp + c];
+        }
+        gate[row * ld + c] = from_f<T>(g);
+        if (hg) hg[row * ld + c] = from_f<T>(c < D ? to_f(h[row * ld + c]) * g : 0.f);
+    }
+}
+
+// dG = dHG * h ; dH = dHG * gate
+template <typename T>
+__global__ void __launch_bounds__(256) gate_mul_bwd_kernel(const T* __restrict__ dHG, const T* __restrict__ h, const T* __restrict__ gate,
+                                                           T* __restrict__ dG, T* __restrict__ dH, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float g = to_f(dHG[i]);
+        dG[i] = from_f<T>(g * to_f(h[i]));
+        dH[i] = from_f<T>(g * to_f(gate[i]));
+    }
+}
+
+// dWp[c, pred_f] += sum_{t: tmin < t + lag} dG[b,t,c]  (fc_predicate.weight is (D, NP)); one CTA per (b, f)
+template <typename T>
+__global__ void __launch_bounds__(128) pred_gate_bwd_kernel(const T* __restrict__ dG, const int* __restrict__ tmin,
+                                                            const long long* __restrict__ facts, float* __restrict__ gflat, int wp_off,
+                                                            int T_, int F, int D, int ld, int NP, int lag) {
+    const int b = blockIdx.y, f = blockIdx.x;
+    const int tm = tmin[(size_t)b * F + f];
+    if (tm >= FIRST_NONE) return;
+    const int p = min(max((int)facts[((size_t)b * F + f) * 3 + 2], 0), NP - 1);
+    const int tbeg = max(0, tm + 1 - lag);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s = 0.f;
+        for (int t = tbeg; t < T_; ++t) s += to_f(dG[((size_t)b * T_ + t) * ld + c]);
+        atomicAdd(gflat + wp_off + (size_t)c * NP + p, s);
+    }
+}
+
+// ---- pointer heads -----------------------------------------------------------------------------------------------------
+// scores[b,t,col0+s] = bias + mask(b,t,s) * sum_d h[b,t,d] * w[d] * ctx[b,s,d];   mask = first_t[b,s] < t + lag (facts only)
+constexpr int PT_T = 16;  // time steps per CTA
+template <typename T>
+__global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ h, const T* __restrict__ ctx, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const int* __restrict__ first_t,
+                                                          float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
+                                                          int col0, int lag) {
+    extern __shared__ __align__(16) float hw[];  // [PT_T][Dp]
+    const int Dp = (D + 7) & ~7;
+    const int b = blockIdx.z, tt0 = blockIdx.y * PT_T;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int idx = threadIdx.x; idx < PT_T * Dp; idx += blockDim.x) {
+        const int t = idx / Dp, d = idx % Dp;
+        hw[idx] = (tt0 + t < Tn && d < D) ? to_f(h[((size_t)b * Tn + tt0 + t) * ld + d]) * w[d] : 0.f;
+    }
+    __syncthreads();
+    if (s >= S) return;
+    float acc[PT_T];
+#pragma unroll
+    for (int t = 0; t < PT_T; ++t) acc[t] = 0.f;
+    const T* cr = ctx + ((size_t)b * S + s) * ld;
+    for (int d = 0; d < Dp; d += 8) {
+        float c[8];
+        ld8(cr + d, c);  // pad columns of ctx rows are zero and hw is zero there too
+#pragma unroll
+        for (int t = 0; t < PT_T; ++t) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&hw[t * Dp + d]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&hw[t * Dp + d + 4]);
+            acc[t] += a0.x * c[0] + a0.y * c[1] + a0.z * c[2] + a0.w * c[3] + a1.x * c[4] + a1.y * c[5] + a1.z * c[6] + a1.w * c[7];
+        }
+    }
+    const float bv = bias[0];
+    const int ft = first_t ? first_t[(size_t)b * S + s] : -1;
+#pragma unroll
+    for (int t = 0; t < PT_T; ++t) {
+        if (tt0 + t >= Tn) break;
+        const float m = (ft < t0 + tt0 + t + lag) ? 1.f : 0.f;
+        scores[((size_t)b * Tn + tt0 + t) * lds + col0 + s] = acc[t] * m + bv;
+    }
+}
+
+constexpr int PB_D = 32;  // feature columns per CTA in the backward kernels
+// dCtx[b,s,d] += w[d] * sum_t m * dS[b,t,col0+s] * h[b,t,d];   dbias += sum m-independent dS   (thread per slot)
+template <typename T>
+__global__ void __launch_bounds__(128) pointer_bwd_ctx_kernel(const T* __restrict__ dS, const T* __restrict__ h, const float* __restrict__ w,
+                                                              const int* __restrict__ first_t, float* __restrict__ dCtx,
+                                                              float* __restrict__ gflat, int bias_off, int T_, int S, int D, int ld,
+                                                              int ldds, int col0, int lag) {
+    __shared__ __align__(16) float hs[32][PB_D];
+    __shared__ float red[4];
+    const int b = blockIdx.z, d0 = blockIdx.y * PB_D;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = s < S;
+    const int ft = (first_t && active) ? first_t[(size_t)b * S + s] : -1;
+    float acc[PB_D];
+#pragma unroll
+    for (int i = 0; i < PB_D; ++i) acc[i] = 0.f;
+    float bsum = 0.f;
+    for (int tb = 0; tb < T_; tb += 32) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * PB_D; idx += blockDim.x) {
+            const int t = idx / PB_D, d = idx % PB_D;
+            hs[t][d] = (tb + t < T_ && d0 + d < D) ? to_f(h[((size_t)b * T_ + tb + t) * ld + d0 + d]) : 0.f;
+        }
+        __syncthreads();
+        if (!active) continue;
+        const int nt = min(32, T_ - tb);
+        for (int t = 0; t < nt; ++t) {
+            const float g = to_f(dS[((size_t)b * T_ + tb + t) * ldds + col0 + s]);
+            bsum += g;
+            if (ft < tb + t + lag) {
+#pragma unroll
+                for (int i = 0; i < PB_D; i += 4) {
+                    const float4 hv = *reinterpret_cast<const float4*>(&hs[t][i]);
+                    acc[i] = fmaf(g, hv.x, acc[i]);
+                    acc[i + 1] = fmaf(g, hv.y, acc[i + 1]);
+                    acc[i + 2] = fmaf(g, hv.z, acc[i + 2]);
+                    acc[i + 3] = fmaf(g, hv.w, acc[i + 3]);
+                }
+            }
+        }
+    }
+    if (active) {
+        float* o = dCtx + ((size_t)b * S + s) * ld + d0;
+#pragma unroll
+        for (int i = 0; i < PB_D; ++i)
+            if (d0 + i < D) o[i] += acc[i] * w[d0 + i];
+    }
+    if (blockIdx.y == 0) {
+        bsum = warp_sum(active ? bsum : 0.f);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bsum;
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(gflat + bias_off, red[0] + red[1] + red[2] + red[3]);
+    }
+}
+
+// G[t,d] = sum_s m * dS[b,t,col0+s] * ctx[b,s,d];  dH[b,t,d] += w[d]*G;  dw[d] += sum_{b,t} h[b,t,d]*G   (thread per step)
+template <typename T>
+__global__ void __launch_bounds__(128) pointer_bwd_h_kernel(const T* __restrict__ dS, const T* __restrict__ h, const T* __restrict__ ctx,
+                                                            const float* __restrict__ w, const int* __restrict__ first_t,
+                                                            T* __restrict__ dH, float* __restrict__ gflat, int w_off, int T_, int S, int D,
+                                                            int ld, int ldds, int col0, int lag) {
+    __shared__ __align__(16) float cs[32][PB_D];
+    __shared__ int sft[32];
+    __shared__ float red[4][PB_D];
+    const int b = blockIdx.z, d0 = blockIdx.y * PB_D;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < T_;
+    float acc[PB_D];
+#pragma unroll
+    for (int i = 0; i < PB_D; ++i) acc[i] = 0.f;
+    for (int sb = 0; sb < S; sb += 32) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * PB_D; idx += blockDim.x) {
+            const int s = idx / PB_D, d = idx % PB_D;
+            cs[s][d] = (sb + s < S && d0 + d < D) ? to_f(ctx[((size_t)b * S + sb + s) * ld + d0 + d]) : 0.f;
+        }
+        if (threadIdx.x < 32) sft[threadIdx.x] = (first_t && sb + threadIdx.x < S) ? first_t[(size_t)b * S + sb + threadIdx.x] : -1;
+        __syncthreads();
+        if (!active) continue;
+        const int ns = min(32, S - sb);
+        for (int s = 0; s < ns; ++s) {
+            if (!(sft[s] < t + lag)) continue;
+            const float g = to_f(dS[((size_t)b * T_ + t) * ldds + col0 + sb + s]);
+#pragma unroll
+            for (int i = 0; i < PB_D; i += 4) {
+                const float4 cv = *reinterpret_cast<const float4*>(&cs[s][i]);
+                acc[i] = fmaf(g, cv.x, acc[i]);
+                acc[i + 1] = fmaf(g, cv.y, acc[i + 1]);
+                acc[i + 2] = fmaf(g, cv.z, acc[i + 2]);
+                acc[i + 3] = fmaf(g, cv.w, acc[i + 3]);
+            }
+        }
+    }
+    // dH and the per-column dw partial
+    float dwp[PB_D];
+#pragma unroll
+    for (int i = 0; i < PB_D; ++i) dwp[i] = 0.f;
+    if (active) {
+        const size_t r = ((size_t)b * T_ + t) * ld + d0;
+#pragma unroll
+        for (int i = 0; i < PB_D; ++i)
+            if (d0 + i < D) {
+                const float hv = to_f(h[r + i]);
+                dwp[i] = hv * acc[i];
+                dH[r + i] = from_f<T>(to_f(dH[r + i]) + acc[i] * w[d0 + i]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < PB_D; ++i) {
+        const float v = warp_sum(dwp[i]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PB_D && d0 + threadIdx.x < D)
+        atomicAdd(gflat + w_off + d0 + threadIdx.x,
+                  red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+inline int rows_grid(long long rows) { return (int)((rows * 32 + 255) / 256); }
+
+}  // namespace
+
+#define ICK_BAD_DT(name, dt)                       \
+    do {                                           \
+        ick_set_error(name ": bad dtype %d", (dt)); \
+        return ICK_ERR_UNSUPPORTED;                \
+    } while (0)
+
+extern "C" int ick_entity_encode_fwd(const float* entities, const long long* facts, const float* type_emb, const void* word_emb,
+                                     void* out, int dt, int variant, int B, int E, int C, int F, int D, int ld, int ldw, int ntypes,
+                                     int V, cudaStream_t stream) {
+    ICK_REQUIRE(variant >= 0 && variant <= 2, "entity_encode_fwd: bad variant %d", variant);
+    ICK_REQUIRE(variant == 0 || facts != nullptr, "entity_encode_fwd: variant needs facts");
+    ICK_REQUIRE(variant != 2 || (word_emb != nullptr && C >= 10), "entity_encode_fwd: news variant needs word embeddings and 10 columns");
+    ICK_REQUIRE(C >= 5 && D <= ld && ntypes > 0, "entity_encode_fwd: bad sizes");
+    if (B * E == 0) return ICK_OK;
+    const int grid = rows_grid((long long)B * E);
+    if (dt == ICK_F32)
+        entity_encode_fwd_kernel<float><<<grid, 256, 0, stream>>>(entities, facts, type_emb, (const float*)word_emb, (float*)out, variant, B,
+                                                                   E, C, F, D, ld, ldw, ntypes, V);
+    else if (dt == ICK_BF16)
+        entity_encode_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(entities, facts, type_emb, (const bf16*)word_emb, (bf16*)out, variant, B, E,
+                                                                  C, F, D, ld, ldw, ntypes, V);
+    else ICK_BAD_DT("entity_encode_fwd", dt);
+    return ick_check_launch("entity_encode_fwd");
+}
+
+extern "C" int ick_entity_encode_bwd(const float* dEnt, const float* entities, const long long* facts, const float* type_emb,
+                                     const void* word_emb, float* gflat, int type_off, int word_off, int dt, int variant, int B, int E,
+                                     int C, int F, int D, int ld, int ldw, int ntypes, int V, cudaStream_t stream) {
+    ICK_REQUIRE(variant >= 0 && variant <= 2, "entity_encode_bwd: bad variant %d", variant);
+    ICK_REQUIRE(variant != 2 || (word_emb != nullptr && facts != nullptr && C >= 10), "entity_encode_bwd: news variant inputs missing");
+    if (B * E == 0) return ICK_OK;
+    const int grid = rows_grid((long long)B * E);
+    if (dt == ICK_F32)
+        entity_encode_bwd_kernel<float><<<grid, 256, 0, stream>>>(dEnt, entities, facts, type_emb, (const float*)word_emb, gflat, type_off,
+                                                                   word_off, variant, B, E, C, F, D, ld, ldw, ntypes, V);
+    else if (dt == ICK_BF16)
+        entity_encode_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(dEnt, entities, facts, type_emb, (const bf16*)word_emb, gflat, type_off,
+                                                                  word_off, variant, B, E, C, F, D, ld, ldw, ntypes, V);
+    else ICK_BAD_DT("entity_encode_bwd", dt);
+    return ick_check_launch("entity_encode_bwd");
+}
+
+extern "C" int ick_fact_encode_fwd(const long long* facts, const void* ent_enc, const float* pred_emb, void* out, int dt, int B, int E,
+                                   int F, int D, int ld, int NP, cudaStream_t stream) {
+    ICK_REQUIRE(D <= ld && NP > 0 && E > 0, "fact_encode_fwd: bad sizes");
+    if (B * F == 0) return ICK_OK;
+    const int grid = rows_grid((long long)B * F);
+    if (dt == ICK_F32)
+        fact_encode_fwd_kernel<float><<<grid, 256, 0, stream>>>(facts, (const float*)ent_enc, pred_emb, (float*)out, B, E, F, D, ld, NP);
+    else if (dt == ICK_BF16)
+        fact_encode_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(facts, (const bf16*)ent_enc, pred_emb, (bf16*)out, B, E, F, D, ld, NP);
+    else ICK_BAD_DT("fact_encode_fwd", dt);
+    return ick_check_launch("fact_encode_fwd");
+}
+
+extern "C" int ick_fact_encode_bwd(const float* dFact, const long long* facts, float* dEnt, float* gflat, int pred_off, int B, int E,
+                                   int F, int D, int ld, int NP, cudaStream_t stream) {
+    if (B * F == 0) return ICK_OK;
+    fact_encode_bwd_kernel<<<rows_grid((long long)B * F), 256, 0, stream>>>(dFact, facts, dEnt, gflat, pred_off, B, E, F, D, ld, NP);
+    return ick_check_launch("fact_encode_bwd");
+}
+
+extern "C" int ick_caption_embed_fwd(const long long* captions, const long long* masks, const void* word_emb, const void* ent_enc,
+                                     const void* fact_enc, const float* pe, void* out, int dt, int B, int Tstride, int t0, int Tn, int V,
+                                     int E, int F, int D, int ld, int ldw, int pad, float scale, float drop_p, unsigned seed,
+                                     unsigned site, cudaStream_t stream) {
+    ICK_REQUIRE(t0 >= 0 && t0 + Tn <= Tstride && D <= ld, "caption_embed_fwd: bad sizes");
+    ICK_REQUIRE(F == 0 || fact_enc != nullptr, "caption_embed_fwd: facts expected");
+    if (B * Tn == 0) return ICK_OK;
+    DropCfg dc = make_drop(drop_p, seed, site);
+    const int grid = rows_grid((long long)B * Tn);
+    if (dt == ICK_F32)
+        caption_embed_fwd_kernel<float><<<grid, 256, 0, stream>>>(captions, masks, (const float*)word_emb, (const float*)ent_enc,
+                                                                   (const float*)fact_enc, pe, (float*)out, B, Tstride, t0, Tn, V, E, F, D,
+                                                                   ld, ldw, pad, scale, dc);
+    else if (dt == ICK_BF16)
+        caption_embed_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(captions, masks, (const bf16*)word_emb, (const bf16*)ent_enc,
+                                                                  (const bf16*)fact_enc, pe, (bf16*)out, B, Tstride, t0, Tn, V, E, F, D, ld,
+                                                                  ldw, pad, scale, dc);
+    else ICK_BAD_DT("caption_embed_fwd", dt);
+    return ick_check_launch("caption_embed_fwd");
+}
+
+extern "C" int ick_caption_embed_bwd(const void* dX, const long long* captions, const long long* masks, float* dEnt, float* dFact,
+                                     float* gflat, int word_off, int dt, int B, int T, int V, int E, int F, int D, int ld, int pad,
+                                     float scale, float drop_p, unsigned seed, unsigned site, cudaStream_t stream) {
+    ICK_REQUIRE(F == 0 || dFact != nullptr, "caption_embed_bwd: dFact expected");
+    if (B * T == 0) return ICK_OK;
+    DropCfg dc = make_drop(drop_p, seed, site);
+    const int grid = rows_grid((long long)B * T);
+    if (dt == ICK_F32)
+        caption_embed_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V,
+                                                                   E, F, D, ld, pad, scale, dc);
+    else if (dt == ICK_BF16)
+        caption_embed_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V, E,
+                                                                  F, D, ld, pad, scale, dc);
+    else ICK_BAD_DT("caption_embed_bwd", dt);
+    return ick_check_launch("caption_embed_bwd");
+}
+
+extern "C" int ick_pixels_fwd(const float* encoder_out, void* memory, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream) {
+    ICK_REQUIRE(P <= M && D <= ld, "pixels_fwd: bad sizes");
+    if (B * P == 0) return ICK_OK;
+    dim3 grid((P + 31) / 32, (ld + 31) / 32, B);
+    if (dt == ICK_F32) pixels_fwd_kernel<float><<<grid, 256, 0, stream>>>(encoder_out, (float*)memory, D, P, M, ld);
+    else if (dt == ICK_BF16) pixels_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(encoder_out, (bf16*)memory, D, P, M, ld);
+    else ICK_BAD_DT("pixels_fwd", dt);
+    return ick_check_launch("pixels_fwd");
+}
+
+extern "C" int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream) {
+    ICK_REQUIRE(P <= M && D <= ld, "pixels_bwd: bad sizes");
+    if (B * P == 0) return ICK_OK;
+    dim3 grid((P + 31) / 32, (D + 31) / 32, B);
+    if (dt == ICK_F32) pixels_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dmemory, d_encoder_out, D, P, M, ld);
+    else if (dt == ICK_BF16) pixels_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dmemory, d_encoder_out, D, P, M, ld);
+    else ICK_BAD_DT("pixels_bwd", dt);
+    return ick_check_launch("pixels_bwd");
+}
+
+extern "C" int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F,
+                                      int V, int E, cudaStream_t stream) {
+    ICK_REQUIRE(F > 0 && F <= 4096, "fact_first_mention: F=%d out of range", F);
+    if (B == 0) return ICK_OK;
+    fact_first_mention_kernel<<<B, 256, 2 * F * sizeof(int), stream>>>(captions, facts, first_t, tmin, T, F, V, E);
+    return ick_check_launch("fact_first_mention");
+}
+
+extern "C" int ick_pred_gate_fwd(const int* tmin, const long long* facts, const float* WpT, const float* bias, const void* h, void* gate,
+                                 void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag,
+                                 cudaStream_t stream) {
+    ICK_REQUIRE(F > 0 && F <= 4096 && D <= ld && D <= ldp, "pred_gate_fwd: bad sizes");
+    ICK_REQUIRE(hg == nullptr || h != nullptr, "pred_gate_fwd: hg needs h");
+    if (B * Tn == 0) return ICK_OK;
+    dim3 grid(Tn, B);
+    if (dt == ICK_F32)
+        pred_gate_fwd_kernel<float><<<grid, 128, F * sizeof(int), stream>>>(tmin, facts, WpT, bias, (const float*)h, (float*)gate, (float*)hg,
+                                                                            Tn, t0, F, D, ld, ldp, NP, lag);
+    else if (dt == ICK_BF16)
+        pred_gate_fwd_kernel<bf16><<<grid, 128, F * sizeof(int), stream>>>(tmin, facts, WpT, bias, (const bf16*)h, (bf16*)gate, (bf16*)hg, Tn,
+                                                                           t0, F, D, ld, ldp, NP, lag);
+    else ICK_BAD_DT("pred_gate_fwd", dt);
+    return ick_check_launch("pred_gate_fwd");
+}
+
+extern "C" int ick_gate_mul_bwd(const void* dHG, const void* h, const void* gate, void* dG, void* dH, int dt, long long n,
+                                cudaStream_t stream) {
+    if (n == 0) return ICK_OK;
+    const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    if (dt == ICK_F32)
+        gate_mul_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dHG, (const float*)h, (const float*)gate, (float*)dG, (float*)dH, (size_t)n);
+    else if (dt == ICK_BF16)
+        gate_mul_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dHG, (const bf16*)h, (const bf16*)gate, (bf16*)dG, (bf16*)dH, (size_t)n);
+    else ICK_BAD_DT("gate_mul_bwd", dt);
+    return ick_check_launch("gate_mul_bwd");
+}
+
+extern "C" int ick_pred_gate_bwd(const void* dG, const int* tmin, const long long* facts, float* gflat, int wp_off, int dt, int B, int T,
+                                 int F, int D, int ld, int NP, int lag, cudaStream_t stream) {
+    if (B * F == 0) return ICK_OK;
+    dim3 grid(F, B);
+    if (dt == ICK_F32)
+        pred_gate_bwd_kernel<float><<<grid, 128, 0, stream>>>((const float*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
+    else if (dt == ICK_BF16)
+        pred_gate_bwd_kernel<bf16><<<grid, 128, 0, stream>>>((const bf16*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
+    else ICK_BAD_DT("pred_gate_bwd", dt);
+    return ick_check_launch("pred_gate_bwd");
+}
+
+extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores,
+                               int dt, int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream) {
+    ICK_REQUIRE(D <= ld && ld % 8 == 0 && ((D + 7) & ~7) <= ld, "pointer_fwd: bad sizes D=%d ld=%d", D, ld);
+    if (B * Tn * S == 0) return ICK_OK;
+    const int Dp = (D + 7) & ~7;
+    const size_t smem = (size_t)PT_T * Dp * sizeof(float);
+    dim3 grid((S + 127) / 128, (Tn + PT_T - 1) / PT_T, B);
+    if (dt == ICK_F32)
+        pointer_fwd_kernel<float><<<grid, 128, smem, stream>>>((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
+                                                               ldscores, col0, lag);
+    else if (dt == ICK_BF16)
+        pointer_fwd_kernel<bf16><<<grid, 128, smem, stream>>>((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
+                                                              ldscores, col0, lag);
+    else ICK_BAD_DT("pointer_fwd", dt);
+    return ick_check_launch("pointer_fwd");
+}
+
+extern "C" int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, const float* w, const int* first_t, float* dCtx, void* dH,
+                               float* gflat, int w_off, int bias_off, int dt, int B, int T, int S, int D, int ld, int ldds, int col0,
+                               int lag, cudaStream_t stream) {
+    ICK_REQUIRE(D <= ld, "pointer_bwd: bad sizes");
+    if (B * T * S == 0) return ICK_OK;
+    dim3 g1((S + 127) / 128, (D + PB_D - 1) / PB_D, B), g2((T + 127) / 128, (D + PB_D - 1) / PB_D, B);
+    if (dt == ICK_F32) {
+        pointer_bwd_ctx_kernel<float><<<g1, 128, 0, stream>>>((const float*)dS, (const float*)h, w, first_t, dCtx, gflat, bias_off, T, S, D,
+                                                              ld, ldds, col0, lag);
+        pointer_bwd_h_kernel<float><<<g2, 128, 0, stream>>>((const float*)dS, (const float*)h, (const float*)ctx, w, first_t, (float*)dH,
+                                                            gflat, w_off, T, S, D, ld, ldds, col0, lag);
+    } else if (dt == ICK_BF16) {
+        pointer_bwd_ctx_kernel<bf16><<<g1, 128, 0, stream>>>((const bf16*)dS, (const bf16*)h, w, first_t, dCtx, gflat, bias_off, T, S, D, ld,
+                                                             ldds, col0, lag);
+        pointer_bwd_h_kernel<bf16><<<g2, 128, 0, stream>>>((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, (bf16*)dH, gflat,
+                                                           w_off, T, S, D, ld, ldds, col0, lag);
+    } else ICK_BAD_DT("pointer_bwd", dt);
+    return ick_check_launch("pointer_bwd");
+}

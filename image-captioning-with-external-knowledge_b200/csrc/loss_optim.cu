@@ -1,0 +1,315 @@
+// Loss, optimizer, packing and decode-selection kernels.
+//   masked cross-entropy  = pack_padded_sequence + CrossEntropyLoss(ignore_index=<pad>)      G/train.py:275-281
+//   clamp + Adam + repack = ut.clip_gradient (G/utils.py:75-85) + torch.optim.Adam step      G/train.py:287-292
+//   greedy select         = argmax / top-2 / repetition clean-up state machine of predict()  G/models.py:409-442
+#include "common.cuh"
+#include "ickb200.h"
+
+namespace {
+
+__device__ __forceinline__ void online_merge(float& m, float& l, float m2, float l2) {
+    const float mn = fmaxf(m, m2);
+    if (mn == -INFINITY) return;
+    l = l * __expf(m - mn) + l2 * __expf(m2 - mn);
+    m = mn;
+}
+
+// One CTA per (b,t) row.  Valid rows: t < decode_len[b] and target = captions[b,t+1] != pad.
+// loss_acc[0] += sum(lse - s[target]); loss_acc[1] += #valid.  dS (optional) = softmax - onehot (UNSCALED: the 1/N of
+// the mean is folded into the optimizer step, which also makes multi-GPU normalisation exact); zeros on invalid rows.
+template <typename TD>
+__global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ scores, const long long* __restrict__ caps,
+                                                 const int* __restrict__ decode_len, float* __restrict__ loss_acc, TD* __restrict__ dS,
+                                                 int T_, int W, int lds, int ldd, int pad) {
+    __shared__ float sm[8], sl[8];
+    __shared__ float s_lse;
+    const int row = blockIdx.x, b = row / T_, t = row % T_;
+    const float* s = scores + (size_t)row * lds;
+    TD* d = dS ? dS + (size_t)row * ldd : nullptr;
+    long long target = pad;
+    if (t < decode_len[b] && t + 1 < T_) target = caps[(size_t)b * T_ + t + 1];
+    const bool valid = target != pad && target >= 0 && target < W;
+    if (!valid) {
+        if (d)
+            for (int c = threadIdx.x; c < ldd; c += blockDim.x) d[c] = from_f<TD>(0.f);
+        return;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        const float x = s[c];
+        const float mn = fmaxf(m, x);
+        l = l * __expf(m - mn) + __expf(x - mn);
+        m = mn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+        online_merge(m, l, m2, l2);
+    }
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; sl[threadIdx.x >> 5] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = sm[0], ll = sl[0];
+        for (int w = 1; w < 8; ++w) online_merge(mm, ll, sm[w], sl[w]);
+        const float lse = mm + logf(ll);
+        s_lse = lse;
+        atomicAdd(loss_acc, lse - s[target]);
+        atomicAdd(loss_acc + 1, 1.f);
+    }
+    __syncthreads();
+    if (d) {
+        const float lse = s_lse;
+        for (int c = threadIdx.x; c < ldd; c += blockDim.x) {
+            float g = 0.f;
+            if (c < W) g = __expf(s[c] - lse) - (c == (int)target ? 1.f : 0.f);
+            d[c] = from_f<TD>(g);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float clip, const float* __restrict__ count,
+                                                   float grad_scale, const int* __restrict__ dstA, const int* __restrict__ dstB,
+                                                   const int* __restrict__ dstC, T* __restrict__ packT, float* __restrict__ packF,
+                                                   int update) {
+    float gs = grad_scale;
+    if (count) gs /= fmaxf(count[0], 1.f);
+    const float step = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float pv = p[i];
+        if (update) {
+            float gv = g[i] * gs;
+            if (clip > 0.f) gv = fminf(fmaxf(gv, -clip), clip);
+            const float mv = b1 * m[i] + (1.f - b1) * gv;
+            const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+            m[i] = mv;
+            v[i] = vv;
+            pv -= step * mv / (sqrtf(vv) / bc2_sqrt + eps);
+            p[i] = pv;
+        }
+        if (dstA) { const int a = dstA[i]; if (a >= 0) packT[a] = from_f<T>(pv); }
+        if (dstB) { const int a = dstB[i]; if (a >= 0) packT[a] = from_f<T>(pv); }
+        if (dstC) { const int a = dstC[i]; if (a >= 0) packF[a] = pv; }
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast2d_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long rows, int cols, int lds,
+                                                     int ldd) {
+    const long long total = rows * ldd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ldd;
+        const int c = (int)(i % ldd);
+        dst[i] = from_f<TD>(c < cols ? to_f(src[r * lds + c]) : 0.f);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) accum_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] += to_f(src[i]);
+}
+
+// out[c] += sum_r x[r, c]; grid-stride over row blocks, columns across threads
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols, int ld,
+                                                     int rows_per_block) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float s = 0.f;
+        for (long long r = r0; r < r1; ++r) s += to_f(x[r * ld + c]);
+        atomicAdd(out + c, s);
+    }
+}
+
+// ---- greedy decode selection ------------------------------------------------------------------------------------------
+struct Top2 {
+    float v1, v2;
+    int i1, i2;
+};
+__device__ __forceinline__ void top2_push(Top2& t, float v, int i) {
+    // ties keep the lower index first (torch argmax returns the first maximal index)
+    if (v > t.v1 || (v == t.v1 && i < t.i1)) {
+        t.v2 = t.v1; t.i2 = t.i1; t.v1 = v; t.i1 = i;
+    } else if (v > t.v2 || (v == t.v2 && i < t.i2)) {
+        t.v2 = v; t.i2 = i;
+    }
+}
+__device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
+    top2_push(a, b.v1, b.i1);
+    top2_push(a, b.v2, b.i2);
+}
+
+__global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restrict__ scores, int W, int lds, long long* __restrict__ output,
+                                                            int* __restrict__ second, long long* __restrict__ captions,
+                                                            long long* __restrict__ masks, int* __restrict__ done, float* __restrict__ margins,
+                                                            int step, int Tmax, int V, int E, int has_facts, int end_tok) {
+    __shared__ Top2 st[8];
+    const int b = blockIdx.x;
+    if (done[b]) return;
+    const float* s = scores + (size_t)b * lds;
+    Top2 t{-INFINITY, -INFINITY, 0x7fffffff, 0x7fffffff};
+    for (int c = threadIdx.x; c < W; c += blockDim.x) top2_push(t, s[c], c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Top2 u;
+        u.v1 = __shfl_xor_sync(0xffffffffu, t.v1, o);
+        u.v2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+        u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+        u.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+        top2_merge(t, u);
+    }
+    if ((threadIdx.x & 31) == 0) st[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int w = 1; w < 8; ++w) top2_merge(t, st[w]);
+    long long* out = output + (size_t)b * Tmax;
+    int* sec = second + (size_t)b * Tmax;
+    out[step] = t.i1;
+    if (margins) margins[(size_t)b * Tmax + step] = t.v1 - t.v2;
+    if (t.i1 == end_tok) {  // <end> is checked before the clean-up, G/models.py:414-416
+        done[b] = 1;
+        return;
+    }
+    sec[step] = t.i2;
+    // repetition clean-up: repeat lengths 1,2,3 (dupl_idx 0,2,4), shortest first, first match wins (G/models.py:421-435)
+    for (int dupl = 0; dupl <= 4; dupl += 2) {
+        if (step > dupl) {
+            const int n = (dupl + 2) / 2;
+            bool same = true;
+            for (int k = 0; k < n; ++k) same = same && (out[step - k] == out[step - n - k]);
+            if (same) {
+                const int nrw = dupl == 0 ? 1 : dupl;
+                for (int k = 0; k < nrw; ++k) out[step - k] = sec[step - k];
+                break;
+            }
+        }
+    }
+    if (step < Tmax - 1) {
+        const long long o = out[step];
+        captions[(size_t)b * Tmax + step + 1] = o;
+        masks[(size_t)b * Tmax + step + 1] = (has_facts && o >= (long long)V + E) ? 2 : (o >= V ? 1 : 0);
+    }
+}
+
+inline int ew_grid(long long n) {
+    long long g = (n + 255) / 256;
+    return (int)(g < 148 * 16 ? (g < 1 ? 1 : g) : 148 * 16);
+}
+
+}  // namespace
+
+extern "C" int ick_ce_fwd_bwd(const float* scores, const long long* captions_sorted, const int* decode_len, float* loss_acc,
+                              void* dscores, int dt, int B, int T, int W, int lds, int ldd, int pad, cudaStream_t stream) {
+    ICK_REQUIRE(B >= 0 && T > 0 && W > 0 && lds >= W, "ce: bad sizes");
+    ICK_REQUIRE(dscores == nullptr || ldd >= W, "ce: ldd < W");
+    if (B == 0) return ICK_OK;
+    if (dscores == nullptr || dt == ICK_F32)
+        ce_kernel<float><<<B * T, 256, 0, stream>>>(scores, captions_sorted, decode_len, loss_acc, (float*)dscores, T, W, lds, ldd, pad);
+    else if (dt == ICK_BF16)
+        ce_kernel<bf16><<<B * T, 256, 0, stream>>>(scores, captions_sorted, decode_len, loss_acc, (bf16*)dscores, T, W, lds, ldd, pad);
+    else {
+        ick_set_error("ce: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("ce_fwd_bwd");
+}
+
+extern "C" int ick_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                             float bias_corr1, float bias_corr2, float clip, const float* count, float grad_scale, const int* dstA,
+                             const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, cudaStream_t stream) {
+    ICK_REQUIRE(n >= 0, "adam: bad n");
+    ICK_REQUIRE(!update || (g && m && v), "adam: update needs g, m, v");
+    ICK_REQUIRE((!dstA && !dstB) || packT, "adam: packT missing");
+    ICK_REQUIRE(!dstC || packF, "adam: packF missing");
+    if (n == 0) return ICK_OK;
+    const float bc2s = sqrtf(bias_corr2);
+    if (dt == ICK_F32)
+        adam_kernel<float><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
+                                                           dstA, dstB, dstC, (float*)packT, packF, update);
+    else if (dt == ICK_BF16)
+        adam_kernel<bf16><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
+                                                          dstA, dstB, dstC, (bf16*)packT, packF, update);
+    else {
+        ick_set_error("adam: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("adam_step");
+}
+
+extern "C" int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, long long rows, int cols, int lds, int ldd,
+                          cudaStream_t stream) {
+    ICK_REQUIRE(rows >= 0 && cols >= 0 && lds >= cols, "cast2d: bad sizes");
+    if (rows * ldd == 0) return ICK_OK;
+    const int grid = ew_grid(rows * ldd);
+    if (src_dt == ICK_F32 && dst_dt == ICK_BF16)
+        cast2d_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)src, (bf16*)dst, rows, cols, lds, ldd);
+    else if (src_dt == ICK_F32 && dst_dt == ICK_F32)
+        cast2d_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, rows, cols, lds, ldd);
+    else if (src_dt == ICK_BF16 && dst_dt == ICK_F32)
+        cast2d_kernel<bf16, float><<<grid, 256, 0, stream>>>((const bf16*)src, (float*)dst, rows, cols, lds, ldd);
+    else if (src_dt == ICK_BF16 && dst_dt == ICK_BF16)
+        cast2d_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)src, (bf16*)dst, rows, cols, lds, ldd);
+    else {
+        ick_set_error("cast2d: bad dtypes %d -> %d", src_dt, dst_dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("cast2d");
+}
+
+extern "C" int ick_accum_f32(const void* src, int dt, float* dst, long long n, cudaStream_t stream) {
+    if (n == 0) return ICK_OK;
+    if (dt == ICK_F32) accum_f32_kernel<float><<<ew_grid(n), 256, 0, stream>>>((const float*)src, dst, n);
+    else if (dt == ICK_BF16) accum_f32_kernel<bf16><<<ew_grid(n), 256, 0, stream>>>((const bf16*)src, dst, n);
+    else {
+        ick_set_error("accum_f32: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("accum_f32");
+}
+
+extern "C" int ick_colsum(const void* x, int dt, float* out, long long rows, int cols, int ld, cudaStream_t stream) {
+    if (rows == 0 || cols == 0) return ICK_OK;
+    const int rpb = 64;
+    const int grid = (int)((rows + rpb - 1) / rpb);
+    if (dt == ICK_F32) colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, out, rows, cols, ld, rpb);
+    else if (dt == ICK_BF16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, out, rows, cols, ld, rpb);
+    else {
+        ick_set_error("colsum: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("colsum");
+}
+
+extern "C" int ick_greedy_select(const float* scores, int W, int lds, long long* output, int* second, long long* captions,
+                                 long long* masks, int* done, float* margins, int B, int step, int Tmax, int V, int E, int has_facts,
+                                 int end_tok, cudaStream_t stream) {
+    ICK_REQUIRE(B >= 0 && step >= 0 && step < Tmax && W >= 2, "greedy_select: bad sizes");
+    if (B == 0) return ICK_OK;
+    greedy_select_kernel<<<B, 256, 0, stream>>>(scores, W, lds, output, second, captions, masks, done, margins, step, Tmax, V, E, has_facts,
+                                                end_tok);
+    return ick_check_launch("greedy_select");
+}
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------------
+#include <cstdarg>
+#include <cstdio>
+static thread_local char g_err[512] = "";
+void ick_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int ick_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ick_set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return ICK_ERR_CUDA;
+    }
+    return ICK_OK;
+}
+extern "C" const char* ick_last_error(void) { return g_err; }
+extern "C" int ick_abi_version(void) { return ICK_ABI_VERSION; }

@@ -1,0 +1,231 @@
+// Fused residual-add + dropout + LayerNorm (post-LN Transformer sublayer tail), forward and backward.
+//   s = x + dropout(sub);  y = (s - mean) * rstd * gamma + beta          (torch LayerNorm: biased variance, eps 1e-5)
+// `sub` is overwritten with s (needed by the backward pass, saves one tensor); y can be written with a per-batch row
+// remap so that the last encoder layer writes straight into the decoder's memory buffer [pixels; entities; facts]
+// (the reference concatenates, G/models.py:349 / K/models.py:497-499).  One warp per row, HBM-bound.
+#include "common.cuh"
+#include "ickb200.h"
+
+namespace {
+
+constexpr int MAXP = 8;  // pairs per lane: supports d <= 512
+
+struct RowMap {
+    int s_in, s_out, off;  // out_row = (r / s_in) * s_out + off + r % s_in ; s_in == 0 -> identity
+    __device__ __forceinline__ size_t map(int r) const {
+        return s_in == 0 ? (size_t)r : (size_t)(r / s_in) * s_out + off + (r % s_in);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ X, T* __restrict__ SUB,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         T* __restrict__ Y, float* __restrict__ MEAN, float* __restrict__ RSTD,
+                                                         int rows, int d, int ldx, int lds, int ldy, float eps, RowMap ymap,
+                                                         DropCfg drop) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int npairs = d >> 1;
+    for (int r = warp; r < rows; r += nwarps) {
+        const T* x = X ? X + (size_t)r * ldx : nullptr;
+        T* s = SUB + (size_t)r * lds;
+        float v[2 * MAXP];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            float a = 0.f, b = 0.f;
+            if (p < npairs) {
+                const float2 u = ld2(s + 2 * p);
+                const uint64_t idx = (uint64_t)r * (uint64_t)d + 2 * p;
+                a = u.x * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx);
+                b = u.y * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx + 1);
+                if (x) {
+                    const float2 xr = ld2(x + 2 * p);
+                    a += xr.x;
+                    b += xr.y;
+                }
+                st2(s + 2 * p, a, b);
+            }
+            v[2 * i] = a;
+            v[2 * i + 1] = b;
+            sum += a + b;
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            if (p < npairs) {
+                const float a = v[2 * i] - mean, b = v[2 * i + 1] - mean;
+                var += a * a + b * b;
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
+        T* y = Y + ymap.map(r) * ldy;
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            if (p < npairs) {
+                const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * p);
+                const float2 bb = *reinterpret_cast<const float2*>(beta + 2 * p);
+                st2(y + 2 * p, (v[2 * i] - mean) * rstd * g.x + bb.x, (v[2 * i + 1] - mean) * rstd * g.y + bb.y);
+            } else if (2 * p < ldy) {
+                st2(y + 2 * p, 0.f, 0.f);  // zero the pad columns [d, ld)
+            }
+        }
+        if (lane == 0) {
+            MEAN[r] = mean;
+            RSTD[r] = rstd;
+        }
+    }
+}
+
+// dy rows may be remapped (dymap) when the gradient arrives through the memory buffer.
+// Outputs: DRES (= ds, or += ds when acc_res) and DSUB (= ds * dropmask); dgamma/dbeta accumulate atomically.
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ DY, const T* __restrict__ S,
+                                                         const float* __restrict__ MEAN, const float* __restrict__ RSTD,
+                                                         const float* __restrict__ gamma, T* DRES, T* __restrict__ DSUB,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
+                                                         int lddy, int lds, int ldres, int ldsub, RowMap dymap, int acc_res,
+                                                         DropCfg drop) {
+    __shared__ float sg[2 * MAXP * 32], sb[2 * MAXP * 32];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int npairs = d >> 1;
+    for (int i = threadIdx.x; i < 2 * MAXP * 32; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+
+    float gam[2 * MAXP], ag[2 * MAXP], ab[2 * MAXP];
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int p = lane + 32 * i;
+        gam[2 * i] = p < npairs ? gamma[2 * p] : 0.f;
+        gam[2 * i + 1] = p < npairs ? gamma[2 * p + 1] : 0.f;
+        ag[2 * i] = ag[2 * i + 1] = ab[2 * i] = ab[2 * i + 1] = 0.f;
+    }
+    for (int r = warp; r < rows; r += nwarps) {
+        const T* dy = DY + dymap.map(r) * lddy;
+        const T* s = S + (size_t)r * lds;
+        const float mean = MEAN[r], rstd = RSTD[r];
+        float g[2 * MAXP], xh[2 * MAXP];
+        float sum_g = 0.f, sum_gx = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            float2 dyv = make_float2(0.f, 0.f), sv = make_float2(mean, mean);
+            if (p < npairs) {
+                dyv = ld2(dy + 2 * p);
+                sv = ld2(s + 2 * p);
+            }
+            xh[2 * i] = (sv.x - mean) * rstd;
+            xh[2 * i + 1] = (sv.y - mean) * rstd;
+            g[2 * i] = dyv.x * gam[2 * i];
+            g[2 * i + 1] = dyv.y * gam[2 * i + 1];
+            ag[2 * i] += dyv.x * xh[2 * i];
+            ag[2 * i + 1] += dyv.y * xh[2 * i + 1];
+            ab[2 * i] += dyv.x;
+            ab[2 * i + 1] += dyv.y;
+            sum_g += g[2 * i] + g[2 * i + 1];
+            sum_gx += g[2 * i] * xh[2 * i] + g[2 * i + 1] * xh[2 * i + 1];
+        }
+        const float mg = warp_sum(sum_g) / (float)d;
+        const float mgx = warp_sum(sum_gx) / (float)d;
+        T* dres = DRES ? DRES + (size_t)r * ldres : nullptr;
+        T* dsub = DSUB ? DSUB + (size_t)r * ldsub : nullptr;
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) {
+            const int p = lane + 32 * i;
+            if (p < npairs) {
+                float a = rstd * (g[2 * i] - mg - xh[2 * i] * mgx);
+                float b = rstd * (g[2 * i + 1] - mg - xh[2 * i + 1] * mgx);
+                if (dsub) {
+                    const uint64_t idx = (uint64_t)r * (uint64_t)d + 2 * p;
+                    st2(dsub + 2 * p, a * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx),
+                        b * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx + 1));
+                }
+                if (dres) {
+                    if (acc_res) {
+                        const float2 o = ld2(dres + 2 * p);
+                        a += o.x;
+                        b += o.y;
+                    }
+                    st2(dres + 2 * p, a, b);
+                }
+            } else {
+                if (dsub && 2 * p < ldsub) st2(dsub + 2 * p, 0.f, 0.f);
+                if (dres && !acc_res && 2 * p < ldres) st2(dres + 2 * p, 0.f, 0.f);
+            }
+        }
+    }
+    // block reduction of the per-lane dgamma/dbeta partials, then one atomic per column per CTA
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int p = lane + 32 * i;
+        if (p < npairs) {
+            atomicAdd(&sg[2 * p], ag[2 * i]);
+            atomicAdd(&sg[2 * p + 1], ag[2 * i + 1]);
+            atomicAdd(&sb[2 * p], ab[2 * i]);
+            atomicAdd(&sb[2 * p + 1], ab[2 * i + 1]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        if (dgamma) atomicAdd(dgamma + c, sg[c]);
+        if (dbeta) atomicAdd(dbeta + c, sb[c]);
+    }
+}
+
+}  // namespace
+
+extern "C" int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, const float* beta, void* y, float* mean,
+                              float* rstd, int dt, int rows, int d, int ldx, int lds, int ldy, float eps, int map_s_in,
+                              int map_s_out, int map_off, float drop_p, unsigned seed, unsigned site, cudaStream_t stream) {
+    ICK_REQUIRE(rows >= 0 && d > 0 && d % 2 == 0 && d <= 2 * MAXP * 32, "add_ln_fwd: d=%d must be even and <= 512", d);
+    ICK_REQUIRE(ldx % 2 == 0 && lds % 2 == 0 && ldy % 2 == 0 && lds >= d && ldy >= d, "add_ln_fwd: bad leading dims");
+    ICK_REQUIRE(ldy <= 2 * MAXP * 32, "add_ln_fwd: ldy too large");
+    if (rows == 0) return ICK_OK;
+    RowMap m{map_s_in, map_s_out, map_off};
+    DropCfg dc = make_drop(drop_p, seed, site);
+    const int blocks = min((rows + 7) / 8, 148 * 8);
+    if (dt == ICK_F32)
+        add_ln_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (float*)sub, gamma, beta, (float*)y, mean, rstd, rows,
+                                                             d, ldx, lds, ldy, eps, m, dc);
+    else if (dt == ICK_BF16)
+        add_ln_fwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)x, (bf16*)sub, gamma, beta, (bf16*)y, mean, rstd, rows, d,
+                                                            ldx, lds, ldy, eps, m, dc);
+    else {
+        ick_set_error("add_ln_fwd: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("add_ln_fwd");
+}
+
+extern "C" int ick_add_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma,
+                              void* dres, void* dsub, float* dgamma, float* dbeta, int dt, int rows, int d, int lddy, int lds,
+                              int ldres, int ldsub, int map_s_in, int map_s_out, int map_off, int acc_res, float drop_p,
+                              unsigned seed, unsigned site, cudaStream_t stream) {
+    ICK_REQUIRE(rows >= 0 && d > 0 && d % 2 == 0 && d <= 2 * MAXP * 32, "add_ln_bwd: d=%d must be even and <= 512", d);
+    ICK_REQUIRE(lddy % 2 == 0 && lds % 2 == 0 && ldres % 2 == 0 && ldsub % 2 == 0, "add_ln_bwd: bad leading dims");
+    ICK_REQUIRE(ldres <= 2 * MAXP * 32 && ldsub <= 2 * MAXP * 32, "add_ln_bwd: leading dims too large");
+    if (rows == 0) return ICK_OK;
+    RowMap m{map_s_in, map_s_out, map_off};
+    DropCfg dc = make_drop(drop_p, seed, site);
+    const int blocks = min((rows + 7) / 8, 148 * 2);
+    if (dt == ICK_F32)
+        add_ln_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)s, mean, rstd, gamma, (float*)dres,
+                                                             (float*)dsub, dgamma, dbeta, rows, d, lddy, lds, ldres, ldsub, m,
+                                                             acc_res, dc);
+    else if (dt == ICK_BF16)
+        add_ln_bwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)s, mean, rstd, gamma, (bf16*)dres,
+                                                            (bf16*)dsub, dgamma, dbeta, rows, d, lddy, lds, ldres, ldsub, m, acc_res,
+                                                            dc);
+    else {
+        ick_set_error("add_ln_bwd: bad dtype %d", dt);
+        return ICK_ERR_UNSUPPORTED;
+    }
+    return ick_check_launch("add_ln_bwd");
+}

@@ -1,0 +1,484 @@
+"""
+Forward / hand-written backward orchestration of ``DecoderTransformer`` over the kernel set (kernels.CudaKernels).
+
+Mirrors the reference's call stack: entity encoder -> fact encoder -> caption embedder -> entity /
+fact Transformer encoders -> memory = [pixels; entities; facts] -> 3 post-LN decoder layers -> context indicators ->
+vocabulary + pointer scores (G/models.py:315-361, K/models.py:457-514, N/models.py:440-497), in batch-major rows.
+The backward pass is written out by hand (no autograd inside): every weight gradient is accumulated by the kernels
+straight into one flat fp32 buffer laid out like the reference's parameters.
+
+torch is used here for device memory and streams only; every arithmetic step is a kernel from include/ickb200.h.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace as NS
+from typing import Dict, Optional
+
+import torch
+
+from .layout import HD, Linear, PackPlan, site_id
+
+VARIANT_CODE = {"G": 0, "K": 1, "N": 2}
+
+
+class LinearViews:
+    def __init__(self, lin: Linear, W, WT, b, rowoff, colmap, biasoff):
+        self.lin, self.W, self.WT, self.b = lin, W, WT, b
+        self.rowoff, self.colmap, self.biasoff = rowoff, colmap, biasoff
+
+
+class DecoderEngine:
+    def __init__(self, plan: PackPlan, kernels, device, dtype: torch.dtype, pad: int, start: int, end: int,
+                 p_dec: float = 0.5, p_enc: float = 0.5, p_pos: float = 0.1, max_len: int = 5000):
+        self.plan, self.K, self.device, self.dtype = plan, kernels, device, dtype
+        self.pad, self.start, self.end = pad, start, end
+        self.p_dec, self.p_enc, self.p_pos = p_dec, p_enc, p_pos
+        self.D, self.DP, self.H, self.L, self.dh = plan.D, plan.DP, plan.H, plan.L, plan.dh
+        self.V, self.NP = plan.V, plan.NP
+        self.variant = plan.variant
+        self.has_facts = plan.has_facts
+        self.P: Optional[torch.Tensor] = None
+        self.packT = torch.zeros(plan.packT_size, dtype=dtype, device=device)
+        self.packF = torch.zeros(plan.packF_size, dtype=torch.float32, device=device)
+        self.dstA = torch.from_numpy(plan.dstA).to(device)
+        self.dstB = torch.from_numpy(plan.dstB).to(device)
+        self.dstC = torch.from_numpy(plan.dstC).to(device)
+        self.lin: Dict[str, LinearViews] = {}
+        for name, l in plan.linears.items():
+            W, WT, b = plan.linear_views(l, self.packT, self.packF)
+            self.lin[name] = LinearViews(l, W, WT, b, torch.from_numpy(l.rowoff).to(device), torch.from_numpy(l.colmap).to(device),
+                                         torch.from_numpy(l.biasoff).to(device))
+        o, r, c = plan.regions_T["word_embedding"]
+        self.wemb = self.packT[o : o + r * c].view(r, c)
+        if self.has_facts:
+            o, r, c = plan.regions_F["fc_predicate_T"]
+            self.WpT = self.packF[o : o + r * c].view(r, c)
+        # sinusoidal table, PositionEncoder.__init__ (G/models.py:184-205); host-side constant
+        pe = torch.zeros(max_len, self.D)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, self.D, 2).float() * (-math.log(10000.0) / self.D))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.pe = pe.to(device)
+
+    # ---- parameters ----------------------------------------------------------------------------------------------------
+    def attach(self, flat_params: torch.Tensor) -> None:
+        assert flat_params.dtype == torch.float32 and flat_params.numel() == self.plan.n_params
+        self.P = flat_params
+
+    def param(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        buf = self.P if buf is None else buf
+        off = self.plan.offsets[name]
+        shp = self.plan.shapes[name]
+        n = 1
+        for s in shp:
+            n *= s
+        return buf[off : off + n].view(*shp)
+
+    def off(self, name: str) -> int:
+        return self.plan.offsets[name]
+
+    def repack(self) -> None:
+        """master fp32 parameters -> padded / transposed operand copies (one launch)."""
+        self.K.adam_step(self.P, None, None, None, 0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, None, 1.0, self.dstA, self.dstB, self.dstC,
+                         self.packT, self.packF, update=False)
+
+    # ---- helpers ----------------------------------------------------------------------------------------------------------
+    def _new(self, rows, cols, dtype=None):
+        return torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
+
+    def _newf(self, n):
+        return torch.empty(n, dtype=torch.float32, device=self.device)
+
+    def _drop(self, p, seed, name):
+        return (p, seed, site_id(name)) if (p > 0.0 and seed is not None) else None
+
+    # ---- Transformer encoder layer (self-attention over context slots) -----------------------------------------------------
+    def _enc_layer_fwd(self, stack, l, x, B, S, p, seed, out=None, rowmap=(0, 0, 0)):
+        K, DP, D, H, dh = self.K, self.DP, self.D, self.H, self.dh
+        pre = f"{stack}.layers.{l}."
+        site = f"{stack}.{l}"
+        R = B * S
+        qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+        f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+        sv = NS(x=x)
+        sv.qkv = self._new(R, 3 * DP)
+        K.gemm(x, qkv_l.W, sv.qkv, bias=qkv_l.b)
+        sv.o = self._new(R, DP)
+        sv.lse = self._newf(B * H * S)
+        K.mha_fwd(sv.qkv[:, :DP], sv.qkv[:, DP : 2 * DP], sv.qkv[:, 2 * DP :], sv.o, sv.lse, B, H, S, S, dh, causal=False,
+                  drop=self._drop(p, seed, site + ".sa.attn"))
+        sv.s1 = self._new(R, DP)
+        K.gemm(sv.o, out_l.W, sv.s1, bias=out_l.b)
+        sv.y1 = self._new(R, DP)
+        sv.mean1, sv.rstd1 = self._newf(R), self._newf(R)
+        K.add_ln_fwd(x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1, sv.rstd1, D,
+                     drop=self._drop(p, seed, site + ".d1"))
+        sv.h1 = self._new(R, f1.lin.Np)
+        K.gemm(sv.y1, f1.W, sv.h1, bias=f1.b, epi=1, drop=self._drop(p, seed, site + ".ffn"))
+        sv.s2 = self._new(R, DP)
+        K.gemm(sv.h1, f2.W, sv.s2, bias=f2.b)
+        y2 = out if out is not None else self._new(R, DP)
+        sv.mean2, sv.rstd2 = self._newf(R), self._newf(R)
+        K.add_ln_fwd(sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), y2, sv.mean2, sv.rstd2, D,
+                     rowmap=rowmap, drop=self._drop(p, seed, site + ".d2"))
+        return y2, sv
+
+    def _ffn_bwd(self, pre, site, f1, f2, dB, h1, y_in, dA, gflat, p, seed):
+        """dB = grad of the FFN output; accumulates the FFN input gradient into dA and the weight grads into gflat."""
+        K = self.K
+        R = dB.shape[0]
+        K.wgrad(dB, h1, gflat, f2.rowoff, f2.colmap, f2.biasoff)
+        dh1 = self._new(R, f1.lin.Np)
+        K.gemm(dB, f2.WT, dh1, aux=h1, epi=2, drop=(p if seed is not None else 0.0, seed or 0, 0))
+        K.wgrad(dh1, y_in, gflat, f1.rowoff, f1.colmap, f1.biasoff)
+        K.gemm(dh1, f1.WT, dA, accumulate=True)
+
+    def _self_attn_bwd(self, pre, site, qkv_l, out_l, dB, sv_qkv, sv_o, sv_lse, x_in, dC, B, S, causal, gflat, p, seed):
+        """dB = grad of the out-projection output; accumulates the block-input gradient into dC."""
+        K, DP, H, dh = self.K, self.DP, self.H, self.dh
+        R = B * S
+        K.wgrad(dB, sv_o, gflat, out_l.rowoff, out_l.colmap, out_l.biasoff)
+        dO = self._new(R, DP)
+        K.gemm(dB, out_l.WT, dO)
+        dqkv = self._new(R, 3 * DP)
+        dsum = self._newf(B * H * S)
+        K.mha_bwd(sv_qkv[:, :DP], sv_qkv[:, DP : 2 * DP], sv_qkv[:, 2 * DP :], sv_o, dO, sv_lse, dsum, dqkv[:, :DP],
+                  dqkv[:, DP : 2 * DP], dqkv[:, 2 * DP :], B, H, S, S, dh, causal=causal, drop=self._drop(p, seed, site + ".sa.attn"))
+        K.wgrad(dqkv, x_in, gflat, qkv_l.rowoff, qkv_l.colmap, qkv_l.biasoff)
+        K.gemm(dqkv, qkv_l.WT, dC, accumulate=True)
+
+    def _enc_layer_bwd(self, stack, l, sv, dy, dy_rowmap, B, S, gflat, p, seed):
+        K, DP, D = self.K, self.DP, self.D
+        pre = f"{stack}.layers.{l}."
+        site = f"{stack}.{l}"
+        R = B * S
+        qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+        f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+        dA, dB = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dy, sv.s2, sv.mean2, sv.rstd2, self.param(pre + "norm2.weight"), dA, dB, self.param(pre + "norm2.weight", gflat),
+                     self.param(pre + "norm2.bias", gflat), D, rowmap=dy_rowmap, drop=self._drop(p, seed, site + ".d2"))
+        self._ffn_bwd(pre, site, f1, f2, dB, sv.h1, sv.y1, dA, gflat, p, seed)
+        dC = self._new(R, DP)
+        K.add_ln_bwd(dA, sv.s1, sv.mean1, sv.rstd1, self.param(pre + "norm1.weight"), dC, dB, self.param(pre + "norm1.weight", gflat),
+                     self.param(pre + "norm1.bias", gflat), D, drop=self._drop(p, seed, site + ".d1"))
+        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB, sv.qkv, sv.o, sv.lse, sv.x, dC, B, S, False, gflat, p, seed)
+        return dC
+
+    # ---- Transformer decoder layer -------------------------------------------------------------------------------------------
+    def _dec_layer_fwd(self, l, x, kv, B, T, M, p, seed):
+        K, DP, D, H, dh = self.K, self.DP, self.D, self.H, self.dh
+        pre = f"transformer_decoder.layers.{l}."
+        site = f"transformer_decoder.{l}"
+        R = B * T
+        qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+        q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
+        f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+        sv = NS(x=x)
+        # causal self-attention
+        sv.qkv = self._new(R, 3 * DP)
+        K.gemm(x, qkv_l.W, sv.qkv, bias=qkv_l.b)
+        sv.o = self._new(R, DP)
+        sv.lse = self._newf(B * H * T)
+        K.mha_fwd(sv.qkv[:, :DP], sv.qkv[:, DP : 2 * DP], sv.qkv[:, 2 * DP :], sv.o, sv.lse, B, H, T, T, dh, causal=True,
+                  drop=self._drop(p, seed, site + ".sa.attn"))
+        sv.s1 = self._new(R, DP)
+        K.gemm(sv.o, out_l.W, sv.s1, bias=out_l.b)
+        sv.y1 = self._new(R, DP)
+        sv.mean1, sv.rstd1 = self._newf(R), self._newf(R)
+        K.add_ln_fwd(x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1, sv.rstd1, D,
+                     drop=self._drop(p, seed, site + ".d1"))
+        # cross-attention over the memory (its K/V projections were computed for all layers at once)
+        sv.q = self._new(R, DP)
+        K.gemm(sv.y1, q_l.W, sv.q, bias=q_l.b)
+        sv.k = kv[:, l * 2 * DP : l * 2 * DP + DP]
+        sv.v = kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP]
+        sv.o2 = self._new(R, DP)
+        sv.lse2 = self._newf(B * H * T)
+        K.mha_fwd(sv.q, sv.k, sv.v, sv.o2, sv.lse2, B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"))
+        sv.s2 = self._new(R, DP)
+        K.gemm(sv.o2, out2_l.W, sv.s2, bias=out2_l.b)
+        sv.y2 = self._new(R, DP)
+        sv.mean2, sv.rstd2 = self._newf(R), self._newf(R)
+        K.add_ln_fwd(sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), sv.y2, sv.mean2, sv.rstd2, D,
+                     drop=self._drop(p, seed, site + ".d2"))
+        # feed-forward
+        sv.h1 = self._new(R, f1.lin.Np)
+        K.gemm(sv.y2, f1.W, sv.h1, bias=f1.b, epi=1, drop=self._drop(p, seed, site + ".ffn"))
+        sv.s3 = self._new(R, DP)
+        K.gemm(sv.h1, f2.W, sv.s3, bias=f2.b)
+        y3 = self._new(R, DP)
+        sv.mean3, sv.rstd3 = self._newf(R), self._newf(R)
+        K.add_ln_fwd(sv.y2, sv.s3, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), y3, sv.mean3, sv.rstd3, D,
+                     drop=self._drop(p, seed, site + ".d3"))
+        return y3, sv
+
+    def _dec_layer_bwd(self, l, sv, dy, dkv, B, T, M, gflat, p, seed):
+        K, DP, D, H, dh = self.K, self.DP, self.D, self.H, self.dh
+        pre = f"transformer_decoder.layers.{l}."
+        site = f"transformer_decoder.{l}"
+        R = B * T
+        qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+        q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
+        f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+        g = lambda n: self.param(pre + n, gflat)  # noqa: E731
+        w = lambda n: self.param(pre + n)  # noqa: E731
+        dA, dB = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dy, sv.s3, sv.mean3, sv.rstd3, w("norm3.weight"), dA, dB, g("norm3.weight"), g("norm3.bias"), D,
+                     drop=self._drop(p, seed, site + ".d3"))
+        self._ffn_bwd(pre, site, f1, f2, dB, sv.h1, sv.y2, dA, gflat, p, seed)
+        dC = self._new(R, DP)
+        K.add_ln_bwd(dA, sv.s2, sv.mean2, sv.rstd2, w("norm2.weight"), dC, dB, g("norm2.weight"), g("norm2.bias"), D,
+                     drop=self._drop(p, seed, site + ".d2"))
+        # cross-attention backward
+        K.wgrad(dB, sv.o2, gflat, out2_l.rowoff, out2_l.colmap, out2_l.biasoff)
+        dO2 = self._new(R, DP)
+        K.gemm(dB, out2_l.WT, dO2)
+        dq = self._new(R, DP)
+        dsum = self._newf(B * H * T)
+        K.mha_bwd(sv.q, sv.k, sv.v, sv.o2, dO2, sv.lse2, dsum, dq, dkv[:, l * 2 * DP : l * 2 * DP + DP],
+                  dkv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"))
+        K.wgrad(dq, sv.y1, gflat, q_l.rowoff, q_l.colmap, q_l.biasoff)
+        K.gemm(dq, q_l.WT, dC, accumulate=True)
+        dE = self._new(R, DP)
+        K.add_ln_bwd(dC, sv.s1, sv.mean1, sv.rstd1, w("norm1.weight"), dE, dB, g("norm1.weight"), g("norm1.bias"), D,
+                     drop=self._drop(p, seed, site + ".d1"))
+        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB, sv.qkv, sv.o, sv.lse, sv.x, dE, B, T, True, gflat, p, seed)
+        return dE
+
+    # ---- context encoders -------------------------------------------------------------------------------------------------------
+    def _encode_context(self, inp, B, E, F):
+        K, D, DP = self.K, self.D, self.DP
+        ent_enc = self._new(B * E, DP)
+        K.entity_encode_fwd(inp.entities, inp.facts, self.param("entity_encoder.type_embedding.weight"),
+                            self.wemb if self.variant == "N" else None, ent_enc, VARIANT_CODE[self.variant], B, E, F, D,
+                            self.plan.shapes["entity_encoder.type_embedding.weight"][0], self.V)
+        fact_enc = None
+        if self.has_facts:
+            fact_enc = self._new(B * F, DP)
+            K.fact_encode_fwd(inp.facts, ent_enc, self.param("predicate_embedding.weight"), fact_enc, B, E, F, D, self.NP)
+        return ent_enc, fact_enc
+
+    def _build_memory(self, inp, ent_enc, fact_enc, B, E, F, P, M, p_enc, seed):
+        K, D, DP, L = self.K, self.D, self.DP, self.L
+        mem = self._new(B * M, DP)
+        K.pixels_fwd(inp.encoder_out, mem, B, D, P, M)
+        saves = {}
+        stacks = [("transformer_encoder_entities", ent_enc, E, P)]
+        if self.has_facts:
+            stacks.append(("transformer_encoder_facts", fact_enc, F, P + E))
+        for stack, x, S, off in stacks:
+            svs = []
+            for l in range(L):
+                last = l == L - 1
+                x, sv = self._enc_layer_fwd(stack, l, x, B, S, p_enc, seed, out=mem if last else None,
+                                            rowmap=(S, M, off) if last else (0, 0, 0))
+                svs.append(sv)
+            saves[stack] = svs
+        return mem, saves
+
+    # ---- forward -------------------------------------------------------------------------------------------------------------------
+    def forward(self, inp, train: bool = False, seed: Optional[int] = None):
+        """
+        inp: namespace of DEVICE tensors already sorted by decreasing length (the module does the sort):
+          captions (B,T) i64, caption_masks (B,T) i64, encoder_out (B,D,P) f32, entities (B,E,C) f32, facts (B,F,3) i64|None.
+        Returns (scores (B,T,W) fp32, ctx for backward).
+        """
+        K, D, DP, L = self.K, self.D, self.DP, self.L
+        B, T = inp.captions.shape
+        E = inp.entities.shape[1]
+        F = inp.facts.shape[1] if self.has_facts else 0
+        P = inp.encoder_out.shape[2]
+        M = P + E + F
+        W = self.V + E + F
+        p_dec = self.p_dec if train else 0.0
+        p_enc = self.p_enc if train else 0.0
+        p_pos = self.p_pos if train else 0.0
+        if not train:
+            seed = None
+        ctx = NS(inp=inp, B=B, T=T, E=E, F=F, P=P, M=M, W=W, seed=seed, p_dec=p_dec, p_enc=p_enc, p_pos=p_pos)
+        ctx.ent_enc, ctx.fact_enc = self._encode_context(inp, B, E, F)
+        x0 = self._new(B * T, DP)
+        K.caption_embed_fwd(inp.captions, inp.caption_masks, self.wemb, ctx.ent_enc, ctx.fact_enc, self.pe, x0, B, T, 0, T, self.V, E, F,
+                            D, self.pad, math.sqrt(D), drop=self._drop(p_pos, seed, "pos"))
+        ctx.mem, ctx.enc_saves = self._build_memory(inp, ctx.ent_enc, ctx.fact_enc, B, E, F, P, M, p_enc, seed)
+        kv_l = self.lin["transformer_decoder.kv_all"]
+        ctx.kv = self._new(B * M, kv_l.lin.Np)
+        K.gemm(ctx.mem, kv_l.W, ctx.kv, bias=kv_l.b)
+        x = x0
+        ctx.dec_saves = []
+        for l in range(L):
+            x, sv = self._dec_layer_fwd(l, x, ctx.kv, B, T, M, p_dec, seed)
+            ctx.dec_saves.append(sv)
+        ctx.h = x
+        scores = torch.empty(B, T, W, dtype=torch.float32, device=self.device)
+        s2 = scores.view(B * T, W)
+        self._heads_fwd(ctx, inp.captions, x, s2, B, T, 0, T, E, F, lag=0)
+        return scores, ctx
+
+    def _heads_fwd(self, ctx, captions, h, s2, B, Tn, t0, Tcap, E, F, lag):
+        """get_scores (K/models.py:420-455): gate + vocabulary GEMM + entity / fact pointer scores into one buffer."""
+        K, D, DP, V = self.K, self.D, self.DP, self.V
+        fv = self.lin["fc_vocab"]
+        if self.has_facts:
+            ctx.first_t = torch.empty(B * F, dtype=torch.int32, device=self.device)
+            ctx.tmin = torch.empty(B * F, dtype=torch.int32, device=self.device)
+            K.fact_first_mention(captions, ctx.inp.facts, ctx.first_t, ctx.tmin, B, Tcap, F, V, E)
+            ctx.gate = self._new(B * Tn, DP)
+            ctx.hg = self._new(B * Tn, DP)
+            K.pred_gate_fwd(ctx.tmin, ctx.inp.facts, self.WpT, self.param("fc_predicate.bias"), h, ctx.gate, ctx.hg, B, Tn, t0, F, D,
+                            self.NP, lag)
+            vin = ctx.hg
+        else:
+            vin = h
+        K.gemm(vin, fv.W, s2[:, :V], bias=fv.b)
+        K.pointer_fwd(h, ctx.ent_enc, self.param("fc_entity.weight"), self.param("fc_entity.bias"), None, s2, B, Tn, t0, E, D, V, lag)
+        if self.has_facts:
+            K.pointer_fwd(h, ctx.fact_enc, self.param("fc_fact.weight"), self.param("fc_fact.bias"), ctx.first_t, s2, B, Tn, t0, F, D,
+                          V + E, lag)
+
+    # ---- loss ------------------------------------------------------------------------------------------------------------------------
+    def loss(self, scores, captions_sorted, decode_len_dev, want_grad: bool = True):
+        """pack_padded_sequence + CrossEntropyLoss(ignore_index=pad) (G/train.py:275-281) fused with its gradient.
+        Returns (loss_acc = [sum of row losses, kept rows] fp32 on device, dscores (B*T, ldW) activation dtype, UNSCALED)."""
+        B, T, W = scores.shape
+        ldW = (W + 7) // 8 * 8
+        loss_acc = torch.zeros(2, dtype=torch.float32, device=self.device)
+        ds = self._new(B * T, ldW) if want_grad else None
+        self.K.ce(scores.view(B * T, W), captions_sorted, decode_len_dev, loss_acc, ds, B, T, W, self.pad)
+        return loss_acc, ds
+
+    # ---- backward --------------------------------------------------------------------------------------------------------------------
+    def backward(self, ctx, dscores, gflat, need_encoder_grad: bool = False):
+        """
+        dscores: (B*T, ld>=W) in the activation dtype (pad columns ignored).  Accumulates every parameter gradient into
+        gflat (flat fp32, reference parameter order) and returns d encoder_out (B,D,P) fp32 or None.
+        """
+        K, D, DP, L, V = self.K, self.D, self.DP, self.L, self.V
+        B, T, E, F, P, M = ctx.B, ctx.T, ctx.E, ctx.F, ctx.P, ctx.M
+        inp, seed = ctx.inp, ctx.seed
+        R = B * T
+        dEnt = torch.zeros(B * E, DP, dtype=torch.float32, device=self.device)
+        dFact = torch.zeros(B * F, DP, dtype=torch.float32, device=self.device) if self.has_facts else None
+        fv = self.lin["fc_vocab"]
+        dSv = dscores[:, :V]
+        dh = self._new(R, DP)
+        if self.has_facts:
+            dhg = self._new(R, DP)
+            K.gemm(dSv, fv.WT, dhg)
+            K.wgrad(dSv, ctx.hg, gflat, fv.rowoff, fv.colmap, fv.biasoff)
+            dG = self._new(R, DP)
+            K.gate_mul_bwd(dhg, ctx.h, ctx.gate, dG, dh)
+            K.pred_gate_bwd(dG, ctx.tmin, inp.facts, gflat, self.off("fc_predicate.weight"), B, T, F, D, self.NP, 0)
+            K.colsum(dG, self.param("fc_predicate.bias", gflat), D)
+        else:
+            K.gemm(dSv, fv.WT, dh)
+            K.wgrad(dSv, ctx.h, gflat, fv.rowoff, fv.colmap, fv.biasoff)
+        K.pointer_bwd(dscores, ctx.h, ctx.ent_enc, self.param("fc_entity.weight"), None, dEnt, dh, gflat, self.off("fc_entity.weight"),
+                      self.off("fc_entity.bias"), B, T, E, D, V, 0)
+        if self.has_facts:
+            K.pointer_bwd(dscores, ctx.h, ctx.fact_enc, self.param("fc_fact.weight"), ctx.first_t, dFact, dh, gflat,
+                          self.off("fc_fact.weight"), self.off("fc_fact.bias"), B, T, F, D, V + E, 0)
+        # decoder layers
+        kv_l = self.lin["transformer_decoder.kv_all"]
+        dkv = self._new(B * M, kv_l.lin.Np)
+        dx = dh
+        for l in reversed(range(L)):
+            dx = self._dec_layer_bwd(l, ctx.dec_saves[l], dx, dkv, B, T, M, gflat, ctx.p_dec, seed)
+        K.caption_embed_bwd(dx, inp.captions, inp.caption_masks, dEnt, dFact, gflat, self.off("word_embedding.weight"), B, T, V, E, F, D,
+                            self.pad, math.sqrt(D), drop=self._drop(ctx.p_pos, seed, "pos"))
+        # memory K/V projections (all layers at once)
+        K.wgrad(dkv, ctx.mem, gflat, kv_l.rowoff, kv_l.colmap, kv_l.biasoff)
+        dmem = self._new(B * M, DP)
+        K.gemm(dkv, kv_l.WT, dmem)
+        d_enc = None
+        if need_encoder_grad:
+            d_enc = torch.empty(B, D, P, dtype=torch.float32, device=self.device)
+            K.pixels_bwd(dmem, d_enc, B, D, P, M)
+        # context encoders, facts first (their input gradient also flows into the entity encodings)
+        if self.has_facts:
+            d = dmem
+            rowmap = (F, M, P + E)
+            for l in reversed(range(L)):
+                d = self._enc_layer_bwd("transformer_encoder_facts", l, ctx.enc_saves["transformer_encoder_facts"][l], d, rowmap, B, F,
+                                        gflat, ctx.p_enc, seed)
+                rowmap = (0, 0, 0)
+            K.accum_f32(d, dFact)
+            K.fact_encode_bwd(dFact, inp.facts, dEnt, gflat, self.off("predicate_embedding.weight"), B, E, F, D, self.NP)
+        d = dmem
+        rowmap = (E, M, P)
+        for l in reversed(range(L)):
+            d = self._enc_layer_bwd("transformer_encoder_entities", l, ctx.enc_saves["transformer_encoder_entities"][l], d, rowmap, B, E,
+                                    gflat, ctx.p_enc, seed)
+            rowmap = (0, 0, 0)
+        K.accum_f32(d, dEnt)
+        K.entity_encode_bwd(dEnt, inp.entities, inp.facts, self.param("entity_encoder.type_embedding.weight"),
+                            self.wemb if self.variant == "N" else None, gflat, self.off("entity_encoder.type_embedding.weight"),
+                            self.off("word_embedding.weight"), 0 if self.dtype == torch.float32 else 1, VARIANT_CODE[self.variant], B, E, F,
+                            D, self.plan.shapes["entity_encoder.type_embedding.weight"][0], self.V)
+        return d_enc
+
+    # ---- greedy decode (predict) -----------------------------------------------------------------------------------------------------
+    def greedy_decode(self, inp, Tmax: int, return_margins: bool = False):
+        """
+        DecoderTransformer.predict (G/models.py:363-443, K/models.py:516-609) for a BATCH of images, device-resident:
+        KV-cached incremental decoding (the reference re-decodes all positions every step), and the argmax / top-2 /
+        <end> / repetition clean-up / next-token bookkeeping runs in one kernel per step, so there is no host
+        round-trip inside the loop.  inp: encoder_out (B,D,P) f32, entities (B,E,C) f32, facts (B,F,3) i64 | None.
+        Returns output (B, Tmax) int64 (pad-filled after <end>).
+        """
+        K, D, DP, L, H, dh, V = self.K, self.D, self.DP, self.L, self.H, self.dh, self.V
+        B = inp.encoder_out.shape[0]
+        E = inp.entities.shape[1]
+        F = inp.facts.shape[1] if self.has_facts else 0
+        P = inp.encoder_out.shape[2]
+        M = P + E + F
+        W = V + E + F
+        dev = self.device
+        ctx = NS(inp=inp)
+        ctx.ent_enc, ctx.fact_enc = self._encode_context(inp, B, E, F)
+        mem, _ = self._build_memory(inp, ctx.ent_enc, ctx.fact_enc, B, E, F, P, M, 0.0, None)
+        kv_l = self.lin["transformer_decoder.kv_all"]
+        kvw = kv_l.lin.Np
+        kv = self._new(B * M, kvw)
+        K.gemm(mem, kv_l.W, kv, bias=kv_l.b)
+        captions = torch.full((B, Tmax), self.start, dtype=torch.int64, device=dev)
+        masks = torch.zeros((B, Tmax), dtype=torch.int64, device=dev)
+        output = torch.full((B, Tmax), self.pad, dtype=torch.int64, device=dev)
+        second = torch.zeros((B, Tmax), dtype=torch.int32, device=dev)
+        done = torch.zeros(B, dtype=torch.int32, device=dev)
+        margins = torch.zeros((B, Tmax), dtype=torch.float32, device=dev) if return_margins else None
+        cache = [self._new(B * Tmax, 3 * DP) for _ in range(L)]
+        scores = torch.empty(B, W, dtype=torch.float32, device=dev)
+        mean, rstd = self._newf(B), self._newf(B)
+        x0 = self._new(B, DP)
+        bufs = [NS(o=self._new(B, DP), s=self._new(B, DP), y1=self._new(B, DP), q=self._new(B, DP), y2=self._new(B, DP),
+                   h1=self._new(B, self.lin[f"transformer_decoder.layers.{l}.ffn1"].lin.Np), y3=self._new(B, DP)) for l in range(L)]
+        for i in range(Tmax):
+            K.caption_embed_fwd(captions, masks, self.wemb, ctx.ent_enc, ctx.fact_enc, self.pe, x0, B, Tmax, i, 1, V, E, F, D, self.pad,
+                                math.sqrt(D))
+            x = x0
+            for l in range(L):
+                pre = f"transformer_decoder.layers.{l}."
+                qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+                q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
+                f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+                b = bufs[l]
+                row = cache[l].view(B, Tmax, 3 * DP)[:, i, :]  # this step's q|k|v rows inside the cache
+                K.gemm(x, qkv_l.W, row, bias=qkv_l.b)
+                K.mha_decode(row[:, :DP], cache[l][:, DP : 2 * DP], cache[l][:, 2 * DP :], b.o, B, H, dh, Tmax * 3 * DP, Tmax * 3 * DP, i + 1)
+                K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
+                K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
+                K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
+                K.mha_decode(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, B, H, dh, M * kvw,
+                             M * kvw, M)
+                K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
+                K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
+                K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
+                K.gemm(b.h1, f2.W, b.s, bias=f2.b)
+                K.add_ln_fwd(b.y2, b.s, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), b.y3, mean, rstd, D)
+                x = b.y3
+            self._heads_fwd(ctx, captions, x, scores, B, 1, i, Tmax, E, F, lag=1)
+            K.greedy_select(scores, W, output, second, captions, masks, done, margins, B, i, Tmax, V, E, self.has_facts, self.end)
+        return (output, margins) if return_margins else output

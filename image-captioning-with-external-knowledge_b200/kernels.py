@@ -1,0 +1,204 @@
+"""
+Tensor-level wrappers over the C ABI (include/ickb200.h).  Every method takes CUDA tensors that the caller allocated
+and launches hand-written sm_100a kernels on torch's current stream; nothing here computes with torch ops.
+
+2-D operands are row-major views: ``x.shape = (rows, cols)``, ``x.stride(0) = ld`` (may exceed cols), ``x.stride(1) = 1``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+Drop = Optional[Tuple[float, int, int]]  # (p, seed, site)
+
+
+def dt_of(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), (t.shape, t.stride())
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _drop(d: Drop) -> Tuple[float, int, int]:
+    if d is None:
+        return 0.0, 0, 0
+    p, seed, site = d
+    return float(p), int(seed) & 0xFFFFFFFF, int(site) & 0xFFFFFFFF
+
+
+class CudaKernels:
+    """The product kernel set.  Constructing it loads csrc/libickb200.so or raises."""
+
+    name = "cuda"
+
+    def __init__(self, use_tensor_cores: bool = True):
+        import os
+
+        self.lib = _lib.get()
+        # ICKB200_NO_TC=1 routes bf16 GEMMs through the CUDA-core kernels (bring-up / bisecting aid)
+        self.use_tc = use_tensor_cores and os.environ.get("ICKB200_NO_TC") != "1"
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _s(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _call(self, name, *args, n=1):
+        self.lib.call(name, *args, self._s())
+        self.lib.launches += n - 1
+
+    # ---- dense ---------------------------------------------------------------------------------------------------
+    def gemm(self, A, W, C, bias=None, aux=None, epi=0, accumulate=False, drop: Drop = None, force_simt=False):
+        """C[M,N] (+)= A[M,K] @ W[N,K]^T + bias, fused epilogue (0 none, 1 relu+dropout, 2 relu/dropout backward)."""
+        M, K = A.shape
+        N = W.shape[0]
+        assert W.shape[1] == K and C.shape[0] == M and C.shape[1] == N, (A.shape, W.shape, C.shape)
+        p, seed, site = _drop(drop)
+        tc = (self.use_tc and not force_simt and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+              and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0 and (aux is None or C.dtype == torch.bfloat16))
+        if tc:
+            self._call("ick_gemm_tn_tc", _p(A), _p(W), _p(C), dt_of(C), _p(bias), _p(aux), M, N, K, _ld(A), _ld(W), _ld(C),
+                       _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site)
+        else:
+            self._call("ick_gemm_tn_simt", _p(A), dt_of(A), _p(W), dt_of(W), _p(C), dt_of(C), _p(bias), _p(aux), M, N, K,
+                       _ld(A), _ld(W), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site)
+
+    def wgrad(self, dY, X, gflat, rowoff, colmap=None, biasoff=None, force_simt=False):
+        """gflat[rowoff[n] + colmap[k]] += sum_m dY[m,n] X[m,k];  gflat[biasoff[n]] += sum_m dY[m,n]."""
+        M, N = dY.shape
+        K = X.shape[1]
+        assert X.shape[0] == M and rowoff.numel() >= N and (colmap is None or colmap.numel() >= K)
+        tc = (self.use_tc and not force_simt and dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16
+              and dY.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0)
+        if tc:
+            self._call("ick_wgrad_tc", _p(dY), _p(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N, K, _ld(dY), _ld(X),
+                       n=2 if biasoff is not None else 1)
+        else:
+            self._call("ick_wgrad_simt", _p(dY), dt_of(dY), _p(X), dt_of(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N,
+                       K, _ld(dY), _ld(X))
+
+    # ---- attention -------------------------------------------------------------------------------------------------
+    def mha_fwd(self, Q, K, V, O, lse, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
+        p, seed, site = _drop(drop)
+        self._call("ick_mha_fwd", _p(Q), _p(K), _p(V), _p(O), _p(lse), dt_of(Q), B, H, Sq, Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
+                   int(causal), p, seed, site)
+
+    def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
+        p, seed, site = _drop(drop)
+        self._call("ick_mha_bwd", _p(Q), _p(K), _p(V), _p(O), _p(dO), _p(lse), _p(dsum), _p(dQ), _p(dK), _p(dV), dt_of(Q), B, H, Sq,
+                   Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, n=2)
+
+    def mha_decode(self, Q, K, V, O, B, H, dh, kbatch_stride, vbatch_stride, klen):
+        self._call("ick_mha_decode", _p(Q), _p(K), _p(V), _p(O), dt_of(Q), B, H, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
+                   int(kbatch_stride), int(vbatch_stride), klen)
+
+    # ---- residual + dropout + layer norm ---------------------------------------------------------------------------
+    def add_ln_fwd(self, x, sub, gamma, beta, y, mean, rstd, d, eps=1e-5, rowmap=(0, 0, 0), drop: Drop = None):
+        rows = sub.shape[0]
+        p, seed, site = _drop(drop)
+        self._call("ick_add_ln_fwd", _p(x), _p(sub), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), dt_of(sub), rows, d,
+                   _ld(x) if x is not None else 0, _ld(sub), _ld(y), eps, rowmap[0], rowmap[1], rowmap[2], p, seed, site)
+
+    def add_ln_bwd(self, dy, s, mean, rstd, gamma, dres, dsub, dgamma, dbeta, d, rowmap=(0, 0, 0), acc_res=False, drop: Drop = None):
+        rows = s.shape[0]
+        p, seed, site = _drop(drop)
+        self._call("ick_add_ln_bwd", _p(dy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dsub), _p(dgamma), _p(dbeta),
+                   dt_of(s), rows, d, _ld(dy), _ld(s), _ld(dres) if dres is not None else 0, _ld(dsub) if dsub is not None else 0,
+                   rowmap[0], rowmap[1], rowmap[2], int(acc_res), p, seed, site)
+
+    # ---- context preparation ------------------------------------------------------------------------------------------
+    def entity_encode_fwd(self, entities, facts, type_emb, word_emb, out, variant, B, E, F, D, ntypes, V):
+        self._call("ick_entity_encode_fwd", _p(entities), _p(facts), _p(type_emb), _p(word_emb), _p(out), dt_of(out), variant, B, E,
+                   entities.shape[-1], F, D, _ld(out), _ld(word_emb) if word_emb is not None else 0, ntypes, V)
+
+    def entity_encode_bwd(self, dEnt, entities, facts, type_emb, word_emb, gflat, type_off, word_off, dt, variant, B, E, F, D, ntypes, V):
+        self._call("ick_entity_encode_bwd", _p(dEnt), _p(entities), _p(facts), _p(type_emb), _p(word_emb), _p(gflat), type_off,
+                   word_off, dt, variant, B, E, entities.shape[-1], F, D, _ld(dEnt),
+                   _ld(word_emb) if word_emb is not None else 0, ntypes, V)
+
+    def fact_encode_fwd(self, facts, ent_enc, pred_emb, out, B, E, F, D, NP):
+        self._call("ick_fact_encode_fwd", _p(facts), _p(ent_enc), _p(pred_emb), _p(out), dt_of(out), B, E, F, D, _ld(out), NP)
+
+    def fact_encode_bwd(self, dFact, facts, dEnt, gflat, pred_off, B, E, F, D, NP):
+        self._call("ick_fact_encode_bwd", _p(dFact), _p(facts), _p(dEnt), _p(gflat), pred_off, B, E, F, D, _ld(dFact), NP)
+
+    def caption_embed_fwd(self, captions, masks, word_emb, ent_enc, fact_enc, pe, out, B, Tstride, t0, Tn, V, E, F, D, pad, scale,
+                          drop: Drop = None):
+        p, seed, site = _drop(drop)
+        self._call("ick_caption_embed_fwd", _p(captions), _p(masks), _p(word_emb), _p(ent_enc), _p(fact_enc), _p(pe), _p(out),
+                   dt_of(out), B, Tstride, t0, Tn, V, E, F, D, _ld(out), _ld(word_emb), pad, scale, p, seed, site)
+
+    def caption_embed_bwd(self, dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V, E, F, D, pad, scale, drop: Drop = None):
+        p, seed, site = _drop(drop)
+        self._call("ick_caption_embed_bwd", _p(dX), _p(captions), _p(masks), _p(dEnt), _p(dFact), _p(gflat), word_off, dt_of(dX), B,
+                   T, V, E, F, D, _ld(dX), pad, scale, p, seed, site)
+
+    def pixels_fwd(self, encoder_out, memory, B, D, P, M):
+        self._call("ick_pixels_fwd", _p(encoder_out), _p(memory), dt_of(memory), B, D, P, M, _ld(memory))
+
+    def pixels_bwd(self, dmemory, d_encoder_out, B, D, P, M):
+        self._call("ick_pixels_bwd", _p(dmemory), _p(d_encoder_out), dt_of(dmemory), B, D, P, M, _ld(dmemory))
+
+    # ---- indicators / gate ------------------------------------------------------------------------------------------------
+    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E):
+        self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E)
+
+    def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag):
+        self._call("ick_pred_gate_fwd", _p(tmin), _p(facts), _p(WpT), _p(bias), _p(h), _p(gate), _p(hg), dt_of(gate), B, Tn, t0, F, D,
+                   _ld(gate), _ld(WpT), NP, lag)
+
+    def gate_mul_bwd(self, dHG, h, gate, dG, dH):
+        assert dHG.is_contiguous() and h.is_contiguous() and gate.is_contiguous() and dG.is_contiguous() and dH.is_contiguous()
+        self._call("ick_gate_mul_bwd", _p(dHG), _p(h), _p(gate), _p(dG), _p(dH), dt_of(h), h.numel())
+
+    def pred_gate_bwd(self, dG, tmin, facts, gflat, wp_off, B, T, F, D, NP, lag):
+        self._call("ick_pred_gate_bwd", _p(dG), _p(tmin), _p(facts), _p(gflat), wp_off, dt_of(dG), B, T, F, D, _ld(dG), NP, lag)
+
+    # ---- pointer heads -----------------------------------------------------------------------------------------------------
+    def pointer_fwd(self, h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, col0, lag):
+        self._call("ick_pointer_fwd", _p(h), _p(ctx), _p(w), _p(bias), _p(first_t), _p(scores), dt_of(h), B, Tn, t0, S, D, _ld(h),
+                   _ld(scores), col0, lag)
+
+    def pointer_bwd(self, dS, h, ctx, w, first_t, dCtx, dH, gflat, w_off, bias_off, B, T, S, D, col0, lag):
+        self._call("ick_pointer_bwd", _p(dS), _p(h), _p(ctx), _p(w), _p(first_t), _p(dCtx), _p(dH), _p(gflat), w_off, bias_off,
+                   dt_of(h), B, T, S, D, _ld(h), _ld(dS), col0, lag, n=2)
+
+    # ---- loss / optimizer / misc ---------------------------------------------------------------------------------------------
+    def ce(self, scores, captions_sorted, decode_len, loss_acc, dscores, B, T, W, pad):
+        self._call("ick_ce_fwd_bwd", _p(scores), _p(captions_sorted), _p(decode_len), _p(loss_acc), _p(dscores),
+                   dt_of(dscores) if dscores is not None else F32, B, T, W, _ld(scores), _ld(dscores) if dscores is not None else W, pad)
+
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2, clip, count, grad_scale, dstA, dstB, dstC, packT, packF,
+                  update=True):
+        self._call("ick_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, bc1, bc2, clip, _p(count),
+                   grad_scale, _p(dstA), _p(dstB), _p(dstC), _p(packT), dt_of(packT), _p(packF), int(update))
+
+    def cast2d(self, src, dst, cols):
+        rows = src.shape[0]
+        self._call("ick_cast2d", _p(src), dt_of(src), _p(dst), dt_of(dst), rows, cols, _ld(src), _ld(dst))
+
+    def accum_f32(self, src, dst):
+        assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+        self._call("ick_accum_f32", _p(src), dt_of(src), _p(dst), src.numel())
+
+    def colsum(self, x, out, cols):
+        self._call("ick_colsum", _p(x), dt_of(x), _p(out), x.shape[0], cols, _ld(x))
+
+    def greedy_select(self, scores, W, output, second, captions, masks, done, margins, B, step, Tmax, V, E, has_facts, end_tok):
+        self._call("ick_greedy_select", _p(scores), W, _ld(scores), _p(output), _p(second), _p(captions), _p(masks), _p(done),
+                   _p(margins), B, step, Tmax, V, E, int(has_facts), end_tok)

@@ -1,0 +1,299 @@
+"""
+Drop-in module API: ``Encoder`` and ``DecoderTransformer`` with the reference's constructor and call signatures
+(G/models.py:9-60, 212-443; K/models.py:290-609; N/models.py:273-592) and the reference's ``state_dict`` key names,
+backed by the sm_100a kernel engine.  Variant modules: ``ickb200.geo_aware``, ``ickb200.knowledge_aware``,
+``ickb200.news_knowledge_aware`` (each exports ``Encoder``, ``DecoderTransformer``, ``device``).
+
+    decoder(captions, encoder_out, caption_masks, caption_lengths, entities[, facts])
+        -> (scores (B,T,V+E[+F]) fp32, captions_sorted (B,T) int64, decode_lengths list[int])     G/train.py:270-272
+    decoder.predict(encoder_out, max_pred_len, entities[, facts]) -> (max_pred_len, 1) int64     G/eval.py:83
+
+There is no CPU path: calling the decoder without a CUDA device (or without the built kernel library) raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+from types import SimpleNamespace as NS
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import layout
+from .engine import DecoderEngine
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")  # same module-level name as the reference
+
+
+def _default_dtype() -> torch.dtype:
+    return {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}[
+        os.environ.get("ICKB200_DTYPE", "bf16").lower()]
+
+
+class Encoder(nn.Module):
+    """
+    Image encoder (G/models.py:9-60): ResNet-101 trunk -> AdaptiveAvgPool2d(14) -> 1x1 conv 2048->emb_dim -> (B, emb_dim, 196).
+    The trunk is stock torchvision/cuDNN (out of scope of the B200 path).
+    """
+
+    def __init__(self, encoded_image_size=14, emb_dim=300, encoder_dim=2048):
+        super().__init__()
+        import torchvision
+
+        self.emb_dim = emb_dim
+        try:
+            resnet = torchvision.models.resnet101(pretrained=True)
+        except Exception:  # no network / no cached weights: random init, same architecture
+            resnet = torchvision.models.resnet101(weights=None)
+        self.resnet = nn.Sequential(*list(resnet.children())[:-2])
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((encoded_image_size, encoded_image_size))
+        self.conv1 = nn.Conv2d(encoder_dim, emb_dim, 1)
+        self.fine_tune()
+
+    def forward(self, images):
+        out = self.adaptive_pool(self.resnet(images))
+        out = self.conv1(out)
+        return out.view(out.shape[0], self.emb_dim, -1)
+
+    def fine_tune(self, fine_tune=True):
+        for p in self.resnet.parameters():
+            p.requires_grad = False
+        for c in list(self.resnet.children())[5:]:
+            for p in c.parameters():
+                p.requires_grad = fine_tune
+
+
+def _register(root: nn.Module, key: str, param: nn.Parameter) -> None:
+    parts = key.split(".")
+    m = root
+    for name in parts[:-1]:
+        if name not in m._modules:
+            m.add_module(name, nn.Module())
+        m = m._modules[name]
+    m.register_parameter(parts[-1], param)
+
+
+class _DecoderFn(torch.autograd.Function):
+    """One autograd node for the whole decoder: forward = engine.forward, backward = the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, module, inp, seed, encoder_out, *params):
+        eng = module._engine
+        scores, ectx = eng.forward(inp, train=module.training, seed=seed)
+        ctx.module, ctx.ectx = module, ectx
+        ctx.need_enc = encoder_out.requires_grad
+        ctx.param_req = [p.requires_grad for p in params]
+        return scores
+
+    @staticmethod
+    def backward(ctx, dscores):
+        module, ectx = ctx.module, ctx.ectx
+        eng = module._engine
+        B, T, W = dscores.shape
+        ldW = (W + 7) // 8 * 8
+        ds = torch.empty(B * T, ldW, dtype=eng.dtype, device=dscores.device)
+        eng.K.cast2d(dscores.contiguous().view(B * T, W), ds, W)
+        gflat = torch.zeros(eng.plan.n_params, dtype=torch.float32, device=dscores.device)
+        d_enc = eng.backward(ectx, ds, gflat, need_encoder_grad=ctx.need_enc)
+        if d_enc is not None:
+            d_enc = d_enc[ectx.inp.unsort]  # back to the caller's (unsorted) batch order
+        grads = []
+        for (name, _), req in zip(eng.plan.shapes.items(), ctx.param_req):
+            grads.append(eng.param(name, gflat) if req else None)
+        return (None, None, None, d_enc, *grads)
+
+
+class DecoderTransformer(nn.Module):
+    """Generates the caption.  Subclasses fix ``variant`` ("G" geo-aware, "K" knowledge-aware, "N" news-knowledge-aware)."""
+
+    variant = "G"
+    # Test seam, set ONLY by tests/ (tests/hostsim.py checks the host-side orchestration on a GPU-less box).
+    # The product never sets it: without it a non-CUDA device raises.
+    _test_kernel_factory = None
+
+    def __init__(self, word_map, emb_dim, decoder_dim, encoder_dim, num_heads, num_layers, dropout_dec=0.5, dropout_enc=0.5,
+                 dropout_pos=0.1, compute_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        self.word_map = word_map
+        self.vocab_size = len(word_map)
+        self.emb_dim = emb_dim
+        self.decoder_dim, self.encoder_dim = decoder_dim, encoder_dim
+        self.num_heads, self.num_layers = num_heads, num_layers
+        self.dropout_dec, self.dropout_enc, self.dropout_pos = dropout_dec, dropout_enc, dropout_pos
+        self.num_predicates = layout.NUM_PRED[self.variant]
+        self.compute_dtype = compute_dtype
+        self.lookahead_mask = None  # kept for attribute parity with the reference (the causal mask lives in the kernel)
+        shapes = layout.param_shapes(self.variant, self.vocab_size, emb_dim, num_layers, decoder_dim, encoder_dim)
+        n = sum(int(math.prod(s)) for s in shapes.values())
+        flat = torch.zeros(n, dtype=torch.float32)
+        off = 0
+        self._param_names: List[str] = list(shapes.keys())
+        for key, shp in shapes.items():
+            cnt = int(math.prod(shp))
+            p = nn.Parameter(flat[off : off + cnt].view(*shp))
+            _register(self, key, p)
+            off += cnt
+        if self.variant != "G":
+            # the reference registers one nn.Embedding under two names (K/models.py:330-331); keep both state_dict keys
+            _register(self, "fact_encoder.predicate_embedding.weight", self._get("predicate_embedding.weight"))
+        pe = torch.zeros(5000, emb_dim)
+        position = torch.arange(0, 5000, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, emb_dim, 2).float() * (-math.log(10000.0) / emb_dim))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        if "pos_encoder" not in self._modules:
+            self.add_module("pos_encoder", nn.Module())
+        self.pos_encoder.register_buffer("pe", pe.unsqueeze(0).transpose(0, 1))
+        self._flat = flat
+        self._engine: Optional[DecoderEngine] = None
+        self._packed_version = None
+        self._step = 0
+        self.init_weights()
+
+    # ---- parameter plumbing -------------------------------------------------------------------------------------------------
+    def _get(self, key: str) -> nn.Parameter:
+        m = self
+        parts = key.split(".")
+        for name in parts[:-1]:
+            m = m._modules[name]
+        return m._parameters[parts[-1]]
+
+    def _params(self) -> List[nn.Parameter]:
+        return [self._get(k) for k in self._param_names]
+
+    def init_weights(self):
+        """Same distributions as the reference's constructors (torch defaults) and init_weights (G/models.py:264-272)."""
+        with torch.no_grad():
+            for key in self._param_names:
+                p = self._get(key)
+                if key.endswith("in_proj_weight"):
+                    nn.init.xavier_uniform_(p)
+                elif key.endswith(("in_proj_bias", "out_proj.bias")) or (".norm" in key and key.endswith("bias")):
+                    p.zero_()
+                elif ".norm" in key and key.endswith("weight"):
+                    p.fill_(1.0)
+                elif key.endswith(("out_proj.weight", "linear1.weight", "linear2.weight")):
+                    nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+                elif key.endswith(("linear1.bias", "linear2.bias")):
+                    fan_in = self._get(key[:-4] + "weight").shape[1]
+                    bound = 1 / math.sqrt(fan_in)
+                    p.uniform_(-bound, bound)
+                elif "embedding" in key:
+                    p.normal_()
+                elif key.startswith("fc_") and key.endswith("weight"):
+                    p.uniform_(-0.1, 0.1)
+                elif key.startswith("fc_") and key.endswith("bias"):
+                    p.zero_()
+
+    def load_pretrained_embeddings(self, embeddings):
+        """G/models.py:274-280 (the reference swaps the Parameter; here the values are copied into the flat storage)."""
+        with torch.no_grad():
+            self._get("word_embedding.weight").copy_(embeddings)
+
+    def fine_tune_embeddings(self, fine_tune=True):
+        """G/models.py:282-289."""
+        self._get("word_embedding.weight").requires_grad = fine_tune
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engine"] = None  # ctypes handles and device buffers are rebuilt lazily after unpickling (G/utils.py:32-46)
+        st["_flat"] = None
+        st["_packed_version"] = None
+        return st
+
+    # ---- engine -----------------------------------------------------------------------------------------------------------------
+    def _ensure_engine(self) -> DecoderEngine:
+        params = self._params()
+        dev = params[0].device
+        if dev.type != "cuda" and type(self)._test_kernel_factory is None:
+            raise RuntimeError("ickb200 DecoderTransformer runs on a CUDA device only (no CPU fallback); call .to('cuda') first")
+        flat = self._flat
+        ok = flat is not None and flat.device == dev
+        if ok:
+            base, off = flat.data_ptr(), 0
+            for p in params:
+                if p.data_ptr() != base + 4 * off or p.dtype != torch.float32:
+                    ok = False
+                    break
+                off += p.numel()
+        if not ok:
+            # .to(device) / load_state_dict replaced the storages: gather into one flat buffer again and re-point the views
+            n = sum(p.numel() for p in params)
+            flat = torch.empty(n, dtype=torch.float32, device=dev)
+            off = 0
+            with torch.no_grad():
+                for p in params:
+                    cnt = p.numel()
+                    flat[off : off + cnt].copy_(p.detach().reshape(-1).float())
+                    p.data = flat[off : off + cnt].view(p.shape)
+                    off += cnt
+            self._flat = flat
+            self._packed_version = None
+            if self._engine is not None and self._engine.device != dev:
+                self._engine = None
+        if self._engine is None:
+            if type(self)._test_kernel_factory is not None:
+                kernels = type(self)._test_kernel_factory()
+            else:
+                from .kernels import CudaKernels
+
+                kernels = CudaKernels()
+            plan = layout.PackPlan(self.variant, self.vocab_size, self.emb_dim, self.num_heads, self.num_layers, self.decoder_dim,
+                                   self.encoder_dim)
+            self._engine = DecoderEngine(plan, kernels, dev, self.compute_dtype or _default_dtype(), self.word_map["<pad>"],
+                                         self.word_map["<start>"], self.word_map["<end>"], self.dropout_dec, self.dropout_enc,
+                                         self.dropout_pos)
+            self._packed_version = None
+        self._engine.attach(self._flat)
+        ver = (self._flat.data_ptr(), sum(p._version for p in params))
+        if ver != self._packed_version:
+            self._engine.repack()
+            self._packed_version = ver
+        return self._engine
+
+    # ---- reference API --------------------------------------------------------------------------------------------------------------
+    def _sorted_inputs(self, dev, captions, encoder_out, caption_masks, caption_lengths, entities, facts):
+        lengths, sort_ind = caption_lengths.to(dev).squeeze(1).sort(dim=0, descending=True)  # G/models.py:330
+        inp = NS()
+        inp.captions = captions.to(dev)[sort_ind].contiguous()
+        inp.caption_masks = caption_masks.to(dev)[sort_ind].contiguous()
+        inp.encoder_out = encoder_out.detach().to(dev, torch.float32)[sort_ind].contiguous()
+        inp.entities = entities.to(dev, torch.float32)[sort_ind].contiguous()  # arrives on the CPU (G/train.py:263-266)
+        inp.facts = facts.to(dev)[sort_ind].contiguous() if facts is not None else None
+        return inp, lengths, sort_ind
+
+    def forward(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None):
+        if (self.variant == "G") != (facts is None):
+            raise TypeError(f"variant {self.variant}: facts {'not accepted' if self.variant == 'G' else 'required'}")
+        eng = self._ensure_engine()
+        inp, lengths, sort_ind = self._sorted_inputs(eng.device, captions, encoder_out, caption_masks, caption_lengths, entities, facts)
+        decode_lengths = (lengths - 1).tolist()
+        seed = None
+        if self.training:
+            self._step += 1
+            seed = (int(torch.initial_seed()) * 1000003 + self._step) & 0x7FFFFFFF
+        params = self._params()
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in params)):
+            # the autograd node needs the inverse permutation to hand d(encoder_out) back in the caller's order
+            inp.unsort = torch.empty_like(sort_ind)
+            inp.unsort[sort_ind] = torch.arange(sort_ind.numel(), device=sort_ind.device)
+            scores = _DecoderFn.apply(self, inp, seed, encoder_out, *params)
+        else:
+            scores, _ = eng.forward(inp, train=self.training, seed=seed)
+        return scores, inp.captions, decode_lengths
+
+    def predict_batch(self, encoder_out, max_pred_len, entities, facts=None, return_margins=False):
+        """Greedy decoding of a batch of images at once -> (B, max_pred_len) int64.  (The reference API is batch 1.)"""
+        eng = self._ensure_engine()
+        dev = eng.device
+        inp = NS(encoder_out=encoder_out.detach().to(dev, torch.float32).contiguous(),
+                 entities=entities.to(dev, torch.float32).contiguous(),
+                 facts=facts.to(dev).contiguous() if facts is not None else None)
+        with torch.no_grad():
+            return eng.greedy_decode(inp, max_pred_len, return_margins=return_margins)
+
+    def predict(self, encoder_out, max_pred_len, entities, facts=None):
+        """G/models.py:363-443: batch-1 greedy decode -> (max_pred_len, 1) int64."""
+        out = self.predict_batch(encoder_out, max_pred_len, entities, facts)
+        return out.transpose(0, 1).contiguous()

@@ -1,0 +1,143 @@
+/*
+ * ickb200 — C ABI of the B200-native caption-decoder kernels (libickb200.so).
+ *
+ * The reference (sonniki/image-captioning-with-external-knowledge) has no FFI layer: its hot path is the Python
+ * nn.Module API `models.DecoderTransformer.forward / .predict` (geo-aware/models.py:315,363;
+ * knowledge-aware/models.py:457,516; news-knowledge-aware/models.py:440,499), whose arithmetic is stock PyTorch.
+ * This header is the boundary that replaces those PyTorch library calls: every entry point takes raw DEVICE
+ * pointers, explicit sizes / leading dimensions and a cudaStream_t, writes only caller-allocated outputs, keeps no
+ * global state, and returns 0 on success (non-zero: see ick_last_error()).  The Python host side
+ * (image-captioning-with-external-knowledge_b200/kernels.py) parses THIS FILE to build its ctypes signatures.
+ *
+ * Conventions
+ *   dt            activation dtype: 0 = fp32, 1 = bf16 (fp32 accumulation everywhere)
+ *   rows          activations are row-major (batch, position) rows of `ld` elements; logical width D = 300, pad
+ *                 columns [D, ld) hold zeros ("dense layout"); projections to/from attention use the "head layout":
+ *                 head h in columns [32h, 32h+30), two zero pad lanes per head (10 x 32 = 320 columns)
+ *   gflat         flat fp32 gradient buffer in the reference's parameter order (state_dict order); *_off arguments
+ *                 are element offsets into it; weight/bias gradients ACCUMULATE (+=) like autograd
+ *   dropout       counter-hash masks: keep iff hash(seed, site, element index) >= p * 2^32, scaled by 1/(1-p);
+ *                 p = 0 disables.  Backward kernels regenerate the mask from (seed, site).
+ */
+#ifndef ICKB200_H
+#define ICKB200_H
+
+#include <cuda_runtime_api.h>
+
+#define ICK_ABI_VERSION 1
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ick_last_error(void);
+int ick_abi_version(void);
+
+/* ---- dense projections: nn.Linear inside nn.MultiheadAttention / Transformer*Layer, fc_vocab --------------------- */
+/* C[M,N] (+)= A[M,K] * W[N,K]^T + bias.  epi: 0 none, 1 ReLU+dropout (linear1 -> activation -> dropout),
+ * 2 ReLU/dropout backward (C = aux != 0 ? acc / (1-p) : 0).  Replaces F.linear at G/models.py:303 (fc_vocab) and inside
+ * torch's TransformerEncoderLayer/DecoderLayer (constructed G/models.py:241-244).  CUDA-core path (fp32 parity mode). */
+int ick_gemm_tn_simt(const void* A, int a_dt, const void* W, int w_dt, void* C, int c_dt, const float* bias, const void* aux,
+                     int M, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p,
+                     unsigned seed, unsigned site, cudaStream_t stream);
+/* gflat[rowoff[n] + colmap[k]] += sum_m dY[m,n] X[m,k]; gflat[biasoff[n]] += sum_m dY[m,n].  rowoff/colmap/biasoff
+ * translate packed (padded, head-layout) indices to the reference's parameter layout; -1 skips.  autograd of F.linear. */
+int ick_wgrad_simt(const void* dY, int y_dt, const void* X, int x_dt, float* gflat, const int* rowoff, const int* colmap,
+                   const int* biasoff, int M, int N, int K, int ldy, int ldx, cudaStream_t stream);
+
+/* Same contracts on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators, TMA operand staging); bf16 operands.
+ * ick_gemm_tn_tc additionally needs K % 64 == 0 or TMA zero-fill (handled), lda/ldw multiples of 8. */
+int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float* bias, const void* aux, int M, int N, int K, int lda,
+                   int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p, unsigned seed, unsigned site,
+                   cudaStream_t stream);
+int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M, int N,
+                 int K, int ldy, int ldx, cudaStream_t stream);
+
+/* ---- attention: F.multi_head_attention_forward inside the Transformer layers ------------------------------------------ */
+/* O = dropout(softmax(Q K^T / sqrt(dh) [+ causal mask])) V per (batch, head); lse[b,h,i] (log2 domain) is saved for backward.
+ * Causal mask = _generate_square_subsequent_mask, G/models.py:256-262. */
+int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O, float* lse, int dt, int B, int H, int Sq, int Sk, int dh,
+                int ldq, int ldk, int ldv, int ldo, int causal, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
+int ick_mha_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
+                void* dK, void* dV, int dt, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo,
+                int lddq, int lddk, int lddv, int causal, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
+/* one query per (batch, head) against klen cached keys/values (KV-cached greedy decode; predict() re-decodes instead) */
+int ick_mha_decode(const void* Q, const void* K, const void* V, void* O, int dt, int B, int H, int dh, int ldq, int ldk, int ldv,
+                   int ldo, long long kbatch_stride, long long vbatch_stride, int klen, cudaStream_t stream);
+
+/* ---- residual + dropout + LayerNorm (post-LN sublayer tails of the Transformer layers) --------------------------------- */
+/* sub <- s = x + dropout(sub); y[map(r)] = LN(s).  map: out_row = (r / map_s_in) * map_s_out + map_off + r % map_s_in
+ * (map_s_in = 0: identity) lets the last encoder layer write into the memory buffer = torch.cat at K/models.py:497-499. */
+int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int dt,
+                   int rows, int d, int ldx, int lds, int ldy, float eps, int map_s_in, int map_s_out, int map_off, float drop_p,
+                   unsigned seed, unsigned site, cudaStream_t stream);
+int ick_add_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* dres, void* dsub,
+                   float* dgamma, float* dbeta, int dt, int rows, int d, int lddy, int lds, int ldres, int ldsub, int map_s_in,
+                   int map_s_out, int map_off, int acc_res, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
+
+/* ---- context preparation ------------------------------------------------------------------------------------------------- */
+/* EntityEncoder.forward: variant 0 = geo (G/models.py:82-104), 1 = knowledge (K/models.py:82-133), 2 = news (N/models.py:79-134) */
+int ick_entity_encode_fwd(const float* entities, const long long* facts, const float* type_emb, const void* word_emb, void* out,
+                          int dt, int variant, int B, int E, int C, int F, int D, int ld, int ldw, int ntypes, int V,
+                          cudaStream_t stream);
+int ick_entity_encode_bwd(const float* dEnt, const float* entities, const long long* facts, const float* type_emb,
+                          const void* word_emb, float* gflat, int type_off, int word_off, int dt, int variant, int B, int E, int C,
+                          int F, int D, int ld, int ldw, int ntypes, int V, cudaStream_t stream);
+/* FactEncoder.forward, K/models.py:170-188 */
+int ick_fact_encode_fwd(const long long* facts, const void* ent_enc, const float* pred_emb, void* out, int dt, int B, int E, int F,
+                        int D, int ld, int NP, cudaStream_t stream);
+int ick_fact_encode_bwd(const float* dFact, const long long* facts, float* dEnt, float* gflat, int pred_off, int B, int E, int F,
+                        int D, int ld, int NP, cudaStream_t stream);
+/* CaptionEmbedder.forward (K/models.py:209-259) fused with *sqrt(d) and PositionEncoder (K/models.py:505-507); positions
+ * [t0, t0+Tn) of captions with row stride Tstride */
+int ick_caption_embed_fwd(const long long* captions, const long long* masks, const void* word_emb, const void* ent_enc,
+                          const void* fact_enc, const float* pe, void* out, int dt, int B, int Tstride, int t0, int Tn, int V, int E,
+                          int F, int D, int ld, int ldw, int pad, float scale, float drop_p, unsigned seed, unsigned site,
+                          cudaStream_t stream);
+int ick_caption_embed_bwd(const void* dX, const long long* captions, const long long* masks, float* dEnt, float* dFact, float* gflat,
+                          int word_off, int dt, int B, int T, int V, int E, int F, int D, int ld, int pad, float scale, float drop_p,
+                          unsigned seed, unsigned site, cudaStream_t stream);
+/* encoder_out (B, D, P) fp32 channel-major -> rows [b*M, b*M+P) of the memory buffer; encoder_out.permute(2,0,1), G/models.py:347 */
+int ick_pixels_fwd(const float* encoder_out, void* memory, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream);
+int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream);
+
+/* ---- context indicators + predicate gate: get_context_indicators K/models.py:380-418, fc_predicate K/models.py:436-437 ---- */
+int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F, int V,
+                           int E, cudaStream_t stream);
+int ick_pred_gate_fwd(const int* tmin, const long long* facts, const float* WpT, const float* bias, const void* h, void* gate,
+                      void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag, cudaStream_t stream);
+int ick_gate_mul_bwd(const void* dHG, const void* h, const void* gate, void* dG, void* dH, int dt, long long n, cudaStream_t stream);
+int ick_pred_gate_bwd(const void* dG, const int* tmin, const long long* facts, float* gflat, int wp_off, int dt, int B, int T, int F,
+                      int D, int ld, int NP, int lag, cudaStream_t stream);
+
+/* ---- pointer heads: fc_entity / fc_fact over h*ctx, get_scores K/models.py:440-452 ----------------------------------------- */
+int ick_pointer_fwd(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores, int dt,
+                    int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream);
+int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, const float* w, const int* first_t, float* dCtx, void* dH,
+                    float* gflat, int w_off, int bias_off, int dt, int B, int T, int S, int D, int ld, int ldds, int col0, int lag,
+                    cudaStream_t stream);
+
+/* ---- loss / optimizer / packing --------------------------------------------------------------------------------------------- */
+/* pack_padded_sequence + CrossEntropyLoss(ignore_index=pad), G/train.py:275-281.  loss_acc[0] += sum of row losses,
+ * loss_acc[1] += number of kept rows; dscores = softmax - onehot (unscaled, zeros on dropped rows) or NULL. */
+int ick_ce_fwd_bwd(const float* scores, const long long* captions_sorted, const int* decode_len, float* loss_acc, void* dscores,
+                   int dt, int B, int T, int W, int lds, int ldd, int pad, cudaStream_t stream);
+/* grad = g * grad_scale / max(count[0],1), clamped to +-clip (ut.clip_gradient, G/utils.py:75-85), torch.optim.Adam update
+ * (G/train.py:85-88, 292); then every parameter element is scattered to its packed copies: dstA/dstB index the dt-typed
+ * packT (forward and transposed layouts), dstC the fp32 packF.  update = 0 only repacks. */
+int ick_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float bias_corr1, float bias_corr2, float clip, const float* count, float grad_scale, const int* dstA,
+                  const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, cudaStream_t stream);
+int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, long long rows, int cols, int lds, int ldd, cudaStream_t stream);
+int ick_accum_f32(const void* src, int dt, float* dst, long long n, cudaStream_t stream);
+int ick_colsum(const void* x, int dt, float* out, long long rows, int cols, int ld, cudaStream_t stream);
+
+/* ---- greedy decode step: argmax, top-2, <end> check, repetition clean-up, next input token/mask; G/models.py:409-442 -------- */
+int ick_greedy_select(const float* scores, int W, int lds, long long* output, int* second, long long* captions, long long* masks,
+                      int* done, float* margins, int B, int step, int Tmax, int V, int E, int has_facts, int end_tok,
+                      cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICKB200_H */

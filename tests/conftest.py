@@ -16,7 +16,7 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
 
-    if torch.cuda.is_available():
+    if torch.cuda.is_available() or os.environ.get("ICK_DRYRUN") == "1":
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

@@ -42,3 +42,42 @@ def nmax_err(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- building the product module for tests -------------------------------------------------------------------------------
+def module_cls(variant):
+    from ickb200 import geo_aware, knowledge_aware, news_knowledge_aware
+
+    return {"G": geo_aware, "K": knowledge_aware, "N": news_knowledge_aware}[variant].DecoderTransformer
+
+
+def build_module(cfg, device, dtype=torch.float32, seed=0, dropouts=(0.5, 0.5, 0.1)):
+    wm = syn.make_word_map(cfg.V)
+    dec = module_cls(cfg.variant)(wm, cfg.D, cfg.ff, cfg.ff, cfg.H, cfg.L, dropout_dec=dropouts[0], dropout_enc=dropouts[1],
+                                  dropout_pos=dropouts[2], compute_dtype=dtype)
+    shapes = layout.param_shapes(cfg.variant, cfg.V, cfg.D, cfg.L, cfg.ff, cfg.ff)
+    w = syn.det_weights(shapes, seed=seed)
+    missing = dec.load_state_dict(w, strict=False)
+    assert set(missing.missing_keys) <= {"pos_encoder.pe", "fact_encoder.predicate_embedding.weight"}, missing
+    return dec.to(device)
+
+
+def oracle_drop_fn(seed, ps):
+    """DropFn for the oracle that reproduces the kernels' masks: site name -> hash-derived multiplier tensor."""
+    from dropout_ref import drop_mul
+
+    def fn(site, shape):
+        if site == "pos":
+            p = ps["pos"]
+        elif site.startswith("transformer_decoder"):
+            p = ps["dec"]
+        else:
+            p = ps["enc"]
+        if p <= 0:
+            return None
+        n = 1
+        for s in shape:
+            n *= s
+        return drop_mul(p, seed, layout.site_id(site), n).view(*shape)
+
+    return fn

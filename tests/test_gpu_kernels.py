@@ -1,0 +1,451 @@
+"""
+GPU: every C-ABI kernel (through ickb200.kernels.CudaKernels -> libickb200.so) against the host simulation
+(tests/hostsim.py, itself checked against the oracle by test_host_wiring.py) on identical seeded inputs.
+Integer / index outputs must match exactly; floating point within the tolerance written next to each check
+(fp32: 1e-4 of the output's max magnitude; bf16 storage: 2e-2, north_star).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hostsim import FIRST_NONE, HostKernels
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+DRYRUN = os.environ.get("ICK_DRYRUN") == "1"  # debugging aid for the test code itself on a GPU-less box
+DEV = "cpu" if DRYRUN else "cuda"
+if DRYRUN:
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+@pytest.fixture(scope="module")
+def K():
+    if DRYRUN:
+        return HostKernels()
+    from ickb200.kernels import CudaKernels
+
+    return CudaKernels()
+
+
+@pytest.fixture(scope="module")
+def Hk():
+    return HostKernels()
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(shape, dtype, seed, scale=1.0):
+    return (torch.randn(*shape, generator=g(seed)) * scale).to(dtype)
+
+
+def cu(x):
+    return None if x is None else x.cuda()
+
+
+def err(a, b):
+    a, b = a.detach().float().cpu().double(), b.detach().float().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def headify(x, H, dh):
+    """zero the two pad lanes of every 32-wide head block"""
+    R = x.shape[0]
+    v = x.view(R, -1, 32).clone()
+    v[:, :, dh:] = 0
+    return v.view(R, -1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K_", [(300, 960, 320), (128, 320, 512), (77, 57, 320), (513, 1000, 320), (260, 320, 1000), (1, 960, 320)])
+def test_gemm_plain_bias(K, Hk, tc, dtype, M, N, K_):
+    if tc and dtype != torch.bfloat16:
+        pytest.skip("tensor-core path is bf16")
+    A, W = rnd((M, K_), dtype, 1), rnd((N, K_), dtype, 2, 0.1)
+    bias = rnd((N,), torch.float32, 3)
+    for out_dtype in ([dtype, torch.float32] if dtype == torch.bfloat16 else [dtype]):
+        ldc = N + 5
+        Cr = torch.zeros(M, ldc, dtype=out_dtype)
+        Cg = torch.zeros(M, ldc, dtype=out_dtype).cuda()
+        Hk.gemm(A, W, Cr[:, :N], bias=bias)
+        K.gemm(cu(A), cu(W), Cg[:, :N], bias=cu(bias), force_simt=not tc)
+        assert err(Cg[:, :N], Cr[:, :N]) < TOL[out_dtype]
+        assert float(Cg[:, N:].abs().max()) == 0.0  # columns beyond N untouched
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_epilogues(K, Hk, tc, dtype):
+    if tc and dtype != torch.bfloat16:
+        pytest.skip("tensor-core path is bf16")
+    M, N, K_ = 333, 512, 320
+    A, W, bias = rnd((M, K_), dtype, 1), rnd((N, K_), dtype, 2, 0.1), rnd((N,), torch.float32, 3)
+    drop = (0.3, 1234, 77)
+    # relu + dropout
+    Cr, Cg = torch.zeros(M, N, dtype=dtype), torch.zeros(M, N, dtype=dtype).cuda()
+    Hk.gemm(A, W, Cr, bias=bias, epi=1, drop=drop)
+    K.gemm(cu(A), cu(W), Cg, bias=cu(bias), epi=1, drop=drop, force_simt=not tc)
+    assert err(Cg, Cr) < TOL[dtype]
+    assert torch.equal(Cg.cpu() == 0, Cr == 0)  # identical dropout mask and ReLU pattern
+    # relu/dropout backward against the saved activation
+    dY, W2 = rnd((M, 320), dtype, 5), rnd((N, 320), dtype, 6, 0.1)
+    Dr, Dg = torch.zeros(M, N, dtype=dtype), torch.zeros(M, N, dtype=dtype).cuda()
+    Hk.gemm(dY, W2, Dr, aux=Cr, epi=2, drop=(0.3, 0, 0))
+    K.gemm(cu(dY), cu(W2), Dg, aux=cu(Cr), epi=2, drop=(0.3, 0, 0), force_simt=not tc)
+    assert err(Dg, Dr) < TOL[dtype]
+    # accumulate
+    C0 = rnd((M, N), dtype, 7)
+    Er, Eg = C0.clone(), C0.clone().cuda()
+    Hk.gemm(A, W, Er, accumulate=True)
+    K.gemm(cu(A), cu(W), Eg, accumulate=True, force_simt=not tc)
+    assert err(Eg, Er) < TOL[dtype]
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K_", [(1000, 960, 320), (203, 320, 512), (4100, 130, 320), (64, 1000, 320)])
+def test_wgrad(K, Hk, tc, dtype, M, N, K_):
+    if tc and dtype != torch.bfloat16:
+        pytest.skip("tensor-core path is bf16")
+    dY, X = rnd((M, N), dtype, 1), rnd((M, K_), dtype, 2)
+    # scatter maps with holes: every 7th packed row and every 11th packed column is padding
+    n_real = [n for n in range(N) if n % 7 != 6]
+    k_real = [k for k in range(K_) if k % 11 != 10]
+    Ko = len(k_real)
+    rowoff = torch.full((N,), -1, dtype=torch.int32)
+    rowoff[n_real] = (100 + torch.arange(len(n_real)) * Ko).int()
+    colmap = torch.full((K_,), -1, dtype=torch.int32)
+    colmap[k_real] = torch.arange(Ko).int()
+    bias0 = 100 + len(n_real) * Ko
+    biasoff = torch.full((N,), -1, dtype=torch.int32)
+    biasoff[n_real] = (bias0 + torch.arange(len(n_real))).int()
+    size = bias0 + len(n_real) + 50
+    Gr = rnd((size,), torch.float32, 9)
+    Gg = Gr.clone().cuda()
+    Hk.wgrad(dY, X, Gr, rowoff, colmap, biasoff)
+    K.wgrad(cu(dY), cu(X), Gg, cu(rowoff), cu(colmap), cu(biasoff), force_simt=not tc)
+    assert err(Gg, Gr) < 5e-4 if dtype == torch.float32 else err(Gg, Gr) < 5e-3  # fp32 accumulation of the same products
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+ATT_CASES = [(2, 10, 301, 301, 30, False), (3, 10, 102, 102, 30, True), (2, 10, 37, 548, 30, False), (1, 4, 5, 5, 32, True),
+             (2, 10, 130, 130, 30, True)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("p", [0.0, 0.5])
+@pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", ATT_CASES)
+def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
+    ld = 3 * H * 32 + 8
+    qkv_q = headify(rnd((B * Sq, H * 32), torch.float32, 1), H, dh).to(dtype)
+    qkv_k = headify(rnd((B * Sk, H * 32), torch.float32, 2), H, dh).to(dtype)
+    qkv_v = headify(rnd((B * Sk, H * 32), torch.float32, 3), H, dh).to(dtype)
+    # Q lives in a wider buffer (leading dimension != width), like the packed QKV projection output
+    Qbuf = torch.zeros(B * Sq, ld, dtype=dtype)
+    Qbuf[:, : H * 32] = qkv_q
+    Q = Qbuf[:, : H * 32]
+    drop = (p, 99, 5) if p > 0 else None
+    Or, lr = torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * H * Sq)
+    Og, lg = torch.zeros(B * Sq, H * 32, dtype=dtype).cuda(), torch.zeros(B * H * Sq).cuda()
+    Hk.mha_fwd(Q, qkv_k, qkv_v, Or, lr, B, H, Sq, Sk, dh, causal, drop)
+    Qg = cu(Qbuf)[:, : H * 32]
+    K.mha_fwd(Qg, cu(qkv_k), cu(qkv_v), Og, lg, B, H, Sq, Sk, dh, causal, drop)
+    assert err(Og, Or) < TOL[dtype]
+    assert float((lg.cpu() - lr).abs().max()) < (1e-3 if dtype == torch.float32 else 5e-2)
+    # backward (uses the reference forward outputs so that errors do not compound)
+    dO = headify(rnd((B * Sq, H * 32), torch.float32, 4), H, dh).to(dtype)
+    outs_r = [torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype)]
+    outs_g = [torch.full_like(o, float("nan")).cuda() for o in outs_r]
+    dsr, dsg = torch.zeros(B * H * Sq), torch.zeros(B * H * Sq).cuda()
+    Hk.mha_bwd(Q, qkv_k, qkv_v, Or, dO, lr, dsr, *outs_r, B, H, Sq, Sk, dh, causal, drop)
+    K.mha_bwd(Qg, cu(qkv_k), cu(qkv_v), cu(Or), cu(dO), cu(lr), dsg, *outs_g, B, H, Sq, Sk, dh, causal, drop)
+    for a, b, name in zip(outs_g, outs_r, ["dQ", "dK", "dV"]):
+        assert not torch.isnan(a).any(), name  # every element (pads included) is written
+        assert err(a, b) < TOL[dtype] * 2, name
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mha_decode(K, Hk, dtype):
+    B, H, dh, Tmax, klen = 5, 10, 30, 12, 7
+    ldc = 3 * H * 32
+    cache = headify(rnd((B * Tmax, ldc), torch.float32, 1), 3 * H, dh).to(dtype)
+    Q = cache.view(B, Tmax, ldc)[:, klen - 1, : H * 32]
+    Or, Og = torch.zeros(B, H * 32, dtype=dtype), torch.zeros(B, H * 32, dtype=dtype).cuda()
+    Hk.mha_decode(Q, cache[:, H * 32 : 2 * H * 32], cache[:, 2 * H * 32 :], Or, B, H, dh, Tmax * ldc, Tmax * ldc, klen)
+    cg = cu(cache)
+    K.mha_decode(cg.view(B, Tmax, ldc)[:, klen - 1, : H * 32], cg[:, H * 32 : 2 * H * 32], cg[:, 2 * H * 32 :], Og, B, H, dh, Tmax * ldc,
+                 Tmax * ldc, klen)
+    assert err(Og, Or) < TOL[dtype]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("p", [0.0, 0.4])
+@pytest.mark.parametrize("rows,rowmap,yrows", [(301 * 2, (301, 548, 196), 548 * 2), (77, (0, 0, 0), 77)])
+def test_add_ln_fwd_bwd(K, Hk, dtype, p, rows, rowmap, yrows):
+    d, ld = 300, 320
+    x, sub = rnd((rows, ld), dtype, 1), rnd((rows, ld), dtype, 2)
+    gamma, beta = 1 + 0.1 * rnd((d,), torch.float32, 3), rnd((d,), torch.float32, 4)
+    drop = (p, 7, 3) if p > 0 else None
+    yr, yg = torch.zeros(yrows, ld, dtype=dtype), torch.full((yrows, ld), 7.0, dtype=dtype).cuda()
+    sr, sg = sub.clone(), sub.clone().cuda()
+    mr, rr, mg, rg = torch.zeros(rows), torch.zeros(rows), torch.zeros(rows).cuda(), torch.zeros(rows).cuda()
+    Hk.add_ln_fwd(x, sr, gamma, beta, yr, mr, rr, d, 1e-5, rowmap, drop)
+    K.add_ln_fwd(cu(x), sg, cu(gamma), cu(beta), yg, mg, rg, d, 1e-5, rowmap, drop)
+    from hostsim import _rows
+
+    idx = _rows(rowmap, rows)
+    assert err(yg[idx.cuda()], yr[idx]) < TOL[dtype]
+    assert float(yg[idx.cuda()][:, d:].abs().max()) == 0.0  # pad columns zeroed
+    assert err(sg[:, :d], sr[:, :d]) < TOL[dtype]
+    assert err(mg, mr) < 1e-3 and err(rg, rr) < 1e-3
+    # backward
+    dy = rnd((yrows, ld), dtype, 5)
+    for acc in (False, True):
+        dres_r = rnd((rows, ld), dtype, 6) if acc else torch.zeros(rows, ld, dtype=dtype)
+        dres_g = dres_r.clone().cuda()
+        dsub_r, dsub_g = torch.zeros(rows, ld, dtype=dtype), torch.full((rows, ld), float("nan"), dtype=dtype).cuda()
+        dgr, dbr = rnd((d,), torch.float32, 8), rnd((d,), torch.float32, 9)
+        dgg, dbg = dgr.clone().cuda(), dbr.clone().cuda()
+        Hk.add_ln_bwd(dy, sr, mr, rr, gamma, dres_r, dsub_r, dgr, dbr, d, rowmap, acc, drop)
+        K.add_ln_bwd(cu(dy), cu(sr), cu(mr), cu(rr), cu(gamma), dres_g, dsub_g, dgg, dbg, d, rowmap, acc, drop)
+        assert err(dres_g[:, :d], dres_r[:, :d]) < TOL[dtype] * 2
+        assert err(dsub_g, dsub_r) < TOL[dtype] * 2
+        assert err(dgg, dgr) < 1e-3 and err(dbg, dbr) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+def make_context(variant, B, E, F, V, seed=0):
+    from ickb200 import synthetic as syn
+
+    cfg = syn.Config({0: "G", 1: "K", 2: "N"}[variant], B=B, T=14, E=E, F=F, V=V, P=20)
+    return cfg, syn.make_batch(cfg, seed=seed)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_entity_fact_caption_kernels(K, Hk, dtype, variant):
+    B, E, F, V, D, ld = 3, 23, (0 if variant == 0 else 11), 61, 300, 320
+    cfg, batch = make_context(variant, B, E, F, V)
+    nf = {0: 4, 1: 6, 2: 5}[variant]
+    ntypes = 1000 if variant < 2 else 20
+    type_emb = rnd((ntypes, D - nf), torch.float32, 1, 0.1)
+    wemb = torch.zeros(V, ld, dtype=dtype)
+    wemb[:, :D] = rnd((V, D), dtype, 2, 0.1)
+    ent, facts = batch["entities"], batch.get("facts")
+    outr, outg = torch.zeros(B * E, ld, dtype=dtype), torch.full((B * E, ld), float("nan"), dtype=dtype).cuda()
+    Hk.entity_encode_fwd(ent, facts, type_emb, wemb if variant == 2 else None, outr, variant, B, E, F, D, ntypes, V)
+    K.entity_encode_fwd(cu(ent), cu(facts), cu(type_emb), cu(wemb) if variant == 2 else None, outg, variant, B, E, F, D, ntypes, V)
+    assert err(outg, outr) < TOL[dtype]
+    # backward: type-embedding (and, news, word-embedding) gradients
+    n_flat = ntypes * (D - nf) + V * D + 10
+    type_off, word_off = 3, 3 + ntypes * (D - nf) + 2
+    dEnt = torch.zeros(B * E, ld)
+    dEnt[:, :D] = rnd((B * E, D), torch.float32, 3)
+    Gr, Gg = torch.zeros(n_flat), torch.zeros(n_flat).cuda()
+    dt = 0 if dtype == torch.float32 else 1
+    Hk.entity_encode_bwd(dEnt, ent, facts, type_emb, wemb if variant == 2 else None, Gr, type_off, word_off, dt, variant, B, E, F, D, ntypes, V)
+    K.entity_encode_bwd(cu(dEnt), cu(ent), cu(facts), cu(type_emb), cu(wemb) if variant == 2 else None, Gg, type_off, word_off, dt, variant, B, E,
+                        F, D, ntypes, V)
+    assert err(Gg, Gr) < 1e-4
+    fact_r = None
+    if variant != 0:
+        NP = 3000
+        pred_emb = rnd((NP, D), torch.float32, 4, 0.1)
+        fact_r, fact_g = torch.zeros(B * F, ld, dtype=dtype), torch.full((B * F, ld), float("nan"), dtype=dtype).cuda()
+        Hk.fact_encode_fwd(facts, outr, pred_emb, fact_r, B, E, F, D, NP)
+        K.fact_encode_fwd(cu(facts), cu(outr), cu(pred_emb), fact_g, B, E, F, D, NP)
+        assert err(fact_g, fact_r) < TOL[dtype]
+        dFact = torch.zeros(B * F, ld)
+        dFact[:, :D] = rnd((B * F, D), torch.float32, 5)
+        dEr, dEg = torch.zeros(B * E, ld), torch.zeros(B * E, ld).cuda()
+        Pr, Pg = torch.zeros(NP * D + 7), torch.zeros(NP * D + 7).cuda()
+        Hk.fact_encode_bwd(dFact, facts, dEr, Pr, 7, B, E, F, D, NP)
+        K.fact_encode_bwd(cu(dFact), cu(facts), dEg, Pg, 7, B, E, F, D, NP)
+        assert err(dEg, dEr) < 1e-5 and err(Pg, Pr) < 1e-5
+    # caption embedder (+ sqrt(d), positional table, dropout), whole sequence and single position
+    T = cfg.T
+    caps, masks = batch["captions"].clone(), batch["caption_masks"].clone()
+    caps[0, 3], masks[0, 3] = V + E + F + 5, 1   # out-of-range pointer -> <unk_ent>
+    caps[1, 2], masks[1, 2] = V + 2, 0           # pointer id with mask 0 -> <pad> word row
+    pe = rnd((T + 3, D), torch.float32, 6)
+    for (t0, Tn), p in (((0, T), 0.0), ((0, T), 0.2), ((5, 1), 0.0)):
+        drop = (p, 3, 9) if p > 0 else None
+        xr, xg = torch.zeros(B * Tn, ld, dtype=dtype), torch.full((B * Tn, ld), float("nan"), dtype=dtype).cuda()
+        Hk.caption_embed_fwd(caps, masks, wemb, outr, fact_r, pe, xr, B, T, t0, Tn, V, E, F, D, 0, math.sqrt(D), drop)
+        K.caption_embed_fwd(cu(caps), cu(masks), cu(wemb), cu(outr), cu(fact_r), cu(pe), xg, B, T, t0, Tn, V, E, F, D, 0, math.sqrt(D), drop)
+        assert err(xg, xr) < TOL[dtype]
+    dX = rnd((B * T, ld), dtype, 7)
+    drop = (0.2, 3, 9)
+    dEr, dEg = torch.zeros(B * E, ld), torch.zeros(B * E, ld).cuda()
+    dFr = torch.zeros(B * F, ld) if F else None
+    dFg = cu(dFr.clone()) if F else None
+    Wr, Wg = torch.zeros(V * D + 5), torch.zeros(V * D + 5).cuda()
+    Hk.caption_embed_bwd(dX, caps, masks, dEr, dFr, Wr, 5, B, T, V, E, F, D, 0, math.sqrt(D), drop)
+    K.caption_embed_bwd(cu(dX), cu(caps), cu(masks), dEg, dFg, Wg, 5, B, T, V, E, F, D, 0, math.sqrt(D), drop)
+    assert err(dEg, dEr) < 1e-4 and err(Wg, Wr) < 1e-4
+    if F:
+        assert err(dFg, dFr) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pixels(K, Hk, dtype):
+    B, D, P, M, ld = 3, 300, 196, 250, 320
+    enc = rnd((B, D, P), torch.float32, 1)
+    mr, mg = torch.full((B * M, ld), 3.0, dtype=dtype), torch.full((B * M, ld), 3.0, dtype=dtype).cuda()
+    Hk.pixels_fwd(enc, mr, B, D, P, M)
+    K.pixels_fwd(cu(enc), mg, B, D, P, M)
+    assert err(mg, mr) < TOL[dtype] and torch.equal(mg.cpu()[:, D:], mr[:, D:])
+    dr, dg = torch.zeros(B, D, P), torch.zeros(B, D, P).cuda()
+    Hk.pixels_bwd(mr, dr, B, D, P, M)
+    K.pixels_bwd(cu(mr), dg, B, D, P, M)
+    assert torch.equal(dg.cpu(), dr)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("lag,Tn,t0", [(0, 14, 0), (1, 1, 6)])
+def test_indicators_gate_pointer(K, Hk, dtype, lag, Tn, t0):
+    B, E, F, V, D, ld, NP = 4, 23, 17, 61, 300, 320, 3000
+    cfg, batch = make_context(1, B, E, F, V, seed=5)
+    T = cfg.T
+    caps, facts = batch["captions"], batch["facts"]
+    ftr, tmr = torch.zeros(B * F, dtype=torch.int32), torch.zeros(B * F, dtype=torch.int32)
+    ftg, tmg = ftr.clone().cuda(), tmr.clone().cuda()
+    Hk.fact_first_mention(caps, facts, ftr, tmr, B, T, F, V, E)
+    K.fact_first_mention(cu(caps), cu(facts), ftg, tmg, B, T, F, V, E)
+    assert torch.equal(ftg.cpu(), ftr) and torch.equal(tmg.cpu(), tmr)  # integer work: bit-exact
+    assert int((ftr < FIRST_NONE).sum()) > 0
+    WpT = torch.zeros(NP, ld)
+    WpT[:, :D] = rnd((NP, D), torch.float32, 1, 0.3)
+    bias = rnd((D,), torch.float32, 2)
+    h = torch.zeros(B * Tn, ld, dtype=dtype)
+    h[:, :D] = rnd((B * Tn, D), dtype, 3)
+    gr, hgr = torch.zeros(B * Tn, ld, dtype=dtype), torch.zeros(B * Tn, ld, dtype=dtype)
+    gg, hgg = torch.full_like(gr, float("nan")).cuda(), torch.full_like(gr, float("nan")).cuda()
+    Hk.pred_gate_fwd(tmr, facts, WpT, bias, h, gr, hgr, B, Tn, t0, F, D, NP, lag)
+    K.pred_gate_fwd(tmg, cu(facts), cu(WpT), cu(bias), cu(h), gg, hgg, B, Tn, t0, F, D, NP, lag)
+    assert err(gg, gr) < TOL[dtype] and err(hgg, hgr) < TOL[dtype]
+    # pointer scores into a shared score buffer
+    ctx = torch.zeros(B * F, ld, dtype=dtype)
+    ctx[:, :D] = rnd((B * F, D), dtype, 4)
+    w, b1 = rnd((D,), torch.float32, 5), rnd((1,), torch.float32, 6)
+    Wd = V + E + F
+    sr, sg = torch.zeros(B * Tn, Wd), torch.zeros(B * Tn, Wd).cuda()
+    Hk.pointer_fwd(h, ctx, w, b1, ftr, sr, B, Tn, t0, F, D, V + E, lag)
+    K.pointer_fwd(cu(h), cu(ctx), cu(w), cu(b1), ftg, sg, B, Tn, t0, F, D, V + E, lag)
+    assert err(sg, sr) < TOL[dtype]
+    if Tn == 1:
+        return
+    # backward kernels (teacher-forced only)
+    ldd = (Wd + 7) // 8 * 8
+    dS = torch.zeros(B * T, ldd, dtype=dtype)
+    dS[:, :Wd] = rnd((B * T, Wd), dtype, 7)
+    n_flat = D + 1 + D * NP + 9
+    for first in (ftr, None):
+        dCr, dCg = rnd((B * F, ld), torch.float32, 8), None
+        dCg = dCr.clone().cuda()
+        dHr = rnd((B * T, ld), dtype, 9)
+        dHg = dHr.clone().cuda()
+        Gr, Gg = torch.zeros(n_flat), torch.zeros(n_flat).cuda()
+        Hk.pointer_bwd(dS, h, ctx, w, first, dCr, dHr, Gr, 1, 0, B, T, F, D, V + E, 0)
+        K.pointer_bwd(cu(dS), cu(h), cu(ctx), cu(w), cu(first), dCg, dHg, Gg, 1, 0, B, T, F, D, V + E, 0)
+        assert err(dCg[:, :D], dCr[:, :D]) < TOL[dtype] and err(dHg[:, :D], dHr[:, :D]) < TOL[dtype] * 2
+        assert err(Gg, Gr) < (1e-4 if dtype == torch.float32 else 1e-3)
+    dhg = torch.zeros(B * T, ld, dtype=dtype)
+    dhg[:, :D] = rnd((B * T, D), dtype, 10)
+    outs_r = [torch.zeros(B * T, ld, dtype=dtype) for _ in range(2)]
+    outs_g = [torch.zeros(B * T, ld, dtype=dtype).cuda() for _ in range(2)]
+    Hk.gate_mul_bwd(dhg, h, gr, *outs_r)
+    K.gate_mul_bwd(cu(dhg), cu(h), cu(gr), *outs_g)
+    assert err(outs_g[0], outs_r[0]) < TOL[dtype] and err(outs_g[1], outs_r[1]) < TOL[dtype]
+    Gr, Gg = torch.zeros(n_flat), torch.zeros(n_flat).cuda()
+    Hk.pred_gate_bwd(outs_r[0], tmr, facts, Gr, 5, B, T, F, D, NP, 0)
+    K.pred_gate_bwd(cu(outs_r[0]), tmg, cu(facts), Gg, 5, B, T, F, D, NP, 0)
+    assert err(Gg, Gr) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ce_adam_misc(K, Hk, dtype):
+    B, T, Wd = 5, 9, 1037
+    scores = rnd((B * T, Wd), torch.float32, 1, 3.0)
+    caps = torch.randint(0, Wd, (B, T), generator=g(2))
+    caps[:, 0] = 3
+    caps[1, 4:] = 0  # pad targets inside the decode length are ignored
+    dl = torch.tensor([8, 8, 5, 3, 0], dtype=torch.int32)
+    ldd = (Wd + 7) // 8 * 8
+    accr, accg = torch.zeros(2), torch.zeros(2).cuda()
+    dr, dg = torch.zeros(B * T, ldd, dtype=dtype), torch.full((B * T, ldd), float("nan"), dtype=dtype).cuda()
+    Hk.ce(scores, caps, dl, accr, dr, B, T, Wd, 0)
+    K.ce(cu(scores), cu(caps), cu(dl), accg, dg, B, T, Wd, 0)
+    assert float(accg[1]) == float(accr[1]) and abs(float(accg[0]) - float(accr[0])) < 1e-3 * float(accr[0])
+    assert err(dg, dr) < TOL[dtype]
+    # adam + packing
+    n = 5000
+    p0, gr_, m0, v0 = rnd((n,), torch.float32, 3), rnd((n,), torch.float32, 4, 10.0), rnd((n,), torch.float32, 5, 0.1), rnd((n,), torch.float32, 6).abs()
+    dstA = torch.randperm(n, generator=g(7)).int()
+    dstA[::5] = -1
+    dstB = (n + torch.randperm(n, generator=g(8))).int()
+    dstC = torch.randperm(n, generator=g(9)).int()
+    dstC[::3] = -1
+    cnt = torch.tensor([7.0])
+    args = (4e-4, 0.9, 0.999, 1e-8, 1 - 0.9 ** 3, 1 - 0.999 ** 3, 5.0)
+    pr, mr_, vr = p0.clone(), m0.clone(), v0.clone()
+    pTr, pFr = torch.zeros(2 * n, dtype=dtype), torch.zeros(n)
+    Hk.adam_step(pr, gr_, mr_, vr, *args, cnt, 2.0, dstA, dstB, dstC, pTr, pFr, True)
+    pg, mg_, vg = p0.clone().cuda(), m0.clone().cuda(), v0.clone().cuda()
+    pTg, pFg = torch.zeros(2 * n, dtype=dtype).cuda(), torch.zeros(n).cuda()
+    K.adam_step(pg, cu(gr_), mg_, vg, *args, cu(cnt), 2.0, cu(dstA), cu(dstB), cu(dstC), pTg, pFg, True)
+    assert err(pg, pr) < 1e-6 and err(mg_, mr_) < 1e-6 and err(vg, vr) < 1e-6
+    assert err(pTg, pTr) < (1e-6 if dtype == torch.float32 else 1e-2) and err(pFg, pFr) < 1e-6
+    # cast2d / accum / colsum
+    src = rnd((37, 50), torch.float32, 10)
+    dr2, dg2 = torch.zeros(37, 56, dtype=dtype), torch.full((37, 56), float("nan"), dtype=dtype).cuda()
+    Hk.cast2d(src[:, :45], dr2, 45)
+    K.cast2d(cu(src)[:, :45], dg2, 45)
+    assert torch.equal(dg2.cpu(), dr2)
+    a = rnd((1000,), dtype, 11)
+    br, bg = rnd((1000,), torch.float32, 12), None
+    bg = br.clone().cuda()
+    Hk.accum_f32(a, br)
+    K.accum_f32(cu(a), bg)
+    assert err(bg, br) < 1e-6
+    x = rnd((777, 320), dtype, 13)
+    cr, cg = torch.zeros(300), torch.zeros(300).cuda()
+    Hk.colsum(x, cr, 300)
+    K.colsum(cu(x), cg, 300)
+    assert err(cg, cr) < 1e-4
+
+
+def test_greedy_select_state_machine(K, Hk):
+    """Scripted score sequences that trigger <end>, and the 1/2/3-token repetition clean-up (G/models.py:418-435)."""
+    B, Wd, Tmax, V, E = 6, 40, 12, 30, 6
+    scripts = [[5, 5, 5, 5, 7, 29], [1, 2, 1, 2, 1, 2, 9], [1, 2, 3, 1, 2, 3, 1, 2, 3, 4], [31, 37, 31, 37, 3, 29],
+               [8, 8, 9, 9, 9, 8, 8, 29], [29]]
+    state = {}
+    for name, dev in (("r", "cpu"), ("g", DEV)):
+        state[name] = dict(output=torch.zeros(B, Tmax, dtype=torch.int64, device=dev), second=torch.zeros(B, Tmax, dtype=torch.int32, device=dev),
+                           captions=torch.full((B, Tmax), 28, dtype=torch.int64, device=dev), masks=torch.zeros(B, Tmax, dtype=torch.int64, device=dev),
+                           done=torch.zeros(B, dtype=torch.int32, device=dev), margins=torch.zeros(B, Tmax, device=dev))
+    for step in range(Tmax):
+        sc = rnd((B, Wd), torch.float32, 100 + step)
+        for b, s in enumerate(scripts):
+            tok = s[step] if step < len(s) else 29
+            sc[b, tok] = 50.0
+            sc[b, (tok + 3) % Wd] = 40.0
+        for name, kern in (("r", Hk), ("g", K)):
+            st = state[name]
+            kern.greedy_select(sc.to(st["output"].device), Wd, st["output"], st["second"], st["captions"], st["masks"], st["done"], st["margins"], B,
+                               step, Tmax, V, E, True, 29)
+    for k in ("output", "captions", "masks", "done"):
+        assert torch.equal(state["g"][k].cpu(), state["r"][k]), k
+    assert int(state["r"]["done"].sum()) == B

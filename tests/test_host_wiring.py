@@ -1,0 +1,126 @@
+"""
+CPU: the host-side orchestration (engine forward + hand-written backward chain, packing plan and gradient index maps,
+module sort/autograd/flat-parameter plumbing, greedy-decode loop) run over tests/hostsim.py and compared with the
+oracle and the golden vectors.  No CUDA kernel runs here; the `-m gpu` tests repeat these checks on the real kernels.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import batch_args, build_module, load_golden, module_cls, nmax_err, oracle_drop_fn, oracle_params, spec_for
+from hostsim import HostKernels
+from ickb200 import models as M, synthetic as syn
+from oracle import decoder_oracle as orc
+
+
+@pytest.fixture(autouse=True)
+def host_kernels():
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    yield
+    M.DecoderTransformer._test_kernel_factory = None
+
+
+def test_product_refuses_cpu_without_seam():
+    M.DecoderTransformer._test_kernel_factory = None
+    cfg = syn.SMALL_CONFIGS["G"]
+    dec = build_module(cfg, "cpu")
+    batch = syn.make_batch(cfg, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        dec(*batch_args(cfg, batch))
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_state_dict_keys_match_reference(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    dec = build_module(cfg, "cpu")
+    g = load_golden(variant)
+    ref_keys = {k[len("gnorm_"):] for k in g if k.startswith("gnorm_")}
+    assert {k for k, _ in dec.named_parameters()} == ref_keys
+    sd = dec.state_dict()
+    assert "pos_encoder.pe" in sd and tuple(sd["pos_encoder.pe"].shape) == (5000, 1, cfg.D)
+    if variant != "G":
+        assert sd["fact_encoder.predicate_embedding.weight"].data_ptr() == sd["predicate_embedding.weight"].data_ptr()
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_forward_backward_vs_golden(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    dec = build_module(cfg, "cpu").eval()
+    batch = syn.make_batch(cfg, seed=1)
+    batch["encoder_out"].requires_grad_(True)
+    scores, caps, dl = dec(*batch_args(cfg, batch))
+    assert np.array_equal(caps.numpy(), g["captions_sorted"]) and dl == g["decode_lengths"].tolist()
+    assert nmax_err(scores.detach(), g["scores"]) < 1e-4
+    loss = orc.caption_loss(scores, caps, dl)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4
+    loss.backward()
+    assert nmax_err(batch["encoder_out"].grad, g["grad_encoder_out"]) < 1e-3
+    for k, p in dec.named_parameters():
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        ref_norm = float(g[f"gnorm_{k}"])
+        assert abs(float(gr.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6), k
+        if f"grad_{k}" in g and ref_norm > 1e-12:
+            assert nmax_err(gr, g[f"grad_{k}"]) < 2e-3, k
+
+
+@pytest.mark.parametrize("variant", ["G", "K"])
+def test_train_mode_dropout_matches_oracle_with_injected_masks(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    ps = dict(dec=0.3, enc=0.4, pos=0.1)
+    dec = build_module(cfg, "cpu", dropouts=(ps["dec"], ps["enc"], ps["pos"])).train()
+    batch = syn.make_batch(cfg, seed=3)
+    scores, caps, dl = dec(*batch_args(cfg, batch))
+    seed = (int(torch.initial_seed()) * 1000003 + dec._step) & 0x7FFFFFFF
+    p = oracle_params(cfg, requires_grad=True)
+    ref_scores, _, _ = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch), drop=oracle_drop_fn(seed, ps))
+    assert nmax_err(scores.detach(), ref_scores.detach()) < 1e-4
+    orc.caption_loss(scores, caps, dl).backward()
+    orc.caption_loss(ref_scores, caps, dl).backward()
+    for k, prm in dec.named_parameters():
+        ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
+        got = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        assert float((got - ref).abs().max()) <= 2e-3 * max(float(ref.abs().max()), 1e-6) + 1e-7, k
+
+
+def test_fused_loss_matches_train_py_loss():
+    cfg = syn.SMALL_CONFIGS["K"]
+    dec = build_module(cfg, "cpu").eval()
+    batch = syn.make_batch(cfg, seed=1, equal_lengths=False)
+    with torch.no_grad():
+        scores, caps, dl = dec(*batch_args(cfg, batch))
+    eng = dec._engine
+    acc, ds = eng.loss(scores, caps, torch.tensor(dl, dtype=torch.int32))
+    ref = orc.caption_loss(scores, caps, dl)
+    assert abs(float(acc[0] / acc[1]) - float(ref)) < 1e-5
+    s = scores.clone().requires_grad_(True)
+    orc.caption_loss(s, caps, dl).backward()
+    W = scores.shape[-1]
+    assert nmax_err(ds[:, :W].view_as(s) / acc[1], s.grad) < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_predict_tokens_vs_golden(variant):
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    dec = build_module(cfg, "cpu").eval()
+    pb = syn.make_batch(cfg, seed=int(g["predict_seed"]))
+    T = int(g["predict_max_len"])
+    out = dec.predict_batch(pb["encoder_out"], T, pb["entities"], pb.get("facts"))
+    assert out.tolist() == g["predict_tokens"].tolist()
+    one = dec.predict(pb["encoder_out"][:1], T, pb["entities"][:1], pb["facts"][:1] if cfg.has_facts else None)
+    assert tuple(one.shape) == (T, 1) and one.reshape(-1).tolist() == g["predict_tokens"][0].tolist()
+
+
+def test_module_pickles_like_reference_checkpoints(tmp_path):
+    cfg = syn.SMALL_CONFIGS["G"]
+    dec = build_module(cfg, "cpu").eval()
+    batch = syn.make_batch(cfg, seed=1)
+    with torch.no_grad():
+        s0, _, _ = dec(*batch_args(cfg, batch))
+    path = tmp_path / "ckpt.pth.tar"
+    torch.save({"decoder": dec}, path)  # G/utils.py:32-46 pickles whole modules
+    dec2 = torch.load(path, weights_only=False)["decoder"]
+    with torch.no_grad():
+        s1, _, _ = dec2(*batch_args(cfg, batch))
+    assert torch.equal(s0, s1)

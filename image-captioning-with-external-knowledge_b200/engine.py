@@ -339,12 +339,13 @@ class DecoderEngine:
                           V + E, lag)
 
     # ---- loss ------------------------------------------------------------------------------------------------------------------------
-    def loss(self, scores, captions_sorted, decode_len_dev, want_grad: bool = True):
+    def loss(self, scores, captions_sorted, decode_len_dev, want_grad: bool = True, loss_acc=None):
         """pack_padded_sequence + CrossEntropyLoss(ignore_index=pad) (G/train.py:275-281) fused with its gradient.
         Returns (loss_acc = [sum of row losses, kept rows] fp32 on device, dscores (B*T, ldW) activation dtype, UNSCALED)."""
         B, T, W = scores.shape
         ldW = (W + 7) // 8 * 8
-        loss_acc = torch.zeros(2, dtype=torch.float32, device=self.device)
+        if loss_acc is None:
+            loss_acc = torch.zeros(2, dtype=torch.float32, device=self.device)
         ds = self._new(B * T, ldW) if want_grad else None
         self.K.ce(scores.view(B * T, W), captions_sorted, decode_len_dev, loss_acc, ds, B, T, W, self.pad)
         return loss_acc, ds

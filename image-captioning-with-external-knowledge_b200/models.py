@@ -254,7 +254,9 @@ class DecoderTransformer(nn.Module):
 
     # ---- reference API --------------------------------------------------------------------------------------------------------------
     def _sorted_inputs(self, dev, captions, encoder_out, caption_masks, caption_lengths, entities, facts):
-        lengths, sort_ind = caption_lengths.to(dev).squeeze(1).sort(dim=0, descending=True)  # G/models.py:330
+        # G/models.py:330.  stable=True: the reference's tie order is whatever torch.sort yields on its device; the CPU order
+        # (which the golden vectors record) is the stable one, and CUDA's unstable sort would permute equal-length captions.
+        lengths, sort_ind = caption_lengths.to(dev).squeeze(1).sort(dim=0, descending=True, stable=True)
         inp = NS()
         inp.captions = captions.to(dev)[sort_ind].contiguous()
         inp.caption_masks = caption_masks.to(dev)[sort_ind].contiguous()

@@ -348,7 +348,7 @@ def forward(
     sorted by decreasing length, decode_lengths).
     """
     H, L, D = spec.num_heads, spec.num_layers, spec.emb_dim
-    lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
+    lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True, stable=True)
     encoder_out = encoder_out[sort_ind]
     captions = captions[sort_ind]
     caption_masks = caption_masks[sort_ind]

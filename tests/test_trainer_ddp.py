@@ -1,0 +1,107 @@
+"""
+CPU: the fused train step (trainer.Trainer) over the host simulation:
+  * one step equals the reference recipe  loss.backward(); clip_gradient(+-5); Adam.step()  done with torch on the oracle,
+  * two gloo ranks, each with half of the batch, end with the same parameters as one process with the whole batch
+    (gradient all-reduce before the clamp, normalisation by the global kept-token count — SURVEY.md §8e).
+"""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import batch_args, build_module, oracle_params, spec_for
+from hostsim import HostKernels
+from ickb200 import models as M, synthetic as syn
+from ickb200.trainer import Trainer
+from oracle import decoder_oracle as orc
+
+
+def _trainer_step(cfg, batch, steps=2, distributed=False, pg=None):
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu", dropouts=(0.0, 0.0, 0.0)).train()
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, process_group=pg)
+    accs = []
+    for _ in range(steps):
+        accs.append(tr.train_step(*batch_args(cfg, batch)).clone())
+    return dec, accs, tr
+
+
+def test_fused_step_equals_reference_recipe():
+    cfg = syn.SMALL_CONFIGS["K"]
+    batch = syn.make_batch(cfg, seed=4, equal_lengths=False)
+    dec, accs, tr = _trainer_step(cfg, batch, steps=2)
+    # reference recipe on the oracle: G/train.py:275-292 with ut.clip_gradient (G/utils.py:75-85)
+    p = oracle_params(cfg, requires_grad=True)
+    names = [k for k in p if k != "pos_encoder.pe"]
+    opt = torch.optim.Adam([p[k] for k in names], lr=4e-4)
+    losses = []
+    for _ in range(2):
+        scores, caps, dl = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch))
+        loss = orc.caption_loss(scores, caps, dl)
+        opt.zero_grad()
+        loss.backward()
+        for k in names:
+            if p[k].grad is not None:
+                p[k].grad.data.clamp_(-5.0, 5.0)
+        opt.step()
+        losses.append(float(loss))
+    for a, l in zip(accs, losses):
+        assert abs(float(a[0] / a[1]) - l) < 1e-4
+    eng = dec._engine
+    for k, prm in dec.named_parameters():
+        ref = p[k].detach()
+        # Adam normalises by sqrt(v): where |g| ~ eps the update direction is fp32 noise, so the weights are compared at a
+        # fraction of the 2*lr total step, and the first/second moments (linear/quadratic in g) are compared tightly.
+        st = opt.state[p[k]]
+        m_ref, v_ref = st["exp_avg"], st["exp_avg_sq"]
+        d = (prm.detach() - ref).abs()
+        sig = v_ref.sqrt() > 1e-3 * max(float(v_ref.sqrt().max()), 1e-12)  # e.g. the key bias has an exactly-zero true gradient
+        assert float(d.max()) < 1e-3, k
+        if bool(sig.any()):
+            assert float((d[sig] < 2e-5).float().mean()) > 0.98, k
+        assert float((eng.param(k, tr.m) - m_ref).abs().max()) <= 2e-3 * float(m_ref.abs().max()) + 1e-9, k
+        assert float((eng.param(k, tr.v) - v_ref).abs().max()) <= 4e-3 * float(v_ref.abs().max()) + 1e-12, k
+    # the packed operand copies follow the master weights after the fused step
+    lin = eng.lin["fc_vocab"]
+    assert torch.allclose(lin.W[:, : cfg.D], dec._get("fc_vocab.weight").detach(), atol=0)
+
+
+def _worker(rank, world, port, cfg, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    full = syn.make_batch(cfg, seed=4, equal_lengths=False)
+    n = cfg.B // world
+    shard = {k: v[rank * n : (rank + 1) * n] for k, v in full.items()}
+    dec, accs, _ = _trainer_step(cfg.with_batch(n), shard, steps=2, distributed=True)
+    if rank == 0:
+        q.put(({k: v.detach().numpy().copy() for k, v in dec.named_parameters()}, [a.tolist() for a in accs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_equals_single_process():
+    cfg = syn.SMALL_CONFIGS["K"].with_batch(4)
+    full = syn.make_batch(cfg, seed=4, equal_lengths=False)
+    dec1, accs1, _ = _trainer_step(cfg, full, steps=2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    params2, accs2 = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    for a1, a2 in zip(accs1, accs2):
+        assert abs(float(a1[1]) - a2[1]) == 0 and abs(float(a1[0]) - a2[0]) < 1e-3 * abs(a2[0])
+    n_close = n_all = 0
+    for k, prm in dec1.named_parameters():
+        d = (prm.detach() - torch.from_numpy(params2[k])).abs()
+        assert float(d.max()) < 1e-3, k  # never more than the 2*lr two Adam steps can move a weight
+        n_close += int((d < 2e-5).sum())
+        n_all += d.numel()
+    assert n_close > 0.999 * n_all  # all but noise-gradient elements agree to fp32 summation order

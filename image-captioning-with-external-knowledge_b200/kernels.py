@@ -53,13 +53,23 @@ class CudaKernels:
         self.lib = _lib.get()
         # ICKB200_NO_TC=1 routes bf16 GEMMs through the CUDA-core kernels (bring-up / bisecting aid)
         self.use_tc = use_tensor_cores and os.environ.get("ICKB200_NO_TC") != "1"
+        # bench.py sets prof = [] to bracket every launch with CUDA events on the launching stream and to record the
+        # ALGORITHMIC work of the launch (bytes, flops) for the roofline line; None = no instrumentation.
+        self.prof = None
 
     # ------------------------------------------------------------------------------------------------------------
     def _s(self) -> int:
         return torch.cuda.current_stream().cuda_stream
 
-    def _call(self, name, *args, n=1):
-        self.lib.call(name, *args, self._s())
+    def _call(self, name, *args, n=1, work=None):
+        if self.prof is None:
+            self.lib.call(name, *args, self._s())
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.lib.call(name, *args, self._s())
+            e1.record()
+            self.prof.append((name, e0, e1, work() if work is not None else (0, 0)))
         self.lib.launches += n - 1
 
     # ---- dense ---------------------------------------------------------------------------------------------------
@@ -71,12 +81,14 @@ class CudaKernels:
         p, seed, site = _drop(drop)
         tc = (self.use_tc and not force_simt and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
               and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0 and (aux is None or C.dtype == torch.bfloat16))
+        work = lambda: ((M * K) * A.element_size() + (N * K) * W.element_size() + M * N * C.element_size() * (2 if accumulate else 1),  # noqa: E731
+                        2 * M * N * K)
         if tc:
             self._call("ick_gemm_tn_tc", _p(A), _p(W), _p(C), dt_of(C), _p(bias), _p(aux), M, N, K, _ld(A), _ld(W), _ld(C),
-                       _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site)
+                       _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site, work=work)
         else:
             self._call("ick_gemm_tn_simt", _p(A), dt_of(A), _p(W), dt_of(W), _p(C), dt_of(C), _p(bias), _p(aux), M, N, K,
-                       _ld(A), _ld(W), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site)
+                       _ld(A), _ld(W), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site, work=work)
 
     def wgrad(self, dY, X, gflat, rowoff, colmap=None, biasoff=None, force_simt=False):
         """gflat[rowoff[n] + colmap[k]] += sum_m dY[m,n] X[m,k];  gflat[biasoff[n]] += sum_m dY[m,n]."""
@@ -85,23 +97,28 @@ class CudaKernels:
         assert X.shape[0] == M and rowoff.numel() >= N and (colmap is None or colmap.numel() >= K)
         tc = (self.use_tc and not force_simt and dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16
               and dY.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0)
+        work = lambda: ((M * N) * dY.element_size() + (M * K) * X.element_size() + N * K * 4, 2 * M * N * K)  # noqa: E731
         if tc:
             self._call("ick_wgrad_tc", _p(dY), _p(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N, K, _ld(dY), _ld(X),
-                       n=2 if biasoff is not None else 1)
+                       n=2 if biasoff is not None else 1, work=work)
         else:
             self._call("ick_wgrad_simt", _p(dY), dt_of(dY), _p(X), dt_of(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N,
-                       K, _ld(dY), _ld(X))
+                       K, _ld(dY), _ld(X), work=work)
 
     # ---- attention -------------------------------------------------------------------------------------------------
     def mha_fwd(self, Q, K, V, O, lse, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
         p, seed, site = _drop(drop)
+        c = 0.5 if causal else 1.0
         self._call("ick_mha_fwd", _p(Q), _p(K), _p(V), _p(O), _p(lse), dt_of(Q), B, H, Sq, Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
-                   int(causal), p, seed, site)
+                   int(causal), p, seed, site,
+                   work=lambda: (B * H * dh * (2 * Sq + 2 * Sk) * Q.element_size() + B * H * Sq * 4, int(4 * B * H * Sq * Sk * dh * c)))
 
     def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
         p, seed, site = _drop(drop)
         self._call("ick_mha_bwd", _p(Q), _p(K), _p(V), _p(O), _p(dO), _p(lse), _p(dsum), _p(dQ), _p(dK), _p(dV), dt_of(Q), B, H, Sq,
-                   Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, n=2)
+                   Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, n=2,
+                   work=lambda: (B * H * dh * (4 * Sq + 4 * Sk) * Q.element_size() + 2 * B * H * Sq * 4,
+                                 int(10 * B * H * Sq * Sk * dh * (0.5 if causal else 1.0))))
 
     def mha_decode(self, Q, K, V, O, B, H, dh, kbatch_stride, vbatch_stride, klen):
         self._call("ick_mha_decode", _p(Q), _p(K), _p(V), _p(O), dt_of(Q), B, H, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
@@ -112,14 +129,16 @@ class CudaKernels:
         rows = sub.shape[0]
         p, seed, site = _drop(drop)
         self._call("ick_add_ln_fwd", _p(x), _p(sub), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), dt_of(sub), rows, d,
-                   _ld(x) if x is not None else 0, _ld(sub), _ld(y), eps, rowmap[0], rowmap[1], rowmap[2], p, seed, site)
+                   _ld(x) if x is not None else 0, _ld(sub), _ld(y), eps, rowmap[0], rowmap[1], rowmap[2], p, seed, site,
+                   work=lambda: (rows * d * sub.element_size() * (4 if x is not None else 3), 0))
 
     def add_ln_bwd(self, dy, s, mean, rstd, gamma, dres, dsub, dgamma, dbeta, d, rowmap=(0, 0, 0), acc_res=False, drop: Drop = None):
         rows = s.shape[0]
         p, seed, site = _drop(drop)
         self._call("ick_add_ln_bwd", _p(dy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dsub), _p(dgamma), _p(dbeta),
                    dt_of(s), rows, d, _ld(dy), _ld(s), _ld(dres) if dres is not None else 0, _ld(dsub) if dsub is not None else 0,
-                   rowmap[0], rowmap[1], rowmap[2], int(acc_res), p, seed, site)
+                   rowmap[0], rowmap[1], rowmap[2], int(acc_res), p, seed, site,
+                   work=lambda: (rows * d * s.element_size() * (4 + (1 if acc_res else 0)), 0))
 
     # ---- context preparation ------------------------------------------------------------------------------------------
     def entity_encode_fwd(self, entities, facts, type_emb, word_emb, out, variant, B, E, F, D, ntypes, V):
@@ -181,12 +200,14 @@ class CudaKernels:
     # ---- loss / optimizer / misc ---------------------------------------------------------------------------------------------
     def ce(self, scores, captions_sorted, decode_len, loss_acc, dscores, B, T, W, pad):
         self._call("ick_ce_fwd_bwd", _p(scores), _p(captions_sorted), _p(decode_len), _p(loss_acc), _p(dscores),
-                   dt_of(dscores) if dscores is not None else F32, B, T, W, _ld(scores), _ld(dscores) if dscores is not None else W, pad)
+                   dt_of(dscores) if dscores is not None else F32, B, T, W, _ld(scores), _ld(dscores) if dscores is not None else W, pad,
+                   work=lambda: (B * T * W * (4 + (dscores.element_size() if dscores is not None else 0)), 0))
 
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2, clip, count, grad_scale, dstA, dstB, dstC, packT, packF,
                   update=True):
         self._call("ick_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, bc1, bc2, clip, _p(count),
-                   grad_scale, _p(dstA), _p(dstB), _p(dstC), _p(packT), dt_of(packT), _p(packF), int(update))
+                   grad_scale, _p(dstA), _p(dstB), _p(dstC), _p(packT), dt_of(packT), _p(packF), int(update),
+                   work=lambda: (p.numel() * (4 * (7 if update else 1) + 12 + 2 * packT.element_size()), 0))
 
     def cast2d(self, src, dst, cols):
         rows = src.shape[0]

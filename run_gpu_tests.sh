@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/r1_gpu.txt 2>&1
-(timeout 1200 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -k "not True" --timeout 600 2>&1 | tail -80) > gpurun_out/r1_kernels_simt.log
-(timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -k "True" --timeout 300 2>&1 | tail -80) > gpurun_out/r1_kernels_tc.log
-(ICKB200_NO_TC=1 timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q --tb=short --timeout 600 2>&1 | tail -80) > gpurun_out/r1_model_notc.log
-(timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q --tb=short --timeout 600 2>&1 | tail -80) > gpurun_out/r1_model_tc.log
-(timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -20) > gpurun_out/r1_smoke.log
-tail -5 gpurun_out/r1_*.log
+(timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -k "wgrad" --timeout 300 2>&1 | tail -15) > gpurun_out/r2_wgrad.log
+(timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q --tb=short --timeout 600 2>&1 | tail -60) > gpurun_out/r2_model_tc.log
+(timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -4) > gpurun_out/r2_smoke.log
+(timeout 900 python bench.py --steps 5 --warmup 3 2> gpurun_out/r2_bench.err | tail -2) > gpurun_out/r2_bench.json
+tail -c 3000 gpurun_out/r2_bench.err > gpurun_out/r2_bench.err.tail; rm -f gpurun_out/r2_bench.err
+(timeout 600 python bench.py --steps 3 --warmup 3 --dtype fp32 --no-cpu-baseline 2>&1 | tail -2) > gpurun_out/r2_bench_fp32.json
+for f in gpurun_out/r2_*; do echo "### $f"; tail -n 6 $f | cut -c1-600; done

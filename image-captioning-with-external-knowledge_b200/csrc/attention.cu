@@ -8,6 +8,9 @@
 // operand streams through shared memory in tiles and is read as warp-wide broadcasts; the softmax is online
 // (running max / sum in the exp2 domain) so the score matrix never exists in memory.  Attention-probability dropout
 // (torch applies it after the softmax) is regenerated from the counter hash in the backward pass.
+#include <cstdlib>
+
+#include "attention_internal.h"
 #include "common.cuh"
 #include "ickb200.h"
 
@@ -322,6 +325,16 @@ __global__ void __launch_bounds__(128) mha_decode_kernel(const T* __restrict__ Q
     }
 }
 
+// bf16 runs on the tensor-core kernels (attention_mma.cu); ICKB200_ATTN_SIMT=1 forces the CUDA-core kernels (A/B testing)
+bool use_mma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICKB200_ATTN_SIMT");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int check_dims(const char* what, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo) {
     ICK_REQUIRE(B > 0 && H > 0 && Sq > 0 && Sk > 0, "%s: bad sizes B=%d H=%d Sq=%d Sk=%d", what, B, H, Sq, Sk);
     ICK_REQUIRE(dh > 0 && dh <= HD, "%s: head_dim %d not in (0, 32]", what, dh);
@@ -351,6 +364,7 @@ extern "C" int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O,
     AttnDims d = make_dims(B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal);
     DropCfg dc = make_drop(drop_p, seed, site);
     dim3 grid((Sq + NT - 1) / NT, H, B);
+    if (dt == ICK_BF16 && use_mma()) return ick_mha_fwd_mma(Q, K, V, O, lse, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal, dc, stream);
     if (dt == ICK_F32)
         mha_fwd_kernel<float><<<grid, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (float*)O, lse, d, dc);
     else if (dt == ICK_BF16)
@@ -373,6 +387,9 @@ extern "C" int ick_mha_bwd(const void* Q, const void* K, const void* V, const vo
     AttnDims d = make_dims(B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal);
     DropCfg dc = make_drop(drop_p, seed, site);
     dim3 gq((Sq + NT - 1) / NT, H, B), gk((Sk + NT - 1) / NT, H, B);
+    if (dt == ICK_BF16 && use_mma())
+        return ick_mha_bwd_mma(Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, causal, dc,
+                               stream);
     if (dt == ICK_F32) {
         mha_bwd_dq_kernel<float><<<gq, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (const float*)O,
                                                         (const float*)dO, lse, dsum, (float*)dQ, d, lddo, lddq, dc);

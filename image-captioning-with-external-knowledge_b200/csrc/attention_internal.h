@@ -1,0 +1,10 @@
+// Internal (non-ABI) entry points shared between attention.cu (C-ABI dispatch, CUDA-core kernels) and
+// attention_mma.cu (bf16 tensor-core kernels).
+#pragma once
+#include "common.cuh"
+
+int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk,
+                    int ldv, int ldo, int causal, DropCfg dc, cudaStream_t stream);
+int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
+                    void* dK, void* dV, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk,
+                    int lddv, int causal, DropCfg dc, cudaStream_t stream);

@@ -406,16 +406,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     teardown(warp, tmem_base);
 }
 
-// bias gradient: gflat[biasoff[n]] += sum_m dY[m,n]
+// bias gradient: gflat[biasoff[n]] += sum_m dY[m,n].  HBM-bound column sum: a CTA covers 128 columns x `rpb` rows,
+// 64 threads x bf16x2 per row (128 contiguous bytes per warp-pair) and 4 row groups reduced through shared memory.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dY, float* __restrict__ G, const int* __restrict__ biasoff,
-                                                        int M, int N, int ldy, int rows_per_block) {
-    const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const int bo = biasoff[n];
-        if (bo < 0) continue;
-        float sum = 0.f;
-        for (int r = r0; r < r1; ++r) sum += __bfloat162float(dY[(size_t)r * ldy + n]);
-        atomicAdd(G + bo, sum);
+                                                        int M, int N, int ldy, int rpb) {
+    __shared__ float red[4][128];
+    const int tx = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = blockIdx.x * 128 + 2 * tx;
+    const int r0 = blockIdx.y * rpb, r1 = min(M, r0 + rpb);
+    float s0 = 0.f, s1 = 0.f;
+    if (c + 1 < N) {
+#pragma unroll 4
+        for (int r = r0 + rg; r < r1; r += 4) {
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dY + (size_t)r * ldy + c));
+            s0 += v.x;
+            s1 += v.y;
+        }
+    } else if (c < N) {
+        for (int r = r0 + rg; r < r1; r += 4) s0 += __bfloat162float(dY[(size_t)r * ldy + c]);
+    }
+    red[rg][2 * tx] = s0;
+    red[rg][2 * tx + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < N) {
+            const int bo = biasoff[cc];
+            if (bo >= 0) atomicAdd(G + bo, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+        }
     }
 }
 
@@ -557,8 +575,9 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     wgrad_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmY, tmX, p);
     if ((rc = ick_check_launch("wgrad_tc"))) return rc;
     if (biasoff) {
-        const int rpb = 128;
-        bias_grad_kernel<<<(M + rpb - 1) / rpb, 256, 0, stream>>>((const bf16*)dY, gflat, biasoff, M, N, ldy, rpb);
+        const int rpb = 256;
+        dim3 bgrid((N + 127) / 128, (M + rpb - 1) / rpb);
+        bias_grad_kernel<<<bgrid, 256, 0, stream>>>((const bf16*)dY, gflat, biasoff, M, N, ldy, rpb);
         return ick_check_launch("bias_grad");
     }
     return ICK_OK;

@@ -1,14 +1,19 @@
 // bf16 GEMMs on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, operands staged by TMA
-// (cp.async.bulk.tensor, 128B swizzle) through a 4-stage mbarrier ring, persistent CTAs, warp-specialised:
-//   warp 0   TMA producer (one elected lane)
-//   warp 1   TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2-5 epilogue: tcgen05.ld accumulator -> registers -> bias / ReLU+dropout / ReLU-backward / accumulate -> global
-// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring, persistent CTAs, warp-specialised:
+//   warp 0    TMA producer (one elected lane)
+//   warp 1    TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2-9 epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks): tcgen05.ld -> registers ->
+//             bias / ReLU+dropout / ReLU-backward / accumulate -> 16-byte global stores
 //
-//   gemm_tn : C[M,N] (+)= A[M,K] W[N,K]^T (+bias)   both operands K-major          (nn.Linear forward and dgrad)
-//   wgrad   : G[n,k] += sum_m dY[m,n] X[m,k]        both operands MN-major (TMA boxes of the row-major activations
-//             are exactly the canonical MN-major SWIZZLE_128B layout), split over m across CTAs, fp32 atomics into the
-//             flat master-gradient buffer through the packing maps                    (nn.Linear weight/bias gradient)
+//   gemm_tn : C[M,N] (+)= A[M,K] W[N,K]^T (+bias), both operands K-major (nn.Linear forward and dgrad).  The projections
+//             here have K = 320/512, i.e. 5-8 k-blocks per tile, so the kernel is EPILOGUE/HBM-bound: two TMEM accumulator
+//             stages overlap the epilogue of tile i with the main loop of tile i+1, the epilogue keeps everything in
+//             registers (no local memory) and the tile width is chosen per N to avoid padding waste.
+//   wgrad   : G[n,k] += sum_m dY[m,n] X[m,k], both operands MN-major (TMA boxes of the row-major activations are exactly
+//             the canonical MN-major SWIZZLE_128B layout).  One work item = a 128 x K (K <= 512: the whole TMEM width)
+//             output tile over a slice of the rows; partial tiles go to an fp32 workspace with coalesced 16-byte stores
+//             and a second kernel reduces the slices and scatters through the packing maps into the flat gradient
+//             buffer (no atomics).  L2-bound by construction (rows are streamed once per 128-wide n tile).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -17,15 +22,17 @@
 namespace {
 
 constexpr int BM = 128;       // UMMA M (TMEM lanes)
-constexpr int BK = 64;        // K elements per stage = one 128-byte swizzle row of bf16
+constexpr int BK = 64;        // reduction elements per stage = one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int STAGES = 4;
-constexpr int MAX_BN = 256;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_BN = 256;   // widest single tcgen05.mma N
 constexpr int A_STAGE = BM * BK * 2;      // 16 KiB
-constexpr int B_STAGE = MAX_BN * BK * 2;  // 32 KiB
-constexpr int TMEM_COLS = 512;            // 2 accumulator stages x 256 fp32 columns
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int BAR_BYTES = 1024;           // barriers + TMEM base pointer live in the first KiB
+constexpr int SMEM_DATA = 4 * (A_STAGE + MAX_BN * BK * 2);  // 192 KiB of stage buffers
+constexpr int SMEM_BYTES = SMEM_DATA + BAR_BYTES + 1024 /*align slack*/;
+constexpr int NEPI = 8;                   // epilogue warps
+constexpr int NTHREADS = 64 + 32 * NEPI;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,43 +114,39 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-struct SmemLayout {
-    uint8_t* a[STAGES];
-    uint8_t* b[STAGES];
-    uint32_t full[STAGES], empty[STAGES], tfull[2], tempty[2];
+
+// ---- shared-memory carve-up: [barriers (1 KiB)] [stage 0: A | B] [stage 1: A | B] ... ------------------------------------
+struct Smem {
+    uint32_t base;   // shared-space address of the 1024-aligned region
+    uint32_t stage_bytes;
     uint32_t* tmem_ptr;
+    __device__ __forceinline__ uint32_t full(int i) const { return base + 8 * i; }
+    __device__ __forceinline__ uint32_t empty(int i) const { return base + 8 * (MAX_STAGES + i); }
+    __device__ __forceinline__ uint32_t tfull(int i) const { return base + 8 * (2 * MAX_STAGES + i); }
+    __device__ __forceinline__ uint32_t tempty(int i) const { return base + 8 * (2 * MAX_STAGES + 2 + i); }
+    __device__ __forceinline__ uint32_t a(int stage) const { return base + BAR_BYTES + stage * stage_bytes; }
+    __device__ __forceinline__ uint32_t b(int stage) const { return a(stage) + A_STAGE; }
 };
-__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
-    SmemLayout s;
-    uint8_t* base = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-    for (int i = 0; i < STAGES; ++i) {
-        s.a[i] = base + i * A_STAGE;
-        s.b[i] = base + STAGES * A_STAGE + i * B_STAGE;
-    }
-    uint64_t* bars = (uint64_t*)(base + STAGES * (A_STAGE + B_STAGE));
-    for (int i = 0; i < STAGES; ++i) {
-        s.full[i] = smem_u32(bars + i);
-        s.empty[i] = smem_u32(bars + STAGES + i);
-    }
-    for (int i = 0; i < 2; ++i) {
-        s.tfull[i] = smem_u32(bars + 2 * STAGES + i);
-        s.tempty[i] = smem_u32(bars + 2 * STAGES + 2 + i);
-    }
-    s.tmem_ptr = (uint32_t*)(bars + 2 * STAGES + 4);
+__device__ __forceinline__ Smem carve(uint8_t* raw, uint32_t stage_bytes) {
+    uint8_t* p = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    Smem s;
+    s.base = smem_u32(p);
+    s.stage_bytes = stage_bytes;
+    s.tmem_ptr = (uint32_t*)(p + 8 * (2 * MAX_STAGES + 4));
     return s;
 }
 
-__device__ __forceinline__ void setup(const SmemLayout& s, int warp, int lane, const CUtensorMap* t0, const CUtensorMap* t1) {
+__device__ __forceinline__ void setup(const Smem& s, int warp, int lane, const CUtensorMap* t0, const CUtensorMap* t1) {
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(t0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(t1) : "memory");
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(s.full[i], 1);
-            mbar_init(s.empty[i], 1);
+        for (int i = 0; i < MAX_STAGES; ++i) {
+            mbar_init(s.full(i), 1);
+            mbar_init(s.empty(i), 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(s.tfull[i], 1);
-            mbar_init(s.tempty[i], 4);
+            mbar_init(s.tfull(i), 1);
+            mbar_init(s.tempty(i), NEPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -165,18 +168,61 @@ __device__ __forceinline__ void teardown(int warp, uint32_t tmem_base) {
     }
 }
 
+// ---- register-resident epilogue helpers (every index is a compile-time constant after unrolling) ---------------------------
+__device__ __forceinline__ void ld32_f32(const float* p, bool vec, int nv, float* v) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + j));
+            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? __ldg(p + j) : 0.f;
+    }
+}
+__device__ __forceinline__ void ld32_bf16(const bf16* p, bool vec, int nv, float* v) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) ld8(p + j, v + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? __bfloat162float(p[j]) : 0.f;
+    }
+}
+__device__ __forceinline__ void st32_f32(float* p, bool vec, int nv, const float* v) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nv) p[j] = v[j];
+    }
+}
+__device__ __forceinline__ void st32_bf16(bf16* p, bool vec, int nv, const float* v) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st8(p + j, v + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nv) p[j] = __float2bfloat16_rn(v[j]);
+    }
+}
+
 struct TnParams {
     void* C;
     const float* bias;
     const void* aux;
-    int M, N, K, ldc, ldaux, epi, accumulate, c_f32, BN, n_tiles_n, n_tiles, nkb;
+    int M, N, K, ldc, ldaux, epi, accumulate, c_f32, BN, n_tiles_n, n_tiles, nkb, stages;
     DropCfg drop;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW, TnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout s = carve(smem_raw);
+    const Smem s = carve(smem_raw, A_STAGE + p.BN * BK * 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setup(s, warp, lane, &tmA, &tmW);
     const uint32_t tmem_base = *s.tmem_ptr;
@@ -189,11 +235,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const int m_idx = (tile / p.n_tiles_n) * BM, n_idx = (tile % p.n_tiles_n) * p.BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
-                    mbar_wait(s.empty[stage], phase ^ 1);
-                    mbar_expect_tx(s.full[stage], tx);
-                    tma_load_2d(smem_u32(s.a[stage]), &tmA, s.full[stage], kb * BK, m_idx);
-                    tma_load_2d(smem_u32(s.b[stage]), &tmW, s.full[stage], kb * BK, n_idx);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_wait(s.empty(stage), phase ^ 1);
+                    mbar_expect_tx(s.full(stage), tx);
+                    tma_load_2d(s.a(stage), &tmA, s.full(stage), kb * BK, m_idx);
+                    tma_load_2d(s.b(stage), &tmW, s.full(stage), kb * BK, n_idx);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -203,13 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                mbar_wait(s.tempty[acc], acc_phase ^ 1);
+                mbar_wait(s.tempty(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * MAX_BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
-                    mbar_wait(s.full[stage], phase);
+                    mbar_wait(s.full(stage), phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(s.a[stage]), b0 = smem_u32(s.b[stage]);
+                    const uint32_t a0 = s.a(stage), b0 = s.b(stage);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major SWIZZLE_128B: 8-row groups 1024 B apart; a K step of 16 elements = 32 B inside the row
@@ -217,47 +263,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                         const uint64_t bd = make_desc(b0 + k * UMMA_K * 2, 16, 1024);
                         tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
-                    tc_commit(s.empty[stage]);  // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    tc_commit(s.empty(stage));  // frees the smem stage once these MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(s.tfull[acc]);  // accumulator complete
+                tc_commit(s.tfull(acc));  // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int q = warp & 3;           // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;  // which of the two warps of the quadrant: even / odd 32-column chunks
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool c_al = (p.ldc % (p.c_f32 ? 4 : 8) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+        const bool aux_al = p.aux != nullptr && (p.ldaux % 8 == 0) && ((((uintptr_t)p.aux) & 15) == 0);
+        const bool bias_al = p.bias != nullptr && ((((uintptr_t)p.bias) & 15) == 0);
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int m_idx = (tile / p.n_tiles_n) * BM, n_idx = (tile % p.n_tiles_n) * p.BN;
-            mbar_wait(s.tfull[acc], acc_phase);
+            mbar_wait(s.tfull(acc), acc_phase);
             tc_fence_after();
             const int row = m_idx + q * 32 + lane;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BN + c0, r);
                 const int col0 = n_idx + c0;
                 if (row < p.M && col0 < p.N) {
+                    const int nv = min(32, p.N - col0);
+                    const bool full = nv == 32 && (col0 & 7) == 0;
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    const int nv = min(32, p.N - col0);
-                    if (p.bias)
+                    if (p.bias) {
+                        float t[32];
+                        ld32_f32(p.bias + col0, full && bias_al, nv, t);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nv) v[j] += p.bias[col0 + j];
+                        for (int j = 0; j < 32; ++j) v[j] += t[j];
+                    }
                     if (p.accumulate) {
-                        if (p.c_f32) {
-                            const float* cp = (const float*)p.C + (size_t)row * p.ldc + col0;
+                        float t[32];
+                        if (p.c_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
+                        else ld32_bf16((const bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, t);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nv) v[j] += cp[j];
-                        } else {
-                            const bf16* cp = (const bf16*)p.C + (size_t)row * p.ldc + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nv) v[j] += __bfloat162float(cp[j]);
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] += t[j];
                     }
                     if (p.epi == 1) {
 #pragma unroll
@@ -265,33 +312,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                             v[j] = fmaxf(v[j], 0.f) * ick_drop_mul(p.drop.thr, p.drop.inv_keep, p.drop.seed, p.drop.site,
                                                                    (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + j));
                     } else if (p.epi == 2) {
-                        const bf16* ap = (const bf16*)p.aux + (size_t)row * p.ldaux + col0;
+                        float t[32];
+                        ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nv) v[j] = (__bfloat162float(ap[j]) != 0.f) ? v[j] * p.drop.inv_keep : 0.f;
+                        for (int j = 0; j < 32; ++j) v[j] = t[j] != 0.f ? v[j] * p.drop.inv_keep : 0.f;
                     }
-                    if (p.c_f32) {
-                        float* cp = (float*)p.C + (size_t)row * p.ldc + col0;
-                        if (nv == 32 && (((uintptr_t)cp) & 15) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-                            for (int j = 0; j < nv; ++j) cp[j] = v[j];
-                        }
-                    } else {
-                        bf16* cp = (bf16*)p.C + (size_t)row * p.ldc + col0;
-                        if (nv == 32 && (((uintptr_t)cp) & 15) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) st8(cp + j, v + j);
-                        } else {
-                            for (int j = 0; j < nv; ++j) cp[j] = __float2bfloat16_rn(v[j]);
-                        }
-                    }
+                    if (p.c_f32) st32_f32((float*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
+                    else st32_bf16((bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s.tempty[acc]);
+            if (lane == 0) mbar_arrive(s.tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -299,27 +331,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
-// wgrad: D[n (128 lanes), k (BN cols)] = sum over an m-range of dY[m,n] * X[m,k].  TMA boxes are [64 rows of m][64 columns]:
-// in shared memory that is the canonical MN-major SWIZZLE_128B layout (64 contiguous MN elements per 128-byte row, one row
-// per K index), SBO = 1024 B between 8-row K groups, LBO = one whole box (BK*128 B) between 64-wide MN blocks.
+// wgrad: D[n (128 lanes), k (KT <= 512 columns)] = sum over a row slice of dY[m,n] * X[m,k].  TMA boxes are
+// [64 rows of m][64 columns]: in shared memory that is the canonical MN-major SWIZZLE_128B layout (64 contiguous MN
+// elements per 128-byte row, one row per reduction index), SBO = 1024 B between 8-row groups, LBO = one whole box
+// (BK*128 B) between 64-wide MN blocks.  KT > 256 is issued as two tcgen05.mma per k-step (N <= 256 each).
 constexpr int WG_BOX = BK * 128;  // bytes of one [64 x 64] bf16 box
 struct WgParams {
     float* G;
+    float* ws;  // [splits][N][Kws] partial tiles, or nullptr -> atomics straight into G
     const int* rowoff;
     const int* colmap;
-    const int* biasoff;
-    int M, N, K, BN, n_tiles_n, n_tiles_k, splits, m_per_split;
+    int M, N, K, KT, Kws, n_tiles_n, n_tiles_k, splits, m_per_split, stages;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                 const __grid_constant__ CUtensorMap tmX, WgParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const SmemLayout s = carve(smem_raw);
+    const int nbx = p.KT / 64;  // X boxes per stage
+    const Smem s = carve(smem_raw, A_STAGE + nbx * WG_BOX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setup(s, warp, lane, &tmY, &tmX);
     const uint32_t tmem_base = *s.tmem_ptr;
     const int n_work = p.n_tiles_n * p.n_tiles_k * p.splits;
-    const int nbx = p.BN / 64;  // X boxes per stage
 
     if (warp == 0) {
         if (lane == 0) {
@@ -328,65 +361,73 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
             const uint32_t tx = (uint32_t)(2 + nbx) * WG_BOX;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const int split = w % p.splits, t = w / p.splits;
-                const int n_idx = (t / p.n_tiles_k) * BM, k_idx = (t % p.n_tiles_k) * p.BN;
+                const int n_idx = (t / p.n_tiles_k) * BM, k_idx = (t % p.n_tiles_k) * p.KT;
                 const int m0 = split * p.m_per_split, m1 = min(p.M, m0 + p.m_per_split);
                 for (int m = m0; m < m1; m += BK) {
-                    mbar_wait(s.empty[stage], phase ^ 1);
-                    mbar_expect_tx(s.full[stage], tx);
-                    // rows beyond M are zero-filled by TMA; rows in [m1, M) of the last partial block would double count,
-                    // so m_per_split is a multiple of BK (host) and only the global tail is partial.
-                    tma_load_2d(smem_u32(s.a[stage]), &tmY, s.full[stage], n_idx, m);
-                    tma_load_2d(smem_u32(s.a[stage]) + WG_BOX, &tmY, s.full[stage], n_idx + 64, m);
-                    for (int j = 0; j < nbx; ++j) tma_load_2d(smem_u32(s.b[stage]) + j * WG_BOX, &tmX, s.full[stage], k_idx + 64 * j, m);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_wait(s.empty(stage), phase ^ 1);
+                    mbar_expect_tx(s.full(stage), tx);
+                    // m_per_split is a multiple of BK, so only the global tail block is partial (TMA zero-fills rows >= M)
+                    tma_load_2d(s.a(stage), &tmY, s.full(stage), n_idx, m);
+                    tma_load_2d(s.a(stage) + WG_BOX, &tmY, s.full(stage), n_idx + 64, m);
+                    for (int j = 0; j < nbx; ++j) tma_load_2d(s.b(stage) + j * WG_BOX, &tmX, s.full(stage), k_idx + 64 * j, m);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.BN, 1, 1);
-            int stage = 0, acc = 0;
+            const int n1 = p.KT > MAX_BN ? MAX_BN : p.KT, n2 = p.KT - n1;
+            const uint32_t idesc1 = make_idesc(n1, 1, 1), idesc2 = make_idesc(n2 > 0 ? n2 : 16, 1, 1);
+            int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 const int split = w % p.splits;
                 const int m0 = split * p.m_per_split, m1 = min(p.M, m0 + p.m_per_split);
-                mbar_wait(s.tempty[acc], acc_phase ^ 1);
+                mbar_wait(s.tempty(0), acc_phase ^ 1);  // single accumulator stage: wait until the epilogue drained it
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * MAX_BN;
                 int it = 0;
                 for (int m = m0; m < m1; m += BK, ++it) {
-                    mbar_wait(s.full[stage], phase);
+                    mbar_wait(s.full(stage), phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(s.a[stage]), b0 = smem_u32(s.b[stage]);
+                    const uint32_t a0 = s.a(stage), b0 = s.b(stage);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // a K step of 16 = 16 rows of 128 B
+                        // a reduction step of 16 = 16 rows of 128 B
                         const uint64_t ad = make_desc(a0 + k * UMMA_K * 128, WG_BOX, 1024);
-                        const uint64_t bd = make_desc(b0 + k * UMMA_K * 128, WG_BOX, 1024);
-                        tc_mma_bf16(d_tmem, ad, bd, idesc, (it | k) != 0);
+                        tc_mma_bf16(tmem_base, ad, make_desc(b0 + k * UMMA_K * 128, WG_BOX, 1024), idesc1, (it | k) != 0);
+                        if (n2 > 0)
+                            tc_mma_bf16(tmem_base + MAX_BN, ad, make_desc(b0 + 4 * WG_BOX + k * UMMA_K * 128, WG_BOX, 1024), idesc2,
+                                        (it | k) != 0);
                     }
-                    tc_commit(s.empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    tc_commit(s.empty(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(s.tfull[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                tc_commit(s.tfull(0));
+                acc_phase ^= 1;
             }
         }
     } else {
-        const int q = warp & 3;
-        int acc = 0;
+        const int q = warp & 3, half = (warp - 2) >> 2;
         uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            const int t = w / p.splits;
-            const int n_idx = (t / p.n_tiles_k) * BM, k_idx = (t % p.n_tiles_k) * p.BN;
-            mbar_wait(s.tfull[acc], acc_phase);
+            const int split = w % p.splits, t = w / p.splits;
+            const int n_idx = (t / p.n_tiles_k) * BM, k_idx = (t % p.n_tiles_k) * p.KT;
+            mbar_wait(s.tfull(0), acc_phase);
             tc_fence_after();
             const int n = n_idx + q * 32 + lane;
-            const int ro = n < p.N ? p.rowoff[n] : -1;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            const int ro = (n < p.N && p.ws == nullptr) ? p.rowoff[n] : -1;
+            for (int c0 = half * 32; c0 < p.KT; c0 += 64) {
                 uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BN + c0, r);
-                if (ro >= 0) {
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                if (p.ws != nullptr) {
+                    if (n < p.N && k_idx + c0 < p.Kws) {  // Kws is a multiple of 32: whole chunks only
+                        float* dst = p.ws + ((size_t)split * p.N + n) * p.Kws + k_idx + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) =
+                                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    }
+                } else if (ro >= 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int k = k_idx + c0 + j;
@@ -399,11 +440,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(s.tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (lane == 0) mbar_arrive(s.tempty(0));
+            acc_phase ^= 1;
         }
     }
     teardown(warp, tmem_base);
+}
+
+// sum the row-slice partials and scatter into the flat gradient buffer: G[rowoff[n] + colmap[k]] += sum_s ws[s][n][k]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ G, const int* __restrict__ rowoff,
+                                                           const int* __restrict__ colmap, int N, int K, int Kws, int splits) {
+    const int n = blockIdx.y;
+    const int ro = rowoff[n];
+    if (ro < 0) return;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        const int cm = colmap ? colmap[k] : k;
+        if (cm < 0) continue;
+        float acc = 0.f;
+        for (int sp = 0; sp < splits; ++sp) acc += ws[((size_t)sp * N + n) * Kws + k];
+        G[ro + cm] += acc;
+    }
 }
 
 // bias gradient: gflat[biasoff[n]] += sum_m dY[m,n].  HBM-bound column sum: a CTA covers 128 columns x `rpb` rows,
@@ -493,7 +549,7 @@ int num_sms() {
 
 template <typename K>
 int set_smem(K kernel) {
-    static bool done = false;
+    static bool done = false;  // one static per kernel type (template instantiation)
     if (!done) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
             ick_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed", SMEM_BYTES);
@@ -525,6 +581,7 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
     p.n_tiles_n = (N + p.BN - 1) / p.BN;
     p.n_tiles = ((M + BM - 1) / BM) * p.n_tiles_n;
     p.nkb = (K + BK - 1) / BK;
+    p.stages = MAX_STAGES;
     p.drop = make_drop(drop_p, seed, site);
     CUtensorMap tmA, tmW;
     if ((rc = make_tmap(&tmA, A, K, M, lda, BM))) return rc;
@@ -535,7 +592,7 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
 }
 
 extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M,
-                            int N, int K, int ldy, int ldx, cudaStream_t stream) {
+                            int N, int K, int ldy, int ldx, void* workspace, long long workspace_bytes, cudaStream_t stream) {
     ICK_REQUIRE(M >= 0 && N > 0 && K > 0, "wgrad_tc: bad sizes M=%d N=%d K=%d", M, N, K);
     ICK_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0, "wgrad_tc: ldy/ldx must be multiples of 8");
     ICK_REQUIRE((((uintptr_t)dY) & 15) == 0 && (((uintptr_t)X) & 15) == 0, "wgrad_tc: operands must be 16-byte aligned");
@@ -544,29 +601,28 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     int rc = set_smem(wgrad_tc_kernel);
     if (rc) return rc;
     WgParams p;
-    p.G = gflat; p.rowoff = rowoff; p.colmap = colmap; p.biasoff = biasoff;
+    p.G = gflat; p.rowoff = rowoff; p.colmap = colmap;
     p.M = M; p.N = N; p.K = K;
-    // k tile: multiple of 64 (whole TMA boxes), as wide as TMEM allows
-    p.BN = K >= 256 ? 256 : (K + 63) / 64 * 64;
-    {
-        int best = p.BN, best_pad = 1 << 30;
-        for (int bn = 256; bn >= 64; bn -= 64) {
-            const int pad = (K + bn - 1) / bn * bn - K;
-            if (pad < best_pad) { best_pad = pad; best = bn; }
-        }
-        p.BN = best;
-    }
+    const int Kpad = (K + 63) / 64 * 64;
+    p.n_tiles_k = (Kpad + TMEM_COLS - 1) / TMEM_COLS;
+    p.KT = ((Kpad / 64 + p.n_tiles_k - 1) / p.n_tiles_k) * 64;  // even split of the 64-wide boxes over the k tiles, <= 512
     p.n_tiles_n = (N + BM - 1) / BM;
-    p.n_tiles_k = (K + p.BN - 1) / p.BN;
     const int tiles = p.n_tiles_n * p.n_tiles_k;
-    int splits = (2 * num_sms() + tiles - 1) / tiles;
-    const int max_splits = (M + 4 * BK - 1) / (4 * BK);
+    const int stage_bytes = A_STAGE + (p.KT / 64) * WG_BOX;
+    p.stages = SMEM_DATA / stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    ICK_REQUIRE(p.stages >= 2, "wgrad_tc: tile does not fit");
+    int splits = (num_sms() + tiles - 1) / tiles;
+    const int max_splits = (M + 8 * BK - 1) / (8 * BK);  // at least 8 k-blocks per work item
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int mps = (M + splits - 1) / splits;
     mps = (mps + BK - 1) / BK * BK;
     p.splits = (M + mps - 1) / mps;
     p.m_per_split = mps;
+    p.Kws = (K + 31) / 32 * 32;
+    const long long need = (long long)p.splits * N * p.Kws * 4;
+    p.ws = (workspace != nullptr && workspace_bytes >= need && (((uintptr_t)workspace) & 15) == 0) ? (float*)workspace : nullptr;
     CUtensorMap tmY, tmX;
     if ((rc = make_tmap(&tmY, dY, N, M, ldy, BK))) return rc;
     if ((rc = make_tmap(&tmX, X, K, M, ldx, BK))) return rc;
@@ -574,6 +630,11 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     const int grid = n_work < num_sms() ? n_work : num_sms();
     wgrad_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmY, tmX, p);
     if ((rc = ick_check_launch("wgrad_tc"))) return rc;
+    if (p.ws != nullptr) {
+        dim3 rgrid((K + 255) / 256, N);
+        wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, gflat, rowoff, colmap, N, K, p.Kws, p.splits);
+        if ((rc = ick_check_launch("wgrad_reduce"))) return rc;
+    }
     if (biasoff) {
         const int rpb = 256;
         dim3 bgrid((N + 127) / 128, (M + rpb - 1) / rpb);

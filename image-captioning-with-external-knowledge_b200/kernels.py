@@ -56,6 +56,7 @@ class CudaKernels:
         # bench.py sets prof = [] to bracket every launch with CUDA events on the launching stream and to record the
         # ALGORITHMIC work of the launch (bytes, flops) for the roofline line; None = no instrumentation.
         self.prof = None
+        self._ws = None  # fp32 workspace for the split-partials of the tensor-core wgrad
 
     # ------------------------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -99,8 +100,10 @@ class CudaKernels:
               and dY.data_ptr() % 16 == 0 and X.data_ptr() % 16 == 0)
         work = lambda: ((M * N) * dY.element_size() + (M * K) * X.element_size() + N * K * 4, 2 * M * N * K)  # noqa: E731
         if tc:
+            if self._ws is None or self._ws.device != dY.device:
+                self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=dY.device)
             self._call("ick_wgrad_tc", _p(dY), _p(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N, K, _ld(dY), _ld(X),
-                       n=2 if biasoff is not None else 1, work=work)
+                       _p(self._ws), self._ws.numel(), n=3 if biasoff is not None else 2, work=work)
         else:
             self._call("ick_wgrad_simt", _p(dY), dt_of(dY), _p(X), dt_of(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N,
                        K, _ld(dY), _ld(X), work=work)

@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 1
+#define ICK_ABI_VERSION 2
 
 #ifdef __cplusplus
 extern "C" {
@@ -50,8 +50,10 @@ int ick_wgrad_simt(const void* dY, int y_dt, const void* X, int x_dt, float* gfl
 int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float* bias, const void* aux, int M, int N, int K, int lda,
                    int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p, unsigned seed, unsigned site,
                    cudaStream_t stream);
+/* workspace (optional, fp32, >= splits*N*ceil32(K)*4 bytes): row-slice partial tiles are stored there and reduced by a
+ * second kernel; without it the partials are added with fp32 atomics. */
 int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M, int N,
-                 int K, int ldy, int ldx, cudaStream_t stream);
+                 int K, int ldy, int ldx, void* workspace, long long workspace_bytes, cudaStream_t stream);
 
 /* ---- attention: F.multi_head_attention_forward inside the Transformer layers ------------------------------------------ */
 /* O = dropout(softmax(Q K^T / sqrt(dh) [+ causal mask])) V per (batch, head); lse[b,h,i] (log2 domain) is saved for backward.

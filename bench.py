@@ -198,7 +198,7 @@ def run_ours(a):
     if a.batch:
         cfg = cfg.with_batch(a.batch)
     dec = build_decoder(cfg, dev, dtype)
-    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed)
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=(not a.no_graph) and (world == 1 or a.graph))
     K = tr.eng.K
     lib = _lib.get()
     hb = host_batch(cfg, seed=rank, pin=True)
@@ -225,12 +225,19 @@ def run_ours(a):
     # ---- arm 1: inputs resident in HBM ------------------------------------------------------------------------------------
     inp = tr.prepare(*args_of(cfg, hb))
     torch.cuda.synchronize()
+    graph = "on" if tr.use_graph else "off"
+    try:
+        tr.step(inp)  # captures the CUDA graph of the step when enabled
+    except Exception as e:  # e.g. a collective that cannot be captured on this NCCL build: fall back to eager launches
+        if not tr.use_graph:
+            raise
+        sys.stderr.write(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); running eager\n")
+        tr.use_graph, tr._graph, graph = False, None, "capture failed -> off"
+        torch.cuda.synchronize()
     for _ in range(a.warmup):
         tr.step(inp)
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = lib.launches
     ms = timed(lambda: tr.step(inp), a.steps)
-    launches = lib.launches - l0
     clocks = sampler.stop() if sampler else None
     loss_acc = tr.loss_acc.clone()
     value = cfg.B * world * a.steps / (ms / 1e3)
@@ -248,12 +255,16 @@ def run_ours(a):
     # ---- instrumented pass: CUDA events around every launch (same steps, not part of `value`) -----------------------------------
     roof = None
     breakdown = {}
+    # every rank runs these steps (they contain the gradient all-reduce); only rank 0 keeps the per-launch events
+    nprof = min(a.steps, 3)
+    l0 = lib.launches
     if rank == 0:
         K.prof = []
-        nprof = min(a.steps, 3)
-        for _ in range(nprof):
-            tr.step(inp)
-        torch.cuda.synchronize()
+    for _ in range(nprof):
+        tr._step_impl(inp)  # eager launches (events cannot bracket kernels inside a graph replay)
+    sync_all()
+    launches_per_step = (lib.launches - l0) // nprof
+    if rank == 0:
         agg = {}
         for name, e0, e1, work in K.prof:
             t = e0.elapsed_time(e1)
@@ -291,10 +302,12 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_desc(cfg, a.dtype), "global_batch": cfg.B * world, "parallelism": f"dp{world}",
+                       "cuda_graph": graph,
                        "l2": "no explicit flush: each step streams > 4 GB of activations/gradients, far beyond the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
-            "gpu_launches": launches,
+            "gpu_launches": launches_per_step * a.steps,  # our kernels per step (counted on an eager pass) x timed steps
+            "gpu_launches_per_step": launches_per_step,
             "roofline": roof,
             "cpu_baseline": cpu,
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),
@@ -315,6 +328,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="also capture the step (including the NCCL all-reduce) when N > 1")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, co
                                                      AttnDims d, DropCfg drop) {
     __shared__ __align__(16) float Ks[KT][HD];
     __shared__ __align__(16) float Vs[KT][HD];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * NT + threadIdx.x;
     const bool active = i < d.Sq;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
                                                         int lddo, int lddq, DropCfg drop) {
     __shared__ __align__(16) float Ks[KT][HD];
     __shared__ __align__(16) float Vs[KT][HD];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * NT + threadIdx.x;
     const bool active = i < d.Sq;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dkv_kernel(const T* __restrict__ Q
     __shared__ __align__(16) float Qs[QT][HD];
     __shared__ __align__(16) float Gs[QT][HD];
     __shared__ float Ls[QT], Ds[QT];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y;
     const int j = blockIdx.x * NT + threadIdx.x;
     const bool active = j < d.Sk;

@@ -44,6 +44,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ uint32_t lds32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 // rows [r0, r0+64) x 32 columns of a (rows, ld) bf16 matrix -> smem tile; rows >= rmax and columns >= dh are zeroed
+// (synchronous; used for the operand that becomes A fragments, whose pad lanes MUST be zero)
 __device__ __forceinline__ void load_tile(const bf16* __restrict__ base, size_t ld, int r0, int rmax, int dh, bf16 (*dst)[LDS]) {
     for (int idx = threadIdx.x; idx < TK * 4; idx += blockDim.x) {
         const int r = idx >> 2, c = (idx & 3) * 8;
@@ -56,6 +57,24 @@ __device__ __forceinline__ void load_tile(const bf16* __restrict__ base, size_t 
                 if (c + i >= dh) e[i] = __float2bfloat16_rn(0.f);
         }
         *reinterpret_cast<uint4*>(&dst[r][c]) = u;
+    }
+}
+
+// asynchronous variant for the STREAMED operand (cp.async, zero-fill for rows >= rmax).  Its pad lanes only ever meet
+// zero A-fragment lanes or output columns that are masked at the store, so they need no zeroing.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void load_tile_async(const bf16* __restrict__ base, size_t ld, int r0, int rmax, bf16 (*dst)[LDS]) {
+    for (int idx = threadIdx.x; idx < TK * 4; idx += blockDim.x) {
+        const int r = idx >> 2, c = (idx & 3) * 8;
+        const bool ok = r0 + r < rmax;
+        cp_async16((uint32_t)__cvta_generic_to_shared(&dst[r][c]), base + (size_t)(ok ? r0 + r : rmax - 1) * ld + c, ok);
     }
 }
 
@@ -103,10 +122,6 @@ __device__ __forceinline__ void mma_p_t(float (*out)[4], const float (*p)[4], co
     }
 }
 
-__device__ __forceinline__ uint64_t pidx(const Dims& d, int b, int h, int i, int j) {
-    return (((uint64_t)b * d.H + h) * (uint64_t)d.Sq + i) * (uint64_t)d.Sk + j;
-}
-
 // write a 16 x 32 accumulator slab (4 n-tiles) as bf16 rows; columns >= dh are written as zero
 __device__ __forceinline__ void store_slab(bf16* base, size_t ld, int row_g, int row_g8, int rmax, const float (*o)[4], float s0, float s1,
                                            int dh, int tq) {
@@ -119,54 +134,76 @@ __device__ __forceinline__ void store_slab(bf16* base, size_t ld, int row_g, int
     }
 }
 
+// dropout multiplier of probability (row base index + key); the 64-bit row base is computed once per tile row
+__device__ __forceinline__ float drop_at(const DropCfg& drop, uint64_t rowbase, int key) {
+    return ick_hash(drop.seed, drop.site, rowbase + (uint64_t)key) >= drop.thr ? drop.inv_keep : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) fwd_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K, const bf16* __restrict__ V,
                                                   bf16* __restrict__ O, float* __restrict__ LSE, Dims d, DropCfg drop) {
     __shared__ __align__(16) bf16 Qs[TQ][LDS];
-    __shared__ __align__(16) bf16 Ks[TK][LDS];
-    __shared__ __align__(16) bf16 Vs[TK][LDS];
+    __shared__ __align__(16) bf16 Ks[2][TK][LDS];
+    __shared__ __align__(16) bf16 Vs[2][TK][LDS];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const bf16* Qb = Q + (size_t)b * d.Sq * d.ldq + h * HD;
     const bf16* Kb = K + (size_t)b * d.Sk * d.ldk + h * HD;
     const bf16* Vb = V + (size_t)b * d.Sk * d.ldv + h * HD;
+    const int kend = d.causal ? min(d.Sk, q0 + TQ) : d.Sk;
+    const int nt = (kend + TK - 1) / TK;
+    load_tile_async(Kb, d.ldk, 0, d.Sk, Ks[0]);
+    load_tile_async(Vb, d.ldv, 0, d.Sk, Vs[0]);
+    cp_commit();
     load_tile(Qb, d.ldq, q0, d.Sq, d.dh, Qs);
     __syncthreads();
     uint32_t qa[2][4];
     load_a_frags(Qs, 16 * warp, g, tq, qa);
     const int qi0 = q0 + 16 * warp + g, qi1 = qi0 + 8;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const uint64_t rb0 = (((uint64_t)b * d.H + h) * (uint64_t)d.Sq + qi0) * (uint64_t)d.Sk, rb1 = rb0 + 8ull * (uint64_t)d.Sk;
+    const float c = d.scale_log2;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max of the RAW scores, running sum
     float o[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 
-    const int kend = d.causal ? min(d.Sk, q0 + TQ) : d.Sk;
-    for (int k0 = 0; k0 < kend; k0 += TK) {
-        __syncthreads();
-        load_tile(Kb, d.ldk, k0, d.Sk, d.dh, Ks);
-        load_tile(Vb, d.ldv, k0, d.Sk, d.dh, Vs);
-        __syncthreads();
+    for (int it = 0; it < nt; ++it) {
+        const int k0 = it * TK, buf = it & 1;
+        cp_wait_all();
+        __syncthreads();  // tile `it` has landed for everyone, and everyone is done with tile it-1 (buffer buf^1)
+        if (it + 1 < nt) {
+            load_tile_async(Kb, d.ldk, k0 + TK, d.Sk, Ks[buf ^ 1]);
+            load_tile_async(Vb, d.ldv, k0 + TK, d.Sk, Vs[buf ^ 1]);
+            cp_commit();
+        }
         float s[8][4];
-        mma_a_tT(s, qa, Ks, g, tq);
+        mma_a_tT(s, qa, Ks[buf], g, tq);
+        // masking is needed only on the ragged last tile and on tiles that cross this warp's causal diagonal
+        if (k0 + TK > d.Sk || (d.causal && k0 + TK - 1 > q0 + 16 * warp)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = k0 + 8 * j + 2 * tq + (e & 1);
+                    const bool vis = key < d.Sk && (!d.causal || key <= (e < 2 ? qi0 : qi1));
+                    if (!vis) s[j][e] = -INFINITY;
+                }
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = k0 + 8 * j + 2 * tq + (e & 1);
-                const int qi = e < 2 ? qi0 : qi1;
-                const bool vis = key < d.Sk && (!d.causal || key <= qi);
-                s[j][e] = vis ? s[j][e] * d.scale_log2 : -INFINITY;
-                if (e < 2) mx0 = fmaxf(mx0, s[j][e]); else mx1 = fmaxf(mx1, s[j][e]);
-            }
+        for (int j = 0; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
         // a row with no visible key so far keeps m = -inf; use 0 as the exponent base there (all p are exp2(-inf) = 0)
-        const float e0 = mn0 == -INFINITY ? 0.f : mn0, e1 = mn1 == -INFINITY ? 0.f : mn1;
-        const float c0 = exp2f(m0 - e0), c1 = exp2f(m1 - e1);
+        const float e0 = mn0 == -INFINITY ? 0.f : mn0 * c, e1 = mn1 == -INFINITY ? 0.f : mn1 * c;
+        const float c0 = exp2f(m0 * c - e0), c1 = exp2f(m1 * c - e1);
         l0 *= c0;
         l1 *= c1;
 #pragma unroll
@@ -177,15 +214,17 @@ __global__ void __launch_bounds__(128) fwd_kernel(const bf16* __restrict__ Q, co
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float p = exp2f(s[j][e] - (e < 2 ? e0 : e1));
+                const float p = exp2f(fmaf(s[j][e], c, -(e < 2 ? e0 : e1)));
                 if (e < 2) l0 += p; else l1 += p;
-                float mul = 1.f;
-                if (drop.thr != 0u)
-                    mul = ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site,
-                                       pidx(d, b, h, e < 2 ? qi0 : qi1, k0 + 8 * j + 2 * tq + (e & 1)));
-                s[j][e] = p * mul;
+                s[j][e] = p;
             }
-        mma_p_t(o, s, Vs, lane);
+        if (drop.thr != 0u) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[j][e] *= drop_at(drop, e < 2 ? rb0 : rb1, k0 + 8 * j + 2 * tq + (e & 1));
+        }
+        mma_p_t(o, s, Vs[buf], lane);
         m0 = mn0;
         m1 = mn1;
     }
@@ -197,8 +236,8 @@ __global__ void __launch_bounds__(128) fwd_kernel(const bf16* __restrict__ Q, co
     store_slab(Ob, d.ldo, qi0, qi1, d.Sq, o, 1.f / l0, 1.f / l1, d.dh, tq);
     if (tq == 0) {
         float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
-        if (qi0 < d.Sq) L[qi0] = m0 + log2f(l0);
-        if (qi1 < d.Sq) L[qi1] = m1 + log2f(l1);
+        if (qi0 < d.Sq) L[qi0] = m0 * c + log2f(l0);
+        if (qi1 < d.Sq) L[qi1] = m1 * c + log2f(l1);
     }
 }
 
@@ -208,9 +247,10 @@ __global__ void __launch_bounds__(128) bwd_dq_kernel(const bf16* __restrict__ Q,
                                                      float* __restrict__ Dsum, bf16* __restrict__ dQ, Dims d, int lddo, int lddq, DropCfg drop) {
     __shared__ __align__(16) bf16 Qs[TQ][LDS];
     __shared__ __align__(16) bf16 Gs[TQ][LDS];
-    __shared__ __align__(16) bf16 Ks[TK][LDS];
-    __shared__ __align__(16) bf16 Vs[TK][LDS];
+    __shared__ __align__(16) bf16 Ks[2][TK][LDS];
+    __shared__ __align__(16) bf16 Vs[2][TK][LDS];
     __shared__ float Ds[TQ];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const bf16* Qb = Q + (size_t)b * d.Sq * d.ldq + h * HD;
@@ -218,51 +258,64 @@ __global__ void __launch_bounds__(128) bwd_dq_kernel(const bf16* __restrict__ Q,
     const bf16* Vb = V + (size_t)b * d.Sk * d.ldv + h * HD;
     const bf16* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
     const bf16* Ob = O + (size_t)b * d.Sq * d.ldo + h * HD;
+    const int kend = d.causal ? min(d.Sk, q0 + TQ) : d.Sk;
+    const int nt = (kend + TK - 1) / TK;
+    load_tile_async(Kb, d.ldk, 0, d.Sk, Ks[0]);
+    load_tile_async(Vb, d.ldv, 0, d.Sk, Vs[0]);
+    cp_commit();
     load_tile(Qb, d.ldq, q0, d.Sq, d.dh, Qs);
     load_tile(Gb, lddo, q0, d.Sq, d.dh, Gs);
-    load_tile(Ob, d.ldo, q0, d.Sq, d.dh, Ks);  // O staged in the K buffer for the row dot products
+    load_tile(Ob, d.ldo, q0, d.Sq, d.dh, Ks[1]);  // O staged in the second K buffer for the row dot products
     __syncthreads();
     if (threadIdx.x < TQ) {
         float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < HD; ++c) acc = fmaf(__bfloat162float(Gs[threadIdx.x][c]), __bfloat162float(Ks[threadIdx.x][c]), acc);
+        for (int cc = 0; cc < HD; ++cc) acc = fmaf(__bfloat162float(Gs[threadIdx.x][cc]), __bfloat162float(Ks[1][threadIdx.x][cc]), acc);
         Ds[threadIdx.x] = acc;
         if (q0 + threadIdx.x < d.Sq) Dsum[((size_t)b * d.H + h) * d.Sq + q0 + threadIdx.x] = acc;
     }
     uint32_t qa[2][4], ga[2][4];
     load_a_frags(Qs, 16 * warp, g, tq, qa);
     load_a_frags(Gs, 16 * warp, g, tq, ga);
-    __syncthreads();
+    __syncthreads();  // Ds visible; the staged O may be overwritten from here on
     const int qi0 = q0 + 16 * warp + g, qi1 = qi0 + 8;
+    const uint64_t rb0 = (((uint64_t)b * d.H + h) * (uint64_t)d.Sq + qi0) * (uint64_t)d.Sk, rb1 = rb0 + 8ull * (uint64_t)d.Sk;
     const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
     const float lse0 = qi0 < d.Sq ? L[qi0] : 0.f, lse1 = qi1 < d.Sq ? L[qi1] : 0.f;
     const float D0 = Ds[16 * warp + g], D1 = Ds[16 * warp + g + 8];
+    const float c = d.scale_log2;
     float dq[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
 
-    const int kend = d.causal ? min(d.Sk, q0 + TQ) : d.Sk;
-    for (int k0 = 0; k0 < kend; k0 += TK) {
+    for (int it = 0; it < nt; ++it) {
+        const int k0 = it * TK, buf = it & 1;
+        cp_wait_all();
         __syncthreads();
-        load_tile(Kb, d.ldk, k0, d.Sk, d.dh, Ks);
-        load_tile(Vb, d.ldv, k0, d.Sk, d.dh, Vs);
-        __syncthreads();
+        if (it + 1 < nt) {
+            load_tile_async(Kb, d.ldk, k0 + TK, d.Sk, Ks[buf ^ 1]);
+            load_tile_async(Vb, d.ldv, k0 + TK, d.Sk, Vs[buf ^ 1]);
+            cp_commit();
+        }
         float s[8][4], dp[8][4];
-        mma_a_tT(s, qa, Ks, g, tq);
-        mma_a_tT(dp, ga, Vs, g, tq);
+        mma_a_tT(s, qa, Ks[buf], g, tq);
+        mma_a_tT(dp, ga, Vs[buf], g, tq);
+        const bool need_mask = k0 + TK > d.Sk || q0 + TQ > d.Sq || (d.causal && k0 + TK - 1 > q0 + 16 * warp);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int key = k0 + 8 * j + 2 * tq + (e & 1);
-                const int qi = e < 2 ? qi0 : qi1;
-                const bool vis = key < d.Sk && qi < d.Sq && (!d.causal || key <= qi);
-                const float p = vis ? exp2f(s[j][e] * d.scale_log2 - (e < 2 ? lse0 : lse1)) : 0.f;
-                float mul = 1.f;
-                if (drop.thr != 0u) mul = ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, qi, key));
-                s[j][e] = p * (dp[j][e] * mul - (e < 2 ? D0 : D1));
+                float p = exp2f(fmaf(s[j][e], c, -(e < 2 ? lse0 : lse1)));
+                if (need_mask) {
+                    const int qi = e < 2 ? qi0 : qi1;
+                    if (!(key < d.Sk && qi < d.Sq && (!d.causal || key <= qi))) p = 0.f;
+                }
+                float g_ = dp[j][e];
+                if (drop.thr != 0u) g_ *= drop_at(drop, e < 2 ? rb0 : rb1, key);
+                s[j][e] = p * (g_ - (e < 2 ? D0 : D1));
             }
-        mma_p_t(dq, s, Ks, lane);
+        mma_p_t(dq, s, Ks[buf], lane);
     }
     bf16* dQb = dQ + (size_t)b * d.Sq * lddq + h * HD;
     store_slab(dQb, lddq, qi0, qi1, d.Sq, dq, d.scale, d.scale, d.dh, tq);
@@ -275,9 +328,10 @@ __global__ void __launch_bounds__(128) bwd_dkv_kernel(const bf16* __restrict__ Q
                                                       DropCfg drop) {
     __shared__ __align__(16) bf16 Ks[TQ][LDS];
     __shared__ __align__(16) bf16 Vs[TQ][LDS];
-    __shared__ __align__(16) bf16 Qs[TK][LDS];
-    __shared__ __align__(16) bf16 Gs[TK][LDS];
-    __shared__ float Ls[TK], Ds[TK];
+    __shared__ __align__(16) bf16 Qs[2][TK][LDS];
+    __shared__ __align__(16) bf16 Gs[2][TK][LDS];
+    __shared__ float Ls[2][TK], Ds[2][TK];
+    ick_resolve_seed(drop);
     const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const bf16* Qb = Q + (size_t)b * d.Sq * d.ldq + h * HD;
@@ -286,6 +340,22 @@ __global__ void __launch_bounds__(128) bwd_dkv_kernel(const bf16* __restrict__ Q
     const bf16* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
     const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
     const float* Dg = Dsum + ((size_t)b * d.H + h) * d.Sq;
+    // causal: queries before the first key of this CTA see none of its keys
+    const int qbeg = d.causal ? (j0 / TK) * TK : 0;
+    const int nt = (d.Sq - qbeg + TK - 1) / TK;
+
+    auto issue = [&](int q0, int buf) {
+        load_tile_async(Qb, d.ldq, q0, d.Sq, Qs[buf]);
+        load_tile_async(Gb, lddo, q0, d.Sq, Gs[buf]);
+        if (threadIdx.x < TK) {
+            const int i = q0 + threadIdx.x;
+            const bool ok = i < d.Sq;
+            cp_async4((uint32_t)__cvta_generic_to_shared(&Ls[buf][threadIdx.x]), L + (ok ? i : 0), ok);
+            cp_async4((uint32_t)__cvta_generic_to_shared(&Ds[buf][threadIdx.x]), Dg + (ok ? i : 0), ok);
+        }
+        cp_commit();
+    };
+    issue(qbeg, 0);
     load_tile(Kb, d.ldk, j0, d.Sk, d.dh, Ks);
     load_tile(Vb, d.ldv, j0, d.Sk, d.dh, Vs);
     __syncthreads();
@@ -293,27 +363,23 @@ __global__ void __launch_bounds__(128) bwd_dkv_kernel(const bf16* __restrict__ Q
     load_a_frags(Ks, 16 * warp, g, tq, ka);
     load_a_frags(Vs, 16 * warp, g, tq, va);
     const int kj0 = j0 + 16 * warp + g, kj1 = kj0 + 8;
+    const uint64_t hb = ((uint64_t)b * d.H + h) * (uint64_t)d.Sq;
+    const float c = d.scale_log2;
     float dk[4][4], dv[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
         dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
         dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
     }
-    // causal: queries before the first key of this CTA see none of its keys
-    const int qbeg = d.causal ? (j0 / TK) * TK : 0;
-    for (int q0 = qbeg; q0 < d.Sq; q0 += TK) {
+    for (int it = 0; it < nt; ++it) {
+        const int q0 = qbeg + it * TK, buf = it & 1;
+        cp_wait_all();
         __syncthreads();
-        load_tile(Qb, d.ldq, q0, d.Sq, d.dh, Qs);
-        load_tile(Gb, lddo, q0, d.Sq, d.dh, Gs);
-        if (threadIdx.x < TK) {
-            const int i = q0 + threadIdx.x;
-            Ls[threadIdx.x] = i < d.Sq ? L[i] : 0.f;
-            Ds[threadIdx.x] = i < d.Sq ? Dg[i] : 0.f;
-        }
-        __syncthreads();
+        if (it + 1 < nt) issue(q0 + TK, buf ^ 1);
         float st[8][4], dpt[8][4];
-        mma_a_tT(st, ka, Qs, g, tq);
-        mma_a_tT(dpt, va, Gs, g, tq);
+        mma_a_tT(st, ka, Qs[buf], g, tq);
+        mma_a_tT(dpt, va, Gs[buf], g, tq);
+        const bool need_mask = q0 + TK > d.Sq || j0 + TQ > d.Sk || (d.causal && j0 + 16 * warp + 15 > q0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -321,15 +387,17 @@ __global__ void __launch_bounds__(128) bwd_dkv_kernel(const bf16* __restrict__ Q
                 const int qc = 8 * j + 2 * tq + (e & 1);
                 const int qi = q0 + qc;
                 const int key = e < 2 ? kj0 : kj1;
-                const bool vis = key < d.Sk && qi < d.Sq && (!d.causal || key <= qi);
-                const float p = vis ? exp2f(st[j][e] * d.scale_log2 - Ls[qc]) : 0.f;
+                float p = exp2f(fmaf(st[j][e], c, -Ls[buf][qc]));
+                if (need_mask) {
+                    if (!(key < d.Sk && qi < d.Sq && (!d.causal || key <= qi))) p = 0.f;
+                }
                 float mul = 1.f;
-                if (drop.thr != 0u) mul = ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, qi, key));
-                st[j][e] = p * mul;                           // P^T with dropout -> dV
-                dpt[j][e] = p * (dpt[j][e] * mul - Ds[qc]);   // dS^T              -> dK
+                if (drop.thr != 0u) mul = drop_at(drop, (hb + (uint64_t)qi) * (uint64_t)d.Sk, key);
+                st[j][e] = p * mul;                                // P^T with dropout -> dV
+                dpt[j][e] = p * (dpt[j][e] * mul - Ds[buf][qc]);   // dS^T              -> dK
             }
-        mma_p_t(dv, st, Gs, lane);
-        mma_p_t(dk, dpt, Qs, lane);
+        mma_p_t(dv, st, Gs[buf], lane);
+        mma_p_t(dk, dpt, Qs[buf], lane);
     }
     bf16* dKb = dK + (size_t)b * d.Sk * lddk + h * HD;
     bf16* dVb = dV + (size_t)b * d.Sk * lddv + h * HD;

@@ -107,9 +107,17 @@ struct DropCfg {
     float inv_keep;  // 1 / (1 - p)
     uint32_t seed;
     uint32_t site;
+    const uint32_t* seed_dev;  // optional device-resident seed offset (lets a captured CUDA graph draw new masks per replay)
 };
+// host-side registry of the device seed offset (ick_set_seed_source); defined in loss_optim.cu
+const uint32_t* ick_seed_source();
+// kernels call this once on their by-value DropCfg copy
+__device__ __forceinline__ void ick_resolve_seed(DropCfg& d) {
+    if (d.seed_dev != nullptr) d.seed += *d.seed_dev;
+}
 static inline DropCfg make_drop(float p, unsigned seed, unsigned site) {
     DropCfg d;
+    d.seed_dev = ick_seed_source();
     if (p <= 0.f) {
         d.thr = 0u;
         d.inv_keep = 1.f;

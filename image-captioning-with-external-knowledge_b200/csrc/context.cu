@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) caption_embed_fwd_kernel(const long long*
                                                                 const T* __restrict__ factenc, const float* __restrict__ pe,
                                                                 T* __restrict__ out, int B, int Tstride, int t0, int Tn, int V, int E,
                                                                 int F, int D, int ld, int ldw, int pad, float scale, DropCfg drop) {
+    ick_resolve_seed(drop);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * Tn) return;
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restr
                                                                 float* __restrict__ dFact, float* __restrict__ gflat, int word_off,
                                                                 int B, int T_, int V, int E, int F, int D, int ld, int pad, float scale,
                                                                 DropCfg drop) {
+    ick_resolve_seed(drop);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * T_) return;

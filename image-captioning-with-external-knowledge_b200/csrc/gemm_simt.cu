@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, 
                                                       int accumulate, DropCfg drop) {
     __shared__ __align__(16) float As[2][BK][LDS];
     __shared__ __align__(16) float Ws[2][BK][LDS];
+    ick_resolve_seed(drop);
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int lrow = tid & 127, lk = (tid >> 7) * 8;

@@ -222,6 +222,7 @@ struct TnParams {
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW, TnParams p) {
     extern __shared__ uint8_t smem_raw[];
+    ick_resolve_seed(p.drop);
     const Smem s = carve(smem_raw, A_STAGE + p.BN * BK * 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setup(s, warp, lane, &tmA, &tmW);

@@ -73,9 +73,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float bc1, float bc2_sqrt, float clip, const float* __restrict__ count,
                                                    float grad_scale, const int* __restrict__ dstA, const int* __restrict__ dstB,
                                                    const int* __restrict__ dstC, T* __restrict__ packT, float* __restrict__ packF,
-                                                   int update) {
+                                                   int update, const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
     float gs = grad_scale;
     if (count) gs /= fmaxf(count[0], 1.f);
+    if (step_dev) {  // bias corrections from a device-resident step counter (CUDA-graph replay)
+        const float t = (float)step_dev[0];
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
+    if (lr_dev) lr = lr_dev[0];
     const float step = lr / bc1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float pv = p[i];
@@ -219,7 +225,8 @@ extern "C" int ick_ce_fwd_bwd(const float* scores, const long long* captions_sor
 
 extern "C" int ick_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                              float bias_corr1, float bias_corr2, float clip, const float* count, float grad_scale, const int* dstA,
-                             const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, cudaStream_t stream) {
+                             const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, const int* step_dev,
+                             const float* lr_dev, cudaStream_t stream) {
     ICK_REQUIRE(n >= 0, "adam: bad n");
     ICK_REQUIRE(!update || (g && m && v), "adam: update needs g, m, v");
     ICK_REQUIRE((!dstA && !dstB) || packT, "adam: packT missing");
@@ -228,10 +235,10 @@ extern "C" int ick_adam_step(float* p, const float* g, float* m, float* v, long 
     const float bc2s = sqrtf(bias_corr2);
     if (dt == ICK_F32)
         adam_kernel<float><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
-                                                           dstA, dstB, dstC, (float*)packT, packF, update);
+                                                           dstA, dstB, dstC, (float*)packT, packF, update, step_dev, lr_dev);
     else if (dt == ICK_BF16)
         adam_kernel<bf16><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
-                                                          dstA, dstB, dstC, (bf16*)packT, packF, update);
+                                                          dstA, dstB, dstC, (bf16*)packT, packF, update, step_dev, lr_dev);
     else {
         ick_set_error("adam: bad dtype %d", dt);
         return ICK_ERR_UNSUPPORTED;
@@ -312,4 +319,10 @@ int ick_check_launch(const char* what) {
     return ICK_OK;
 }
 extern "C" const char* ick_last_error(void) { return g_err; }
+static const uint32_t* g_seed_source = nullptr;
+const uint32_t* ick_seed_source() { return g_seed_source; }
+extern "C" int ick_set_seed_source(const unsigned* seed_dev) {
+    g_seed_source = seed_dev;
+    return ICK_OK;
+}
 extern "C" int ick_abi_version(void) { return ICK_ABI_VERSION; }

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ X
                                                          T* __restrict__ Y, float* __restrict__ MEAN, float* __restrict__ RSTD,
                                                          int rows, int d, int ldx, int lds, int ldy, float eps, RowMap ymap,
                                                          DropCfg drop) {
+    ick_resolve_seed(drop);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ D
                                                          int lddy, int lds, int ldres, int ldsub, RowMap dymap, int acc_res,
                                                          DropCfg drop) {
     __shared__ float sg[2 * MAXP * 32], sb[2 * MAXP * 32];
+    ick_resolve_seed(drop);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;

@@ -206,10 +206,15 @@ class CudaKernels:
                    dt_of(dscores) if dscores is not None else F32, B, T, W, _ld(scores), _ld(dscores) if dscores is not None else W, pad,
                    work=lambda: (B * T * W * (4 + (dscores.element_size() if dscores is not None else 0)), 0))
 
+    def set_seed_source(self, seed_dev):
+        """int32/uint32 device tensor whose value is added to every dropout seed at kernel run time (None = off)."""
+        rc = self.lib.fn["ick_set_seed_source"](_p(seed_dev))
+        assert rc == 0
+
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2, clip, count, grad_scale, dstA, dstB, dstC, packT, packF,
-                  update=True):
+                  update=True, step_dev=None, lr_dev=None):
         self._call("ick_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, bc1, bc2, clip, _p(count),
-                   grad_scale, _p(dstA), _p(dstB), _p(dstC), _p(packT), dt_of(packT), _p(packF), int(update),
+                   grad_scale, _p(dstA), _p(dstB), _p(dstC), _p(packT), dt_of(packT), _p(packF), int(update), _p(step_dev), _p(lr_dev),
                    work=lambda: (p.numel() * (4 * (7 if update else 1) + 12 + 2 * packT.element_size()), 0))
 
     def cast2d(self, src, dst, cols):

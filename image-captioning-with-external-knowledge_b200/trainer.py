@@ -6,10 +6,14 @@ cross-entropy, backward, elementwise gradient clamp at +-5, Adam) without autogr
     -> [data-parallel: one NCCL all-reduce of that buffer, which also carries the loss sum and the token count]
     -> one kernel: scale by 1/tokens, clamp, Adam, and re-pack the bf16 / transposed operand copies.
 
+The ~280 launches of a step are captured ONCE into a CUDA graph (``use_graph=True``) and replayed: the step counter
+(dropout seed offset, Adam bias corrections) and the learning rate live in device memory, so a replay draws new dropout
+masks and applies the right corrections without any host work beyond copying the next batch into the static inputs.
+
 Data-parallel semantics: captions are independent samples, so ranks shard the batch; the reference
 clamps the FULL-batch mean gradient, therefore gradients are summed un-normalised, all-reduced BEFORE the clamp, and
-divided by the GLOBAL kept-token count inside the optimizer kernel — bit-for-bit the single-process large-batch update
-up to fp32 summation order.
+divided by the GLOBAL kept-token count inside the optimizer kernel — the single-process large-batch update up to fp32
+summation order.
 """
 from __future__ import annotations
 
@@ -21,7 +25,7 @@ import torch
 
 class Trainer:
     def __init__(self, decoder, lr: float = 4e-4, betas=(0.9, 0.999), eps: float = 1e-8, grad_clip: Optional[float] = 5.0,
-                 process_group=None, distributed: bool = False):
+                 process_group=None, distributed: bool = False, use_graph: bool = False):
         self.decoder = decoder
         self.eng = decoder._ensure_engine()
         n = self.eng.plan.n_params
@@ -33,14 +37,29 @@ class Trainer:
         self.loss_acc = self.gbuf[n:]
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.lr, self.betas, self.eps = lr, betas, eps
+        self.betas, self.eps = betas, eps
         self.clip = float(grad_clip) if grad_clip else 0.0
-        self.t = 0
         self.distributed = distributed
         self.pg = process_group
         self.seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
+        # device-resident step state: read by the kernels at run time (graph replay needs no new kernel arguments)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=dev)
+        self._lr = lr
         # parameters that the reference would not update (requires_grad False) keep a zero gradient
         self._frozen = [k for k in decoder._param_names if not decoder._get(k).requires_grad]
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    def adjust_learning_rate(self, shrink_factor: float) -> None:
+        """ut.adjust_learning_rate, G/utils.py:87-97."""
+        self._lr *= shrink_factor
+        self.lr_dev.fill_(self._lr)
 
     def prepare(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None):
         """Host->device moves and the sort-by-length of DecoderTransformer.forward (G/models.py:330-335); no host sync."""
@@ -48,15 +67,18 @@ class Trainer:
         inp.decode_len = (lengths - 1).to(torch.int32)
         return inp
 
-    def step(self, inp) -> torch.Tensor:
-        """One optimisation step on a prepared batch.  Returns a device tensor [loss_sum, kept_tokens] (global under DDP)."""
+    # ---- one step, eager ----------------------------------------------------------------------------------------------------
+    def _step_impl(self, inp) -> None:
         eng, K = self.eng, self.eng.K
-        self.t += 1
-        seed = (self.seed_base * 1000003 + self.t) & 0x7FFFFFFF
+        self.step_dev.add_(1)
         self.gbuf.zero_()
-        scores, ctx = eng.forward(inp, train=self.decoder.training, seed=seed)
-        _, ds = eng.loss(scores, inp.captions, inp.decode_len, loss_acc=self.loss_acc)
-        eng.backward(ctx, ds, self.g, need_encoder_grad=False)
+        K.set_seed_source(self.step_dev)  # effective dropout seed = seed_base + step (read on the device)
+        try:
+            scores, ctx = eng.forward(inp, train=self.decoder.training, seed=self.seed_base)
+            _, ds = eng.loss(scores, inp.captions, inp.decode_len, loss_acc=self.loss_acc)
+            eng.backward(ctx, ds, self.g, need_encoder_grad=False)
+        finally:
+            K.set_seed_source(None)
         for k in self._frozen:
             eng.param(k, self.g).zero_()
         if self.distributed:
@@ -64,13 +86,41 @@ class Trainer:
 
             dist.all_reduce(self.gbuf, group=self.pg)
         b1, b2 = self.betas
-        K.adam_step(eng.P, self.g, self.m, self.v, self.lr, b1, b2, self.eps, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, self.clip,
-                    self.loss_acc[1:], 1.0, eng.dstA, eng.dstB, eng.dstC, eng.packT, eng.packF, update=True)
+        K.adam_step(eng.P, self.g, self.m, self.v, self._lr, b1, b2, self.eps, 1.0, 1.0, self.clip, self.loss_acc[1:], 1.0, eng.dstA,
+                    eng.dstB, eng.dstC, eng.packT, eng.packF, update=True, step_dev=self.step_dev, lr_dev=self.lr_dev)
+
+    def step(self, inp) -> torch.Tensor:
+        """One optimisation step on a prepared batch.  Returns a device tensor [loss_sum, kept_tokens] (global under DDP)."""
+        if not self.use_graph:
+            self._step_impl(inp)
+            return self.loss_acc
+        if self._graph is None:
+            self._capture(inp)
+        else:
+            for k, v in vars(self._static).items():
+                if torch.is_tensor(v):
+                    v.copy_(getattr(inp, k), non_blocking=True)
+        self._graph.replay()
         return self.loss_acc
+
+    def _capture(self, inp) -> None:
+        self._static = NS(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in vars(inp).items()})
+        # One eager warm-up step on a side stream (lazy one-time initialisation must not happen during capture); the
+        # optimizer state is snapshotted and restored around it so that the first call still performs exactly one step.
+        snap = [t.clone() for t in (self.eng.P, self.m, self.v, self.step_dev)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_impl(self._static)
+        torch.cuda.current_stream().wait_stream(s)
+        for t, c in zip((self.eng.P, self.m, self.v, self.step_dev), snap):
+            t.copy_(c)
+        self.eng.repack()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_impl(self._static)  # capture only: nothing executes here
+        self._graph = g
 
     def train_step(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None) -> torch.Tensor:
         return self.step(self.prepare(captions, encoder_out, caption_masks, caption_lengths, entities, facts))
-
-    def adjust_learning_rate(self, shrink_factor: float) -> None:
-        """ut.adjust_learning_rate, G/utils.py:87-97."""
-        self.lr *= shrink_factor

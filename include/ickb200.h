@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 2
+#define ICK_ABI_VERSION 3
 
 #ifdef __cplusplus
 extern "C" {
@@ -129,7 +129,12 @@ int ick_ce_fwd_bwd(const float* scores, const long long* captions_sorted, const 
  * packT (forward and transposed layouts), dstC the fp32 packF.  update = 0 only repacks. */
 int ick_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   float bias_corr1, float bias_corr2, float clip, const float* count, float grad_scale, const int* dstA,
-                  const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, cudaStream_t stream);
+                  const int* dstB, const int* dstC, void* packT, int dt, float* packF, int update, const int* step_dev,
+                  const float* lr_dev, cudaStream_t stream);
+/* Dropout kernels launched after this call add *seed_dev (device memory, may be NULL) to their seed argument when they
+ * run: a captured CUDA graph then draws fresh masks on every replay.  step_dev / lr_dev of ick_adam_step play the same
+ * role for the Adam bias corrections and the learning rate. */
+int ick_set_seed_source(const unsigned* seed_dev);
 int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, long long rows, int cols, int lds, int ldd, cudaStream_t stream);
 int ick_accum_f32(const void* src, int dt, float* dst, long long n, cudaStream_t stream);
 int ick_colsum(const void* x, int dt, float* out, long long rows, int cols, int ld, cudaStream_t stream);

@@ -18,12 +18,17 @@ FIRST_NONE = 1 << 29
 HD = 32
 
 
+_SEED_SRC = [None]
+
+
 def _mul(drop, numel):
     if drop is None:
         return None
     p, seed, site = drop
     if p <= 0:
         return None
+    if _SEED_SRC[0] is not None:
+        seed = (seed + int(_SEED_SRC[0][0])) & 0xFFFFFFFF
     return drop_mul(p, seed, site, numel)
 
 
@@ -422,8 +427,17 @@ class HostKernels:
             dscores.zero_()
             dscores.view(B, T, -1)[:, :, :W] = g.to(dscores.dtype)
 
-    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2, clip, count, grad_scale, dstA, dstB, dstC, packT, packF, update=True):
+    def set_seed_source(self, seed_dev):
+        _SEED_SRC[0] = seed_dev
+
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, bc1, bc2, clip, count, grad_scale, dstA, dstB, dstC, packT, packF, update=True,
+                  step_dev=None, lr_dev=None):
         self.calls += 1
+        if update and step_dev is not None:
+            t = float(step_dev[0])
+            bc1, bc2 = 1.0 - beta1 ** t, 1.0 - beta2 ** t
+        if update and lr_dev is not None:
+            lr = float(lr_dev[0])
         if update:
             gs = grad_scale / max(float(count[0]), 1.0) if count is not None else grad_scale
             gv = g * gs

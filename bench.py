@@ -316,6 +316,10 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if distributed:
+        # drop a captured graph (it holds NCCL work) before tearing the communicator down
+        tr._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -78,9 +78,9 @@ struct AttnDims {
     float scale;       // 1/sqrt(dh)
 };
 
-// dropout index of probability (b,h,i,j)
-__device__ __forceinline__ uint64_t pidx(const AttnDims& d, int b, int h, int i, int j) {
-    return (((uint64_t)b * d.H + h) * (uint64_t)d.Sq + i) * (uint64_t)d.Sk + j;
+// dropout row of query (b,h,i): probabilities are addressed as (row, key)
+__device__ __forceinline__ uint64_t prow(const AttnDims& d, int b, int h, int i) {
+    return ((uint64_t)b * d.H + h) * (uint64_t)d.Sq + i;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, co
 #pragma unroll
     for (int c = 0; c < HD; ++c) q[c] = (c < d.dh) ? q[c] * d.scale_log2 : 0.f;  // pad lanes never contribute
     float m = -INFINITY, l = 0.f;
+    const uint32_t rmix = ick_rowmix(drop.seed, drop.site, prow(d, b, h, i));
 
     // causal: no key beyond the last query of this CTA is visible
     const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, co
             for (int jj = 0; jj < 8; ++jj) {
                 const float p = exp2f(s[jj] - mnew);  // masked -> exp2(-inf) = 0
                 l += p;
-                const float pd = p * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, k0 + j0 + jj));
+                const float pd = p * ick_drop_mul(drop, rmix, (uint32_t)(k0 + j0 + jj));
                 axpy32(acc, pd, Vs[j0 + jj]);
             }
             m = mnew;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
         go[c] = (c < d.dh) ? go[c] : 0.f;
     }
 
+    const uint32_t rmix = ick_rowmix(drop.seed, drop.site, prow(d, b, h, i));
     const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
     for (int k0 = 0; k0 < kmax; k0 += KT) {
         __syncthreads();
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
             const int j = k0 + jj;
             if (d.causal && j > i) break;
             const float p = exp2f(dot32(q, Ks[jj]) - lse);
-            const float dp = dot32(go, Vs[jj]) * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, j));
+            const float dp = dot32(go, Vs[jj]) * ick_drop_mul(drop, rmix, (uint32_t)j);
             const float ds = p * (dp - Di);
             axpy32(dq, ds, Ks[jj]);
         }
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dkv_kernel(const T* __restrict__ Q
             const int i = q0 + ii;
             if (d.causal && j > i) continue;
             const float p = exp2f(dot32(k, Qs[ii]) - Ls[ii]);
-            const float mul = ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, pidx(d, b, h, i, j));
+            const float mul = ick_drop_mul(drop, ick_rowmix(drop.seed, drop.site, prow(d, b, h, i)), (uint32_t)j);
             axpy32(dv, p * mul, Gs[ii]);
             const float dp = dot32(v, Gs[ii]) * mul;
             const float ds = p * (dp - Ds[ii]);

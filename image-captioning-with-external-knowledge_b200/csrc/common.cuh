@@ -84,11 +84,14 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- counter-based dropout hash -------------------------------------------------------------------------------------
-// keep(seed, site, idx) is a pure function so the backward pass regenerates the mask instead of storing it.
-// tests/dropout_ref.py holds the numpy port used to inject identical masks into the oracle.
-__host__ __device__ __forceinline__ uint32_t ick_hash(uint32_t seed, uint32_t site, uint64_t idx) {
-    uint32_t lo = (uint32_t)idx, hi = (uint32_t)(idx >> 32);
-    uint32_t h = (lo * 0x9E3779B1u) ^ ((hi + site * 0x7F4A7C15u) * 0x85EBCA77u) ^ seed;
+// keep(seed, site, row, col) is a pure function, so the backward pass regenerates the mask instead of storing it.
+// An element is addressed as (row, col) = (flat index of the leading dimensions, index in the last dimension).  The
+// row is mixed once (ick_rowmix); ONE 32-bit hash then serves the column pair (2k, 2k+1) as two 15-bit uniform fields
+// (bits 0-14 for the even column, bits 16-30 for the odd one), compared against thr = floor(p * 32768): keep iff
+// field >= thr.  15 bits leave the top bit of each half-word free, so both comparisons can be done with one add.  tests/dropout_ref.py is the numpy port used to inject the same masks into
+// the oracle.
+__host__ __device__ __forceinline__ uint32_t ick_rowmix(uint32_t seed, uint32_t site, uint64_t row) {
+    uint32_t h = seed ^ (site * 0x7F4A7C15u) ^ ((uint32_t)row * 0x9E3779B1u) ^ ((uint32_t)(row >> 32) * 0x85EBCA77u);
     h ^= h >> 16;
     h *= 0x85EBCA6Bu;
     h ^= h >> 13;
@@ -96,14 +99,24 @@ __host__ __device__ __forceinline__ uint32_t ick_hash(uint32_t seed, uint32_t si
     h ^= h >> 16;
     return h;
 }
-// thr = p * 2^32 (0 disables dropout); returns the multiplier 0 or 1/(1-p)
-__device__ __forceinline__ float ick_drop_mul(uint32_t thr, float inv_keep, uint32_t seed, uint32_t site, uint64_t idx) {
-    if (thr == 0u) return 1.0f;
-    return ick_hash(seed, site, idx) >= thr ? inv_keep : 0.0f;
+__host__ __device__ __forceinline__ uint32_t ick_pairhash(uint32_t rowmix, uint32_t col) {
+    uint32_t h = ((col >> 1) * 0x9E3779B1u) ^ rowmix;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+__host__ __device__ __forceinline__ bool ick_keep_lo(uint32_t pairhash, uint32_t thr) { return (pairhash & 0x7FFFu) >= thr; }
+__host__ __device__ __forceinline__ bool ick_keep_hi(uint32_t pairhash, uint32_t thr) { return ((pairhash >> 16) & 0x7FFFu) >= thr; }
+// multiplier (0 or 1/(1-p)) of column `col` given the hash of its pair
+__device__ __forceinline__ float ick_keep(uint32_t thr, float inv_keep, uint32_t pairhash, uint32_t col) {
+    return ((col & 1u) ? ick_keep_hi(pairhash, thr) : ick_keep_lo(pairhash, thr)) ? inv_keep : 0.0f;
 }
 
 struct DropCfg {
-    uint32_t thr;    // p * 2^32, 0 = off
+    uint32_t thr;    // floor(p * 32768), 0 = off
     float inv_keep;  // 1 / (1 - p)
     uint32_t seed;
     uint32_t site;
@@ -115,6 +128,11 @@ const uint32_t* ick_seed_source();
 __device__ __forceinline__ void ick_resolve_seed(DropCfg& d) {
     if (d.seed_dev != nullptr) d.seed += *d.seed_dev;
 }
+// convenience for kernels that touch one element at a time
+__device__ __forceinline__ float ick_drop_mul(const DropCfg& d, uint32_t rowmix, uint32_t col) {
+    if (d.thr == 0u) return 1.0f;
+    return ick_keep(d.thr, d.inv_keep, ick_pairhash(rowmix, col), col);
+}
 static inline DropCfg make_drop(float p, unsigned seed, unsigned site) {
     DropCfg d;
     d.seed_dev = ick_seed_source();
@@ -122,8 +140,8 @@ static inline DropCfg make_drop(float p, unsigned seed, unsigned site) {
         d.thr = 0u;
         d.inv_keep = 1.f;
     } else {
-        double t = (double)p * 4294967296.0;
-        d.thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+        double t = (double)p * 32768.0;
+        d.thr = t >= 32767.0 ? 32767u : (uint32_t)t;
         d.inv_keep = 1.0f / (1.0f - p);
     }
     d.seed = seed;

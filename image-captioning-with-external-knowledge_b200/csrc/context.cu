@@ -199,11 +199,10 @@ __global__ void __launch_bounds__(256) caption_embed_fwd_kernel(const long long*
                                : factenc + ((size_t)b * F + s.idx) * ld;
     const float* per = pe + (size_t)t * D;
     T* o = out + (size_t)row * ld;
+    const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)row);
     for (int c = lane; c < ld; c += 32) {
         float v = 0.f;
-        if (c < D)
-            v = (to_f(src[c]) * scale + per[c]) *
-                ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, (uint64_t)row * (uint64_t)D + c);
+        if (c < D) v = (to_f(src[c]) * scale + per[c]) * ick_drop_mul(drop, rmix, (uint32_t)c);
         o[c] = from_f<T>(v);
     }
 }
@@ -224,9 +223,9 @@ __global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restr
                : s.kind == 1 ? dEnt + ((size_t)b * E + s.idx) * ld
                              : dFact + ((size_t)b * F + s.idx) * ld;
     const T* g = dX + (size_t)row * ld;
+    const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)row);
     for (int c = lane; c < D; c += 32) {
-        const float v = to_f(g[c]) * scale *
-                        ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, (uint64_t)row * (uint64_t)D + c);
+        const float v = to_f(g[c]) * scale * ick_drop_mul(drop, rmix, (uint32_t)c);
         atomicAdd(dst + c, v);
     }
 }

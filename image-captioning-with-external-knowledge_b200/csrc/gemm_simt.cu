@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, 
     for (int i = 0; i < 8; ++i) {
         const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (row >= M) continue;
+        const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)row);
 #pragma unroll
         for (int jh = 0; jh < 2; ++jh) {
             const int col = n0 + jh * 64 + tx * 4;
@@ -117,8 +118,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, 
                     if (bias) x += bias[c];
                     if (accumulate) x += to_f(C[(size_t)row * ldc + c]);
                     if (epi == EPI_RELU_DROP) {
-                        x = fmaxf(x, 0.f) * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site,
-                                                         (uint64_t)row * (uint64_t)N + (uint64_t)c);
+                        x = fmaxf(x, 0.f) * ick_drop_mul(drop, rmix, (uint32_t)c);
                     } else if (epi == EPI_RELU_BWD) {
                         x = (to_f(aux[(size_t)row * ldaux + c]) != 0.f) ? x * drop.inv_keep : 0.f;
                     }

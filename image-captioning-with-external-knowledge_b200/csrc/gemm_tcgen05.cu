@@ -308,10 +308,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                         for (int j = 0; j < 32; ++j) v[j] += t[j];
                     }
                     if (p.epi == 1) {
+                        const uint32_t rmix = ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            v[j] = fmaxf(v[j], 0.f) * ick_drop_mul(p.drop.thr, p.drop.inv_keep, p.drop.seed, p.drop.site,
-                                                                   (uint64_t)row * (uint64_t)p.N + (uint64_t)(col0 + j));
+                        for (int j = 0; j < 32; j += 2) {  // col0 is even: (j, j+1) is one hash pair
+                            float k0 = 1.f, k1 = 1.f;
+                            if (p.drop.thr != 0u) {
+                                const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(col0 + j));
+                                k0 = ick_keep_lo(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
+                                k1 = ick_keep_hi(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
+                            }
+                            v[j] = fmaxf(v[j], 0.f) * k0;
+                            v[j + 1] = fmaxf(v[j + 1], 0.f) * k1;
+                        }
                     } else if (p.epi == 2) {
                         float t[32];
                         ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);

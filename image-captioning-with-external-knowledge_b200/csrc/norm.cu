@@ -33,15 +33,20 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ X
         T* s = SUB + (size_t)r * lds;
         float v[2 * MAXP];
         float sum = 0.f;
+        const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)r);
 #pragma unroll
         for (int i = 0; i < MAXP; ++i) {
             const int p = lane + 32 * i;
             float a = 0.f, b = 0.f;
             if (p < npairs) {
                 const float2 u = ld2(s + 2 * p);
-                const uint64_t idx = (uint64_t)r * (uint64_t)d + 2 * p;
-                a = u.x * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx);
-                b = u.y * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx + 1);
+                a = u.x;
+                b = u.y;
+                if (drop.thr != 0u) {
+                    const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(2 * p));
+                    a *= ick_keep_lo(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                    b *= ick_keep_hi(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                }
                 if (x) {
                     const float2 xr = ld2(x + 2 * p);
                     a += xr.x;
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ D
         const T* dy = DY + dymap.map(r) * lddy;
         const T* s = S + (size_t)r * lds;
         const float mean = MEAN[r], rstd = RSTD[r];
+        const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)r);
         float g[2 * MAXP], xh[2 * MAXP];
         float sum_g = 0.f, sum_gx = 0.f;
 #pragma unroll
@@ -145,9 +151,13 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ D
                 float a = rstd * (g[2 * i] - mg - xh[2 * i] * mgx);
                 float b = rstd * (g[2 * i + 1] - mg - xh[2 * i + 1] * mgx);
                 if (dsub) {
-                    const uint64_t idx = (uint64_t)r * (uint64_t)d + 2 * p;
-                    st2(dsub + 2 * p, a * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx),
-                        b * ick_drop_mul(drop.thr, drop.inv_keep, drop.seed, drop.site, idx + 1));
+                    float k0 = 1.f, k1 = 1.f;
+                    if (drop.thr != 0u) {
+                        const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(2 * p));
+                        k0 = ick_keep_lo(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                        k1 = ick_keep_hi(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                    }
+                    st2(dsub + 2 * p, a * k0, b * k1);
                 }
                 if (dres) {
                     if (acc_res) {

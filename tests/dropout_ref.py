@@ -1,16 +1,23 @@
-"""Test-side port of the kernels' counter-based dropout hash (csrc/common.cuh: ick_hash / ick_drop_mul)."""
+"""Test-side port of the kernels' counter-based dropout hash (csrc/common.cuh: ick_rowmix / ick_pairhash / ick_keep).
+
+An element is addressed as (row, col): row = flat index over the leading dimensions, col = index in the last one.  One
+32-bit hash serves the column pair (2k, 2k+1) as two 15-bit uniform fields (bits 0-14 / 16-30) compared against
+thr = floor(p * 32768)."""
 import numpy as np
 import torch
 
 M32 = np.uint64(0xFFFFFFFF)
 
 
-def ick_hash(seed: int, site: int, idx: np.ndarray) -> np.ndarray:
-    idx = idx.astype(np.uint64)
-    lo = idx & M32
-    hi = (idx >> np.uint64(32)) & M32
-    h = ((lo * np.uint64(0x9E3779B1)) & M32) ^ (((hi + np.uint64((site * 0x7F4A7C15) & 0xFFFFFFFF)) & M32) * np.uint64(0x85EBCA77) & M32) \
-        ^ np.uint64(seed & 0xFFFFFFFF)
+def _u(x):
+    return np.uint64(x & 0xFFFFFFFF)
+
+
+def ick_rowmix(seed: int, site: int, row: np.ndarray) -> np.ndarray:
+    row = row.astype(np.uint64)
+    lo = row & M32
+    hi = (row >> np.uint64(32)) & M32
+    h = _u(seed) ^ _u(site * 0x7F4A7C15) ^ ((lo * np.uint64(0x9E3779B1)) & M32) ^ ((hi * np.uint64(0x85EBCA77)) & M32)
     h ^= h >> np.uint64(16)
     h = (h * np.uint64(0x85EBCA6B)) & M32
     h ^= h >> np.uint64(13)
@@ -19,12 +26,25 @@ def ick_hash(seed: int, site: int, idx: np.ndarray) -> np.ndarray:
     return h
 
 
-def drop_mul(p: float, seed: int, site: int, numel: int) -> torch.Tensor:
-    """multiplier (0 or 1/(1-p)) for flat element indices 0..numel-1, as float32"""
+def ick_pairhash(rowmix: np.ndarray, col: np.ndarray) -> np.ndarray:
+    h = (((col.astype(np.uint64) >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M32) ^ rowmix
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x2C1B3C6D)) & M32
+    h ^= h >> np.uint64(12)
+    h = (h * np.uint64(0x297A2D39)) & M32
+    h ^= h >> np.uint64(15)
+    return h
+
+
+def drop_mul(p: float, seed: int, site: int, rows: int, cols: int) -> torch.Tensor:
+    """multiplier (0 or 1/(1-p)) for a (rows, cols) tensor, as float32"""
     if p <= 0.0:
-        return torch.ones(numel, dtype=torch.float32)
-    t = float(p) * 4294967296.0
-    thr = 4294967295 if t >= 4294967295.0 else int(t)
-    h = ick_hash(seed, site, np.arange(numel, dtype=np.uint64))
+        return torch.ones(rows, cols, dtype=torch.float32)
+    t = float(p) * 32768.0
+    thr = 32767 if t >= 32767.0 else int(t)
+    rm = ick_rowmix(seed, site, np.arange(rows, dtype=np.uint64))[:, None]
+    col = np.arange(cols, dtype=np.uint64)[None, :]
+    h = ick_pairhash(rm, col)
+    f = np.where((col & np.uint64(1)) != 0, h >> np.uint64(16), h) & np.uint64(0x7FFF)
     inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
-    return torch.from_numpy(np.where(h >= np.uint64(thr), inv, np.float32(0.0)).astype(np.float32))
+    return torch.from_numpy(np.where(f >= np.uint64(thr), inv, np.float32(0.0)).astype(np.float32))

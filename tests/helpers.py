@@ -75,9 +75,9 @@ def oracle_drop_fn(seed, ps):
             p = ps["enc"]
         if p <= 0:
             return None
-        n = 1
-        for s in shape:
-            n *= s
-        return drop_mul(p, seed, layout.site_id(site), n).view(*shape)
+        rows = 1
+        for s in shape[:-1]:
+            rows *= s
+        return drop_mul(p, seed, layout.site_id(site), rows, shape[-1]).view(*shape)
 
     return fn

@@ -21,7 +21,7 @@ HD = 32
 _SEED_SRC = [None]
 
 
-def _mul(drop, numel):
+def _mul(drop, rows, cols):
     if drop is None:
         return None
     p, seed, site = drop
@@ -29,7 +29,7 @@ def _mul(drop, numel):
         return None
     if _SEED_SRC[0] is not None:
         seed = (seed + int(_SEED_SRC[0][0])) & 0xFFFFFFFF
-    return drop_mul(p, seed, site, numel)
+    return drop_mul(p, seed, site, rows, cols)
 
 
 def _rows(rowmap, R):
@@ -58,7 +58,7 @@ class HostKernels:
             acc = acc + C.float()
         if epi == 1:
             acc = torch.relu(acc)
-            m = _mul(drop, M * N)
+            m = _mul(drop, M, N)
             if m is not None:
                 acc = acc * m.view(M, N)
         elif epi == 2:
@@ -101,7 +101,7 @@ class HostKernels:
         v = self._heads(V, B, Sk, H)[..., :dh]
         p = torch.softmax(s, dim=-1)
         lse.copy_((torch.logsumexp(s, dim=-1) * 1.4426950408889634).reshape(-1))
-        m = _mul(drop, p.numel())
+        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1])
         pd = p * m.view_as(p) if m is not None else p
         o = pd @ v  # (B,H,Sq,dh)
         out = torch.zeros(B, H, Sq, HD)
@@ -114,7 +114,7 @@ class HostKernels:
         v = self._heads(V, B, Sk, H)[..., :dh]
         go = self._heads(dO, B, Sq, H)[..., :dh]
         p = torch.softmax(s, dim=-1)
-        m = _mul(drop, p.numel())
+        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1])
         mm = m.view_as(p) if m is not None else torch.ones_like(p)
         dv = (p * mm).transpose(-1, -2) @ go
         dp = (go @ v.transpose(-1, -2)) * mm
@@ -152,7 +152,7 @@ class HostKernels:
         self.calls += 1
         R = sub.shape[0]
         s = sub[:, :d].float()
-        m = _mul(drop, R * d)
+        m = _mul(drop, R, d)
         if m is not None:
             s = s * m.view(R, d)
         if x is not None:
@@ -182,7 +182,7 @@ class HostKernels:
         if dbeta is not None:
             dbeta.add_(g_in.sum(0).view_as(dbeta))
         if dsub is not None:
-            m = _mul(drop, R * d)
+            m = _mul(drop, R, d)
             v = dx * m.view(R, d) if m is not None else dx
             dsub.zero_()
             dsub[:, :d] = v.to(dsub.dtype)
@@ -294,7 +294,7 @@ class HostKernels:
             gf = torch.gather(f, 1, torch.where(kind == 2, idx, torch.zeros_like(idx)).unsqueeze(-1).expand(-1, -1, D))
             emb = torch.where((kind == 2).unsqueeze(-1), gf, emb)
         x = emb * scale + pe[t0 : t0 + Tn].float().unsqueeze(0)
-        m = _mul(drop, B * Tn * D)
+        m = _mul(drop, B * Tn, D)
         if m is not None:
             x = x * m.view(B, Tn, D)
         out.zero_()
@@ -304,7 +304,7 @@ class HostKernels:
         self.calls += 1
         kind, idx = self._select(captions.view(B, T), masks.view(B, T), V, E, F, pad)
         g = dX[:, :D].float() * scale
-        m = _mul(drop, B * T * D)
+        m = _mul(drop, B * T, D)
         if m is not None:
             g = g * m.view(B * T, D)
         kind, idx = kind.reshape(-1), idx.reshape(-1)

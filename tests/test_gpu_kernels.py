@@ -139,7 +139,9 @@ def test_wgrad(K, Hk, tc, dtype, M, N, K_):
 
 # ---------------------------------------------------------------------------------------------------------------------------
 ATT_CASES = [(2, 10, 301, 301, 30, False), (3, 10, 102, 102, 30, True), (2, 10, 37, 548, 30, False), (1, 4, 5, 5, 32, True),
-             (2, 10, 130, 130, 30, True)]
+             (2, 10, 130, 130, 30, True),
+             # more than 640 streamed positions: the resident-tile chunk loop of the bf16 kernels (K/V in fwd and dQ, Q/dO in dK-dV)
+             (1, 2, 70, 700, 30, False), (1, 2, 700, 700, 30, True)]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -172,3 +172,20 @@ def test_trainer_cuda_graph_replay_matches_eager(dtype):
     for (a0, n0), (a1, n1) in zip(l0, l1):
         assert n0 == n1 and abs(a0 - a1) <= 2e-3 * abs(a0)  # same masks (seed_base + device step), same arithmetic
     assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
+
+
+@pytest.mark.parametrize("name", ["geo_b32", "news_b8"])
+def test_other_variants_at_baseline_sizes(name):
+    """BASELINE configs[0] (geo, B=32) and the per-GPU shard of configs[2] (news, B=8): one fused train step in bf16 runs,
+    the loss is finite and falls when the same batch is repeated (end-to-end sanity of fwd + bwd + Adam at full sizes)."""
+    from ickb200.trainer import Trainer
+
+    cfg = syn.BASELINE_CONFIGS[name]
+    dec = build_module(cfg, "cuda", torch.bfloat16, dropouts=(0.0, 0.0, 0.0)).train()
+    tr = Trainer(dec, lr=4e-4)
+    batch = to_dev(cfg, syn.make_batch(cfg, seed=11))
+    losses = []
+    for _ in range(6):
+        acc = tr.train_step(*batch_args(cfg, batch))
+        losses.append(float(acc[0] / acc[1]))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses

@@ -4,7 +4,9 @@
 // counter hash, log2-domain LSE saved.
 //
 //   ownership : a warp owns 16 "own" rows (queries in fwd / dQ, keys in dK-dV) whose A fragments are read straight from
-//               global memory once; a CTA is 1..8 such warps.
+//               global memory once.
+//   scheduling: persistent CTAs (one per SM, 15 compute warps + 1 TMA producer warp) pipeline whole (image, head) items
+//               through 2-6 shared-memory stages; a chunked one-CTA-per-block variant covers sequences longer than 640.
 //   streaming : the other operand (K,V for fwd / dQ; Q,dO for dK-dV) is brought in by TMA as 64-row x 64-byte boxes of a
 //               3-D tensor map (column, position, image), 64B-swizzled, one mbarrier per box pair.  Up to 10 tiles (640
 //               positions, every shape of the reference) are resident at once, so one elected thread issues all copies up
@@ -220,7 +222,260 @@ __device__ __forceinline__ uint32_t keep_mask_bf16x2(uint32_t kb) {
     return m;
 }
 
-// ------------------------------------------------------------------------------------------------------------------------
+// ---- per-warp tile bodies (shared by the chunked and the persistent kernels) ------------------------------------------------
+struct OwnRows {
+    int r0, r1;         // own rows of the accumulator halves (lane group g and g + 8)
+    int wrow;           // first own row of the warp
+    uint32_t rm0, rm1;  // dropout row mixes of r0 / r1 (fwd, dQ)
+};
+struct TileEnv {
+    Dims d;
+    float c;        // scale * log2(e)
+    float ik;       // 1 / keep
+    uint32_t thr;   // dropout threshold (0 = off)
+    uint32_t addc;  // keep_addc(thr)
+    LaneOff lo;
+    int tq;
+};
+
+struct FwdAcc {
+    float m0, m1, l0, l1;  // running max of the RAW scores, running sum
+    float o[4][4];
+};
+__device__ __forceinline__ void fwd_init(FwdAcc& a) {
+    a.m0 = a.m1 = -INFINITY;
+    a.l0 = a.l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) a.o[n][0] = a.o[n][1] = a.o[n][2] = a.o[n][3] = 0.f;
+}
+// one 64-key tile: S = Q K^T, online softmax, dropout, O += P V
+__device__ __forceinline__ void fwd_tile(FwdAcc& a, const uint32_t (*qa)[4], uint32_t kt, uint32_t vt, int k0, const OwnRows& r,
+                                         const TileEnv& e) {
+    const Dims& d = e.d;
+    // causal: tiles entirely beyond this warp's last query contribute nothing
+    if (d.causal && k0 > r.wrow + 15) return;
+    const float c = e.c;
+    const int tq = e.tq;
+    float s[8][4];
+    mma_a_tT<8>(s, qa, kt, 0, e.lo);
+    // masking is needed only on the ragged last tile and on tiles that cross this warp's causal diagonal
+    if (k0 + TK > d.Sk || (d.causal && k0 + TK - 1 > r.wrow)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int key = k0 + 8 * j + 2 * tq + (x & 1);
+                const bool vis = key < d.Sk && (!d.causal || key <= (x < 2 ? r.r0 : r.r1));
+                if (!vis) s[j][x] = -INFINITY;
+            }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(a.m0, mx0), mn1 = fmaxf(a.m1, mx1);
+    // a row with no visible key so far keeps m = -inf; use 0 as the exponent base there (all p are ex2(-inf) = 0)
+    const float e0 = mn0 == -INFINITY ? 0.f : mn0 * c, e1 = mn1 == -INFINITY ? 0.f : mn1 * c;
+    const float c0f = ex2(a.m0 * c - e0), c1f = ex2(a.m1 * c - e1);
+    a.l0 *= c0f;
+    a.l1 *= c1f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        a.o[n][0] *= c0f; a.o[n][1] *= c0f; a.o[n][2] *= c1f; a.o[n][3] *= c1f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j][0] = ex2(fmaf(s[j][0], c, -e0));
+        s[j][1] = ex2(fmaf(s[j][1], c, -e0));
+        s[j][2] = ex2(fmaf(s[j][2], c, -e1));
+        s[j][3] = ex2(fmaf(s[j][3], c, -e1));
+        a.l0 += s[j][0] + s[j][1];
+        a.l1 += s[j][2] + s[j][3];
+    }
+    uint32_t pa[4][4];
+    pack_p<8>(s, pa);
+    if (e.thr != 0u) {
+        const uint32_t pr = (uint32_t)(k0 >> 1) + (uint32_t)tq;  // pair index of this lane's keys in n-tile 0; + 4 per n-tile
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                pa[kk][2 * jj] &= keep_mask_bf16x2(keep_bits(ick_pairhash_idx(r.rm0, pr + 4 * (2 * kk + jj)), e.addc));
+                pa[kk][2 * jj + 1] &= keep_mask_bf16x2(keep_bits(ick_pairhash_idx(r.rm1, pr + 4 * (2 * kk + jj)), e.addc));
+            }
+    }
+    mma_p_t<8>(a.o, pa, vt, 0, e.lo);
+    a.m0 = mn0;
+    a.m1 = mn1;
+}
+__device__ __forceinline__ void fwd_finish(FwdAcc& a, bf16* Ob, int ldo, float* L, const OwnRows& r, const TileEnv& e) {
+    a.l0 += __shfl_xor_sync(0xffffffffu, a.l0, 1);
+    a.l0 += __shfl_xor_sync(0xffffffffu, a.l0, 2);
+    a.l1 += __shfl_xor_sync(0xffffffffu, a.l1, 1);
+    a.l1 += __shfl_xor_sync(0xffffffffu, a.l1, 2);
+    store_slab(Ob, ldo, r.r0, r.r1, e.d.Sq, a.o, e.ik / a.l0, e.ik / a.l1, e.d.dh, e.tq);
+    if (e.tq == 0) {
+        if (r.r0 < e.d.Sq) L[r.r0] = a.m0 * e.c + log2f(a.l0);
+        if (r.r1 < e.d.Sq) L[r.r1] = a.m1 * e.c + log2f(a.l1);
+    }
+}
+
+// own-row prologue of dQ: D = rowsum(dO * O) (lane pair (2r, 2r+1) handles the two 16-column halves of own row r)
+__device__ __forceinline__ void dq_rowdot(const bf16* Ob, int ldo, const bf16* Gb, int lddo, float* Dsum, int wrow, int Sq, int dh, int lane,
+                                          float& D0, float& D1) {
+    const int rr = wrow + (lane >> 1), cb = (lane & 1) * 16, g = lane >> 2;
+    float acc = 0.f;
+    if (rr < Sq) {
+        const bf16* op = Ob + (size_t)rr * ldo + cb;
+        const bf16* gp = Gb + (size_t)rr * lddo + cb;
+        float x[8], y[8];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            ld8(op + 8 * v, x);
+            ld8(gp + 8 * v, y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (cb + 8 * v + i < dh) acc = fmaf(x[i], y[i], acc);
+        }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if ((lane & 1) == 0 && rr < Sq) Dsum[rr] = acc;
+    D0 = __shfl_sync(0xffffffffu, acc, 2 * g);
+    D1 = __shfl_sync(0xffffffffu, acc, 2 * g + 16);
+}
+// one 64-key tile of dQ: S and dP recomputed, dS = P (drop(dP) - D), dQ += dS K
+__device__ __forceinline__ void dq_tile(float (*dq)[4], const uint32_t (*qa)[4], const uint32_t (*ga)[4], uint32_t kt, uint32_t vt, int kt0,
+                                        const OwnRows& r, float lse0, float lse1, float D0, float D1, const TileEnv& e) {
+    const Dims& d = e.d;
+    const int tq = e.tq;
+#pragma unroll 1
+    for (int sub = 0; sub < TK / SUB; ++sub) {
+        const int k0 = kt0 + sub * SUB;
+        if (d.causal && k0 > r.wrow + 15) break;
+        // keys past Sk are zero rows (TMA fill): they add nothing to dQ = dS K, so only the causal diagonal needs a mask
+        const bool need_mask = d.causal && k0 + SUB - 1 > r.wrow;
+        float s[4][4], dp[4][4];
+        mma_a_tT<4>(s, qa, kt, 4 * sub, e.lo);
+        mma_a_tT<4>(dp, ga, vt, 4 * sub, e.lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e.thr != 0u) {
+                const uint32_t pr = (uint32_t)(k0 >> 1) + (uint32_t)(4 * j + tq);
+                const uint32_t kb0 = keep_bits(ick_pairhash_idx(r.rm0, pr), e.addc), kb1 = keep_bits(ick_pairhash_idx(r.rm1, pr), e.addc);
+                dp[j][0] = (kb0 & 0x8000u) ? dp[j][0] * e.ik : 0.f;
+                dp[j][1] = (kb0 & 0x80000000u) ? dp[j][1] * e.ik : 0.f;
+                dp[j][2] = (kb1 & 0x8000u) ? dp[j][2] * e.ik : 0.f;
+                dp[j][3] = (kb1 & 0x80000000u) ? dp[j][3] * e.ik : 0.f;
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                float p = ex2(fmaf(s[j][x], e.c, -(x < 2 ? lse0 : lse1)));
+                if (need_mask && k0 + 8 * j + 2 * tq + (x & 1) > (x < 2 ? r.r0 : r.r1)) p = 0.f;
+                s[j][x] = p * (dp[j][x] - (x < 2 ? D0 : D1));
+            }
+        }
+        uint32_t pa[2][4];
+        pack_p<4>(s, pa);
+        mma_p_t<4>(dq, pa, kt, 4 * sub, e.lo);
+    }
+}
+
+// one 64-query tile of dK/dV for the warp's 16 keys.  ls / ds / rm: LSE, D and dropout row mix of the tile's queries (smem).
+// Lanes g and g^1 own keys of the same dropout pair and see the same queries: each computes the pair hashes of ONE of its two
+// key rows (even g: r0, odd g: r1) and receives the other from its partner (lane ^ 4).
+__device__ __forceinline__ void dkv_tile(float (*dk)[4], float (*dv)[4], const uint32_t (*ka)[4], const uint32_t (*va)[4], uint32_t qt,
+                                         uint32_t gt, int qt0, const float* ls, const float* ds, const uint32_t* rm, const OwnRows& r,
+                                         bool odd, const TileEnv& e) {
+    const Dims& d = e.d;
+    const int tq = e.tq;
+    const uint32_t mypair = (uint32_t)(odd ? r.r1 : r.r0) >> 1;
+    const uint32_t bit0 = odd ? 0x80000000u : 0x8000u;  // keep bit of this lane's key parity
+#pragma unroll 1
+    for (int sub = 0; sub < TK / SUB; ++sub) {
+        const int q0 = qt0 + sub * SUB;                      // first query of the sub-step
+        if (d.causal && q0 + SUB - 1 < r.wrow) continue;     // every query precedes every key of this warp
+        // queries past Sq are zero rows of Q and dO (TMA fill) and add nothing; own keys past Sk are never stored
+        const bool need_mask = d.causal && r.wrow + 15 > q0;
+        const float* lsp = ls + sub * SUB + 2 * tq;
+        const float* dsp = ds + sub * SUB + 2 * tq;
+        const uint32_t* rmp = rm + sub * SUB + 2 * tq;
+        float st[4][4], dpt[4][4];
+        mma_a_tT<4>(st, ka, qt, 4 * sub, e.lo);
+        mma_a_tT<4>(dpt, va, gt, 4 * sub, e.lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 l2 = *reinterpret_cast<const float2*>(lsp + 8 * j);
+            const float2 d2 = *reinterpret_cast<const float2*>(dsp + 8 * j);
+            uint32_t hq0a = 0, hq0b = 0, hq1a = 0, hq1b = 0;  // keep bits of (query 0/1 of the pair, key row a = r0 / b = r1)
+            if (e.thr != 0u) {
+                const uint2 r2 = *reinterpret_cast<const uint2*>(rmp + 8 * j);
+                const uint32_t m0 = keep_bits(ick_pairhash_idx(r2.x, mypair), e.addc), m1 = keep_bits(ick_pairhash_idx(r2.y, mypair), e.addc);
+                const uint32_t o0 = __shfl_xor_sync(0xffffffffu, m0, 4), o1 = __shfl_xor_sync(0xffffffffu, m1, 4);
+                hq0a = odd ? o0 : m0; hq0b = odd ? m0 : o0;
+                hq1a = odd ? o1 : m1; hq1b = odd ? m1 : o1;
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int qi = q0 + 8 * j + 2 * tq + (x & 1);
+                float p = ex2(fmaf(st[j][x], e.c, -((x & 1) ? l2.y : l2.x)));
+                if (need_mask && (x < 2 ? r.r0 : r.r1) > qi) p = 0.f;
+                float gp = dpt[j][x];
+                float pm = p;
+                if (e.thr != 0u) {
+                    const uint32_t kb = (x == 0) ? hq0a : (x == 1) ? hq1a : (x == 2) ? hq0b : hq1b;
+                    const bool keep = (kb & bit0) != 0u;
+                    pm = keep ? p : 0.f;
+                    gp = keep ? gp * e.ik : 0.f;
+                }
+                st[j][x] = pm;                                   // P^T with dropout (1/keep applied at the store) -> dV
+                dpt[j][x] = p * (gp - ((x & 1) ? d2.y : d2.x));  // dS^T -> dK
+            }
+        }
+        uint32_t pa[2][4];
+        pack_p<4>(st, pa);
+        mma_p_t<4>(dv, pa, gt, 4 * sub, e.lo);
+        pack_p<4>(dpt, pa);
+        mma_p_t<4>(dk, pa, qt, 4 * sub, e.lo);
+    }
+}
+__device__ __forceinline__ void zero16(float (*a)[4]) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) a[n][0] = a[n][1] = a[n][2] = a[n][3] = 0.f;
+}
+__device__ __forceinline__ TileEnv make_env(const Dims& d, const DropCfg& drop, int lane) {
+    TileEnv e;
+    e.d = d;
+    e.c = d.scale_log2;
+    e.ik = drop.inv_keep;
+    e.thr = drop.thr;
+    e.addc = keep_addc(drop.thr);
+    e.lo = lane_offsets(lane);
+    e.tq = lane & 3;
+    return e;
+}
+__device__ __forceinline__ OwnRows own_rows(int wrow, int g, const DropCfg& drop, int b, int H, int h, int Sq, bool mix) {
+    OwnRows r;
+    r.wrow = wrow;
+    r.r0 = wrow + g;
+    r.r1 = r.r0 + 8;
+    r.rm0 = r.rm1 = 0u;
+    if (mix) {
+        r.rm0 = ick_rowmix(drop.seed, drop.site, prob_row(b, H, h, Sq, r.r0));
+        r.rm1 = ick_rowmix(drop.seed, drop.site, prob_row(b, H, h, Sq, r.r1));
+    }
+    return r;
+}
+
+// =============================================================================================================================
+// Chunked kernels: one CTA per (own block, head, image), up to CH tiles resident, re-filled chunk by chunk.  Any length; used
+// when an image has more than CH streamed tiles (the persistent kernels below cover every shape of the reference).
+// =============================================================================================================================
 __global__ void __launch_bounds__(32 * NWMAX, 2)
     fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                bf16* __restrict__ O, float* __restrict__ LSE, Dims d, int ldq, int ldo, int ntc, DropCfg drop) {
@@ -234,20 +489,13 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     init_bars(sm, ntc, &tmK, &tmV);
     if (threadIdx.x == 0) issue_tiles(sm, &tmK, &tmV, 0, min(nt, ntc), h, b);
 
-    const int qi0 = q0 + 16 * warp + g, qi1 = qi0 + 8;
     const bool active = q0 + 16 * warp < d.Sq;
+    const TileEnv env = make_env(d, drop, lane);
+    const OwnRows r = own_rows(q0 + 16 * warp, g, drop, b, d.H, h, d.Sq, true);
     uint32_t qa[2][4];
-    load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, qi0, qi1, d.Sq, d.dh, tq, qa);
-    const LaneOff lo = lane_offsets(lane);
-    const uint32_t rm0 = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, qi0));
-    const uint32_t rm1 = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, qi1));
-    const uint32_t addc = keep_addc(drop.thr);
-    const float c = d.scale_log2;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max of the RAW scores, running sum
-    float o[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-
+    load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
+    FwdAcc acc;
+    fwd_init(acc);
     for (int c0 = 0; c0 < nt; c0 += ntc) {
         const int n = min(ntc, nt - c0);
         if (c0 > 0) {
@@ -257,84 +505,12 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
         const uint32_t parity = (uint32_t)(c0 / ntc) & 1u;
         for (int t = 0; t < n; ++t) {
             mbar_wait(sm.bars + 8 * t, parity);
-            if (!active) continue;
-            const int k0 = (c0 + t) * TK;
-            // causal: tiles entirely beyond this warp's last query contribute nothing
-            if (d.causal && k0 > q0 + 16 * warp + 15) continue;
-            float s[8][4];
-            mma_a_tT<8>(s, qa, sm.t0 + t * TILE_BYTES, 0, lo);
-            // masking is needed only on the ragged last tile and on tiles that cross this warp's causal diagonal
-            if (k0 + TK > d.Sk || (d.causal && k0 + TK - 1 > q0 + 16 * warp)) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int key = k0 + 8 * j + 2 * tq + (e & 1);
-                        const bool vis = key < d.Sk && (!d.causal || key <= (e < 2 ? qi0 : qi1));
-                        if (!vis) s[j][e] = -INFINITY;
-                    }
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
-            }
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-            // a row with no visible key so far keeps m = -inf; use 0 as the exponent base there (all p are ex2(-inf) = 0)
-            const float e0 = mn0 == -INFINITY ? 0.f : mn0 * c, e1 = mn1 == -INFINITY ? 0.f : mn1 * c;
-            const float c0f = ex2(m0 * c - e0), c1f = ex2(m1 * c - e1);
-            l0 *= c0f;
-            l1 *= c1f;
-#pragma unroll
-            for (int nn = 0; nn < 4; ++nn) {
-                o[nn][0] *= c0f; o[nn][1] *= c0f; o[nn][2] *= c1f; o[nn][3] *= c1f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                s[j][0] = ex2(fmaf(s[j][0], c, -e0));
-                s[j][1] = ex2(fmaf(s[j][1], c, -e0));
-                s[j][2] = ex2(fmaf(s[j][2], c, -e1));
-                s[j][3] = ex2(fmaf(s[j][3], c, -e1));
-                l0 += s[j][0] + s[j][1];
-                l1 += s[j][2] + s[j][3];
-            }
-            uint32_t pa[4][4];
-            pack_p<8>(s, pa);
-            if (drop.thr != 0u) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const uint32_t kc = (uint32_t)(k0 + 8 * (2 * kk + jj) + 2 * tq);
-                        pa[kk][2 * jj] &= keep_mask_bf16x2(keep_bits(ick_pairhash(rm0, kc), addc));
-                        pa[kk][2 * jj + 1] &= keep_mask_bf16x2(keep_bits(ick_pairhash(rm1, kc), addc));
-                    }
-            }
-            mma_p_t<8>(o, pa, sm.t1 + t * TILE_BYTES, 0, lo);
-            m0 = mn0;
-            m1 = mn1;
+            if (active) fwd_tile(acc, qa, sm.t0 + t * TILE_BYTES, sm.t1 + t * TILE_BYTES, (c0 + t) * TK, r, env);
         }
     }
-    if (!active) return;
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    bf16* Ob = O + (size_t)b * d.Sq * ldo + h * HD;
-    store_slab(Ob, ldo, qi0, qi1, d.Sq, o, drop.inv_keep / l0, drop.inv_keep / l1, d.dh, tq);
-    if (tq == 0) {
-        float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
-        if (qi0 < d.Sq) L[qi0] = m0 * c + log2f(l0);
-        if (qi1 < d.Sq) L[qi1] = m1 * c + log2f(l1);
-    }
+    if (active) fwd_finish(acc, O + (size_t)b * d.Sq * ldo + h * HD, ldo, LSE + ((size_t)b * d.H + h) * d.Sq, r, env);
 }
 
-// ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * NWMAX, 2)
     bwd_dq_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                   const bf16* __restrict__ O, const bf16* __restrict__ dO, const float* __restrict__ LSE, float* __restrict__ Dsum,
@@ -349,46 +525,19 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     init_bars(sm, ntc, &tmK, &tmV);
     if (threadIdx.x == 0) issue_tiles(sm, &tmK, &tmV, 0, min(nt, ntc), h, b);
 
-    const int qi0 = q0 + 16 * warp + g, qi1 = qi0 + 8;
     const bool active = q0 + 16 * warp < d.Sq;
+    const TileEnv env = make_env(d, drop, lane);
+    const OwnRows r = own_rows(q0 + 16 * warp, g, drop, b, d.H, h, d.Sq, true);
     const bf16* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
     uint32_t qa[2][4], ga[2][4];
-    load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, qi0, qi1, d.Sq, d.dh, tq, qa);
-    load_own(Gb, lddo, qi0, qi1, d.Sq, d.dh, tq, ga);
-    // D = rowsum(dO * O): lane pair (2r, 2r+1) handles the two 16-column halves of own row r
+    load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
+    load_own(Gb, lddo, r.r0, r.r1, d.Sq, d.dh, tq, ga);
     float D0, D1;
-    {
-        const int r = q0 + 16 * warp + (lane >> 1), cb = (lane & 1) * 16;
-        float acc = 0.f;
-        if (r < d.Sq) {
-            const bf16* op = O + ((size_t)b * d.Sq + r) * ldo + h * HD + cb;
-            const bf16* gp = Gb + (size_t)r * lddo + cb;
-            float x[8], y[8];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                ld8(op + 8 * v, x);
-                ld8(gp + 8 * v, y);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (cb + 8 * v + i < d.dh) acc = fmaf(x[i], y[i], acc);
-            }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if ((lane & 1) == 0 && r < d.Sq) Dsum[((size_t)b * d.H + h) * d.Sq + r] = acc;
-        D0 = __shfl_sync(0xffffffffu, acc, 2 * g);
-        D1 = __shfl_sync(0xffffffffu, acc, 2 * g + 16);
-    }
-    const LaneOff lo = lane_offsets(lane);
-    const uint32_t rm0 = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, qi0));
-    const uint32_t rm1 = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, qi1));
-    const uint32_t addc = keep_addc(drop.thr);
+    dq_rowdot(O + (size_t)b * d.Sq * ldo + h * HD, ldo, Gb, lddo, Dsum + ((size_t)b * d.H + h) * d.Sq, r.wrow, d.Sq, d.dh, lane, D0, D1);
     const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
-    const float lse0 = qi0 < d.Sq ? L[qi0] : 0.f, lse1 = qi1 < d.Sq ? L[qi1] : 0.f;
-    const float c = d.scale_log2, ik = drop.inv_keep;
+    const float lse0 = r.r0 < d.Sq ? L[r.r0] : 0.f, lse1 = r.r1 < d.Sq ? L[r.r1] : 0.f;
     float dq[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
-
+    zero16(dq);
     for (int c0 = 0; c0 < nt; c0 += ntc) {
         const int n = min(ntc, nt - c0);
         if (c0 > 0) {
@@ -398,46 +547,24 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
         const uint32_t parity = (uint32_t)(c0 / ntc) & 1u;
         for (int t = 0; t < n; ++t) {
             mbar_wait(sm.bars + 8 * t, parity);
-            if (!active) continue;
-            const uint32_t kt = sm.t0 + t * TILE_BYTES, vt = sm.t1 + t * TILE_BYTES;
-#pragma unroll 1
-            for (int sub = 0; sub < TK / SUB; ++sub) {
-                const int k0 = (c0 + t) * TK + sub * SUB;
-                if (d.causal && k0 > q0 + 16 * warp + 15) break;
-                // keys past Sk are zero rows (TMA fill): they add nothing to dQ = dS K, so only the causal diagonal needs a mask
-                const bool need_mask = d.causal && k0 + SUB - 1 > q0 + 16 * warp;
-                float s[4][4], dp[4][4];
-                mma_a_tT<4>(s, qa, kt, 4 * sub, lo);
-                mma_a_tT<4>(dp, ga, vt, 4 * sub, lo);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (drop.thr != 0u) {
-                        const uint32_t kc = (uint32_t)(k0 + 8 * j + 2 * tq);
-                        const uint32_t kb0 = keep_bits(ick_pairhash(rm0, kc), addc), kb1 = keep_bits(ick_pairhash(rm1, kc), addc);
-                        dp[j][0] = (kb0 & 0x8000u) ? dp[j][0] * ik : 0.f;
-                        dp[j][1] = (kb0 & 0x80000000u) ? dp[j][1] * ik : 0.f;
-                        dp[j][2] = (kb1 & 0x8000u) ? dp[j][2] * ik : 0.f;
-                        dp[j][3] = (kb1 & 0x80000000u) ? dp[j][3] * ik : 0.f;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float p = ex2(fmaf(s[j][e], c, -(e < 2 ? lse0 : lse1)));
-                        if (need_mask && k0 + 8 * j + 2 * tq + (e & 1) > (e < 2 ? qi0 : qi1)) p = 0.f;
-                        s[j][e] = p * (dp[j][e] - (e < 2 ? D0 : D1));
-                    }
-                }
-                uint32_t pa[2][4];
-                pack_p<4>(s, pa);
-                mma_p_t<4>(dq, pa, kt, 4 * sub, lo);
-            }
+            if (active) dq_tile(dq, qa, ga, sm.t0 + t * TILE_BYTES, sm.t1 + t * TILE_BYTES, (c0 + t) * TK, r, lse0, lse1, D0, D1, env);
         }
     }
-    if (!active) return;
-    bf16* dQb = dQ + (size_t)b * d.Sq * lddq + h * HD;
-    store_slab(dQb, lddq, qi0, qi1, d.Sq, dq, d.scale, d.scale, d.dh, tq);
+    if (active) store_slab(dQ + (size_t)b * d.Sq * lddq + h * HD, lddq, r.r0, r.r1, d.Sq, dq, d.scale, d.scale, d.dh, tq);
 }
 
-// ------------------------------------------------------------------------------------------------------------------------
+// fill the per-query scalars of `n` resident tiles starting at query q_first (any number of threads: tid / nthr)
+__device__ __forceinline__ void fill_scalars(float* Ls, float* Ds, uint32_t* Rm, const float* L, const float* Dg, int q_first, int n, int Sq,
+                                             const DropCfg& drop, uint64_t row_base, int tid, int nthr) {
+    for (int i = tid; i < n * TK; i += nthr) {
+        const int qi = q_first + i;
+        const bool ok = qi < Sq;
+        Ls[i] = ok ? L[qi] : 0.f;
+        Ds[i] = ok ? Dg[qi] : 0.f;
+        Rm[i] = ick_rowmix(drop.seed, drop.site, row_base + (uint64_t)qi);
+    }
+}
+
 __global__ void __launch_bounds__(32 * NWMAX, 2)
     bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                    const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
@@ -456,100 +583,252 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     init_bars(sm, ntc, &tmQ, &tmG);
     if (threadIdx.x == 0) issue_tiles(sm, &tmQ, &tmG, tbeg, min(nt - tbeg, ntc), h, b);
 
-    const int kj0 = j0 + 16 * warp + g, kj1 = kj0 + 8;
     const bool active = j0 + 16 * warp < d.Sk;
+    const TileEnv env = make_env(d, drop, lane);
+    const OwnRows r = own_rows(j0 + 16 * warp, g, drop, b, d.H, h, d.Sq, false);
     uint32_t ka[2][4], va[2][4];
-    load_own(K + (size_t)b * d.Sk * ldk + h * HD, ldk, kj0, kj1, d.Sk, d.dh, tq, ka);
-    load_own(V + (size_t)b * d.Sk * ldv + h * HD, ldv, kj0, kj1, d.Sk, d.dh, tq, va);
-    const LaneOff lo = lane_offsets(lane);
+    load_own(K + (size_t)b * d.Sk * ldk + h * HD, ldk, r.r0, r.r1, d.Sk, d.dh, tq, ka);
+    load_own(V + (size_t)b * d.Sk * ldv + h * HD, ldv, r.r0, r.r1, d.Sk, d.dh, tq, va);
     const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
     const float* Dg = Dsum + ((size_t)b * d.H + h) * d.Sq;
-    // Lanes g and g^1 own keys of the same dropout pair and see the same queries: each computes the pair hashes of ONE of its
-    // two key rows (even g: kj0, odd g: kj1) and receives the other from its partner (lane ^ 4).
     const bool odd = (g & 1) != 0;
-    const uint32_t mykey = (uint32_t)(odd ? kj1 : kj0);
-    const uint32_t bit0 = odd ? 0x80000000u : 0x8000u;  // keep bit of this lane's key parity
-    const uint32_t addc = keep_addc(drop.thr);
-    const float c = d.scale_log2, ik = drop.inv_keep;
     float dk[4][4], dv[4][4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-        dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
-        dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
-    }
+    zero16(dk);
+    zero16(dv);
     for (int c0 = tbeg; c0 < nt; c0 += ntc) {
         const int n = min(ntc, nt - c0);
         if (c0 > tbeg) {
             __syncthreads();
             if (threadIdx.x == 0) issue_tiles(sm, &tmQ, &tmG, c0, n, h, b);
         }
-        for (int i = threadIdx.x; i < n * TK; i += blockDim.x) {
-            const int qi = c0 * TK + i;
-            const bool ok = qi < d.Sq;
-            Ls[i] = ok ? L[qi] : 0.f;
-            Ds[i] = ok ? Dg[qi] : 0.f;
-            Rm[i] = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, qi));
-        }
+        fill_scalars(Ls, Ds, Rm, L, Dg, c0 * TK, n, d.Sq, drop, prob_row(b, d.H, h, d.Sq, 0), threadIdx.x, blockDim.x);
         __syncthreads();
         const uint32_t parity = (uint32_t)((c0 - tbeg) / ntc) & 1u;
         for (int t = 0; t < n; ++t) {
             mbar_wait(sm.bars + 8 * t, parity);
-            if (!active) continue;
-            const uint32_t qt = sm.t0 + t * TILE_BYTES, gt = sm.t1 + t * TILE_BYTES;
-#pragma unroll 1
-            for (int sub = 0; sub < TK / SUB; ++sub) {
-                const int q0 = (c0 + t) * TK + sub * SUB;  // first query of the sub-step
-                if (d.causal && q0 + SUB - 1 < j0 + 16 * warp) continue;  // every query precedes every key of this warp
-                // queries past Sq are zero rows of Q and dO (TMA fill) and add nothing; own keys past Sk are never stored
-                const bool need_mask = d.causal && j0 + 16 * warp + 15 > q0;
-                const float* ls = Ls + t * TK + sub * SUB + 2 * tq;
-                const float* ds = Ds + t * TK + sub * SUB + 2 * tq;
-                const uint32_t* rm = Rm + t * TK + sub * SUB + 2 * tq;
-                float st[4][4], dpt[4][4];
-                mma_a_tT<4>(st, ka, qt, 4 * sub, lo);
-                mma_a_tT<4>(dpt, va, gt, 4 * sub, lo);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 l2 = *reinterpret_cast<const float2*>(ls + 8 * j);
-                    const float2 d2 = *reinterpret_cast<const float2*>(ds + 8 * j);
-                    uint32_t hq0a = 0, hq0b = 0, hq1a = 0, hq1b = 0;  // keep bits of (query 0/1 of the pair, key row a = kj0 / b = kj1)
-                    if (drop.thr != 0u) {
-                        const uint2 r2 = *reinterpret_cast<const uint2*>(rm + 8 * j);
-                        const uint32_t m0 = keep_bits(ick_pairhash(r2.x, mykey), addc), m1 = keep_bits(ick_pairhash(r2.y, mykey), addc);
-                        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, m0, 4), o1 = __shfl_xor_sync(0xffffffffu, m1, 4);
-                        hq0a = odd ? o0 : m0; hq0b = odd ? m0 : o0;
-                        hq1a = odd ? o1 : m1; hq1b = odd ? m1 : o1;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int qi = q0 + 8 * j + 2 * tq + (e & 1);
-                        float p = ex2(fmaf(st[j][e], c, -((e & 1) ? l2.y : l2.x)));
-                        if (need_mask && (e < 2 ? kj0 : kj1) > qi) p = 0.f;
-                        float gp = dpt[j][e];
-                        float pm = p;
-                        if (drop.thr != 0u) {
-                            const uint32_t kb = (e == 0) ? hq0a : (e == 1) ? hq1a : (e == 2) ? hq0b : hq1b;
-                            const bool keep = (kb & bit0) != 0u;
-                            pm = keep ? p : 0.f;
-                            gp = keep ? gp * ik : 0.f;
-                        }
-                        st[j][e] = pm;                                   // P^T with dropout (1/keep applied at the store) -> dV
-                        dpt[j][e] = p * (gp - ((e & 1) ? d2.y : d2.x));  // dS^T -> dK
-                    }
-                }
-                uint32_t pa[2][4];
-                pack_p<4>(st, pa);
-                mma_p_t<4>(dv, pa, gt, 4 * sub, lo);
-                pack_p<4>(dpt, pa);
-                mma_p_t<4>(dk, pa, qt, 4 * sub, lo);
-            }
+            if (active)
+                dkv_tile(dk, dv, ka, va, sm.t0 + t * TILE_BYTES, sm.t1 + t * TILE_BYTES, (c0 + t) * TK, Ls + t * TK, Ds + t * TK, Rm + t * TK, r,
+                         odd, env);
         }
     }
     if (!active) return;
-    bf16* dKb = dK + (size_t)b * d.Sk * lddk + h * HD;
-    bf16* dVb = dV + (size_t)b * d.Sk * lddv + h * HD;
-    store_slab(dKb, lddk, kj0, kj1, d.Sk, dk, d.scale, d.scale, d.dh, tq);
-    store_slab(dVb, lddv, kj0, kj1, d.Sk, dv, ik, ik, d.dh, tq);
+    store_slab(dK + (size_t)b * d.Sk * lddk + h * HD, lddk, r.r0, r.r1, d.Sk, dk, d.scale, d.scale, d.dh, tq);
+    store_slab(dV + (size_t)b * d.Sk * lddv + h * HD, lddv, r.r0, r.r1, d.Sk, dv, env.ik, env.ik, d.dh, tq);
+}
+
+// =============================================================================================================================
+// Persistent kernels: one CTA per SM, PNW compute warps + one producer warp.  A work item is one (image, head): all of its
+// streamed tiles (<= CH) form one pipeline stage; the producer keeps `nstage` items in flight (TMA into the stage as soon as
+// every compute warp has released it), so the copies of item i+1.. overlap the math of item i and nothing but the very first
+// load is exposed.  The 16-row own slabs of successive items are dealt round-robin to the compute warps (global slab number
+// modulo PNW), which keeps the warps balanced to within one slab over the whole launch.
+// =============================================================================================================================
+constexpr int PNW = 15;
+constexpr int PBAR = CH + 2;  // mbarriers of a stage: full[CH] (one per tile), scalars-ready, empty
+struct Pipe {
+    uint32_t bars, data, stage_bytes;
+    uint8_t* gen;  // generic pointer to `data`
+    int ntc;
+    __device__ __forceinline__ uint32_t full(int s, int t) const { return bars + 8 * (s * PBAR + t); }
+    __device__ __forceinline__ uint32_t sfull(int s) const { return bars + 8 * (s * PBAR + CH); }
+    __device__ __forceinline__ uint32_t empty(int s) const { return bars + 8 * (s * PBAR + CH + 1); }
+    __device__ __forceinline__ uint32_t t0(int s) const { return data + s * stage_bytes; }
+    __device__ __forceinline__ uint32_t t1(int s) const { return t0(s) + ntc * TILE_BYTES; }
+    __device__ __forceinline__ float* scal(int s) const { return (float*)(gen + (size_t)s * stage_bytes + 2 * ntc * TILE_BYTES); }
+};
+__device__ __forceinline__ Pipe make_pipe(uint8_t* raw, int ntc, int nstage, uint32_t stage_bytes, const CUtensorMap* a, const CUtensorMap* b) {
+    uint8_t* p = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    Pipe pp;
+    pp.bars = smem_u32(p);
+    pp.data = pp.bars + 1024;
+    pp.gen = p + 1024;
+    pp.stage_bytes = stage_bytes;
+    pp.ntc = ntc;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(b) : "memory");
+        for (int s = 0; s < nstage; ++s) {
+            for (int t = 0; t < ntc; ++t) mbar_init(pp.full(s, t), 1);
+            mbar_init(pp.sfull(s), 32);
+            mbar_init(pp.empty(s), PNW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    return pp;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void produce_item(const Pipe& pp, int s, const CUtensorMap* a, const CUtensorMap* b2, int h, int b) {
+    for (int t = 0; t < pp.ntc; ++t) {
+        const uint32_t bar = pp.full(s, t);
+        mbar_expect_tx(bar, 2 * TILE_BYTES);
+        tma_load_3d(pp.t0(s) + t * TILE_BYTES, a, bar, h * HD, t * TK, b);
+        tma_load_3d(pp.t1(s) + t * TILE_BYTES, b2, bar, h * HD, t * TK, b);
+    }
+}
+// first own slab of compute warp `warp` in local item `li` (slabs are numbered globally: li * nslabs + slab)
+__device__ __forceinline__ int first_slab(int li, int nslabs, int warp) { return (warp + PNW - (int)(((long long)li * nslabs) % PNW)) % PNW; }
+
+struct PArgs {
+    Dims d;
+    int nslabs, ntc, nstage;
+    uint32_t stage_bytes;
+};
+
+__global__ void __launch_bounds__(32 * (PNW + 1), 1)
+    fwd_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
+                bf16* __restrict__ O, float* __restrict__ LSE, PArgs a, int ldq, int ldo, DropCfg drop) {
+    extern __shared__ uint8_t smem_raw[];
+    const Dims& d = a.d;
+    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
+    ick_resolve_seed(drop);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int n_items = d.B * d.H;
+    if (warp == PNW) {
+        if (lane == 0) {
+            int li = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+                const int s = li % a.nstage;
+                mbar_wait(pp.empty(s), ((uint32_t)(li / a.nstage) & 1u) ^ 1u);
+                produce_item(pp, s, &tmK, &tmV, item % d.H, item / d.H);
+            }
+        }
+        return;
+    }
+    const TileEnv env = make_env(d, drop, lane);
+    int li = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const int s = li % a.nstage, b = item / d.H, h = item % d.H;
+        const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
+        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+            const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, true);
+            uint32_t qa[2][4];
+            load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
+            FwdAcc acc;
+            fwd_init(acc);
+            const int nt = d.causal ? (min(d.Sk, 16 * slab + 16) + TK - 1) / TK : a.ntc;
+            for (int t = 0; t < nt; ++t) {
+                mbar_wait(pp.full(s, t), ph);
+                fwd_tile(acc, qa, pp.t0(s) + t * TILE_BYTES, pp.t1(s) + t * TILE_BYTES, t * TK, r, env);
+            }
+            fwd_finish(acc, O + (size_t)b * d.Sq * ldo + h * HD, ldo, LSE + ((size_t)b * d.H + h) * d.Sq, r, env);
+        }
+        // Every warp passes through every item in order (a warp without a slab here still waits for the item's first tile), so
+        // no warp can release a stage for the item that re-uses it before the producer has started that item.
+        mbar_wait(pp.full(s, 0), ph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pp.empty(s));
+    }
+}
+
+__global__ void __launch_bounds__(32 * (PNW + 1), 1)
+    bwd_dq_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
+                   const bf16* __restrict__ O, const bf16* __restrict__ dO, const float* __restrict__ LSE, float* __restrict__ Dsum,
+                   bf16* __restrict__ dQ, PArgs a, int ldq, int ldo, int lddo, int lddq, DropCfg drop) {
+    extern __shared__ uint8_t smem_raw[];
+    const Dims& d = a.d;
+    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
+    ick_resolve_seed(drop);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int n_items = d.B * d.H;
+    if (warp == PNW) {
+        if (lane == 0) {
+            int li = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+                const int s = li % a.nstage;
+                mbar_wait(pp.empty(s), ((uint32_t)(li / a.nstage) & 1u) ^ 1u);
+                produce_item(pp, s, &tmK, &tmV, item % d.H, item / d.H);
+            }
+        }
+        return;
+    }
+    const TileEnv env = make_env(d, drop, lane);
+    int li = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const int s = li % a.nstage, b = item / d.H, h = item % d.H;
+        const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
+        const bf16* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
+        const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
+        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+            const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, true);
+            uint32_t qa[2][4], ga[2][4];
+            load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
+            load_own(Gb, lddo, r.r0, r.r1, d.Sq, d.dh, tq, ga);
+            float D0, D1;
+            dq_rowdot(O + (size_t)b * d.Sq * ldo + h * HD, ldo, Gb, lddo, Dsum + ((size_t)b * d.H + h) * d.Sq, r.wrow, d.Sq, d.dh, lane, D0, D1);
+            const float lse0 = r.r0 < d.Sq ? L[r.r0] : 0.f, lse1 = r.r1 < d.Sq ? L[r.r1] : 0.f;
+            float dq[4][4];
+            zero16(dq);
+            const int nt = d.causal ? (min(d.Sk, 16 * slab + 16) + TK - 1) / TK : a.ntc;
+            for (int t = 0; t < nt; ++t) {
+                mbar_wait(pp.full(s, t), ph);
+                dq_tile(dq, qa, ga, pp.t0(s) + t * TILE_BYTES, pp.t1(s) + t * TILE_BYTES, t * TK, r, lse0, lse1, D0, D1, env);
+            }
+            store_slab(dQ + (size_t)b * d.Sq * lddq + h * HD, lddq, r.r0, r.r1, d.Sq, dq, d.scale, d.scale, d.dh, tq);
+        }
+        mbar_wait(pp.full(s, 0), ph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pp.empty(s));
+    }
+}
+
+__global__ void __launch_bounds__(32 * (PNW + 1), 1)
+    bwd_dkv_pkernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
+                    const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
+                    bf16* __restrict__ dV, PArgs a, int ldk, int ldv, int lddk, int lddv, DropCfg drop) {
+    extern __shared__ uint8_t smem_raw[];
+    const Dims& d = a.d;
+    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmQ, &tmG);
+    ick_resolve_seed(drop);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int n_items = d.B * d.H;
+    if (warp == PNW) {  // the whole producer warp: lane 0 issues the copies, all lanes fill the per-query scalars of the stage
+        int li = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+            const int s = li % a.nstage, b = item / d.H, h = item % d.H;
+            mbar_wait(pp.empty(s), ((uint32_t)(li / a.nstage) & 1u) ^ 1u);
+            if (lane == 0) produce_item(pp, s, &tmQ, &tmG, h, b);
+            float* Ls = pp.scal(s);
+            float* Ds = Ls + a.ntc * TK;
+            uint32_t* Rm = (uint32_t*)(Ds + a.ntc * TK);
+            fill_scalars(Ls, Ds, Rm, LSE + ((size_t)b * d.H + h) * d.Sq, Dsum + ((size_t)b * d.H + h) * d.Sq, 0, a.ntc, d.Sq, drop,
+                         prob_row(b, d.H, h, d.Sq, 0), lane, 32);
+            mbar_arrive(pp.sfull(s));  // release: this lane's scalars are visible to whoever observes the phase
+        }
+        return;
+    }
+    const TileEnv env = make_env(d, drop, lane);
+    const bool odd = (g & 1) != 0;
+    int li = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
+        const int s = li % a.nstage, b = item / d.H, h = item % d.H;
+        const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
+        const float* Ls = pp.scal(s);
+        const float* Ds = Ls + a.ntc * TK;
+        const uint32_t* Rm = (const uint32_t*)(Ds + a.ntc * TK);
+        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+            const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, false);
+            uint32_t ka[2][4], va[2][4];
+            load_own(K + (size_t)b * d.Sk * ldk + h * HD, ldk, r.r0, r.r1, d.Sk, d.dh, tq, ka);
+            load_own(V + (size_t)b * d.Sk * ldv + h * HD, ldv, r.r0, r.r1, d.Sk, d.dh, tq, va);
+            float dk[4][4], dv[4][4];
+            zero16(dk);
+            zero16(dv);
+            mbar_wait(pp.sfull(s), ph);
+            // causal: queries before the warp's first key see none of its keys
+            for (int t = d.causal ? (16 * slab) / TK : 0; t < a.ntc; ++t) {
+                mbar_wait(pp.full(s, t), ph);
+                dkv_tile(dk, dv, ka, va, pp.t0(s) + t * TILE_BYTES, pp.t1(s) + t * TILE_BYTES, t * TK, Ls + t * TK, Ds + t * TK, Rm + t * TK, r, odd,
+                         env);
+            }
+            store_slab(dK + (size_t)b * d.Sk * lddk + h * HD, lddk, r.r0, r.r1, d.Sk, dk, d.scale, d.scale, d.dh, tq);
+            store_slab(dV + (size_t)b * d.Sk * lddv + h * HD, lddv, r.r0, r.r1, d.Sk, dv, env.ik, env.ik, d.dh, tq);
+        }
+        mbar_wait(pp.full(s, 0), ph);
+        mbar_wait(pp.sfull(s), ph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pp.empty(s));
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
@@ -602,11 +881,39 @@ void split_own(int S, int* nctas, int* nw) {
 }
 int smem_bytes(int ntc, bool scalars) { return 1024 + 1024 + 2 * ntc * TILE_BYTES + (scalars ? 3 * ntc * TK * 4 : 0); }
 
+constexpr int SMEM_MAX = 232448;  // 227 KiB: largest dynamic shared memory of a CTA on sm_100
+// persistent-kernel plan for `ntc` streamed tiles per item: stage size and stage count (0 = does not fit, use the chunked kernel)
+void plan_pipe(int ntc, bool scalars, PArgs* a) {
+    a->ntc = ntc;
+    a->stage_bytes = (uint32_t)((2 * ntc * TILE_BYTES + (scalars ? 3 * ntc * TK * 4 : 0) + 1023) / 1024 * 1024);
+    int ns = ntc <= CH ? (SMEM_MAX - 2048) / (int)a->stage_bytes : 0;
+    a->nstage = ns > 6 ? 6 : (ns < 2 ? 0 : ns);
+}
+int pipe_smem(const PArgs& a) { return 2048 + a.nstage * (int)a.stage_bytes; }
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+bool use_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_ATTN_PERSISTENT");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <typename K>
-int set_smem(K kernel) {
+int set_smem(K kernel, bool persistent = false) {
     static bool done = false;  // one static per kernel
     if (!done) {
-        const int bytes = smem_bytes(CH, true);
+        const int bytes = persistent ? SMEM_MAX : smem_bytes(CH, true);
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
             ick_set_error("attention: cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed", bytes);
             return ICK_ERR_CUDA;
@@ -621,15 +928,25 @@ int set_smem(K kernel) {
 int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk,
                     int ldv, int ldo, int causal, DropCfg dc, cudaStream_t stream) {
     ICK_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)Q & 3) == 0, "mha_fwd: operands must be 16-byte aligned");
-    int rc = set_smem(fwd_kernel);
-    if (rc) return rc;
+    int rc;
     Dims d = make_dims(B, H, Sq, Sk, dh, causal);
     CUtensorMap tmK, tmV;
     if ((rc = make_tmap3(&tmK, K, H, Sk, B, ldk))) return rc;
     if ((rc = make_tmap3(&tmV, V, H, Sk, B, ldv))) return rc;
+    const int nt = (Sk + TK - 1) / TK, ntc = nt < CH ? nt : CH;
+    PArgs pa;
+    pa.d = d;
+    pa.nslabs = (Sq + 15) / 16;
+    plan_pipe(nt, false, &pa);
+    if (pa.nstage && use_persistent()) {
+        if ((rc = set_smem(fwd_pkernel, true))) return rc;
+        const int grid = B * H < num_sms() ? B * H : num_sms();
+        fwd_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
+        return ick_check_launch("mha_fwd_mma(persistent)");
+    }
+    if ((rc = set_smem(fwd_kernel))) return rc;
     int nctas, nw;
     split_own(Sq, &nctas, &nw);
-    const int nt = (Sk + TK - 1) / TK, ntc = nt < CH ? nt : CH;
     dim3 grid(nctas, H, B);
     fwd_kernel<<<grid, 32 * nw, smem_bytes(ntc, false), stream>>>(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, d, ldq, ldo, ntc, dc);
     return ick_check_launch("mha_fwd_mma");
@@ -641,24 +958,43 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     ICK_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)Q & 15) == 0 && ((uintptr_t)dO & 15) == 0 &&
                     ((uintptr_t)O & 15) == 0,
                 "mha_bwd: operands must be 16-byte aligned");
-    int rc = set_smem(bwd_dq_kernel);
-    if (rc) return rc;
-    if ((rc = set_smem(bwd_dkv_kernel))) return rc;
+    int rc;
     Dims d = make_dims(B, H, Sq, Sk, dh, causal);
     CUtensorMap tmK, tmV, tmQ, tmG;
     if ((rc = make_tmap3(&tmK, K, H, Sk, B, ldk))) return rc;
     if ((rc = make_tmap3(&tmV, V, H, Sk, B, ldv))) return rc;
     if ((rc = make_tmap3(&tmQ, Q, H, Sq, B, ldq))) return rc;
     if ((rc = make_tmap3(&tmG, dO, H, Sq, B, lddo))) return rc;
+    const int grid = B * H < num_sms() ? B * H : num_sms();
     int nctas, nw;
-    split_own(Sq, &nctas, &nw);
     int nt = (Sk + TK - 1) / TK, ntc = nt < CH ? nt : CH;
-    bwd_dq_kernel<<<dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, false), stream>>>(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse,
+    PArgs pa;
+    pa.d = d;
+    pa.nslabs = (Sq + 15) / 16;
+    plan_pipe(nt, false, &pa);
+    if (pa.nstage && use_persistent()) {
+        if ((rc = set_smem(bwd_dq_pkernel, true))) return rc;
+        bwd_dq_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse, dsum,
+                                                                        (bf16*)dQ, pa, ldq, ldo, lddo, lddq, dc);
+    } else {
+        if ((rc = set_smem(bwd_dq_kernel))) return rc;
+        split_own(Sq, &nctas, &nw);
+        bwd_dq_kernel<<<dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, false), stream>>>(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse,
                                                                                  dsum, (bf16*)dQ, d, ldq, ldo, lddo, lddq, ntc, dc);
+    }
     if ((rc = ick_check_launch("mha_bwd_mma(dq)"))) return rc;
-    split_own(Sk, &nctas, &nw);
     nt = (Sq + TK - 1) / TK;
     ntc = nt < CH ? nt : CH;
+    pa.nslabs = (Sk + 15) / 16;
+    plan_pipe(nt, true, &pa);
+    if (pa.nstage && use_persistent()) {
+        if ((rc = set_smem(bwd_dkv_pkernel, true))) return rc;
+        bwd_dkv_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
+                                                                         pa, ldk, ldv, lddk, lddv, dc);
+        return ick_check_launch("mha_bwd_mma(dkv, persistent)");
+    }
+    if ((rc = set_smem(bwd_dkv_kernel))) return rc;
+    split_own(Sk, &nctas, &nw);
     bwd_dkv_kernel<<<dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, true), stream>>>(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK,
                                                                                  (bf16*)dV, d, ldk, ldv, lddk, lddv, ntc, dc);
     return ick_check_launch("mha_bwd_mma(dkv)");

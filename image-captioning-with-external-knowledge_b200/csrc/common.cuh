@@ -99,15 +99,16 @@ __host__ __device__ __forceinline__ uint32_t ick_rowmix(uint32_t seed, uint32_t 
     h ^= h >> 16;
     return h;
 }
-__host__ __device__ __forceinline__ uint32_t ick_pairhash(uint32_t rowmix, uint32_t col) {
-    uint32_t h = ((col >> 1) * 0x9E3779B1u) ^ rowmix;
-    h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 12;
-    h *= 0x297A2D39u;
-    h ^= h >> 15;
+// hash of column pair `pair` (= col >> 1) of a row: the row mix is already a full avalanche of (seed, site, row), so one
+// add-multiply, one xor-shift and one multiply are enough for dropout-quality bits in both 15-bit fields (checked in
+// tests/test_host_wiring.py: keep rate, neighbour correlations along rows / columns / pairs)
+__host__ __device__ __forceinline__ uint32_t ick_pairhash_idx(uint32_t rowmix, uint32_t pair) {
+    uint32_t h = rowmix + pair * 0x9E3779B1u;
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
     return h;
 }
+__host__ __device__ __forceinline__ uint32_t ick_pairhash(uint32_t rowmix, uint32_t col) { return ick_pairhash_idx(rowmix, col >> 1); }
 __host__ __device__ __forceinline__ bool ick_keep_lo(uint32_t pairhash, uint32_t thr) { return (pairhash & 0x7FFFu) >= thr; }
 __host__ __device__ __forceinline__ bool ick_keep_hi(uint32_t pairhash, uint32_t thr) { return ((pairhash >> 16) & 0x7FFFu) >= thr; }
 // multiplier (0 or 1/(1-p)) of column `col` given the hash of its pair

@@ -7,6 +7,7 @@
 //   pointer heads       fc_entity / fc_fact as a bilinear form, K/models.py:440-452 (no (T,B,E,300) tensor)
 // Row layout everywhere: (batch, position) rows of `ld` elements, logical width D, pad columns [D, ld) zero.
 #include "common.cuh"
+#include "pointer_internal.h"
 #include "ickb200.h"
 
 namespace {
@@ -696,6 +697,10 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
                                int dt, int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream) {
     ICK_REQUIRE(D <= ld && ld % 8 == 0 && ((D + 7) & ~7) <= ld, "pointer_fwd: bad sizes D=%d ld=%d", D, ld);
     if (B * Tn * S == 0) return ICK_OK;
+    if (dt == ICK_BF16 && Tn >= 16) {  // tensor-core path (teacher-forced forward); single-step decode stays on the CUDA cores
+        const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, ld, ldscores, col0, lag, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     const int Dp = (D + 7) & ~7;
     const size_t smem = (size_t)PT_T * Dp * sizeof(float);
     dim3 grid((S + 127) / 128, (Tn + PT_T - 1) / PT_T, B);
@@ -714,6 +719,10 @@ extern "C" int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, c
                                int lag, cudaStream_t stream) {
     ICK_REQUIRE(D <= ld, "pointer_bwd: bad sizes");
     if (B * T * S == 0) return ICK_OK;
+    if (dt == ICK_BF16 && T >= 16) {
+        const int rc = ick_pointer_bwd_mma(dS, h, ctx, w, first_t, dCtx, dH, gflat, w_off, bias_off, B, T, S, D, ld, ldds, col0, lag, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     dim3 g1((S + 127) / 128, (D + PB_D - 1) / PB_D, B), g2((T + 127) / 128, (D + PB_D - 1) / PB_D, B);
     if (dt == ICK_F32) {
         pointer_bwd_ctx_kernel<float><<<g1, 128, 0, stream>>>((const float*)dS, (const float*)h, w, first_t, dCtx, gflat, bias_off, T, S, D,

@@ -1,0 +1,287 @@
+// Pointer heads (fc_entity / fc_fact over h * ctx, get_scores K/models.py:440-452) as per-image bf16 GEMMs on the tensor
+// cores (mma.sync m16n8k16, fp32 accumulate):
+//   fwd : scores[b,t,col0+s] = bias + mask(t,s) * sum_d (h[b,t,d] w[d]) ctx[b,s,d]           one CTA per (64 slots, image)
+//   bwd : G  = (mask*dS)   ctx   -> dH[b,t,:]   += w * G,   dw += sum_{b,t} h * G              one CTA per (64 features, image)
+//         C2 = (mask*dS)^T h     -> dCtx[b,s,:] += w * C2,  dbias += sum dS (unmasked)
+// mask(t,s) = first_t[b,s] < t + lag for the fact head (the indicator multiplies fc_fact's INPUT, so the bias survives), 1 for
+// the entity head.  Operand tiles are staged in shared memory with row strides that are odd multiples of 16 bytes, which makes
+// every ldmatrix conflict-free; (mask*dS)^T is never materialised - its A fragments come from ldmatrix.trans of the dS tile.
+#include "mma.cuh"
+#include "pointer_internal.h"
+
+namespace {
+
+constexpr int NT = 256;   // threads per CTA (8 warps)
+constexpr int CW = 64;    // slots (fwd) / feature columns (bwd) per CTA
+constexpr int CLD = CW + 8;
+constexpr int SMEM_MAX = 232448;
+
+__device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
+
+// A fragment (16 rows x 16 k) of a row-major [rows][ld] tile: rows r0.., k columns k0..
+__device__ __forceinline__ void a_frag(uint32_t* a, const bf16* tile, int ld, int r0, int k0, int lane) {
+    ick_ldsm_x4(a[0], a[1], a[2], a[3], ick_smem_u32(tile + (size_t)(r0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * ld + k0 + 8 * (lane >> 4)));
+}
+// A fragment of the TRANSPOSE of a row-major tile: A[m][k] = tile[k0 + k][m0 + m]
+__device__ __forceinline__ void a_frag_t(uint32_t* a, const bf16* tile, int ld, int m0, int k0, int lane) {
+    const int mi = lane >> 3;
+    ick_ldsm_x4_trans(a[0], a[1], a[2], a[3], ick_smem_u32(tile + (size_t)(k0 + (lane & 7) + 8 * (mi >> 1)) * ld + m0 + 8 * (mi & 1)));
+}
+// B fragments of two n-tiles (16 n) from a tile stored [n][k] (k contiguous): {b0,b1} of n-tile 0, {b0,b1} of n-tile 1
+__device__ __forceinline__ void b_frag_nk(uint32_t* r, const bf16* tile, int ld, int n0, int k0, int lane) {
+    ick_ldsm_x4(r[0], r[1], r[2], r[3], ick_smem_u32(tile + (size_t)(n0 + (lane & 7) + 8 * (lane >> 4)) * ld + k0 + 8 * ((lane >> 3) & 1)));
+}
+// same from a tile stored [k][n] (n contiguous)
+__device__ __forceinline__ void b_frag_kn(uint32_t* r, const bf16* tile, int ld, int n0, int k0, int lane) {
+    ick_ldsm_x4_trans(r[0], r[1], r[2], r[3], ick_smem_u32(tile + (size_t)(k0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * ld + n0 + 8 * (lane >> 4)));
+}
+
+__global__ void __launch_bounds__(NT) pointer_fwd_mma_kernel(const bf16* __restrict__ h, const bf16* __restrict__ ctx, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const int* __restrict__ first_t,
+                                                             float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
+                                                             int col0, int lag, int Tp, int KP) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int PLD = KP + 8;
+    bf16* hw = reinterpret_cast<bf16*>(smem);  // [Tp][PLD]  h * w
+    bf16* cs = hw + (size_t)Tp * PLD;           // [CW][PLD]  ctx rows of this slot tile
+    const int b = blockIdx.y, s0 = blockIdx.x * CW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int kc = KP / 8;
+    for (int idx = threadIdx.x; idx < Tp * kc; idx += NT) {
+        const int t = idx / kc, c = (idx % kc) * 8;
+        uint4 out = zero4();
+        if (t < Tn) {
+            float x[8];
+            ld8(h + ((size_t)b * Tn + t) * ld + c, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = c + i < D ? x[i] * __ldg(w + c + i) : 0.f;
+            st8(reinterpret_cast<bf16*>(&out), x);
+        }
+        *reinterpret_cast<uint4*>(hw + (size_t)t * PLD + c) = out;
+    }
+    for (int idx = threadIdx.x; idx < CW * kc; idx += NT) {
+        const int s = idx / kc, c = (idx % kc) * 8;
+        uint4 v = zero4();
+        if (s0 + s < S) v = *reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s0 + s) * ld + c);
+        *reinterpret_cast<uint4*>(cs + (size_t)s * PLD + c) = v;
+    }
+    __syncthreads();
+    const float bv = bias[0];
+    for (int mt = warp; mt < Tp / 16; mt += NT / 32) {
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int k0 = 0; k0 < KP; k0 += 16) {
+            uint32_t a[4];
+            a_frag(a, hw, PLD, 16 * mt, k0, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t r[4];
+                b_frag_nk(r, cs, PLD, 16 * np, k0, lane);
+                ick_mma16816(acc[2 * np], a, r[0], r[1]);
+                ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int t = 16 * mt + g + (x >> 1) * 8, s = s0 + 8 * j + 2 * tq + (x & 1);
+                if (t < Tn && s < S) {
+                    const bool on = first_t == nullptr || first_t[(size_t)b * S + s] < t0 + t + lag;
+                    scores[((size_t)b * Tn + t) * lds + col0 + s] = (on ? acc[j][x] : 0.f) + bv;
+                }
+            }
+    }
+}
+
+__global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restrict__ dS, const bf16* __restrict__ h, const bf16* __restrict__ ctx,
+                                                             const float* __restrict__ w, const int* __restrict__ first_t,
+                                                             float* __restrict__ dCtx, bf16* __restrict__ dH, float* __restrict__ gflat,
+                                                             int w_off, int bias_off, int T, int S, int D, int ld, int ldds, int col0, int lag,
+                                                             int Tp, int Sp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int DLD = Sp + 8;
+    bf16* ds = reinterpret_cast<bf16*>(smem);  // [Tp][DLD]  mask * dS of this image
+    bf16* cs = ds + (size_t)Tp * DLD;           // [Sp][CLD]  ctx columns d0..d0+63
+    bf16* hs = cs + (size_t)Sp * CLD;           // [Tp][CLD]  h   columns d0..d0+63
+    float* red = reinterpret_cast<float*>(hs + (size_t)Tp * CLD);  // [8][CW] per-warp dw partials
+    int* ft = reinterpret_cast<int*>(red + 8 * CW);                // [Sp]
+    const int d0 = blockIdx.x * CW, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    for (int s = threadIdx.x; s < Sp; s += NT) ft[s] = (first_t != nullptr && s < S) ? first_t[(size_t)b * S + s] : -0x40000000;
+    for (int idx = threadIdx.x; idx < Sp * (CW / 8); idx += NT) {
+        const int s = idx / (CW / 8), c = (idx % (CW / 8)) * 8;
+        uint4 v = zero4();
+        if (s < S && d0 + c < ld) v = *reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s) * ld + d0 + c);
+        *reinterpret_cast<uint4*>(cs + (size_t)s * CLD + c) = v;
+    }
+    for (int idx = threadIdx.x; idx < Tp * (CW / 8); idx += NT) {
+        const int t = idx / (CW / 8), c = (idx % (CW / 8)) * 8;
+        uint4 v = zero4();
+        if (t < T && d0 + c < ld) v = *reinterpret_cast<const uint4*>(h + ((size_t)b * T + t) * ld + d0 + c);
+        *reinterpret_cast<uint4*>(hs + (size_t)t * CLD + c) = v;
+    }
+    __syncthreads();  // ft visible
+    // dS tile (+ mask); the slice may start at an odd column (col0 = V + E), so pairs are used only when 4-byte aligned
+    float bsum = 0.f;
+    const bool pair_ok = ((col0 | ldds) & 1) == 0;
+    const int sp2 = Sp / 2;
+    for (int idx = threadIdx.x; idx < Tp * sp2; idx += NT) {
+        const int t = idx / sp2, s = (idx % sp2) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (t < T) {
+            const bf16* src = dS + ((size_t)b * T + t) * ldds + col0 + s;
+            if (pair_ok && s + 1 < S) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+                v0 = f.x;
+                v1 = f.y;
+            } else {
+                if (s < S) v0 = __bfloat162float(src[0]);
+                if (s + 1 < S) v1 = __bfloat162float(src[1]);
+            }
+            bsum += v0 + v1;
+            if (!(ft[s] < t + lag)) v0 = 0.f;
+            if (!(ft[s + 1] < t + lag)) v1 = 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(ds + (size_t)t * DLD + s) = ick_pack2(v0, v1);
+    }
+    if (blockIdx.x == 0) {  // dbias = sum of the UNMASKED dS
+        bsum = warp_sum(bsum);
+        if (lane == 0) atomicAdd(gflat + bias_off, bsum);
+    }
+    __syncthreads();
+
+    // ---- G = ds * cs  (T x 64), K = slots ---------------------------------------------------------------------------------
+    float dwp[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwp[j][0] = dwp[j][1] = 0.f;
+    for (int mt = warp; mt < Tp / 16; mt += NT / 32) {
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int k0 = 0; k0 < Sp; k0 += 16) {
+            uint32_t a[4];
+            a_frag(a, ds, DLD, 16 * mt, k0, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t r[4];
+                b_frag_kn(r, cs, CLD, 16 * np, k0, lane);
+                ick_mma16816(acc[2 * np], a, r[0], r[1]);
+                ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * j + 2 * tq, d = d0 + c;
+            if (d >= D) continue;  // D is even (d-model 300): a column pair is inside or outside together
+            const float w0 = __ldg(w + d), w1 = d + 1 < D ? __ldg(w + d + 1) : 0.f;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int t = 16 * mt + g + 8 * hh;
+                if (t >= T) continue;
+                const float g0 = acc[j][2 * hh], g1 = acc[j][2 * hh + 1];
+                const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hs + (size_t)t * CLD + c));
+                dwp[j][0] = fmaf(hv.x, g0, dwp[j][0]);
+                dwp[j][1] = fmaf(hv.y, g1, dwp[j][1]);
+                __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dH + ((size_t)b * T + t) * ld + d);
+                const float2 old = __bfloat1622float2(*o);
+                *o = __floats2bfloat162_rn(old.x + w0 * g0, old.y + w1 * g1);
+            }
+        }
+    }
+    // dw: reduce the per-thread partials over the 8 row groups of the warp, then over warps through shared memory
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            float v = dwp[j][x];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) red[warp * CW + 8 * j + 2 * tq + x] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < CW && d0 + threadIdx.x < D) {
+        float v = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < NT / 32; ++wi) v += red[wi * CW + threadIdx.x];
+        atomicAdd(gflat + w_off + d0 + threadIdx.x, v);
+    }
+
+    // ---- C2 = ds^T * hs  (S x 64), K = time steps ------------------------------------------------------------------------
+    for (int mt = warp; mt < Sp / 16; mt += NT / 32) {
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int k0 = 0; k0 < Tp; k0 += 16) {
+            uint32_t a[4];
+            a_frag_t(a, ds, DLD, 16 * mt, k0, lane);
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t r[4];
+                b_frag_kn(r, hs, CLD, 16 * np, k0, lane);
+                ick_mma16816(acc[2 * np], a, r[0], r[1]);
+                ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d = d0 + 8 * j + 2 * tq;
+            if (d >= D) continue;
+            const float w0 = __ldg(w + d), w1 = d + 1 < D ? __ldg(w + d + 1) : 0.f;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int s = 16 * mt + g + 8 * hh;
+                if (s >= S) continue;
+                float2* o = reinterpret_cast<float2*>(dCtx + ((size_t)b * S + s) * ld + d);
+                float2 v = *o;
+                v.x += w0 * acc[j][2 * hh];
+                v.y += w1 * acc[j][2 * hh + 1];
+                *o = v;
+            }
+        }
+    }
+}
+
+template <typename K>
+int set_smem(K kernel) {
+    static bool done = false;
+    if (!done) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX) != cudaSuccess) {
+            ick_set_error("pointer: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+            return ICK_ERR_CUDA;
+        }
+        done = true;
+    }
+    return ICK_OK;
+}
+
+}  // namespace
+
+int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores, int B, int Tn,
+                        int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream) {
+    const int Tp = (Tn + 15) / 16 * 16, KP = (D + 15) / 16 * 16;
+    const size_t smem = (size_t)(Tp + CW) * (KP + 8) * 2;
+    if (KP > ld || ld % 8 != 0 || smem > SMEM_MAX || (((uintptr_t)h | (uintptr_t)ctx) & 15) != 0) return ICK_ERR_UNSUPPORTED;
+    int rc = set_smem(pointer_fwd_mma_kernel);
+    if (rc) return rc;
+    dim3 grid((S + CW - 1) / CW, B);
+    pointer_fwd_mma_kernel<<<grid, NT, smem, stream>>>((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld, ldscores,
+                                                       col0, lag, Tp, KP);
+    return ick_check_launch("pointer_fwd_mma");
+}
+
+int ick_pointer_bwd_mma(const void* dS, const void* h, const void* ctx, const float* w, const int* first_t, float* dCtx, void* dH, float* gflat,
+                        int w_off, int bias_off, int B, int T, int S, int D, int ld, int ldds, int col0, int lag, cudaStream_t stream) {
+    const int Tp = (T + 15) / 16 * 16, Sp = (S + 15) / 16 * 16;
+    const size_t smem = ((size_t)Tp * (Sp + 8) + (size_t)(Sp + Tp) * CLD) * 2 + 8 * CW * 4 + (size_t)Sp * 4;
+    if (ld % 8 != 0 || (D & 1) != 0 || smem > SMEM_MAX || (((uintptr_t)h | (uintptr_t)ctx | (uintptr_t)dCtx) & 15) != 0 || ((uintptr_t)dH & 3) != 0)
+        return ICK_ERR_UNSUPPORTED;
+    int rc = set_smem(pointer_bwd_mma_kernel);
+    if (rc) return rc;
+    dim3 grid((D + CW - 1) / CW, B);
+    pointer_bwd_mma_kernel<<<grid, NT, smem, stream>>>((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, dCtx, (bf16*)dH, gflat, w_off,
+                                                       bias_off, T, S, D, ld, ldds, col0, lag, Tp, Sp);
+    return ick_check_launch("pointer_bwd_mma");
+}

@@ -27,12 +27,9 @@ def ick_rowmix(seed: int, site: int, row: np.ndarray) -> np.ndarray:
 
 
 def ick_pairhash(rowmix: np.ndarray, col: np.ndarray) -> np.ndarray:
-    h = (((col.astype(np.uint64) >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M32) ^ rowmix
-    h ^= h >> np.uint64(15)
-    h = (h * np.uint64(0x2C1B3C6D)) & M32
-    h ^= h >> np.uint64(12)
-    h = (h * np.uint64(0x297A2D39)) & M32
-    h ^= h >> np.uint64(15)
+    h = (rowmix + (col.astype(np.uint64) >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M32
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85EBCA6B)) & M32
     return h
 
 

@@ -376,6 +376,39 @@ def test_indicators_gate_pointer(K, Hk, dtype, lag, Tn, t0):
     assert err(Gg, Gr) < 1e-4
 
 
+@pytest.mark.parametrize("S,col0,masked", [(51, 87, True), (301, 64, False), (130, 64, True)])
+def test_pointer_tensor_core_path(K, Hk, S, col0, masked):
+    """bf16 pointer heads at teacher-forced sizes (T >= 16): the mma.sync kernels of pointer_mma.cu, including a score slice
+    that starts at an odd column (col0 = V + E in the reference layout) and slot counts that are not multiples of 16."""
+    dtype = torch.bfloat16
+    B, T, D, ld = 3, 37, 300, 320
+    Wd = col0 + S + 3
+    h = torch.zeros(B * T, ld, dtype=dtype)
+    h[:, :D] = rnd((B * T, D), dtype, 3)
+    ctx = torch.zeros(B * S, ld, dtype=dtype)
+    ctx[:, :D] = rnd((B * S, D), dtype, 4)
+    w, b1 = rnd((D,), torch.float32, 5), rnd((1,), torch.float32, 6)
+    first = torch.randint(0, T + 6, (B * S,), generator=g(11)).int() if masked else None
+    sr, sg = torch.zeros(B * T, Wd), torch.zeros(B * T, Wd).cuda()
+    Hk.pointer_fwd(h, ctx, w, b1, first, sr, B, T, 0, S, D, col0, 0)
+    K.pointer_fwd(cu(h), cu(ctx), cu(w), cu(b1), cu(first), sg, B, T, 0, S, D, col0, 0)
+    assert err(sg, sr) < TOL[dtype]
+    assert torch.equal(sg.cpu()[:, :col0], sr[:, :col0]) and torch.equal(sg.cpu()[:, col0 + S:], sr[:, col0 + S:])  # nothing else touched
+    ldd = (Wd + 7) // 8 * 8
+    dS = torch.zeros(B * T, ldd, dtype=dtype)
+    dS[:, :Wd] = rnd((B * T, Wd), dtype, 7)
+    dCr = rnd((B * S, ld), torch.float32, 8)
+    dCg = dCr.clone().cuda()
+    dHr = rnd((B * T, ld), dtype, 9)
+    dHg = dHr.clone().cuda()
+    Gr, Gg = torch.zeros(D + 9), torch.zeros(D + 9).cuda()
+    Hk.pointer_bwd(dS, h, ctx, w, first, dCr, dHr, Gr, 1, 0, B, T, S, D, col0, 0)
+    K.pointer_bwd(cu(dS), cu(h), cu(ctx), cu(w), cu(first), dCg, dHg, Gg, 1, 0, B, T, S, D, col0, 0)
+    assert err(dCg[:, :D], dCr[:, :D]) < TOL[dtype] and err(dHg[:, :D], dHr[:, :D]) < TOL[dtype] * 2
+    assert torch.equal(dCg.cpu()[:, D:], dCr[:, D:])  # pad columns untouched
+    assert err(Gg, Gr) < 2e-3
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_ce_adam_misc(K, Hk, dtype):
     B, T, Wd = 5, 9, 1037

@@ -124,3 +124,28 @@ def test_module_pickles_like_reference_checkpoints(tmp_path):
     with torch.no_grad():
         s1, _, _ = dec2(*batch_args(cfg, batch))
     assert torch.equal(s0, s1)
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_dropout_hash_statistics(p):
+    """The counter hash behind every dropout mask (csrc/common.cuh, ported in dropout_ref.py): keep rate within sampling error
+    of 1-p, and no visible correlation between the two columns of a pair, neighbouring pairs, or neighbouring rows."""
+    from dropout_ref import drop_mul
+
+    rows, cols = 2048, 640
+    k = (drop_mul(p, 1234, 7, rows, cols) > 0).double()
+    thr = int(p * 32768)
+    assert abs(float(k.mean()) - (1 - thr / 32768)) < 4 * (p * (1 - p) / (rows * cols)) ** 0.5
+    kc = k - k.mean()
+
+    def corr(a, b):
+        return float((a * b).mean() / ((a * a).mean() * (b * b).mean()).sqrt())
+
+    lim = 5.0 / (rows * cols / 2) ** 0.5
+    assert abs(corr(kc[:, 0::2], kc[:, 1::2])) < lim       # the two 15-bit fields of one hash
+    assert abs(corr(kc[:, 0:-2:2], kc[:, 2::2])) < lim     # consecutive pairs
+    assert abs(corr(kc[:-1], kc[1:])) < lim                # consecutive rows
+    assert abs(corr(kc[:, :-8], kc[:, 8:])) < lim          # the stride an MMA fragment lane sees
+    # each row / column keeps its own share close to 1-p
+    assert float(k.mean(1).std()) < 1.3 * (p * (1 - p) / cols) ** 0.5
+    assert float(k.mean(0).std()) < 1.3 * (p * (1 - p) / rows) ** 0.5

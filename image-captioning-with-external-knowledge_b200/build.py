@@ -15,7 +15,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libickb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
+         "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC] + os.environ.get("ICK_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

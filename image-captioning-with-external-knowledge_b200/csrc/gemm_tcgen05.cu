@@ -19,19 +19,45 @@
 #include "common.cuh"
 #include "ickb200.h"
 
+#ifdef ICK_TRACE
+// Debug build only (-DICK_TRACE): per-role timeline of CTA 0 of the last gemm_tn_tc launch, read back by tools/gemm_trace.py.
+// Each role appends to its own 1024-entry lane with a thread-local counter (plain stores, no atomics: a few cycles per event).
+__device__ unsigned long long ick_trace_buf[4 * 2048];
+#define ICK_TR_DECL(role) unsigned int tr_i_ = 0; const unsigned int tr_role_ = (role)
+#define ICK_TR(ev, tile)                                                                              \
+    do {                                                                                              \
+        if (blockIdx.x == 0 && tr_i_ < 1023) {                                                        \
+            ick_trace_buf[tr_role_ * 2048 + 2 * tr_i_] = ((unsigned long long)(ev) << 32) | (unsigned)(tile); \
+            ick_trace_buf[tr_role_ * 2048 + 2 * tr_i_ + 1] = clock64();                               \
+            ++tr_i_;                                                                                  \
+            ick_trace_buf[tr_role_ * 2048 + 2 * tr_i_] = 0xFFFFFFFFFFFFFFFFull;                       \
+        }                                                                                             \
+    } while (0)
+extern "C" int ick_debug_trace_read(unsigned long long* out, int max_entries) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ick_trace_buf, sizeof(unsigned long long) * 4 * 2048);
+    return 4 * 1024;
+}
+#else
+#define ICK_TR_DECL(role) do {} while (0)
+#define ICK_TR(ev, tile) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;       // UMMA M (TMEM lanes)
 constexpr int BK = 64;        // reduction elements per stage = one 128-byte swizzle row of bf16
 constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_WKB = 16;   // k-blocks of a resident weight panel (K <= 1024)
 constexpr int MAX_BN = 256;   // widest single tcgen05.mma N
 constexpr int A_STAGE = BM * BK * 2;      // 16 KiB
 constexpr int TMEM_COLS = 512;
 constexpr int BAR_BYTES = 1024;           // barriers + TMEM base pointer live in the first KiB
-constexpr int SMEM_DATA = 4 * (A_STAGE + MAX_BN * BK * 2);  // 192 KiB of stage buffers
-constexpr int SMEM_BYTES = SMEM_DATA + BAR_BYTES + 1024 /*align slack*/;
+constexpr int SMEM_BYTES = 232448;        // all 227 KiB a CTA may have
+constexpr int SMEM_DATA = SMEM_BYTES - BAR_BYTES - 1024 /*align slack*/;  // 225 KiB of operand buffers
 constexpr int NEPI = 8;                   // epilogue warps
+constexpr int NSBOX = 2;                  // staging boxes per epilogue warp (bulk stores in flight)
 constexpr int NTHREADS = 64 + 32 * NEPI;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -71,6 +97,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         "l"(tm), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -119,20 +154,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_m
 struct Smem {
     uint32_t base;   // shared-space address of the 1024-aligned region
     uint32_t stage_bytes;
+    uint32_t panel_bytes;
     uint32_t* tmem_ptr;
     __device__ __forceinline__ uint32_t full(int i) const { return base + 8 * i; }
     __device__ __forceinline__ uint32_t empty(int i) const { return base + 8 * (MAX_STAGES + i); }
     __device__ __forceinline__ uint32_t tfull(int i) const { return base + 8 * (2 * MAX_STAGES + i); }
     __device__ __forceinline__ uint32_t tempty(int i) const { return base + 8 * (2 * MAX_STAGES + 2 + i); }
-    __device__ __forceinline__ uint32_t a(int stage) const { return base + BAR_BYTES + stage * stage_bytes; }
+    __device__ __forceinline__ uint32_t wfull(int i) const { return base + 8 * (2 * MAX_STAGES + 4 + i); }
+    __device__ __forceinline__ uint32_t panel() const { return base + BAR_BYTES; }  // resident weight panel (W-stationary mode)
+    __device__ __forceinline__ uint32_t a(int stage) const { return base + BAR_BYTES + panel_bytes + stage * stage_bytes; }
     __device__ __forceinline__ uint32_t b(int stage) const { return a(stage) + A_STAGE; }
 };
-__device__ __forceinline__ Smem carve(uint8_t* raw, uint32_t stage_bytes) {
+__device__ __forceinline__ Smem carve(uint8_t* raw, uint32_t stage_bytes, uint32_t panel_bytes = 0) {
     uint8_t* p = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     Smem s;
     s.base = smem_u32(p);
     s.stage_bytes = stage_bytes;
-    s.tmem_ptr = (uint32_t*)(p + 8 * (2 * MAX_STAGES + 4));
+    s.panel_bytes = panel_bytes;
+    s.tmem_ptr = (uint32_t*)(p + 8 * (2 * MAX_STAGES + 4 + MAX_WKB));
     return s;
 }
 
@@ -148,6 +187,7 @@ __device__ __forceinline__ void setup(const Smem& s, int warp, int lane, const C
             mbar_init(s.tfull(i), 1);
             mbar_init(s.tempty(i), NEPI);
         }
+        for (int i = 0; i < MAX_WKB; ++i) mbar_init(s.wfull(i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -216,14 +256,50 @@ struct TnParams {
     const float* bias;
     const void* aux;
     int M, N, K, ldc, ldaux, epi, accumulate, c_f32, BN, n_tiles_n, n_tiles, nkb, stages;
+    int wstat;    // W-stationary: CTA c keeps weight panel (c % n_tiles_n) resident and streams only A tiles
+    int m_tiles;  // row tiles
+    int tma_store;  // output through per-warp shared-memory staging + TMA bulk stores (needs 16-byte aligned C rows)
     DropCfg drop;
+};
+// Work of a CTA.  Streaming mode: tiles blockIdx.x, +gridDim.x, ... over the (m, n) grid, n fastest.  W-stationary mode:
+// gridDim.x = n_tiles_n * cpp; CTA c owns panel c % n_tiles_n and row tiles c / n_tiles_n, + cpp, ... (CTAs that share a row
+// tile run side by side, so the A tile is fetched from HBM once and re-read from L2).
+struct TileIter {
+    int m_tile, n_tile, step_m, it, end;
+    bool wstat;
+    int n_tiles_n;
+    __device__ __forceinline__ TileIter(const TnParams& p) {
+        wstat = p.wstat != 0;
+        n_tiles_n = p.n_tiles_n;
+        if (wstat) {
+            n_tile = blockIdx.x % p.n_tiles_n;
+            it = blockIdx.x / p.n_tiles_n;
+            step_m = gridDim.x / p.n_tiles_n;
+            end = p.m_tiles;
+        } else {
+            it = blockIdx.x;
+            step_m = gridDim.x;
+            end = p.n_tiles;
+            n_tile = 0;
+        }
+        m_tile = 0;
+    }
+    __device__ __forceinline__ bool next() {  // sets m_tile / n_tile of the current work item, then advances
+        if (it >= end) return false;
+        if (wstat) m_tile = it;
+        else { m_tile = it / n_tiles_n; n_tile = it % n_tiles_n; }
+        it += step_m;
+        return true;
+    }
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmW, TnParams p) {
+                                                                  const __grid_constant__ CUtensorMap tmW,
+                                                                  const __grid_constant__ CUtensorMap tmC, TnParams p) {
     extern __shared__ uint8_t smem_raw[];
     ick_resolve_seed(p.drop);
-    const Smem s = carve(smem_raw, A_STAGE + p.BN * BK * 2);
+    const uint32_t wbox = (uint32_t)p.BN * BK * 2;  // one k-block of the weight tile
+    const Smem s = p.wstat ? carve(smem_raw, A_STAGE, (uint32_t)p.nkb * wbox) : carve(smem_raw, A_STAGE + wbox);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setup(s, warp, lane, &tmA, &tmW);
     const uint32_t tmem_base = *s.tmem_ptr;
@@ -232,14 +308,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (uint32_t)(BM + p.BN) * BK * 2;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const int m_idx = (tile / p.n_tiles_n) * BM, n_idx = (tile % p.n_tiles_n) * p.BN;
+            ICK_TR_DECL(0);
+            TileIter ti(p);
+            if (p.wstat && ti.it < ti.end) {  // the CTA's weight panel, once
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_expect_tx(s.wfull(kb), wbox);
+                    tma_load_2d(s.panel() + kb * wbox, &tmW, s.wfull(kb), kb * BK, ti.n_tile * p.BN);
+                }
+            }
+            const uint32_t tx = p.wstat ? (uint32_t)A_STAGE : (uint32_t)A_STAGE + wbox;
+            ICK_TR(1, 0);
+            while (ti.next()) {
+                const int m_idx = ti.m_tile * BM, n_idx = ti.n_tile * p.BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(s.empty(stage), phase ^ 1);
+                    ICK_TR(2, ti.m_tile * 100 + kb);
                     mbar_expect_tx(s.full(stage), tx);
                     tma_load_2d(s.a(stage), &tmA, s.full(stage), kb * BK, m_idx);
-                    tma_load_2d(s.b(stage), &tmW, s.full(stage), kb * BK, n_idx);
+                    if (!p.wstat) tma_load_2d(s.b(stage), &tmW, s.full(stage), kb * BK, n_idx);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -249,14 +335,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             const uint32_t idesc = make_idesc(p.BN, 0, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            bool first = true;
+            ICK_TR_DECL(1);
+            TileIter ti(p);
+            while (ti.next()) {
                 mbar_wait(s.tempty(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * MAX_BN;
+                ICK_TR(3, ti.m_tile);
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(s.full(stage), phase);
+                    if (p.wstat && first) mbar_wait(s.wfull(kb), 0);
+                    ICK_TR(4, ti.m_tile * 100 + kb);
                     tc_fence_after();
-                    const uint32_t a0 = s.a(stage), b0 = s.b(stage);
+                    const uint32_t a0 = s.a(stage), b0 = p.wstat ? s.panel() + kb * wbox : s.b(stage);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major SWIZZLE_128B: 8-row groups 1024 B apart; a K step of 16 elements = 32 B inside the row
@@ -268,6 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(s.tfull(acc));  // accumulator complete
+                first = false;
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -279,62 +372,116 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
         const bool c_al = (p.ldc % (p.c_f32 ? 4 : 8) == 0) && ((((uintptr_t)p.C) & 15) == 0);
         const bool aux_al = p.aux != nullptr && (p.ldaux % 8 == 0) && ((((uintptr_t)p.aux) & 15) == 0);
         const bool bias_al = p.bias != nullptr && ((((uintptr_t)p.bias) & 15) == 0);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int m_idx = (tile / p.n_tiles_n) * BM, n_idx = (tile % p.n_tiles_n) * p.BN;
+        // Bulk-store path: each warp owns NSBOX staging boxes of [32 rows x 32 columns] behind the operand stages (64-byte rows
+        // swizzled 64B for bf16, 128-byte rows swizzled 128B for fp32; lane r writes row r, so each 16-byte chunk column is
+        // bank-conflict free); one lane issues the TMA store of a finished box and the warp goes on with its next chunk.  Stores
+        // issued by the warps themselves (row per lane, or transposed through shared memory) measured 35-40% slower.
+        const uint32_t sbox = p.c_f32 ? 4096u : 2048u;
+        const uint32_t stg = s.a(0) + (uint32_t)p.stages * s.stage_bytes + (uint32_t)(warp - 2) * NSBOX * sbox;
+        int sb = 0;
+        ICK_TR_DECL(2);
+        TileIter ti(p);
+        while (ti.next()) {
+            const int m_idx = ti.m_tile * BM, n_idx = ti.n_tile * p.BN;
+            if (warp == 2 && lane == 0) ICK_TR(5, ti.m_tile);
             mbar_wait(s.tfull(acc), acc_phase);
+            if (warp == 2 && lane == 0) ICK_TR(6, ti.m_tile);
             tc_fence_after();
             const int row = m_idx + q * 32 + lane;
             for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+                float bv[32];  // bias of this chunk's columns, requested before the TMEM load so that the two latencies overlap
+                {
+                    const int col0 = n_idx + c0;
+                    const int nv = min(32, p.N - col0);
+                    if (p.bias != nullptr && nv > 0) ld32_f32(p.bias + col0, nv == 32 && (col0 & 7) == 0 && bias_al, nv, bv);
+                }
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BN + c0, r);
+                if (warp == 2 && lane == 0) ICK_TR(7, ti.m_tile * 100 + c0 / 32);
+                if (c0 + 64 >= p.BN) {  // this warp's last chunk of the accumulator is in registers: hand the TMEM stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s.tempty(acc));
+                }
                 const int col0 = n_idx + c0;
-                if (row < p.M && col0 < p.N) {
-                    const int nv = min(32, p.N - col0);
-                    const bool full = nv == 32 && (col0 & 7) == 0;
-                    float v[32];
+                if (col0 >= p.N || m_idx + q * 32 >= p.M) continue;  // warp-uniform: nothing of this chunk is inside C
+                const int nv = min(32, p.N - col0);
+                const bool full = nv == 32 && (col0 & 7) == 0;
+                const bool live = row < p.M;
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (p.bias) {
-                        float t[32];
-                        ld32_f32(p.bias + col0, full && bias_al, nv, t);
+                for (int j = 0; j < 32; ++j) v[j] = p.bias ? __uint_as_float(r[j]) + bv[j] : __uint_as_float(r[j]);
+                if (p.accumulate && live) {
+                    float t[32];
+                    if (p.c_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
+                    else ld32_bf16((const bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, t);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += t[j];
-                    }
-                    if (p.accumulate) {
-                        float t[32];
-                        if (p.c_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
-                        else ld32_bf16((const bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, t);
+                    for (int j = 0; j < 32; ++j) v[j] += t[j];
+                }
+                if (p.epi == 1) {
+                    const uint32_t rmix = ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += t[j];
-                    }
-                    if (p.epi == 1) {
-                        const uint32_t rmix = ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {  // col0 is even: (j, j+1) is one hash pair
-                            float k0 = 1.f, k1 = 1.f;
-                            if (p.drop.thr != 0u) {
-                                const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(col0 + j));
-                                k0 = ick_keep_lo(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
-                                k1 = ick_keep_hi(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
-                            }
-                            v[j] = fmaxf(v[j], 0.f) * k0;
-                            v[j + 1] = fmaxf(v[j + 1], 0.f) * k1;
+                    for (int j = 0; j < 32; j += 2) {  // col0 is even: (j, j+1) is one hash pair
+                        float k0 = 1.f, k1 = 1.f;
+                        if (p.drop.thr != 0u) {
+                            const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(col0 + j));
+                            k0 = ick_keep_lo(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
+                            k1 = ick_keep_hi(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
                         }
-                    } else if (p.epi == 2) {
-                        float t[32];
-                        ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = t[j] != 0.f ? v[j] * p.drop.inv_keep : 0.f;
+                        v[j] = fmaxf(v[j], 0.f) * k0;
+                        v[j + 1] = fmaxf(v[j + 1], 0.f) * k1;
                     }
+                } else if (p.epi == 2 && live) {
+                    float t[32];
+                    ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = t[j] != 0.f ? v[j] * p.drop.inv_keep : 0.f;
+                }
+                if (p.tma_store) {
+                    const uint32_t box = stg + (uint32_t)sb * sbox;
+                    if (lane == 0) bulk_wait_read<NSBOX - 1>();  // the bulk store that last read this box is done with it
+                    __syncwarp();
+                    if (p.c_f32) {
+                        const uint32_t rowa = box + (uint32_t)lane * 128u;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((c ^ (lane & 7)) << 4)), "f"(v[4 * c]),
+                                         "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                                         : "memory");
+                    } else {
+                        const uint32_t rowa = box + (uint32_t)lane * 64u;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), t1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), t3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4)),
+                                         "r"(*reinterpret_cast<uint32_t*>(&t0)), "r"(*reinterpret_cast<uint32_t*>(&t1)),
+                                         "r"(*reinterpret_cast<uint32_t*>(&t2)), "r"(*reinterpret_cast<uint32_t*>(&t3))
+                                         : "memory");
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, box, col0, m_idx + q * 32);  // rows >= M and columns >= N are clipped by the tensor map
+                        bulk_commit();
+                    }
+                    sb = sb + 1 == NSBOX ? 0 : sb + 1;
+                    if (warp == 2 && lane == 0) ICK_TR(8, ti.m_tile * 100 + c0 / 32);
+                } else if (live) {
                     if (p.c_f32) st32_f32((float*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
                     else st32_bf16((bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s.tempty(acc));
+            if (half * 32 >= p.BN) {  // (BN = 32 only) a warp without a chunk still releases the accumulator stage
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s.tempty(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && lane == 0) bulk_wait_read<0>();  // staging boxes must outlive their stores
+        if (warp == 2 && lane == 0) ICK_TR(9, 0);
     }
     teardown(warp, tmem_base);
 }
@@ -350,6 +497,8 @@ struct WgParams {
     float* ws;  // [splits][N][Kws] partial tiles, or nullptr -> atomics straight into G
     const int* rowoff;
     const int* colmap;
+    const int* biasoff;  // fused bias gradient (column sums of dY) or nullptr
+    float* wsb;          // [splits][N] bias partials (with ws)
     int M, N, K, KT, Kws, n_tiles_n, n_tiles_k, splits, m_per_split, stages;
 };
 
@@ -359,6 +508,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     const int nbx = p.KT / 64;  // X boxes per stage
     const Smem s = carve(smem_raw, A_STAGE + nbx * WG_BOX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Fused bias gradient: one more N=16 MMA per k-step against a constant box of ones (an all-ones operand is invariant under
+    // the 128B swizzle), i.e. D[n, KT..KT+15] = sum_m dY[m,n].  The box lives behind the last stage.
+    const uint32_t ones = s.a(0) + (uint32_t)p.stages * s.stage_bytes;
+    if (p.biasoff != nullptr) {
+        uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023) + BAR_BYTES + (size_t)p.stages * s.stage_bytes;
+        for (int i = threadIdx.x; i < WG_BOX / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(base)[i] = 0x3F803F80u;  // bf16 1.0 x2
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     setup(s, warp, lane, &tmY, &tmX);
     const uint32_t tmem_base = *s.tmem_ptr;
     const int n_work = p.n_tiles_n * p.n_tiles_k * p.splits;
@@ -386,7 +543,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     } else if (warp == 1) {
         if (lane == 0) {
             const int n1 = p.KT > MAX_BN ? MAX_BN : p.KT, n2 = p.KT - n1;
-            const uint32_t idesc1 = make_idesc(n1, 1, 1), idesc2 = make_idesc(n2 > 0 ? n2 : 16, 1, 1);
+            const uint32_t idesc1 = make_idesc(n1, 1, 1), idesc2 = make_idesc(n2 > 0 ? n2 : 16, 1, 1), idesc_b = make_idesc(16, 1, 1);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -407,6 +564,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
                         if (n2 > 0)
                             tc_mma_bf16(tmem_base + MAX_BN, ad, make_desc(b0 + 4 * WG_BOX + k * UMMA_K * 128, WG_BOX, 1024), idesc2,
                                         (it | k) != 0);
+                        if (p.biasoff != nullptr)
+                            tc_mma_bf16(tmem_base + p.KT, ad, make_desc(ones + k * UMMA_K * 128, WG_BOX, 1024), idesc_b, (it | k) != 0);
                     }
                     tc_commit(s.empty(stage));
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -447,6 +606,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
                     }
                 }
             }
+            if (p.biasoff != nullptr && half == 0) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + p.KT, r);
+                if (n < p.N) {
+                    if (p.wsb != nullptr) p.wsb[(size_t)split * p.N + n] = __uint_as_float(r[0]);
+                    else if (p.biasoff[n] >= 0) atomicAdd(p.G + p.biasoff[n], __uint_as_float(r[0]));
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s.tempty(0));
@@ -458,8 +625,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
 
 // sum the row-slice partials and scatter into the flat gradient buffer: G[rowoff[n] + colmap[k]] += sum_s ws[s][n][k]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ G, const int* __restrict__ rowoff,
-                                                           const int* __restrict__ colmap, int N, int K, int Kws, int splits) {
+                                                           const int* __restrict__ colmap, int N, int K, int Kws, int splits,
+                                                           const float* __restrict__ wsb, const int* __restrict__ biasoff) {
     const int n = blockIdx.y;
+    if (wsb != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && biasoff[n] >= 0) {
+        float acc = 0.f;
+        for (int sp = 0; sp < splits; ++sp) acc += wsb[(size_t)sp * N + n];
+        G[biasoff[n]] += acc;
+    }
     const int ro = rowoff[n];
     if (ro < 0) return;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
@@ -535,6 +708,27 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int inner, int rows, int ld, int
     return ICK_OK;
 }
 
+// 2D output map for the epilogue's bulk stores: box = 32 columns x 32 rows, swizzle matching the row width (64 B / 128 B)
+int make_tmap_out(CUtensorMap* tm, const void* ptr, int c_f32, int N, int M, int ldc) {
+    EncodeFn enc = get_encode();
+    if (!enc) {
+        ick_set_error("cuTensorMapEncodeTiled entry point not available");
+        return ICK_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * (c_f32 ? 4 : 2)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tm, c_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, c_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ick_set_error("cuTensorMapEncodeTiled(out) failed (%d): ptr=%p N=%d M=%d ldc=%d", (int)r, ptr, N, M, ldc);
+        return ICK_ERR_CUDA;
+    }
+    return ICK_OK;
+}
+
 int pick_bn(int N) {
     // widest tile whose padding waste is smallest; multiples of 32 (epilogue chunk) up to 256
     int best = 128, best_pad = 1 << 30;
@@ -543,6 +737,43 @@ int pick_bn(int N) {
         if (pad < best_pad) { best_pad = pad; best = bn; }
     }
     return best;
+}
+
+// Tile plan.  Streaming mode re-loads the weight tile with every A tile; W-stationary mode keeps a K-deep weight panel of
+// BN columns resident per CTA and streams only A.  Both are scored by the bytes that must enter shared memory per useful
+// output column (padding counted), and W-stationary needs >= 4 A stages next to the panel and at most 16 panels.
+struct Plan {
+    int wstat, BN, stages;
+};
+Plan plan_tiles(int N, int nkb, int avail, bool allow_wstat) {
+    Plan best;
+    best.wstat = 0;
+    best.BN = pick_bn(N);
+    best.stages = avail / (A_STAGE + best.BN * BK * 2);
+    if (best.stages > MAX_STAGES) best.stages = MAX_STAGES;
+    const auto padded = [&](int bn) { return (N + bn - 1) / bn * bn; };
+    double best_cost = (double)(BM + best.BN) / best.BN * padded(best.BN) / N;  // x K*2 bytes, common to all candidates
+    if (!allow_wstat || nkb > MAX_WKB) return best;
+    for (int bn = 256; bn >= 64; bn -= 32) {
+        const int st = (avail - nkb * bn * BK * 2) / A_STAGE;
+        if (st < 4 || padded(bn) / bn > 16) continue;
+        const double cost = (double)BM / bn * padded(bn) / N;
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best.wstat = 1;
+            best.BN = bn;
+            best.stages = st > MAX_STAGES ? MAX_STAGES : st;
+        }
+    }
+    return best;
+}
+bool use_wstat() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_GEMM_WSTAT");  // measured slower than streaming on every shape of the step: opt-in only
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
 }
 
 int num_sms() {
@@ -586,17 +817,37 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
     p.C = C; p.bias = bias; p.aux = aux;
     p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldaux = ldaux; p.epi = epi; p.accumulate = accumulate;
     p.c_f32 = c_dt == ICK_F32;
-    p.BN = pick_bn(N);
-    p.n_tiles_n = (N + p.BN - 1) / p.BN;
-    p.n_tiles = ((M + BM - 1) / BM) * p.n_tiles_n;
     p.nkb = (K + BK - 1) / BK;
-    p.stages = MAX_STAGES;
+    p.m_tiles = (M + BM - 1) / BM;
+    // the bulk-store epilogue needs 16-byte aligned rows of C; otherwise (e.g. the 10301-wide fp32 score rows of the geo
+    // variant) the epilogue writes straight from registers, row per lane
+    const int es = c_dt == ICK_F32 ? 4 : 2;
+    p.tma_store = ((((uintptr_t)C) & 15) == 0 && ((size_t)ldc * es) % 16 == 0) ? 1 : 0;
+    const int staging = p.tma_store ? NEPI * NSBOX * (c_dt == ICK_F32 ? 4096 : 2048) : 0;
+    const Plan pl = plan_tiles(N, p.nkb, SMEM_DATA - staging, use_wstat());
+    p.wstat = pl.wstat;
+    p.BN = pl.BN;
+    p.stages = pl.stages;
+    ICK_REQUIRE(p.stages >= 2, "gemm_tn_tc: tile does not fit");
+    p.n_tiles_n = (N + p.BN - 1) / p.BN;
+    p.n_tiles = p.m_tiles * p.n_tiles_n;
     p.drop = make_drop(drop_p, seed, site);
-    CUtensorMap tmA, tmW;
+    CUtensorMap tmA, tmW, tmC;
     if ((rc = make_tmap(&tmA, A, K, M, lda, BM))) return rc;
     if ((rc = make_tmap(&tmW, W, K, N, ldw, p.BN))) return rc;
-    const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    gemm_tn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmW, p);
+    if (p.tma_store) {
+        if ((rc = make_tmap_out(&tmC, C, p.c_f32, N, M, ldc))) return rc;
+    } else {
+        tmC = tmA;  // unused
+    }
+    int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
+    if (p.wstat) {
+        int cpp = num_sms() / p.n_tiles_n;  // CTAs per weight panel
+        if (cpp < 1) cpp = 1;
+        if (cpp > p.m_tiles) cpp = p.m_tiles;
+        grid = cpp * p.n_tiles_n;
+    }
+    gemm_tn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmW, tmC, p);
     return ick_check_launch("gemm_tn_tc");
 }
 
@@ -618,7 +869,10 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     p.n_tiles_n = (N + BM - 1) / BM;
     const int tiles = p.n_tiles_n * p.n_tiles_k;
     const int stage_bytes = A_STAGE + (p.KT / 64) * WG_BOX;
-    p.stages = SMEM_DATA / stage_bytes;
+    // the bias gradient rides along as 16 extra accumulator columns when they fit behind the tile (KT + 32 <= 512 TMEM columns)
+    const bool fuse_bias = biasoff != nullptr && p.n_tiles_k == 1 && p.KT + 32 <= TMEM_COLS;
+    p.biasoff = fuse_bias ? biasoff : nullptr;
+    p.stages = (SMEM_DATA - (fuse_bias ? WG_BOX : 0)) / stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     ICK_REQUIRE(p.stages >= 2, "wgrad_tc: tile does not fit");
     int splits = (num_sms() + tiles - 1) / tiles;
@@ -630,8 +884,9 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     p.splits = (M + mps - 1) / mps;
     p.m_per_split = mps;
     p.Kws = (K + 31) / 32 * 32;
-    const long long need = (long long)p.splits * N * p.Kws * 4;
+    const long long need = (long long)p.splits * N * (p.Kws + 1) * 4;
     p.ws = (workspace != nullptr && workspace_bytes >= need && (((uintptr_t)workspace) & 15) == 0) ? (float*)workspace : nullptr;
+    p.wsb = (p.ws != nullptr && fuse_bias) ? p.ws + (size_t)p.splits * N * p.Kws : nullptr;
     CUtensorMap tmY, tmX;
     if ((rc = make_tmap(&tmY, dY, N, M, ldy, BK))) return rc;
     if ((rc = make_tmap(&tmX, X, K, M, ldx, BK))) return rc;
@@ -641,10 +896,10 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     if ((rc = ick_check_launch("wgrad_tc"))) return rc;
     if (p.ws != nullptr) {
         dim3 rgrid((K + 255) / 256, N);
-        wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, gflat, rowoff, colmap, N, K, p.Kws, p.splits);
+        wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, gflat, rowoff, colmap, N, K, p.Kws, p.splits, p.wsb, biasoff);
         if ((rc = ick_check_launch("wgrad_reduce"))) return rc;
     }
-    if (biasoff) {
+    if (biasoff && !fuse_bias) {
         const int rpb = 256;
         dim3 bgrid((N + 127) / 128, (M + rpb - 1) / rpb);
         bias_grad_kernel<<<bgrid, 256, 0, stream>>>((const bf16*)dY, gflat, biasoff, M, N, ldy, rpb);

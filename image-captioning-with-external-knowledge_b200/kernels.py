@@ -103,7 +103,9 @@ class CudaKernels:
             if self._ws is None or self._ws.device != dY.device:
                 self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=dY.device)
             self._call("ick_wgrad_tc", _p(dY), _p(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N, K, _ld(dY), _ld(X),
-                       _p(self._ws), self._ws.numel(), n=3 if biasoff is not None else 2, work=work)
+                       _p(self._ws), self._ws.numel(),
+                       # launches: wgrad + reduce; the bias gradient is a third kernel only when it cannot ride along (K > 480)
+                       n=3 if (biasoff is not None and (K + 63) // 64 * 64 + 32 > 512) else 2, work=work)
         else:
             self._call("ick_wgrad_simt", _p(dY), dt_of(dY), _p(X), dt_of(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N,
                        K, _ld(dY), _ld(X), work=work)

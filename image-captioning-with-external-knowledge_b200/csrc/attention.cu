@@ -88,6 +88,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, const T* __restrict__ K,
                                                      const T* __restrict__ V, T* __restrict__ O, float* __restrict__ LSE,
                                                      AttnDims d, DropCfg drop) {
+    ick_pdl_entry();
     __shared__ __align__(16) float Ks[KT][HD];
     __shared__ __align__(16) float Vs[KT][HD];
     ick_resolve_seed(drop);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
                                                         const T* __restrict__ dO, const float* __restrict__ LSE,
                                                         float* __restrict__ Dsum, T* __restrict__ dQ, AttnDims d,
                                                         int lddo, int lddq, DropCfg drop) {
+    ick_pdl_entry();
     __shared__ __align__(16) float Ks[KT][HD];
     __shared__ __align__(16) float Vs[KT][HD];
     ick_resolve_seed(drop);
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dkv_kernel(const T* __restrict__ Q
                                                          const float* __restrict__ LSE, const float* __restrict__ Dsum,
                                                          T* __restrict__ dK, T* __restrict__ dV, AttnDims d, int lddo,
                                                          int lddk, int lddv, DropCfg drop) {
+    ick_pdl_entry();
     __shared__ __align__(16) float Qs[QT][HD];
     __shared__ __align__(16) float Gs[QT][HD];
     __shared__ float Ls[QT], Ds[QT];
@@ -288,6 +291,7 @@ __global__ void __launch_bounds__(128) mha_decode_kernel(const T* __restrict__ Q
                                                          const T* __restrict__ V, T* __restrict__ O, int B, int H, int dh,
                                                          int ldq, int ldk, int ldv, int ldo, long long kbatch_stride,
                                                          long long vbatch_stride, int klen, float scale_log2) {
+    ick_pdl_entry();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= B * H) return;
@@ -371,9 +375,9 @@ extern "C" int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O,
     dim3 grid((Sq + NT - 1) / NT, H, B);
     if (dt == ICK_BF16 && use_mma()) return ick_mha_fwd_mma(Q, K, V, O, lse, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal, dc, stream);
     if (dt == ICK_F32)
-        mha_fwd_kernel<float><<<grid, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (float*)O, lse, d, dc);
+        ick_launch(mha_fwd_kernel<float>, grid, NT, 0, stream)((const float*)Q, (const float*)K, (const float*)V, (float*)O, lse, d, dc);
     else if (dt == ICK_BF16)
-        mha_fwd_kernel<bf16><<<grid, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, lse, d, dc);
+        ick_launch(mha_fwd_kernel<bf16>, grid, NT, 0, stream)((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, lse, d, dc);
     else {
         ick_set_error("mha_fwd: bad dtype %d", dt);
         return ICK_ERR_UNSUPPORTED;
@@ -396,14 +400,14 @@ extern "C" int ick_mha_bwd(const void* Q, const void* K, const void* V, const vo
         return ick_mha_bwd_mma(Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, causal, dc,
                                stream);
     if (dt == ICK_F32) {
-        mha_bwd_dq_kernel<float><<<gq, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (const float*)O,
+        ick_launch(mha_bwd_dq_kernel<float>, gq, NT, 0, stream)((const float*)Q, (const float*)K, (const float*)V, (const float*)O,
                                                         (const float*)dO, lse, dsum, (float*)dQ, d, lddo, lddq, dc);
-        mha_bwd_dkv_kernel<float><<<gk, NT, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (const float*)dO,
+        ick_launch(mha_bwd_dkv_kernel<float>, gk, NT, 0, stream)((const float*)Q, (const float*)K, (const float*)V, (const float*)dO,
                                                          lse, dsum, (float*)dK, (float*)dV, d, lddo, lddk, lddv, dc);
     } else if (dt == ICK_BF16) {
-        mha_bwd_dq_kernel<bf16><<<gq, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)O,
+        ick_launch(mha_bwd_dq_kernel<bf16>, gq, NT, 0, stream)((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)O,
                                                        (const bf16*)dO, lse, dsum, (bf16*)dQ, d, lddo, lddq, dc);
-        mha_bwd_dkv_kernel<bf16><<<gk, NT, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)dO, lse,
+        ick_launch(mha_bwd_dkv_kernel<bf16>, gk, NT, 0, stream)((const bf16*)Q, (const bf16*)K, (const bf16*)V, (const bf16*)dO, lse,
                                                         dsum, (bf16*)dK, (bf16*)dV, d, lddo, lddk, lddv, dc);
     } else {
         ick_set_error("mha_bwd: bad dtype %d", dt);
@@ -422,10 +426,10 @@ extern "C" int ick_mha_decode(const void* Q, const void* K, const void* V, void*
     const int warps = B * H;
     dim3 grid((warps * 32 + 127) / 128);
     if (dt == ICK_F32)
-        mha_decode_kernel<float><<<grid, 128, 0, stream>>>((const float*)Q, (const float*)K, (const float*)V, (float*)O, B, H, dh,
+        ick_launch(mha_decode_kernel<float>, grid, 128, 0, stream)((const float*)Q, (const float*)K, (const float*)V, (float*)O, B, H, dh,
                                                            ldq, ldk, ldv, ldo, kbatch_stride, vbatch_stride, klen, sl2);
     else if (dt == ICK_BF16)
-        mha_decode_kernel<bf16><<<grid, 128, 0, stream>>>((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, B, H, dh, ldq,
+        ick_launch(mha_decode_kernel<bf16>, grid, 128, 0, stream)((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, B, H, dh, ldq,
                                                           ldk, ldv, ldo, kbatch_stride, vbatch_stride, klen, sl2);
     else {
         ick_set_error("mha_decode: bad dtype %d", dt);

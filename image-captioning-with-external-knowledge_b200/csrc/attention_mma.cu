@@ -479,6 +479,7 @@ __device__ __forceinline__ OwnRows own_rows(int wrow, int g, const DropCfg& drop
 __global__ void __launch_bounds__(32 * NWMAX, 2)
     fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                bf16* __restrict__ O, float* __restrict__ LSE, Dims d, int ldq, int ldo, int ntc, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, ntc);
     ick_resolve_seed(drop);
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     bwd_dq_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                   const bf16* __restrict__ O, const bf16* __restrict__ dO, const float* __restrict__ LSE, float* __restrict__ Dsum,
                   bf16* __restrict__ dQ, Dims d, int ldq, int ldo, int lddo, int lddq, int ntc, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, ntc);
     ick_resolve_seed(drop);
@@ -569,6 +571,7 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                    const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
                    bf16* __restrict__ dV, Dims d, int ldk, int ldv, int lddk, int lddv, int ntc, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, ntc);
     float* Ls = sm.scal;                        // log2-domain LSE of each resident query
@@ -678,6 +681,7 @@ struct PArgs {
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     fwd_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                 bf16* __restrict__ O, float* __restrict__ LSE, PArgs a, int ldq, int ldo, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
     const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
@@ -725,6 +729,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dq_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                    const bf16* __restrict__ O, const bf16* __restrict__ dO, const float* __restrict__ LSE, float* __restrict__ Dsum,
                    bf16* __restrict__ dQ, PArgs a, int ldq, int ldo, int lddo, int lddq, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
     const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
@@ -776,6 +781,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dkv_pkernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                     const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
                     bf16* __restrict__ dV, PArgs a, int ldk, int ldv, int lddk, int lddv, DropCfg drop) {
+    ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
     const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmQ, &tmG);
@@ -941,14 +947,14 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
     if (pa.nstage && use_persistent()) {
         if ((rc = set_smem(fwd_pkernel, true))) return rc;
         const int grid = B * H < num_sms() ? B * H : num_sms();
-        fwd_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
+        ick_launch(fwd_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
         return ick_check_launch("mha_fwd_mma(persistent)");
     }
     if ((rc = set_smem(fwd_kernel))) return rc;
     int nctas, nw;
     split_own(Sq, &nctas, &nw);
     dim3 grid(nctas, H, B);
-    fwd_kernel<<<grid, 32 * nw, smem_bytes(ntc, false), stream>>>(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, d, ldq, ldo, ntc, dc);
+    ick_launch(fwd_kernel, grid, 32 * nw, smem_bytes(ntc, false), stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, d, ldq, ldo, ntc, dc);
     return ick_check_launch("mha_fwd_mma");
 }
 
@@ -974,12 +980,12 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     plan_pipe(nt, false, &pa);
     if (pa.nstage && use_persistent()) {
         if ((rc = set_smem(bwd_dq_pkernel, true))) return rc;
-        bwd_dq_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse, dsum,
+        ick_launch(bwd_dq_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse, dsum,
                                                                         (bf16*)dQ, pa, ldq, ldo, lddo, lddq, dc);
     } else {
         if ((rc = set_smem(bwd_dq_kernel))) return rc;
         split_own(Sq, &nctas, &nw);
-        bwd_dq_kernel<<<dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, false), stream>>>(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse,
+        ick_launch(bwd_dq_kernel, dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, false), stream)(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse,
                                                                                  dsum, (bf16*)dQ, d, ldq, ldo, lddo, lddq, ntc, dc);
     }
     if ((rc = ick_check_launch("mha_bwd_mma(dq)"))) return rc;
@@ -989,13 +995,13 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     plan_pipe(nt, true, &pa);
     if (pa.nstage && use_persistent()) {
         if ((rc = set_smem(bwd_dkv_pkernel, true))) return rc;
-        bwd_dkv_pkernel<<<grid, 32 * (PNW + 1), pipe_smem(pa), stream>>>(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
+        ick_launch(bwd_dkv_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
                                                                          pa, ldk, ldv, lddk, lddv, dc);
         return ick_check_launch("mha_bwd_mma(dkv, persistent)");
     }
     if ((rc = set_smem(bwd_dkv_kernel))) return rc;
     split_own(Sk, &nctas, &nw);
-    bwd_dkv_kernel<<<dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, true), stream>>>(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK,
+    ick_launch(bwd_dkv_kernel, dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, true), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK,
                                                                                  (bf16*)dV, d, ldk, ldv, lddk, lddv, ntc, dc);
     return ick_check_launch("mha_bwd_mma(dkv)");
 }

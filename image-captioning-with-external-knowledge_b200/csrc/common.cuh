@@ -26,6 +26,46 @@ int ick_check_launch(const char* what);
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// ick_pdl_entry(): `launch_dependents` lets the NEXT kernel of the stream be scheduled onto SMs as they drain (its launch
+// latency, CTA ramp-up and barrier/TMEM/tensor-map prologue overlap this kernel's tail), `wait` blocks until the PREVIOUS
+// kernel has completed and its writes are visible.  Nothing before the wait may touch global memory.  Because every
+// kernel waits, completion is transitive along the stream.  ICK_PDL=0 in the environment falls back to plain launches.
+__device__ __forceinline__ void ick_pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ick_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ick_pdl_entry() {
+    ick_pdl_launch();
+    ick_pdl_wait();
+}
+bool ick_pdl_enabled();  // loss_optim.cu
+
+template <typename... KArgs>
+struct IckLauncher {
+    void (*kernel)(KArgs...);
+    dim3 grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    template <typename... Args>
+    void operator()(Args&&... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = ick_pdl_enabled() ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through ick_check_launch()
+    }
+};
+template <typename... KArgs>
+static inline IckLauncher<KArgs...> ick_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    return IckLauncher<KArgs...>{kernel, grid, block, smem, stream};
+}
+
 // ---- dtype conversion -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) entity_encode_fwd_kernel(const float* __r
                                                                 const float* __restrict__ type_emb, const T* __restrict__ wemb,
                                                                 T* __restrict__ out, int variant, int B, int E, int C, int F,
                                                                 int D, int ld, int ldw, int ntypes, int V) {
+    ick_pdl_entry();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * E) return;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) entity_encode_bwd_kernel(const float* __r
                                                                 float* __restrict__ gflat, int type_off, int word_off, int variant,
                                                                 int B, int E, int C, int F, int D, int ld, int ldw, int ntypes,
                                                                 int V) {
+    ick_pdl_entry();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * E) return;
@@ -130,6 +132,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) fact_encode_fwd_kernel(const long long* __restrict__ facts, const T* __restrict__ entenc,
                                                               const float* __restrict__ pred_emb, T* __restrict__ out, int B, int E,
                                                               int F, int D, int ld, int NP) {
+    ick_pdl_entry();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * F) return;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) fact_encode_fwd_kernel(const long long* _
 __global__ void __launch_bounds__(256) fact_encode_bwd_kernel(const float* __restrict__ dFact, const long long* __restrict__ facts,
                                                               float* __restrict__ dEnt, float* __restrict__ gflat, int pred_off,
                                                               int B, int E, int F, int D, int ld, int NP) {
+    ick_pdl_entry();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * F) return;
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(256) caption_embed_fwd_kernel(const long long*
                                                                 const T* __restrict__ factenc, const float* __restrict__ pe,
                                                                 T* __restrict__ out, int B, int Tstride, int t0, int Tn, int V, int E,
                                                                 int F, int D, int ld, int ldw, int pad, float scale, DropCfg drop) {
+    ick_pdl_entry();
     ick_resolve_seed(drop);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restr
                                                                 float* __restrict__ dFact, float* __restrict__ gflat, int word_off,
                                                                 int B, int T_, int V, int E, int F, int D, int ld, int pad, float scale,
                                                                 DropCfg drop) {
+    ick_pdl_entry();
     ick_resolve_seed(drop);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -225,15 +231,30 @@ __global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restr
                              : dFact + ((size_t)b * F + s.idx) * ld;
     const T* g = dX + (size_t)row * ld;
     const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)row);
-    for (int c = lane; c < D; c += 32) {
-        const float v = to_f(g[c]) * scale * ick_drop_mul(drop, rmix, (uint32_t)c);
-        atomicAdd(dst + c, v);
+    // Rows behind the end of a caption carry an exactly-zero gradient (their targets are <pad>, ignored by the loss, and the
+    // causal decoder lets nothing flow back into them) and they all hit the same <pad> embedding row: skip them instead of
+    // serialising thousands of atomic adds of 0.0 on one address.
+    constexpr int MAXC = 16;  // columns per lane: supports D <= 512
+    float v[MAXC];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < D ? to_f(g[c]) : 0.f;
+        any |= v[i] != 0.f;
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) atomicAdd(dst + c, v[i] * scale * ick_drop_mul(drop, rmix, (uint32_t)c));
     }
 }
 
 // ---- pixels: (B, D, P) fp32 channel-major  <->  memory rows (b*M + p, c) ------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) pixels_fwd_kernel(const float* __restrict__ enc, T* __restrict__ mem, int D, int P, int M, int ld) {
+    ick_pdl_entry();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -250,6 +271,7 @@ __global__ void __launch_bounds__(256) pixels_fwd_kernel(const float* __restrict
 
 template <typename T>
 __global__ void __launch_bounds__(256) pixels_bwd_kernel(const T* __restrict__ dmem, float* __restrict__ denc, int D, int P, int M, int ld) {
+    ick_pdl_entry();
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -271,6 +293,7 @@ __global__ void __launch_bounds__(256) pixels_bwd_kernel(const T* __restrict__ d
 __global__ void __launch_bounds__(256) fact_first_mention_kernel(const long long* __restrict__ caps, const long long* __restrict__ facts,
                                                                  int* __restrict__ first_t, int* __restrict__ tmin, int T_, int F,
                                                                  int V, int E) {
+    ick_pdl_entry();
     extern __shared__ int sm[];
     int* sfirst = sm;
     int* spred = sm + F;
@@ -309,6 +332,7 @@ __global__ void __launch_bounds__(128) pred_gate_fwd_kernel(const int* __restric
                                                             const float* __restrict__ WpT, const float* __restrict__ bias,
                                                             const T* __restrict__ h, T* __restrict__ gate, T* __restrict__ hg, int Tn,
                                                             int t0, int F, int D, int ld, int ldp, int NP, int lag) {
+    ick_pdl_entry();
     extern __shared__ int sact[];  // predicate ids of the active facts
     __shared__ int nact;
     const int b = blockIdx.y, tt = blockIdx.x, t = t0 + tt;
@@ -336,6 +360,7 @@ __global__ void __launch_bounds__(128) pred_gate_fwd_kernel(const int* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) gate_mul_bwd_kernel(const T* __restrict__ dHG, const T* __restrict__ h, const T* __restrict__ gate,
                                                            T* __restrict__ dG, T* __restrict__ dH, size_t n) {
+    ick_pdl_entry();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float g = to_f(dHG[i]);
         dG[i] = from_f<T>(g * to_f(h[i]));
@@ -348,15 +373,24 @@ template <typename T>
 __global__ void __launch_bounds__(128) pred_gate_bwd_kernel(const T* __restrict__ dG, const int* __restrict__ tmin,
                                                             const long long* __restrict__ facts, float* __restrict__ gflat, int wp_off,
                                                             int T_, int F, int D, int ld, int NP, int lag) {
+    ick_pdl_entry();
     const int b = blockIdx.y, f = blockIdx.x;
     const int tm = tmin[(size_t)b * F + f];
     if (tm >= FIRST_NONE) return;
     const int p = min(max((int)facts[((size_t)b * F + f) * 3 + 2], 0), NP - 1);
     const int tbeg = max(0, tm + 1 - lag);
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        float s = 0.f;
-        for (int t = tbeg; t < T_; ++t) s += to_f(dG[((size_t)b * T_ + t) * ld + c]);
-        atomicAdd(gflat + wp_off + (size_t)c * NP + p, s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains: the loop is load-latency bound
+        const T* col = dG + (size_t)b * T_ * ld + c;
+        int t = tbeg;
+        for (; t + 3 < T_; t += 4) {
+            s0 += to_f(col[(size_t)t * ld]);
+            s1 += to_f(col[(size_t)(t + 1) * ld]);
+            s2 += to_f(col[(size_t)(t + 2) * ld]);
+            s3 += to_f(col[(size_t)(t + 3) * ld]);
+        }
+        for (; t < T_; ++t) s0 += to_f(col[(size_t)t * ld]);
+        atomicAdd(gflat + wp_off + (size_t)c * NP + p, (s0 + s1) + (s2 + s3));
     }
 }
 
@@ -368,6 +402,7 @@ __global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ 
                                                           const float* __restrict__ bias, const int* __restrict__ first_t,
                                                           float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
                                                           int col0, int lag) {
+    ick_pdl_entry();
     extern __shared__ __align__(16) float hw[];  // [PT_T][Dp]
     const int Dp = (D + 7) & ~7;
     const int b = blockIdx.z, tt0 = blockIdx.y * PT_T;
@@ -409,6 +444,7 @@ __global__ void __launch_bounds__(128) pointer_bwd_ctx_kernel(const T* __restric
                                                               const int* __restrict__ first_t, float* __restrict__ dCtx,
                                                               float* __restrict__ gflat, int bias_off, int T_, int S, int D, int ld,
                                                               int ldds, int col0, int lag) {
+    ick_pdl_entry();
     __shared__ __align__(16) float hs[32][PB_D];
     __shared__ float red[4];
     const int b = blockIdx.z, d0 = blockIdx.y * PB_D;
@@ -463,6 +499,7 @@ __global__ void __launch_bounds__(128) pointer_bwd_h_kernel(const T* __restrict_
                                                             const float* __restrict__ w, const int* __restrict__ first_t,
                                                             T* __restrict__ dH, float* __restrict__ gflat, int w_off, int T_, int S, int D,
                                                             int ld, int ldds, int col0, int lag) {
+    ick_pdl_entry();
     __shared__ __align__(16) float cs[32][PB_D];
     __shared__ int sft[32];
     __shared__ float red[4][PB_D];
@@ -540,10 +577,10 @@ extern "C" int ick_entity_encode_fwd(const float* entities, const long long* fac
     if (B * E == 0) return ICK_OK;
     const int grid = rows_grid((long long)B * E);
     if (dt == ICK_F32)
-        entity_encode_fwd_kernel<float><<<grid, 256, 0, stream>>>(entities, facts, type_emb, (const float*)word_emb, (float*)out, variant, B,
+        ick_launch(entity_encode_fwd_kernel<float>, grid, 256, 0, stream)(entities, facts, type_emb, (const float*)word_emb, (float*)out, variant, B,
                                                                    E, C, F, D, ld, ldw, ntypes, V);
     else if (dt == ICK_BF16)
-        entity_encode_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(entities, facts, type_emb, (const bf16*)word_emb, (bf16*)out, variant, B, E,
+        ick_launch(entity_encode_fwd_kernel<bf16>, grid, 256, 0, stream)(entities, facts, type_emb, (const bf16*)word_emb, (bf16*)out, variant, B, E,
                                                                   C, F, D, ld, ldw, ntypes, V);
     else ICK_BAD_DT("entity_encode_fwd", dt);
     return ick_check_launch("entity_encode_fwd");
@@ -557,10 +594,10 @@ extern "C" int ick_entity_encode_bwd(const float* dEnt, const float* entities, c
     if (B * E == 0) return ICK_OK;
     const int grid = rows_grid((long long)B * E);
     if (dt == ICK_F32)
-        entity_encode_bwd_kernel<float><<<grid, 256, 0, stream>>>(dEnt, entities, facts, type_emb, (const float*)word_emb, gflat, type_off,
+        ick_launch(entity_encode_bwd_kernel<float>, grid, 256, 0, stream)(dEnt, entities, facts, type_emb, (const float*)word_emb, gflat, type_off,
                                                                    word_off, variant, B, E, C, F, D, ld, ldw, ntypes, V);
     else if (dt == ICK_BF16)
-        entity_encode_bwd_kernel<bf16><<<grid, 256, 0, stream>>>(dEnt, entities, facts, type_emb, (const bf16*)word_emb, gflat, type_off,
+        ick_launch(entity_encode_bwd_kernel<bf16>, grid, 256, 0, stream)(dEnt, entities, facts, type_emb, (const bf16*)word_emb, gflat, type_off,
                                                                   word_off, variant, B, E, C, F, D, ld, ldw, ntypes, V);
     else ICK_BAD_DT("entity_encode_bwd", dt);
     return ick_check_launch("entity_encode_bwd");
@@ -572,9 +609,9 @@ extern "C" int ick_fact_encode_fwd(const long long* facts, const void* ent_enc, 
     if (B * F == 0) return ICK_OK;
     const int grid = rows_grid((long long)B * F);
     if (dt == ICK_F32)
-        fact_encode_fwd_kernel<float><<<grid, 256, 0, stream>>>(facts, (const float*)ent_enc, pred_emb, (float*)out, B, E, F, D, ld, NP);
+        ick_launch(fact_encode_fwd_kernel<float>, grid, 256, 0, stream)(facts, (const float*)ent_enc, pred_emb, (float*)out, B, E, F, D, ld, NP);
     else if (dt == ICK_BF16)
-        fact_encode_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(facts, (const bf16*)ent_enc, pred_emb, (bf16*)out, B, E, F, D, ld, NP);
+        ick_launch(fact_encode_fwd_kernel<bf16>, grid, 256, 0, stream)(facts, (const bf16*)ent_enc, pred_emb, (bf16*)out, B, E, F, D, ld, NP);
     else ICK_BAD_DT("fact_encode_fwd", dt);
     return ick_check_launch("fact_encode_fwd");
 }
@@ -582,7 +619,7 @@ extern "C" int ick_fact_encode_fwd(const long long* facts, const void* ent_enc, 
 extern "C" int ick_fact_encode_bwd(const float* dFact, const long long* facts, float* dEnt, float* gflat, int pred_off, int B, int E,
                                    int F, int D, int ld, int NP, cudaStream_t stream) {
     if (B * F == 0) return ICK_OK;
-    fact_encode_bwd_kernel<<<rows_grid((long long)B * F), 256, 0, stream>>>(dFact, facts, dEnt, gflat, pred_off, B, E, F, D, ld, NP);
+    ick_launch(fact_encode_bwd_kernel, rows_grid((long long)B * F), 256, 0, stream)(dFact, facts, dEnt, gflat, pred_off, B, E, F, D, ld, NP);
     return ick_check_launch("fact_encode_bwd");
 }
 
@@ -596,11 +633,11 @@ extern "C" int ick_caption_embed_fwd(const long long* captions, const long long*
     DropCfg dc = make_drop(drop_p, seed, site);
     const int grid = rows_grid((long long)B * Tn);
     if (dt == ICK_F32)
-        caption_embed_fwd_kernel<float><<<grid, 256, 0, stream>>>(captions, masks, (const float*)word_emb, (const float*)ent_enc,
+        ick_launch(caption_embed_fwd_kernel<float>, grid, 256, 0, stream)(captions, masks, (const float*)word_emb, (const float*)ent_enc,
                                                                    (const float*)fact_enc, pe, (float*)out, B, Tstride, t0, Tn, V, E, F, D,
                                                                    ld, ldw, pad, scale, dc);
     else if (dt == ICK_BF16)
-        caption_embed_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(captions, masks, (const bf16*)word_emb, (const bf16*)ent_enc,
+        ick_launch(caption_embed_fwd_kernel<bf16>, grid, 256, 0, stream)(captions, masks, (const bf16*)word_emb, (const bf16*)ent_enc,
                                                                   (const bf16*)fact_enc, pe, (bf16*)out, B, Tstride, t0, Tn, V, E, F, D, ld,
                                                                   ldw, pad, scale, dc);
     else ICK_BAD_DT("caption_embed_fwd", dt);
@@ -611,14 +648,15 @@ extern "C" int ick_caption_embed_bwd(const void* dX, const long long* captions, 
                                      float* gflat, int word_off, int dt, int B, int T, int V, int E, int F, int D, int ld, int pad,
                                      float scale, float drop_p, unsigned seed, unsigned site, cudaStream_t stream) {
     ICK_REQUIRE(F == 0 || dFact != nullptr, "caption_embed_bwd: dFact expected");
+    ICK_REQUIRE(D <= 512, "caption_embed_bwd: D=%d > 512", D);
     if (B * T == 0) return ICK_OK;
     DropCfg dc = make_drop(drop_p, seed, site);
     const int grid = rows_grid((long long)B * T);
     if (dt == ICK_F32)
-        caption_embed_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V,
+        ick_launch(caption_embed_bwd_kernel<float>, grid, 256, 0, stream)((const float*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V,
                                                                    E, F, D, ld, pad, scale, dc);
     else if (dt == ICK_BF16)
-        caption_embed_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V, E,
+        ick_launch(caption_embed_bwd_kernel<bf16>, grid, 256, 0, stream)((const bf16*)dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V, E,
                                                                   F, D, ld, pad, scale, dc);
     else ICK_BAD_DT("caption_embed_bwd", dt);
     return ick_check_launch("caption_embed_bwd");
@@ -628,8 +666,8 @@ extern "C" int ick_pixels_fwd(const float* encoder_out, void* memory, int dt, in
     ICK_REQUIRE(P <= M && D <= ld, "pixels_fwd: bad sizes");
     if (B * P == 0) return ICK_OK;
     dim3 grid((P + 31) / 32, (ld + 31) / 32, B);
-    if (dt == ICK_F32) pixels_fwd_kernel<float><<<grid, 256, 0, stream>>>(encoder_out, (float*)memory, D, P, M, ld);
-    else if (dt == ICK_BF16) pixels_fwd_kernel<bf16><<<grid, 256, 0, stream>>>(encoder_out, (bf16*)memory, D, P, M, ld);
+    if (dt == ICK_F32) ick_launch(pixels_fwd_kernel<float>, grid, 256, 0, stream)(encoder_out, (float*)memory, D, P, M, ld);
+    else if (dt == ICK_BF16) ick_launch(pixels_fwd_kernel<bf16>, grid, 256, 0, stream)(encoder_out, (bf16*)memory, D, P, M, ld);
     else ICK_BAD_DT("pixels_fwd", dt);
     return ick_check_launch("pixels_fwd");
 }
@@ -638,8 +676,8 @@ extern "C" int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt,
     ICK_REQUIRE(P <= M && D <= ld, "pixels_bwd: bad sizes");
     if (B * P == 0) return ICK_OK;
     dim3 grid((P + 31) / 32, (D + 31) / 32, B);
-    if (dt == ICK_F32) pixels_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dmemory, d_encoder_out, D, P, M, ld);
-    else if (dt == ICK_BF16) pixels_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dmemory, d_encoder_out, D, P, M, ld);
+    if (dt == ICK_F32) ick_launch(pixels_bwd_kernel<float>, grid, 256, 0, stream)((const float*)dmemory, d_encoder_out, D, P, M, ld);
+    else if (dt == ICK_BF16) ick_launch(pixels_bwd_kernel<bf16>, grid, 256, 0, stream)((const bf16*)dmemory, d_encoder_out, D, P, M, ld);
     else ICK_BAD_DT("pixels_bwd", dt);
     return ick_check_launch("pixels_bwd");
 }
@@ -648,7 +686,7 @@ extern "C" int ick_fact_first_mention(const long long* captions, const long long
                                       int V, int E, cudaStream_t stream) {
     ICK_REQUIRE(F > 0 && F <= 4096, "fact_first_mention: F=%d out of range", F);
     if (B == 0) return ICK_OK;
-    fact_first_mention_kernel<<<B, 256, 2 * F * sizeof(int), stream>>>(captions, facts, first_t, tmin, T, F, V, E);
+    ick_launch(fact_first_mention_kernel, B, 256, 2 * F * sizeof(int), stream)(captions, facts, first_t, tmin, T, F, V, E);
     return ick_check_launch("fact_first_mention");
 }
 
@@ -660,10 +698,10 @@ extern "C" int ick_pred_gate_fwd(const int* tmin, const long long* facts, const 
     if (B * Tn == 0) return ICK_OK;
     dim3 grid(Tn, B);
     if (dt == ICK_F32)
-        pred_gate_fwd_kernel<float><<<grid, 128, F * sizeof(int), stream>>>(tmin, facts, WpT, bias, (const float*)h, (float*)gate, (float*)hg,
+        ick_launch(pred_gate_fwd_kernel<float>, grid, 128, F * sizeof(int), stream)(tmin, facts, WpT, bias, (const float*)h, (float*)gate, (float*)hg,
                                                                             Tn, t0, F, D, ld, ldp, NP, lag);
     else if (dt == ICK_BF16)
-        pred_gate_fwd_kernel<bf16><<<grid, 128, F * sizeof(int), stream>>>(tmin, facts, WpT, bias, (const bf16*)h, (bf16*)gate, (bf16*)hg, Tn,
+        ick_launch(pred_gate_fwd_kernel<bf16>, grid, 128, F * sizeof(int), stream)(tmin, facts, WpT, bias, (const bf16*)h, (bf16*)gate, (bf16*)hg, Tn,
                                                                            t0, F, D, ld, ldp, NP, lag);
     else ICK_BAD_DT("pred_gate_fwd", dt);
     return ick_check_launch("pred_gate_fwd");
@@ -674,9 +712,9 @@ extern "C" int ick_gate_mul_bwd(const void* dHG, const void* h, const void* gate
     if (n == 0) return ICK_OK;
     const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
     if (dt == ICK_F32)
-        gate_mul_bwd_kernel<float><<<grid, 256, 0, stream>>>((const float*)dHG, (const float*)h, (const float*)gate, (float*)dG, (float*)dH, (size_t)n);
+        ick_launch(gate_mul_bwd_kernel<float>, grid, 256, 0, stream)((const float*)dHG, (const float*)h, (const float*)gate, (float*)dG, (float*)dH, (size_t)n);
     else if (dt == ICK_BF16)
-        gate_mul_bwd_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dHG, (const bf16*)h, (const bf16*)gate, (bf16*)dG, (bf16*)dH, (size_t)n);
+        ick_launch(gate_mul_bwd_kernel<bf16>, grid, 256, 0, stream)((const bf16*)dHG, (const bf16*)h, (const bf16*)gate, (bf16*)dG, (bf16*)dH, (size_t)n);
     else ICK_BAD_DT("gate_mul_bwd", dt);
     return ick_check_launch("gate_mul_bwd");
 }
@@ -686,9 +724,9 @@ extern "C" int ick_pred_gate_bwd(const void* dG, const int* tmin, const long lon
     if (B * F == 0) return ICK_OK;
     dim3 grid(F, B);
     if (dt == ICK_F32)
-        pred_gate_bwd_kernel<float><<<grid, 128, 0, stream>>>((const float*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
+        ick_launch(pred_gate_bwd_kernel<float>, grid, 128, 0, stream)((const float*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
     else if (dt == ICK_BF16)
-        pred_gate_bwd_kernel<bf16><<<grid, 128, 0, stream>>>((const bf16*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
+        ick_launch(pred_gate_bwd_kernel<bf16>, grid, 128, 0, stream)((const bf16*)dG, tmin, facts, gflat, wp_off, T, F, D, ld, NP, lag);
     else ICK_BAD_DT("pred_gate_bwd", dt);
     return ick_check_launch("pred_gate_bwd");
 }
@@ -705,10 +743,10 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
     const size_t smem = (size_t)PT_T * Dp * sizeof(float);
     dim3 grid((S + 127) / 128, (Tn + PT_T - 1) / PT_T, B);
     if (dt == ICK_F32)
-        pointer_fwd_kernel<float><<<grid, 128, smem, stream>>>((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
+        ick_launch(pointer_fwd_kernel<float>, grid, 128, smem, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
                                                                ldscores, col0, lag);
     else if (dt == ICK_BF16)
-        pointer_fwd_kernel<bf16><<<grid, 128, smem, stream>>>((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
+        ick_launch(pointer_fwd_kernel<bf16>, grid, 128, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
                                                               ldscores, col0, lag);
     else ICK_BAD_DT("pointer_fwd", dt);
     return ick_check_launch("pointer_fwd");
@@ -725,14 +763,14 @@ extern "C" int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, c
     }
     dim3 g1((S + 127) / 128, (D + PB_D - 1) / PB_D, B), g2((T + 127) / 128, (D + PB_D - 1) / PB_D, B);
     if (dt == ICK_F32) {
-        pointer_bwd_ctx_kernel<float><<<g1, 128, 0, stream>>>((const float*)dS, (const float*)h, w, first_t, dCtx, gflat, bias_off, T, S, D,
+        ick_launch(pointer_bwd_ctx_kernel<float>, g1, 128, 0, stream)((const float*)dS, (const float*)h, w, first_t, dCtx, gflat, bias_off, T, S, D,
                                                               ld, ldds, col0, lag);
-        pointer_bwd_h_kernel<float><<<g2, 128, 0, stream>>>((const float*)dS, (const float*)h, (const float*)ctx, w, first_t, (float*)dH,
+        ick_launch(pointer_bwd_h_kernel<float>, g2, 128, 0, stream)((const float*)dS, (const float*)h, (const float*)ctx, w, first_t, (float*)dH,
                                                             gflat, w_off, T, S, D, ld, ldds, col0, lag);
     } else if (dt == ICK_BF16) {
-        pointer_bwd_ctx_kernel<bf16><<<g1, 128, 0, stream>>>((const bf16*)dS, (const bf16*)h, w, first_t, dCtx, gflat, bias_off, T, S, D, ld,
+        ick_launch(pointer_bwd_ctx_kernel<bf16>, g1, 128, 0, stream)((const bf16*)dS, (const bf16*)h, w, first_t, dCtx, gflat, bias_off, T, S, D, ld,
                                                              ldds, col0, lag);
-        pointer_bwd_h_kernel<bf16><<<g2, 128, 0, stream>>>((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, (bf16*)dH, gflat,
+        ick_launch(pointer_bwd_h_kernel<bf16>, g2, 128, 0, stream)((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, (bf16*)dH, gflat,
                                                            w_off, T, S, D, ld, ldds, col0, lag);
     } else ICK_BAD_DT("pointer_bwd", dt);
     return ick_check_launch("pointer_bwd");

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const TA* __restrict__ A, 
                                                       const float* __restrict__ bias, const TC* __restrict__ aux, int M,
                                                       int N, int K, int lda, int ldw, int ldc, int ldaux, int epi,
                                                       int accumulate, DropCfg drop) {
+    ick_pdl_entry();
     __shared__ __align__(16) float As[2][BK][LDS];
     __shared__ __align__(16) float Ws[2][BK][LDS];
     ick_resolve_seed(drop);
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const TY* __restrict__ dY, c
                                                     const int* __restrict__ rowoff, const int* __restrict__ colmap,
                                                     const int* __restrict__ biasoff, int M, int N, int K, int ldy, int ldx,
                                                     int m_per_split) {
+    ick_pdl_entry();
     __shared__ __align__(16) float Ys[BK][LDS];
     __shared__ __align__(16) float Xs[BK][LDS];
     const int tid = threadIdx.x;
@@ -207,7 +209,7 @@ template <typename TA, typename TW, typename TC>
 int launch_tn(const void* A, const void* W, void* C, const float* bias, const void* aux, int M, int N, int K, int lda,
               int ldw, int ldc, int ldaux, int epi, int accumulate, DropCfg drop, cudaStream_t st) {
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    gemm_tn_kernel<TA, TW, TC><<<grid, 256, 0, st>>>((const TA*)A, (const TW*)W, (TC*)C, bias, (const TC*)aux, M, N, K, lda,
+    ick_launch(gemm_tn_kernel<TA, TW, TC>, grid, 256, 0, st)((const TA*)A, (const TW*)W, (TC*)C, bias, (const TC*)aux, M, N, K, lda,
                                                      ldw, ldc, ldaux, epi, accumulate, drop);
     return ick_check_launch("gemm_tn_simt");
 }
@@ -250,7 +252,7 @@ extern "C" int ick_wgrad_simt(const void* dY, int y_dt, const void* X, int x_dt,
     splits = (M + mps - 1) / mps;
     dim3 grid((N + BN - 1) / BN, (K + BN - 1) / BN, splits);
 #define ICK_GO(TY, TX)                                                                                               \
-    wgrad_kernel<TY, TX><<<grid, 256, 0, stream>>>((const TY*)dY, (const TX*)X, gflat, rowoff, colmap, biasoff, M, N, K, \
+    ick_launch(wgrad_kernel<TY, TX>, grid, 256, 0, stream)((const TY*)dY, (const TX*)X, gflat, rowoff, colmap, biasoff, M, N, K, \
                                                    ldy, ldx, mps);                                                   \
     return ick_check_launch("wgrad_simt")
     if (y_dt == ICK_F32 && x_dt == ICK_F32) { ICK_GO(float, float); }

@@ -296,13 +296,15 @@ struct TileIter {
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW,
                                                                   const __grid_constant__ CUtensorMap tmC, TnParams p) {
+    ick_pdl_launch();
     extern __shared__ uint8_t smem_raw[];
-    ick_resolve_seed(p.drop);
     const uint32_t wbox = (uint32_t)p.BN * BK * 2;  // one k-block of the weight tile
     const Smem s = p.wstat ? carve(smem_raw, A_STAGE, (uint32_t)p.nkb * wbox) : carve(smem_raw, A_STAGE + wbox);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setup(s, warp, lane, &tmA, &tmW);
     const uint32_t tmem_base = *s.tmem_ptr;
+    ick_pdl_wait();  // barriers, TMEM and tensor maps are ready: from here on the previous kernel's results are needed
+    ick_resolve_seed(p.drop);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -504,6 +506,7 @@ struct WgParams {
 
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                 const __grid_constant__ CUtensorMap tmX, WgParams p) {
+    ick_pdl_launch();
     extern __shared__ uint8_t smem_raw[];
     const int nbx = p.KT / 64;  // X boxes per stage
     const Smem s = carve(smem_raw, A_STAGE + nbx * WG_BOX);
@@ -518,6 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     }
     setup(s, warp, lane, &tmY, &tmX);
     const uint32_t tmem_base = *s.tmem_ptr;
+    ick_pdl_wait();
     const int n_work = p.n_tiles_n * p.n_tiles_k * p.splits;
 
     if (warp == 0) {
@@ -623,24 +627,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const __grid_cons
     teardown(warp, tmem_base);
 }
 
-// sum the row-slice partials and scatter into the flat gradient buffer: G[rowoff[n] + colmap[k]] += sum_s ws[s][n][k]
+// sum the row-slice partials and scatter into the flat gradient buffer: G[rowoff[n] + colmap[k]] += sum_s ws[s][n][k].
+// One thread per 4 consecutive k (Kws is a multiple of 32), 16-byte loads, four splits in flight.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ G, const int* __restrict__ rowoff,
                                                            const int* __restrict__ colmap, int N, int K, int Kws, int splits,
                                                            const float* __restrict__ wsb, const int* __restrict__ biasoff) {
-    const int n = blockIdx.y;
-    if (wsb != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && biasoff[n] >= 0) {
+    ick_pdl_entry();
+    const int q4 = Kws >> 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * q4) return;
+    const int n = (int)(idx / q4), k = (int)(idx % q4) * 4;
+    if (wsb != nullptr && k == 0 && biasoff[n] >= 0) {
         float acc = 0.f;
         for (int sp = 0; sp < splits; ++sp) acc += wsb[(size_t)sp * N + n];
         G[biasoff[n]] += acc;
     }
     const int ro = rowoff[n];
-    if (ro < 0) return;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-        const int cm = colmap ? colmap[k] : k;
-        if (cm < 0) continue;
-        float acc = 0.f;
-        for (int sp = 0; sp < splits; ++sp) acc += ws[((size_t)sp * N + n) * Kws + k];
-        G[ro + cm] += acc;
+    if (ro < 0 || k >= K) return;
+    const float* src = ws + (size_t)n * Kws + k;
+    const size_t stride = (size_t)N * Kws;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    int sp = 0;
+    for (; sp + 3 < splits; sp += 4) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride);
+        const float4 v2 = *reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * stride);
+        const float4 v3 = *reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * stride);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; sp < splits; ++sp) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    const float r[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (k + j >= K) break;
+        const int cm = colmap ? colmap[k + j] : k + j;
+        if (cm >= 0) G[ro + cm] += r[j];
     }
 }
 
@@ -648,6 +675,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // 64 threads x bf16x2 per row (128 contiguous bytes per warp-pair) and 4 row groups reduced through shared memory.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dY, float* __restrict__ G, const int* __restrict__ biasoff,
                                                         int M, int N, int ldy, int rpb) {
+    ick_pdl_entry();
     __shared__ float red[4][128];
     const int tx = threadIdx.x & 63, rg = threadIdx.x >> 6;
     const int c = blockIdx.x * 128 + 2 * tx;
@@ -847,7 +875,7 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
         if (cpp > p.m_tiles) cpp = p.m_tiles;
         grid = cpp * p.n_tiles_n;
     }
-    gemm_tn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmW, tmC, p);
+    ick_launch(gemm_tn_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmC, p);
     return ick_check_launch("gemm_tn_tc");
 }
 
@@ -875,15 +903,29 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     p.stages = (SMEM_DATA - (fuse_bias ? WG_BOX : 0)) / stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     ICK_REQUIRE(p.stages >= 2, "wgrad_tc: tile does not fit");
-    int splits = (num_sms() + tiles - 1) / tiles;
-    const int max_splits = (M + 8 * BK - 1) / (8 * BK);  // at least 8 k-blocks per work item
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    int mps = (M + splits - 1) / splits;
-    mps = (mps + BK - 1) / BK * BK;
-    p.splits = (M + mps - 1) / mps;
-    p.m_per_split = mps;
+    // Row split: every (tile, split) work item costs a pipeline fill + an epilogue, a launch runs ceil(items / SMs) waves of
+    // them, and every split adds a partial tile that the reduce kernel must read back.  Pick the split count that minimises
+    //   waves * (k-blocks per item * t_kb + t_fix) + splits * (partial-tile bytes / reduce bandwidth)
+    // (t_kb scaled by the stage size; constants from the B200 microbenchmarks in profiles/).  The naive ceil(SMs / tiles)
+    // put 152 items on 148 SMs for the 960-wide projections: two waves for one wave's worth of work.
     p.Kws = (K + 31) / 32 * 32;
+    {
+        const int max_splits = (M + 8 * BK - 1) / (8 * BK);  // at least 8 k-blocks per work item
+        const double t_kb = 0.4 * (128 + p.KT) / 448.0, t_fix = 6.0;          // microseconds
+        const double t_red = (double)N * p.Kws * 4 / 1.5e6;                    // per split, ~1.5 TB/s out of L2
+        double best = 1e30;
+        int best_mps = (M + BK - 1) / BK * BK;
+        for (int sp = 1; sp <= (max_splits > 0 ? max_splits : 1); ++sp) {
+            int mps = (M + sp - 1) / sp;
+            mps = (mps + BK - 1) / BK * BK;
+            const int real = (M + mps - 1) / mps;
+            const int waves = (tiles * real + num_sms() - 1) / num_sms();
+            const double t = waves * ((mps / BK) * t_kb + t_fix) + real * t_red;
+            if (t < best - 1e-9) { best = t; best_mps = mps; }
+        }
+        p.m_per_split = best_mps;
+        p.splits = (M + best_mps - 1) / best_mps;
+    }
     const long long need = (long long)p.splits * N * (p.Kws + 1) * 4;
     p.ws = (workspace != nullptr && workspace_bytes >= need && (((uintptr_t)workspace) & 15) == 0) ? (float*)workspace : nullptr;
     p.wsb = (p.ws != nullptr && fuse_bias) ? p.ws + (size_t)p.splits * N * p.Kws : nullptr;
@@ -892,17 +934,18 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     if ((rc = make_tmap(&tmX, X, K, M, ldx, BK))) return rc;
     const int n_work = tiles * p.splits;
     const int grid = n_work < num_sms() ? n_work : num_sms();
-    wgrad_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmY, tmX, p);
+    ick_launch(wgrad_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmY, tmX, p);
     if ((rc = ick_check_launch("wgrad_tc"))) return rc;
     if (p.ws != nullptr) {
-        dim3 rgrid((K + 255) / 256, N);
-        wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, gflat, rowoff, colmap, N, K, p.Kws, p.splits, p.wsb, biasoff);
+        const long long nthreads = (long long)N * (p.Kws / 4);
+        const int rgrid = (int)((nthreads + 255) / 256);
+        ick_launch(wgrad_reduce_kernel, rgrid, 256, 0, stream)(p.ws, gflat, rowoff, colmap, N, K, p.Kws, p.splits, p.wsb, biasoff);
         if ((rc = ick_check_launch("wgrad_reduce"))) return rc;
     }
     if (biasoff && !fuse_bias) {
         const int rpb = 256;
         dim3 bgrid((N + 127) / 128, (M + rpb - 1) / rpb);
-        bias_grad_kernel<<<bgrid, 256, 0, stream>>>((const bf16*)dY, gflat, biasoff, M, N, ldy, rpb);
+        ick_launch(bias_grad_kernel, bgrid, 256, 0, stream)((const bf16*)dY, gflat, biasoff, M, N, ldy, rpb);
         return ick_check_launch("bias_grad");
     }
     return ICK_OK;

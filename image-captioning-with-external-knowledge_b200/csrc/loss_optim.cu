@@ -2,6 +2,8 @@
 //   masked cross-entropy  = pack_padded_sequence + CrossEntropyLoss(ignore_index=<pad>)      G/train.py:275-281
 //   clamp + Adam + repack = ut.clip_gradient (G/utils.py:75-85) + torch.optim.Adam step      G/train.py:287-292
 //   greedy select         = argmax / top-2 / repetition clean-up state machine of predict()  G/models.py:409-442
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ickb200.h"
 
@@ -21,6 +23,7 @@ template <typename TD>
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ scores, const long long* __restrict__ caps,
                                                  const int* __restrict__ decode_len, float* __restrict__ loss_acc, TD* __restrict__ dS,
                                                  int T_, int W, int lds, int ldd, int pad) {
+    ick_pdl_entry();
     __shared__ float sm[8], sl[8];
     __shared__ float s_lse;
     const int row = blockIdx.x, b = row / T_, t = row % T_;
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float grad_scale, const int* __restrict__ dstA, const int* __restrict__ dstB,
                                                    const int* __restrict__ dstC, T* __restrict__ packT, float* __restrict__ packF,
                                                    int update, const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
+    ick_pdl_entry();
     float gs = grad_scale;
     if (count) gs /= fmaxf(count[0], 1.f);
     if (step_dev) {  // bias corrections from a device-resident step counter (CUDA-graph replay)
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) cast2d_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long rows, int cols, int lds,
                                                      int ldd) {
+    ick_pdl_entry();
     const long long total = rows * ldd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / ldd;
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(256) cast2d_kernel(const TS* __restrict__ src,
 
 template <typename T>
 __global__ void __launch_bounds__(256) accum_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
+    ick_pdl_entry();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] += to_f(src[i]);
 }
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(256) accum_f32_kernel(const T* __restrict__ sr
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int cols, int ld,
                                                      int rows_per_block) {
+    ick_pdl_entry();
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     for (int c = threadIdx.x; c < cols; c += blockDim.x) {
         float s = 0.f;
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
                                                             int* __restrict__ second, long long* __restrict__ captions,
                                                             long long* __restrict__ masks, int* __restrict__ done, float* __restrict__ margins,
                                                             int step, int Tmax, int V, int E, int has_facts, int end_tok) {
+    ick_pdl_entry();
     __shared__ Top2 st[8];
     const int b = blockIdx.x;
     if (done[b]) return;
@@ -213,9 +221,9 @@ extern "C" int ick_ce_fwd_bwd(const float* scores, const long long* captions_sor
     ICK_REQUIRE(dscores == nullptr || ldd >= W, "ce: ldd < W");
     if (B == 0) return ICK_OK;
     if (dscores == nullptr || dt == ICK_F32)
-        ce_kernel<float><<<B * T, 256, 0, stream>>>(scores, captions_sorted, decode_len, loss_acc, (float*)dscores, T, W, lds, ldd, pad);
+        ick_launch(ce_kernel<float>, B * T, 256, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (float*)dscores, T, W, lds, ldd, pad);
     else if (dt == ICK_BF16)
-        ce_kernel<bf16><<<B * T, 256, 0, stream>>>(scores, captions_sorted, decode_len, loss_acc, (bf16*)dscores, T, W, lds, ldd, pad);
+        ick_launch(ce_kernel<bf16>, B * T, 256, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (bf16*)dscores, T, W, lds, ldd, pad);
     else {
         ick_set_error("ce: bad dtype %d", dt);
         return ICK_ERR_UNSUPPORTED;
@@ -234,10 +242,10 @@ extern "C" int ick_adam_step(float* p, const float* g, float* m, float* v, long 
     if (n == 0) return ICK_OK;
     const float bc2s = sqrtf(bias_corr2);
     if (dt == ICK_F32)
-        adam_kernel<float><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
+        ick_launch(adam_kernel<float>, ew_grid(n), 256, 0, stream)(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
                                                            dstA, dstB, dstC, (float*)packT, packF, update, step_dev, lr_dev);
     else if (dt == ICK_BF16)
-        adam_kernel<bf16><<<ew_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
+        ick_launch(adam_kernel<bf16>, ew_grid(n), 256, 0, stream)(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
                                                           dstA, dstB, dstC, (bf16*)packT, packF, update, step_dev, lr_dev);
     else {
         ick_set_error("adam: bad dtype %d", dt);
@@ -252,13 +260,13 @@ extern "C" int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, lo
     if (rows * ldd == 0) return ICK_OK;
     const int grid = ew_grid(rows * ldd);
     if (src_dt == ICK_F32 && dst_dt == ICK_BF16)
-        cast2d_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)src, (bf16*)dst, rows, cols, lds, ldd);
+        ick_launch(cast2d_kernel<float, bf16>, grid, 256, 0, stream)((const float*)src, (bf16*)dst, rows, cols, lds, ldd);
     else if (src_dt == ICK_F32 && dst_dt == ICK_F32)
-        cast2d_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)src, (float*)dst, rows, cols, lds, ldd);
+        ick_launch(cast2d_kernel<float, float>, grid, 256, 0, stream)((const float*)src, (float*)dst, rows, cols, lds, ldd);
     else if (src_dt == ICK_BF16 && dst_dt == ICK_F32)
-        cast2d_kernel<bf16, float><<<grid, 256, 0, stream>>>((const bf16*)src, (float*)dst, rows, cols, lds, ldd);
+        ick_launch(cast2d_kernel<bf16, float>, grid, 256, 0, stream)((const bf16*)src, (float*)dst, rows, cols, lds, ldd);
     else if (src_dt == ICK_BF16 && dst_dt == ICK_BF16)
-        cast2d_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)src, (bf16*)dst, rows, cols, lds, ldd);
+        ick_launch(cast2d_kernel<bf16, bf16>, grid, 256, 0, stream)((const bf16*)src, (bf16*)dst, rows, cols, lds, ldd);
     else {
         ick_set_error("cast2d: bad dtypes %d -> %d", src_dt, dst_dt);
         return ICK_ERR_UNSUPPORTED;
@@ -268,8 +276,8 @@ extern "C" int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, lo
 
 extern "C" int ick_accum_f32(const void* src, int dt, float* dst, long long n, cudaStream_t stream) {
     if (n == 0) return ICK_OK;
-    if (dt == ICK_F32) accum_f32_kernel<float><<<ew_grid(n), 256, 0, stream>>>((const float*)src, dst, n);
-    else if (dt == ICK_BF16) accum_f32_kernel<bf16><<<ew_grid(n), 256, 0, stream>>>((const bf16*)src, dst, n);
+    if (dt == ICK_F32) ick_launch(accum_f32_kernel<float>, ew_grid(n), 256, 0, stream)((const float*)src, dst, n);
+    else if (dt == ICK_BF16) ick_launch(accum_f32_kernel<bf16>, ew_grid(n), 256, 0, stream)((const bf16*)src, dst, n);
     else {
         ick_set_error("accum_f32: bad dtype %d", dt);
         return ICK_ERR_UNSUPPORTED;
@@ -281,8 +289,8 @@ extern "C" int ick_colsum(const void* x, int dt, float* out, long long rows, int
     if (rows == 0 || cols == 0) return ICK_OK;
     const int rpb = 64;
     const int grid = (int)((rows + rpb - 1) / rpb);
-    if (dt == ICK_F32) colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, out, rows, cols, ld, rpb);
-    else if (dt == ICK_BF16) colsum_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)x, out, rows, cols, ld, rpb);
+    if (dt == ICK_F32) ick_launch(colsum_kernel<float>, grid, 256, 0, stream)((const float*)x, out, rows, cols, ld, rpb);
+    else if (dt == ICK_BF16) ick_launch(colsum_kernel<bf16>, grid, 256, 0, stream)((const bf16*)x, out, rows, cols, ld, rpb);
     else {
         ick_set_error("colsum: bad dtype %d", dt);
         return ICK_ERR_UNSUPPORTED;
@@ -295,7 +303,7 @@ extern "C" int ick_greedy_select(const float* scores, int W, int lds, long long*
                                  int end_tok, cudaStream_t stream) {
     ICK_REQUIRE(B >= 0 && step >= 0 && step < Tmax && W >= 2, "greedy_select: bad sizes");
     if (B == 0) return ICK_OK;
-    greedy_select_kernel<<<B, 256, 0, stream>>>(scores, W, lds, output, second, captions, masks, done, margins, step, Tmax, V, E, has_facts,
+    ick_launch(greedy_select_kernel, B, 256, 0, stream)(scores, W, lds, output, second, captions, masks, done, margins, step, Tmax, V, E, has_facts,
                                                 end_tok);
     return ick_check_launch("greedy_select");
 }
@@ -321,6 +329,15 @@ int ick_check_launch(const char* what) {
 extern "C" const char* ick_last_error(void) { return g_err; }
 static const uint32_t* g_seed_source = nullptr;
 const uint32_t* ick_seed_source() { return g_seed_source; }
+
+bool ick_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 extern "C" int ick_set_seed_source(const unsigned* seed_dev) {
     g_seed_source = seed_dev;
     return ICK_OK;

@@ -17,12 +17,218 @@ struct RowMap {
     }
 };
 
+
+// ---- specialised kernels for the model width (compile-time D / LD: no per-pair predicates, address or loop arithmetic) ----
+// Same arithmetic contract as the generic kernels below; the profile of the generic backward kernel showed it issue-bound
+// (IMAD / ISETP / BRA were a third of all instructions), so everything that depends on d is folded at compile time, the
+// normalisation is written as FMAs and the per-row scalars are hoisted.
+template <int NP, int I>
+__device__ __forceinline__ bool pair_valid(int lane) {
+    if constexpr (32 * I + 31 < NP) return true;
+    else if constexpr (32 * I >= NP) return false;
+    else return lane + 32 * I < NP;
+}
+
+template <typename T, int D, int LD, int MINB>
+__global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __restrict__ X, T* __restrict__ SUB,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    T* __restrict__ Y, float* __restrict__ MEAN, float* __restrict__ RSTD,
+                                                                    int rows, float eps, RowMap ymap, DropCfg drop) {
+    ick_pdl_entry();
+    ick_resolve_seed(drop);
+    constexpr int NP = D / 2, NPL = LD / 2, NI = (NPL + 31) / 32;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool has_x = X != nullptr;
+    const bool dropping = drop.thr != 0u;
+    float2 gm[NI], bt[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int p = lane + 32 * i;
+        const bool ok = p < NP;
+        gm[i] = ok ? *reinterpret_cast<const float2*>(gamma + 2 * p) : make_float2(0.f, 0.f);
+        bt[i] = ok ? *reinterpret_cast<const float2*>(beta + 2 * p) : make_float2(0.f, 0.f);
+    }
+    for (int r = warp; r < rows; r += nwarps) {
+        const T* x = X + (size_t)r * LD;
+        T* s = SUB + (size_t)r * LD;
+        float2 v[NI], xr[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {  // all loads of the row first (memory-level parallelism)
+            const int p = lane + 32 * i;
+            v[i] = make_float2(0.f, 0.f);
+            xr[i] = make_float2(0.f, 0.f);
+            if (p < NP) {
+                v[i] = ld2(s + 2 * p);
+                if (has_x) xr[i] = ld2(x + 2 * p);
+            }
+        }
+        float sum = 0.f;
+        if (dropping) {
+            const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)r);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int p = lane + 32 * i;
+                const uint32_t hsh = ick_pairhash_idx(rmix, (uint32_t)p);
+                v[i].x *= ick_keep_lo(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                v[i].y *= ick_keep_hi(hsh, drop.thr) ? drop.inv_keep : 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            v[i].x += xr[i].x;
+            v[i].y += xr[i].y;
+            if (p < NP) st2(s + 2 * p, v[i].x, v[i].y);
+            sum += v[i].x + v[i].y;
+        }
+        const float mean = warp_sum(sum) * (1.0f / (float)D);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            const float a = v[i].x - mean, b = v[i].y - mean;
+            if (p < NP) var += a * a + b * b;
+        }
+        const float rstd = rsqrtf(warp_sum(var) * (1.0f / (float)D) + eps);
+        const float nmr = -mean * rstd;
+        T* y = Y + ymap.map(r) * LD;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            if (p < NP) {
+                st2(y + 2 * p, fmaf(fmaf(v[i].x, rstd, nmr), gm[i].x, bt[i].x), fmaf(fmaf(v[i].y, rstd, nmr), gm[i].y, bt[i].y));
+            } else if (p < NPL) {
+                st2(y + 2 * p, 0.f, 0.f);  // zero the pad columns [D, LD)
+            }
+        }
+        if (lane == 0) {
+            MEAN[r] = mean;
+            RSTD[r] = rstd;
+        }
+    }
+}
+
+template <typename T, int D, int LD, int MINB>
+__global__ void __launch_bounds__(256, MINB) add_ln_bwd_fast_kernel(const T* __restrict__ DY, const T* __restrict__ S,
+                                                                    const float* __restrict__ MEAN, const float* __restrict__ RSTD,
+                                                                    const float* __restrict__ gamma, T* DRES, T* __restrict__ DSUB,
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                                                                    RowMap dymap, int acc_res, DropCfg drop) {
+    ick_pdl_entry();
+    constexpr int NP = D / 2, NPL = LD / 2, NI = (NPL + 31) / 32;
+    __shared__ float sg[2 * NI * 32], sb[2 * NI * 32];
+    ick_resolve_seed(drop);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool dropping = drop.thr != 0u;
+    const bool has_res = DRES != nullptr, has_sub = DSUB != nullptr;
+    for (int i = threadIdx.x; i < 2 * NI * 32; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    float2 gm[NI], ag[NI], ab[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int p = lane + 32 * i;
+        gm[i] = p < NP ? *reinterpret_cast<const float2*>(gamma + 2 * p) : make_float2(0.f, 0.f);
+        ag[i] = make_float2(0.f, 0.f);
+        ab[i] = make_float2(0.f, 0.f);
+    }
+    constexpr float inv_d = 1.0f / (float)D;
+    for (int r = warp; r < rows; r += nwarps) {
+        const T* dy = DY + dymap.map(r) * LD;
+        const T* s = S + (size_t)r * LD;
+        const float mean = MEAN[r], rstd = RSTD[r];
+        const float nmr = -mean * rstd;
+        float2 g[NI], xh[NI];
+        float sum_g = 0.f, sum_gx = 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            g[i] = make_float2(0.f, 0.f);
+            xh[i] = make_float2(0.f, 0.f);
+            if (p < NP) {
+                g[i] = ld2(dy + 2 * p);
+                xh[i] = ld2(s + 2 * p);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            const bool ok = p < NP;
+            xh[i].x = ok ? fmaf(xh[i].x, rstd, nmr) : 0.f;
+            xh[i].y = ok ? fmaf(xh[i].y, rstd, nmr) : 0.f;
+            ag[i].x = fmaf(g[i].x, xh[i].x, ag[i].x);
+            ag[i].y = fmaf(g[i].y, xh[i].y, ag[i].y);
+            ab[i].x += g[i].x;
+            ab[i].y += g[i].y;
+            g[i].x *= gm[i].x;
+            g[i].y *= gm[i].y;
+            sum_g += g[i].x + g[i].y;
+            sum_gx = fmaf(g[i].x, xh[i].x, fmaf(g[i].y, xh[i].y, sum_gx));
+        }
+        const float c1 = warp_sum(sum_g) * inv_d * rstd;
+        const float c2 = warp_sum(sum_gx) * inv_d * rstd;
+        T* dres = DRES + (size_t)r * LD;
+        T* dsub = DSUB + (size_t)r * LD;
+        const uint32_t rmix = dropping ? ick_rowmix(drop.seed, drop.site, (uint64_t)r) : 0u;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int p = lane + 32 * i;
+            if (p < NP) {
+                float a = fmaf(-xh[i].x, c2, fmaf(g[i].x, rstd, -c1));
+                float b = fmaf(-xh[i].y, c2, fmaf(g[i].y, rstd, -c1));
+                if (has_sub) {
+                    float k0 = 1.f, k1 = 1.f;
+                    if (dropping) {
+                        const uint32_t hsh = ick_pairhash_idx(rmix, (uint32_t)p);
+                        k0 = ick_keep_lo(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                        k1 = ick_keep_hi(hsh, drop.thr) ? drop.inv_keep : 0.f;
+                    }
+                    st2(dsub + 2 * p, a * k0, b * k1);
+                }
+                if (has_res) {
+                    if (acc_res) {
+                        const float2 o = ld2(dres + 2 * p);
+                        a += o.x;
+                        b += o.y;
+                    }
+                    st2(dres + 2 * p, a, b);
+                }
+            } else if (p < NPL) {
+                if (has_sub) st2(dsub + 2 * p, 0.f, 0.f);
+                if (has_res && !acc_res) st2(dres + 2 * p, 0.f, 0.f);
+            }
+        }
+    }
+    // block reduction of the per-lane dgamma/dbeta partials, then one atomic per column per CTA
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int p = lane + 32 * i;
+        if (p < NP) {
+            atomicAdd(&sg[2 * p], ag[i].x);
+            atomicAdd(&sg[2 * p + 1], ag[i].y);
+            atomicAdd(&sb[2 * p], ab[i].x);
+            atomicAdd(&sb[2 * p + 1], ab[i].y);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        if (dgamma) atomicAdd(dgamma + c, sg[c]);
+        if (dbeta) atomicAdd(dbeta + c, sb[c]);
+    }
+}
+
+constexpr int FAST_D = 300, FAST_LD = 320;  // the model width of all three reference variants (emb_dim 300, G/train.py:28)
+
 template <typename T>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const T* __restrict__ X, T* __restrict__ SUB,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          T* __restrict__ Y, float* __restrict__ MEAN, float* __restrict__ RSTD,
                                                          int rows, int d, int ldx, int lds, int ldy, float eps, RowMap ymap,
                                                          DropCfg drop) {
+    ick_pdl_entry();
     ick_resolve_seed(drop);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -97,6 +303,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ D
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
                                                          int lddy, int lds, int ldres, int ldsub, RowMap dymap, int acc_res,
                                                          DropCfg drop) {
+    ick_pdl_entry();
     __shared__ float sg[2 * MAXP * 32], sb[2 * MAXP * 32];
     ick_resolve_seed(drop);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -202,12 +409,22 @@ extern "C" int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, cons
     if (rows == 0) return ICK_OK;
     RowMap m{map_s_in, map_s_out, map_off};
     DropCfg dc = make_drop(drop_p, seed, site);
+    if (d == FAST_D && ldx == FAST_LD && lds == FAST_LD && ldy == FAST_LD && (dt == ICK_F32 || dt == ICK_BF16)) {
+        const int blocks = min((rows + 7) / 8, 148 * 4);
+        if (dt == ICK_F32)
+            ick_launch(add_ln_fwd_fast_kernel<float, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const float*)x, (float*)sub, gamma, beta, (float*)y,
+                                                                                               mean, rstd, rows, eps, m, dc);
+        else
+            ick_launch(add_ln_fwd_fast_kernel<bf16, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const bf16*)x, (bf16*)sub, gamma, beta, (bf16*)y,
+                                                                                              mean, rstd, rows, eps, m, dc);
+        return ick_check_launch("add_ln_fwd");
+    }
     const int blocks = min((rows + 7) / 8, 148 * 8);
     if (dt == ICK_F32)
-        add_ln_fwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (float*)sub, gamma, beta, (float*)y, mean, rstd, rows,
+        ick_launch(add_ln_fwd_kernel<float>, blocks, 256, 0, stream)((const float*)x, (float*)sub, gamma, beta, (float*)y, mean, rstd, rows,
                                                              d, ldx, lds, ldy, eps, m, dc);
     else if (dt == ICK_BF16)
-        add_ln_fwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)x, (bf16*)sub, gamma, beta, (bf16*)y, mean, rstd, rows, d,
+        ick_launch(add_ln_fwd_kernel<bf16>, blocks, 256, 0, stream)((const bf16*)x, (bf16*)sub, gamma, beta, (bf16*)y, mean, rstd, rows, d,
                                                             ldx, lds, ldy, eps, m, dc);
     else {
         ick_set_error("add_ln_fwd: bad dtype %d", dt);
@@ -226,13 +443,26 @@ extern "C" int ick_add_ln_bwd(const void* dy, const void* s, const float* mean, 
     if (rows == 0) return ICK_OK;
     RowMap m{map_s_in, map_s_out, map_off};
     DropCfg dc = make_drop(drop_p, seed, site);
+    if (d == FAST_D && lddy == FAST_LD && lds == FAST_LD && (dres == nullptr || ldres == FAST_LD) && (dsub == nullptr || ldsub == FAST_LD) &&
+        (dt == ICK_F32 || dt == ICK_BF16)) {
+        const int blocks = min((rows + 7) / 8, 148 * 3);
+        if (dt == ICK_F32)
+            ick_launch(add_ln_bwd_fast_kernel<float, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const float*)dy, (const float*)s, mean, rstd, gamma,
+                                                                                               (float*)dres, (float*)dsub, dgamma, dbeta, rows, m,
+                                                                                               acc_res, dc);
+        else
+            ick_launch(add_ln_bwd_fast_kernel<bf16, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const bf16*)dy, (const bf16*)s, mean, rstd, gamma,
+                                                                                              (bf16*)dres, (bf16*)dsub, dgamma, dbeta, rows, m,
+                                                                                              acc_res, dc);
+        return ick_check_launch("add_ln_bwd");
+    }
     const int blocks = min((rows + 7) / 8, 148 * 2);
     if (dt == ICK_F32)
-        add_ln_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dy, (const float*)s, mean, rstd, gamma, (float*)dres,
+        ick_launch(add_ln_bwd_kernel<float>, blocks, 256, 0, stream)((const float*)dy, (const float*)s, mean, rstd, gamma, (float*)dres,
                                                              (float*)dsub, dgamma, dbeta, rows, d, lddy, lds, ldres, ldsub, m,
                                                              acc_res, dc);
     else if (dt == ICK_BF16)
-        add_ln_bwd_kernel<bf16><<<blocks, 256, 0, stream>>>((const bf16*)dy, (const bf16*)s, mean, rstd, gamma, (bf16*)dres,
+        ick_launch(add_ln_bwd_kernel<bf16>, blocks, 256, 0, stream)((const bf16*)dy, (const bf16*)s, mean, rstd, gamma, (bf16*)dres,
                                                             (bf16*)dsub, dgamma, dbeta, rows, d, lddy, lds, ldres, ldsub, m, acc_res,
                                                             dc);
     else {

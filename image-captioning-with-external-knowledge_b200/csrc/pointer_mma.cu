@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(NT) pointer_fwd_mma_kernel(const bf16* __restr
                                                              const float* __restrict__ bias, const int* __restrict__ first_t,
                                                              float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
                                                              int col0, int lag, int Tp, int KP) {
+    ick_pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
     const int PLD = KP + 8;
     bf16* hw = reinterpret_cast<bf16*>(smem);  // [Tp][PLD]  h * w
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
                                                              float* __restrict__ dCtx, bf16* __restrict__ dH, float* __restrict__ gflat,
                                                              int w_off, int bias_off, int T, int S, int D, int ld, int ldds, int col0, int lag,
                                                              int Tp, int Sp) {
+    ick_pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
     const int DLD = Sp + 8;
     bf16* ds = reinterpret_cast<bf16*>(smem);  // [Tp][DLD]  mask * dS of this image
@@ -127,6 +129,30 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     float bsum = 0.f;
     const bool pair_ok = ((col0 | ldds) & 1) == 0;
     const int sp2 = Sp / 2;
+    // Unmasked head whose slice starts on a 16-byte boundary (the entity head: col0 = V): 8 gradients per load, four loads in
+    // flight per thread.  The tail chunk is cut at S (the columns behind it belong to the next head).
+    const bool vec_ok = first_t == nullptr && ((col0 | ldds) & 7) == 0 && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
+    if (vec_ok) {
+        const int sp8 = Sp / 8;
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < Tp * sp8; idx += NT) {
+            const int t = idx / sp8, s8 = (idx % sp8) * 8;
+            uint4 v = zero4();
+            if (t < T && s8 < S) {
+                v = *reinterpret_cast<const uint4*>(dS + ((size_t)b * T + t) * ldds + col0 + s8);
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 f = __bfloat1622float2(hp[i]);
+                    if (s8 + 2 * i >= S) f.x = 0.f;
+                    if (s8 + 2 * i + 1 >= S) f.y = 0.f;
+                    if (s8 + 8 > S) hp[i] = __floats2bfloat162_rn(f.x, f.y);
+                    bsum += f.x + f.y;
+                }
+            }
+            *reinterpret_cast<uint4*>(ds + (size_t)t * DLD + s8) = v;
+        }
+    } else
     for (int idx = threadIdx.x; idx < Tp * sp2; idx += NT) {
         const int t = idx / sp2, s = (idx % sp2) * 2;
         float v0 = 0.f, v1 = 0.f;
@@ -267,7 +293,7 @@ int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const fl
     int rc = set_smem(pointer_fwd_mma_kernel);
     if (rc) return rc;
     dim3 grid((S + CW - 1) / CW, B);
-    pointer_fwd_mma_kernel<<<grid, NT, smem, stream>>>((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld, ldscores,
+    ick_launch(pointer_fwd_mma_kernel, grid, NT, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld, ldscores,
                                                        col0, lag, Tp, KP);
     return ick_check_launch("pointer_fwd_mma");
 }
@@ -281,7 +307,7 @@ int ick_pointer_bwd_mma(const void* dS, const void* h, const void* ctx, const fl
     int rc = set_smem(pointer_bwd_mma_kernel);
     if (rc) return rc;
     dim3 grid((D + CW - 1) / CW, B);
-    pointer_bwd_mma_kernel<<<grid, NT, smem, stream>>>((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, dCtx, (bf16*)dH, gflat, w_off,
+    ick_launch(pointer_bwd_mma_kernel, grid, NT, smem, stream)((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, dCtx, (bf16*)dH, gflat, w_off,
                                                        bias_off, T, S, D, ld, ldds, col0, lag, Tp, Sp);
     return ick_check_launch("pointer_bwd_mma");
 }

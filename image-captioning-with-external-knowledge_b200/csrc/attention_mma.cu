@@ -626,7 +626,8 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
 // load is exposed.  The 16-row own slabs of successive items are dealt round-robin to the compute warps (global slab number
 // modulo PNW), which keeps the warps balanced to within one slab over the whole launch.
 // =============================================================================================================================
-constexpr int PNW = 15;
+constexpr int PNW_KV = 15;  // compute warps of the dK/dV kernel (128 registers per thread)
+constexpr int PNW_Q = 19;   // compute warps of the forward / dQ kernels (their tile bodies fit in 96 registers: more warps to hide latency)
 constexpr int PBAR = CH + 2;  // mbarriers of a stage: full[CH] (one per tile), scalars-ready, empty
 struct Pipe {
     uint32_t bars, data, stage_bytes;
@@ -639,6 +640,7 @@ struct Pipe {
     __device__ __forceinline__ uint32_t t1(int s) const { return t0(s) + ntc * TILE_BYTES; }
     __device__ __forceinline__ float* scal(int s) const { return (float*)(gen + (size_t)s * stage_bytes + 2 * ntc * TILE_BYTES); }
 };
+template <int PNW>
 __device__ __forceinline__ Pipe make_pipe(uint8_t* raw, int ntc, int nstage, uint32_t stage_bytes, const CUtensorMap* a, const CUtensorMap* b) {
     uint8_t* p = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     Pipe pp;
@@ -670,6 +672,7 @@ __device__ __forceinline__ void produce_item(const Pipe& pp, int s, const CUtens
     }
 }
 // first own slab of compute warp `warp` in local item `li` (slabs are numbered globally: li * nslabs + slab)
+template <int PNW>
 __device__ __forceinline__ int first_slab(int li, int nslabs, int warp) { return (warp + PNW - (int)(((long long)li * nslabs) % PNW)) % PNW; }
 
 struct PArgs {
@@ -678,13 +681,14 @@ struct PArgs {
     uint32_t stage_bytes;
 };
 
+template <int PNW>
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     fwd_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                 bf16* __restrict__ O, float* __restrict__ LSE, PArgs a, int ldq, int ldo, DropCfg drop) {
     ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
-    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
+    const Pipe pp = make_pipe<PNW>(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
     ick_resolve_seed(drop);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int n_items = d.B * d.H;
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
         const int s = li % a.nstage, b = item / d.H, h = item % d.H;
         const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
-        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+        for (int slab = first_slab<PNW>(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
             const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, true);
             uint32_t qa[2][4];
             load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
@@ -725,6 +729,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     }
 }
 
+template <int PNW>
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dq_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
                    const bf16* __restrict__ O, const bf16* __restrict__ dO, const float* __restrict__ LSE, float* __restrict__ Dsum,
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
-    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
+    const Pipe pp = make_pipe<PNW>(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
     ick_resolve_seed(drop);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int n_items = d.B * d.H;
@@ -754,7 +759,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
         const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
         const bf16* Gb = dO + (size_t)b * d.Sq * lddo + h * HD;
         const float* L = LSE + ((size_t)b * d.H + h) * d.Sq;
-        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+        for (int slab = first_slab<PNW>(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
             const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, true);
             uint32_t qa[2][4], ga[2][4];
             load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
@@ -777,6 +782,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     }
 }
 
+template <int PNW>
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dkv_pkernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                     const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
@@ -784,7 +790,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
-    const Pipe pp = make_pipe(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmQ, &tmG);
+    const Pipe pp = make_pipe<PNW>(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmQ, &tmG);
     ick_resolve_seed(drop);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int n_items = d.B * d.H;
@@ -812,7 +818,7 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
         const float* Ls = pp.scal(s);
         const float* Ds = Ls + a.ntc * TK;
         const uint32_t* Rm = (const uint32_t*)(Ds + a.ntc * TK);
-        for (int slab = first_slab(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
+        for (int slab = first_slab<PNW>(li, a.nslabs, warp); slab < a.nslabs; slab += PNW) {
             const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, false);
             uint32_t ka[2][4], va[2][4];
             load_own(K + (size_t)b * d.Sk * ldk + h * HD, ldk, r.r0, r.r1, d.Sk, d.dh, tq, ka);
@@ -906,6 +912,14 @@ int num_sms() {
     }
     return n;
 }
+bool wide_q() {  // ICK_ATTN_QWARPS=19 selects the 19-warp forward / dQ kernels (96 registers per thread; measured 1.4% slower per step than 15 warps x 128 registers)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_ATTN_QWARPS");
+        v = (e && e[0] == '1' && e[1] == '9') ? 1 : 0;
+    }
+    return v != 0;
+}
 bool use_persistent() {
     static int v = -1;
     if (v < 0) {
@@ -945,9 +959,14 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
     pa.nslabs = (Sq + 15) / 16;
     plan_pipe(nt, false, &pa);
     if (pa.nstage && use_persistent()) {
-        if ((rc = set_smem(fwd_pkernel, true))) return rc;
         const int grid = B * H < num_sms() ? B * H : num_sms();
-        ick_launch(fwd_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
+        if (wide_q()) {
+            if ((rc = set_smem(fwd_pkernel<PNW_Q>, true))) return rc;
+            ick_launch(fwd_pkernel<PNW_Q>, grid, 32 * (PNW_Q + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
+        } else {
+            if ((rc = set_smem(fwd_pkernel<PNW_KV>, true))) return rc;
+            ick_launch(fwd_pkernel<PNW_KV>, grid, 32 * (PNW_KV + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo, dc);
+        }
         return ick_check_launch("mha_fwd_mma(persistent)");
     }
     if ((rc = set_smem(fwd_kernel))) return rc;
@@ -979,9 +998,15 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     pa.nslabs = (Sq + 15) / 16;
     plan_pipe(nt, false, &pa);
     if (pa.nstage && use_persistent()) {
-        if ((rc = set_smem(bwd_dq_pkernel, true))) return rc;
-        ick_launch(bwd_dq_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO, lse, dsum,
-                                                                        (bf16*)dQ, pa, ldq, ldo, lddo, lddq, dc);
+        if (wide_q()) {
+            if ((rc = set_smem(bwd_dq_pkernel<PNW_Q>, true))) return rc;
+            ick_launch(bwd_dq_pkernel<PNW_Q>, grid, 32 * (PNW_Q + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO,
+                                                                                         lse, dsum, (bf16*)dQ, pa, ldq, ldo, lddo, lddq, dc);
+        } else {
+            if ((rc = set_smem(bwd_dq_pkernel<PNW_KV>, true))) return rc;
+            ick_launch(bwd_dq_pkernel<PNW_KV>, grid, 32 * (PNW_KV + 1), pipe_smem(pa), stream)(tmK, tmV, (const bf16*)Q, (const bf16*)O, (const bf16*)dO,
+                                                                                           lse, dsum, (bf16*)dQ, pa, ldq, ldo, lddo, lddq, dc);
+        }
     } else {
         if ((rc = set_smem(bwd_dq_kernel))) return rc;
         split_own(Sq, &nctas, &nw);
@@ -994,8 +1019,8 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     pa.nslabs = (Sk + 15) / 16;
     plan_pipe(nt, true, &pa);
     if (pa.nstage && use_persistent()) {
-        if ((rc = set_smem(bwd_dkv_pkernel, true))) return rc;
-        ick_launch(bwd_dkv_pkernel, grid, 32 * (PNW + 1), pipe_smem(pa), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
+        if ((rc = set_smem(bwd_dkv_pkernel<PNW_KV>, true))) return rc;
+        ick_launch(bwd_dkv_pkernel<PNW_KV>, grid, 32 * (PNW_KV + 1), pipe_smem(pa), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
                                                                          pa, ldk, ldv, lddk, lddv, dc);
         return ick_check_launch("mha_bwd_mma(dkv, persistent)");
     }

@@ -671,6 +671,195 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Grouped wgrad: the weight gradients of several linear layers (one Transformer layer's worth: QKV / out / FFN ...) in ONE
+// persistent launch.  Launched one by one, each of these small problems pays its own launch, pipeline fill, exposed epilogue
+// and partial-tile reduce (15-20 us of fixed cost against 5-10 us of streaming for the decoder-sized ones); grouped, the work
+// items (problem, 128-row n tile, k tile, row split) of all problems are balanced over the SMs in a single wave.  Every
+// problem uses k tiles of at most WG_GKT = 320 columns, so that all stages have one size (2 dY boxes + 5 X boxes), the
+// 16 bias columns always fit behind the tile in TMEM and K = 512 (FFN second layer) becomes two k tiles of 256.
+constexpr int WG_MAXP = 8;
+constexpr int WG_GKT = 320;
+struct WgProb {
+    float* ws;   // [splits][N][Kws] partial tiles
+    float* wsb;  // [splits][N] bias partials (nullptr: no bias gradient)
+    const int* rowoff;
+    const int* colmap;
+    const int* biasoff;
+    int M, N, K, KT, Kws, n_tiles_k, splits, m_per_split;
+    int item0;  // first work item of this problem
+    int q0;     // first float4 of this problem in the grouped reduce
+};
+struct WgGroup {
+    CUtensorMap tmY[WG_MAXP], tmX[WG_MAXP];
+    WgProb pr[WG_MAXP];
+    float* G;
+    int nprob, n_items, stages, n_q4;
+};
+struct WgItem {
+    int pi, split, n_idx, k_idx, k_tile, m0, m1;
+};
+__device__ __forceinline__ WgItem wg_item(const WgGroup& g, int w) {
+    WgItem it;
+    it.pi = 0;
+    while (it.pi + 1 < g.nprob && w >= g.pr[it.pi + 1].item0) ++it.pi;
+    const WgProb& p = g.pr[it.pi];
+    const int local = w - p.item0;
+    it.split = local % p.splits;
+    const int t = local / p.splits;
+    it.k_tile = t % p.n_tiles_k;
+    it.n_idx = (t / p.n_tiles_k) * BM;
+    it.k_idx = it.k_tile * p.KT;
+    it.m0 = it.split * p.m_per_split;
+    it.m1 = min(p.M, it.m0 + p.m_per_split);
+    return it;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_group_tc_kernel(const __grid_constant__ WgGroup g) {
+    ick_pdl_launch();
+    extern __shared__ uint8_t smem_raw[];
+    const Smem s = carve(smem_raw, A_STAGE + (WG_GKT / 64) * WG_BOX);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ones = s.a(0) + (uint32_t)g.stages * s.stage_bytes;  // constant box of bf16 1.0 (bias gradient operand)
+    {
+        uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023) + BAR_BYTES + (size_t)g.stages * s.stage_bytes;
+        for (int i = threadIdx.x; i < WG_BOX / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(base)[i] = 0x3F803F80u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    setup(s, warp, lane, &g.tmY[0], &g.tmX[0]);
+    const uint32_t tmem_base = *s.tmem_ptr;
+    ick_pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < g.n_items; w += gridDim.x) {
+                const WgItem it = wg_item(g, w);
+                const WgProb& p = g.pr[it.pi];
+                const int nbx = p.KT / 64;
+                const uint32_t tx = (uint32_t)(2 + nbx) * WG_BOX;
+                const CUtensorMap* tY = &g.tmY[it.pi];
+                const CUtensorMap* tX = &g.tmX[it.pi];
+                for (int m = it.m0; m < it.m1; m += BK) {
+                    mbar_wait(s.empty(stage), phase ^ 1);
+                    mbar_expect_tx(s.full(stage), tx);
+                    tma_load_2d(s.a(stage), tY, s.full(stage), it.n_idx, m);
+                    tma_load_2d(s.a(stage) + WG_BOX, tY, s.full(stage), it.n_idx + 64, m);
+                    for (int j = 0; j < nbx; ++j) tma_load_2d(s.b(stage) + j * WG_BOX, tX, s.full(stage), it.k_idx + 64 * j, m);
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_b = make_idesc(16, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int w = blockIdx.x; w < g.n_items; w += gridDim.x) {
+                const WgItem it = wg_item(g, w);
+                const WgProb& p = g.pr[it.pi];
+                const int n1 = p.KT > MAX_BN ? MAX_BN : p.KT, n2 = p.KT - n1;
+                const uint32_t idesc1 = make_idesc(n1, 1, 1), idesc2 = make_idesc(n2 > 0 ? n2 : 16, 1, 1);
+                const bool bias = p.wsb != nullptr && it.k_tile == 0;
+                mbar_wait(s.tempty(0), acc_phase ^ 1);
+                tc_fence_after();
+                int k_it = 0;
+                for (int m = it.m0; m < it.m1; m += BK, ++k_it) {
+                    mbar_wait(s.full(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = s.a(stage), b0 = s.b(stage);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(a0 + k * UMMA_K * 128, WG_BOX, 1024);
+                        tc_mma_bf16(tmem_base, ad, make_desc(b0 + k * UMMA_K * 128, WG_BOX, 1024), idesc1, (k_it | k) != 0);
+                        if (n2 > 0)
+                            tc_mma_bf16(tmem_base + MAX_BN, ad, make_desc(b0 + 4 * WG_BOX + k * UMMA_K * 128, WG_BOX, 1024), idesc2,
+                                        (k_it | k) != 0);
+                        if (bias) tc_mma_bf16(tmem_base + p.KT, ad, make_desc(ones + k * UMMA_K * 128, WG_BOX, 1024), idesc_b, (k_it | k) != 0);
+                    }
+                    tc_commit(s.empty(stage));
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(s.tfull(0));
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < g.n_items; w += gridDim.x) {
+            const WgItem it = wg_item(g, w);
+            const WgProb& p = g.pr[it.pi];
+            mbar_wait(s.tfull(0), acc_phase);
+            tc_fence_after();
+            const int n = it.n_idx + q * 32 + lane;
+            for (int c0 = half * 32; c0 < p.KT; c0 += 64) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+                if (n < p.N && it.k_idx + c0 < p.Kws) {  // Kws is a multiple of 32: whole chunks only
+                    float* dst = p.ws + ((size_t)it.split * p.N + n) * p.Kws + it.k_idx + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) =
+                            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
+            if (p.wsb != nullptr && it.k_tile == 0 && half == 0) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + p.KT, r);
+                if (n < p.N) p.wsb[(size_t)it.split * p.N + n] = __uint_as_float(r[0]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s.tempty(0));
+            acc_phase ^= 1;
+        }
+    }
+    teardown(warp, tmem_base);
+}
+
+// grouped reduce: one thread per 4 consecutive k of one (problem, n)
+__global__ void __launch_bounds__(256) wgrad_group_reduce_kernel(const __grid_constant__ WgGroup g) {
+    ick_pdl_entry();
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.n_q4) return;
+    int pi = 0;
+    while (pi + 1 < g.nprob && idx >= g.pr[pi + 1].q0) ++pi;
+    const WgProb& p = g.pr[pi];
+    const int q4 = p.Kws >> 2, local = idx - p.q0;
+    const int n = local / q4, k = (local % q4) * 4;
+    float* G = g.G;
+    if (p.wsb != nullptr && k == 0 && p.biasoff[n] >= 0) {
+        float acc = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) acc += p.wsb[(size_t)sp * p.N + n];
+        G[p.biasoff[n]] += acc;
+    }
+    const int ro = p.rowoff[n];
+    if (ro < 0 || k >= p.K) return;
+    const float* src = p.ws + (size_t)n * p.Kws + k;
+    const size_t stride = (size_t)p.N * p.Kws;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int sp = 0;
+    for (; sp + 1 < p.splits; sp += 2) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+    }
+    if (sp < p.splits) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    const float r[4] = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (k + j >= p.K) break;
+        const int cm = p.colmap ? p.colmap[k + j] : k + j;
+        if (cm >= 0) G[ro + cm] += r[j];
+    }
+}
+
 // bias gradient: gflat[biasoff[n]] += sum_m dY[m,n].  HBM-bound column sum: a CTA covers 128 columns x `rpb` rows,
 // 64 threads x bf16x2 per row (128 contiguous bytes per warp-pair) and 4 row groups reduced through shared memory.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ dY, float* __restrict__ G, const int* __restrict__ biasoff,
@@ -758,11 +947,15 @@ int make_tmap_out(CUtensorMap* tm, const void* ptr, int c_f32, int N, int M, int
 }
 
 int pick_bn(int N) {
-    // widest tile whose padding waste is smallest; multiples of 32 (epilogue chunk) up to 256
-    int best = 128, best_pad = 1 << 30;
+    // The kernel is bound by the operand bytes that must enter shared memory: a 128 x BN tile costs (128 + BN) * K * 2 bytes,
+    // i.e. per useful output column  padded(N)/N * (1/BN + 1/128).  Multiples of 32 (epilogue chunk) up to 256.
+    // (Minimising padding alone picked BN = 64 for the 10000-wide vocabulary projection: twice the operand traffic of 256.)
+    int best = 128;
+    double best_cost = 1e30;
     for (int bn = 256; bn >= 64; bn -= 32) {
-        const int pad = (N + bn - 1) / bn * bn - N;
-        if (pad < best_pad) { best_pad = pad; best = bn; }
+        const int padded = (N + bn - 1) / bn * bn;
+        const double cost = (double)padded / N * (1.0 / bn + 1.0 / BM);
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = bn; }
     }
     return best;
 }
@@ -911,8 +1104,10 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
     p.Kws = (K + 31) / 32 * 32;
     {
         const int max_splits = (M + 8 * BK - 1) / (8 * BK);  // at least 8 k-blocks per work item
-        const double t_kb = 0.4 * (128 + p.KT) / 448.0, t_fix = 6.0;          // microseconds
-        const double t_red = (double)N * p.Kws * 4 / 1.5e6;                    // per split, ~1.5 TB/s out of L2
+        // a k-block stage of 128 + KT columns x 64 rows enters shared memory at ~42 B/clk per SM when every SM streams (the
+        // L2 -> SM cap, B300_MICROARCH.md), the partial tiles are re-read from L2 at ~4 TB/s
+        const double t_kb = 0.9 * (128 + p.KT) / 448.0, t_fix = 4.0;          // microseconds
+        const double t_red = (double)N * p.Kws * 4 / 4.0e6;                    // per split
         double best = 1e30;
         int best_mps = (M + BK - 1) / BK * BK;
         for (int sp = 1; sp <= (max_splits > 0 ? max_splits : 1); ++sp) {
@@ -949,4 +1144,77 @@ extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const i
         return ick_check_launch("bias_grad");
     }
     return ICK_OK;
+}
+
+extern "C" int ick_wgrad_group_tc(int nprob, const void* const* dY, const void* const* X, const int* const* rowoff, const int* const* colmap,
+                                  const int* const* biasoff, const int* M, const int* N, const int* K, const int* ldy, const int* ldx,
+                                  float* gflat, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+    ICK_REQUIRE(nprob >= 1 && nprob <= WG_MAXP, "wgrad_group_tc: 1..%d problems, got %d", WG_MAXP, nprob);
+    ICK_REQUIRE(workspace != nullptr && (((uintptr_t)workspace) & 15) == 0, "wgrad_group_tc: a 16-byte aligned workspace is required");
+    int rc = set_smem(wgrad_group_tc_kernel);
+    if (rc) return rc;
+    WgGroup g;  // 2.8 KB: built on the host, passed by value as the kernel parameter
+    g.G = gflat;
+    g.nprob = nprob;
+    int tiles[WG_MAXP], kbtot[WG_MAXP];
+    long long units = 0;
+    int tiles_total = 0, max_kb = 0;
+    for (int i = 0; i < nprob; ++i) {
+        ICK_REQUIRE(M[i] > 0 && N[i] > 0 && K[i] > 0, "wgrad_group_tc: bad sizes of problem %d: M=%d N=%d K=%d", i, M[i], N[i], K[i]);
+        ICK_REQUIRE(ldy[i] % 8 == 0 && ldx[i] % 8 == 0, "wgrad_group_tc: ldy/ldx must be multiples of 8");
+        ICK_REQUIRE((((uintptr_t)dY[i]) & 15) == 0 && (((uintptr_t)X[i]) & 15) == 0, "wgrad_group_tc: operands must be 16-byte aligned");
+        ICK_REQUIRE(rowoff[i] != nullptr, "wgrad_group_tc: rowoff is required");
+        WgProb& p = g.pr[i];
+        p.rowoff = rowoff[i]; p.colmap = colmap[i]; p.biasoff = biasoff[i];
+        p.M = M[i]; p.N = N[i]; p.K = K[i];
+        const int Kpad = (K[i] + 63) / 64 * 64;
+        p.n_tiles_k = (Kpad + WG_GKT - 1) / WG_GKT;
+        p.KT = ((Kpad / 64 + p.n_tiles_k - 1) / p.n_tiles_k) * 64;
+        p.Kws = (K[i] + 31) / 32 * 32;
+        tiles[i] = ((N[i] + BM - 1) / BM) * p.n_tiles_k;
+        kbtot[i] = (M[i] + BK - 1) / BK;
+        units += (long long)tiles[i] * kbtot[i];
+        tiles_total += tiles[i];
+        if (kbtot[i] > max_kb) max_kb = kbtot[i];
+        if ((rc = make_tmap(&g.tmY[i], dY[i], N[i], M[i], ldy[i], BK))) return rc;
+        if ((rc = make_tmap(&g.tmX[i], X[i], K[i], M[i], ldx[i], BK))) return rc;
+    }
+    // one wave: the smallest k-blocks-per-item (>= 8) for which all work items fit on the SMs at once
+    int kbt = (int)((units + num_sms() - 1) / num_sms());
+    if (kbt < 8) kbt = 8;
+    for (;; ++kbt) {
+        int items = 0;
+        for (int i = 0; i < nprob; ++i) items += tiles[i] * ((kbtot[i] + kbt - 1) / kbt);
+        if (items <= num_sms() || kbt >= max_kb) break;
+    }
+    int item0 = 0, q0 = 0;
+    size_t ws_off = 0;
+    for (int i = 0; i < nprob; ++i) {
+        WgProb& p = g.pr[i];
+        p.m_per_split = kbt * BK;
+        p.splits = (p.M + p.m_per_split - 1) / p.m_per_split;
+        p.item0 = item0;
+        item0 += tiles[i] * p.splits;
+        p.q0 = q0;
+        q0 += p.N * (p.Kws / 4);
+        p.ws = (float*)workspace + ws_off;
+        ws_off += (size_t)p.splits * p.N * p.Kws;
+        p.wsb = nullptr;
+        if (p.biasoff != nullptr) {
+            p.wsb = (float*)workspace + ws_off;
+            ws_off += ((size_t)p.splits * p.N + 3) / 4 * 4;
+        }
+    }
+    ICK_REQUIRE((long long)ws_off * 4 <= workspace_bytes, "wgrad_group_tc: workspace too small (%lld > %lld bytes)", (long long)ws_off * 4,
+                workspace_bytes);
+    g.n_items = item0;
+    g.n_q4 = q0;
+    g.stages = (SMEM_DATA - WG_BOX) / (A_STAGE + (WG_GKT / 64) * WG_BOX);
+    if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+    ICK_REQUIRE(g.stages >= 2, "wgrad_group_tc: stage does not fit");
+    const int grid = g.n_items < num_sms() ? g.n_items : num_sms();
+    ick_launch(wgrad_group_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(g);
+    if ((rc = ick_check_launch("wgrad_group_tc"))) return rc;
+    ick_launch(wgrad_group_reduce_kernel, (g.n_q4 + 255) / 256, 256, 0, stream)(g);
+    return ick_check_launch("wgrad_group_reduce");
 }

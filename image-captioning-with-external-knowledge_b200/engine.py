@@ -125,28 +125,35 @@ class DecoderEngine:
                      rowmap=rowmap, drop=self._drop(p, seed, site + ".d2"))
         return y2, sv
 
-    def _ffn_bwd(self, pre, site, f1, f2, dB, h1, y_in, dA, gflat, p, seed):
-        """dB = grad of the FFN output; accumulates the FFN input gradient into dA and the weight grads into gflat."""
+    # The weight gradients of a layer do not feed its input gradient, so the backward helpers only RECORD them
+    # (wg.append((dY, X, rowoff, colmap, biasoff))) and the layer issues them together at its end (kernels.wgrad_group: one
+    # grouped tensor-core launch instead of 4-6 small ones).  Every recorded dY therefore needs its own buffer.
+    @staticmethod
+    def _wg(wg, dY, X, lin):
+        wg.append((dY, X, lin.rowoff, lin.colmap, lin.biasoff))
+
+    def _ffn_bwd(self, pre, site, f1, f2, dB, h1, y_in, dA, wg, p, seed):
+        """dB = grad of the FFN output; accumulates the FFN input gradient into dA and records the weight grads in wg."""
         K = self.K
         R = dB.shape[0]
-        K.wgrad(dB, h1, gflat, f2.rowoff, f2.colmap, f2.biasoff)
+        self._wg(wg, dB, h1, f2)
         dh1 = self._new(R, f1.lin.Np)
         K.gemm(dB, f2.WT, dh1, aux=h1, epi=2, drop=(p if seed is not None else 0.0, seed or 0, 0))
-        K.wgrad(dh1, y_in, gflat, f1.rowoff, f1.colmap, f1.biasoff)
+        self._wg(wg, dh1, y_in, f1)
         K.gemm(dh1, f1.WT, dA, accumulate=True)
 
-    def _self_attn_bwd(self, pre, site, qkv_l, out_l, dB, sv_qkv, sv_o, sv_lse, x_in, dC, B, S, causal, gflat, p, seed):
+    def _self_attn_bwd(self, pre, site, qkv_l, out_l, dB, sv_qkv, sv_o, sv_lse, x_in, dC, B, S, causal, wg, p, seed):
         """dB = grad of the out-projection output; accumulates the block-input gradient into dC."""
         K, DP, H, dh = self.K, self.DP, self.H, self.dh
         R = B * S
-        K.wgrad(dB, sv_o, gflat, out_l.rowoff, out_l.colmap, out_l.biasoff)
+        self._wg(wg, dB, sv_o, out_l)
         dO = self._new(R, DP)
         K.gemm(dB, out_l.WT, dO)
         dqkv = self._new(R, 3 * DP)
         dsum = self._newf(B * H * S)
         K.mha_bwd(sv_qkv[:, :DP], sv_qkv[:, DP : 2 * DP], sv_qkv[:, 2 * DP :], sv_o, dO, sv_lse, dsum, dqkv[:, :DP],
                   dqkv[:, DP : 2 * DP], dqkv[:, 2 * DP :], B, H, S, S, dh, causal=causal, drop=self._drop(p, seed, site + ".sa.attn"))
-        K.wgrad(dqkv, x_in, gflat, qkv_l.rowoff, qkv_l.colmap, qkv_l.biasoff)
+        self._wg(wg, dqkv, x_in, qkv_l)
         K.gemm(dqkv, qkv_l.WT, dC, accumulate=True)
 
     def _enc_layer_bwd(self, stack, l, sv, dy, dy_rowmap, B, S, gflat, p, seed):
@@ -156,14 +163,16 @@ class DecoderEngine:
         R = B * S
         qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
         f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
-        dA, dB = self._new(R, DP), self._new(R, DP)
-        K.add_ln_bwd(dy, sv.s2, sv.mean2, sv.rstd2, self.param(pre + "norm2.weight"), dA, dB, self.param(pre + "norm2.weight", gflat),
+        wg = []
+        dA, dB2 = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dy, sv.s2, sv.mean2, sv.rstd2, self.param(pre + "norm2.weight"), dA, dB2, self.param(pre + "norm2.weight", gflat),
                      self.param(pre + "norm2.bias", gflat), D, rowmap=dy_rowmap, drop=self._drop(p, seed, site + ".d2"))
-        self._ffn_bwd(pre, site, f1, f2, dB, sv.h1, sv.y1, dA, gflat, p, seed)
-        dC = self._new(R, DP)
-        K.add_ln_bwd(dA, sv.s1, sv.mean1, sv.rstd1, self.param(pre + "norm1.weight"), dC, dB, self.param(pre + "norm1.weight", gflat),
+        self._ffn_bwd(pre, site, f1, f2, dB2, sv.h1, sv.y1, dA, wg, p, seed)
+        dC, dB1 = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dA, sv.s1, sv.mean1, sv.rstd1, self.param(pre + "norm1.weight"), dC, dB1, self.param(pre + "norm1.weight", gflat),
                      self.param(pre + "norm1.bias", gflat), D, drop=self._drop(p, seed, site + ".d1"))
-        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB, sv.qkv, sv.o, sv.lse, sv.x, dC, B, S, False, gflat, p, seed)
+        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB1, sv.qkv, sv.o, sv.lse, sv.x, dC, B, S, False, wg, p, seed)
+        K.wgrad_group(wg, gflat)
         return dC
 
     # ---- Transformer decoder layer -------------------------------------------------------------------------------------------
@@ -224,27 +233,29 @@ class DecoderEngine:
         f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
         g = lambda n: self.param(pre + n, gflat)  # noqa: E731
         w = lambda n: self.param(pre + n)  # noqa: E731
-        dA, dB = self._new(R, DP), self._new(R, DP)
-        K.add_ln_bwd(dy, sv.s3, sv.mean3, sv.rstd3, w("norm3.weight"), dA, dB, g("norm3.weight"), g("norm3.bias"), D,
+        wg = []
+        dA, dB3 = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dy, sv.s3, sv.mean3, sv.rstd3, w("norm3.weight"), dA, dB3, g("norm3.weight"), g("norm3.bias"), D,
                      drop=self._drop(p, seed, site + ".d3"))
-        self._ffn_bwd(pre, site, f1, f2, dB, sv.h1, sv.y2, dA, gflat, p, seed)
-        dC = self._new(R, DP)
-        K.add_ln_bwd(dA, sv.s2, sv.mean2, sv.rstd2, w("norm2.weight"), dC, dB, g("norm2.weight"), g("norm2.bias"), D,
+        self._ffn_bwd(pre, site, f1, f2, dB3, sv.h1, sv.y2, dA, wg, p, seed)
+        dC, dB2 = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dA, sv.s2, sv.mean2, sv.rstd2, w("norm2.weight"), dC, dB2, g("norm2.weight"), g("norm2.bias"), D,
                      drop=self._drop(p, seed, site + ".d2"))
         # cross-attention backward
-        K.wgrad(dB, sv.o2, gflat, out2_l.rowoff, out2_l.colmap, out2_l.biasoff)
+        self._wg(wg, dB2, sv.o2, out2_l)
         dO2 = self._new(R, DP)
-        K.gemm(dB, out2_l.WT, dO2)
+        K.gemm(dB2, out2_l.WT, dO2)
         dq = self._new(R, DP)
         dsum = self._newf(B * H * T)
         K.mha_bwd(sv.q, sv.k, sv.v, sv.o2, dO2, sv.lse2, dsum, dq, dkv[:, l * 2 * DP : l * 2 * DP + DP],
                   dkv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"))
-        K.wgrad(dq, sv.y1, gflat, q_l.rowoff, q_l.colmap, q_l.biasoff)
+        self._wg(wg, dq, sv.y1, q_l)
         K.gemm(dq, q_l.WT, dC, accumulate=True)
-        dE = self._new(R, DP)
-        K.add_ln_bwd(dC, sv.s1, sv.mean1, sv.rstd1, w("norm1.weight"), dE, dB, g("norm1.weight"), g("norm1.bias"), D,
+        dE, dB1 = self._new(R, DP), self._new(R, DP)
+        K.add_ln_bwd(dC, sv.s1, sv.mean1, sv.rstd1, w("norm1.weight"), dE, dB1, g("norm1.weight"), g("norm1.bias"), D,
                      drop=self._drop(p, seed, site + ".d1"))
-        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB, sv.qkv, sv.o, sv.lse, sv.x, dE, B, T, True, gflat, p, seed)
+        self._self_attn_bwd(pre + "self_attn.", site, qkv_l, out_l, dB1, sv.qkv, sv.o, sv.lse, sv.x, dE, B, T, True, wg, p, seed)
+        K.wgrad_group(wg, gflat)
         return dE
 
     # ---- context encoders -------------------------------------------------------------------------------------------------------

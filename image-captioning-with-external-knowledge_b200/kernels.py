@@ -110,6 +110,45 @@ class CudaKernels:
             self._call("ick_wgrad_simt", _p(dY), dt_of(dY), _p(X), dt_of(X), _p(gflat), _p(rowoff), _p(colmap), _p(biasoff), M, N,
                        K, _ld(dY), _ld(X), work=work)
 
+    def wgrad_group(self, probs, gflat):
+        """
+        Weight gradients of several linear layers at once (one Transformer layer's worth): probs = [(dY, X, rowoff, colmap,
+        biasoff), ...], same meaning as wgrad().  bf16 operands go through ONE grouped tensor-core launch (+ one reduce) per 8
+        problems; anything else falls back to one wgrad() per problem.
+        """
+        import ctypes
+
+        probs = list(probs)
+        ok = self.use_tc and all(dY.dtype == torch.bfloat16 and X.dtype == torch.bfloat16 and dY.data_ptr() % 16 == 0
+                                 and X.data_ptr() % 16 == 0 for dY, X, *_ in probs)
+        if not ok or len(probs) < 2:
+            for dY, X, rowoff, colmap, biasoff in probs:
+                self.wgrad(dY, X, gflat, rowoff, colmap, biasoff)
+            return
+        dev = probs[0][0].device
+        if self._ws is None or self._ws.device != dev:
+            self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=dev)
+        for i in range(0, len(probs), 8):
+            chunk = probs[i:i + 8]
+            n = len(chunk)
+            vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+            a_dy = vp(*[_p(c[0]) for c in chunk])
+            a_x = vp(*[_p(c[1]) for c in chunk])
+            a_ro = vp(*[_p(c[2]) for c in chunk])
+            a_cm = vp(*[_p(c[3]) for c in chunk])
+            a_bo = vp(*[_p(c[4]) for c in chunk])
+            a_m = ip(*[c[0].shape[0] for c in chunk])
+            a_n = ip(*[c[0].shape[1] for c in chunk])
+            a_k = ip(*[c[1].shape[1] for c in chunk])
+            a_ldy = ip(*[_ld(c[0]) for c in chunk])
+            a_ldx = ip(*[_ld(c[1]) for c in chunk])
+            work = lambda ch=chunk: (sum(c[0].numel() * 2 + c[1].numel() * 2 + c[0].shape[1] * c[1].shape[1] * 4 for c in ch),  # noqa: E731
+                                     sum(2 * c[0].shape[0] * c[0].shape[1] * c[1].shape[1] for c in ch))
+            self._call("ick_wgrad_group_tc", n, ctypes.addressof(a_dy), ctypes.addressof(a_x), ctypes.addressof(a_ro),
+                       ctypes.addressof(a_cm), ctypes.addressof(a_bo), ctypes.addressof(a_m), ctypes.addressof(a_n),
+                       ctypes.addressof(a_k), ctypes.addressof(a_ldy), ctypes.addressof(a_ldx), _p(gflat), _p(self._ws),
+                       self._ws.numel(), n=2, work=work)
+
     # ---- attention -------------------------------------------------------------------------------------------------
     def mha_fwd(self, Q, K, V, O, lse, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
         p, seed, site = _drop(drop)

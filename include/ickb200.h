@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 3
+#define ICK_ABI_VERSION 4
 
 #ifdef __cplusplus
 extern "C" {
@@ -54,6 +54,14 @@ int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float*
  * second kernel; without it the partials are added with fp32 atomics. */
 int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M, int N,
                  int K, int ldy, int ldx, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* The weight (+ bias) gradients of up to 8 linear layers in ONE persistent tensor-core launch plus one reduce launch: the
+ * work items of all problems are balanced over the SMs in a single wave (the backward of one nn.TransformerEncoderLayer /
+ * nn.TransformerDecoderLayer, G/models.py:241-244, holds 4 / 6 such small problems).  Every argument array is a HOST array
+ * of `nprob` entries (device pointers / sizes per problem, same meaning as ick_wgrad_tc); colmap[i] / biasoff[i] may be
+ * NULL.  workspace: fp32 scratch for the row-split partial tiles (sum_i splits_i * N_i * (ceil32(K_i) + 1) * 4 bytes). */
+int ick_wgrad_group_tc(int nprob, const void* const* dY, const void* const* X, const int* const* rowoff, const int* const* colmap,
+                       const int* const* biasoff, const int* M, const int* N, const int* K, const int* ldy, const int* ldx,
+                       float* gflat, void* workspace, long long workspace_bytes, cudaStream_t stream);
 
 /* ---- attention: F.multi_head_attention_forward inside the Transformer layers ------------------------------------------ */
 /* O = dropout(softmax(Q K^T / sqrt(dh) [+ causal mask])) V per (batch, head); lse[b,h,i] (log2 domain) is saved for backward.

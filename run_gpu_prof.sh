@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-python tools/step_prof.py 2 > gpurun_out/r15_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 400 -c 420 --csv --log-file gpurun_out/r15_launches.csv python tools/step_prof.py 2 > gpurun_out/r15_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"gemm_tn_tc_kernel|wgrad_tc_kernel|add_ln" -s 150 -c 24 -o gpurun_out/r15_gemm -f python tools/step_prof.py 2 > gpurun_out/r15_ncu2.log 2>&1
-tail -3 gpurun_out/r15_plain.log gpurun_out/r15_ncu1.log gpurun_out/r15_ncu2.log
+R=r26
+python tools/step_prof.py 2 > gpurun_out/${R}_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"bwd_dkv_pkernel|bwd_dq_pkernel|fwd_pkernel" -s 36 -c 3 -o gpurun_out/${R}_attn -f python tools/step_prof.py 2 > gpurun_out/${R}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc_kernel|gemm_tn_tc_kernel" -s 150 -c 12 -o gpurun_out/${R}_gemm -f python tools/step_prof.py 2 > gpurun_out/${R}_ncu3.log 2>&1
+tail -2 gpurun_out/${R}_ncu2.log gpurun_out/${R}_ncu3.log

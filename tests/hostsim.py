@@ -82,6 +82,10 @@ class HostKernels:
             bv = (bo >= 0).nonzero().flatten()
             gflat.index_add_(0, bo[bv], dY.float().sum(0)[bv])
 
+    def wgrad_group(self, probs, gflat):
+        for dY, X, rowoff, colmap, biasoff in probs:
+            self.wgrad(dY, X, gflat, rowoff, colmap, biasoff)
+
     # ---- attention -------------------------------------------------------------------------------------------------
     @staticmethod
     def _heads(X, B, S, H):

@@ -137,6 +137,44 @@ def test_wgrad(K, Hk, tc, dtype, M, N, K_):
     assert err(Gg, Gr) < 5e-4 if dtype == torch.float32 else err(Gg, Gr) < 5e-3  # fp32 accumulation of the same products
 
 
+def _wgrad_problem(M, N, K_, base, seed):
+    """dY, X and scatter maps with holes (every 7th packed row / 11th packed column is padding) writing at `base`."""
+    dY, X = rnd((M, N), torch.bfloat16, seed), rnd((M, K_), torch.bfloat16, seed + 1)
+    n_real = [n for n in range(N) if n % 7 != 6]
+    k_real = [k for k in range(K_) if k % 11 != 10]
+    Ko = len(k_real)
+    rowoff = torch.full((N,), -1, dtype=torch.int32)
+    rowoff[n_real] = (base + torch.arange(len(n_real)) * Ko).int()
+    colmap = torch.full((K_,), -1, dtype=torch.int32)
+    colmap[k_real] = torch.arange(Ko).int()
+    bias0 = base + len(n_real) * Ko
+    biasoff = torch.full((N,), -1, dtype=torch.int32)
+    biasoff[n_real] = (bias0 + torch.arange(len(n_real))).int()
+    return (dY, X, rowoff, colmap, biasoff), bias0 + len(n_real)
+
+
+@pytest.mark.parametrize("shapes", [
+    # one encoder layer's worth at a small row count (QKV, out, FFN1, FFN2 with K = 512 -> two k tiles)
+    [(1000, 960, 320), (1000, 320, 320), (1000, 512, 320), (1000, 320, 512)],
+    # different row counts per problem, ragged N / K, a problem without bias / colmap, more than 8 problems (two launches)
+    [(130, 104, 72), (4000, 320, 320), (77, 136, 504), (640, 64, 64), (3000, 960, 320), (513, 320, 512), (64, 8, 8), (900, 248, 328),
+     (1200, 320, 320), (333, 96, 200)],
+])
+def test_wgrad_group(K, Hk, shapes):
+    probs, base = [], 64
+    for i, (M, N, K_) in enumerate(shapes):
+        pr, base = _wgrad_problem(M, N, K_, base, 10 * i + 1)
+        if i % 5 == 3:
+            pr = pr[:3] + (pr[3], None)  # no bias gradient
+        probs.append(pr)
+        base += 17
+    Gr = rnd((base + 50,), torch.float32, 9)
+    Gg = Gr.clone().cuda()
+    Hk.wgrad_group(probs, Gr)
+    K.wgrad_group([tuple(cu(t) if t is not None else None for t in pr) for pr in probs], Gg)
+    assert err(Gg, Gr) < 5e-3  # fp32 accumulation of the same bf16 products
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 ATT_CASES = [(2, 10, 301, 301, 30, False), (3, 10, 102, 102, 30, True), (2, 10, 37, 548, 30, False), (1, 4, 5, 5, 32, True),
              (2, 10, 130, 130, 30, True),

@@ -55,7 +55,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -234,23 +234,35 @@ def run_ours(a):
         sys.stderr.write(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); running eager\n")
         tr.use_graph, tr._graph, graph = False, None, "capture failed -> off"
         torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi at 100 ms: sampled under load from the warm-up on
     for _ in range(a.warmup):
         tr.step(inp)
-    sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(lambda: tr.step(inp), a.steps)
-    clocks = sampler.stop() if sampler else None
     loss_acc = tr.loss_acc.clone()
     value = cfg.B * world * a.steps / (ms / 1e3)
 
     # ---- arm 2: end to end through the public call, host buffers --------------------------------------------------------------
-    def e2e_step():
-        acc = tr.train_step(*[t.to(dev, non_blocking=True) if i != 4 else t for i, t in enumerate(args_of(cfg, hb))])
-        return acc.cpu()  # D2H read of [loss_sum, tokens]
+    # Trainer.run(): every step copies its inputs from pinned host memory (H2D of batch i+1 overlaps step i on a copy stream)
+    # and reads its [loss_sum, tokens] back to the host (the read of step i overlaps step i+1)
+    def e2e_loop(n):
+        got = 0
+        for acc in tr.run(args_of(cfg, hb) for _ in range(n)):
+            got += 1
+        assert got == n
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, a.steps)
+    e2e_loop(3)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(a.steps)
+    e1.record()
+    sync_all()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if distributed:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e)
     e2e_value = cfg.B * world * a.steps / (ms_e2e / 1e3)
+    clocks = sampler.stop() if sampler else None
 
     # ---- instrumented pass: CUDA events around every launch (same steps, not part of `value`) -----------------------------------
     roof = None
@@ -287,6 +299,14 @@ def run_ours(a):
         else:
             ach = d[2] / sec / 1e9
             roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None}
+        # DRAM bytes per call of this entry point from the committed ncu launch list of the same step (profiles/ncu_traffic.json,
+        # written by tools/launch_summary.py --traffic-json); ncu flushes caches between kernels, so this is an upper bound
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            roof["traffic"] = tj["per_call"][top]["dram_bytes_per_call"]
+            roof["traffic_source"] = tj["source"]
+        except Exception:
+            pass
         roof.update({"avg_launch_ms": d[0] / d[1], "share_of_step": d[0] / total, "peak_source": pk["src"],
                      "algorithmic_per_launch": {"bytes": d[2] / d[1], "flops": d[3] / d[1]}})
 
@@ -326,7 +346,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])

@@ -197,6 +197,17 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
                 ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
             }
         }
+        // dH += w * G as a read-modify-write: ALL sixteen old values of the lane are requested before the first store (a load
+        // placed after a store through the same base pointer cannot be hoisted by the compiler, which serialised 16 round trips)
+        __nv_bfloat162 oldv[8][2];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int d = d0 + 8 * j + 2 * tq, t = 16 * mt + g + 8 * hh;
+                oldv[j][hh] = (d < D && t < T) ? *reinterpret_cast<const __nv_bfloat162*>(dH + ((size_t)b * T + t) * ld + d)
+                                               : __floats2bfloat162_rn(0.f, 0.f);
+            }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = 8 * j + 2 * tq, d = d0 + c;
@@ -210,9 +221,8 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
                 const float2 hv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(hs + (size_t)t * CLD + c));
                 dwp[j][0] = fmaf(hv.x, g0, dwp[j][0]);
                 dwp[j][1] = fmaf(hv.y, g1, dwp[j][1]);
-                __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dH + ((size_t)b * T + t) * ld + d);
-                const float2 old = __bfloat1622float2(*o);
-                *o = __floats2bfloat162_rn(old.x + w0 * g0, old.y + w1 * g1);
+                const float2 old = __bfloat1622float2(oldv[j][hh]);
+                *reinterpret_cast<__nv_bfloat162*>(dH + ((size_t)b * T + t) * ld + d) = __floats2bfloat162_rn(old.x + w0 * g0, old.y + w1 * g1);
             }
         }
     }
@@ -251,6 +261,14 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
                 ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
             }
         }
+        float2 oldc[8][2];  // same batching of the read-modify-write of dCtx
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int d = d0 + 8 * j + 2 * tq, s = 16 * mt + g + 8 * hh;
+                oldc[j][hh] = (d < D && s < S) ? *reinterpret_cast<const float2*>(dCtx + ((size_t)b * S + s) * ld + d) : make_float2(0.f, 0.f);
+            }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int d = d0 + 8 * j + 2 * tq;
@@ -260,11 +278,8 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
             for (int hh = 0; hh < 2; ++hh) {
                 const int s = 16 * mt + g + 8 * hh;
                 if (s >= S) continue;
-                float2* o = reinterpret_cast<float2*>(dCtx + ((size_t)b * S + s) * ld + d);
-                float2 v = *o;
-                v.x += w0 * acc[j][2 * hh];
-                v.y += w1 * acc[j][2 * hh + 1];
-                *o = v;
+                *reinterpret_cast<float2*>(dCtx + ((size_t)b * S + s) * ld + d) =
+                    make_float2(oldc[j][hh].x + w0 * acc[j][2 * hh], oldc[j][hh].y + w1 * acc[j][2 * hh + 1]);
             }
         }
     }

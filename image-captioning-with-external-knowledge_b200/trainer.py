@@ -124,3 +124,52 @@ class Trainer:
 
     def train_step(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None) -> torch.Tensor:
         return self.step(self.prepare(captions, encoder_out, caption_masks, caption_lengths, entities, facts))
+
+    def run(self, host_batches):
+        """
+        Steady-state training loop over HOST batches (tuples in train.py's argument order, G/train.py:263-272; pinned memory
+        makes the copies asynchronous).  The reference moves a batch to the device and only then starts computing
+        (G/train.py:263-269); here the host->device copies of batch i+1 run on a copy stream while step i computes, and the
+        [loss_sum, kept_tokens] pair of step i is read back into pinned memory while step i+1 runs.  Yields one host tensor
+        of 2 floats per step, in order; every step's inputs are copied and every step's result is read.
+        """
+        dev = self.eng.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._host_acc = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        cs = self._copy_stream
+
+        def stage(hb):
+            with torch.cuda.stream(cs):
+                d = tuple(t.to(dev, non_blocking=True) if torch.is_tensor(t) else t for t in hb)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return d, ev
+
+        it = iter(host_batches)
+        first = next(it, None)
+        nxt = stage(first) if first is not None else None
+        pending = None
+        i = 0
+        while nxt is not None:
+            d, ev = nxt
+            main.wait_event(ev)
+            for t in d:
+                if torch.is_tensor(t):
+                    t.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
+            hb = next(it, None)
+            nxt = stage(hb) if hb is not None else None  # overlaps the step launched below
+            acc = self.train_step(*d)
+            host = self._host_acc[i & 1]
+            host.copy_(acc, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0].clone()
+            pending = (host, done)
+            i += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0].clone()

@@ -11,7 +11,8 @@ from typing import Dict, List, Tuple
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "ickb200.h")
-LIB_PATH = os.path.join(HERE, "csrc", "libickb200.so")
+# ICKB200_LIB overrides the library path (A/B runs of two builds of the same ABI); there is still no non-CUDA fallback
+LIB_PATH = os.environ.get("ICKB200_LIB") or os.path.join(HERE, "csrc", "libickb200.so")
 
 _CTYPES = {
     "int": ctypes.c_int,

@@ -259,6 +259,11 @@ struct TnParams {
     int wstat;    // W-stationary: CTA c keeps weight panel (c % n_tiles_n) resident and streams only A tiles
     int m_tiles;  // row tiles
     int tma_store;  // output through per-warp shared-memory staging + TMA bulk stores (needs 16-byte aligned C rows)
+    // Two row groups with their own weights (ick_gemm_tn_tc_dual): row tiles >= split_tile read the second weight map, the
+    // second bias and hash their dropout with the second site and a row index relative to the split.
+    int split_tile;
+    const float* bias2;
+    uint32_t site2;
     DropCfg drop;
 };
 // Work of a CTA.  Streaming mode: tiles blockIdx.x, +gridDim.x, ... over the (m, n) grid, n fastest.  W-stationary mode:
@@ -295,6 +300,7 @@ struct TileIter {
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW,
+                                                                  const __grid_constant__ CUtensorMap tmW2,
                                                                   const __grid_constant__ CUtensorMap tmC, TnParams p) {
     ick_pdl_launch();
     extern __shared__ uint8_t smem_raw[];
@@ -322,12 +328,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             ICK_TR(1, 0);
             while (ti.next()) {
                 const int m_idx = ti.m_tile * BM, n_idx = ti.n_tile * p.BN;
+                const CUtensorMap* tw = ti.m_tile >= p.split_tile ? &tmW2 : &tmW;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(s.empty(stage), phase ^ 1);
                     ICK_TR(2, ti.m_tile * 100 + kb);
                     mbar_expect_tx(s.full(stage), tx);
                     tma_load_2d(s.a(stage), &tmA, s.full(stage), kb * BK, m_idx);
-                    if (!p.wstat) tma_load_2d(s.b(stage), &tmW, s.full(stage), kb * BK, n_idx);
+                    if (!p.wstat) tma_load_2d(s.b(stage), tw, s.full(stage), kb * BK, n_idx);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
         uint32_t acc_phase = 0;
         const bool c_al = (p.ldc % (p.c_f32 ? 4 : 8) == 0) && ((((uintptr_t)p.C) & 15) == 0);
         const bool aux_al = p.aux != nullptr && (p.ldaux % 8 == 0) && ((((uintptr_t)p.aux) & 15) == 0);
-        const bool bias_al = p.bias != nullptr && ((((uintptr_t)p.bias) & 15) == 0);
+        const bool bias_al = p.bias != nullptr && ((((uintptr_t)p.bias) & 15) == 0) && ((((uintptr_t)p.bias2) & 15) == 0);
         // Bulk-store path: each warp owns NSBOX staging boxes of [32 rows x 32 columns] behind the operand stages (64-byte rows
         // swizzled 64B for bf16, 128-byte rows swizzled 128B for fp32; lane r writes row r, so each 16-byte chunk column is
         // bank-conflict free); one lane issues the TMA store of a finished box and the warp goes on with its next chunk.  Stores
@@ -390,12 +397,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             if (warp == 2 && lane == 0) ICK_TR(6, ti.m_tile);
             tc_fence_after();
             const int row = m_idx + q * 32 + lane;
+            const bool second = ti.m_tile >= p.split_tile;
+            const float* bias_p = second ? p.bias2 : p.bias;
             for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
                 float bv[32];  // bias of this chunk's columns, requested before the TMEM load so that the two latencies overlap
                 {
                     const int col0 = n_idx + c0;
                     const int nv = min(32, p.N - col0);
-                    if (p.bias != nullptr && nv > 0) ld32_f32(p.bias + col0, nv == 32 && (col0 & 7) == 0 && bias_al, nv, bv);
+                    if (bias_p != nullptr && nv > 0) ld32_f32(bias_p + col0, nv == 32 && (col0 & 7) == 0 && bias_al, nv, bv);
                 }
                 uint32_t r[32];
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BN + c0, r);
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                 const bool live = row < p.M;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = p.bias ? __uint_as_float(r[j]) + bv[j] : __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) v[j] = bias_p ? __uint_as_float(r[j]) + bv[j] : __uint_as_float(r[j]);
                 if (p.accumulate && live) {
                     float t[32];
                     if (p.c_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
@@ -421,7 +430,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                     for (int j = 0; j < 32; ++j) v[j] += t[j];
                 }
                 if (p.epi == 1) {
-                    const uint32_t rmix = ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
+                    const uint32_t rmix = second ? ick_rowmix(p.drop.seed, p.site2, (uint64_t)(row - p.split_tile * BM))
+                                                 : ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {  // col0 is even: (j, j+1) is one hash pair
                         float k0 = 1.f, k1 = 1.f;
@@ -1023,10 +1033,15 @@ int set_smem(K kernel) {
 
 }  // namespace
 
-extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float* bias, const void* aux, int M, int N, int K,
-                              int lda, int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p, unsigned seed, unsigned site,
-                              cudaStream_t stream) {
+static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C, int c_dt, const float* bias, const float* bias2,
+                           const void* aux, int M, int M_split, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi, int accumulate,
+                           float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream) {
     ICK_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tn_tc: bad sizes M=%d N=%d K=%d", M, N, K);
+    if (W2 != nullptr) {
+        ICK_REQUIRE(M_split > 0 && M_split % BM == 0 && M_split <= M, "gemm_tn_tc_dual: M_split=%d must be a positive multiple of %d <= M", M_split,
+                    BM);
+        ICK_REQUIRE((((uintptr_t)W2) & 15) == 0 && (bias == nullptr) == (bias2 == nullptr), "gemm_tn_tc_dual: bad second weight / bias");
+    }
     ICK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm_tn_tc: lda/ldw must be multiples of 8 (16-byte TMA strides)");
     ICK_REQUIRE((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0, "gemm_tn_tc: operands must be 16-byte aligned");
     ICK_REQUIRE(c_dt == ICK_F32 || c_dt == ICK_BF16, "gemm_tn_tc: bad output dtype %d", c_dt);
@@ -1045,7 +1060,10 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
     const int es = c_dt == ICK_F32 ? 4 : 2;
     p.tma_store = ((((uintptr_t)C) & 15) == 0 && ((size_t)ldc * es) % 16 == 0) ? 1 : 0;
     const int staging = p.tma_store ? NEPI * NSBOX * (c_dt == ICK_F32 ? 4096 : 2048) : 0;
-    const Plan pl = plan_tiles(N, p.nkb, SMEM_DATA - staging, use_wstat());
+    const Plan pl = plan_tiles(N, p.nkb, SMEM_DATA - staging, use_wstat() && W2 == nullptr);
+    p.split_tile = W2 != nullptr ? M_split / BM : 0x7FFFFFFF;
+    p.bias2 = W2 != nullptr ? bias2 : bias;
+    p.site2 = site2;
     p.wstat = pl.wstat;
     p.BN = pl.BN;
     p.stages = pl.stages;
@@ -1053,9 +1071,14 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
     p.n_tiles_n = (N + p.BN - 1) / p.BN;
     p.n_tiles = p.m_tiles * p.n_tiles_n;
     p.drop = make_drop(drop_p, seed, site);
-    CUtensorMap tmA, tmW, tmC;
+    CUtensorMap tmA, tmW, tmW2, tmC;
     if ((rc = make_tmap(&tmA, A, K, M, lda, BM))) return rc;
     if ((rc = make_tmap(&tmW, W, K, N, ldw, p.BN))) return rc;
+    if (W2 != nullptr) {
+        if ((rc = make_tmap(&tmW2, W2, K, N, ldw, p.BN))) return rc;
+    } else {
+        tmW2 = tmW;
+    }
     if (p.tma_store) {
         if ((rc = make_tmap_out(&tmC, C, p.c_f32, N, M, ldc))) return rc;
     } else {
@@ -1068,8 +1091,23 @@ extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, c
         if (cpp > p.m_tiles) cpp = p.m_tiles;
         grid = cpp * p.n_tiles_n;
     }
-    ick_launch(gemm_tn_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmC, p);
+    ick_launch(gemm_tn_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmW2, tmC, p);
     return ick_check_launch("gemm_tn_tc");
+}
+
+extern "C" int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float* bias, const void* aux, int M, int N, int K,
+                              int lda, int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p, unsigned seed, unsigned site,
+                              cudaStream_t stream) {
+    return gemm_tn_tc_impl(A, W, nullptr, C, c_dt, bias, nullptr, aux, M, 0, N, K, lda, ldw, ldc, ldaux, epi, accumulate, drop_p, seed, site, 0u,
+                           stream);
+}
+
+extern "C" int ick_gemm_tn_tc_dual(const void* A, const void* W, const void* W2, void* C, int c_dt, const float* bias, const float* bias2,
+                                   const void* aux, int M, int M_split, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi,
+                                   int accumulate, float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream) {
+    ICK_REQUIRE(W2 != nullptr, "gemm_tn_tc_dual: W2 is required");
+    return gemm_tn_tc_impl(A, W, W2, C, c_dt, bias, bias2, aux, M, M_split, N, K, lda, ldw, ldc, ldaux, epi, accumulate, drop_p, seed, site, site2,
+                           stream);
 }
 
 extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M,

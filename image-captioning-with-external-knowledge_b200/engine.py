@@ -175,6 +175,117 @@ class DecoderEngine:
         K.wgrad_group(wg, gflat)
         return dC
 
+    # ---- entity + fact encoder stacks in lockstep ---------------------------------------------------------------------------------
+    # The two nn.TransformerEncoder stacks (entities K/models.py:321-322,495; facts :323-324,496) have the same layer shapes and
+    # different parameters.  Their rows live in ONE buffer [entity rows | pad to 128 | fact rows]; every projection of layer l is
+    # a single dual-weight GEMM launch (kernels.gemm_dual), so the fact-sized GEMMs (51 row tiles, pure launch latency on
+    # their own) ride along with the entity-sized ones; attention and LayerNorm run per stack on row slices, and the eight
+    # weight gradients of a layer pair form one grouped wgrad launch.
+    ENC_STACKS = ("transformer_encoder_entities", "transformer_encoder_facts")
+
+    def _dual_geometry(self, B, E, F):
+        Re, Rf = B * E, B * F
+        off = (Re + 127) // 128 * 128
+        return Re, Rf, off, off + Rf
+
+    def _dual_slices(self, B, E, F, P):
+        Re, Rf, off, Rc = self._dual_geometry(B, E, F)
+        # (stack, tokens per image, rows, first row in the concatenated buffer, first memory slot)
+        return ((self.ENC_STACKS[0], E, Re, 0, P), (self.ENC_STACKS[1], F, Rf, off, P + E)), off, Re, Rc
+
+    def _enc_dual_fwd(self, xcat, mem, B, E, F, P, M, p, seed):
+        K, DP, D, H, dh, L = self.K, self.DP, self.D, self.H, self.dh, self.L
+        stacks, off, Re, Rc = self._dual_slices(B, E, F, P)
+        saves = []
+        x = xcat
+        for l in range(L):
+            last = l == L - 1
+            pre = [f"{st[0]}.layers.{l}." for st in stacks]
+            site = [f"{st[0]}.{l}" for st in stacks]
+            lin = lambda n: (self.lin[pre[0] + n], self.lin[pre[1] + n])  # noqa: E731
+            qkv_l, out_l, f1, f2 = lin("self_attn.qkv"), lin("self_attn.out"), lin("ffn1"), lin("ffn2")
+            sv = NS(x=x)
+            sv.qkv = self._new(Rc, 3 * DP)
+            K.gemm_dual(x, qkv_l[0].W, qkv_l[1].W, sv.qkv, off, Re, qkv_l[0].b, qkv_l[1].b)
+            sv.o = self._new(Rc, DP)
+            sv.lse = []
+            for i, (_, S, R, r0, _) in enumerate(stacks):
+                lse = self._newf(B * H * S)
+                q = sv.qkv[r0 : r0 + R]
+                K.mha_fwd(q[:, :DP], q[:, DP : 2 * DP], q[:, 2 * DP :], sv.o[r0 : r0 + R], lse, B, H, S, S, dh, causal=False,
+                          drop=self._drop(p, seed, site[i] + ".sa.attn"))
+                sv.lse.append(lse)
+            sv.s1 = self._new(Rc, DP)
+            K.gemm_dual(sv.o, out_l[0].W, out_l[1].W, sv.s1, off, Re, out_l[0].b, out_l[1].b)
+            sv.y1 = self._new(Rc, DP)
+            sv.mean1, sv.rstd1, sv.mean2, sv.rstd2 = (self._newf(Rc) for _ in range(4))
+            for i, (_, S, R, r0, _) in enumerate(stacks):
+                sl = slice(r0, r0 + R)
+                K.add_ln_fwd(x[sl], sv.s1[sl], self.param(pre[i] + "norm1.weight"), self.param(pre[i] + "norm1.bias"), sv.y1[sl],
+                             sv.mean1[sl], sv.rstd1[sl], D, drop=self._drop(p, seed, site[i] + ".d1"))
+            sv.h1 = self._new(Rc, f1[0].lin.Np)
+            K.gemm_dual(sv.y1, f1[0].W, f1[1].W, sv.h1, off, Re, f1[0].b, f1[1].b, epi=1, drop0=self._drop(p, seed, site[0] + ".ffn"),
+                        drop1=self._drop(p, seed, site[1] + ".ffn"))
+            sv.s2 = self._new(Rc, DP)
+            K.gemm_dual(sv.h1, f2[0].W, f2[1].W, sv.s2, off, Re, f2[0].b, f2[1].b)
+            y2 = None if last else self._new(Rc, DP)
+            for i, (_, S, R, r0, m0) in enumerate(stacks):
+                sl = slice(r0, r0 + R)
+                # the last layer writes straight into the decoder's memory rows (the reference concatenates, K/models.py:497-499)
+                K.add_ln_fwd(sv.y1[sl], sv.s2[sl], self.param(pre[i] + "norm2.weight"), self.param(pre[i] + "norm2.bias"),
+                             mem if last else y2[sl], sv.mean2[sl], sv.rstd2[sl], D, rowmap=(S, M, m0) if last else (0, 0, 0),
+                             drop=self._drop(p, seed, site[i] + ".d2"))
+            x = y2
+            saves.append(sv)
+        return saves
+
+    def _enc_dual_bwd(self, saves, dmem, B, E, F, P, M, gflat, p, seed):
+        """dmem: gradient of the memory buffer.  Returns the gradient of the concatenated stack input (entity rows | pad | fact rows)."""
+        K, DP, D, H, dh, L = self.K, self.DP, self.D, self.H, self.dh, self.L
+        stacks, off, Re, Rc = self._dual_slices(B, E, F, P)
+        ep = (p if seed is not None else 0.0, seed or 0, 0)
+        d = None
+        for l in reversed(range(L)):
+            last = l == L - 1
+            sv = saves[l]
+            pre = [f"{st[0]}.layers.{l}." for st in stacks]
+            site = [f"{st[0]}.{l}" for st in stacks]
+            lin = lambda n: (self.lin[pre[0] + n], self.lin[pre[1] + n])  # noqa: E731
+            qkv_l, out_l, f1, f2 = lin("self_attn.qkv"), lin("self_attn.out"), lin("ffn1"), lin("ffn2")
+            wg = []
+            dA, dB2 = self._new(Rc, DP), self._new(Rc, DP)
+            for i, (_, S, R, r0, m0) in enumerate(stacks):
+                sl = slice(r0, r0 + R)
+                K.add_ln_bwd(dmem if last else d[sl], sv.s2[sl], sv.mean2[sl], sv.rstd2[sl], self.param(pre[i] + "norm2.weight"), dA[sl],
+                             dB2[sl], self.param(pre[i] + "norm2.weight", gflat), self.param(pre[i] + "norm2.bias", gflat), D,
+                             rowmap=(S, M, m0) if last else (0, 0, 0), drop=self._drop(p, seed, site[i] + ".d2"))
+                self._wg(wg, dB2[sl], sv.h1[sl], f2[i])
+            dh1 = self._new(Rc, f1[0].lin.Np)
+            K.gemm_dual(dB2, f2[0].WT, f2[1].WT, dh1, off, Re, aux=sv.h1, epi=2, drop0=ep, drop1=ep)
+            K.gemm_dual(dh1, f1[0].WT, f1[1].WT, dA, off, Re, accumulate=True)
+            dC, dB1 = self._new(Rc, DP), self._new(Rc, DP)
+            for i, (_, S, R, r0, _) in enumerate(stacks):
+                sl = slice(r0, r0 + R)
+                self._wg(wg, dh1[sl], sv.y1[sl], f1[i])
+                K.add_ln_bwd(dA[sl], sv.s1[sl], sv.mean1[sl], sv.rstd1[sl], self.param(pre[i] + "norm1.weight"), dC[sl], dB1[sl],
+                             self.param(pre[i] + "norm1.weight", gflat), self.param(pre[i] + "norm1.bias", gflat), D,
+                             drop=self._drop(p, seed, site[i] + ".d1"))
+                self._wg(wg, dB1[sl], sv.o[sl], out_l[i])
+            dO = self._new(Rc, DP)
+            K.gemm_dual(dB1, out_l[0].WT, out_l[1].WT, dO, off, Re)
+            dqkv = self._new(Rc, 3 * DP)
+            for i, (_, S, R, r0, _) in enumerate(stacks):
+                sl = slice(r0, r0 + R)
+                q, dq = sv.qkv[sl], dqkv[sl]
+                dsum = self._newf(B * H * S)
+                K.mha_bwd(q[:, :DP], q[:, DP : 2 * DP], q[:, 2 * DP :], sv.o[sl], dO[sl], sv.lse[i], dsum, dq[:, :DP], dq[:, DP : 2 * DP],
+                          dq[:, 2 * DP :], B, H, S, S, dh, causal=False, drop=self._drop(p, seed, site[i] + ".sa.attn"))
+                self._wg(wg, dq, sv.x[sl], qkv_l[i])
+            K.gemm_dual(dqkv, qkv_l[0].WT, qkv_l[1].WT, dC, off, Re, accumulate=True)
+            K.wgrad_group(wg, gflat)
+            d = dC
+        return d
+
     # ---- Transformer decoder layer -------------------------------------------------------------------------------------------
     def _dec_layer_fwd(self, l, x, kv, B, T, M, p, seed):
         K, DP, D, H, dh = self.K, self.DP, self.D, self.H, self.dh
@@ -261,13 +372,19 @@ class DecoderEngine:
     # ---- context encoders -------------------------------------------------------------------------------------------------------
     def _encode_context(self, inp, B, E, F):
         K, D, DP = self.K, self.D, self.DP
-        ent_enc = self._new(B * E, DP)
+        if self.has_facts:
+            # entity rows, padding up to a multiple of 128 rows, fact rows: the layout the lockstep encoder stacks work on
+            Re, Rf, off, Rc = self._dual_geometry(B, E, F)
+            self._xcat = self._new(Rc, DP)
+            ent_enc = self._xcat[:Re]
+        else:
+            ent_enc = self._new(B * E, DP)
         K.entity_encode_fwd(inp.entities, inp.facts, self.param("entity_encoder.type_embedding.weight"),
                             self.wemb if self.variant == "N" else None, ent_enc, VARIANT_CODE[self.variant], B, E, F, D,
                             self.plan.shapes["entity_encoder.type_embedding.weight"][0], self.V)
         fact_enc = None
         if self.has_facts:
-            fact_enc = self._new(B * F, DP)
+            fact_enc = self._xcat[off : off + Rf]
             K.fact_encode_fwd(inp.facts, ent_enc, self.param("predicate_embedding.weight"), fact_enc, B, E, F, D, self.NP)
         return ent_enc, fact_enc
 
@@ -275,6 +392,9 @@ class DecoderEngine:
         K, D, DP, L = self.K, self.D, self.DP, self.L
         mem = self._new(B * M, DP)
         K.pixels_fwd(inp.encoder_out, mem, B, D, P, M)
+        if self.has_facts:
+            xcat, self._xcat = self._xcat, None
+            return mem, {"dual": self._enc_dual_fwd(xcat, mem, B, E, F, P, M, p_enc, seed)}
         saves = {}
         stacks = [("transformer_encoder_entities", ent_enc, E, P)]
         if self.has_facts:
@@ -408,22 +528,20 @@ class DecoderEngine:
         if need_encoder_grad:
             d_enc = torch.empty(B, D, P, dtype=torch.float32, device=self.device)
             K.pixels_bwd(dmem, d_enc, B, D, P, M)
-        # context encoders, facts first (their input gradient also flows into the entity encodings)
+        # context encoders; the fact encodings' input gradient also flows into the entity encodings (FactEncoder gathers them)
         if self.has_facts:
-            d = dmem
-            rowmap = (F, M, P + E)
-            for l in reversed(range(L)):
-                d = self._enc_layer_bwd("transformer_encoder_facts", l, ctx.enc_saves["transformer_encoder_facts"][l], d, rowmap, B, F,
-                                        gflat, ctx.p_enc, seed)
-                rowmap = (0, 0, 0)
-            K.accum_f32(d, dFact)
+            Re, Rf, off, Rc = self._dual_geometry(B, E, F)
+            dcat = self._enc_dual_bwd(ctx.enc_saves["dual"], dmem, B, E, F, P, M, gflat, ctx.p_enc, seed)
+            K.accum_f32(dcat[off : off + Rf], dFact)
             K.fact_encode_bwd(dFact, inp.facts, dEnt, gflat, self.off("predicate_embedding.weight"), B, E, F, D, self.NP)
-        d = dmem
-        rowmap = (E, M, P)
-        for l in reversed(range(L)):
-            d = self._enc_layer_bwd("transformer_encoder_entities", l, ctx.enc_saves["transformer_encoder_entities"][l], d, rowmap, B, E,
-                                    gflat, ctx.p_enc, seed)
-            rowmap = (0, 0, 0)
+            d = dcat[:Re]
+        else:
+            d = dmem
+            rowmap = (E, M, P)
+            for l in reversed(range(L)):
+                d = self._enc_layer_bwd("transformer_encoder_entities", l, ctx.enc_saves["transformer_encoder_entities"][l], d, rowmap, B,
+                                        E, gflat, ctx.p_enc, seed)
+                rowmap = (0, 0, 0)
         K.accum_f32(d, dEnt)
         K.entity_encode_bwd(dEnt, inp.entities, inp.facts, self.param("entity_encoder.type_embedding.weight"),
                             self.wemb if self.variant == "N" else None, gflat, self.off("entity_encoder.type_embedding.weight"),

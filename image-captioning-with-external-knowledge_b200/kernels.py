@@ -91,6 +91,31 @@ class CudaKernels:
             self._call("ick_gemm_tn_simt", _p(A), dt_of(A), _p(W), dt_of(W), _p(C), dt_of(C), _p(bias), _p(aux), M, N, K,
                        _ld(A), _ld(W), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), p, seed, site, work=work)
 
+    def gemm_dual(self, A, W0, W1, C, m_split, rows0, bias0=None, bias1=None, aux=None, epi=0, accumulate=False, drop0: Drop = None,
+                  drop1: Drop = None):
+        """
+        Two row groups with their own weights in one launch: rows [0, rows0) use (W0, bias0, drop0), rows [m_split, M) use
+        (W1, bias1, drop1; dropout rows counted from m_split); rows [rows0, m_split) are padding (m_split % 128 == 0).
+        """
+        M, K = A.shape
+        N = W0.shape[0]
+        assert W0.shape == W1.shape and W0.stride(0) == W1.stride(0) and C.shape[0] == M and C.shape[1] == N and rows0 <= m_split <= M
+        p, seed, site0 = _drop(drop0)
+        p1, seed1, site1 = _drop(drop1)
+        assert (p, seed) == (p1, seed1) or drop0 is None or drop1 is None
+        tc = (self.use_tc and A.dtype == torch.bfloat16 and W0.dtype == torch.bfloat16 and A.data_ptr() % 16 == 0
+              and W0.data_ptr() % 16 == 0 and W1.data_ptr() % 16 == 0 and (aux is None or C.dtype == torch.bfloat16)
+              and m_split % 128 == 0 and 0 < m_split < M)
+        if not tc:
+            sl = lambda t, a, b: None if t is None else t[a:b]  # noqa: E731
+            self.gemm(A[:rows0], W0, C[:rows0], bias0, sl(aux, 0, rows0), epi, accumulate, drop0)
+            self.gemm(A[m_split:], W1, C[m_split:], bias1, sl(aux, m_split, M), epi, accumulate, drop1)
+            return
+        rows = rows0 + (M - m_split)
+        work = lambda: ((rows * K) * 2 + 2 * (N * K) * 2 + rows * N * C.element_size() * (2 if accumulate else 1), 2 * rows * N * K)  # noqa: E731
+        self._call("ick_gemm_tn_tc_dual", _p(A), _p(W0), _p(W1), _p(C), dt_of(C), _p(bias0), _p(bias1), _p(aux), M, m_split, N, K, _ld(A),
+                   _ld(W0), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), max(p, p1), seed or seed1, site0, site1, work=work)
+
     def wgrad(self, dY, X, gflat, rowoff, colmap=None, biasoff=None, force_simt=False):
         """gflat[rowoff[n] + colmap[k]] += sum_m dY[m,n] X[m,k];  gflat[biasoff[n]] += sum_m dY[m,n]."""
         M, N = dY.shape

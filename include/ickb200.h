@@ -50,6 +50,14 @@ int ick_wgrad_simt(const void* dY, int y_dt, const void* X, int x_dt, float* gfl
 int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float* bias, const void* aux, int M, int N, int K, int lda,
                    int ldw, int ldc, int ldaux, int epi, int accumulate, float drop_p, unsigned seed, unsigned site,
                    cudaStream_t stream);
+/* Two row groups with their own weights in one launch: rows [0, M_split) use (W, bias, site), rows [M_split, M) use
+ * (W2, bias2, site2, dropout row index relative to M_split); M_split must be a multiple of 128 (pad the first group).  Used
+ * to run the entity and the fact Transformer encoder stacks (same layer shapes, different parameters: G/models.py:243-244,
+ * K/models.py:321-324) in lockstep, so the small fact-sized GEMMs ride along with the entity-sized ones.  W and W2 share
+ * ldw. */
+int ick_gemm_tn_tc_dual(const void* A, const void* W, const void* W2, void* C, int c_dt, const float* bias, const float* bias2,
+                        const void* aux, int M, int M_split, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi,
+                        int accumulate, float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream);
 /* workspace (optional, fp32, >= splits*N*ceil32(K)*4 bytes): row-slice partial tiles are stored there and reduced by a
  * second kernel; without it the partials are added with fp32 atomics. */
 int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M, int N,

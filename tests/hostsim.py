@@ -82,6 +82,12 @@ class HostKernels:
             bv = (bo >= 0).nonzero().flatten()
             gflat.index_add_(0, bo[bv], dY.float().sum(0)[bv])
 
+    def gemm_dual(self, A, W0, W1, C, m_split, rows0, bias0=None, bias1=None, aux=None, epi=0, accumulate=False, drop0=None, drop1=None):
+        sl = lambda t, a, b: None if t is None else t[a:b]  # noqa: E731
+        M = A.shape[0]
+        self.gemm(A[:rows0], W0, C[:rows0], bias0, sl(aux, 0, rows0), epi, accumulate, drop0)
+        self.gemm(A[m_split:], W1, C[m_split:], bias1, sl(aux, m_split, M), epi, accumulate, drop1)
+
     def wgrad_group(self, probs, gflat):
         for dY, X, rowoff, colmap, biasoff in probs:
             self.wgrad(dY, X, gflat, rowoff, colmap, biasoff)

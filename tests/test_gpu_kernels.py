@@ -111,6 +111,34 @@ def test_gemm_epilogues(K, Hk, tc, dtype):
     assert err(Eg, Er) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows0,rows1,N,K_", [(301 * 3, 51 * 3, 960, 320), (128, 7, 320, 512), (1000, 300, 512, 320), (5, 400, 320, 320)])
+def test_gemm_dual(K, Hk, dtype, rows0, rows1, N, K_):
+    """Two row groups (entity rows | pad to 128 | fact rows) with their own weights, biases and dropout sites in one launch."""
+    m_split = (rows0 + 127) // 128 * 128
+    M = m_split + rows1
+    A = rnd((M, K_), dtype, 1)
+    W0, W1 = rnd((N, K_), dtype, 2, 0.1), rnd((N, K_), dtype, 3, 0.1)
+    b0, b1 = rnd((N,), torch.float32, 4), rnd((N,), torch.float32, 5)
+    d0, d1 = (0.3, 99, 11), (0.3, 99, 12)
+    real = torch.cat([torch.arange(rows0), torch.arange(m_split, M)])
+    for epi, acc in ((0, False), (1, False), (0, True)):
+        C0 = rnd((M, N), dtype, 7)
+        Cr, Cg = C0.clone(), C0.clone().cuda()
+        kw = dict(bias0=b0, bias1=b1, epi=epi, accumulate=acc, drop0=d0 if epi else None, drop1=d1 if epi else None)
+        Hk.gemm_dual(A, W0, W1, Cr, m_split, rows0, **kw)
+        K.gemm_dual(cu(A), cu(W0), cu(W1), Cg, m_split, rows0, **{k: (cu(v) if torch.is_tensor(v) else v) for k, v in kw.items()})
+        assert err(Cg[real], Cr[real]) < TOL[dtype]
+        if epi == 1:
+            assert torch.equal(Cg.cpu()[real] == 0, Cr[real] == 0)  # per-group dropout site and row numbering
+    # relu/dropout backward against a saved activation
+    aux = torch.relu(rnd((M, N), dtype, 8))
+    Dr, Dg = torch.zeros(M, N, dtype=dtype), torch.zeros(M, N, dtype=dtype).cuda()
+    Hk.gemm_dual(A, W0, W1, Dr, m_split, rows0, aux=aux, epi=2, drop0=(0.3, 0, 0), drop1=(0.3, 0, 0))
+    K.gemm_dual(cu(A), cu(W0), cu(W1), Dg, m_split, rows0, aux=cu(aux), epi=2, drop0=(0.3, 0, 0), drop1=(0.3, 0, 0))
+    assert err(Dg[real], Dr[real]) < TOL[dtype]
+
+
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,N,K_", [(1000, 960, 320), (203, 320, 512), (4100, 136, 320), (64, 1000, 320)])

@@ -7,4 +7,4 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
                     int ldv, int ldo, int causal, DropCfg dc, cudaStream_t stream);
 int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
                     void* dK, void* dV, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk,
-                    int lddv, int causal, DropCfg dc, cudaStream_t stream);
+                    int lddv, int causal, DropCfg dc, void* workspace, long long workspace_bytes, cudaStream_t stream);

@@ -389,9 +389,11 @@ __device__ __forceinline__ void dq_tile(float (*dq)[4], const uint32_t (*qa)[4],
 // one 64-query tile of dK/dV for the warp's 16 keys.  ls / ds / rm: LSE, D and dropout row mix of the tile's queries (smem).
 // Lanes g and g^1 own keys of the same dropout pair and see the same queries: each computes the pair hashes of ONE of its two
 // key rows (even g: r0, odd g: r1) and receives the other from its partner (lane ^ 4).
+// ds_out (optional): where this warp's key slab keeps dS^T for the dQ-from-dS kernel, [query sub-step][lane][8 words] in exactly
+// the A-fragment order produced here (1 KiB per 16-key x 32-query block, two 16-byte stores per lane).
 __device__ __forceinline__ void dkv_tile(float (*dk)[4], float (*dv)[4], const uint32_t (*ka)[4], const uint32_t (*va)[4], uint32_t qt,
                                          uint32_t gt, int qt0, const float* ls, const float* ds, const uint32_t* rm, const OwnRows& r,
-                                         bool odd, const TileEnv& e) {
+                                         bool odd, const TileEnv& e, uint4* ds_out = nullptr) {
     const Dims& d = e.d;
     const int tq = e.tq;
     const uint32_t mypair = (uint32_t)(odd ? r.r1 : r.r0) >> 1;
@@ -441,6 +443,11 @@ __device__ __forceinline__ void dkv_tile(float (*dk)[4], float (*dv)[4], const u
         pack_p<4>(st, pa);
         mma_p_t<4>(dv, pa, gt, 4 * sub, e.lo);
         pack_p<4>(dpt, pa);
+        if (ds_out != nullptr) {
+            uint4* dst = ds_out + ((size_t)(q0 / SUB) * 32 + (size_t)(4 * (r.r0 - r.wrow) + tq)) * 2;
+            dst[0] = make_uint4(pa[0][0], pa[0][1], pa[0][2], pa[0][3]);
+            dst[1] = make_uint4(pa[1][0], pa[1][1], pa[1][2], pa[1][3]);
+        }
         mma_p_t<4>(dk, pa, qt, 4 * sub, e.lo);
     }
 }
@@ -570,7 +577,7 @@ __device__ __forceinline__ void fill_scalars(float* Ls, float* Ds, uint32_t* Rm,
 __global__ void __launch_bounds__(32 * NWMAX, 2)
     bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                    const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
-                   bf16* __restrict__ dV, Dims d, int ldk, int ldv, int lddk, int lddv, int ntc, DropCfg drop) {
+                   bf16* __restrict__ dV, Dims d, int ldk, int ldv, int lddk, int lddv, int ntc, DropCfg drop, uint4* __restrict__ DS) {
     ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Smem sm = carve(smem_raw, ntc);
@@ -598,6 +605,8 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
     float dk[4][4], dv[4][4];
     zero16(dk);
     zero16(dv);
+    const int nsub_all = 2 * nt, nslabs_all = (d.Sk + 15) / 16;
+    uint4* ds_out = DS ? DS + (((size_t)b * d.H + h) * nslabs_all + (size_t)(j0 / 16 + warp)) * nsub_all * 64 : nullptr;
     for (int c0 = tbeg; c0 < nt; c0 += ntc) {
         const int n = min(ntc, nt - c0);
         if (c0 > tbeg) {
@@ -611,7 +620,7 @@ __global__ void __launch_bounds__(32 * NWMAX, 2)
             mbar_wait(sm.bars + 8 * t, parity);
             if (active)
                 dkv_tile(dk, dv, ka, va, sm.t0 + t * TILE_BYTES, sm.t1 + t * TILE_BYTES, (c0 + t) * TK, Ls + t * TK, Ds + t * TK, Rm + t * TK, r,
-                         odd, env);
+                         odd, env, ds_out);
         }
     }
     if (!active) return;
@@ -786,7 +795,7 @@ template <int PNW>
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dkv_pkernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG, const bf16* __restrict__ K,
                     const bf16* __restrict__ V, const float* __restrict__ LSE, const float* __restrict__ Dsum, bf16* __restrict__ dK,
-                    bf16* __restrict__ dV, PArgs a, int ldk, int ldv, int lddk, int lddv, DropCfg drop) {
+                    bf16* __restrict__ dV, PArgs a, int ldk, int ldv, int lddk, int lddv, DropCfg drop, uint4* __restrict__ DS) {
     ick_pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     const Dims& d = a.d;
@@ -826,12 +835,13 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
             float dk[4][4], dv[4][4];
             zero16(dk);
             zero16(dv);
+            uint4* ds_out = DS ? DS + ((size_t)item * a.nslabs + slab) * (size_t)(2 * a.ntc) * 64 : nullptr;
             mbar_wait(pp.sfull(s), ph);
             // causal: queries before the warp's first key see none of its keys
             for (int t = d.causal ? (16 * slab) / TK : 0; t < a.ntc; ++t) {
                 mbar_wait(pp.full(s, t), ph);
                 dkv_tile(dk, dv, ka, va, pp.t0(s) + t * TILE_BYTES, pp.t1(s) + t * TILE_BYTES, t * TK, Ls + t * TK, Ds + t * TK, Rm + t * TK, r, odd,
-                         env);
+                         env, ds_out);
             }
             store_slab(dK + (size_t)b * d.Sk * lddk + h * HD, lddk, r.r0, r.r1, d.Sk, dk, d.scale, d.scale, d.dh, tq);
             store_slab(dV + (size_t)b * d.Sk * lddv + h * HD, lddv, r.r0, r.r1, d.Sk, dv, env.ik, env.ik, d.dh, tq);
@@ -840,6 +850,136 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
         mbar_wait(pp.sfull(s), ph);
         __syncwarp();
         if (lane == 0) mbar_arrive(pp.empty(s));
+    }
+}
+
+// =============================================================================================================================
+// dQ from the stored dS^T.  The dK/dV kernel has every dS^T block in registers; recomputing S, P, dP and the dropout mask a second
+// time just to contract dS with K (the two-kernel scheme above) costs ~40% of the backward.  With a workspace the order becomes
+//   D = rowsum(dO * O)  ->  dK/dV kernel (also stores dS^T, bf16, A-fragment order)  ->  dQ = scale * dS K  (this kernel),
+// a plain batched GEMM per (image, head): one warp per 32 queries streams the key slabs, turns the stored fragments into
+// A fragments of dS with movmatrix (8x8 transposes inside the warp), and accumulates 32 x 32 in registers.
+// =============================================================================================================================
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__global__ void __launch_bounds__(256) rowdot_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ Dsum, int B,
+                                                     int H, int Sq, int dh, int ldo, int lddo) {
+    ick_pdl_entry();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * Sq * H) return;
+    const int h = (int)(idx % H);
+    const long long row = idx / H;  // b * Sq + q
+    const bf16* op = O + (size_t)row * ldo + h * HD;
+    const bf16* gp = dO + (size_t)row * lddo + h * HD;
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        float x[8], y[8];
+        ld8(op + 8 * v, x);
+        ld8(gp + 8 * v, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (8 * v + i < dh) acc = fmaf(x[i], y[i], acc);
+    }
+    const int b = (int)(row / Sq), q = (int)(row % Sq);
+    Dsum[((size_t)b * H + h) * Sq + q] = acc;
+}
+
+constexpr int DQ_MAXW = 20;  // warps per CTA of the dQ-from-dS kernel (one CTA per (image, head)): 640 threads x <= 102 registers
+constexpr int DQ_KLD = 40;   // shared-memory row stride of the K tile in elements: 80 bytes make every ldmatrix phase conflict-free
+// Warp w works on query block w % nsub and on part w / nsub of the key slabs (ksplit parts; partial 32 x 32 tiles are summed
+// through shared memory), so that even a 102-query cross-attention item keeps 16 warps' worth of loads in flight.  When there
+// are more query blocks than warps (Sq > 640) ksplit is 1 and the warps loop over the blocks.
+__global__ void __launch_bounds__(32 * DQ_MAXW) bwd_dq_ds_kernel(const uint4* __restrict__ DS, const bf16* __restrict__ K, bf16* __restrict__ dQ,
+                                                                 Dims d, int ldk, int lddq, int nslabs, int nsub, int ksplit) {
+    ick_pdl_entry();
+    extern __shared__ __align__(16) uint8_t dq_smem[];
+    bf16* ks = reinterpret_cast<bf16*>(dq_smem);  // [16 * nslabs][DQ_KLD], rows >= Sk and columns >= dh zero
+    float* red = reinterpret_cast<float*>(dq_smem + (size_t)16 * nslabs * DQ_KLD * 2);  // [warps][32 values][32 lanes] (ksplit > 1)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3, nw = blockDim.x >> 5;
+    const int item = blockIdx.x, b = item / d.H, h = item % d.H;
+    const bf16* Kb = K + (size_t)b * d.Sk * ldk + h * HD;
+    for (int idx = threadIdx.x; idx < 16 * nslabs * 4; idx += blockDim.x) {
+        const int r = idx >> 2, c = (idx & 3) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < d.Sk) {
+            v = *reinterpret_cast<const uint4*>(Kb + (size_t)r * ldk + c);
+            if (c + 8 > d.dh) {  // zero the pad lanes of the head (dh = 30: columns 30, 31)
+                bf16* e = reinterpret_cast<bf16*>(&v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (c + i >= d.dh) e[i] = __float2bfloat16_rn(0.f);
+            }
+        }
+        *reinterpret_cast<uint4*>(ks + (size_t)r * DQ_KLD + c) = v;
+    }
+    __syncthreads();
+    // per-lane ldmatrix.trans address of a (16 keys x 16 d) block: row (lane&7) + 8*((lane>>3)&1), column 8*(lane>>4)
+    const uint32_t ks_lane = smem_u32(ks) + (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * DQ_KLD + 8 * (lane >> 4)) * 2u;
+    bf16* out = dQ + (size_t)b * d.Sq * lddq + h * HD;
+    const int per = (nslabs + ksplit - 1) / ksplit;
+    for (int task = warp; task < nsub * ksplit; task += nw) {
+        const int sub = task % nsub, part = task / nsub;
+        const int q0 = sub * SUB;
+        // causal: the dK/dV kernel skipped (never wrote) the blocks whose queries all precede the slab's keys
+        const int slab_lim = d.causal ? min(nslabs, (q0 + SUB - 1) / 16 + 1) : nslabs;
+        const int slab_beg = part * per, slab_end = q0 < d.Sq ? min(slab_lim, slab_beg + per) : 0;
+        const uint4* src = DS + (((size_t)item * nslabs) * nsub + sub) * 64 + lane * 2;
+        const size_t sstride = (size_t)nsub * 64;
+        float acc[2][4][4];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[kk][j][0] = acc[kk][j][1] = acc[kk][j][2] = acc[kk][j][3] = 0.f;
+#pragma unroll 4
+        for (int slab = slab_beg; slab < slab_end; ++slab) {
+            const uint4 v0 = src[slab * sstride], v1 = src[slab * sstride + 1];
+            // B operand K[key][d] (key pairs along the reduction) by ldmatrix.trans: {b0,b1} of two d tiles per instruction
+            uint32_t kb[4][2];
+            const uint32_t ka = ks_lane + (uint32_t)(16 * slab * DQ_KLD) * 2u;
+            ldsm_x4_trans(kb[0][0], kb[0][1], kb[1][0], kb[1][1], ka);
+            ldsm_x4_trans(kb[2][0], kb[2][1], kb[3][0], kb[3][1], ka + 32u);
+            const uint32_t pa[2][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}};
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                // A fragment of dS (16 queries x 16 keys) from the stored dS^T blocks: (keys 0-7 | 8-15) x (queries 0-7 | 8-15)
+                uint32_t da[4];
+                da[0] = movm_t(pa[kk][0]);
+                da[1] = movm_t(pa[kk][2]);
+                da[2] = movm_t(pa[kk][1]);
+                da[3] = movm_t(pa[kk][3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma16816(acc[kk][j], da, kb[j][0], kb[j][1]);
+            }
+        }
+        if (ksplit > 1) {  // (all tasks fit in one pass of the warps: the host guarantees nsub * ksplit <= warps)
+            float* mine = red + (size_t)warp * 1024 + lane;
+            if (part != 0) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) mine[((kk * 4 + j) * 4 + x) * 32] = acc[kk][j][x];
+            }
+            __syncthreads();
+            if (part != 0) continue;
+            for (int pp = 1; pp < ksplit; ++pp) {
+                const float* other = red + (size_t)(warp + pp * nsub) * 1024 + lane;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) acc[kk][j][x] += other[((kk * 4 + j) * 4 + x) * 32];
+            }
+        }
+        if (q0 >= d.Sq) continue;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) store_slab(out, lddq, q0 + 16 * kk + g, q0 + 16 * kk + g + 8, d.Sq, acc[kk], d.scale, d.scale, d.dh, tq);
     }
 }
 
@@ -920,6 +1060,18 @@ bool wide_q() {  // ICK_ATTN_QWARPS=19 selects the 19-warp forward / dQ kernels 
     }
     return v != 0;
 }
+// dQ-from-dS scheme: ICK_ATTN_DS=0 never, =1 whenever a workspace is given, unset = where it measured faster on B200: long
+// non-causal self-attention (the 301-slot entity / fact encoders, -8% per backward); for the 102-query decoder attentions the
+// extra dS round trip through HBM costs as much as the recomputation it saves.
+bool use_ds(int Sq, int Sk, int causal) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_ATTN_DS");
+        v = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
+    }
+    if (v == 2) return !causal && Sq >= 256;
+    return v != 0;
+}
 bool use_persistent() {
     static int v = -1;
     if (v < 0) {
@@ -979,7 +1131,7 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
 
 int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
                     void* dK, void* dV, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk,
-                    int lddv, int causal, DropCfg dc, cudaStream_t stream) {
+                    int lddv, int causal, DropCfg dc, void* workspace, long long workspace_bytes, cudaStream_t stream) {
     ICK_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)Q & 15) == 0 && ((uintptr_t)dO & 15) == 0 &&
                     ((uintptr_t)O & 15) == 0,
                 "mha_bwd: operands must be 16-byte aligned");
@@ -995,6 +1147,46 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     int nt = (Sk + TK - 1) / TK, ntc = nt < CH ? nt : CH;
     PArgs pa;
     pa.d = d;
+    // dS^T workspace: [image, head][16-key slab][32-query block][1 KiB]; with it dQ is a GEMM over the stored dS (see above)
+    const int ds_nslabs = (Sk + 15) / 16, ds_nsub = 2 * ((Sq + TK - 1) / TK);
+    const long long ds_need = (long long)B * H * ds_nslabs * ds_nsub * 1024;
+    uint4* DS = (workspace != nullptr && workspace_bytes >= ds_need && (((uintptr_t)workspace) & 15) == 0 && use_ds(Sq, Sk, causal) &&
+                 (size_t)ds_nslabs * 16 * DQ_KLD * 2 <= 128 * 1024 && (ldk % 8) == 0)
+                    ? (uint4*)workspace
+                    : nullptr;
+    if (DS != nullptr) {
+        const long long n = (long long)B * Sq * H;
+        ick_launch(rowdot_kernel, (int)((n + 255) / 256), 256, 0, stream)((const bf16*)O, (const bf16*)dO, dsum, B, H, Sq, dh, ldo, lddo);
+        if ((rc = ick_check_launch("mha_bwd_mma(rowdot)"))) return rc;
+        nt = (Sq + TK - 1) / TK;
+        ntc = nt < CH ? nt : CH;
+        pa.nslabs = ds_nslabs;
+        plan_pipe(nt, true, &pa);
+        if (pa.nstage && use_persistent()) {
+            if ((rc = set_smem(bwd_dkv_pkernel<PNW_KV>, true))) return rc;
+            ick_launch(bwd_dkv_pkernel<PNW_KV>, grid, 32 * (PNW_KV + 1), pipe_smem(pa), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK,
+                                                                                            (bf16*)dV, pa, ldk, ldv, lddk, lddv, dc, DS);
+        } else {
+            if ((rc = set_smem(bwd_dkv_kernel))) return rc;
+            split_own(Sk, &nctas, &nw);
+            ick_launch(bwd_dkv_kernel, dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, true), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum,
+                                                                                              (bf16*)dK, (bf16*)dV, d, ldk, ldv, lddk, lddv, ntc, dc, DS);
+        }
+        if ((rc = ick_check_launch("mha_bwd_mma(dkv + dS)"))) return rc;
+        if ((rc = set_smem(bwd_dq_ds_kernel, true))) return rc;
+        int ksplit = 1, warps = DQ_MAXW;
+        if (ds_nsub <= DQ_MAXW) {
+            ksplit = DQ_MAXW / ds_nsub;
+            if (ksplit > 4) ksplit = 4;
+            if (ksplit > (ds_nslabs + 1) / 2) ksplit = (ds_nslabs + 1) / 2;  // at least two slabs per part
+            if (ksplit < 1) ksplit = 1;
+            warps = ds_nsub * ksplit;
+        }
+        const size_t dq_smem_bytes = (size_t)ds_nslabs * 16 * DQ_KLD * 2 + (ksplit > 1 ? (size_t)warps * 4096 : 0);
+        ick_launch(bwd_dq_ds_kernel, B * H, 32 * warps, dq_smem_bytes, stream)(DS, (const bf16*)K, (bf16*)dQ, d, ldk, lddq, ds_nslabs, ds_nsub,
+                                                                              ksplit);
+        return ick_check_launch("mha_bwd_mma(dq from dS)");
+    }
     pa.nslabs = (Sq + 15) / 16;
     plan_pipe(nt, false, &pa);
     if (pa.nstage && use_persistent()) {
@@ -1021,12 +1213,12 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
     if (pa.nstage && use_persistent()) {
         if ((rc = set_smem(bwd_dkv_pkernel<PNW_KV>, true))) return rc;
         ick_launch(bwd_dkv_pkernel<PNW_KV>, grid, 32 * (PNW_KV + 1), pipe_smem(pa), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK, (bf16*)dV,
-                                                                         pa, ldk, ldv, lddk, lddv, dc);
+                                                                         pa, ldk, ldv, lddk, lddv, dc, (uint4*)nullptr);
         return ick_check_launch("mha_bwd_mma(dkv, persistent)");
     }
     if ((rc = set_smem(bwd_dkv_kernel))) return rc;
     split_own(Sk, &nctas, &nw);
     ick_launch(bwd_dkv_kernel, dim3(nctas, H, B), 32 * nw, smem_bytes(ntc, true), stream)(tmQ, tmG, (const bf16*)K, (const bf16*)V, lse, dsum, (bf16*)dK,
-                                                                                 (bf16*)dV, d, ldk, ldv, lddk, lddv, ntc, dc);
+                                                                                 (bf16*)dV, d, ldk, ldv, lddk, lddv, ntc, dc, (uint4*)nullptr);
     return ick_check_launch("mha_bwd_mma(dkv)");
 }

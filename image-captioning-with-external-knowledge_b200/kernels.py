@@ -57,6 +57,7 @@ class CudaKernels:
         # ALGORITHMIC work of the launch (bytes, flops) for the roofline line; None = no instrumentation.
         self.prof = None
         self._ws = None  # fp32 workspace for the split-partials of the tensor-core wgrad
+        self._ds_ws = None  # bf16 dS^T workspace of the attention backward
 
     # ------------------------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -184,8 +185,16 @@ class CudaKernels:
 
     def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
         p, seed, site = _drop(drop)
+        ws = None
+        if Q.dtype == torch.bfloat16:
+            # dS^T workspace of the dQ-from-dS scheme (1 KiB per 16-key x 32-query block); grown on demand, shared by all calls
+            need = B * H * ((Sk + 15) // 16) * 2 * ((Sq + 63) // 64) * 1024
+            if self._ds_ws is None or self._ds_ws.numel() < need or self._ds_ws.device != Q.device:
+                self._ds_ws = torch.empty(need, dtype=torch.uint8, device=Q.device)
+            ws = self._ds_ws
         self._call("ick_mha_bwd", _p(Q), _p(K), _p(V), _p(O), _p(dO), _p(lse), _p(dsum), _p(dQ), _p(dK), _p(dV), dt_of(Q), B, H, Sq,
-                   Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, n=2,
+                   Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, _p(ws),
+                   ws.numel() if ws is not None else 0, n=3 if ws is not None else 2,
                    work=lambda: (B * H * dh * (4 * Sq + 4 * Sk) * Q.element_size() + 2 * B * H * Sq * 4,
                                  int(10 * B * H * Sq * Sk * dh * (0.5 if causal else 1.0))))
 

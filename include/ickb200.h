@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 4
+#define ICK_ABI_VERSION 5
 
 #ifdef __cplusplus
 extern "C" {
@@ -78,7 +78,10 @@ int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O, float* lse
                 int ldq, int ldk, int ldv, int ldo, int causal, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
 int ick_mha_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
                 void* dK, void* dV, int dt, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo,
-                int lddq, int lddk, int lddv, int causal, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
+                int lddq, int lddk, int lddv, int causal, float drop_p, unsigned seed, unsigned site, void* workspace,
+                long long workspace_bytes, cudaStream_t stream);
+/* workspace (optional, bf16 path): B*H*ceil(Sk/16)*2*ceil(Sq/64) KiB.  With it the backward runs as rowsum(dO*O) -> dK/dV (which
+ * also stores dS^T) -> dQ = dS K as a GEMM over the stored dS; without it dS is recomputed by a separate dQ kernel. */
 /* one query per (batch, head) against klen cached keys/values (KV-cached greedy decode; predict() re-decodes instead) */
 int ick_mha_decode(const void* Q, const void* K, const void* V, void* O, int dt, int B, int H, int dh, int ldq, int ldk, int ldv,
                    int ldo, long long kbatch_stride, long long vbatch_stride, int klen, cudaStream_t stream);

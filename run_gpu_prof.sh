@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-R=r29
-(timeout 900 python -m pytest tests -m gpu -q --tb=short -x --timeout 600 2>&1 | tail -4) > gpurun_out/${R}_tests.log
-(timeout 600 python bench.py --steps 20 --warmup 3 2> gpurun_out/${R}_bench.err | tail -1) > gpurun_out/${R}_bench.json
-python tools/step_prof.py 2 > gpurun_out/${R}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 220 -c 240 --csv --log-file gpurun_out/${R}_launches.csv python tools/step_prof.py 2 > gpurun_out/${R}_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"wgrad_group_tc_kernel|gemm_tn_tc_kernel|bwd_dkv_pkernel|bwd_dq_pkernel" -s 100 -c 14 -o gpurun_out/${R}_top -f python tools/step_prof.py 2 > gpurun_out/${R}_ncu2.log 2>&1
-tail -n 3 gpurun_out/${R}_tests.log; cut -c1-200 gpurun_out/${R}_bench.json; tail -n 2 gpurun_out/${R}_ncu2.log
+R=r35
+python tools/attn_prof.py > gpurun_out/${R}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum --clock-control none --csv --log-file gpurun_out/${R}_attn_launches.csv python tools/attn_prof.py > gpurun_out/${R}_ncu1.log 2>&1
+grep -E "pkernel|dq_ds|rowdot" gpurun_out/${R}_attn_launches.csv | tail -20 | awk -F'","' '{print substr($5,1,40), $13, $15}'

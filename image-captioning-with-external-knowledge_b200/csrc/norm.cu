@@ -29,19 +29,42 @@ __device__ __forceinline__ bool pair_valid(int lane) {
     else return lane + 32 * I < NP;
 }
 
+// Up to two row groups with their own LayerNorm parameters, dropout site and output row map in one launch (the entity and the
+// fact encoder stacks run in lockstep on one row-concatenated buffer): blocks [0, nb0) take group 0, the rest group 1, so a
+// block (and its dgamma/dbeta partials in the backward) belongs to exactly one parameter set.  Rows and dropout row indices
+// are group-local; tensors are indexed by row_start + r.
+struct LnGroup {
+    const float* gamma;
+    const float* beta;   // forward only
+    float* dgamma;       // backward only
+    float* dbeta;
+    RowMap map;          // forward: output row map; backward: dy row map
+    int rows, row_start;
+    uint32_t site;
+};
+struct LnGroups {
+    LnGroup g[2];
+    int nb0;
+};
+
 template <typename T, int D, int LD, int MINB>
-__global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __restrict__ X, T* __restrict__ SUB,
-                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                    T* __restrict__ Y, float* __restrict__ MEAN, float* __restrict__ RSTD,
-                                                                    int rows, float eps, RowMap ymap, DropCfg drop) {
+__global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __restrict__ X, T* __restrict__ SUB, T* __restrict__ Y,
+                                                                    float* __restrict__ MEAN, float* __restrict__ RSTD, float eps,
+                                                                    LnGroups gs, DropCfg drop) {
     ick_pdl_entry();
     ick_resolve_seed(drop);
     constexpr int NP = D / 2, NPL = LD / 2, NI = (NPL + 31) / 32;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool second = (int)blockIdx.x >= gs.nb0;
+    const LnGroup& G = gs.g[second ? 1 : 0];
+    const int warp = (((int)blockIdx.x - (second ? gs.nb0 : 0)) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nwarps = ((second ? (int)gridDim.x - gs.nb0 : gs.nb0) * blockDim.x) >> 5;
+    const int rows = G.rows;
     const bool has_x = X != nullptr;
     const bool dropping = drop.thr != 0u;
+    const float* gamma = G.gamma;
+    const float* beta = G.beta;
+    const RowMap ymap = G.map;
     float2 gm[NI], bt[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -51,8 +74,9 @@ __global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __r
         bt[i] = ok ? *reinterpret_cast<const float2*>(beta + 2 * p) : make_float2(0.f, 0.f);
     }
     for (int r = warp; r < rows; r += nwarps) {
-        const T* x = X + (size_t)r * LD;
-        T* s = SUB + (size_t)r * LD;
+        const size_t gr = (size_t)(G.row_start + r);
+        const T* x = X + gr * LD;
+        T* s = SUB + gr * LD;
         float2 v[NI], xr[NI];
 #pragma unroll
         for (int i = 0; i < NI; ++i) {  // all loads of the row first (memory-level parallelism)
@@ -66,7 +90,7 @@ __global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __r
         }
         float sum = 0.f;
         if (dropping) {
-            const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)r);
+            const uint32_t rmix = ick_rowmix(drop.seed, G.site, (uint64_t)r);
 #pragma unroll
             for (int i = 0; i < NI; ++i) {
                 const int p = lane + 32 * i;
@@ -93,7 +117,8 @@ __global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __r
         }
         const float rstd = rsqrtf(warp_sum(var) * (1.0f / (float)D) + eps);
         const float nmr = -mean * rstd;
-        T* y = Y + ymap.map(r) * LD;
+        // a row map addresses the output buffer from its base; without one the output shares the input's row numbering
+        T* y = Y + (ymap.s_in == 0 ? gr : ymap.map(r)) * LD;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int p = lane + 32 * i;
@@ -104,25 +129,30 @@ __global__ void __launch_bounds__(256, MINB) add_ln_fwd_fast_kernel(const T* __r
             }
         }
         if (lane == 0) {
-            MEAN[r] = mean;
-            RSTD[r] = rstd;
+            MEAN[gr] = mean;
+            RSTD[gr] = rstd;
         }
     }
 }
 
 template <typename T, int D, int LD, int MINB>
 __global__ void __launch_bounds__(256, MINB) add_ln_bwd_fast_kernel(const T* __restrict__ DY, const T* __restrict__ S,
-                                                                    const float* __restrict__ MEAN, const float* __restrict__ RSTD,
-                                                                    const float* __restrict__ gamma, T* DRES, T* __restrict__ DSUB,
-                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
-                                                                    RowMap dymap, int acc_res, DropCfg drop) {
+                                                                    const float* __restrict__ MEAN, const float* __restrict__ RSTD, T* DRES,
+                                                                    T* __restrict__ DSUB, int acc_res, LnGroups gs, DropCfg drop) {
     ick_pdl_entry();
     constexpr int NP = D / 2, NPL = LD / 2, NI = (NPL + 31) / 32;
     __shared__ float sg[2 * NI * 32], sb[2 * NI * 32];
     ick_resolve_seed(drop);
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool second = (int)blockIdx.x >= gs.nb0;
+    const LnGroup& G = gs.g[second ? 1 : 0];
+    const int warp = (((int)blockIdx.x - (second ? gs.nb0 : 0)) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nwarps = ((second ? (int)gridDim.x - gs.nb0 : gs.nb0) * blockDim.x) >> 5;
+    const int rows = G.rows;
+    const float* gamma = G.gamma;
+    float* dgamma = G.dgamma;
+    float* dbeta = G.dbeta;
+    const RowMap dymap = G.map;
     const bool dropping = drop.thr != 0u;
     const bool has_res = DRES != nullptr, has_sub = DSUB != nullptr;
     for (int i = threadIdx.x; i < 2 * NI * 32; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
@@ -137,9 +167,10 @@ __global__ void __launch_bounds__(256, MINB) add_ln_bwd_fast_kernel(const T* __r
     }
     constexpr float inv_d = 1.0f / (float)D;
     for (int r = warp; r < rows; r += nwarps) {
-        const T* dy = DY + dymap.map(r) * LD;
-        const T* s = S + (size_t)r * LD;
-        const float mean = MEAN[r], rstd = RSTD[r];
+        const size_t gr = (size_t)(G.row_start + r);
+        const T* dy = DY + (dymap.s_in == 0 ? gr : dymap.map(r)) * LD;
+        const T* s = S + gr * LD;
+        const float mean = MEAN[gr], rstd = RSTD[gr];
         const float nmr = -mean * rstd;
         float2 g[NI], xh[NI];
         float sum_g = 0.f, sum_gx = 0.f;
@@ -170,9 +201,9 @@ __global__ void __launch_bounds__(256, MINB) add_ln_bwd_fast_kernel(const T* __r
         }
         const float c1 = warp_sum(sum_g) * inv_d * rstd;
         const float c2 = warp_sum(sum_gx) * inv_d * rstd;
-        T* dres = DRES + (size_t)r * LD;
-        T* dsub = DSUB + (size_t)r * LD;
-        const uint32_t rmix = dropping ? ick_rowmix(drop.seed, drop.site, (uint64_t)r) : 0u;
+        T* dres = DRES + gr * LD;
+        T* dsub = DSUB + gr * LD;
+        const uint32_t rmix = dropping ? ick_rowmix(drop.seed, G.site, (uint64_t)r) : 0u;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int p = lane + 32 * i;
@@ -398,7 +429,75 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const T* __restrict__ D
     }
 }
 
+int launch_ln_fwd_fast(const void* x, void* sub, void* y, float* mean, float* rstd, int dt, float eps, const LnGroups& gs, int blocks,
+                       const DropCfg& dc, cudaStream_t stream) {
+    if (dt == ICK_F32)
+        ick_launch(add_ln_fwd_fast_kernel<float, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const float*)x, (float*)sub, (float*)y, mean, rstd, eps,
+                                                                                           gs, dc);
+    else
+        ick_launch(add_ln_fwd_fast_kernel<bf16, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const bf16*)x, (bf16*)sub, (bf16*)y, mean, rstd, eps, gs,
+                                                                                          dc);
+    return ick_check_launch("add_ln_fwd");
+}
+int launch_ln_bwd_fast(const void* dy, const void* s, const float* mean, const float* rstd, void* dres, void* dsub, int dt, int acc_res,
+                       const LnGroups& gs, int blocks, const DropCfg& dc, cudaStream_t stream) {
+    if (dt == ICK_F32)
+        ick_launch(add_ln_bwd_fast_kernel<float, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const float*)dy, (const float*)s, mean, rstd,
+                                                                                           (float*)dres, (float*)dsub, acc_res, gs, dc);
+    else
+        ick_launch(add_ln_bwd_fast_kernel<bf16, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const bf16*)dy, (const bf16*)s, mean, rstd, (bf16*)dres,
+                                                                                          (bf16*)dsub, acc_res, gs, dc);
+    return ick_check_launch("add_ln_bwd");
+}
+// blocks of a two-group launch: proportional to the rows, at least one block per non-empty group
+void split_blocks(int rows0, int rows1, int max_blocks, int* nb0, int* nb) {
+    int total = min((rows0 + rows1 + 7) / 8, max_blocks);
+    if (total < 2) total = 2;
+    int b0 = (int)((long long)total * rows0 / (rows0 + rows1));
+    if (b0 < 1) b0 = 1;
+    if (b0 > total - 1) b0 = total - 1;
+    *nb0 = b0;
+    *nb = total;
+}
+
 }  // namespace
+
+extern "C" int ick_add_ln_fwd_dual(const void* x, void* sub, void* y, float* mean, float* rstd, int dt, int d, int ld, float eps, int rows0,
+                                   int rows1, int row1_start, const float* gamma0, const float* beta0, const float* gamma1, const float* beta1,
+                                   int map0_s_in, int map0_s_out, int map0_off, int map1_s_in, int map1_s_out, int map1_off, float drop_p,
+                                   unsigned seed, unsigned site0, unsigned site1, cudaStream_t stream) {
+    ICK_REQUIRE(d == FAST_D && ld == FAST_LD && (dt == ICK_F32 || dt == ICK_BF16), "add_ln_fwd_dual: only d=%d, ld=%d rows are supported", FAST_D,
+                FAST_LD);
+    ICK_REQUIRE(rows0 > 0 && rows1 > 0 && row1_start >= rows0, "add_ln_fwd_dual: bad row groups");
+    DropCfg dc = make_drop(drop_p, seed, site0);
+    LnGroups gs = {};
+    gs.g[0].gamma = gamma0; gs.g[0].beta = beta0; gs.g[0].map = RowMap{map0_s_in, map0_s_out, map0_off}; gs.g[0].rows = rows0; gs.g[0].row_start = 0;
+    gs.g[0].site = site0;
+    gs.g[1].gamma = gamma1; gs.g[1].beta = beta1; gs.g[1].map = RowMap{map1_s_in, map1_s_out, map1_off}; gs.g[1].rows = rows1;
+    gs.g[1].row_start = row1_start; gs.g[1].site = site1;
+    int nb;
+    split_blocks(rows0, rows1, 148 * 4, &gs.nb0, &nb);
+    return launch_ln_fwd_fast(x, sub, y, mean, rstd, dt, eps, gs, nb, dc, stream);
+}
+
+extern "C" int ick_add_ln_bwd_dual(const void* dy, const void* s, const float* mean, const float* rstd, void* dres, void* dsub, int dt, int d,
+                                   int ld, int rows0, int rows1, int row1_start, const float* gamma0, const float* gamma1, float* dgamma0,
+                                   float* dbeta0, float* dgamma1, float* dbeta1, int map0_s_in, int map0_s_out, int map0_off, int map1_s_in,
+                                   int map1_s_out, int map1_off, int acc_res, float drop_p, unsigned seed, unsigned site0, unsigned site1,
+                                   cudaStream_t stream) {
+    ICK_REQUIRE(d == FAST_D && ld == FAST_LD && (dt == ICK_F32 || dt == ICK_BF16), "add_ln_bwd_dual: only d=%d, ld=%d rows are supported", FAST_D,
+                FAST_LD);
+    ICK_REQUIRE(rows0 > 0 && rows1 > 0 && row1_start >= rows0, "add_ln_bwd_dual: bad row groups");
+    DropCfg dc = make_drop(drop_p, seed, site0);
+    LnGroups gs = {};
+    gs.g[0].gamma = gamma0; gs.g[0].dgamma = dgamma0; gs.g[0].dbeta = dbeta0; gs.g[0].map = RowMap{map0_s_in, map0_s_out, map0_off};
+    gs.g[0].rows = rows0; gs.g[0].row_start = 0; gs.g[0].site = site0;
+    gs.g[1].gamma = gamma1; gs.g[1].dgamma = dgamma1; gs.g[1].dbeta = dbeta1; gs.g[1].map = RowMap{map1_s_in, map1_s_out, map1_off};
+    gs.g[1].rows = rows1; gs.g[1].row_start = row1_start; gs.g[1].site = site1;
+    int nb;
+    split_blocks(rows0, rows1, 148 * 3, &gs.nb0, &nb);
+    return launch_ln_bwd_fast(dy, s, mean, rstd, dres, dsub, dt, acc_res, gs, nb, dc, stream);
+}
 
 extern "C" int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, const float* beta, void* y, float* mean,
                               float* rstd, int dt, int rows, int d, int ldx, int lds, int ldy, float eps, int map_s_in,
@@ -410,14 +509,10 @@ extern "C" int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, cons
     RowMap m{map_s_in, map_s_out, map_off};
     DropCfg dc = make_drop(drop_p, seed, site);
     if (d == FAST_D && ldx == FAST_LD && lds == FAST_LD && ldy == FAST_LD && (dt == ICK_F32 || dt == ICK_BF16)) {
-        const int blocks = min((rows + 7) / 8, 148 * 4);
-        if (dt == ICK_F32)
-            ick_launch(add_ln_fwd_fast_kernel<float, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const float*)x, (float*)sub, gamma, beta, (float*)y,
-                                                                                               mean, rstd, rows, eps, m, dc);
-        else
-            ick_launch(add_ln_fwd_fast_kernel<bf16, FAST_D, FAST_LD, 4>, blocks, 256, 0, stream)((const bf16*)x, (bf16*)sub, gamma, beta, (bf16*)y,
-                                                                                              mean, rstd, rows, eps, m, dc);
-        return ick_check_launch("add_ln_fwd");
+        LnGroups gs = {};
+        gs.g[0].gamma = gamma; gs.g[0].beta = beta; gs.g[0].map = m; gs.g[0].rows = rows; gs.g[0].row_start = 0; gs.g[0].site = dc.site;
+        gs.nb0 = min((rows + 7) / 8, 148 * 4);
+        return launch_ln_fwd_fast(x, sub, y, mean, rstd, dt, eps, gs, gs.nb0, dc, stream);
     }
     const int blocks = min((rows + 7) / 8, 148 * 8);
     if (dt == ICK_F32)
@@ -445,16 +540,11 @@ extern "C" int ick_add_ln_bwd(const void* dy, const void* s, const float* mean, 
     DropCfg dc = make_drop(drop_p, seed, site);
     if (d == FAST_D && lddy == FAST_LD && lds == FAST_LD && (dres == nullptr || ldres == FAST_LD) && (dsub == nullptr || ldsub == FAST_LD) &&
         (dt == ICK_F32 || dt == ICK_BF16)) {
-        const int blocks = min((rows + 7) / 8, 148 * 3);
-        if (dt == ICK_F32)
-            ick_launch(add_ln_bwd_fast_kernel<float, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const float*)dy, (const float*)s, mean, rstd, gamma,
-                                                                                               (float*)dres, (float*)dsub, dgamma, dbeta, rows, m,
-                                                                                               acc_res, dc);
-        else
-            ick_launch(add_ln_bwd_fast_kernel<bf16, FAST_D, FAST_LD, 3>, blocks, 256, 0, stream)((const bf16*)dy, (const bf16*)s, mean, rstd, gamma,
-                                                                                              (bf16*)dres, (bf16*)dsub, dgamma, dbeta, rows, m,
-                                                                                              acc_res, dc);
-        return ick_check_launch("add_ln_bwd");
+        LnGroups gs = {};
+        gs.g[0].gamma = gamma; gs.g[0].dgamma = dgamma; gs.g[0].dbeta = dbeta; gs.g[0].map = m; gs.g[0].rows = rows; gs.g[0].row_start = 0;
+        gs.g[0].site = dc.site;
+        gs.nb0 = min((rows + 7) / 8, 148 * 3);
+        return launch_ln_bwd_fast(dy, s, mean, rstd, dres, dsub, dt, acc_res, gs, gs.nb0, dc, stream);
     }
     const int blocks = min((rows + 7) / 8, 148 * 2);
     if (dt == ICK_F32)

@@ -219,22 +219,20 @@ class DecoderEngine:
             K.gemm_dual(sv.o, out_l[0].W, out_l[1].W, sv.s1, off, Re, out_l[0].b, out_l[1].b)
             sv.y1 = self._new(Rc, DP)
             sv.mean1, sv.rstd1, sv.mean2, sv.rstd2 = (self._newf(Rc) for _ in range(4))
-            for i, (_, S, R, r0, _) in enumerate(stacks):
-                sl = slice(r0, r0 + R)
-                K.add_ln_fwd(x[sl], sv.s1[sl], self.param(pre[i] + "norm1.weight"), self.param(pre[i] + "norm1.bias"), sv.y1[sl],
-                             sv.mean1[sl], sv.rstd1[sl], D, drop=self._drop(p, seed, site[i] + ".d1"))
+            Rf = stacks[1][2]
+            par = lambda n: (self.param(pre[0] + n), self.param(pre[1] + n))  # noqa: E731
+            K.add_ln_fwd_dual(x, sv.s1, sv.y1, sv.mean1, sv.rstd1, D, Re, Rf, off, par("norm1.weight"), par("norm1.bias"),
+                              drops=(self._drop(p, seed, site[0] + ".d1"), self._drop(p, seed, site[1] + ".d1")))
             sv.h1 = self._new(Rc, f1[0].lin.Np)
             K.gemm_dual(sv.y1, f1[0].W, f1[1].W, sv.h1, off, Re, f1[0].b, f1[1].b, epi=1, drop0=self._drop(p, seed, site[0] + ".ffn"),
                         drop1=self._drop(p, seed, site[1] + ".ffn"))
             sv.s2 = self._new(Rc, DP)
             K.gemm_dual(sv.h1, f2[0].W, f2[1].W, sv.s2, off, Re, f2[0].b, f2[1].b)
             y2 = None if last else self._new(Rc, DP)
-            for i, (_, S, R, r0, m0) in enumerate(stacks):
-                sl = slice(r0, r0 + R)
-                # the last layer writes straight into the decoder's memory rows (the reference concatenates, K/models.py:497-499)
-                K.add_ln_fwd(sv.y1[sl], sv.s2[sl], self.param(pre[i] + "norm2.weight"), self.param(pre[i] + "norm2.bias"),
-                             mem if last else y2[sl], sv.mean2[sl], sv.rstd2[sl], D, rowmap=(S, M, m0) if last else (0, 0, 0),
-                             drop=self._drop(p, seed, site[i] + ".d2"))
+            # the last layer writes straight into the decoder's memory rows (the reference concatenates, K/models.py:497-499)
+            maps = tuple((S, M, m0) if last else (0, 0, 0) for (_, S, _, _, m0) in stacks)
+            K.add_ln_fwd_dual(sv.y1, sv.s2, mem if last else y2, sv.mean2, sv.rstd2, D, Re, Rf, off, par("norm2.weight"), par("norm2.bias"),
+                              rowmaps=maps, drops=(self._drop(p, seed, site[0] + ".d2"), self._drop(p, seed, site[1] + ".d2")))
             x = y2
             saves.append(sv)
         return saves
@@ -254,22 +252,25 @@ class DecoderEngine:
             qkv_l, out_l, f1, f2 = lin("self_attn.qkv"), lin("self_attn.out"), lin("ffn1"), lin("ffn2")
             wg = []
             dA, dB2 = self._new(Rc, DP), self._new(Rc, DP)
+            Rf = stacks[1][2]
+            par = lambda n: (self.param(pre[0] + n), self.param(pre[1] + n))  # noqa: E731
+            gpar = lambda n: (self.param(pre[0] + n, gflat), self.param(pre[1] + n, gflat))  # noqa: E731
+            maps = tuple((S, M, m0) if last else (0, 0, 0) for (_, S, _, _, m0) in stacks)
+            K.add_ln_bwd_dual(dmem if last else d, sv.s2, sv.mean2, sv.rstd2, dA, dB2, D, Re, Rf, off, par("norm2.weight"), gpar("norm2.weight"),
+                              gpar("norm2.bias"), rowmaps=maps,
+                              drops=(self._drop(p, seed, site[0] + ".d2"), self._drop(p, seed, site[1] + ".d2")))
             for i, (_, S, R, r0, m0) in enumerate(stacks):
                 sl = slice(r0, r0 + R)
-                K.add_ln_bwd(dmem if last else d[sl], sv.s2[sl], sv.mean2[sl], sv.rstd2[sl], self.param(pre[i] + "norm2.weight"), dA[sl],
-                             dB2[sl], self.param(pre[i] + "norm2.weight", gflat), self.param(pre[i] + "norm2.bias", gflat), D,
-                             rowmap=(S, M, m0) if last else (0, 0, 0), drop=self._drop(p, seed, site[i] + ".d2"))
                 self._wg(wg, dB2[sl], sv.h1[sl], f2[i])
             dh1 = self._new(Rc, f1[0].lin.Np)
             K.gemm_dual(dB2, f2[0].WT, f2[1].WT, dh1, off, Re, aux=sv.h1, epi=2, drop0=ep, drop1=ep)
             K.gemm_dual(dh1, f1[0].WT, f1[1].WT, dA, off, Re, accumulate=True)
             dC, dB1 = self._new(Rc, DP), self._new(Rc, DP)
+            K.add_ln_bwd_dual(dA, sv.s1, sv.mean1, sv.rstd1, dC, dB1, D, Re, Rf, off, par("norm1.weight"), gpar("norm1.weight"), gpar("norm1.bias"),
+                              drops=(self._drop(p, seed, site[0] + ".d1"), self._drop(p, seed, site[1] + ".d1")))
             for i, (_, S, R, r0, _) in enumerate(stacks):
                 sl = slice(r0, r0 + R)
                 self._wg(wg, dh1[sl], sv.y1[sl], f1[i])
-                K.add_ln_bwd(dA[sl], sv.s1[sl], sv.mean1[sl], sv.rstd1[sl], self.param(pre[i] + "norm1.weight"), dC[sl], dB1[sl],
-                             self.param(pre[i] + "norm1.weight", gflat), self.param(pre[i] + "norm1.bias", gflat), D,
-                             drop=self._drop(p, seed, site[i] + ".d1"))
                 self._wg(wg, dB1[sl], sv.o[sl], out_l[i])
             dO = self._new(Rc, DP)
             K.gemm_dual(dB1, out_l[0].WT, out_l[1].WT, dO, off, Re)

@@ -218,6 +218,36 @@ class CudaKernels:
                    rowmap[0], rowmap[1], rowmap[2], int(acc_res), p, seed, site,
                    work=lambda: (rows * d * s.element_size() * (4 + (1 if acc_res else 0)), 0))
 
+    # Two row groups (rows [0, rows0) and [row1, row1 + rows1) of the same buffers) with their own LayerNorm parameters, dropout
+    # sites and row maps in one launch; y / dy are the concatenated buffer (identity map) or the row-mapped target of both groups.
+    def add_ln_fwd_dual(self, x, sub, y, mean, rstd, d, rows0, rows1, row1, gammas, betas, rowmaps=((0, 0, 0), (0, 0, 0)), drops=(None, None),
+                        eps=1e-5):
+        (p, seed, site0), (p1, seed1, site1) = _drop(drops[0]), _drop(drops[1])
+        if not (d == 300 and _ld(sub) == 320 and _ld(x) == 320 and _ld(y) == 320 and (p, seed) == (p1, seed1)):
+            for i, (r0, n) in enumerate(((0, rows0), (row1, rows1))):
+                mapped = rowmaps[i][0] != 0
+                self.add_ln_fwd(x[r0:r0 + n], sub[r0:r0 + n], gammas[i], betas[i], y if mapped else y[r0:r0 + n], mean[r0:r0 + n],
+                                rstd[r0:r0 + n], d, eps, rowmaps[i], drops[i])
+            return
+        rows = rows0 + rows1
+        self._call("ick_add_ln_fwd_dual", _p(x), _p(sub), _p(y), _p(mean), _p(rstd), dt_of(sub), d, 320, eps, rows0, rows1, row1,
+                   _p(gammas[0]), _p(betas[0]), _p(gammas[1]), _p(betas[1]), *rowmaps[0], *rowmaps[1], p, seed, site0, site1,
+                   work=lambda: (rows * d * sub.element_size() * 4, 0))
+
+    def add_ln_bwd_dual(self, dy, s, mean, rstd, dres, dsub, d, rows0, rows1, row1, gammas, dgammas, dbetas, rowmaps=((0, 0, 0), (0, 0, 0)),
+                        drops=(None, None), acc_res=False):
+        (p, seed, site0), (p1, seed1, site1) = _drop(drops[0]), _drop(drops[1])
+        if not (d == 300 and _ld(s) == 320 and _ld(dy) == 320 and _ld(dres) == 320 and _ld(dsub) == 320 and (p, seed) == (p1, seed1)):
+            for i, (r0, n) in enumerate(((0, rows0), (row1, rows1))):
+                mapped = rowmaps[i][0] != 0
+                self.add_ln_bwd(dy if mapped else dy[r0:r0 + n], s[r0:r0 + n], mean[r0:r0 + n], rstd[r0:r0 + n], gammas[i], dres[r0:r0 + n],
+                                dsub[r0:r0 + n], dgammas[i], dbetas[i], d, rowmaps[i], acc_res, drops[i])
+            return
+        rows = rows0 + rows1
+        self._call("ick_add_ln_bwd_dual", _p(dy), _p(s), _p(mean), _p(rstd), _p(dres), _p(dsub), dt_of(s), d, 320, rows0, rows1, row1,
+                   _p(gammas[0]), _p(gammas[1]), _p(dgammas[0]), _p(dbetas[0]), _p(dgammas[1]), _p(dbetas[1]), *rowmaps[0], *rowmaps[1],
+                   int(acc_res), p, seed, site0, site1, work=lambda: (rows * d * s.element_size() * (4 + (1 if acc_res else 0)), 0))
+
     # ---- context preparation ------------------------------------------------------------------------------------------
     def entity_encode_fwd(self, entities, facts, type_emb, word_emb, out, variant, B, E, F, D, ntypes, V):
         self._call("ick_entity_encode_fwd", _p(entities), _p(facts), _p(type_emb), _p(word_emb), _p(out), dt_of(out), variant, B, E,

@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 5
+#define ICK_ABI_VERSION 6
 
 #ifdef __cplusplus
 extern "C" {
@@ -95,6 +95,18 @@ int ick_add_ln_fwd(const void* x, void* sub, const float* gamma, const float* be
 int ick_add_ln_bwd(const void* dy, const void* s, const float* mean, const float* rstd, const float* gamma, void* dres, void* dsub,
                    float* dgamma, float* dbeta, int dt, int rows, int d, int lddy, int lds, int ldres, int ldsub, int map_s_in,
                    int map_s_out, int map_off, int acc_res, float drop_p, unsigned seed, unsigned site, cudaStream_t stream);
+/* Two row groups of the same buffers - rows [0, rows0) and [row1_start, row1_start + rows1) - with their own LayerNorm
+ * parameters, dropout sites and row maps in one launch (the lockstep entity / fact encoder stacks).  Rows and dropout row
+ * indices are group-local; a zero row map means "same row as the input".  d = 300 in rows of 320 elements only. */
+int ick_add_ln_fwd_dual(const void* x, void* sub, void* y, float* mean, float* rstd, int dt, int d, int ld, float eps, int rows0,
+                        int rows1, int row1_start, const float* gamma0, const float* beta0, const float* gamma1, const float* beta1,
+                        int map0_s_in, int map0_s_out, int map0_off, int map1_s_in, int map1_s_out, int map1_off, float drop_p,
+                        unsigned seed, unsigned site0, unsigned site1, cudaStream_t stream);
+int ick_add_ln_bwd_dual(const void* dy, const void* s, const float* mean, const float* rstd, void* dres, void* dsub, int dt, int d,
+                        int ld, int rows0, int rows1, int row1_start, const float* gamma0, const float* gamma1, float* dgamma0,
+                        float* dbeta0, float* dgamma1, float* dbeta1, int map0_s_in, int map0_s_out, int map0_off, int map1_s_in,
+                        int map1_s_out, int map1_off, int acc_res, float drop_p, unsigned seed, unsigned site0, unsigned site1,
+                        cudaStream_t stream);
 
 /* ---- context preparation ------------------------------------------------------------------------------------------------- */
 /* EntityEncoder.forward: variant 0 = geo (G/models.py:82-104), 1 = knowledge (K/models.py:82-133), 2 = news (N/models.py:79-134) */

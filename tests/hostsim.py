@@ -177,6 +177,20 @@ class HostKernels:
         mean.copy_(mu.flatten())
         rstd.copy_(rs.flatten())
 
+    def add_ln_fwd_dual(self, x, sub, y, mean, rstd, d, rows0, rows1, row1, gammas, betas, rowmaps=((0, 0, 0), (0, 0, 0)), drops=(None, None),
+                        eps=1e-5):
+        for i, (r0, n) in enumerate(((0, rows0), (row1, rows1))):
+            mapped = rowmaps[i][0] != 0
+            self.add_ln_fwd(x[r0:r0 + n], sub[r0:r0 + n], gammas[i], betas[i], y if mapped else y[r0:r0 + n], mean[r0:r0 + n], rstd[r0:r0 + n],
+                            d, eps, rowmaps[i], drops[i])
+
+    def add_ln_bwd_dual(self, dy, s, mean, rstd, dres, dsub, d, rows0, rows1, row1, gammas, dgammas, dbetas, rowmaps=((0, 0, 0), (0, 0, 0)),
+                        drops=(None, None), acc_res=False):
+        for i, (r0, n) in enumerate(((0, rows0), (row1, rows1))):
+            mapped = rowmaps[i][0] != 0
+            self.add_ln_bwd(dy if mapped else dy[r0:r0 + n], s[r0:r0 + n], mean[r0:r0 + n], rstd[r0:r0 + n], gammas[i], dres[r0:r0 + n],
+                            dsub[r0:r0 + n], dgammas[i], dbetas[i], d, rowmaps[i], acc_res, drops[i])
+
     def add_ln_bwd(self, dy, s, mean, rstd, gamma, dres, dsub, dgamma, dbeta, d, rowmap=(0, 0, 0), acc_res=False, drop=None):
         self.calls += 1
         R = s.shape[0]

@@ -292,6 +292,46 @@ def test_add_ln_fwd_bwd(K, Hk, dtype, p, rows, rowmap, yrows):
         assert err(dgg, dgr) < 1e-3 and err(dbg, dbr) < 1e-3
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("p", [0.0, 0.5])
+@pytest.mark.parametrize("mapped", [False, True])
+def test_add_ln_dual(K, Hk, dtype, p, mapped):
+    """Two row groups (entity rows | pad | fact rows) with their own gamma/beta, dropout sites and row maps in one launch."""
+    d, ld, B, S0, S1, P = 300, 320, 3, 23, 7, 5
+    rows0, rows1 = B * S0, B * S1
+    row1 = (rows0 + 127) // 128 * 128
+    R = row1 + rows1
+    M = P + S0 + S1
+    x, sub = rnd((R, ld), dtype, 1), rnd((R, ld), dtype, 2)
+    gam = [1 + 0.1 * rnd((d,), torch.float32, 3 + i) for i in range(2)]
+    bet = [rnd((d,), torch.float32, 5 + i) for i in range(2)]
+    drops = ((p, 7, 3), (p, 7, 4)) if p > 0 else (None, None)
+    maps = ((S0, M, P), (S1, M, P + S0)) if mapped else ((0, 0, 0), (0, 0, 0))
+    yrows = B * M if mapped else R
+    yr, yg = torch.zeros(yrows, ld, dtype=dtype), torch.zeros(yrows, ld, dtype=dtype).cuda()
+    sr, sg = sub.clone(), sub.clone().cuda()
+    mr, rr, mg, rg = torch.zeros(R), torch.zeros(R), torch.zeros(R).cuda(), torch.zeros(R).cuda()
+    Hk.add_ln_fwd_dual(x, sr, yr, mr, rr, d, rows0, rows1, row1, gam, bet, maps, drops)
+    K.add_ln_fwd_dual(cu(x), sg, yg, mg, rg, d, rows0, rows1, row1, [cu(t) for t in gam], [cu(t) for t in bet], maps, drops)
+    real = torch.cat([torch.arange(rows0), torch.arange(row1, R)])
+    assert err(yg, yr) < TOL[dtype]
+    assert err(sg[real][:, :d], sr[real][:, :d]) < TOL[dtype]
+    assert err(mg[real], mr[real]) < 1e-3 and err(rg[real], rr[real]) < 1e-3
+    dy = rnd((yrows, ld), dtype, 9)
+    for acc in (False, True):
+        dres_r = rnd((R, ld), dtype, 6) if acc else torch.zeros(R, ld, dtype=dtype)
+        dres_g = dres_r.clone().cuda()
+        dsub_r, dsub_g = torch.zeros(R, ld, dtype=dtype), torch.zeros(R, ld, dtype=dtype).cuda()
+        dgr, dbr = [rnd((d,), torch.float32, 11 + i) for i in range(2)], [rnd((d,), torch.float32, 13 + i) for i in range(2)]
+        dgg, dbg = [t.clone().cuda() for t in dgr], [t.clone().cuda() for t in dbr]
+        Hk.add_ln_bwd_dual(dy, sr, mr, rr, dres_r, dsub_r, d, rows0, rows1, row1, gam, dgr, dbr, maps, drops, acc)
+        K.add_ln_bwd_dual(cu(dy), cu(sr), cu(mr), cu(rr), dres_g, dsub_g, d, rows0, rows1, row1, [cu(t) for t in gam], dgg, dbg, maps, drops, acc)
+        assert err(dres_g[real][:, :d], dres_r[real][:, :d]) < TOL[dtype] * 2
+        assert err(dsub_g[real], dsub_r[real]) < TOL[dtype] * 2
+        for i in range(2):
+            assert err(dgg[i], dgr[i]) < 1e-3 and err(dbg[i], dbr[i]) < 1e-3
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def make_context(variant, B, E, F, V, seed=0):
     from ickb200 import synthetic as syn

@@ -310,6 +310,40 @@ def run_ours(a):
         roof.update({"avg_launch_ms": d[0] / d[1], "share_of_step": d[0] / total, "peak_source": pk["src"],
                      "algorithmic_per_launch": {"bytes": d[2] / d[1], "flops": d[3] / d[1]}})
 
+    # ---- greedy caption generation (BASELINE configs[3]: 5k images over 8 GPUs = 625 images per GPU, no communication) ---------------
+    # The reference has no beam search; its eval path is the batch-1 greedy predict() with the repetition
+    # clean-up, which predict_batch runs device-resident for the whole shard.  Host inputs, D2H of the tokens, 40 steps.
+    decode = None
+    if not a.no_decode:
+        try:
+            n_img, t_max = 625, 40
+            dcfg = cfg.with_batch(n_img)
+            db = syn.make_batch(dcfg, seed=100 + rank)
+            d_enc, d_ent, d_facts = db["encoder_out"].pin_memory(), db["entities"], db["facts"].pin_memory()
+            dec.eval()
+
+            def decode_once():
+                return dec.predict_batch(d_enc.to(dev, non_blocking=True), t_max, d_ent, d_facts.to(dev, non_blocking=True)).cpu()
+
+            decode_once()
+            sync_all()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                toks = decode_once()
+            sync_all()
+            dt_dec = torch.tensor([(time.perf_counter() - t0) / reps], device=dev)
+            if distributed:
+                dist.all_reduce(dt_dec, op=dist.ReduceOp.MAX)
+            decode = {"metric": "greedy_decode_captions_per_sec", "value": n_img * world / float(dt_dec), "unit": "captions/s",
+                      "images_per_gpu": n_img, "max_len": t_max, "sec_per_shard": float(dt_dec),
+                      "mean_generated_len": float((toks != 0).sum(1).float().mean()),
+                      "note": "greedy predict() + repetition clean-up (the reference has no beam search), KV-cached, device-resident loop"}
+            dec.train()
+        except Exception as e:  # the decode figure is an extra; never lose the train line over it
+            decode = {"error": f"{type(e).__name__}: {e}"}
+            dec.train()
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -330,6 +364,7 @@ def run_ours(a):
             "gpu_launches_per_step": launches_per_step,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "greedy_decode": decode,
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),
             "kernel_breakdown": breakdown,
             "lib": lib.path.replace(ROOT + "/", ""),
@@ -352,6 +387,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode extra")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph", action="store_true", help="also capture the step (including the NCCL all-reduce) when N > 1")
     a = ap.parse_args()

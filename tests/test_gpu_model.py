@@ -174,6 +174,36 @@ def test_trainer_cuda_graph_replay_matches_eager(dtype):
     assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_run_pipeline_matches_sequential_steps(use_graph):
+    """Trainer.run (H2D of batch i+1 and the loss read-back overlapped with step i) must produce, step by step and in order,
+    the losses of plain sequential train_step calls on the same host batches."""
+    from ickb200.trainer import Trainer
+
+    cfg = syn.SMALL_CONFIGS["K"]
+    host = [syn.make_batch(cfg, seed=s, equal_lengths=False) for s in (4, 5, 6, 7, 8)]
+    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    out = []
+    for pipelined in (False, True):
+        torch.manual_seed(0)
+        dec = build_module(cfg, "cuda", torch.float32, dropouts=(0.3, 0.3, 0.1)).train()
+        tr = Trainer(dec, lr=4e-4, grad_clip=5.0, use_graph=use_graph)
+        if pipelined:
+            losses = [(float(a[0]), float(a[1])) for a in tr.run(batch_args(cfg, b) for b in host)]
+        else:
+            losses = []
+            for b in host:
+                acc = tr.train_step(*batch_args(cfg, to_dev(cfg, b)))
+                losses.append((float(acc[0]), float(acc[1])))
+        out.append((losses, tr.m.clone()))
+    (l0, m0), (l1, m1) = out
+    assert len(l1) == len(host)
+    for (a0, n0), (a1, n1) in zip(l0, l1):
+        assert n0 == n1 and abs(a0 - a1) <= 1e-4 * abs(a0)
+    # Adam's first moment (the parameters themselves amplify atomics-order noise of near-zero gradients to +-lr per step)
+    assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
+
+
 @pytest.mark.parametrize("name", ["geo_b32", "news_b8"])
 def test_other_variants_at_baseline_sizes(name):
     """BASELINE configs[0] (geo, B=32) and the per-GPU shard of configs[2] (news, B=8): one fused train step in bf16 runs,

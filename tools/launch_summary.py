@@ -37,21 +37,33 @@ if "--all" in sys.argv:
                  f"rd {v.get('dram__bytes_read.sum', 0) / 1e6:7.1f} wr {v.get('dram__bytes_write.sum', 0) / 1e6:7.1f} MB")
 
 # --traffic-json PATH: DRAM bytes (read + write) per CALL of each C-ABI entry point, for bench.py's roofline.traffic.
-# A call of ick_mha_bwd is one dQ + one dK/dV launch, ick_wgrad_group_tc one grouped wgrad + one reduce, ...
-FAMILY = {"ick_mha_bwd": ["bwd_dq_pkernel", "bwd_dkv_pkernel", "bwd_dq_kernel", "bwd_dkv_kernel"], "ick_mha_fwd": ["fwd_pkernel", "fwd_kernel"],
-          "ick_gemm_tn_tc": ["gemm_tn_tc_kernel"], "ick_wgrad_group_tc": ["wgrad_group_tc_kernel", "wgrad_group_reduce_kernel"],
-          "ick_wgrad_tc": ["wgrad_tc_kernel", "wgrad_reduce_kernel", "bias_grad_kernel"], "ick_add_ln_fwd": ["add_ln_fwd_fast_kernel", "add_ln_fwd_kernel"],
-          "ick_add_ln_bwd": ["add_ln_bwd_fast_kernel", "add_ln_bwd_kernel"], "ick_adam_step": ["adam_kernel"], "ick_ce_fwd_bwd": ["ce_kernel"],
-          "ick_pointer_bwd": ["pointer_bwd_mma_kernel"], "ick_pointer_fwd": ["pointer_fwd_mma_kernel"]}
+# A call of ick_mha_bwd is one dK/dV launch plus either a recomputing dQ launch or rowdot + dQ-from-dS; a call of
+# ick_wgrad_group_tc one grouped wgrad + one reduce, ...  (counting kernel, kernels of the family, entry points that share them)
+FAMILY = {
+    "ick_mha_bwd": ("bwd_dkv_pkernel", ["bwd_dq_pkernel", "bwd_dkv_pkernel", "bwd_dq_ds_kernel", "rowdot_kernel", "bwd_dq_kernel", "bwd_dkv_kernel"], []),
+    "ick_mha_fwd": ("fwd_pkernel", ["fwd_pkernel", "fwd_kernel"], []),
+    "ick_gemm_tn_tc": ("gemm_tn_tc_kernel", ["gemm_tn_tc_kernel"], ["ick_gemm_tn_tc_dual"]),
+    "ick_wgrad_group_tc": ("wgrad_group_tc_kernel", ["wgrad_group_tc_kernel", "wgrad_group_reduce_kernel"], []),
+    "ick_wgrad_tc": ("wgrad_tc_kernel", ["wgrad_tc_kernel", "wgrad_reduce_kernel", "bias_grad_kernel"], []),
+    "ick_add_ln_fwd": ("add_ln_fwd_fast_kernel", ["add_ln_fwd_fast_kernel", "add_ln_fwd_kernel"], ["ick_add_ln_fwd_dual"]),
+    "ick_add_ln_bwd": ("add_ln_bwd_fast_kernel", ["add_ln_bwd_fast_kernel", "add_ln_bwd_kernel"], ["ick_add_ln_bwd_dual"]),
+    "ick_adam_step": ("adam_kernel", ["adam_kernel"], []),
+    "ick_ce_fwd_bwd": ("ce_kernel", ["ce_kernel"], []),
+    "ick_pointer_bwd": ("pointer_bwd_mma_kernel", ["pointer_bwd_mma_kernel"], []),
+    "ick_pointer_fwd": ("pointer_fwd_mma_kernel", ["pointer_fwd_mma_kernel"], []),
+}
 if "--traffic-json" in sys.argv:
     import json
 
     out = {}
-    for fam, kernels in FAMILY.items():
-        present = [k for k in kernels if k in agg]
-        if not present:
+    for fam, (counter, kernels, aliases) in FAMILY.items():
+        if counter not in agg:
             continue
-        calls = agg[present[0]][1]  # launches of the family's first kernel = calls of the entry point
-        out[fam] = {"dram_bytes_per_call": sum(agg[k][2] + agg[k][3] for k in present) / calls, "calls": calls,
-                    "kernel_us_per_call": sum(agg[k][0] for k in present) / 1e3 / calls}
+        calls = agg[counter][1]
+        present = [k for k in kernels if k in agg]
+        rec = {"dram_bytes_per_call": sum(agg[k][2] + agg[k][3] for k in present) / calls, "calls": calls,
+               "kernel_us_per_call": sum(agg[k][0] for k in present) / 1e3 / calls}
+        out[fam] = rec
+        for a in aliases:
+            out[a] = dict(rec, note=f"same kernels as {fam}: average over both entry points")
     json.dump({"source": sys.argv[1], "per_call": out}, open(sys.argv[sys.argv.index("--traffic-json") + 1], "w"), indent=1)

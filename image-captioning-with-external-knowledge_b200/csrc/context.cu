@@ -286,6 +286,39 @@ __global__ void __launch_bounds__(256) pixels_bwd_kernel(const T* __restrict__ d
     }
 }
 
+// ---- encoder hand-off: AdaptiveAvgPool2d + layout change for the 1x1 convolution --------------------------------------------------
+// Encoder.forward (G/models.py:42-46) pools the ResNet trunk output (B, C, Hin, Win) to (B, C, Hout, Wout) and applies a 1x1
+// convolution, i.e. a GEMM over channels.  This kernel writes the pooled features directly as the K-major A operand of that
+// GEMM: rows[(b*Hout + oy)*Wout + ox][c] = mean of x[b, c, window(oy), window(ox)], window(o) = [floor(o*In/Out),
+// ceil((o+1)*In/Out)) (torch's adaptive pooling).  One CTA per (image, 64 channels): the 64 input planes go through shared
+// memory (coalesced plane reads), each output row segment is 64 contiguous channels.
+constexpr int PR_C = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict__ x, T* __restrict__ rows, int C, int Hin, int Win, int Hout,
+                                                        int Wout, int ldo) {
+    ick_pdl_entry();
+    extern __shared__ float planes[];  // [PR_C][Hin*Win + 1]
+    const int b = blockIdx.y, c0 = blockIdx.x * PR_C;
+    const int npix = Hin * Win, pst = npix + 1;
+    for (int idx = threadIdx.x; idx < PR_C * npix; idx += blockDim.x) {
+        const int c = idx / npix, p = idx % npix;
+        planes[c * pst + p] = c0 + c < C ? x[((size_t)b * C + c0 + c) * npix + p] : 0.f;
+    }
+    __syncthreads();
+    const int nout = Hout * Wout;
+    for (int idx = threadIdx.x; idx < nout * PR_C; idx += blockDim.x) {
+        const int o = idx / PR_C, c = idx % PR_C;
+        if (c0 + c >= C) continue;
+        const int oy = o / Wout, ox = o % Wout;
+        const int y0 = (oy * Hin) / Hout, y1 = ((oy + 1) * Hin + Hout - 1) / Hout;
+        const int x0 = (ox * Win) / Wout, x1 = ((ox + 1) * Win + Wout - 1) / Wout;
+        float acc = 0.f;
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) acc += planes[c * pst + yy * Win + xx];
+        rows[((size_t)b * nout + o) * ldo + c0 + c] = from_f<T>(acc / (float)((y1 - y0) * (x1 - x0)));
+    }
+}
+
 // ---- context indicators ----------------------------------------------------------------------------------------------
 // first_t[b,f]: first caption position holding an entity token (value in [V, V+E)) whose slot is the subject of fact f.
 // tmin[b,f]   : for the representative (lowest-index) fact of each distinct predicate, the earliest first_t over all
@@ -774,4 +807,17 @@ extern "C" int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, c
                                                            w_off, T, S, D, ld, ldds, col0, lag);
     } else ICK_BAD_DT("pointer_bwd", dt);
     return ick_check_launch("pointer_bwd");
+}
+
+extern "C" int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
+                                 cudaStream_t stream) {
+    ICK_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && ldo >= C, "pool_rows_fwd: bad sizes");
+    const size_t smem = (size_t)PR_C * (Hin * Win + 1) * sizeof(float);
+    ICK_REQUIRE(smem <= 48 * 1024, "pool_rows_fwd: input planes of %d x %d do not fit the staging buffer", Hin, Win);
+    if (B == 0) return ICK_OK;
+    dim3 grid((C + PR_C - 1) / PR_C, B);
+    if (dt == ICK_F32) ick_launch(pool_rows_kernel<float>, grid, 256, smem, stream)(x, (float*)rows, C, Hin, Win, Hout, Wout, ldo);
+    else if (dt == ICK_BF16) ick_launch(pool_rows_kernel<bf16>, grid, 256, smem, stream)(x, (bf16*)rows, C, Hin, Win, Hout, Wout, ldo);
+    else ICK_BAD_DT("pool_rows_fwd", dt);
+    return ick_check_launch("pool_rows_fwd");
 }

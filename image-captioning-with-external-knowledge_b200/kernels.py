@@ -281,6 +281,10 @@ class CudaKernels:
     def pixels_bwd(self, dmemory, d_encoder_out, B, D, P, M):
         self._call("ick_pixels_bwd", _p(dmemory), _p(d_encoder_out), dt_of(dmemory), B, D, P, M, _ld(dmemory))
 
+    def pool_rows_fwd(self, x, rows, B, C, Hin, Win, Hout, Wout):
+        self._call("ick_pool_rows_fwd", _p(x), _p(rows), dt_of(rows), B, C, Hin, Win, Hout, Wout, _ld(rows),
+                   work=lambda: (x.numel() * 4 + B * Hout * Wout * C * rows.element_size(), 0))
+
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
     def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E):
         self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E)

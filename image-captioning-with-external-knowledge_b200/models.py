@@ -37,14 +37,19 @@ class Encoder(nn.Module):
     The trunk is stock torchvision/cuDNN (out of scope of the B200 path).
     """
 
-    def __init__(self, encoded_image_size=14, emb_dim=300, encoder_dim=2048):
+    def __init__(self, encoded_image_size=14, emb_dim=300, encoder_dim=2048, pretrained=True, compute_dtype: Optional[torch.dtype] = None):
         super().__init__()
         import torchvision
 
         self.emb_dim = emb_dim
-        try:
-            resnet = torchvision.models.resnet101(pretrained=True)
-        except Exception:  # no network / no cached weights: random init, same architecture
+        self.compute_dtype = compute_dtype  # dtype of the hand-off GEMM (None: ICKB200_DTYPE / bf16)
+        resnet = None
+        if pretrained:  # the reference always asks for the ImageNet weights (G/models.py:24)
+            try:
+                resnet = torchvision.models.resnet101(pretrained=True)
+            except Exception:  # no network / no cached weights: random init, same architecture
+                resnet = None
+        if resnet is None:
             resnet = torchvision.models.resnet101(weights=None)
         self.resnet = nn.Sequential(*list(resnet.children())[:-2])
         self.adaptive_pool = nn.AdaptiveAvgPool2d((encoded_image_size, encoded_image_size))
@@ -52,9 +57,49 @@ class Encoder(nn.Module):
         self.fine_tune()
 
     def forward(self, images):
-        out = self.adaptive_pool(self.resnet(images))
-        out = self.conv1(out)
-        return out.view(out.shape[0], self.emb_dim, -1)
+        return self.head(self.resnet(images))
+
+    def head(self, feats):
+        """
+        Trunk output (B, encoder_dim, h, w) -> (B, emb_dim, 14*14): AdaptiveAvgPool2d + 1x1 conv + view (G/models.py:43-46).
+        On a CUDA device without autograd through ``conv1`` (eval.py, or train.py's frozen encoder under ``torch.no_grad``)
+        this is the B200 hand-off path: one pooling kernel that writes the GEMM's K-major A operand, the 1x1 convolution as a
+        tcgen05 GEMM with the bias in its epilogue, one transpose to the channel-major layout the reference returns.  When
+        ``conv1`` (or the trunk) needs gradients the stock PyTorch ops run, so autograd semantics are unchanged.
+        """
+        needs_grad = torch.is_grad_enabled() and (feats.requires_grad or self.conv1.weight.requires_grad or self.conv1.bias.requires_grad)
+        if not feats.is_cuda or needs_grad:
+            out = self.conv1(self.adaptive_pool(feats))
+            return out.view(out.shape[0], self.emb_dim, -1)
+        from .kernels import CudaKernels
+
+        K = self.__dict__.get("_kernels")
+        if K is None:
+            K = self.__dict__["_kernels"] = CudaKernels()
+        dt = getattr(self, "compute_dtype", None) or _default_dtype()
+        B, C, h, w = feats.shape
+        ho, wo = self.adaptive_pool.output_size
+        P, D = ho * wo, self.emb_dim
+        ldo = (D + 7) // 8 * 8
+        # packed copy of the (frozen) 1x1 convolution, refreshed when the parameter changes
+        ver = (self.conv1.weight._version, self.conv1.weight.data_ptr(), dt)
+        if self.__dict__.get("_wver") != ver:
+            self.__dict__["_wpack"] = self.conv1.weight.detach().view(D, C).to(dt).contiguous()
+            self.__dict__["_bpack"] = self.conv1.bias.detach().float().contiguous()
+            self.__dict__["_wver"] = ver
+        rows = torch.empty(B * P, C, dtype=dt, device=feats.device)
+        K.pool_rows_fwd(feats.detach().float().contiguous(), rows, B, C, h, w, ho, wo)
+        y = torch.zeros(B * P, ldo, dtype=dt, device=feats.device)
+        K.gemm(rows, self.__dict__["_wpack"], y[:, :D], bias=self.__dict__["_bpack"])
+        out = torch.empty(B, D, P, dtype=torch.float32, device=feats.device)
+        K.pixels_bwd(y, out, B, D, P, P)
+        return out
+
+    def __getstate__(self):  # checkpoints pickle whole modules (G/utils.py:32-46): drop the device-side caches
+        d = dict(self.__dict__)
+        for k in ("_kernels", "_wpack", "_bpack", "_wver"):
+            d.pop(k, None)
+        return d
 
     def fine_tune(self, fine_tune=True):
         for p in self.resnet.parameters():

@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 6
+#define ICK_ABI_VERSION 7
 
 #ifdef __cplusplus
 extern "C" {
@@ -133,6 +133,12 @@ int ick_caption_embed_bwd(const void* dX, const long long* captions, const long 
 /* encoder_out (B, D, P) fp32 channel-major -> rows [b*M, b*M+P) of the memory buffer; encoder_out.permute(2,0,1), G/models.py:347 */
 int ick_pixels_fwd(const float* encoder_out, void* memory, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream);
 int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream);
+/* Encoder hand-off: AdaptiveAvgPool2d((Hout, Wout)) of the ResNet trunk output x (B, C, Hin, Win) fp32, written
+ * as rows[(b*Hout + oy)*Wout + ox][c] - the K-major A operand of the 1x1 convolution conv1 (G/models.py:32,43-45), which then
+ * is ick_gemm_tn_* with W = conv1.weight (emb_dim, C); ick_pixels_bwd(M = P) turns the GEMM output into the (B, emb_dim, P)
+ * layout Encoder.forward returns (G/models.py:46). */
+int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
+                      cudaStream_t stream);
 
 /* ---- context indicators + predicate gate: get_context_indicators K/models.py:380-418, fc_predicate K/models.py:436-437 ---- */
 int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F, int V,

@@ -352,6 +352,11 @@ class HostKernels:
         self.calls += 1
         d_encoder_out.copy_(dmemory.view(B, M, -1)[:, :P, :D].float().permute(0, 2, 1))
 
+    def pool_rows_fwd(self, x, rows, B, C, Hin, Win, Hout, Wout):
+        self.calls += 1
+        pooled = torch.nn.functional.adaptive_avg_pool2d(x.float().view(B, C, Hin, Win), (Hout, Wout))
+        rows[:, :C] = pooled.permute(0, 2, 3, 1).reshape(B * Hout * Wout, C).to(rows.dtype)
+
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
     def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E):
         self.calls += 1

@@ -332,6 +332,18 @@ def test_add_ln_dual(K, Hk, dtype, p, mapped):
             assert err(dgg[i], dgr[i]) < 1e-3 and err(dbg[i], dbr[i]) < 1e-3
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,C,Hin,Win,Hout,Wout", [(3, 2048, 8, 8, 14, 14), (2, 100, 7, 7, 14, 14), (1, 64, 10, 6, 4, 5)])
+def test_pool_rows(K, Hk, dtype, B, C, Hin, Win, Hout, Wout):
+    """AdaptiveAvgPool2d written as the K-major rows of the 1x1-convolution GEMM (Encoder hand-off, G/models.py:43-45)."""
+    x = rnd((B, C, Hin, Win), torch.float32, 1)
+    ld = (C + 7) // 8 * 8
+    rr, rg = torch.zeros(B * Hout * Wout, ld, dtype=dtype), torch.zeros(B * Hout * Wout, ld, dtype=dtype).cuda()
+    Hk.pool_rows_fwd(x, rr, B, C, Hin, Win, Hout, Wout)
+    K.pool_rows_fwd(cu(x), rg, B, C, Hin, Win, Hout, Wout)
+    assert err(rg, rr) < TOL[dtype]
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 def make_context(variant, B, E, F, V, seed=0):
     from ickb200 import synthetic as syn

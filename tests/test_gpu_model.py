@@ -204,6 +204,31 @@ def test_trainer_run_pipeline_matches_sequential_steps(use_graph):
     assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("hw", [8, 7])
+def test_encoder_head_matches_torch_ops(dtype, tol, hw):
+    """Encoder hand-off (pool kernel -> 1x1 conv as a GEMM -> channel-major transpose) against AdaptiveAvgPool2d + Conv2d + view
+    of the reference (G/models.py:43-46) on random trunk features; 8x8 is the trunk output for the reference's 256-pixel images."""
+    from ickb200.geo_aware import Encoder
+
+    torch.manual_seed(3)
+    enc = Encoder(pretrained=False, compute_dtype=dtype).cuda().eval()
+    feats = torch.randn(5, 2048, hw, hw, device="cuda")
+    with torch.no_grad():
+        got = enc.head(feats)  # kernels
+        # the same ops in float64 on the host (cuDNN's own fp32 convolution runs in TF32 and is the less exact of the two)
+        pooled = torch.nn.functional.adaptive_avg_pool2d(feats.double().cpu(), (14, 14))
+        ref = torch.nn.functional.conv2d(pooled, enc.conv1.weight.double().cpu(), enc.conv1.bias.double().cpu()).view(5, 300, -1).float()
+        stock = enc.conv1(enc.adaptive_pool(feats)).view(5, 300, -1)
+    assert got.shape == ref.shape == (5, 300, 196) and got.dtype == torch.float32
+    assert nmax_err(got.cpu(), ref) < tol
+    assert nmax_err(stock.cpu(), ref) < 2e-2  # and the stock path agrees with the same reference
+    # with autograd through conv1 the stock ops run and gradients flow as in the reference
+    out = enc.head(feats)
+    out.sum().backward()
+    assert enc.conv1.weight.grad is not None
+
+
 @pytest.mark.parametrize("name", ["geo_b32", "news_b8"])
 def test_other_variants_at_baseline_sizes(name):
     """BASELINE configs[0] (geo, B=32) and the per-GPU shard of configs[2] (news, B=8): one fused train step in bf16 runs,

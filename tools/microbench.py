@@ -78,3 +78,22 @@ for name, (Sq, Sk, causal) in {"entity self": (301, 301, False), "cross": (102, 
         ds = torch.empty(B * H * Sq, device=dev)
         ms = timeit(lambda: K.mha_bwd(q, k, v, o, do, lse, ds, dq, dk, dv, B, H, Sq, Sk, dh, causal, drop))
         print(f"bwd {name:16s} p={p}  {ms*1e3:8.1f} us  {2.5*fl/ms/1e9:7.1f} TFLOP/s")
+
+print("== encoder hand-off (pool 8x8 -> 14x14 rows, 1x1 conv 2048 -> 300 as a GEMM, transpose to (B,300,196))")
+feats = torch.randn(B, 2048, 8, 8, device=dev)
+rows = torch.empty(B * 196, 2048, device=dev, dtype=bf)
+Wc = (torch.randn(300, 2048, device=dev) * 0.02).to(bf)
+bc = torch.randn(300, device=dev)
+y = torch.zeros(B * 196, 304, device=dev, dtype=bf)
+out = torch.empty(B, 300, 196, device=dev)
+t_pool = timeit(lambda: K.pool_rows_fwd(feats, rows, B, 2048, 8, 8, 14, 14))
+t_gemm = timeit(lambda: K.gemm(rows, Wc, y[:, :300], bias=bc))
+t_tr = timeit(lambda: K.pixels_bwd(y, out, B, 300, 196, 196))
+fl = 2 * B * 196 * 2048 * 300
+print(f"pool_rows {t_pool*1e3:6.1f} us ({(feats.numel()*4 + rows.numel()*2)/t_pool/1e6:6.0f} GB/s)   conv1 gemm {t_gemm*1e3:6.1f} us "
+      f"({fl/t_gemm/1e9:6.1f} TFLOP/s)   transpose {t_tr*1e3:6.1f} us   total {(t_pool+t_gemm+t_tr)*1e3:6.1f} us for {B} images")
+conv = torch.nn.Conv2d(2048, 300, 1).to(dev)
+pool = torch.nn.AdaptiveAvgPool2d((14, 14))
+with torch.no_grad():
+    t_ref = timeit(lambda: conv(pool(feats)).view(B, 300, -1))
+print(f"stock PyTorch (AdaptiveAvgPool2d + cuDNN Conv2d, TF32) {t_ref*1e3:6.1f} us")

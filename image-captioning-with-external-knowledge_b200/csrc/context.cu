@@ -297,25 +297,32 @@ template <typename T>
 __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict__ x, T* __restrict__ rows, int C, int Hin, int Win, int Hout,
                                                         int Wout, int ldo) {
     ick_pdl_entry();
-    extern __shared__ float planes[];  // [PR_C][Hin*Win + 1]
+    extern __shared__ float planes[];  // [PR_C][Hin*Win + 1], then the pooling windows of the Hout*Wout outputs
     const int b = blockIdx.y, c0 = blockIdx.x * PR_C;
-    const int npix = Hin * Win, pst = npix + 1;
-    for (int idx = threadIdx.x; idx < PR_C * npix; idx += blockDim.x) {
-        const int c = idx / npix, p = idx % npix;
-        planes[c * pst + p] = c0 + c < C ? x[((size_t)b * C + c0 + c) * npix + p] : 0.f;
-    }
-    __syncthreads();
-    const int nout = Hout * Wout;
-    for (int idx = threadIdx.x; idx < nout * PR_C; idx += blockDim.x) {
-        const int o = idx / PR_C, c = idx % PR_C;
-        if (c0 + c >= C) continue;
+    const int npix = Hin * Win, pst = npix + 1, nout = Hout * Wout;
+    int4* win = reinterpret_cast<int4*>(planes + ((PR_C * pst + 3) & ~3));  // (first pixel, window width, window height, -)
+    float* inv = reinterpret_cast<float*>(win + nout);
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {  // the integer divisions of the window bounds, once per CTA
         const int oy = o / Wout, ox = o % Wout;
         const int y0 = (oy * Hin) / Hout, y1 = ((oy + 1) * Hin + Hout - 1) / Hout;
         const int x0 = (ox * Win) / Wout, x1 = ((ox + 1) * Win + Wout - 1) / Wout;
+        win[o] = make_int4(y0 * Win + x0, x1 - x0, y1 - y0, 0);
+        inv[o] = 1.0f / (float)((y1 - y0) * (x1 - x0));
+    }
+    for (int idx = threadIdx.x; idx < PR_C * npix; idx += blockDim.x) {
+        const int c = idx / npix, p = idx - c * npix;
+        planes[c * pst + p] = c0 + c < C ? x[((size_t)b * C + c0 + c) * npix + p] : 0.f;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % PR_C;
+    if (c0 + c >= C) return;
+    const float* pl = planes + c * pst;
+    for (int o = threadIdx.x / PR_C; o < nout; o += blockDim.x / PR_C) {
+        const int4 w = win[o];
         float acc = 0.f;
-        for (int yy = y0; yy < y1; ++yy)
-            for (int xx = x0; xx < x1; ++xx) acc += planes[c * pst + yy * Win + xx];
-        rows[((size_t)b * nout + o) * ldo + c0 + c] = from_f<T>(acc / (float)((y1 - y0) * (x1 - x0)));
+        for (int yy = 0; yy < w.z; ++yy)
+            for (int xx = 0; xx < w.y; ++xx) acc += pl[w.x + yy * Win + xx];
+        rows[((size_t)b * nout + o) * ldo + c0 + c] = from_f<T>(acc * inv[o]);
     }
 }
 
@@ -812,7 +819,7 @@ extern "C" int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, c
 extern "C" int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
                                  cudaStream_t stream) {
     ICK_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && ldo >= C, "pool_rows_fwd: bad sizes");
-    const size_t smem = (size_t)PR_C * (Hin * Win + 1) * sizeof(float);
+    const size_t smem = (size_t)((PR_C * (Hin * Win + 1) + 3) & ~3) * sizeof(float) + (size_t)Hout * Wout * (sizeof(int4) + sizeof(float));
     ICK_REQUIRE(smem <= 48 * 1024, "pool_rows_fwd: input planes of %d x %d do not fit the staging buffer", Hin, Win);
     if (B == 0) return ICK_OK;
     dim3 grid((C + PR_C - 1) / PR_C, B);

@@ -337,6 +337,29 @@ def run_ours(a):
                            "launches_per_step": dd[1] / nprof})
         roof["others"] = others
 
+    # ---- extra: dynamic padding (Trainer(trim_padding=True)) ------------------------------------------------------------------------
+    # Same batch, same loss and update, but the batch is cut to its longest caption (rounded up to 8 positions) before the step
+    # instead of the dataset-wide T.  NOT the headline: `value` / `e2e` above do the reference's full-width work.
+    trimmed = None
+    if not a.no_trim_extra:
+        try:
+            tr2 = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=tr.use_graph, trim_padding=True)
+            inp2 = tr2.prepare(*args_of(cfg, hb))
+            for _ in range(max(a.warmup, 3) + 1):
+                tr2.step(inp2)
+            ms2 = timed(lambda: tr2.step(inp2), a.steps)
+            la2 = tr2.loss_acc.clone()
+            trimmed = {"value": cfg.B * world * a.steps / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2 / a.steps,
+                       "caption_width": int(inp2.captions.shape[1]), "full_width": cfg.T, "loss": float(la2[0] / la2[1].clamp_min(1)),
+                       "kept_tokens": float(la2[1]),
+                       "note": "batch cut to its longest caption (multiple of 8): same loss and update, positions behind every caption's "
+                               "end contribute exact zeros; reported beside the full-width headline, not instead of it"}
+            tr2._graph = None
+            tr2._graphs = {}
+            del tr2, inp2
+        except Exception as e:
+            trimmed = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- greedy caption generation (BASELINE configs[3]: 5k images over 8 GPUs = 625 images per GPU, no communication) ---------------
     # The reference has no beam search; its eval path is the batch-1 greedy predict() with the repetition
     # clean-up, which predict_batch runs device-resident for the whole shard.  Host inputs, D2H of the tokens, 40 steps.
@@ -395,6 +418,8 @@ def run_ours(a):
             "roofline": roof,
             "cpu_baseline": cpu,
             "greedy_decode": decode,
+            "trimmed_padding": trimmed,
+            "kept_tokens": float(loss_acc[1]),
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),
             "kernel_breakdown": breakdown,
             "lib": lib.path.replace(ROOT + "/", ""),
@@ -403,6 +428,7 @@ def run_ours(a):
     if distributed:
         # drop a captured graph (it holds NCCL work) before tearing the communicator down
         tr._graph = None
+        tr._graphs = {}
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -420,6 +446,7 @@ def main():
                     help="BASELINE.json config; the default (configs[1], knowledge-aware batch 128) is the one the metric is quoted on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode extra")
+    ap.add_argument("--no-trim-extra", action="store_true", help="skip the dynamic-padding extra")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph", action="store_true", help="also capture the step (including the NCCL all-reduce) when N > 1")
     a = ap.parse_args()

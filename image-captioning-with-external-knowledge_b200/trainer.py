@@ -25,7 +25,7 @@ import torch
 
 class Trainer:
     def __init__(self, decoder, lr: float = 4e-4, betas=(0.9, 0.999), eps: float = 1e-8, grad_clip: Optional[float] = 5.0,
-                 process_group=None, distributed: bool = False, use_graph: bool = False):
+                 process_group=None, distributed: bool = False, use_graph: bool = False, trim_padding: bool = False):
         self.decoder = decoder
         self.eng = decoder._ensure_engine()
         n = self.eng.plan.n_params
@@ -51,6 +51,13 @@ class Trainer:
         self.use_graph = use_graph
         self._graph = None
         self._static = None
+        self._graphs = {}  # captured graphs by caption width (trim_padding produces one width per bucket of 8 positions)
+        # Dynamic padding: the reference pads every caption to the dataset maximum (T = max_len + 2, K/create_input_files.py:347)
+        # and lets ignore_index drop the <pad> targets.  Positions behind the longest caption of a BATCH feed nothing into the
+        # loss and, the decoder being causal, nothing into any gradient, so cutting the batch to that width (rounded up to 8)
+        # gives the same loss and the same update.  Off by default: the default step does the reference's full-width work.
+        self.trim_padding = trim_padding
+        self.pad_id = decoder.word_map.get("<pad>", 0) if hasattr(decoder, "word_map") else 0
 
     @property
     def lr(self) -> float:
@@ -61,8 +68,23 @@ class Trainer:
         self._lr *= shrink_factor
         self.lr_dev.fill_(self._lr)
 
+    def trimmed_width(self, captions) -> int:
+        """Width that keeps every non-<pad> token of the batch (multiple of 8, at least 8).  A host tensor costs nothing; a
+        device tensor costs one small D2H sync."""
+        T = captions.shape[1]
+        nonpad = (captions != self.pad_id).any(dim=0)
+        idx = torch.nonzero(nonpad).flatten()
+        last = int(idx[-1]) if idx.numel() else 0
+        return min(T, max(8, (last + 1 + 7) // 8 * 8))
+
     def prepare(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None):
-        """Host->device moves and the sort-by-length of DecoderTransformer.forward (G/models.py:330-335); no host sync."""
+        """Host->device moves and the sort-by-length of DecoderTransformer.forward (G/models.py:330-335); no host sync
+        (unless trim_padding has to look at captions that already live on the device)."""
+        if self.trim_padding:
+            Tw = self.trimmed_width(captions)
+            if Tw < captions.shape[1]:
+                captions, caption_masks = captions[:, :Tw], caption_masks[:, :Tw]
+                caption_lengths = caption_lengths.clamp(max=Tw)
         inp, lengths, _ = self.decoder._sorted_inputs(self.eng.device, captions, encoder_out, caption_masks, caption_lengths, entities, facts)
         inp.decode_len = (lengths - 1).to(torch.int32)
         return inp
@@ -94,9 +116,12 @@ class Trainer:
         if not self.use_graph:
             self._step_impl(inp)
             return self.loss_acc
-        if self._graph is None:
+        key = tuple(inp.captions.shape)
+        if key not in self._graphs:
             self._capture(inp)
+            self._graphs[key] = (self._graph, self._static)
         else:
+            self._graph, self._static = self._graphs[key]
             for k, v in vars(self._static).items():
                 if torch.is_tensor(v):
                     v.copy_(getattr(inp, k), non_blocking=True)

@@ -204,6 +204,35 @@ def test_trainer_run_pipeline_matches_sequential_steps(use_graph):
     assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_trim_padding_gives_the_same_loss_and_update(use_graph):
+    """Dynamic padding: cutting the batch to its longest caption changes neither the loss, the kept-token count nor the update
+    (dropout off: the masks are indexed by row and would differ)."""
+    from ickb200.trainer import Trainer
+
+    cfg = syn.Config("K", B=4, T=40, E=13, F=7, V=57, P=20)
+    batches = [to_dev(cfg, syn.make_batch(cfg, seed=s)) for s in (4, 5, 6)]
+    for b in batches:  # captions of at most 17 tokens in 40 positions, caption_lengths == T as the K/N preprocessing writes them
+        b["captions"][:, 17:] = 0
+        b["caption_masks"][:, 17:] = 0
+    out = []
+    for trim in (False, True):
+        torch.manual_seed(0)
+        dec = build_module(cfg, "cuda", torch.float32, dropouts=(0.0, 0.0, 0.0)).train()
+        tr = Trainer(dec, lr=4e-4, grad_clip=5.0, use_graph=use_graph, trim_padding=trim)
+        losses = []
+        for b in batches:
+            acc = tr.train_step(*batch_args(cfg, b))
+            losses.append((float(acc[0]), float(acc[1])))
+        if trim:
+            assert tr.trimmed_width(batches[0]["captions"]) == 24
+        out.append((losses, tr.m.clone()))
+    (l0, m0), (l1, m1) = out
+    for (a0, n0), (a1, n1) in zip(l0, l1):
+        assert n0 == n1 and abs(a0 - a1) <= 1e-4 * abs(a0)
+    assert float((m0 - m1).abs().max()) <= 2e-2 * float(m0.abs().max())
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("hw", [8, 7])
 def test_encoder_head_matches_torch_ops(dtype, tol, hw):

@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-R=r54
-(timeout 900 python -m pytest tests -m gpu -q --tb=short -x --timeout 600 2>&1 | tail -5) > gpurun_out/${R}_tests.log
-(timeout 600 python bench.py --steps 50 --warmup 3 --no-cpu-baseline 2> gpurun_out/${R}_bench.err | tail -1) > gpurun_out/${R}_bench.json
-tail -n 5 gpurun_out/${R}_tests.log; cut -c1-200 gpurun_out/${R}_bench.json; tail -n 3 gpurun_out/${R}_bench.err; python -c "
-import json; d=json.loads(open('gpurun_out/${R}_bench.json').read()); print(d['trimmed_padding']); print(d['loss'], d['kept_tokens'])"
+R=r56
+(timeout 300 python tools/microbench.py 2>&1 | head -14) > gpurun_out/${R}_micro_old.log
+(ICK_GEMM_DIRECT_SMALL=1 timeout 300 python tools/microbench.py 2>&1 | head -14) > gpurun_out/${R}_micro_new.log
+for i in 1 2; do
+(timeout 600 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-decode --no-trim-extra 2> gpurun_out/${R}_bench_old.err | tail -1) > gpurun_out/${R}_bench_old$i.json
+(ICK_GEMM_DIRECT_SMALL=1 timeout 600 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-decode --no-trim-extra 2> gpurun_out/${R}_bench.err | tail -1) > gpurun_out/${R}_bench$i.json
+done
+paste gpurun_out/${R}_micro_old.log gpurun_out/${R}_micro_new.log | cut -c1-240; for i in 1 2; do cut -c1-160 gpurun_out/${R}_bench_old$i.json;  cut -c1-160 gpurun_out/${R}_bench$i.json; done

@@ -436,32 +436,33 @@ __global__ void __launch_bounds__(128) pred_gate_bwd_kernel(const T* __restrict_
 
 // ---- pointer heads -----------------------------------------------------------------------------------------------------
 // scores[b,t,col0+s] = bias + mask(b,t,s) * sum_d h[b,t,d] * w[d] * ctx[b,s,d];   mask = first_t[b,s] < t + lag (facts only)
-constexpr int PT_T = 16;  // time steps per CTA
-template <typename T>
+constexpr int PT_T = 16;  // time steps per CTA (teacher-forced forward); the single-step decode instantiates PT = 1
+template <typename T, int PT>
 __global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ h, const T* __restrict__ ctx, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const int* __restrict__ first_t,
                                                           float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
                                                           int col0, int lag) {
     ick_pdl_entry();
-    extern __shared__ __align__(16) float hw[];  // [PT_T][Dp]
+    extern __shared__ __align__(16) float hw[];  // [PT][Dp]
     const int Dp = (D + 7) & ~7;
-    const int b = blockIdx.z, tt0 = blockIdx.y * PT_T;
+    const int b = blockIdx.z, tt0 = blockIdx.y * PT;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int idx = threadIdx.x; idx < PT_T * Dp; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < PT * Dp; idx += blockDim.x) {
         const int t = idx / Dp, d = idx % Dp;
         hw[idx] = (tt0 + t < Tn && d < D) ? to_f(h[((size_t)b * Tn + tt0 + t) * ld + d]) * w[d] : 0.f;
     }
     __syncthreads();
     if (s >= S) return;
-    float acc[PT_T];
+    float acc[PT];
 #pragma unroll
-    for (int t = 0; t < PT_T; ++t) acc[t] = 0.f;
+    for (int t = 0; t < PT; ++t) acc[t] = 0.f;
     const T* cr = ctx + ((size_t)b * S + s) * ld;
+#pragma unroll 4
     for (int d = 0; d < Dp; d += 8) {
         float c[8];
         ld8(cr + d, c);  // pad columns of ctx rows are zero and hw is zero there too
 #pragma unroll
-        for (int t = 0; t < PT_T; ++t) {
+        for (int t = 0; t < PT; ++t) {
             const float4 a0 = *reinterpret_cast<const float4*>(&hw[t * Dp + d]);
             const float4 a1 = *reinterpret_cast<const float4*>(&hw[t * Dp + d + 4]);
             acc[t] += a0.x * c[0] + a0.y * c[1] + a0.z * c[2] + a0.w * c[3] + a1.x * c[4] + a1.y * c[5] + a1.z * c[6] + a1.w * c[7];
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ 
     const float bv = bias[0];
     const int ft = first_t ? first_t[(size_t)b * S + s] : -1;
 #pragma unroll
-    for (int t = 0; t < PT_T; ++t) {
+    for (int t = 0; t < PT; ++t) {
         if (tt0 + t >= Tn) break;
         const float m = (ft < t0 + tt0 + t + lag) ? 1.f : 0.f;
         scores[((size_t)b * Tn + tt0 + t) * lds + col0 + s] = acc[t] * m + bv;
@@ -780,14 +781,26 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
         if (rc != ICK_ERR_UNSUPPORTED) return rc;
     }
     const int Dp = (D + 7) & ~7;
+    if (Tn == 1) {  // greedy decode: one time step per image - no 16-step register tile, the ctx rows stream through
+        const size_t smem1 = (size_t)Dp * sizeof(float);
+        dim3 grid1((S + 127) / 128, 1, B);
+        if (dt == ICK_F32)
+            ick_launch(pointer_fwd_kernel<float, 1>, grid1, 128, smem1, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S,
+                                                                          D, ld, ldscores, col0, lag);
+        else if (dt == ICK_BF16)
+            ick_launch(pointer_fwd_kernel<bf16, 1>, grid1, 128, smem1, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
+                                                                         ld, ldscores, col0, lag);
+        else ICK_BAD_DT("pointer_fwd", dt);
+        return ick_check_launch("pointer_fwd");
+    }
     const size_t smem = (size_t)PT_T * Dp * sizeof(float);
     dim3 grid((S + 127) / 128, (Tn + PT_T - 1) / PT_T, B);
     if (dt == ICK_F32)
-        ick_launch(pointer_fwd_kernel<float>, grid, 128, smem, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
-                                                               ldscores, col0, lag);
+        ick_launch(pointer_fwd_kernel<float, PT_T>, grid, 128, smem, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
+                                                                       ld, ldscores, col0, lag);
     else if (dt == ICK_BF16)
-        ick_launch(pointer_fwd_kernel<bf16>, grid, 128, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld,
-                                                              ldscores, col0, lag);
+        ick_launch(pointer_fwd_kernel<bf16, PT_T>, grid, 128, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
+                                                                      ld, ldscores, col0, lag);
     else ICK_BAD_DT("pointer_fwd", dt);
     return ick_check_launch("pointer_fwd");
 }

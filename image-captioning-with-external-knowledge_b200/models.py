@@ -243,6 +243,7 @@ class DecoderTransformer(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engine"] = None  # ctypes handles and device buffers are rebuilt lazily after unpickling (G/utils.py:32-46)
+        st.pop("_decode_graphs", None)
         st["_flat"] = None
         st["_packed_version"] = None
         return st
@@ -337,8 +338,47 @@ class DecoderTransformer(nn.Module):
         inp = NS(encoder_out=encoder_out.detach().to(dev, torch.float32).contiguous(),
                  entities=entities.to(dev, torch.float32).contiguous(),
                  facts=facts.to(dev).contiguous() if facts is not None else None)
+        graphed = (dev.type == "cuda" and not return_margins and type(self)._test_kernel_factory is None
+                   and os.environ.get("ICKB200_DECODE_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing())
         with torch.no_grad():
-            return eng.greedy_decode(inp, max_pred_len, return_margins=return_margins)
+            if not graphed:
+                return eng.greedy_decode(inp, max_pred_len, return_margins=return_margins)
+            return self._graphed_decode(eng, inp, max_pred_len)
+
+    def _graphed_decode(self, eng, inp, max_pred_len):
+        """
+        The whole decode loop (context encoders, memory K/V, max_pred_len x ~40 kernels, all device-resident) as ONE CUDA graph
+        per input shape: launched eagerly from Python the loop is bound by the host (~20 us per launch), replayed it is bound by
+        the GPU.  Weights are read from the packed operand buffers at fixed addresses, so parameter updates are picked up by the
+        usual re-pack; inputs are copied into the graph's static buffers, the tokens are copied out.
+        """
+        cache = self.__dict__.setdefault("_decode_graphs", {})
+        key = (id(eng), max_pred_len, tuple(inp.encoder_out.shape), tuple(inp.entities.shape),
+               tuple(inp.facts.shape) if inp.facts is not None else None)
+        entry = cache.get(key)
+        if entry is None:
+            static = NS(encoder_out=inp.encoder_out.clone(), entities=inp.entities.clone(),
+                        facts=inp.facts.clone() if inp.facts is not None else None)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # eager warm-up: one-time initialisation must not happen during capture
+                eng.greedy_decode(static, max_pred_len)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = eng.greedy_decode(static, max_pred_len)
+            if len(cache) >= 4:  # each graph owns its activation pool: keep a few shapes only
+                cache.pop(next(iter(cache)))
+            entry = cache[key] = (graph, static, out)
+        graph, static, out = entry
+        static.encoder_out.copy_(inp.encoder_out, non_blocking=True)
+        static.entities.copy_(inp.entities, non_blocking=True)
+        if static.facts is not None:
+            static.facts.copy_(inp.facts, non_blocking=True)
+        graph.replay()
+        return out.clone()
 
     def predict(self, encoder_out, max_pred_len, entities, facts=None):
         """G/models.py:363-443: batch-1 greedy decode -> (max_pred_len, 1) int64."""

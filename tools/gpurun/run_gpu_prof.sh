@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-R=r49
-ncu --nvtx --nvtx-include "profile_step/" --set full --clock-control none --import-source on -k regex:"pointer_bwd_mma|pointer_fwd_mma|adam_kernel|ce_kernel" -c 6 -o gpurun_out/${R}_misc -f python tools/step_prof.py 3 > gpurun_out/${R}_ncu2.log 2>&1
-tail -n 2 gpurun_out/${R}_ncu2.log
+R=r58
+ICKB200_DECODE_GRAPH=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 400 -c 200 --csv --log-file gpurun_out/${R}_decode_launches.csv python tools/bench_predict.py --variant K --reps 1 > gpurun_out/${R}_ncu1.log 2>&1
+tail -n 2 gpurun_out/${R}_ncu1.log | cut -c1-200

@@ -203,7 +203,7 @@ def run_ours(a):
     if a.batch:
         cfg = cfg.with_batch(a.batch)
     dec = build_decoder(cfg, dev, dtype)
-    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=(not a.no_graph) and (world == 1 or a.graph))
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=not a.no_graph)
     K = tr.eng.K
     lib = _lib.get()
     hb = host_batch(cfg, seed=rank, pin=True)
@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode extra")
     ap.add_argument("--no-trim-extra", action="store_true", help="skip the dynamic-padding extra")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--graph", action="store_true", help="also capture the step (including the NCCL all-reduce) when N > 1")
+    ap.add_argument("--graph", action="store_true", help="(default since the N = 2 and N = 8 runs of profiles/) capture the step, incl. the NCCL all-reduce")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":

@@ -12,8 +12,9 @@
 namespace {
 
 constexpr int NT = 256;   // threads per CTA (8 warps)
-constexpr int CW = 64;    // slots (fwd) / feature columns (bwd) per CTA
-constexpr int CLD = CW + 8;
+constexpr int CW = 64;    // slots per CTA of the forward kernel
+constexpr int CWB = 32;   // feature columns per CTA of the backward kernel: 103 KB of tiles for the 301-slot head -> two CTAs per SM
+constexpr int CLD = CWB + 8;
 constexpr int SMEM_MAX = 232448;
 
 __device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
@@ -105,21 +106,21 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     extern __shared__ __align__(16) uint8_t smem[];
     const int DLD = Sp + 8;
     bf16* ds = reinterpret_cast<bf16*>(smem);  // [Tp][DLD]  mask * dS of this image
-    bf16* cs = ds + (size_t)Tp * DLD;           // [Sp][CLD]  ctx columns d0..d0+63
-    bf16* hs = cs + (size_t)Sp * CLD;           // [Tp][CLD]  h   columns d0..d0+63
-    float* red = reinterpret_cast<float*>(hs + (size_t)Tp * CLD);  // [8][CW] per-warp dw partials
-    int* ft = reinterpret_cast<int*>(red + 8 * CW);                // [Sp]
-    const int d0 = blockIdx.x * CW, b = blockIdx.y;
+    bf16* cs = ds + (size_t)Tp * DLD;           // [Sp][CLD]  ctx columns d0..d0+CWB-1
+    bf16* hs = cs + (size_t)Sp * CLD;           // [Tp][CLD]  h   columns d0..d0+CWB-1
+    float* red = reinterpret_cast<float*>(hs + (size_t)Tp * CLD);  // [8][CWB] per-warp dw partials
+    int* ft = reinterpret_cast<int*>(red + 8 * CWB);                // [Sp]
+    const int d0 = blockIdx.x * CWB, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     for (int s = threadIdx.x; s < Sp; s += NT) ft[s] = (first_t != nullptr && s < S) ? first_t[(size_t)b * S + s] : -0x40000000;
-    for (int idx = threadIdx.x; idx < Sp * (CW / 8); idx += NT) {
-        const int s = idx / (CW / 8), c = (idx % (CW / 8)) * 8;
+    for (int idx = threadIdx.x; idx < Sp * (CWB / 8); idx += NT) {
+        const int s = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
         uint4 v = zero4();
         if (s < S && d0 + c < ld) v = *reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s) * ld + d0 + c);
         *reinterpret_cast<uint4*>(cs + (size_t)s * CLD + c) = v;
     }
-    for (int idx = threadIdx.x; idx < Tp * (CW / 8); idx += NT) {
-        const int t = idx / (CW / 8), c = (idx % (CW / 8)) * 8;
+    for (int idx = threadIdx.x; idx < Tp * (CWB / 8); idx += NT) {
+        const int t = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
         uint4 v = zero4();
         if (t < T && d0 + c < ld) v = *reinterpret_cast<const uint4*>(h + ((size_t)b * T + t) * ld + d0 + c);
         *reinterpret_cast<uint4*>(hs + (size_t)t * CLD + c) = v;
@@ -179,18 +180,18 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     __syncthreads();
 
     // ---- G = ds * cs  (T x 64), K = slots ---------------------------------------------------------------------------------
-    float dwp[8][2];
+    float dwp[CWB / 8][2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dwp[j][0] = dwp[j][1] = 0.f;
+    for (int j = 0; j < CWB / 8; ++j) dwp[j][0] = dwp[j][1] = 0.f;
     for (int mt = warp; mt < Tp / 16; mt += NT / 32) {
-        float acc[8][4];
+        float acc[CWB / 8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int j = 0; j < CWB / 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
         for (int k0 = 0; k0 < Sp; k0 += 16) {
             uint32_t a[4];
             a_frag(a, ds, DLD, 16 * mt, k0, lane);
 #pragma unroll
-            for (int np = 0; np < 4; ++np) {
+            for (int np = 0; np < CWB / 16; ++np) {
                 uint32_t r[4];
                 b_frag_kn(r, cs, CLD, 16 * np, k0, lane);
                 ick_mma16816(acc[2 * np], a, r[0], r[1]);
@@ -199,9 +200,9 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
         }
         // dH += w * G as a read-modify-write: ALL sixteen old values of the lane are requested before the first store (a load
         // placed after a store through the same base pointer cannot be hoisted by the compiler, which serialised 16 round trips)
-        __nv_bfloat162 oldv[8][2];
+        __nv_bfloat162 oldv[CWB / 8][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < CWB / 8; ++j)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int d = d0 + 8 * j + 2 * tq, t = 16 * mt + g + 8 * hh;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
                                                : __floats2bfloat162_rn(0.f, 0.f);
             }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CWB / 8; ++j) {
             const int c = 8 * j + 2 * tq, d = d0 + c;
             if (d >= D) continue;  // D is even (d-model 300): a column pair is inside or outside together
             const float w0 = __ldg(w + d), w1 = d + 1 < D ? __ldg(w + d + 1) : 0.f;
@@ -228,49 +229,49 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     }
     // dw: reduce the per-thread partials over the 8 row groups of the warp, then over warps through shared memory
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < CWB / 8; ++j)
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
             float v = dwp[j][x];
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (g == 0) red[warp * CW + 8 * j + 2 * tq + x] = v;
+            if (g == 0) red[warp * CWB + 8 * j + 2 * tq + x] = v;
         }
     __syncthreads();
-    if (threadIdx.x < CW && d0 + threadIdx.x < D) {
+    if (threadIdx.x < CWB && d0 + threadIdx.x < D) {
         float v = 0.f;
 #pragma unroll
-        for (int wi = 0; wi < NT / 32; ++wi) v += red[wi * CW + threadIdx.x];
+        for (int wi = 0; wi < NT / 32; ++wi) v += red[wi * CWB + threadIdx.x];
         atomicAdd(gflat + w_off + d0 + threadIdx.x, v);
     }
 
     // ---- C2 = ds^T * hs  (S x 64), K = time steps ------------------------------------------------------------------------
     for (int mt = warp; mt < Sp / 16; mt += NT / 32) {
-        float acc[8][4];
+        float acc[CWB / 8][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int j = 0; j < CWB / 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
         for (int k0 = 0; k0 < Tp; k0 += 16) {
             uint32_t a[4];
             a_frag_t(a, ds, DLD, 16 * mt, k0, lane);
 #pragma unroll
-            for (int np = 0; np < 4; ++np) {
+            for (int np = 0; np < CWB / 16; ++np) {
                 uint32_t r[4];
                 b_frag_kn(r, hs, CLD, 16 * np, k0, lane);
                 ick_mma16816(acc[2 * np], a, r[0], r[1]);
                 ick_mma16816(acc[2 * np + 1], a, r[2], r[3]);
             }
         }
-        float2 oldc[8][2];  // same batching of the read-modify-write of dCtx
+        float2 oldc[CWB / 8][2];  // same batching of the read-modify-write of dCtx
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < CWB / 8; ++j)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int d = d0 + 8 * j + 2 * tq, s = 16 * mt + g + 8 * hh;
                 oldc[j][hh] = (d < D && s < S) ? *reinterpret_cast<const float2*>(dCtx + ((size_t)b * S + s) * ld + d) : make_float2(0.f, 0.f);
             }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CWB / 8; ++j) {
             const int d = d0 + 8 * j + 2 * tq;
             if (d >= D) continue;
             const float w0 = __ldg(w + d), w1 = d + 1 < D ? __ldg(w + d + 1) : 0.f;
@@ -316,12 +317,12 @@ int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const fl
 int ick_pointer_bwd_mma(const void* dS, const void* h, const void* ctx, const float* w, const int* first_t, float* dCtx, void* dH, float* gflat,
                         int w_off, int bias_off, int B, int T, int S, int D, int ld, int ldds, int col0, int lag, cudaStream_t stream) {
     const int Tp = (T + 15) / 16 * 16, Sp = (S + 15) / 16 * 16;
-    const size_t smem = ((size_t)Tp * (Sp + 8) + (size_t)(Sp + Tp) * CLD) * 2 + 8 * CW * 4 + (size_t)Sp * 4;
+    const size_t smem = ((size_t)Tp * (Sp + 8) + (size_t)(Sp + Tp) * CLD) * 2 + 8 * CWB * 4 + (size_t)Sp * 4;
     if (ld % 8 != 0 || (D & 1) != 0 || smem > SMEM_MAX || (((uintptr_t)h | (uintptr_t)ctx | (uintptr_t)dCtx) & 15) != 0 || ((uintptr_t)dH & 3) != 0)
         return ICK_ERR_UNSUPPORTED;
     int rc = set_smem(pointer_bwd_mma_kernel);
     if (rc) return rc;
-    dim3 grid((D + CW - 1) / CW, B);
+    dim3 grid((D + CWB - 1) / CWB, B);
     ick_launch(pointer_bwd_mma_kernel, grid, NT, smem, stream)((const bf16*)dS, (const bf16*)h, (const bf16*)ctx, w, first_t, dCtx, (bf16*)dH, gflat, w_off,
                                                        bias_off, T, S, D, ld, ldds, col0, lag, Tp, Sp);
     return ick_check_launch("pointer_bwd_mma");

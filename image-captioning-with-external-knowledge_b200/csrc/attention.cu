@@ -334,6 +334,73 @@ __global__ void __launch_bounds__(128) mha_decode_kernel(const T* __restrict__ Q
     }
 }
 
+// bf16 decode attention over a cache whose K and V blocks are adjacent (K columns [0, H*32), V columns [H*32, 2*H*32) of the
+// same row - both the per-layer memory K/V projection and the self-attention q|k|v cache are laid out like that).  One CTA per
+// image; a thread owns (key group, head, quarter of the head): 40 consecutive threads read the contiguous 640-byte K block and
+// the 640-byte V block of one cached position with 16-byte loads, eight positions per iteration.  The warp-per-(image, head)
+// kernel above reads 64-byte rows 3840 bytes apart, which is what limits it to ~3 TB/s.
+constexpr int DR_KG = 8;  // cached positions per iteration
+__global__ void __launch_bounds__(DR_KG * 40) mha_decode_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ KV, bf16* __restrict__ O,
+                                                                     int H, int dh, int ldq, int ldkv, int ldo, long long batch_stride,
+                                                                     int klen, float scale_log2) {
+    ick_pdl_entry();
+    extern __shared__ float dr_red[];  // [DR_KG][H*4][10]: m, l, acc[8] of every (key group, head, quarter)
+    const int slots = H * 4;           // threads per cached position
+    const int kg = threadIdx.x / slots, sl = threadIdx.x % slots, h = sl >> 2, qd = sl & 3;
+    const int b = blockIdx.x;
+    float q[8];
+    ld8(Q + (size_t)b * ldq + h * HD + qd * 8, q);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) q[c] = (qd * 8 + c < dh) ? q[c] * scale_log2 : 0.f;  // pad lanes never contribute
+    const bf16* base = KV + (size_t)b * batch_stride + h * HD + qd * 8;
+    const int voff = H * HD;
+    const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll 2
+    for (int j = kg; j < klen; j += DR_KG) {
+        float kx[8], vx[8];
+        ld8(base + (size_t)j * ldkv, kx);
+        ld8(base + (size_t)j * ldkv + voff, vx);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s = fmaf(q[c], kx[c], s);
+        s += __shfl_xor_sync(qmask, s, 1);  // the four quarter threads of a (position, head) iterate together; other lanes of the
+        s += __shfl_xor_sync(qmask, s, 2);  // warp may belong to another key group with a different trip count
+        const float mnew = fmaxf(m, s);
+        const float corr = exp2f(m - mnew);
+        const float p = exp2f(s - mnew);
+        l = l * corr + p;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(p, vx[c], acc[c] * corr);
+        m = mnew;
+    }
+    float* mine = dr_red + ((size_t)kg * slots + sl) * 10;
+    mine[0] = m;
+    mine[1] = l;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mine[2 + c] = acc[c];
+    __syncthreads();
+    if (kg != 0) return;
+    float mall = m;
+    for (int g = 1; g < DR_KG; ++g) mall = fmaxf(mall, dr_red[((size_t)g * slots + sl) * 10]);
+    float lsum = 0.f, out[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] = 0.f;
+    for (int g = 0; g < DR_KG; ++g) {
+        const float* r = dr_red + ((size_t)g * slots + sl) * 10;
+        const float f = r[0] == -INFINITY ? 0.f : exp2f(r[0] - mall);
+        lsum = fmaf(r[1], f, lsum);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = fmaf(r[2 + c], f, out[c]);
+    }
+    const float inv = 1.f / lsum;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] = (qd * 8 + c < dh) ? out[c] * inv : 0.f;
+    st8(O + (size_t)b * ldo + h * HD + qd * 8, out);
+}
+
 // bf16 runs on the tensor-core kernels (attention_mma.cu); ICKB200_ATTN_SIMT=1 forces the CUDA-core kernels (A/B testing)
 bool use_mma() {
     static int v = -1;
@@ -342,6 +409,15 @@ bool use_mma() {
         v = (e && e[0] == '1') ? 0 : 1;
     }
     return v == 1;
+}
+
+bool decode_rows() {  // ICK_DECODE_ROWS=0: always the warp-per-(image, head) decode kernel (A/B aid)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_DECODE_ROWS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 int check_dims(const char* what, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo) {
@@ -423,6 +499,13 @@ extern "C" int ick_mha_decode(const void* Q, const void* K, const void* V, void*
     ICK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && kbatch_stride % 8 == 0 && vbatch_stride % 8 == 0,
                 "mha_decode: strides must be multiples of 8");
     const float sl2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+    if (dt == ICK_BF16 && (const bf16*)V == (const bf16*)K + H * HD && ldk == ldv && kbatch_stride == vbatch_stride && H <= 10 &&
+        ((((uintptr_t)K) | ((uintptr_t)Q) | ((uintptr_t)O)) & 15) == 0 && decode_rows()) {
+        const size_t smem = (size_t)DR_KG * H * 4 * 10 * sizeof(float);
+        ick_launch(mha_decode_rows_kernel, B, DR_KG * H * 4, smem, stream)((const bf16*)Q, (const bf16*)K, (bf16*)O, H, dh, ldq, ldk, ldo, kbatch_stride,
+                                                                        klen, sl2);
+        return ick_check_launch("mha_decode(rows)");
+    }
     const int warps = B * H;
     dim3 grid((warps * 32 + 127) / 128);
     if (dt == ICK_F32)

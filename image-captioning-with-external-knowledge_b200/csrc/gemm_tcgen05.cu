@@ -976,10 +976,22 @@ int pick_bn(int N) {
 struct Plan {
     int wstat, BN, stages;
 };
-Plan plan_tiles(int N, int nkb, int avail, bool allow_wstat) {
+int num_sms();
+Plan plan_tiles(int N, int nkb, int avail, bool allow_wstat, int m_tiles) {
     Plan best;
     best.wstat = 0;
     best.BN = pick_bn(N);
+    // Few row tiles (single-step decode: M = images; small batches): the launch is one tile per CTA and bound by the latency of
+    // that tile - its operand load and, above all, its epilogue (BN / 64 serial 32-column chunks per warp).  Spread the columns
+    // over the idle SMs instead: the narrowest tile (>= 32) that still fits all tiles in one wave.
+    if (m_tiles * ((N + best.BN - 1) / best.BN) * 2 <= num_sms()) {
+        for (int bn = 32; bn < best.BN; bn += 32) {
+            if (m_tiles * ((N + bn - 1) / bn) <= num_sms()) {
+                best.BN = bn;
+                break;
+            }
+        }
+    }
     best.stages = avail / (A_STAGE + best.BN * BK * 2);
     if (best.stages > MAX_STAGES) best.stages = MAX_STAGES;
     const auto padded = [&](int bn) { return (N + bn - 1) / bn * bn; };
@@ -1060,7 +1072,7 @@ static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C
     const int es = c_dt == ICK_F32 ? 4 : 2;
     p.tma_store = ((((uintptr_t)C) & 15) == 0 && ((size_t)ldc * es) % 16 == 0) ? 1 : 0;
     const int staging = p.tma_store ? NEPI * NSBOX * (c_dt == ICK_F32 ? 4096 : 2048) : 0;
-    const Plan pl = plan_tiles(N, p.nkb, SMEM_DATA - staging, use_wstat() && W2 == nullptr);
+    const Plan pl = plan_tiles(N, p.nkb, SMEM_DATA - staging, use_wstat() && W2 == nullptr, p.m_tiles);
     p.split_tile = W2 != nullptr ? M_split / BM : 0x7FFFFFFF;
     p.bias2 = W2 != nullptr ? bias2 : bias;
     p.site2 = site2;

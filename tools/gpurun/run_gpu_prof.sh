@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-R=r58
+R=r67
 ICKB200_DECODE_GRAPH=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 400 -c 200 --csv --log-file gpurun_out/${R}_decode_launches.csv python tools/bench_predict.py --variant K --reps 1 > gpurun_out/${R}_ncu1.log 2>&1
-tail -n 2 gpurun_out/${R}_ncu1.log | cut -c1-200
+tail -n 1 gpurun_out/${R}_ncu1.log | cut -c1-120

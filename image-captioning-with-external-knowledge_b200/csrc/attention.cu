@@ -401,6 +401,131 @@ __global__ void __launch_bounds__(DR_KG * 40) mha_decode_rows_kernel(const bf16*
     st8(O + (size_t)b * ldo + h * HD + qd * 8, out);
 }
 
+// Beam-search decode attention (extension: the reference decodes greedily): the G beams of an image are
+// consecutive query rows.  Same thread layout as mha_decode_rows_kernel - a thread owns (key group, head, quarter of the
+// head) - but every cached K / V row that is loaded serves all G queries of the CTA.
+//   anc == nullptr (cross-attention): one CTA per image, G = beams per image; the beams share the image's memory K/V, which
+//     is therefore streamed once per image instead of once per beam.
+//   anc != nullptr (self-attention): one CTA per beam row r (G = 1).  The cache is position-major, row (j, r') of it holds
+//     the K/V that beam slot r' produced at step j, and anc[r*anc_ld + j] names the slot of row r's ancestor at step j:
+//     re-ordering the beams only rewrites the small ancestor table, the cached rows never move.
+template <typename T, int G>
+__global__ void __launch_bounds__(DR_KG * 40) mha_decode_beam_kernel(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict__ V,
+                                                                     T* __restrict__ O, int H, int dh, int ldq, int ldk, int ldv, int ldo,
+                                                                     long long kimg_stride, long long vimg_stride, int klen, float scale_log2,
+                                                                     const int* __restrict__ anc, int anc_ld, int group,
+                                                                     long long kpos_stride, long long vpos_stride) {
+    ick_pdl_entry();
+    extern __shared__ float dr_red[];  // [DR_KG][H*4][10]: m, l, acc[8] of every (key group, head, quarter), one query at a time
+    const int slots = H * 4;
+    const int kg = threadIdx.x / slots, sl = threadIdx.x % slots, h = sl >> 2, qd = sl & 3;
+    const int r0 = blockIdx.x * G;  // first query row of this CTA
+    const int col = h * HD + qd * 8;
+    float q[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        ld8(Q + (size_t)(r0 + g) * ldq + col, q[g]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[g][c] = (qd * 8 + c < dh) ? q[g][c] * scale_log2 : 0.f;
+    }
+    const int img = anc ? r0 / group : blockIdx.x;
+    const T* kbase = K + (anc ? (size_t)img * group * ldk : (size_t)img * kimg_stride) + col;
+    const T* vbase = V + (anc ? (size_t)img * group * ldv : (size_t)img * vimg_stride) + col;
+    const int* arow = anc ? anc + (size_t)r0 * anc_ld : nullptr;
+    const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+    float m[G], l[G], acc[G][8];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        m[g] = -INFINITY;
+        l[g] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[g][c] = 0.f;
+    }
+    for (int j = kg; j < klen; j += DR_KG) {
+        float kx[8], vx[8];
+        if (anc) {
+            const int slot = arow[j];
+            ld8(kbase + (size_t)j * kpos_stride + (size_t)slot * ldk, kx);
+            ld8(vbase + (size_t)j * vpos_stride + (size_t)slot * ldv, vx);
+        } else {
+            ld8(kbase + (size_t)j * ldk, kx);
+            ld8(vbase + (size_t)j * ldv, vx);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s = fmaf(q[g][c], kx[c], s);
+            s += __shfl_xor_sync(qmask, s, 1);
+            s += __shfl_xor_sync(qmask, s, 2);
+            const float mnew = fmaxf(m[g], s);
+            const float corr = exp2f(m[g] - mnew);
+            const float p = exp2f(s - mnew);
+            l[g] = l[g] * corr + p;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[g][c] = fmaf(p, vx[c], acc[g][c] * corr);
+            m[g] = mnew;
+        }
+    }
+    float* mine = dr_red + ((size_t)kg * slots + sl) * 10;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g) __syncthreads();
+        mine[0] = m[g];
+        mine[1] = l[g];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mine[2 + c] = acc[g][c];
+        __syncthreads();
+        if (kg == 0) {
+            float mall = m[g];
+            for (int k2 = 1; k2 < DR_KG; ++k2) mall = fmaxf(mall, dr_red[((size_t)k2 * slots + sl) * 10]);
+            float lsum = 0.f, out[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) out[c] = 0.f;
+            for (int k2 = 0; k2 < DR_KG; ++k2) {
+                const float* r = dr_red + ((size_t)k2 * slots + sl) * 10;
+                const float f = r[0] == -INFINITY ? 0.f : exp2f(r[0] - mall);
+                lsum = fmaf(r[1], f, lsum);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) out[c] = fmaf(r[2 + c], f, out[c]);
+            }
+            const float inv = 1.f / lsum;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) out[c] = (qd * 8 + c < dh) ? out[c] * inv : 0.f;
+            st8(O + (size_t)(r0 + g) * ldo + col, out);
+        }
+    }
+}
+
+template <typename T>
+int launch_decode_beam(const T* Q, const T* K, const T* V, T* O, int rows, int group, int H, int dh, int ldq, int ldk, int ldv, int ldo,
+                       long long kimg_stride, long long vimg_stride, int klen, const int* anc, int anc_ld, long long kpos_stride,
+                       long long vpos_stride, cudaStream_t stream) {
+    const float sl2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+    const size_t smem = (size_t)DR_KG * H * 4 * 10 * sizeof(float);
+    const int nt = DR_KG * H * 4;
+#define ICK_BEAM_CASE(GG)                                                                                                              \
+    case GG:                                                                                                                           \
+        ick_launch(mha_decode_beam_kernel<T, GG>, rows / GG, nt, smem, stream)(Q, K, V, O, H, dh, ldq, ldk, ldv, ldo, kimg_stride, vimg_stride, \
+                                                                                klen, sl2, anc, anc_ld, group, kpos_stride, vpos_stride);  \
+        break;
+    switch (anc ? 1 : group) {
+        ICK_BEAM_CASE(1)
+        ICK_BEAM_CASE(2)
+        ICK_BEAM_CASE(3)
+        ICK_BEAM_CASE(4)
+        ICK_BEAM_CASE(5)
+        ICK_BEAM_CASE(6)
+        ICK_BEAM_CASE(7)
+        ICK_BEAM_CASE(8)
+        default:
+            ick_set_error("mha_decode_beam: group %d not in [1, 8]", group);
+            return ICK_ERR_UNSUPPORTED;
+    }
+#undef ICK_BEAM_CASE
+    return ick_check_launch("mha_decode_beam");
+}
+
 // bf16 runs on the tensor-core kernels (attention_mma.cu); ICKB200_ATTN_SIMT=1 forces the CUDA-core kernels (A/B testing)
 bool use_mma() {
     static int v = -1;
@@ -519,4 +644,25 @@ extern "C" int ick_mha_decode(const void* Q, const void* K, const void* V, void*
         return ICK_ERR_UNSUPPORTED;
     }
     return ick_check_launch("mha_decode");
+}
+
+extern "C" int ick_mha_decode_beam(const void* Q, const void* K, const void* V, void* O, int dt, int rows, int group, int H, int dh,
+                                   int ldq, int ldk, int ldv, int ldo, long long kimg_stride, long long vimg_stride, int klen,
+                                   const int* anc, int anc_ld, long long kpos_stride, long long vpos_stride, cudaStream_t stream) {
+    ICK_REQUIRE(rows > 0 && group >= 1 && group <= 8 && rows % group == 0, "mha_decode_beam: rows=%d group=%d", rows, group);
+    ICK_REQUIRE(H > 0 && H <= 10 && klen > 0 && dh > 0 && dh <= HD, "mha_decode_beam: bad sizes H=%d klen=%d dh=%d", H, klen, dh);
+    ICK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && kimg_stride % 8 == 0 && vimg_stride % 8 == 0 &&
+                    kpos_stride % 8 == 0 && vpos_stride % 8 == 0,
+                "mha_decode_beam: strides must be multiples of 8");
+    ICK_REQUIRE(anc == nullptr || anc_ld >= klen, "mha_decode_beam: ancestor table narrower than klen");
+    const uintptr_t al = dt == ICK_F32 ? 31 : 15;
+    ICK_REQUIRE(((((uintptr_t)Q) | ((uintptr_t)K) | ((uintptr_t)V) | ((uintptr_t)O)) & al) == 0, "mha_decode_beam: misaligned operand");
+    if (dt == ICK_F32)
+        return launch_decode_beam((const float*)Q, (const float*)K, (const float*)V, (float*)O, rows, group, H, dh, ldq, ldk, ldv, ldo,
+                                  kimg_stride, vimg_stride, klen, anc, anc_ld, kpos_stride, vpos_stride, stream);
+    if (dt == ICK_BF16)
+        return launch_decode_beam((const bf16*)Q, (const bf16*)K, (const bf16*)V, (bf16*)O, rows, group, H, dh, ldq, ldk, ldv, ldo,
+                                  kimg_stride, vimg_stride, klen, anc, anc_ld, kpos_stride, vpos_stride, stream);
+    ick_set_error("mha_decode_beam: bad dtype %d", dt);
+    return ICK_ERR_UNSUPPORTED;
 }

@@ -192,17 +192,19 @@ __global__ void __launch_bounds__(256) caption_embed_fwd_kernel(const long long*
                                                                 const T* __restrict__ wemb, const T* __restrict__ entenc,
                                                                 const T* __restrict__ factenc, const float* __restrict__ pe,
                                                                 T* __restrict__ out, int B, int Tstride, int t0, int Tn, int V, int E,
-                                                                int F, int D, int ld, int ldw, int pad, float scale, DropCfg drop) {
+                                                                int F, int D, int ld, int ldw, int pad, float scale, int group,
+                                                                DropCfg drop) {
     ick_pdl_entry();
     ick_resolve_seed(drop);
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= B * Tn) return;
     const int b = row / Tn, t = t0 + row % Tn;
+    const int bc = b / group;  // `group` consecutive caption rows (the beams of one image) share one entity / fact context
     const TokSel s = select_token(caps[(size_t)b * Tstride + t], masks[(size_t)b * Tstride + t], V, E, F, pad);
     const T* src = s.kind == 0 ? wemb + (size_t)s.idx * ldw
-                 : s.kind == 1 ? entenc + ((size_t)b * E + s.idx) * ld
-                               : factenc + ((size_t)b * F + s.idx) * ld;
+                 : s.kind == 1 ? entenc + ((size_t)bc * E + s.idx) * ld
+                               : factenc + ((size_t)bc * F + s.idx) * ld;
     const float* per = pe + (size_t)t * D;
     T* o = out + (size_t)row * ld;
     const uint32_t rmix = ick_rowmix(drop.seed, drop.site, (uint64_t)row);
@@ -332,14 +334,14 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
 //               facts sharing that predicate; FIRST_NONE for the others (the predicate indicator is a SET of predicates).
 __global__ void __launch_bounds__(256) fact_first_mention_kernel(const long long* __restrict__ caps, const long long* __restrict__ facts,
                                                                  int* __restrict__ first_t, int* __restrict__ tmin, int T_, int F,
-                                                                 int V, int E) {
+                                                                 int V, int E, int group) {
     ick_pdl_entry();
     extern __shared__ int sm[];
     int* sfirst = sm;
     int* spred = sm + F;
     const int b = blockIdx.x;
     const long long* cb = caps + (size_t)b * T_;
-    const long long* fb = facts + (size_t)b * F * 3;
+    const long long* fb = facts + (size_t)(b / group) * F * 3;  // the `group` beams of an image share its fact list
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const long long subj = fb[3 * f + 1];
         int first = FIRST_NONE;
@@ -371,7 +373,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) pred_gate_fwd_kernel(const int* __restrict__ tmin, const long long* __restrict__ facts,
                                                             const float* __restrict__ WpT, const float* __restrict__ bias,
                                                             const T* __restrict__ h, T* __restrict__ gate, T* __restrict__ hg, int Tn,
-                                                            int t0, int F, int D, int ld, int ldp, int NP, int lag) {
+                                                            int t0, int F, int D, int ld, int ldp, int NP, int lag, int group) {
     ick_pdl_entry();
     extern __shared__ int sact[];  // predicate ids of the active facts
     __shared__ int nact;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(128) pred_gate_fwd_kernel(const int* __restric
     __syncthreads();
     for (int f = threadIdx.x; f < F; f += blockDim.x)
         if (tmin[(size_t)b * F + f] < t + lag) {
-            const int p = min(max((int)facts[((size_t)b * F + f) * 3 + 2], 0), NP - 1);
+            const int p = min(max((int)facts[((size_t)(b / group) * F + f) * 3 + 2], 0), NP - 1);
             sact[atomicAdd(&nact, 1)] = p;
         }
     __syncthreads();
@@ -441,7 +443,9 @@ template <typename T, int PT>
 __global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ h, const T* __restrict__ ctx, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const int* __restrict__ first_t,
                                                           float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
-                                                          int col0, int lag) {
+                                                          int col0, int lag, int beams) {
+    // beams != 0: the Tn rows of "image" b are the beams of one image at the SAME time step t0 - they share the ctx rows,
+    // each has its own first_t row (its own caption history) and time does not advance along the rows.
     ick_pdl_entry();
     extern __shared__ __align__(16) float hw[];  // [PT][Dp]
     const int Dp = (D + 7) & ~7;
@@ -469,11 +473,13 @@ __global__ void __launch_bounds__(128) pointer_fwd_kernel(const T* __restrict__ 
         }
     }
     const float bv = bias[0];
-    const int ft = first_t ? first_t[(size_t)b * S + s] : -1;
+    const int ft = (first_t && !beams) ? first_t[(size_t)b * S + s] : -1;
 #pragma unroll
     for (int t = 0; t < PT; ++t) {
         if (tt0 + t >= Tn) break;
-        const float m = (ft < t0 + tt0 + t + lag) ? 1.f : 0.f;
+        float m;
+        if (beams) m = (!first_t || first_t[((size_t)b * Tn + tt0 + t) * S + s] < t0 + lag) ? 1.f : 0.f;
+        else m = (ft < t0 + tt0 + t + lag) ? 1.f : 0.f;
         scores[((size_t)b * Tn + tt0 + t) * lds + col0 + s] = acc[t] * m + bv;
     }
 }
@@ -666,9 +672,10 @@ extern "C" int ick_fact_encode_bwd(const float* dFact, const long long* facts, f
 
 extern "C" int ick_caption_embed_fwd(const long long* captions, const long long* masks, const void* word_emb, const void* ent_enc,
                                      const void* fact_enc, const float* pe, void* out, int dt, int B, int Tstride, int t0, int Tn, int V,
-                                     int E, int F, int D, int ld, int ldw, int pad, float scale, float drop_p, unsigned seed,
-                                     unsigned site, cudaStream_t stream) {
+                                     int E, int F, int D, int ld, int ldw, int pad, float scale, int group, float drop_p,
+                                     unsigned seed, unsigned site, cudaStream_t stream) {
     ICK_REQUIRE(t0 >= 0 && t0 + Tn <= Tstride && D <= ld, "caption_embed_fwd: bad sizes");
+    ICK_REQUIRE(group >= 1 && B % group == 0, "caption_embed_fwd: B=%d is not a multiple of group=%d", B, group);
     ICK_REQUIRE(F == 0 || fact_enc != nullptr, "caption_embed_fwd: facts expected");
     if (B * Tn == 0) return ICK_OK;
     DropCfg dc = make_drop(drop_p, seed, site);
@@ -676,11 +683,11 @@ extern "C" int ick_caption_embed_fwd(const long long* captions, const long long*
     if (dt == ICK_F32)
         ick_launch(caption_embed_fwd_kernel<float>, grid, 256, 0, stream)(captions, masks, (const float*)word_emb, (const float*)ent_enc,
                                                                    (const float*)fact_enc, pe, (float*)out, B, Tstride, t0, Tn, V, E, F, D,
-                                                                   ld, ldw, pad, scale, dc);
+                                                                   ld, ldw, pad, scale, group, dc);
     else if (dt == ICK_BF16)
         ick_launch(caption_embed_fwd_kernel<bf16>, grid, 256, 0, stream)(captions, masks, (const bf16*)word_emb, (const bf16*)ent_enc,
                                                                   (const bf16*)fact_enc, pe, (bf16*)out, B, Tstride, t0, Tn, V, E, F, D, ld,
-                                                                  ldw, pad, scale, dc);
+                                                                  ldw, pad, scale, group, dc);
     else ICK_BAD_DT("caption_embed_fwd", dt);
     return ick_check_launch("caption_embed_fwd");
 }
@@ -724,26 +731,28 @@ extern "C" int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt,
 }
 
 extern "C" int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F,
-                                      int V, int E, cudaStream_t stream) {
+                                      int V, int E, int group, cudaStream_t stream) {
     ICK_REQUIRE(F > 0 && F <= 4096, "fact_first_mention: F=%d out of range", F);
+    ICK_REQUIRE(group >= 1 && B % group == 0, "fact_first_mention: B=%d is not a multiple of group=%d", B, group);
     if (B == 0) return ICK_OK;
-    ick_launch(fact_first_mention_kernel, B, 256, 2 * F * sizeof(int), stream)(captions, facts, first_t, tmin, T, F, V, E);
+    ick_launch(fact_first_mention_kernel, B, 256, 2 * F * sizeof(int), stream)(captions, facts, first_t, tmin, T, F, V, E, group);
     return ick_check_launch("fact_first_mention");
 }
 
 extern "C" int ick_pred_gate_fwd(const int* tmin, const long long* facts, const float* WpT, const float* bias, const void* h, void* gate,
-                                 void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag,
+                                 void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag, int group,
                                  cudaStream_t stream) {
     ICK_REQUIRE(F > 0 && F <= 4096 && D <= ld && D <= ldp, "pred_gate_fwd: bad sizes");
+    ICK_REQUIRE(group >= 1 && B % group == 0, "pred_gate_fwd: B=%d is not a multiple of group=%d", B, group);
     ICK_REQUIRE(hg == nullptr || h != nullptr, "pred_gate_fwd: hg needs h");
     if (B * Tn == 0) return ICK_OK;
     dim3 grid(Tn, B);
     if (dt == ICK_F32)
         ick_launch(pred_gate_fwd_kernel<float>, grid, 128, F * sizeof(int), stream)(tmin, facts, WpT, bias, (const float*)h, (float*)gate, (float*)hg,
-                                                                            Tn, t0, F, D, ld, ldp, NP, lag);
+                                                                            Tn, t0, F, D, ld, ldp, NP, lag, group);
     else if (dt == ICK_BF16)
         ick_launch(pred_gate_fwd_kernel<bf16>, grid, 128, F * sizeof(int), stream)(tmin, facts, WpT, bias, (const bf16*)h, (bf16*)gate, (bf16*)hg, Tn,
-                                                                           t0, F, D, ld, ldp, NP, lag);
+                                                                           t0, F, D, ld, ldp, NP, lag, group);
     else ICK_BAD_DT("pred_gate_fwd", dt);
     return ick_check_launch("pred_gate_fwd");
 }
@@ -773,9 +782,25 @@ extern "C" int ick_pred_gate_bwd(const void* dG, const int* tmin, const long lon
 }
 
 extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores,
-                               int dt, int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream) {
+                               int dt, int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, int group,
+                               cudaStream_t stream) {
     ICK_REQUIRE(D <= ld && ld % 8 == 0 && ((D + 7) & ~7) <= ld, "pointer_fwd: bad sizes D=%d ld=%d", D, ld);
+    ICK_REQUIRE(group >= 1 && B % group == 0, "pointer_fwd: B=%d is not a multiple of group=%d", B, group);
     if (B * Tn * S == 0) return ICK_OK;
+    if (group > 1) {  // beam decode: `group` consecutive rows are the beams of one image (one time step each)
+        ICK_REQUIRE(Tn == 1 && group <= 8, "pointer_fwd: group=%d needs Tn == 1 and group <= 8", group);
+        const int Dp8 = (D + 7) & ~7;
+        const size_t smemb = (size_t)8 * Dp8 * sizeof(float);
+        dim3 gridb((S + 127) / 128, 1, B / group);
+        if (dt == ICK_F32)
+            ick_launch(pointer_fwd_kernel<float, 8>, gridb, 128, smemb, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, group,
+                                                                           t0, S, D, ld, ldscores, col0, lag, 1);
+        else if (dt == ICK_BF16)
+            ick_launch(pointer_fwd_kernel<bf16, 8>, gridb, 128, smemb, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, group, t0,
+                                                                          S, D, ld, ldscores, col0, lag, 1);
+        else ICK_BAD_DT("pointer_fwd", dt);
+        return ick_check_launch("pointer_fwd");
+    }
     if (dt == ICK_BF16 && Tn >= 16) {  // tensor-core path (teacher-forced forward); single-step decode stays on the CUDA cores
         const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, ld, ldscores, col0, lag, stream);
         if (rc != ICK_ERR_UNSUPPORTED) return rc;
@@ -786,10 +811,10 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
         dim3 grid1((S + 127) / 128, 1, B);
         if (dt == ICK_F32)
             ick_launch(pointer_fwd_kernel<float, 1>, grid1, 128, smem1, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S,
-                                                                          D, ld, ldscores, col0, lag);
+                                                                          D, ld, ldscores, col0, lag, 0);
         else if (dt == ICK_BF16)
             ick_launch(pointer_fwd_kernel<bf16, 1>, grid1, 128, smem1, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
-                                                                         ld, ldscores, col0, lag);
+                                                                         ld, ldscores, col0, lag, 0);
         else ICK_BAD_DT("pointer_fwd", dt);
         return ick_check_launch("pointer_fwd");
     }
@@ -797,10 +822,10 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
     dim3 grid((S + 127) / 128, (Tn + PT_T - 1) / PT_T, B);
     if (dt == ICK_F32)
         ick_launch(pointer_fwd_kernel<float, PT_T>, grid, 128, smem, stream)((const float*)h, (const float*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
-                                                                       ld, ldscores, col0, lag);
+                                                                       ld, ldscores, col0, lag, 0);
     else if (dt == ICK_BF16)
         ick_launch(pointer_fwd_kernel<bf16, PT_T>, grid, 128, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D,
-                                                                      ld, ldscores, col0, lag);
+                                                                      ld, ldscores, col0, lag, 0);
     else ICK_BAD_DT("pointer_fwd", dt);
     return ick_check_launch("pointer_fwd");
 }

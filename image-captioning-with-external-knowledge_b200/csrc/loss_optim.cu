@@ -208,6 +208,158 @@ __global__ void __launch_bounds__(256) greedy_select_kernel(const float* __restr
     }
 }
 
+// ---- beam search step (extension - the reference decodes greedily) -------------------------------------------
+// One CTA per image.  Rows [img*G, img*G + nrows) of `scores` are the live beams (nrows = 1 at step 0, else k = ksel[img]).
+// candidate(j, c) = cum[j] + log_softmax(scores[j])[c]; the k best candidates over the live rows are taken in descending
+// order (ties: lower row, then lower column).  A candidate whose token is <end> completes a caption - it replaces `result`
+// if its score beats the best completed one - and lowers k; the others become the new beams 0..k'-1 in that order: token and
+// mask history and the ancestor table of the parent are copied from the *_in to the *_out buffers and extended by the new token.
+template <int G>
+__device__ __forceinline__ void beam_insert(float (&v)[G], int (&ix)[G], float x, int i) {
+    if (!(x > v[G - 1] || (x == v[G - 1] && i < ix[G - 1]))) return;
+    v[G - 1] = x;
+    ix[G - 1] = i;
+#pragma unroll
+    for (int k = G - 1; k > 0; --k) {
+        const bool up = v[k] > v[k - 1] || (v[k] == v[k - 1] && ix[k] < ix[k - 1]);
+        if (up) {
+            const float tv = v[k]; v[k] = v[k - 1]; v[k - 1] = tv;
+            const int ti = ix[k]; ix[k] = ix[k - 1]; ix[k - 1] = ti;
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) beam_select_kernel(const float* __restrict__ scores, int W, int lds, float* __restrict__ cum,
+                                                          int* __restrict__ ksel, const long long* __restrict__ tok_in,
+                                                          const long long* __restrict__ mask_in, long long* __restrict__ tok_out,
+                                                          long long* __restrict__ mask_out, const int* __restrict__ anc_in,
+                                                          int* __restrict__ anc_out, float* __restrict__ best, long long* __restrict__ result,
+                                                          int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok) {
+    ick_pdl_entry();
+    __shared__ float red_m[8], red_l[8], red_v[8];
+    __shared__ int red_i[8];
+    __shared__ float sel_v[G];
+    __shared__ int sel_i[G], sel_slot[G];
+    __shared__ int s_nalive, s_bestr;
+    __shared__ float s_logz;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = ksel[img];
+    if (k <= 0) return;
+    const int nrows = step == 0 ? 1 : k;
+    float gv[G];
+    int gi[G];
+#pragma unroll
+    for (int a = 0; a < G; ++a) { gv[a] = -INFINITY; gi[a] = 0x7fffffff; }
+    for (int j = 0; j < nrows; ++j) {
+        const float* s = scores + (size_t)(img * G + j) * lds;
+        float rm = -INFINITY, rl = 0.f, rv[G];
+        int ri[G];
+#pragma unroll
+        for (int a = 0; a < G; ++a) { rv[a] = -INFINITY; ri[a] = 0x7fffffff; }
+        for (int c = tid; c < W; c += 256) {
+            const float x = s[c];
+            if (x > rm) {
+                rl = rl * expf(rm - x) + 1.f;
+                rm = x;
+            } else {
+                rl += expf(x - rm);
+            }
+            beam_insert<G>(rv, ri, x, c);
+        }
+        // block log-sum-exp
+        float wm = warp_max(rm);
+        float wl = warp_sum(rm == -INFINITY ? 0.f : rl * expf(rm - wm));
+        if (lane == 0) { red_m[wid] = wm; red_l[wid] = wl; }
+        __syncthreads();
+        if (tid == 0) {
+            float M = red_m[0];
+            for (int w = 1; w < 8; ++w) M = fmaxf(M, red_m[w]);
+            float L = 0.f;
+            for (int w = 0; w < 8; ++w) L += red_m[w] == -INFINITY ? 0.f : red_l[w] * expf(red_m[w] - M);
+            s_logz = M + logf(L);
+        }
+        __syncthreads();
+        const float logz = s_logz, cj = cum[img * G + j];
+#pragma unroll
+        for (int a = 0; a < G; ++a)
+            if (ri[a] != 0x7fffffff) beam_insert<G>(gv, gi, cj + (rv[a] - logz), j * W + ri[a]);
+    }
+    // the k best of the block, one per round: every thread offers the head of its own sorted list
+    for (int r = 0; r < k; ++r) {
+        float v = gv[0];
+        int i = gi[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+        if (lane == 0) { red_v[wid] = v; red_i[wid] = i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) { v = red_v[w]; i = red_i[w]; }
+            sel_v[r] = v;
+            sel_i[r] = i;
+        }
+        __syncthreads();
+        if (gi[0] == sel_i[r] && sel_i[r] != 0x7fffffff) {  // the winner pops its head
+#pragma unroll
+            for (int a = 0; a + 1 < G; ++a) { gv[a] = gv[a + 1]; gi[a] = gi[a + 1]; }
+            gv[G - 1] = -INFINITY;
+            gi[G - 1] = 0x7fffffff;
+        }
+    }
+    if (tid == 0) {
+        int nalive = 0, bestr = -1;
+        float bv = best[img];
+        for (int r = 0; r < k; ++r) {
+            const int c = sel_i[r] % W;
+            if (c == end_tok) {
+                sel_slot[r] = -1;
+                if (sel_v[r] > bv) { bv = sel_v[r]; bestr = r; }
+            } else {
+                sel_slot[r] = nalive++;
+            }
+        }
+        if (step == Tmax - 1 && bv == -INFINITY && nalive > 0)  // nothing ever completed: the best live beam is the caption
+            for (int r = 0; r < k; ++r)
+                if (sel_slot[r] == 0) { bv = sel_v[r]; bestr = r; }
+        best[img] = bv;
+        s_nalive = nalive;
+        s_bestr = bestr;
+        ksel[img] = nalive;
+    }
+    __syncthreads();
+    const int hist = step + 1;  // positions 0..step of the parent's history
+    for (int e = tid; e < k * hist; e += 256) {
+        const int r = e / hist, t = e % hist, slot = sel_slot[r];
+        if (slot < 0) continue;
+        const size_t src = (size_t)(img * G + sel_i[r] / W) * Tmax + t, dst = (size_t)(img * G + slot) * Tmax + t;
+        tok_out[dst] = tok_in[src];
+        mask_out[dst] = mask_in[src];
+        anc_out[dst] = anc_in[src];
+    }
+    if (tid < k && sel_slot[tid] >= 0) {
+        const int slot = sel_slot[tid];
+        cum[img * G + slot] = sel_v[tid];
+        if (step + 1 < Tmax) {
+            const long long c = sel_i[tid] % W;
+            const size_t dst = (size_t)(img * G + slot) * Tmax + step + 1;
+            tok_out[dst] = c;
+            mask_out[dst] = (has_facts && c >= (long long)V + E) ? 2 : (c >= V ? 1 : 0);
+            anc_out[dst] = slot;
+        }
+    }
+    const int bestr = s_bestr;
+    if (bestr >= 0) {
+        const size_t src = (size_t)(img * G + sel_i[bestr] / W) * Tmax;
+        for (int t = tid; t < Tmax; t += 256)
+            result[(size_t)img * Tmax + t] = t < step ? tok_in[src + t + 1] : (t == step ? (long long)(sel_i[bestr] % W) : (long long)pad_tok);
+    }
+}
+
 inline int ew_grid(long long n) {
     long long g = (n + 255) / 256;
     return (int)(g < 148 * 16 ? (g < 1 ? 1 : g) : 148 * 16);
@@ -306,6 +458,33 @@ extern "C" int ick_greedy_select(const float* scores, int W, int lds, long long*
     ick_launch(greedy_select_kernel, B, 256, 0, stream)(scores, W, lds, output, second, captions, masks, done, margins, step, Tmax, V, E, has_facts,
                                                 end_tok);
     return ick_check_launch("greedy_select");
+}
+
+extern "C" int ick_beam_select(const float* scores, int W, int lds, float* cum, int* ksel, const long long* tok_in,
+                               const long long* mask_in, long long* tok_out, long long* mask_out, const int* anc_in, int* anc_out,
+                               float* best, long long* result, int images, int group, int step, int Tmax, int V, int E, int has_facts,
+                               int end_tok, int pad_tok, cudaStream_t stream) {
+    ICK_REQUIRE(images >= 0 && step >= 0 && step < Tmax && W >= 2, "beam_select: bad sizes");
+    ICK_REQUIRE(group >= 1 && group <= 8 && (long long)group * W < 0x7fffffffLL, "beam_select: group=%d out of range", group);
+    ICK_REQUIRE(tok_in != tok_out && mask_in != mask_out && anc_in != anc_out, "beam_select: histories must be double-buffered");
+    if (images == 0) return ICK_OK;
+#define ICK_BEAM_SEL(GG)                                                                                                              \
+    case GG:                                                                                                                          \
+        ick_launch(beam_select_kernel<GG>, images, 256, 0, stream)(scores, W, lds, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, \
+                                                                    anc_out, best, result, step, Tmax, V, E, has_facts, end_tok, pad_tok); \
+        break;
+    switch (group) {
+        ICK_BEAM_SEL(1)
+        ICK_BEAM_SEL(2)
+        ICK_BEAM_SEL(3)
+        ICK_BEAM_SEL(4)
+        ICK_BEAM_SEL(5)
+        ICK_BEAM_SEL(6)
+        ICK_BEAM_SEL(7)
+        ICK_BEAM_SEL(8)
+    }
+#undef ICK_BEAM_SEL
+    return ick_check_launch("beam_select");
 }
 
 // ---- error plumbing ---------------------------------------------------------------------------------------------------

@@ -202,6 +202,13 @@ class CudaKernels:
         self._call("ick_mha_decode", _p(Q), _p(K), _p(V), _p(O), dt_of(Q), B, H, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
                    int(kbatch_stride), int(vbatch_stride), klen)
 
+    def mha_decode_beam(self, Q, K, V, O, rows, group, H, dh, klen, kimg_stride=0, vimg_stride=0, anc=None, kpos_stride=0, vpos_stride=0):
+        """Beam-search decode attention (include/ickb200.h): anc=None -> the `group` beams of an image share its keys (image
+        strides), else position-major cache with the (rows, Tmax) int32 ancestor-slot table `anc` (position strides)."""
+        self._call("ick_mha_decode_beam", _p(Q), _p(K), _p(V), _p(O), dt_of(Q), rows, group, H, dh, _ld(Q), _ld(K), _ld(V), _ld(O),
+                   int(kimg_stride), int(vimg_stride), klen, _p(anc), anc.stride(0) if anc is not None else 0, int(kpos_stride),
+                   int(vpos_stride))
+
     # ---- residual + dropout + layer norm ---------------------------------------------------------------------------
     def add_ln_fwd(self, x, sub, gamma, beta, y, mean, rstd, d, eps=1e-5, rowmap=(0, 0, 0), drop: Drop = None):
         rows = sub.shape[0]
@@ -265,10 +272,10 @@ class CudaKernels:
         self._call("ick_fact_encode_bwd", _p(dFact), _p(facts), _p(dEnt), _p(gflat), pred_off, B, E, F, D, _ld(dFact), NP)
 
     def caption_embed_fwd(self, captions, masks, word_emb, ent_enc, fact_enc, pe, out, B, Tstride, t0, Tn, V, E, F, D, pad, scale,
-                          drop: Drop = None):
+                          drop: Drop = None, group=1):
         p, seed, site = _drop(drop)
         self._call("ick_caption_embed_fwd", _p(captions), _p(masks), _p(word_emb), _p(ent_enc), _p(fact_enc), _p(pe), _p(out),
-                   dt_of(out), B, Tstride, t0, Tn, V, E, F, D, _ld(out), _ld(word_emb), pad, scale, p, seed, site)
+                   dt_of(out), B, Tstride, t0, Tn, V, E, F, D, _ld(out), _ld(word_emb), pad, scale, group, p, seed, site)
 
     def caption_embed_bwd(self, dX, captions, masks, dEnt, dFact, gflat, word_off, B, T, V, E, F, D, pad, scale, drop: Drop = None):
         p, seed, site = _drop(drop)
@@ -286,12 +293,12 @@ class CudaKernels:
                    work=lambda: (x.numel() * 4 + B * Hout * Wout * C * rows.element_size(), 0))
 
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
-    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E):
-        self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E)
+    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1):
+        self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E, group)
 
-    def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag):
+    def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag, group=1):
         self._call("ick_pred_gate_fwd", _p(tmin), _p(facts), _p(WpT), _p(bias), _p(h), _p(gate), _p(hg), dt_of(gate), B, Tn, t0, F, D,
-                   _ld(gate), _ld(WpT), NP, lag)
+                   _ld(gate), _ld(WpT), NP, lag, group)
 
     def gate_mul_bwd(self, dHG, h, gate, dG, dH):
         assert dHG.is_contiguous() and h.is_contiguous() and gate.is_contiguous() and dG.is_contiguous() and dH.is_contiguous()
@@ -301,9 +308,9 @@ class CudaKernels:
         self._call("ick_pred_gate_bwd", _p(dG), _p(tmin), _p(facts), _p(gflat), wp_off, dt_of(dG), B, T, F, D, _ld(dG), NP, lag)
 
     # ---- pointer heads -----------------------------------------------------------------------------------------------------
-    def pointer_fwd(self, h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, col0, lag):
+    def pointer_fwd(self, h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, col0, lag, group=1):
         self._call("ick_pointer_fwd", _p(h), _p(ctx), _p(w), _p(bias), _p(first_t), _p(scores), dt_of(h), B, Tn, t0, S, D, _ld(h),
-                   _ld(scores), col0, lag)
+                   _ld(scores), col0, lag, group)
 
     def pointer_bwd(self, dS, h, ctx, w, first_t, dCtx, dH, gflat, w_off, bias_off, B, T, S, D, col0, lag):
         self._call("ick_pointer_bwd", _p(dS), _p(h), _p(ctx), _p(w), _p(first_t), _p(dCtx), _p(dH), _p(gflat), w_off, bias_off,
@@ -340,3 +347,8 @@ class CudaKernels:
     def greedy_select(self, scores, W, output, second, captions, masks, done, margins, B, step, Tmax, V, E, has_facts, end_tok):
         self._call("ick_greedy_select", _p(scores), W, _ld(scores), _p(output), _p(second), _p(captions), _p(masks), _p(done),
                    _p(margins), B, step, Tmax, V, E, int(has_facts), end_tok)
+
+    def beam_select(self, scores, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, anc_out, best, result, images, group, step,
+                    Tmax, V, E, has_facts, end_tok, pad_tok):
+        self._call("ick_beam_select", _p(scores), W, _ld(scores), _p(cum), _p(ksel), _p(tok_in), _p(mask_in), _p(tok_out), _p(mask_out),
+                   _p(anc_in), _p(anc_out), _p(best), _p(result), images, group, step, Tmax, V, E, int(has_facts), end_tok, pad_tok)

@@ -345,7 +345,27 @@ class DecoderTransformer(nn.Module):
                 return eng.greedy_decode(inp, max_pred_len, return_margins=return_margins)
             return self._graphed_decode(eng, inp, max_pred_len)
 
-    def _graphed_decode(self, eng, inp, max_pred_len):
+    def beam_search_batch(self, encoder_out, max_pred_len, entities, facts=None, beam_size=5, return_scores=False):
+        """
+        EXTENSION (no reference counterpart: the reference's predict() is greedy): beam-search captions for a batch
+        of images -> (B, max_pred_len) int64 in predict()'s token convention (no <start>, <end> included, <pad>-filled), and
+        with return_scores the summed log-probability of each returned caption.  Device-resident, see engine.beam_decode.
+        """
+        eng = self._ensure_engine()
+        dev = eng.device
+        inp = NS(encoder_out=encoder_out.detach().to(dev, torch.float32).contiguous(),
+                 entities=entities.to(dev, torch.float32).contiguous(),
+                 facts=facts.to(dev).contiguous() if facts is not None else None)
+        graphed = (dev.type == "cuda" and type(self)._test_kernel_factory is None
+                   and os.environ.get("ICKB200_DECODE_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing())
+        with torch.no_grad():
+            if graphed:
+                out, score = self._graphed_decode(eng, inp, max_pred_len, beam=int(beam_size))
+            else:
+                out, score = eng.beam_decode(inp, max_pred_len, int(beam_size))
+        return (out, score) if return_scores else out
+
+    def _graphed_decode(self, eng, inp, max_pred_len, beam=0):
         """
         The whole decode loop (context encoders, memory K/V, max_pred_len x ~40 kernels, all device-resident) as ONE CUDA graph
         per input shape: launched eagerly from Python the loop is bound by the host (~20 us per launch), replayed it is bound by
@@ -354,7 +374,8 @@ class DecoderTransformer(nn.Module):
         """
         cache = self.__dict__.setdefault("_decode_graphs", {})
         key = (id(eng), max_pred_len, tuple(inp.encoder_out.shape), tuple(inp.entities.shape),
-               tuple(inp.facts.shape) if inp.facts is not None else None)
+               tuple(inp.facts.shape) if inp.facts is not None else None, beam)
+        run = (lambda x: eng.beam_decode(x, max_pred_len, beam)) if beam else (lambda x: eng.greedy_decode(x, max_pred_len))
         entry = cache.get(key)
         if entry is None:
             static = NS(encoder_out=inp.encoder_out.clone(), entities=inp.entities.clone(),
@@ -363,12 +384,12 @@ class DecoderTransformer(nn.Module):
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # eager warm-up: one-time initialisation must not happen during capture
-                eng.greedy_decode(static, max_pred_len)
+                run(static)
             cur.wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = eng.greedy_decode(static, max_pred_len)
+                out = run(static)
             if len(cache) >= 4:  # each graph owns its activation pool: keep a few shapes only
                 cache.pop(next(iter(cache)))
             entry = cache[key] = (graph, static, out)
@@ -378,7 +399,7 @@ class DecoderTransformer(nn.Module):
         if static.facts is not None:
             static.facts.copy_(inp.facts, non_blocking=True)
         graph.replay()
-        return out.clone()
+        return tuple(o.clone() for o in out) if beam else out.clone()
 
     def predict(self, encoder_out, max_pred_len, entities, facts=None):
         """G/models.py:363-443: batch-1 greedy decode -> (max_pred_len, 1) int64."""

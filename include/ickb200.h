@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 7
+#define ICK_ABI_VERSION 8
 
 #ifdef __cplusplus
 extern "C" {
@@ -122,11 +122,13 @@ int ick_fact_encode_fwd(const long long* facts, const void* ent_enc, const float
 int ick_fact_encode_bwd(const float* dFact, const long long* facts, float* dEnt, float* gflat, int pred_off, int B, int E, int F,
                         int D, int ld, int NP, cudaStream_t stream);
 /* CaptionEmbedder.forward (K/models.py:209-259) fused with *sqrt(d) and PositionEncoder (K/models.py:505-507); positions
- * [t0, t0+Tn) of captions with row stride Tstride */
+ * [t0, t0+Tn) of captions with row stride Tstride.
+ * `group` (here and in the three entry points below that take it): that many consecutive caption rows share ONE image context
+ * (entity / fact encodings, fact list) - the beams of an image during beam-search decoding; 1 = every row has its own. */
 int ick_caption_embed_fwd(const long long* captions, const long long* masks, const void* word_emb, const void* ent_enc,
                           const void* fact_enc, const float* pe, void* out, int dt, int B, int Tstride, int t0, int Tn, int V, int E,
-                          int F, int D, int ld, int ldw, int pad, float scale, float drop_p, unsigned seed, unsigned site,
-                          cudaStream_t stream);
+                          int F, int D, int ld, int ldw, int pad, float scale, int group, float drop_p, unsigned seed,
+                          unsigned site, cudaStream_t stream);
 int ick_caption_embed_bwd(const void* dX, const long long* captions, const long long* masks, float* dEnt, float* dFact, float* gflat,
                           int word_off, int dt, int B, int T, int V, int E, int F, int D, int ld, int pad, float scale, float drop_p,
                           unsigned seed, unsigned site, cudaStream_t stream);
@@ -142,16 +144,17 @@ int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin,
 
 /* ---- context indicators + predicate gate: get_context_indicators K/models.py:380-418, fc_predicate K/models.py:436-437 ---- */
 int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F, int V,
-                           int E, cudaStream_t stream);
+                           int E, int group, cudaStream_t stream);
 int ick_pred_gate_fwd(const int* tmin, const long long* facts, const float* WpT, const float* bias, const void* h, void* gate,
-                      void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag, cudaStream_t stream);
+                      void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag, int group,
+                      cudaStream_t stream);
 int ick_gate_mul_bwd(const void* dHG, const void* h, const void* gate, void* dG, void* dH, int dt, long long n, cudaStream_t stream);
 int ick_pred_gate_bwd(const void* dG, const int* tmin, const long long* facts, float* gflat, int wp_off, int dt, int B, int T, int F,
                       int D, int ld, int NP, int lag, cudaStream_t stream);
 
 /* ---- pointer heads: fc_entity / fc_fact over h*ctx, get_scores K/models.py:440-452 ----------------------------------------- */
 int ick_pointer_fwd(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores, int dt,
-                    int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream);
+                    int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, int group, cudaStream_t stream);
 int ick_pointer_bwd(const void* dS, const void* h, const void* ctx, const float* w, const int* first_t, float* dCtx, void* dH,
                     float* gflat, int w_off, int bias_off, int dt, int B, int T, int S, int D, int ld, int ldds, int col0, int lag,
                     cudaStream_t stream);
@@ -180,6 +183,31 @@ int ick_colsum(const void* x, int dt, float* out, long long rows, int cols, int 
 int ick_greedy_select(const float* scores, int W, int lds, long long* output, int* second, long long* captions, long long* masks,
                       int* done, float* margins, int B, int step, int Tmax, int V, int E, int has_facts, int end_tok,
                       cudaStream_t stream);
+
+
+/* ---- beam-search decoding: EXTENSION, no reference counterpart (the reference's predict() is greedy; BASELINE.json
+ * asks for beam-5).  The algorithm is the beam search of the Show-Attend-Tell tutorial the reference's READMEs name as their
+ * starting point (G/README.md:37), restated in oracle/decoder_oracle.py:beam_search over the reference-pinned scoring function. -- */
+/* `rows` query rows, `group` consecutive rows = the beams of one image, one query per (row, head) against klen cached positions.
+ * anc == NULL: the beams share the image's keys/values (cross-attention over the memory): row j of image i is at
+ *   K + i*kimg_stride + j*ldk, read once per image for all its beams.
+ * anc != NULL: position-major self-attention cache; the key of query row r at position j is row
+ *   (r/group)*group + anc[r*anc_ld + j] of the block at K + j*kpos_stride, i.e. anc names the beam slot that held row r's
+ *   ancestor at step j - re-ordering beams rewrites only that table. */
+int ick_mha_decode_beam(const void* Q, const void* K, const void* V, void* O, int dt, int rows, int group, int H, int dh, int ldq,
+                        int ldk, int ldv, int ldo, long long kimg_stride, long long vimg_stride, int klen, const int* anc, int anc_ld,
+                        long long kpos_stride, long long vpos_stride, cudaStream_t stream);
+/* One beam-search step for `images` images of `group` beam slots each (rows img*group + slot of scores / cum / histories).
+ * ksel[img] = k, the number of captions still wanted (starts at group; live rows = 1 at step 0, else k).  Candidates
+ * cum[row] + log_softmax(scores[row])[c] over the live rows; the k best in descending order: token <end> completes a caption
+ * (kept in result/best if it beats the best completed one; k decreases), the others become beams 0..k'-1: histories
+ * tok/mask/anc (rows of Tmax) are copied parent -> new slot from *_in to *_out and extended at position step+1 with the token,
+ * its mask class (0 word, 1 entity, 2 fact) and the slot itself; cum is updated in place.  result (images, Tmax): tokens
+ * without <start>, <end> included, pad-filled.  At the last step an image without a completed caption takes its best live beam. */
+int ick_beam_select(const float* scores, int W, int lds, float* cum, int* ksel, const long long* tok_in, const long long* mask_in,
+                    long long* tok_out, long long* mask_out, const int* anc_in, int* anc_out, float* best, long long* result,
+                    int images, int group, int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok,
+                    cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -464,3 +464,98 @@ def predict(
                 masks[0, i + 1] = 1
     res = output.view(T, 1)
     return (res, margins) if return_margins else res
+
+
+def beam_search(
+    spec: Spec,
+    p: Params,
+    encoder_out: torch.Tensor,
+    max_pred_len: int,
+    entities: torch.Tensor,
+    facts: Optional[torch.Tensor] = None,
+    beam_size: int = 5,
+    return_margin: bool = False,
+):
+    """
+    EXTENSION — PARITY UNPINNED BY THE REFERENCE.  /root/reference has no beam search (its predict() is greedy, SURVEY.md §0);
+    BASELINE.json asks for beam-5.  This restates the published beam search of the Show-Attend-Tell tutorial that the
+    reference's READMEs name as the origin of their infrastructure (geo-aware/README.md:37; tutorial eval.py,
+    `evaluate(beam_size)`), run over THIS file's reference-pinned scoring function (the same caption_embed / decoder_stack /
+    context_indicators / get_scores calls as `predict` above, i.e. K/models.py:548-575 for a batch of k partial captions):
+
+        k live captions, all starting with <start>;  per step: candidate = score_so_far + log_softmax(scores)[token];
+        step 1 takes the k best tokens of the single start row, later steps the k best of the flattened (k, W) table;
+        a candidate ending in <end> is moved to the completed list and k shrinks; stop when k == 0 or after
+        max_pred_len steps; the answer is the completed caption with the highest summed log-probability (no length
+        normalisation, first maximum wins).  No repetition clean-up (that heuristic belongs to the greedy predict()).
+        If nothing completed within max_pred_len steps (the tutorial would fail there) the best live caption is returned.
+
+    Batch 1.  Returns (max_pred_len,) int64: tokens without <start>, <end> included, <pad>-filled — predict()'s convention.
+    With return_margin also the smallest gap between the k-th selected and the best rejected candidate over all steps
+    (test diagnostic for near-ties, where fp32 rounding may legitimately pick another beam).
+    """
+    assert encoder_out.shape[0] == 1
+    H, L, D, V = spec.num_heads, spec.num_layers, spec.emb_dim, spec.vocab_size
+    T = max_pred_len
+    ent_enc = entity_encode(spec, p, entities, facts)
+    E = ent_enc.shape[1]
+    ctx = [encoder_out.permute(0, 2, 1), encoder_stack(p, "transformer_encoder_entities", ent_enc, H, L)]
+    fact_enc = None
+    if spec.has_facts:
+        fact_enc = fact_encode(p, facts, ent_enc)
+        ctx.append(encoder_stack(p, "transformer_encoder_facts", fact_enc, H, L))
+    memory = torch.cat(ctx, dim=1)
+    pe = p["pos_encoder.pe"][:T, 0, :].unsqueeze(0)
+    k = beam_size
+    seqs = torch.full((1, T), spec.start, dtype=torch.long)  # input tokens; row r, position i+1 = output of step i
+    masks = torch.zeros((1, T), dtype=torch.long)
+    outs: List[List[int]] = [[]]
+    cum = torch.zeros(1)
+    done: List[Tuple[float, List[int]]] = []
+    margin = float("inf")
+    for i in range(T):
+        n = seqs.shape[0]
+        x = caption_embed(spec, p, seqs, masks, ent_enc.expand(n, -1, -1), fact_enc.expand(n, -1, -1) if fact_enc is not None else None)
+        x = x * math.sqrt(D) + pe
+        h = decoder_stack(p, x, memory.expand(n, -1, -1), H, L)[:, i : i + 1]
+        if spec.has_facts:
+            eb, pi = context_indicators(spec, seqs, facts.expand(n, -1, -1), E, 1)
+        else:
+            eb = pi = None
+        sc = get_scores(spec, p, h, ent_enc.expand(n, -1, -1), fact_enc.expand(n, -1, -1) if fact_enc is not None else None, eb, pi)[:, 0]
+        W = sc.shape[1]
+        cand = (cum.unsqueeze(1) + F.log_softmax(sc, dim=1)).reshape(-1)
+        top = torch.topk(cand, min(k + 1, cand.numel()))
+        if top.values.numel() > k:
+            margin = min(margin, float(top.values[k - 1] - top.values[k]))
+        vals, idx = top.values[:k], top.indices[:k]
+        prev, nxt = (idx // W).tolist(), (idx % W).tolist()
+        keep_rows, keep_tok, keep_val, new_outs = [], [], [], []
+        for r in range(k):
+            seq = outs[prev[r]] + [nxt[r]]
+            if nxt[r] == spec.end:
+                done.append((float(vals[r]), seq))
+            else:
+                keep_rows.append(prev[r])
+                keep_tok.append(nxt[r])
+                keep_val.append(vals[r])
+                new_outs.append(seq)
+        k = len(keep_rows)
+        if k == 0:
+            break
+        outs = new_outs
+        cum = torch.stack(keep_val)
+        seqs = seqs[keep_rows].clone()
+        masks = masks[keep_rows].clone()
+        if i < T - 1:
+            for r, tok in enumerate(keep_tok):
+                seqs[r, i + 1] = tok
+                masks[r, i + 1] = 2 if (spec.has_facts and tok >= V + E) else (1 if tok >= V else 0)
+    if done:
+        best = max(range(len(done)), key=lambda j: (done[j][0], -j))  # highest score, first one on ties
+        seq = done[best][1]
+    else:
+        seq = outs[0]
+    res = torch.full((T,), spec.pad, dtype=torch.long)
+    res[: len(seq)] = torch.tensor(seq, dtype=torch.long)
+    return (res, margin) if return_margin else res

@@ -157,6 +157,25 @@ class HostKernels:
             o[:, :dh] = torch.einsum("hk,khd->hd", p, v)
             O[b] = o.reshape(-1).to(O.dtype)
 
+    def mha_decode_beam(self, Q, K, V, O, rows, group, H, dh, klen, kimg_stride=0, vimg_stride=0, anc=None, kpos_stride=0, vpos_stride=0):
+        self.calls += 1
+        ldk, ldv = K.stride(0), V.stride(0)
+        for r in range(rows):
+            img = r // group
+            if anc is None:
+                kr = [img * (kimg_stride // ldk) + j for j in range(klen)]
+                vr = [img * (vimg_stride // ldv) + j for j in range(klen)]
+            else:
+                kr = [j * (kpos_stride // ldk) + img * group + int(anc[r, j]) for j in range(klen)]
+                vr = [j * (vpos_stride // ldv) + img * group + int(anc[r, j]) for j in range(klen)]
+            q = Q[r].float().view(H, HD)[:, :dh]
+            k = K[kr].float().reshape(klen, H, HD)[..., :dh]
+            v = V[vr].float().reshape(klen, H, HD)[..., :dh]
+            p = torch.softmax(torch.einsum("hd,khd->hk", q, k) / math.sqrt(dh), dim=-1)
+            o = torch.zeros(H, HD)
+            o[:, :dh] = torch.einsum("hk,khd->hd", p, v)
+            O[r] = o.reshape(-1).to(O.dtype)
+
     # ---- residual + dropout + layer norm ---------------------------------------------------------------------------
     def add_ln_fwd(self, x, sub, gamma, beta, y, mean, rstd, d, eps=1e-5, rowmap=(0, 0, 0), drop=None):
         self.calls += 1
@@ -304,8 +323,13 @@ class HostKernels:
             idx = torch.where(mask == 2, f, idx)
         return kind, idx
 
-    def caption_embed_fwd(self, captions, masks, word_emb, ent_enc, fact_enc, pe, out, B, Tstride, t0, Tn, V, E, F, D, pad, scale, drop=None):
+    def caption_embed_fwd(self, captions, masks, word_emb, ent_enc, fact_enc, pe, out, B, Tstride, t0, Tn, V, E, F, D, pad, scale, drop=None,
+                          group=1):
         self.calls += 1
+        if group > 1:  # beams of an image share its context
+            ent_enc = ent_enc.view(B // group, E, -1).repeat_interleave(group, 0).reshape(B * E, -1)
+            if F > 0:
+                fact_enc = fact_enc.view(B // group, F, -1).repeat_interleave(group, 0).reshape(B * F, -1)
         tok = captions.view(B, Tstride)[:, t0 : t0 + Tn]
         mk = masks.view(B, Tstride)[:, t0 : t0 + Tn]
         kind, idx = self._select(tok, mk, V, E, F, pad)
@@ -358,8 +382,10 @@ class HostKernels:
         rows[:, :C] = pooled.permute(0, 2, 3, 1).reshape(B * Hout * Wout, C).to(rows.dtype)
 
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
-    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E):
+    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1):
         self.calls += 1
+        if group > 1:
+            facts = facts.repeat_interleave(group, 0)
         caps = captions.view(B, T)
         ft = first_t.view(B, F)
         tm = tmin.view(B, F)
@@ -380,8 +406,10 @@ class HostKernels:
                 same = [g for g in range(F) if pred[g] == pred[f]]
                 tm[b, f] = min(firsts[g] for g in same) if same[0] == f else FIRST_NONE
 
-    def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag):
+    def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag, group=1):
         self.calls += 1
+        if group > 1:
+            facts = facts.repeat_interleave(group, 0)
         tm = tmin.view(B, F)
         gate.zero_()
         for b in range(B):
@@ -418,8 +446,11 @@ class HostKernels:
         t = (t0 + torch.arange(Tn) + lag).view(1, Tn, 1)
         return (first_t.view(B, 1, S) < t).float()
 
-    def pointer_fwd(self, h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, col0, lag):
+    def pointer_fwd(self, h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, col0, lag, group=1):
         self.calls += 1
+        if group > 1:
+            assert Tn == 1
+            ctx = ctx.view(B // group, S, -1).repeat_interleave(group, 0).reshape(B * S, -1)
         hh = h[:, :D].float().view(B, Tn, D) * w.float().view(1, 1, D)
         c = ctx[:, :D].float().view(B, S, D)
         s = torch.einsum("btd,bsd->bts", hh, c) * self._mask(first_t, B, Tn, t0, S, lag) + bias.float().view(1, 1, 1)
@@ -518,3 +549,44 @@ class HostKernels:
                 o = int(output[b, step])
                 captions[b, step + 1] = o
                 masks[b, step + 1] = 2 if (has_facts and o >= V + E) else (1 if o >= V else 0)
+
+    def beam_select(self, scores, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, anc_out, best, result, images, group, step,
+                    Tmax, V, E, has_facts, end_tok, pad_tok):
+        self.calls += 1
+        G = group
+        for img in range(images):
+            k = int(ksel[img])
+            if k <= 0:
+                continue
+            nrows = 1 if step == 0 else k
+            rows = slice(img * G, img * G + nrows)
+            cand = (cum[rows].unsqueeze(1) + torch.log_softmax(scores[rows, :W].float(), dim=1)).reshape(-1)
+            top = torch.topk(cand, k)
+            nalive, bv, bestseq = 0, float(best[img]), None
+            first_alive = None
+            for r in range(k):
+                val, j, c = float(top.values[r]), int(top.indices[r]) // W, int(top.indices[r]) % W
+                src = img * G + j
+                if c == end_tok:
+                    if val > bv:
+                        bv, bestseq = val, tok_in[src, 1 : step + 1].tolist() + [c]
+                    continue
+                dst = img * G + nalive
+                tok_out[dst, : step + 1] = tok_in[src, : step + 1]
+                mask_out[dst, : step + 1] = mask_in[src, : step + 1]
+                anc_out[dst, : step + 1] = anc_in[src, : step + 1]
+                cum[dst] = val
+                if step + 1 < Tmax:
+                    tok_out[dst, step + 1] = c
+                    mask_out[dst, step + 1] = 2 if (has_facts and c >= V + E) else (1 if c >= V else 0)
+                    anc_out[dst, step + 1] = nalive
+                if first_alive is None:
+                    first_alive = (val, tok_in[src, 1 : step + 1].tolist() + [c])
+                nalive += 1
+            if step == Tmax - 1 and bv == float("-inf") and first_alive is not None:
+                bv, bestseq = first_alive
+            best[img] = bv
+            ksel[img] = nalive
+            if bestseq is not None:
+                result[img] = pad_tok
+                result[img, : len(bestseq)] = torch.tensor(bestseq, dtype=result.dtype)

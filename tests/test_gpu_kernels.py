@@ -602,3 +602,120 @@ def test_greedy_select_state_machine(K, Hk):
     for k in ("output", "captions", "masks", "done"):
         assert torch.equal(state["g"][k].cpu(), state["r"][k]), k
     assert int(state["r"]["done"].sum()) == B
+
+
+# ---- beam-search extension kernels ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("group", [1, 3, 5])
+def test_mha_decode_beam(K, Hk, dtype, group):
+    NI, H, dh, Tmax, klen, M = 4, 10, 30, 9, 6, 45
+    R = NI * group
+    ldc = 3 * H * 32
+    # self-attention: position-major cache + ancestor-slot table
+    cache = headify(rnd((Tmax * R, ldc), torch.float32, 1), 3 * H, dh).to(dtype)
+    anc = torch.randint(0, group, (R, Tmax), generator=g(2), dtype=torch.int32)
+    Q = cache[(klen - 1) * R : klen * R, : H * 32]
+    Or, Og = torch.zeros(R, H * 32, dtype=dtype), torch.zeros(R, H * 32, dtype=dtype).cuda()
+    Hk.mha_decode_beam(Q, cache[:, H * 32 : 2 * H * 32], cache[:, 2 * H * 32 :], Or, R, group, H, dh, klen, anc=anc, kpos_stride=R * ldc,
+                       vpos_stride=R * ldc)
+    cg = cu(cache)
+    K.mha_decode_beam(cg[(klen - 1) * R : klen * R, : H * 32], cg[:, H * 32 : 2 * H * 32], cg[:, 2 * H * 32 :], Og, R, group, H, dh, klen,
+                      anc=cu(anc), kpos_stride=R * ldc, vpos_stride=R * ldc)
+    assert err(Og, Or) < TOL[dtype]
+    # cross-attention: the beams of an image share its keys / values
+    ldkv = 2 * H * 32
+    kv = headify(rnd((NI * M, ldkv), torch.float32, 3), 2 * H, dh).to(dtype)
+    q = headify(rnd((R, H * 32), torch.float32, 4), H, dh).to(dtype)
+    Or.zero_()
+    Og.zero_()
+    Hk.mha_decode_beam(q, kv[:, : H * 32], kv[:, H * 32 :], Or, R, group, H, dh, M, kimg_stride=M * ldkv, vimg_stride=M * ldkv)
+    kg = cu(kv)
+    K.mha_decode_beam(cu(q), kg[:, : H * 32], kg[:, H * 32 :], Og, R, group, H, dh, M, kimg_stride=M * ldkv, vimg_stride=M * ldkv)
+    assert err(Og, Or) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_grouped_context_kernels(K, Hk, dtype):
+    """caption embed / indicators / gate / pointer heads with `group` rows per image context (beam search)."""
+    NI, G, E, F, V, D, ld, NP, T = 3, 5, 23, 17, 61, 300, 320, 3000, 9
+    R = NI * G
+    cfg, batch = make_context(1, NI, E, F, V, seed=5)
+    facts = batch["facts"]
+    caps = torch.randint(1, V + E + F, (R, T), generator=g(1))
+    caps[:, 0] = V - 2
+    masks = torch.where(caps >= V + E, 2, torch.where(caps >= V, 1, 0))
+    ent = torch.zeros(NI * E, ld, dtype=dtype)
+    ent[:, :D] = rnd((NI * E, D), dtype, 2)
+    fct = torch.zeros(NI * F, ld, dtype=dtype)
+    fct[:, :D] = rnd((NI * F, D), dtype, 3)
+    wemb = torch.zeros(V, ld, dtype=dtype)
+    wemb[:, :D] = rnd((V, D), dtype, 4)
+    pe = rnd((T, D), torch.float32, 5)
+    t0 = 4
+    xr, xg = torch.zeros(R, ld, dtype=dtype), torch.full((R, ld), float("nan"), dtype=dtype).cuda()
+    Hk.caption_embed_fwd(caps, masks, wemb, ent, fct, pe, xr, R, T, t0, 1, V, E, F, D, 0, math.sqrt(D), group=G)
+    K.caption_embed_fwd(cu(caps), cu(masks), cu(wemb), cu(ent), cu(fct), cu(pe), xg, R, T, t0, 1, V, E, F, D, 0, math.sqrt(D), group=G)
+    assert err(xg, xr) < TOL[dtype]
+    ftr, tmr = torch.zeros(R * F, dtype=torch.int32), torch.zeros(R * F, dtype=torch.int32)
+    ftg, tmg = ftr.clone().cuda(), tmr.clone().cuda()
+    Hk.fact_first_mention(caps, facts, ftr, tmr, R, T, F, V, E, group=G)
+    K.fact_first_mention(cu(caps), cu(facts), ftg, tmg, R, T, F, V, E, group=G)
+    assert torch.equal(ftg.cpu(), ftr) and torch.equal(tmg.cpu(), tmr)
+    assert int((ftr < FIRST_NONE).sum()) > 0
+    WpT = torch.zeros(NP, ld)
+    WpT[:, :D] = rnd((NP, D), torch.float32, 6, 0.3)
+    bias = rnd((D,), torch.float32, 7)
+    h = torch.zeros(R, ld, dtype=dtype)
+    h[:, :D] = rnd((R, D), dtype, 8)
+    gr, hgr = torch.zeros(R, ld, dtype=dtype), torch.zeros(R, ld, dtype=dtype)
+    gg, hgg = torch.full_like(gr, float("nan")).cuda(), torch.full_like(gr, float("nan")).cuda()
+    Hk.pred_gate_fwd(tmr, facts, WpT, bias, h, gr, hgr, R, 1, t0, F, D, NP, 1, group=G)
+    K.pred_gate_fwd(tmg, cu(facts), cu(WpT), cu(bias), cu(h), gg, hgg, R, 1, t0, F, D, NP, 1, group=G)
+    assert err(gg, gr) < TOL[dtype] and err(hgg, hgr) < TOL[dtype]
+    w, b1 = rnd((D,), torch.float32, 9), rnd((1,), torch.float32, 10)
+    Wd = V + E + F
+    sr, sg = torch.zeros(R, Wd), torch.zeros(R, Wd).cuda()
+    Hk.pointer_fwd(h, ent, w, b1, None, sr, R, 1, t0, E, D, V, 1, group=G)
+    Hk.pointer_fwd(h, fct, w, b1, ftr, sr, R, 1, t0, F, D, V + E, 1, group=G)
+    K.pointer_fwd(cu(h), cu(ent), cu(w), cu(b1), None, sg, R, 1, t0, E, D, V, 1, group=G)
+    K.pointer_fwd(cu(h), cu(fct), cu(w), cu(b1), ftg, sg, R, 1, t0, F, D, V + E, 1, group=G)
+    assert err(sg, sr) < TOL[dtype]
+
+
+@pytest.mark.parametrize("G", [1, 3, 5])
+def test_beam_select_state_machine(K, Hk, G):
+    """Random score tables with <end> pushed into the top candidates at scripted steps: live-beam count, histories, ancestor
+    tables, cumulative scores and the best completed caption must match the host restatement exactly (fp32 scores: 1e-5)."""
+    NI, Wd, Tmax, V, E, end, pad = 7, 47, 8, 30, 6, 29, 0
+    R = NI * G
+    state = {}
+    for name, dev in (("r", "cpu"), ("g", DEV)):
+        own = (torch.arange(R, dtype=torch.int32) % G).unsqueeze(1).expand(R, Tmax).contiguous()
+        state[name] = dict(tok=[torch.full((R, Tmax), 28, dtype=torch.int64, device=dev) for _ in range(2)],
+                           msk=[torch.zeros(R, Tmax, dtype=torch.int64, device=dev) for _ in range(2)],
+                           anc=[own.clone().to(dev) for _ in range(2)], cum=torch.zeros(R, device=dev),
+                           ksel=torch.full((NI,), G, dtype=torch.int32, device=dev), best=torch.full((NI,), float("-inf"), device=dev),
+                           result=torch.full((NI, Tmax), pad, dtype=torch.int64, device=dev))
+    for step in range(Tmax):
+        sc = rnd((R, Wd), torch.float32, 200 + step, 2.0)
+        for img in range(NI):
+            if img == 6:
+                sc[img * G : (img + 1) * G, end] = -50.0  # never completes: best live beam at the last step
+            elif (step + img) % 3 == 1:
+                sc[img * G + (step % G), end] = 6.0  # one beam of the image very likely ends here
+        cur, nxt = step & 1, (step + 1) & 1
+        for name, kern in (("r", Hk), ("g", K)):
+            st = state[name]
+            kern.beam_select(sc.to(st["cum"].device), Wd, st["cum"], st["ksel"], st["tok"][cur], st["msk"][cur], st["tok"][nxt], st["msk"][nxt],
+                             st["anc"][cur], st["anc"][nxt], st["best"], st["result"], NI, G, step, Tmax, V, E, True, end, pad)
+        kr = state["r"]["ksel"]
+        assert torch.equal(state["g"]["ksel"].cpu(), kr), step
+        for img in range(NI):  # live rows only (dead slots hold stale data by design)
+            rows = slice(img * G, img * G + int(kr[img]))
+            upto = min(step + 2, Tmax)
+            for key in ("tok", "msk", "anc"):
+                assert torch.equal(state["g"][key][nxt][rows, :upto].cpu(), state["r"][key][nxt][rows, :upto]), (key, step, img)
+            assert torch.allclose(state["g"]["cum"][rows].cpu(), state["r"]["cum"][rows], atol=1e-5)
+    assert torch.equal(state["g"]["result"].cpu(), state["r"]["result"])
+    assert torch.allclose(state["g"]["best"].cpu(), state["r"]["best"], atol=1e-5)
+    assert int((state["r"]["ksel"] < G).sum()) > 0 and torch.isfinite(state["r"]["best"]).all()

@@ -119,6 +119,61 @@ def test_fp32_predict_token_identical(variant):
     assert tuple(one.shape) == (T, 1) and one.reshape(-1).tolist() == ref[0].tolist()
 
 
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_fp32_beam_search_token_identical(variant):
+    """Extension (the reference decodes greedily): beam-5 captions of the CUDA path against the captions the tutorial
+    beam search yields with the unmodified reference modules as the scoring function (tests/golden/make_golden_beam.py).  Images
+    whose k-th / (k+1)-th candidates are closer than 1e-4 at some step are exempt (fp32 rounding may pick either)."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"golden_beam_{variant}.npz")))
+    T, k, B = int(g["max_len"]), int(g["beam"]), int(g["batch"])
+    pb = syn.make_batch(cfg.with_batch(B), seed=int(g["seed"]))
+    facts = pb["facts"].cuda() if cfg.has_facts else None
+    for j, bias in enumerate(g["end_bias"].tolist()):
+        dec = build_module(cfg, "cuda", torch.float32).eval()
+        with torch.no_grad():
+            dec._get("fc_vocab.bias")[cfg.V - 1] += bias
+        dec._ensure_engine().repack()
+        for graphed in ("0", "1"):  # eager launches, then the whole search as one CUDA graph
+            os.environ["ICKB200_DECODE_GRAPH"] = graphed
+            try:
+                out, score = dec.beam_search_batch(pb["encoder_out"].cuda(), T, pb["entities"], facts, beam_size=k, return_scores=True)
+            finally:
+                os.environ.pop("ICKB200_DECODE_GRAPH", None)
+            ok = g[f"margins_{j}"] > 1e-4
+            assert ok.sum() >= B - 1
+            assert out.cpu().numpy()[ok].tolist() == g[f"tokens_{j}"][ok].tolist(), (j, graphed)
+            assert np.allclose(score.cpu().numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
+
+
+def test_beam_search_properties_at_baseline_size():
+    """bf16, knowledge-aware at the BASELINE shapes (E=301, F=51, V=10000), beam 5: size-independent properties."""
+    cfg = syn.BASELINE_CONFIGS["knowledge_b128"].with_batch(6)
+    dec = build_module(cfg, "cuda", torch.bfloat16).eval()
+    batch = to_dev(cfg, syn.make_batch(cfg, seed=3))
+    T = 10
+    args = (batch["encoder_out"], T, batch["entities"], batch["facts"])
+    out5, sc5 = dec.beam_search_batch(*args, beam_size=5, return_scores=True)
+    out1, sc1 = dec.beam_search_batch(*args, beam_size=1, return_scores=True)
+    greedy, margins = dec.predict_batch(*args, return_margins=True)
+    assert torch.isfinite(sc5).all() and torch.isfinite(sc1).all() and (sc5 <= 0).all()
+    assert ((out5 >= 0) & (out5 < cfg.W)).all()
+    # images are independent: a permuted batch gives the permuted captions
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    outp = dec.beam_search_batch(batch["encoder_out"][perm], T, batch["entities"][perm.cpu()], batch["facts"][perm], beam_size=5)
+    assert torch.equal(outp, out5[perm])
+    # beam 1 == greedy argmax until the first step at which predict()'s repetition clean-up fires (a repeated token)
+    for b in range(cfg.B):
+        g1, o1 = greedy[b].tolist(), out1[b].tolist()
+        n = next((t for t in range(1, T) if o1[t] == o1[t - 1]), T)
+        if float(margins[b, :n].min()) > 1e-2:
+            assert o1[:n] == g1[:n], b
+
+
 def test_size_independent_properties_at_baseline_size():
     """BASELINE config 2 (knowledge-aware, B=128 is benched; B=16 here): properties that need no oracle."""
     cfg = syn.BASELINE_CONFIGS["knowledge_b128"].with_batch(16)

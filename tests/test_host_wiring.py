@@ -112,6 +112,32 @@ def test_predict_tokens_vs_golden(variant):
     assert tuple(one.shape) == (T, 1) and one.reshape(-1).tolist() == g["predict_tokens"][0].tolist()
 
 
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_beam_search_tokens_vs_golden(variant):
+    """Extension (the reference decodes greedily): engine.beam_decode's orchestration - position-major cache + ancestor table,
+    shared image context, double-buffered histories - over the host kernels against the captions that the tutorial beam search
+    produces with the unmodified reference modules as the scoring function (tests/golden/make_golden_beam.py)."""
+    import os
+
+    import numpy as np
+
+    from helpers import GOLDEN_DIR
+
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"golden_beam_{variant}.npz")))
+    T, k, B = int(g["max_len"]), int(g["beam"]), int(g["batch"])
+    pb = syn.make_batch(cfg.with_batch(B), seed=int(g["seed"]))
+    for j, bias in enumerate(g["end_bias"].tolist()):
+        dec = build_module(cfg, "cpu").eval()
+        with torch.no_grad():
+            dec.state_dict()["fc_vocab.bias"][cfg.V - 1] += bias
+        out, score = dec.beam_search_batch(pb["encoder_out"], T, pb["entities"], pb.get("facts"), beam_size=k, return_scores=True)
+        ok = g[f"margins_{j}"] > 1e-4
+        assert ok.sum() >= B - 1
+        assert out[ok].tolist() == g[f"tokens_{j}"][ok].tolist()
+        assert np.allclose(score.numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
+
+
 def test_module_pickles_like_reference_checkpoints(tmp_path):
     cfg = syn.SMALL_CONFIGS["G"]
     dec = build_module(cfg, "cpu").eval()

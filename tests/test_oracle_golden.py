@@ -82,3 +82,41 @@ def test_indicator_predict_mode_has_no_lag():
     assert eb1[0, 0, 3] == 1 and pi1[0, 0, 3] == 1 and eb1.sum() == 1
     ebT, _ = orc.context_indicators(sp, caps, facts, cfg.E, 5)
     assert ebT.sum() == 0  # teacher-forced: only strictly later positions, and there are none
+
+
+def load_beam_golden(variant):
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    return dict(np.load(os.path.join(GOLDEN_DIR, f"golden_beam_{variant}.npz")))
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_beam_search_vs_reference_scored_golden(variant):
+    """Extension (the reference has no beam search): the oracle's beam search against captions computed with the unmodified
+    reference modules as the scoring function (tests/golden/make_golden_beam.py)."""
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_beam_golden(variant)
+    T, k = int(g["max_len"]), int(g["beam"])
+    pb = syn.make_batch(cfg.with_batch(int(g["batch"])), seed=int(g["seed"]))
+    for j, bias in enumerate(g["end_bias"].tolist()):
+        p = oracle_params(cfg)
+        p["fc_vocab.bias"][cfg.V - 1] += bias
+        with torch.no_grad():
+            for i in (0, 3, 4):
+                out, margin = orc.beam_search(spec_for(cfg), p, pb["encoder_out"][i : i + 1], T, pb["entities"][i : i + 1],
+                                              pb["facts"][i : i + 1] if cfg.has_facts else None, beam_size=k, return_margin=True)
+                assert abs(margin - float(g[f"margins_{j}"][i])) < 1e-4
+                assert out.tolist() == g[f"tokens_{j}"][i].tolist(), (j, i, margin)
+
+
+def test_beam_of_one_is_greedy_without_cleanup():
+    cfg = syn.SMALL_CONFIGS["K"]
+    g = load_golden("K")
+    p = oracle_params(cfg)
+    pb = syn.make_batch(cfg, seed=int(g["predict_seed"]))
+    with torch.no_grad():
+        out = orc.beam_search(spec_for(cfg), p, pb["encoder_out"][:1], 4, pb["entities"][:1], pb["facts"][:1], beam_size=1)
+    # step 3 repeats token 27 and predict()'s clean-up rewrites it; the first three steps are plain argmax
+    assert out.tolist()[:3] == g["predict_tokens"][0][:3].tolist() and out.tolist()[3] == out.tolist()[2]

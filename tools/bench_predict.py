@@ -23,6 +23,7 @@ ap.add_argument("--variant", default="K")
 ap.add_argument("--images", type=int, default=625)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--beam", type=int, default=0, help="0 = greedy predict(); k > 0 = beam search of width k (extension, no reference counterpart)")
 a = ap.parse_args()
 name = {"G": "geo_b32", "K": "knowledge_b128", "N": "news_b8"}[a.variant]
 cfg = syn.BASELINE_CONFIGS[name].with_batch(a.images)
@@ -41,7 +42,10 @@ enc, ent, facts = b["encoder_out"].pin_memory(), b["entities"], b.get("facts")
 
 
 def run():
-    out = dec.predict_batch(enc.cuda(non_blocking=True), Tmax, ent, facts.cuda() if facts is not None else None)
+    if a.beam:
+        out = dec.beam_search_batch(enc.cuda(non_blocking=True), Tmax, ent, facts.cuda() if facts is not None else None, beam_size=a.beam)
+    else:
+        out = dec.predict_batch(enc.cuda(non_blocking=True), Tmax, ent, facts.cuda() if facts is not None else None)
     return out.cpu()
 
 
@@ -63,9 +67,12 @@ spec = orc.Spec(cfg.variant, cfg.V, cfg.D, cfg.H, cfg.L, pad=0, start=cfg.V - 2,
 torch.set_num_threads(os.cpu_count())
 t0 = time.perf_counter()
 with torch.no_grad():
-    ref = orc.predict(spec, p, b["encoder_out"][:1], Tmax, ent[:1], facts[:1] if facts is not None else None)
+    if a.beam:
+        ref = orc.beam_search(spec, p, b["encoder_out"][:1], Tmax, ent[:1], facts[:1] if facts is not None else None, beam_size=a.beam)
+    else:
+        ref = orc.predict(spec, p, b["encoder_out"][:1], Tmax, ent[:1], facts[:1] if facts is not None else None)
 cpu_sec = time.perf_counter() - t0
-print(json.dumps({"metric": "greedy_captions_per_sec", "value": a.images / sec, "unit": "captions/s", "n_gpus": 1, "variant": a.variant,
+print(json.dumps({"metric": f"beam{a.beam}_captions_per_sec" if a.beam else "greedy_captions_per_sec", "value": a.images / sec, "unit": "captions/s", "n_gpus": 1, "variant": a.variant,
                   "images": a.images, "max_len": Tmax, "dtype": a.dtype, "sec": sec, "mean_generated_len": float(lens.mean()),
                   "first_image_matches_cpu_port": out[0].tolist() == ref.reshape(-1).tolist(),
                   "cpu_port": {"captions_per_sec": 1.0 / cpu_sec, "cores": os.cpu_count(), "sample": "1 image, batch 1, full re-decode per step"}}))

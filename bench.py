@@ -363,7 +363,7 @@ def run_ours(a):
     # ---- greedy caption generation (BASELINE configs[3]: 5k images over 8 GPUs = 625 images per GPU, no communication) ---------------
     # The reference has no beam search; its eval path is the batch-1 greedy predict() with the repetition
     # clean-up, which predict_batch runs device-resident for the whole shard.  Host inputs, D2H of the tokens, 40 steps.
-    decode = None
+    decode = beam = None
     if not a.no_decode:
         try:
             n_img, t_max = 625, 40
@@ -392,9 +392,33 @@ def run_ours(a):
                       "images_per_gpu": n_img, "max_len": t_max, "sec_per_shard": float(dt_dec),
                       "mean_generated_len": float((toks != 0).sum(1).float().mean()),
                       "note": "greedy predict() + repetition clean-up (the reference has no beam search), KV-cached, device-resident loop"}
+            # beam-5 (BASELINE.json's "beam-5 captions/sec"): an EXTENSION - the reference has no beam search, so this figure has
+            # no reference arm; same shard, same host inputs / token read-back, the tutorial's beam search device-resident
+            def beam_once():
+                return dec.beam_search_batch(d_enc.to(dev, non_blocking=True), t_max, d_ent,
+                                             d_facts.to(dev, non_blocking=True) if d_facts is not None else None, beam_size=5).cpu()
+
+            beam_once()
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                btoks = beam_once()
+            sync_all()
+            dt_beam = torch.tensor([(time.perf_counter() - t0) / reps], device=dev)
+            if distributed:
+                dist.all_reduce(dt_beam, op=dist.ReduceOp.MAX)
+            beam = {"metric": "beam5_captions_per_sec", "value": n_img * world / float(dt_beam), "unit": "captions/s",
+                    "images_per_gpu": n_img, "beam": 5, "max_len": t_max, "sec_per_shard": float(dt_beam),
+                    "mean_generated_len": float((btoks != 0).sum(1).float().mean()),
+                    "note": "extension without a reference counterpart (SURVEY.md §0): Show-Attend-Tell tutorial beam search over the "
+                            "KV-cached decoder, device-resident; parity against oracle/decoder_oracle.py:beam_search and captions "
+                            "scored by the unmodified reference modules (tests/golden/golden_beam_*.npz)"}
             dec.train()
-        except Exception as e:  # the decode figure is an extra; never lose the train line over it
-            decode = {"error": f"{type(e).__name__}: {e}"}
+        except Exception as e:  # the decode figures are extras; never lose the train line over them
+            if decode is None:
+                decode = {"error": f"{type(e).__name__}: {e}"}
+            else:
+                beam = {"error": f"{type(e).__name__}: {e}"}
             dec.train()
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------------------
@@ -418,6 +442,7 @@ def run_ours(a):
             "roofline": roof,
             "cpu_baseline": cpu,
             "greedy_decode": decode,
+            "beam5_decode": beam,
             "trimmed_padding": trimmed,
             "kept_tokens": float(loss_acc[1]),
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),

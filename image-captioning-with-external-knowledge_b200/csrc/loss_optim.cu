@@ -229,66 +229,51 @@ __device__ __forceinline__ void beam_insert(float (&v)[G], int (&ix)[G], float x
     }
 }
 
+// stage 1, one CTA per (image, beam slot): log-sum-exp of the row and its G best columns, as candidates cum + log_softmax
 template <int G>
-__global__ void __launch_bounds__(256) beam_select_kernel(const float* __restrict__ scores, int W, int lds, float* __restrict__ cum,
-                                                          int* __restrict__ ksel, const long long* __restrict__ tok_in,
-                                                          const long long* __restrict__ mask_in, long long* __restrict__ tok_out,
-                                                          long long* __restrict__ mask_out, const int* __restrict__ anc_in,
-                                                          int* __restrict__ anc_out, float* __restrict__ best, long long* __restrict__ result,
-                                                          int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok) {
+__global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restrict__ scores, int W, int lds, const float* __restrict__ cum,
+                                                            const int* __restrict__ ksel, float* __restrict__ cand_v, int* __restrict__ cand_i,
+                                                            int step) {
     ick_pdl_entry();
     __shared__ float red_m[8], red_l[8], red_v[8];
     __shared__ int red_i[8];
-    __shared__ float sel_v[G];
-    __shared__ int sel_i[G], sel_slot[G];
-    __shared__ int s_nalive, s_bestr;
     __shared__ float s_logz;
-    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int s_win;
+    const int row = blockIdx.x, img = row / G, j = row % G, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = ksel[img];
-    if (k <= 0) return;
-    const int nrows = step == 0 ? 1 : k;
-    float gv[G];
-    int gi[G];
+    if (k <= 0 || j >= (step == 0 ? 1 : k)) return;  // not a live beam
+    const float* s = scores + (size_t)row * lds;
+    float rm = -INFINITY, rl = 0.f, rv[G];
+    int ri[G];
 #pragma unroll
-    for (int a = 0; a < G; ++a) { gv[a] = -INFINITY; gi[a] = 0x7fffffff; }
-    for (int j = 0; j < nrows; ++j) {
-        const float* s = scores + (size_t)(img * G + j) * lds;
-        float rm = -INFINITY, rl = 0.f, rv[G];
-        int ri[G];
-#pragma unroll
-        for (int a = 0; a < G; ++a) { rv[a] = -INFINITY; ri[a] = 0x7fffffff; }
-        for (int c = tid; c < W; c += 256) {
-            const float x = s[c];
-            if (x > rm) {
-                rl = rl * expf(rm - x) + 1.f;
-                rm = x;
-            } else {
-                rl += expf(x - rm);
-            }
-            beam_insert<G>(rv, ri, x, c);
+    for (int a = 0; a < G; ++a) { rv[a] = -INFINITY; ri[a] = 0x7fffffff; }
+    for (int c = tid; c < W; c += 256) {
+        const float x = s[c];
+        if (x > rm) {
+            rl = rl * expf(rm - x) + 1.f;
+            rm = x;
+        } else {
+            rl += expf(x - rm);
         }
-        // block log-sum-exp
-        float wm = warp_max(rm);
-        float wl = warp_sum(rm == -INFINITY ? 0.f : rl * expf(rm - wm));
-        if (lane == 0) { red_m[wid] = wm; red_l[wid] = wl; }
-        __syncthreads();
-        if (tid == 0) {
-            float M = red_m[0];
-            for (int w = 1; w < 8; ++w) M = fmaxf(M, red_m[w]);
-            float L = 0.f;
-            for (int w = 0; w < 8; ++w) L += red_m[w] == -INFINITY ? 0.f : red_l[w] * expf(red_m[w] - M);
-            s_logz = M + logf(L);
-        }
-        __syncthreads();
-        const float logz = s_logz, cj = cum[img * G + j];
-#pragma unroll
-        for (int a = 0; a < G; ++a)
-            if (ri[a] != 0x7fffffff) beam_insert<G>(gv, gi, cj + (rv[a] - logz), j * W + ri[a]);
+        beam_insert<G>(rv, ri, x, c);
     }
-    // the k best of the block, one per round: every thread offers the head of its own sorted list
-    for (int r = 0; r < k; ++r) {
-        float v = gv[0];
-        int i = gi[0];
+    const float wm = warp_max(rm);
+    const float wl = warp_sum(rm == -INFINITY ? 0.f : rl * expf(rm - wm));
+    if (lane == 0) { red_m[wid] = wm; red_l[wid] = wl; }
+    __syncthreads();
+    if (tid == 0) {
+        float M = red_m[0];
+        for (int w = 1; w < 8; ++w) M = fmaxf(M, red_m[w]);
+        float L = 0.f;
+        for (int w = 0; w < 8; ++w) L += red_m[w] == -INFINITY ? 0.f : red_l[w] * expf(red_m[w] - M);
+        s_logz = M + logf(L);
+    }
+    __syncthreads();
+    const float logz = s_logz, cj = cum[row];
+    // the G best of the row, one per round: every thread offers the head of its own sorted list
+    for (int r = 0; r < G; ++r) {
+        float v = rv[0];
+        int i = ri[0];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
@@ -300,18 +285,58 @@ __global__ void __launch_bounds__(256) beam_select_kernel(const float* __restric
         if (tid == 0) {
             for (int w = 1; w < 8; ++w)
                 if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) { v = red_v[w]; i = red_i[w]; }
-            sel_v[r] = v;
-            sel_i[r] = i;
+            s_win = i;
+            cand_v[(size_t)row * G + r] = i == 0x7fffffff ? -INFINITY : cj + (v - logz);
+            cand_i[(size_t)row * G + r] = i == 0x7fffffff ? i : j * W + i;
         }
         __syncthreads();
-        if (gi[0] == sel_i[r] && sel_i[r] != 0x7fffffff) {  // the winner pops its head
+        if (ri[0] == s_win && s_win != 0x7fffffff) {  // the winner pops its head
 #pragma unroll
-            for (int a = 0; a + 1 < G; ++a) { gv[a] = gv[a + 1]; gi[a] = gi[a + 1]; }
-            gv[G - 1] = -INFINITY;
-            gi[G - 1] = 0x7fffffff;
+            for (int a = 0; a + 1 < G; ++a) { rv[a] = rv[a + 1]; ri[a] = ri[a + 1]; }
+            rv[G - 1] = -INFINITY;
+            ri[G - 1] = 0x7fffffff;
         }
     }
+}
+
+// stage 2, one CTA per image: the k best of the live rows' candidate lists (each sorted), then the beam bookkeeping
+template <int G>
+__global__ void __launch_bounds__(64) beam_select_kernel(const float* __restrict__ cand_v, const int* __restrict__ cand_i, int W,
+                                                         float* __restrict__ cum, int* __restrict__ ksel, const long long* __restrict__ tok_in,
+                                                         const long long* __restrict__ mask_in, long long* __restrict__ tok_out,
+                                                         long long* __restrict__ mask_out, const int* __restrict__ anc_in,
+                                                         int* __restrict__ anc_out, float* __restrict__ best, long long* __restrict__ result,
+                                                         int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok) {
+    ick_pdl_entry();
+    __shared__ float sel_v[G];
+    __shared__ int sel_i[G], sel_slot[G];
+    __shared__ int s_bestr, s_k;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_k = ksel[img];  // thread 0 rewrites ksel[img] below: everybody takes k from this one read
+    __syncthreads();
+    const int k = s_k;
+    if (k <= 0) return;
+    const int nrows = step == 0 ? 1 : k;
     if (tid == 0) {
+        int head[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) head[j] = 0;
+        for (int r = 0; r < k; ++r) {  // merge of nrows sorted lists; ties: lower (row, column)
+            float bv = -INFINITY;
+            int bi = 0x7fffffff, bj = -1;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (j >= nrows || head[j] >= G) continue;
+                const float v = cand_v[(size_t)(img * G + j) * G + head[j]];
+                const int i = cand_i[(size_t)(img * G + j) * G + head[j]];
+                if (bj < 0 || v > bv || (v == bv && i < bi)) { bv = v; bi = i; bj = j; }
+            }
+            sel_v[r] = bv;
+            sel_i[r] = bi;
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+                if (j == bj) ++head[j];
+        }
         int nalive = 0, bestr = -1;
         float bv = best[img];
         for (int r = 0; r < k; ++r) {
@@ -327,13 +352,12 @@ __global__ void __launch_bounds__(256) beam_select_kernel(const float* __restric
             for (int r = 0; r < k; ++r)
                 if (sel_slot[r] == 0) { bv = sel_v[r]; bestr = r; }
         best[img] = bv;
-        s_nalive = nalive;
         s_bestr = bestr;
         ksel[img] = nalive;
     }
     __syncthreads();
     const int hist = step + 1;  // positions 0..step of the parent's history
-    for (int e = tid; e < k * hist; e += 256) {
+    for (int e = tid; e < k * hist; e += 64) {
         const int r = e / hist, t = e % hist, slot = sel_slot[r];
         if (slot < 0) continue;
         const size_t src = (size_t)(img * G + sel_i[r] / W) * Tmax + t, dst = (size_t)(img * G + slot) * Tmax + t;
@@ -355,7 +379,7 @@ __global__ void __launch_bounds__(256) beam_select_kernel(const float* __restric
     const int bestr = s_bestr;
     if (bestr >= 0) {
         const size_t src = (size_t)(img * G + sel_i[bestr] / W) * Tmax;
-        for (int t = tid; t < Tmax; t += 256)
+        for (int t = tid; t < Tmax; t += 64)
             result[(size_t)img * Tmax + t] = t < step ? tok_in[src + t + 1] : (t == step ? (long long)(sel_i[bestr] % W) : (long long)pad_tok);
     }
 }
@@ -463,15 +487,20 @@ extern "C" int ick_greedy_select(const float* scores, int W, int lds, long long*
 extern "C" int ick_beam_select(const float* scores, int W, int lds, float* cum, int* ksel, const long long* tok_in,
                                const long long* mask_in, long long* tok_out, long long* mask_out, const int* anc_in, int* anc_out,
                                float* best, long long* result, int images, int group, int step, int Tmax, int V, int E, int has_facts,
-                               int end_tok, int pad_tok, cudaStream_t stream) {
+                               int end_tok, int pad_tok, void* workspace, long long workspace_bytes, cudaStream_t stream) {
     ICK_REQUIRE(images >= 0 && step >= 0 && step < Tmax && W >= 2, "beam_select: bad sizes");
     ICK_REQUIRE(group >= 1 && group <= 8 && (long long)group * W < 0x7fffffffLL, "beam_select: group=%d out of range", group);
     ICK_REQUIRE(tok_in != tok_out && mask_in != mask_out && anc_in != anc_out, "beam_select: histories must be double-buffered");
+    const long long ncand = (long long)images * group * group;
+    ICK_REQUIRE(workspace != nullptr && workspace_bytes >= ncand * 8, "beam_select: workspace of %lld bytes needed", ncand * 8);
     if (images == 0) return ICK_OK;
-#define ICK_BEAM_SEL(GG)                                                                                                              \
-    case GG:                                                                                                                          \
-        ick_launch(beam_select_kernel<GG>, images, 256, 0, stream)(scores, W, lds, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, \
-                                                                    anc_out, best, result, step, Tmax, V, E, has_facts, end_tok, pad_tok); \
+    float* cand_v = (float*)workspace;
+    int* cand_i = (int*)(cand_v + ncand);
+#define ICK_BEAM_SEL(GG)                                                                                                               \
+    case GG:                                                                                                                           \
+        ick_launch(beam_row_topk_kernel<GG>, images * GG, 256, 0, stream)(scores, W, lds, cum, ksel, cand_v, cand_i, step);              \
+        ick_launch(beam_select_kernel<GG>, images, 64, 0, stream)(cand_v, cand_i, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, \
+                                                                   anc_out, best, result, step, Tmax, V, E, has_facts, end_tok, pad_tok); \
         break;
     switch (group) {
         ICK_BEAM_SEL(1)

@@ -12,6 +12,7 @@ torch is used here for device memory and streams only; every arithmetic step is 
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace as NS
 from typing import Dict, Optional
 
@@ -663,6 +664,9 @@ class DecoderEngine:
         x0 = self._new(R, DP)
         bufs = [NS(o=self._new(R, DP), s=self._new(R, DP), y1=self._new(R, DP), q=self._new(R, DP), y2=self._new(R, DP),
                    h1=self._new(R, self.lin[f"transformer_decoder.layers.{l}.ffn1"].lin.Np), y3=self._new(R, DP)) for l in range(L)]
+        xattn_flash = os.environ.get("ICK_BEAM_XATTN", "flash") == "flash" and self.dtype != torch.float32
+        lse = self._newf(NI * H * G)
+        cand = self._newf(R * G * 2)  # per-row candidate lists of beam_select
         for i in range(Tmax):
             cur, nxt = i & 1, (i + 1) & 1
             K.caption_embed_fwd(tok[cur], msk[cur], self.wemb, ctx.ent_enc, ctx.fact_enc, self.pe, x0, R, Tmax, i, 1, V, E, F, D,
@@ -681,8 +685,11 @@ class DecoderEngine:
                 K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
                 K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
                 K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
-                K.mha_decode_beam(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, R, G, H, dh, M,
-                                  kimg_stride=M * kvw, vimg_stride=M * kvw)
+                if xattn_flash:  # the G beams of an image are G query positions of one flash-attention item over its memory
+                    K.mha_fwd(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, lse, NI, H, G, M, dh)
+                else:
+                    K.mha_decode_beam(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, R, G, H, dh,
+                                      M, kimg_stride=M * kvw, vimg_stride=M * kvw)
                 K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
                 K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
                 K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
@@ -691,5 +698,5 @@ class DecoderEngine:
                 x = b.y3
             self._heads_fwd(ctx, tok[cur], x, scores, R, 1, i, Tmax, E, F, lag=1, group=G)
             K.beam_select(scores, W, cum, ksel, tok[cur], msk[cur], tok[nxt], msk[nxt], anc[cur], anc[nxt], best, result, NI, G, i, Tmax,
-                          V, E, self.has_facts, self.end, self.pad)
+                          V, E, self.has_facts, self.end, self.pad, workspace=cand)
         return result, best

@@ -349,6 +349,9 @@ class CudaKernels:
                    _p(margins), B, step, Tmax, V, E, int(has_facts), end_tok)
 
     def beam_select(self, scores, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, anc_out, best, result, images, group, step,
-                    Tmax, V, E, has_facts, end_tok, pad_tok):
+                    Tmax, V, E, has_facts, end_tok, pad_tok, workspace=None):
+        if workspace is None:
+            workspace = torch.empty(images * group * group * 2, dtype=torch.float32, device=scores.device)
         self._call("ick_beam_select", _p(scores), W, _ld(scores), _p(cum), _p(ksel), _p(tok_in), _p(mask_in), _p(tok_out), _p(mask_out),
-                   _p(anc_in), _p(anc_out), _p(best), _p(result), images, group, step, Tmax, V, E, int(has_facts), end_tok, pad_tok)
+                   _p(anc_in), _p(anc_out), _p(best), _p(result), images, group, step, Tmax, V, E, int(has_facts), end_tok, pad_tok,
+                   _p(workspace), workspace.numel() * workspace.element_size(), n=2)

@@ -203,11 +203,13 @@ int ick_mha_decode_beam(const void* Q, const void* K, const void* V, void* O, in
  * (kept in result/best if it beats the best completed one; k decreases), the others become beams 0..k'-1: histories
  * tok/mask/anc (rows of Tmax) are copied parent -> new slot from *_in to *_out and extended at position step+1 with the token,
  * its mask class (0 word, 1 entity, 2 fact) and the slot itself; cum is updated in place.  result (images, Tmax): tokens
- * without <start>, <end> included, pad-filled.  At the last step an image without a completed caption takes its best live beam. */
+ * without <start>, <end> included, pad-filled.  At the last step an image without a completed caption takes its best live beam.
+ * Two launches: per live row the log-sum-exp and its `group` best columns (HBM-bound pass over the scores), then per image the
+ * merge and the bookkeeping.  workspace: images*group*group*8 bytes of scratch for the per-row candidates. */
 int ick_beam_select(const float* scores, int W, int lds, float* cum, int* ksel, const long long* tok_in, const long long* mask_in,
                     long long* tok_out, long long* mask_out, const int* anc_in, int* anc_out, float* best, long long* result,
-                    int images, int group, int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok,
-                    cudaStream_t stream);
+                    int images, int group, int step, int Tmax, int V, int E, int has_facts, int end_tok, int pad_tok, void* workspace,
+                    long long workspace_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -551,7 +551,7 @@ class HostKernels:
                 masks[b, step + 1] = 2 if (has_facts and o >= V + E) else (1 if o >= V else 0)
 
     def beam_select(self, scores, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, anc_out, best, result, images, group, step,
-                    Tmax, V, E, has_facts, end_tok, pad_tok):
+                    Tmax, V, E, has_facts, end_tok, pad_tok, workspace=None):
         self.calls += 1
         G = group
         for img in range(images):

@@ -6,6 +6,8 @@
 //   context indicators  K/models.py:380-418 as a first-mention scan (no B*T host syncs) + predicate gate K:436-437
 //   pointer heads       fc_entity / fc_fact as a bilinear form, K/models.py:440-452 (no (T,B,E,300) tensor)
 // Row layout everywhere: (batch, position) rows of `ld` elements, logical width D, pad columns [D, ld) zero.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "pointer_internal.h"
 #include "ickb200.h"
@@ -781,6 +783,15 @@ extern "C" int ick_pred_gate_bwd(const void* dG, const int* tmin, const long lon
     return ick_check_launch("pred_gate_bwd");
 }
 
+static bool ptr_decode_mma() {  // ICK_PTR_DECODE_MMA=0: single-step pointer scores on the CUDA-core kernel (A/B aid)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_PTR_DECODE_MMA");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores,
                                int dt, int B, int Tn, int t0, int S, int D, int ld, int ldscores, int col0, int lag, int group,
                                cudaStream_t stream) {
@@ -789,6 +800,10 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
     if (B * Tn * S == 0) return ICK_OK;
     if (group > 1) {  // beam decode: `group` consecutive rows are the beams of one image (one time step each)
         ICK_REQUIRE(Tn == 1 && group <= 8, "pointer_fwd: group=%d needs Tn == 1 and group <= 8", group);
+        if (dt == ICK_BF16) {  // per-image (group x S x D) GEMM on the tensor cores: the ctx rows are staged with coalesced 16-byte loads
+            const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B / group, group, t0, S, D, ld, ldscores, col0, lag, 1, stream);
+            if (rc != ICK_ERR_UNSUPPORTED) return rc;
+        }
         const int Dp8 = (D + 7) & ~7;
         const size_t smemb = (size_t)8 * Dp8 * sizeof(float);
         dim3 gridb((S + 127) / 128, 1, B / group);
@@ -802,10 +817,14 @@ extern "C" int ick_pointer_fwd(const void* h, const void* ctx, const float* w, c
         return ick_check_launch("pointer_fwd");
     }
     if (dt == ICK_BF16 && Tn >= 16) {  // tensor-core path (teacher-forced forward); single-step decode stays on the CUDA cores
-        const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, ld, ldscores, col0, lag, stream);
+        const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, ld, ldscores, col0, lag, 0, stream);
         if (rc != ICK_ERR_UNSUPPORTED) return rc;
     }
     const int Dp = (D + 7) & ~7;
+    if (Tn == 1 && dt == ICK_BF16 && ptr_decode_mma()) {  // greedy decode, bf16: same tensor-core kernel, ctx rows staged coalesced
+        const int rc = ick_pointer_fwd_mma(h, ctx, w, bias, first_t, scores, B, Tn, t0, S, D, ld, ldscores, col0, lag, 0, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     if (Tn == 1) {  // greedy decode: one time step per image - no 16-step register tile, the ctx rows stream through
         const size_t smem1 = (size_t)Dp * sizeof(float);
         dim3 grid1((S + 127) / 128, 1, B);

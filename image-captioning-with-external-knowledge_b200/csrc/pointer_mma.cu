@@ -40,7 +40,8 @@ __device__ __forceinline__ void b_frag_kn(uint32_t* r, const bf16* tile, int ld,
 __global__ void __launch_bounds__(NT) pointer_fwd_mma_kernel(const bf16* __restrict__ h, const bf16* __restrict__ ctx, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const int* __restrict__ first_t,
                                                              float* __restrict__ scores, int Tn, int t0, int S, int D, int ld, int lds,
-                                                             int col0, int lag, int Tp, int KP) {
+                                                             int col0, int lag, int Tp, int KP, int beams) {
+    // beams != 0 (beam-search decode): the Tn rows of image b are its beams at the same time step t0 - one first_t row each
     ick_pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
     const int PLD = KP + 8;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(NT) pointer_fwd_mma_kernel(const bf16* __restr
             for (int x = 0; x < 4; ++x) {
                 const int t = 16 * mt + g + (x >> 1) * 8, s = s0 + 8 * j + 2 * tq + (x & 1);
                 if (t < Tn && s < S) {
-                    const bool on = first_t == nullptr || first_t[(size_t)b * S + s] < t0 + t + lag;
+                    const bool on = first_t == nullptr || (beams ? first_t[((size_t)b * Tn + t) * S + s] < t0 + lag
+                                                                 : first_t[(size_t)b * S + s] < t0 + t + lag);
                     scores[((size_t)b * Tn + t) * lds + col0 + s] = (on ? acc[j][x] : 0.f) + bv;
                 }
             }
@@ -302,7 +304,7 @@ int set_smem(K kernel) {
 }  // namespace
 
 int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores, int B, int Tn,
-                        int t0, int S, int D, int ld, int ldscores, int col0, int lag, cudaStream_t stream) {
+                        int t0, int S, int D, int ld, int ldscores, int col0, int lag, int beams, cudaStream_t stream) {
     const int Tp = (Tn + 15) / 16 * 16, KP = (D + 15) / 16 * 16;
     const size_t smem = (size_t)(Tp + CW) * (KP + 8) * 2;
     if (KP > ld || ld % 8 != 0 || smem > SMEM_MAX || (((uintptr_t)h | (uintptr_t)ctx) & 15) != 0) return ICK_ERR_UNSUPPORTED;
@@ -310,7 +312,7 @@ int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const fl
     if (rc) return rc;
     dim3 grid((S + CW - 1) / CW, B);
     ick_launch(pointer_fwd_mma_kernel, grid, NT, smem, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, Tn, t0, S, D, ld, ldscores,
-                                                       col0, lag, Tp, KP);
+                                                       col0, lag, Tp, KP, beams);
     return ick_check_launch("pointer_fwd_mma");
 }
 

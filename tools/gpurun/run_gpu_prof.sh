@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-R=r71
+R=r73
 ICKB200_DECODE_GRAPH=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 600 -c 200 --csv --log-file gpurun_out/${R}_beam_launches.csv python tools/bench_predict.py --variant K --beam 5 --reps 1 > gpurun_out/${R}_ncu1.log 2>&1
 tail -n 1 gpurun_out/${R}_ncu1.log | cut -c1-120
-(timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3) > gpurun_out/${R}_smoke.log; cat gpurun_out/${R}_smoke.log

@@ -182,6 +182,148 @@ def run_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
+def run_encoder_e2e(a, steps=None, warmup=None, quiet=False):
+    """
+    BASELINE.json configs[4]: geo-aware END TO END - raw fp16 image batch (the HDF5 storage format) -> ick_image_prep ->
+    ResNet-101 trunk (stock torchvision / cuDNN, bf16 channels-last, frozen and in eval mode as the reference trains it,
+    G/train.py:52, random init: no network for the ImageNet weights) -> Encoder hand-off kernels (pool + conv1 as tcgen05 GEMM +
+    transpose) -> fused decoder train step.  `value`: images resident in HBM; `e2e`: every step copies its raw images and
+    caption tensors from pinned host memory (prefetched on a copy stream) and reads the loss back.
+    """
+    import torch.distributed as dist
+
+    from ickb200 import _lib
+    from ickb200.data import prepare_images
+    from ickb200.geo_aware import Encoder
+    from ickb200.trainer import Trainer
+
+    steps = steps or a.steps
+    warmup = a.warmup if warmup is None else warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = syn.BASELINE_CONFIGS["geo_e2e_b256"]
+    if a.batch:
+        cfg = cfg.with_batch(a.batch)
+    torch.backends.cudnn.benchmark = True  # G/train.py:19
+    dec = build_decoder(cfg, dev, torch.bfloat16)
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=not a.no_graph)
+    K = tr.eng.K
+    lib = _lib.get()
+    enc = Encoder(pretrained=False, compute_dtype=torch.bfloat16).to(dev).eval()
+    enc.resnet.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    hb = host_batch(cfg, seed=rank, pin=True)
+    S = 256  # G/create_input_files.py: images are resized to 256 x 256
+    raw_host = (torch.rand(cfg.B, 3, S, S, generator=torch.Generator().manual_seed(rank)) * 255).half().pin_memory()
+    names = ("captions", "caption_masks", "caption_lengths", "entities")
+    h2d_bytes = raw_host.numel() * 2 + sum(hb[k].numel() * hb[k].element_size() for k in names)
+
+    def sync_all():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def full_step(raw, caps, masks, lens, ents):
+        with torch.no_grad():
+            x = prepare_images(raw, torch.bfloat16, channels_last=True, kernels=K)
+            encoder_out = enc.head(enc.resnet(x))
+        return tr.train_step(caps, encoder_out, masks, lens, ents)
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    resident = [raw_host.to(dev)] + [hb[k].to(dev) for k in names]
+    full_step(*resident)
+    sampler = ClockSampler(local) if rank == 0 and not quiet else None
+    for _ in range(warmup):
+        full_step(*resident)
+    l0 = lib.launches
+    ms = timed(lambda: full_step(*resident), steps)
+    value = cfg.B * world * steps / (ms / 1e3)
+
+    # end to end: host buffers, copy-stream prefetch of step i+1 under step i, loss read back every step
+    main, cs = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    host_acc = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def stage():
+        with torch.cuda.stream(cs):
+            d = [raw_host.to(dev, non_blocking=True)] + [hb[k].to(dev, non_blocking=True) for k in names]
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return d, ev
+
+    def e2e_loop(n):
+        nxt = stage()
+        for i in range(n):
+            d, ev = nxt
+            main.wait_event(ev)
+            for t in d:
+                t.record_stream(main)
+            if i + 1 < n:
+                nxt = stage()
+            host_acc.copy_(full_step(*d), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(2)
+    ms_e2e = timed(lambda: e2e_loop(steps), 1)
+    e2e_value = cfg.B * world * steps / (ms_e2e / 1e3)
+    clocks = sampler.stop() if sampler else None
+
+    # where the step goes (CUDA events, a few iterations each, same tensors)
+    with torch.no_grad():
+        x = prepare_images(resident[0], torch.bfloat16, channels_last=True, kernels=K)
+        feats = enc.resnet(x)
+        eo = enc.head(feats)
+        t_prep = timed(lambda: prepare_images(resident[0], torch.bfloat16, channels_last=True, kernels=K), 5) / 5
+        t_trunk = timed(lambda: enc.resnet(x), 5) / 5
+        t_head = timed(lambda: enc.head(feats), 5) / 5
+    t_dec = timed(lambda: tr.train_step(resident[1], eo, *resident[2:]), 5) / 5
+    pk = peaks()
+    prep_bytes = resident[0].numel() * 4  # fp16 in, bf16 out
+    line = {
+        "metric": "encoder_decoder_train_captions_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"geo-aware end to end (BASELINE configs[4]): raw fp16 images (B,3,{S},{S}) -> image prep -> ResNet-101 trunk "
+                               f"(torchvision/cuDNN, bf16 channels-last, frozen, random init) -> Encoder hand-off -> decoder train step; "
+                               f"per-GPU batch {cfg.B}, T={cfg.T} E={cfg.E} V={cfg.V}",
+                   "global_batch": cfg.B * world, "parallelism": f"dp{world}", "cuda_graph": "decoder step" if tr.use_graph else "off",
+                   "l2": "no explicit flush: a step streams several GB of activations"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
+        "gpu_launches": (lib.launches - l0),
+        "breakdown_ms": {"image_prep": t_prep, "resnet101_trunk_cudnn": t_trunk, "encoder_handoff": t_head, "decoder_train_step": t_dec},
+        "roofline_image_prep": {"bound": "hbm", "achieved": prep_bytes / (t_prep / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": prep_bytes / (t_prep / 1e3) / 1e9 / pk["hbm"], "peak_source": pk["src"]},
+        "loss": float(tr.loss_acc[0] / tr.loss_acc[1].clamp_min(1)),
+    }
+    if distributed and not quiet:
+        tr._graph, tr._graphs = None, {}
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    if quiet:
+        tr._graph, tr._graphs = None, {}
+        return line
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch.distributed as dist
 
@@ -421,6 +563,17 @@ def run_ours(a):
                 beam = {"error": f"{type(e).__name__}: {e}"}
             dec.train()
 
+    # ---- geo-aware end to end with the ResNet-101 trunk (BASELINE configs[4]), N = 1 only; `--workload geo_e2e_b256` runs it at any N ----
+    enc_extra = None
+    if world == 1 and not a.no_encoder_extra and a.workload == CFG_NAME:
+        try:
+            enc_extra = run_encoder_e2e(a, steps=10, warmup=3, quiet=True)
+            for k in ("steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "data", "clocks", "n_gpus"):
+                enc_extra.pop(k, None)
+        except Exception as e:
+            enc_extra = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -443,6 +596,7 @@ def run_ours(a):
             "cpu_baseline": cpu,
             "greedy_decode": decode,
             "beam5_decode": beam,
+            "encoder_e2e": enc_extra,
             "trimmed_padding": trimmed,
             "kept_tokens": float(loss_acc[1]),
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),
@@ -472,12 +626,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode extra")
     ap.add_argument("--no-trim-extra", action="store_true", help="skip the dynamic-padding extra")
+    ap.add_argument("--no-encoder-extra", action="store_true", help="skip the end-to-end-with-ResNet-101 extra (N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph", action="store_true", help="(default since the N = 2 and N = 8 runs of profiles/) capture the step, incl. the NCCL all-reduce")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "geo_e2e_b256":
+        run_encoder_e2e(a)
     else:
         run_ours(a)
 

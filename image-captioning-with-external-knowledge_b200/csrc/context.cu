@@ -8,6 +8,8 @@
 // Row layout everywhere: (batch, position) rows of `ld` elements, logical width D, pad columns [D, ld) zero.
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "pointer_internal.h"
 #include "ickb200.h"
@@ -327,6 +329,47 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
         for (int yy = 0; yy < w.z; ++yy)
             for (int xx = 0; xx < w.y; ++xx) acc += pl[w.x + yy * Win + xx];
         rows[((size_t)b * nout + o) * ldo + c0 + c] = from_f<T>(acc * inv[o]);
+    }
+}
+
+// ---- image preparation (the input pipeline's device half) ------------------------------------------------------
+// The HDF5 files hold images as fp16 (N, 3, H, W) with values in [0, 255] (G/create_input_files.py:99-101, :334-337);
+// CaptionDataset.__getitem__ divides by 255 (numpy fp16 array / python float -> fp16 result), converts to fp32
+// (G/datasets.py:44) and train.py's transform normalises per channel with the ImageNet mean / std (G/train.py:139-141,
+// torchvision Normalize: sub then div in fp32).  Here the raw fp16 batch is copied to the device as stored and one kernel does
+//   y = (float(half(float(raw) / 255)) - mean[c]) / std[c]
+// - the same roundings, so the fp32 output is bit-identical - written as fp32 / bf16 in NCHW or NHWC (channels-last, the
+// layout the cuDNN trunk prefers).  HBM-bound: 2 bytes in, 2-4 bytes out per element; a thread handles 8 pixels of all 3 planes.
+template <typename T>
+__global__ void __launch_bounds__(256) image_prep_kernel(const __half* __restrict__ raw, T* __restrict__ out, long long npix8, int HW,
+                                                         float m0, float m1, float m2, float s0, float s1, float s2, int nhwc) {
+    ick_pdl_entry();
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    const int hw8 = HW / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix8; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / hw8;
+        const int p = (int)(i % hw8) * 8;
+        float v[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(raw + ((size_t)n * 3 + c) * HW + p);
+            const __half* hh = reinterpret_cast<const __half*>(&u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[c][k] = (__half2float(__float2half_rn(__half2float(hh[k]) / 255.0f)) - mean[c]) / sd[c];
+        }
+        if (!nhwc) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st8(out + ((size_t)n * 3 + c) * HW + p, v[c]);
+        } else {
+            float w[24];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) w[3 * k + c] = v[c][k];
+            T* o = out + ((size_t)n * HW + p) * 3;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) st8(o + 8 * q, w + 8 * q);
+        }
     }
 }
 
@@ -884,4 +927,22 @@ extern "C" int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int 
     else if (dt == ICK_BF16) ick_launch(pool_rows_kernel<bf16>, grid, 256, smem, stream)(x, (bf16*)rows, C, Hin, Win, Hout, Wout, ldo);
     else ICK_BAD_DT("pool_rows_fwd", dt);
     return ick_check_launch("pool_rows_fwd");
+}
+
+extern "C" int ick_image_prep(const void* raw_f16, void* out, int dt, long long N, int C, int HW, const float* mean, const float* stdev,
+                              int channels_last, cudaStream_t stream) {
+    ICK_REQUIRE(C == 3 && HW > 0 && HW % 8 == 0 && N >= 0, "image_prep: needs 3 channels and H*W a multiple of 8 (C=%d, HW=%d)", C, HW);
+    ICK_REQUIRE((((uintptr_t)raw_f16 | (uintptr_t)out) & 31) == 0, "image_prep: buffers must be 32-byte aligned");
+    if (N == 0) return ICK_OK;
+    const long long npix8 = N * (HW / 8);
+    const long long want = (npix8 + 255) / 256;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    if (dt == ICK_F32)
+        ick_launch(image_prep_kernel<float>, grid, 256, 0, stream)((const __half*)raw_f16, (float*)out, npix8, HW, mean[0], mean[1], mean[2], stdev[0],
+                                                           stdev[1], stdev[2], channels_last);
+    else if (dt == ICK_BF16)
+        ick_launch(image_prep_kernel<bf16>, grid, 256, 0, stream)((const __half*)raw_f16, (bf16*)out, npix8, HW, mean[0], mean[1], mean[2], stdev[0],
+                                                          stdev[1], stdev[2], channels_last);
+    else ICK_BAD_DT("image_prep", dt);
+    return ick_check_launch("image_prep");
 }

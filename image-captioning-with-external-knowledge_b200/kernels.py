@@ -292,6 +292,17 @@ class CudaKernels:
         self._call("ick_pool_rows_fwd", _p(x), _p(rows), dt_of(rows), B, C, Hin, Win, Hout, Wout, _ld(rows),
                    work=lambda: (x.numel() * 4 + B * Hout * Wout * C * rows.element_size(), 0))
 
+    def image_prep(self, raw, out, mean, std, channels_last=False):
+        """raw (N, 3, H, W) fp16 in [0, 255] (the HDF5 storage format) -> out = ((raw / 255 in fp16) - mean[c]) / std[c], fp32 or bf16,
+        NCHW or channels-last memory order (include/ickb200.h: ick_image_prep)."""
+        import ctypes
+
+        N, C, H, W = raw.shape
+        assert raw.dtype == torch.float16 and raw.is_contiguous() and out.numel() == raw.numel()
+        m, sd = (ctypes.c_float * C)(*mean), (ctypes.c_float * C)(*std)
+        self._call("ick_image_prep", _p(raw), _p(out), dt_of(out), N, C, H * W, ctypes.addressof(m), ctypes.addressof(sd),
+                   int(channels_last), work=lambda: (raw.numel() * (2 + out.element_size()), 0))
+
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
     def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1):
         self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E, group)

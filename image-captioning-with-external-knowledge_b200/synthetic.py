@@ -71,6 +71,8 @@ BASELINE_CONFIGS = {
     "geo_b32": Config("G", B=32, T=32, E=301, F=0, V=10000),
     "knowledge_b128": Config("K", B=128, T=102, E=301, F=51, V=10000),
     "news_b8": Config("N", B=8, T=52, E=101, F=301, V=10000),
+    # configs[4]: geo-aware end to end with the ResNet-101 trunk, per-GPU batch 256 (bench.py --workload geo_e2e_b256)
+    "geo_e2e_b256": Config("G", B=256, T=32, E=301, F=0, V=10000),
 }
 # small parity cases (oracle finishes in seconds; odd sizes on purpose)
 SMALL_CONFIGS = {

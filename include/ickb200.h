@@ -142,6 +142,14 @@ int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt, int B, int
 int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
                       cudaStream_t stream);
 
+/* Input pipeline, device half.  raw: the HDF5 storage format of the images - fp16 (N, 3, H, W), values in
+ * [0, 255] (G/create_input_files.py:99-101).  out = (float(half(raw / 255)) - mean[c]) / std[c], i.e. CaptionDataset.__getitem__'s
+ * `imgs[i] / 255.` (an fp16 numpy division, G/datasets.py:44) followed by train.py's transforms.Normalize (G/train.py:139-141),
+ * written as dt (fp32: bit-identical to the reference's tensor) in NCHW or, channels_last != 0, NHWC order.  mean / stdev: HOST
+ * arrays of C floats.  C = 3, H*W a multiple of 8. */
+int ick_image_prep(const void* raw_f16, void* out, int dt, long long N, int C, int HW, const float* mean, const float* stdev,
+                   int channels_last, cudaStream_t stream);
+
 /* ---- context indicators + predicate gate: get_context_indicators K/models.py:380-418, fc_predicate K/models.py:436-437 ---- */
 int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F, int V,
                            int E, int group, cudaStream_t stream);

@@ -559,3 +559,20 @@ def beam_search(
     res = torch.full((T,), spec.pad, dtype=torch.long)
     res[: len(seq)] = torch.tensor(seq, dtype=torch.long)
     return (res, margin) if return_margin else res
+
+
+def prepare_images(raw_f16, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)) -> torch.Tensor:
+    """
+    Host image path of the reference, restated with the same numpy / torch calls: ``torch.FloatTensor(imgs[i] / 255.)``
+    (G/datasets.py:44 — ``imgs`` is the fp16 HDF5 dataset of G/create_input_files.py:99-101, so the division is numpy's fp16
+    division) followed by ``transforms.Normalize(mean, std)`` (G/train.py:139-147; torchvision: ``tensor.sub_(mean).div_(std)``
+    in fp32).  raw_f16: (N, 3, H, W) numpy float16 array or torch.float16 tensor with values in [0, 255] -> fp32 tensor.
+    """
+    import numpy as np
+
+    a = raw_f16.numpy() if torch.is_tensor(raw_f16) else np.asarray(raw_f16)
+    assert a.dtype == np.float16
+    x = torch.FloatTensor(a / 255.0)
+    m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    return x.sub_(m).div_(s)

@@ -590,3 +590,10 @@ class HostKernels:
             if bestseq is not None:
                 result[img] = pad_tok
                 result[img, : len(bestseq)] = torch.tensor(bestseq, dtype=result.dtype)
+
+    def image_prep(self, raw, out, mean, std, channels_last=False):
+        self.calls += 1
+        x = (raw.float() / 255.0).half().float()
+        m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+        s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+        out.copy_(((x - m) / s).to(out.dtype))

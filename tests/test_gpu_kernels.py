@@ -719,3 +719,28 @@ def test_beam_select_state_machine(K, Hk, G):
     assert torch.equal(state["g"]["result"].cpu(), state["r"]["result"])
     assert torch.allclose(state["g"]["best"].cpu(), state["r"]["best"], atol=1e-5)
     assert int((state["r"]["ksel"] < G).sum()) > 0 and torch.isfinite(state["r"]["best"]).all()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_image_prep_matches_the_reference_host_pipeline(K, dtype, channels_last):
+    """fp16 HDF5 pixels -> normalised encoder input (G/datasets.py:44 + G/train.py:139-147): fp32 output bit-identical."""
+    from oracle import decoder_oracle as orc
+
+    raw = (torch.rand(5, 3, 24, 40, generator=g(3)) * 255).half()
+    raw[0, 0, 0, :4] = torch.tensor([0.0, 255.0, 1.0, 254.5]).half()
+    ref = orc.prepare_images(raw)
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    out = torch.empty(raw.shape, dtype=dtype, device=DEV, memory_format=fmt)
+    from ickb200.data import IMAGENET_MEAN, IMAGENET_STD
+
+    K.image_prep(cu(raw), out, IMAGENET_MEAN, IMAGENET_STD, channels_last=channels_last)
+    if dtype == torch.float32:
+        assert torch.equal(out.cpu(), ref)
+    else:
+        assert torch.equal(out.cpu(), ref.to(torch.bfloat16))  # one rounding of the same fp32 value
+    if not DRYRUN:
+        from ickb200.data import prepare_images
+
+        got = prepare_images(cu(raw), dtype, channels_last)
+        assert got.is_contiguous(memory_format=fmt) and torch.equal(got.cpu(), out.cpu())

@@ -120,3 +120,15 @@ def test_beam_of_one_is_greedy_without_cleanup():
         out = orc.beam_search(spec_for(cfg), p, pb["encoder_out"][:1], 4, pb["entities"][:1], pb["facts"][:1], beam_size=1)
     # step 3 repeats token 27 and predict()'s clean-up rewrites it; the first three steps are plain argmax
     assert out.tolist()[:3] == g["predict_tokens"][0][:3].tolist() and out.tolist()[3] == out.tolist()[2]
+
+
+def test_image_prep_oracle_is_the_reference_host_pipeline():
+    """oracle.prepare_images against the very calls the reference makes: torch.FloatTensor(imgs[i] / 255.) on an fp16 numpy
+    array (G/datasets.py:44) then torchvision's transforms.Normalize (G/train.py:139-147)."""
+    import torchvision.transforms as T
+
+    rng = np.random.default_rng(0)
+    a = (rng.random((3, 3, 16, 24)) * 255).astype(np.float16)
+    norm = T.Compose([T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    ref = torch.stack([norm(torch.FloatTensor(a[i] / 255.0)) for i in range(a.shape[0])])
+    assert torch.equal(orc.prepare_images(a), ref)

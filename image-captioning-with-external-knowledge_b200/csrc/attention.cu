@@ -339,7 +339,14 @@ __global__ void __launch_bounds__(128) mha_decode_kernel(const T* __restrict__ Q
 // image; a thread owns (key group, head, quarter of the head): 40 consecutive threads read the contiguous 640-byte K block and
 // the 640-byte V block of one cached position with 16-byte loads, eight positions per iteration.  The warp-per-(image, head)
 // kernel above reads 64-byte rows 3840 bytes apart, which is what limits it to ~3 TB/s.
-constexpr int DR_KG = 8;  // cached positions per iteration
+#ifndef ICK_DR_KG
+#define ICK_DR_KG 8
+#endif
+constexpr int DR_KG = ICK_DR_KG;  // cached positions per iteration
+#ifndef ICK_DR_UNROLL
+#define ICK_DR_UNROLL 2  // K/V row pairs a thread keeps in flight (A/B builds: -DICK_DR_UNROLL=4)
+#endif
+constexpr int DR_UNROLL = ICK_DR_UNROLL;
 __global__ void __launch_bounds__(DR_KG * 40) mha_decode_rows_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ KV, bf16* __restrict__ O,
                                                                      int H, int dh, int ldq, int ldkv, int ldo, long long batch_stride,
                                                                      int klen, float scale_log2) {
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(DR_KG * 40) mha_decode_rows_kernel(const bf16*
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-#pragma unroll 2
+#pragma unroll DR_UNROLL
     for (int j = kg; j < klen; j += DR_KG) {
         float kx[8], vx[8];
         ld8(base + (size_t)j * ldkv, kx);

@@ -553,6 +553,24 @@ class DecoderEngine:
                             D, self.plan.shapes["entity_encoder.type_embedding.weight"][0], self.V)
         return d_enc
 
+    def _memory_kv(self, mem, rows):
+        """Cross-attention K / V of the memory for the decode loops -> [(K_l, V_l, row stride)] per decoder layer.  One buffer of
+        K|V rows PER LAYER (the training path projects all layers in one [rows, L*2*DP] GEMM): the cached cross-attention of a
+        layer then streams sequential memory instead of 1280-byte pieces 3840 bytes apart (ICK_DECODE_KV_SPLIT=0: old layout)."""
+        K, DP, L = self.K, self.DP, self.L
+        kv_l = self.lin["transformer_decoder.kv_all"]
+        if os.environ.get("ICK_DECODE_KV_SPLIT", "1") == "0":
+            kvw = kv_l.lin.Np
+            kv = self._new(rows, kvw)
+            K.gemm(mem, kv_l.W, kv, bias=kv_l.b)
+            return [(kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], kvw) for l in range(L)]
+        out = []
+        for l in range(L):
+            kvl = self._new(rows, 2 * DP)
+            K.gemm(mem, kv_l.W[l * 2 * DP : (l + 1) * 2 * DP], kvl, bias=kv_l.b[l * 2 * DP : (l + 1) * 2 * DP])
+            out.append((kvl[:, :DP], kvl[:, DP:], 2 * DP))
+        return out
+
     # ---- greedy decode (predict) -----------------------------------------------------------------------------------------------------
     def greedy_decode(self, inp, Tmax: int, return_margins: bool = False):
         """
@@ -573,10 +591,7 @@ class DecoderEngine:
         ctx = NS(inp=inp)
         ctx.ent_enc, ctx.fact_enc = self._encode_context(inp, B, E, F)
         mem, _ = self._build_memory(inp, ctx.ent_enc, ctx.fact_enc, B, E, F, P, M, 0.0, None)
-        kv_l = self.lin["transformer_decoder.kv_all"]
-        kvw = kv_l.lin.Np
-        kv = self._new(B * M, kvw)
-        K.gemm(mem, kv_l.W, kv, bias=kv_l.b)
+        kvs = self._memory_kv(mem, B * M)
         captions = torch.full((B, Tmax), self.start, dtype=torch.int64, device=dev)
         masks = torch.zeros((B, Tmax), dtype=torch.int64, device=dev)
         output = torch.full((B, Tmax), self.pad, dtype=torch.int64, device=dev)
@@ -605,8 +620,8 @@ class DecoderEngine:
                 K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
                 K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
                 K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
-                K.mha_decode(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, B, H, dh, M * kvw,
-                             M * kvw, M)
+                Kl, Vl, kvw = kvs[l]
+                K.mha_decode(b.q, Kl, Vl, b.o, B, H, dh, M * kvw, M * kvw, M)
                 K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
                 K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
                 K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
@@ -645,10 +660,7 @@ class DecoderEngine:
         ctx = NS(inp=inp)
         ctx.ent_enc, ctx.fact_enc = self._encode_context(inp, NI, E, F)
         mem, _ = self._build_memory(inp, ctx.ent_enc, ctx.fact_enc, NI, E, F, P, M, 0.0, None)
-        kv_l = self.lin["transformer_decoder.kv_all"]
-        kvw = kv_l.lin.Np
-        kv = self._new(NI * M, kvw)
-        K.gemm(mem, kv_l.W, kv, bias=kv_l.b)
+        kvs = self._memory_kv(mem, NI * M)
         tok = [torch.full((R, Tmax), self.start, dtype=torch.int64, device=dev) for _ in range(2)]
         msk = [torch.zeros((R, Tmax), dtype=torch.int64, device=dev) for _ in range(2)]
         own = (torch.arange(R, dtype=torch.int32, device=dev) % G).unsqueeze(1).expand(R, Tmax)
@@ -685,11 +697,11 @@ class DecoderEngine:
                 K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
                 K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
                 K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
+                Kl, Vl, kvw = kvs[l]
                 if xattn_flash:  # the G beams of an image are G query positions of one flash-attention item over its memory
-                    K.mha_fwd(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, lse, NI, H, G, M, dh)
+                    K.mha_fwd(b.q, Kl, Vl, b.o, lse, NI, H, G, M, dh)
                 else:
-                    K.mha_decode_beam(b.q, kv[:, l * 2 * DP : l * 2 * DP + DP], kv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], b.o, R, G, H, dh,
-                                      M, kimg_stride=M * kvw, vimg_stride=M * kvw)
+                    K.mha_decode_beam(b.q, Kl, Vl, b.o, R, G, H, dh, M, kimg_stride=M * kvw, vimg_stride=M * kvw)
                 K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
                 K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
                 K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)

@@ -631,6 +631,11 @@ extern "C" int ick_mha_decode(const void* Q, const void* K, const void* V, void*
     ICK_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && kbatch_stride % 8 == 0 && vbatch_stride % 8 == 0,
                 "mha_decode: strides must be multiples of 8");
     const float sl2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+    if (dt == ICK_BF16 && (const bf16*)V == (const bf16*)K + H * HD && ldk == ldv && kbatch_stride == vbatch_stride && klen >= 64) {
+        // long cached sequences with contiguous K|V rows (the cross-attention over the memory): TMA-staged streaming kernel
+        const int rc = ick_mha_decode_tma(Q, K, O, B, H, dh, ldq, ldk, ldo, kbatch_stride, klen, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     if (dt == ICK_BF16 && (const bf16*)V == (const bf16*)K + H * HD && ldk == ldv && kbatch_stride == vbatch_stride && H <= 10 &&
         ((((uintptr_t)K) | ((uintptr_t)Q) | ((uintptr_t)O)) & 15) == 0 && decode_rows()) {
         const size_t smem = (size_t)DR_KG * H * 4 * 10 * sizeof(float);

@@ -744,3 +744,25 @@ def test_image_prep_matches_the_reference_host_pipeline(K, dtype, channels_last)
 
         got = prepare_images(cu(raw), dtype, channels_last)
         assert got.is_contiguous(memory_format=fmt) and torch.equal(got.cpu(), out.cpu())
+
+
+@pytest.mark.parametrize("klen", [548, 497, 64, 71])
+def test_mha_decode_tma_streaming_path(K, Hk, klen):
+    """Per-step cross-attention over contiguous K|V rows (the per-layer memory buffers of the decode loops): bf16, klen >= 64
+    takes the TMA-staged kernel; against the host restatement, and against the CUDA-core kernel on a non-contiguous copy."""
+    B, H, dh = 9, 10, 30
+    ldkv = 2 * H * 32
+    dtype = torch.bfloat16
+    kv = headify(rnd((B * klen, ldkv), torch.float32, 11), 2 * H, dh).to(dtype)
+    q = headify(rnd((B, H * 32), torch.float32, 12), H, dh).to(dtype)
+    Or = torch.zeros(B, H * 32, dtype=dtype)
+    Hk.mha_decode(q, kv[:, : H * 32], kv[:, H * 32 :], Or, B, H, dh, klen * ldkv, klen * ldkv, klen)
+    kg, qg = cu(kv), cu(q)
+    Og = torch.zeros(B, H * 32, dtype=dtype, device=DEV)
+    K.mha_decode(qg, kg[:, : H * 32], kg[:, H * 32 :], Og, B, H, dh, klen * ldkv, klen * ldkv, klen)
+    assert err(Og, Or) < TOL[dtype]
+    wide = torch.zeros(B * klen, ldkv + 64, dtype=dtype, device=DEV)  # same rows, padded stride -> the CUDA-core kernel
+    wide[:, :ldkv] = kg
+    O2 = torch.zeros_like(Og)
+    K.mha_decode(qg, wide[:, : H * 32], wide[:, H * 32 : ldkv], O2, B, H, dh, klen * (ldkv + 64), klen * (ldkv + 64), klen)
+    assert err(Og, O2) < 1e-2

@@ -1,20 +1,7 @@
 mkdir -p gpurun_out
-R=r78
-D=$PWD/image-captioning-with-external-knowledge_b200/csrc
-python - <<'PY' > gpurun_out/r78_readbw.log 2>&1
-import torch
-x = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda").normal_()
-for name, fn in (("sum", lambda: x.sum()), ("amax", lambda: x.amax())):
-    fn(); torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(10):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    print(name, "read-only GB/s", x.numel() * 2 / best / 1e6)
-PY
-cat gpurun_out/r78_readbw.log
-for v in "" _kg4u2 _kg4u4 _kg2u4; do
-  (ICKB200_LIB=$D/libickb200$v.so timeout 600 python tools/bench_predict.py --variant K --reps 5 2>> gpurun_out/${R}.err | tail -n 1) > gpurun_out/${R}_predict_K$v.json
-done
-tail -n 3 gpurun_out/${R}.err; cut -c1-230 gpurun_out/${R}_predict*.json
+R=r79
+(timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short --timeout 300 -k "decode" 2>&1 | tail -n 30) > gpurun_out/${R}_kernels.log
+(timeout 600 python tools/bench_predict.py --variant K --reps 5 2>> gpurun_out/${R}.err | tail -n 1) > gpurun_out/${R}_predict_K.json
+(ICK_DECODE_TMA=0 timeout 600 python tools/bench_predict.py --variant K --reps 5 2>> gpurun_out/${R}.err | tail -n 1) > gpurun_out/${R}_predict_K_notma.json
+(timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q --tb=short --timeout 600 -k "beam or predict" 2>&1 | tail -n 5) > gpurun_out/${R}_model.log
+tail -n 12 gpurun_out/${R}_kernels.log; tail -n 3 gpurun_out/${R}.err gpurun_out/${R}_model.log; cut -c1-330 gpurun_out/${R}_predict*.json

@@ -571,6 +571,49 @@ class DecoderEngine:
             out.append((kvl[:, :DP], kvl[:, DP:], 2 * DP))
         return out
 
+    def _dec_step_layer(self, l, x, row, next_row, b, attn_self, attn_cross, rows, mean, rstd, fused):
+        """One decoder layer of a single-position decode step.  `row` holds this position's q|k|v (already projected when
+        `fused`), `next_row` is where the NEXT layer's q|k|v goes (None for the last layer).  attn_self(q_row, out) and
+        attn_cross(q, out) launch the cached attentions.  fused (bf16, opt-in: ICK_DECODE_CHAIN=1): the row-wise work between two
+        attentions is one ick_decode_chain launch (4 launches per layer instead of 11); else the GEMM / LayerNorm kernels one by one."""
+        K, D, DP = self.K, self.D, self.DP
+        pre = f"transformer_decoder.layers.{l}."
+        qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
+        q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
+        f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
+        n1 = (self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"))
+        n2 = (self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"))
+        n3 = (self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"))
+        if not fused:
+            K.gemm(x, qkv_l.W, row, bias=qkv_l.b)
+            attn_self(row, b.o)
+            K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
+            K.add_ln_fwd(x, b.s, n1[0], n1[1], b.y1, mean, rstd, D)
+            K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
+            attn_cross(b.q, b.o)
+            K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
+            K.add_ln_fwd(b.y1, b.s, n2[0], n2[1], b.y2, mean, rstd, D)
+            K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
+            K.gemm(b.h1, f2.W, b.s, bias=f2.b)
+            K.add_ln_fwd(b.y2, b.s, n3[0], n3[1], b.y3, mean, rstd, D)
+            return b.y3
+        attn_self(row, b.o)
+        K.decode_chain(b.o, x, out_l.W, out_l.b, n1[0], n1[1], b.y1, D, proj=(q_l.W, q_l.b, b.q))
+        attn_cross(b.q, b.o)
+        nxt = None
+        if next_row is not None:
+            nq = self.lin[f"transformer_decoder.layers.{l + 1}.self_attn.qkv"]
+            nxt = (nq.W, nq.b, next_row)
+        K.decode_chain(b.o, b.y1, out2_l.W, out2_l.b, n2[0], n2[1], b.y3, D, ffn=(f1.W, f1.b, f2.W, f2.b, n3[0], n3[1]), proj=nxt)
+        return b.y3
+
+    def _decode_fused(self) -> bool:
+        # OFF by default: measured 30.2 ms against 26.7 ms per 625-image greedy decode on a B200 (profiles/README.md) - the 16-row
+        # mma.sync chains are latency-bound, the tcgen05 GEMMs with programmatic dependent launch are faster.  "1": bf16 decode loops
+        # use it; "force": also for fp32 (host-simulated tests of the orchestration).
+        mode = os.environ.get("ICK_DECODE_CHAIN", "0")
+        return mode == "force" or (self.dtype == torch.bfloat16 and mode == "1")
+
     # ---- greedy decode (predict) -----------------------------------------------------------------------------------------------------
     def greedy_decode(self, inp, Tmax: int, return_margins: bool = False):
         """
@@ -604,30 +647,23 @@ class DecoderEngine:
         x0 = self._new(B, DP)
         bufs = [NS(o=self._new(B, DP), s=self._new(B, DP), y1=self._new(B, DP), q=self._new(B, DP), y2=self._new(B, DP),
                    h1=self._new(B, self.lin[f"transformer_decoder.layers.{l}.ffn1"].lin.Np), y3=self._new(B, DP)) for l in range(L)]
+        fused = self._decode_fused()
         for i in range(Tmax):
             K.caption_embed_fwd(captions, masks, self.wemb, ctx.ent_enc, ctx.fact_enc, self.pe, x0, B, Tmax, i, 1, V, E, F, D, self.pad,
                                 math.sqrt(D))
             x = x0
+            rows_i = [cache[l].view(B, Tmax, 3 * DP)[:, i, :] for l in range(L)]  # this step's q|k|v rows inside the caches
+            if fused:
+                qkv0 = self.lin["transformer_decoder.layers.0.self_attn.qkv"]
+                K.gemm(x, qkv0.W, rows_i[0], bias=qkv0.b)
             for l in range(L):
-                pre = f"transformer_decoder.layers.{l}."
-                qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
-                q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
-                f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
-                b = bufs[l]
-                row = cache[l].view(B, Tmax, 3 * DP)[:, i, :]  # this step's q|k|v rows inside the cache
-                K.gemm(x, qkv_l.W, row, bias=qkv_l.b)
-                K.mha_decode(row[:, :DP], cache[l][:, DP : 2 * DP], cache[l][:, 2 * DP :], b.o, B, H, dh, Tmax * 3 * DP, Tmax * 3 * DP, i + 1)
-                K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
-                K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
-                K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
                 Kl, Vl, kvw = kvs[l]
-                K.mha_decode(b.q, Kl, Vl, b.o, B, H, dh, M * kvw, M * kvw, M)
-                K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
-                K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
-                K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
-                K.gemm(b.h1, f2.W, b.s, bias=f2.b)
-                K.add_ln_fwd(b.y2, b.s, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), b.y3, mean, rstd, D)
-                x = b.y3
+                x = self._dec_step_layer(
+                    l, x, rows_i[l], rows_i[l + 1] if l + 1 < L else None, bufs[l],
+                    lambda row, out, l=l: K.mha_decode(row[:, :DP], cache[l][:, DP : 2 * DP], cache[l][:, 2 * DP :], out, B, H, dh,
+                                                       Tmax * 3 * DP, Tmax * 3 * DP, i + 1),
+                    lambda q, out, Kl=Kl, Vl=Vl, kvw=kvw: K.mha_decode(q, Kl, Vl, out, B, H, dh, M * kvw, M * kvw, M),
+                    B, mean, rstd, fused)
             self._heads_fwd(ctx, captions, x, scores, B, 1, i, Tmax, E, F, lag=1)
             K.greedy_select(scores, W, output, second, captions, masks, done, margins, B, i, Tmax, V, E, self.has_facts, self.end)
         return (output, margins) if return_margins else output
@@ -679,35 +715,30 @@ class DecoderEngine:
         xattn_flash = os.environ.get("ICK_BEAM_XATTN", "flash") == "flash" and self.dtype != torch.float32
         lse = self._newf(NI * H * G)
         cand = self._newf(R * G * 2)  # per-row candidate lists of beam_select
+        fused = self._decode_fused()
         for i in range(Tmax):
             cur, nxt = i & 1, (i + 1) & 1
             K.caption_embed_fwd(tok[cur], msk[cur], self.wemb, ctx.ent_enc, ctx.fact_enc, self.pe, x0, R, Tmax, i, 1, V, E, F, D,
                                 self.pad, math.sqrt(D), group=G)
             x = x0
-            for l in range(L):
-                pre = f"transformer_decoder.layers.{l}."
-                qkv_l, out_l = self.lin[pre + "self_attn.qkv"], self.lin[pre + "self_attn.out"]
-                q_l, out2_l = self.lin[pre + "multihead_attn.q"], self.lin[pre + "multihead_attn.out"]
-                f1, f2 = self.lin[pre + "ffn1"], self.lin[pre + "ffn2"]
-                b = bufs[l]
-                row = cache[l][i * R : (i + 1) * R]
-                K.gemm(x, qkv_l.W, row, bias=qkv_l.b)
-                K.mha_decode_beam(row[:, :DP], cache[l][:, DP : 2 * DP], cache[l][:, 2 * DP :], b.o, R, G, H, dh, i + 1, anc=anc[cur],
-                                  kpos_stride=pos, vpos_stride=pos)
-                K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
-                K.add_ln_fwd(x, b.s, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), b.y1, mean, rstd, D)
-                K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
+            rows_i = [cache[l][i * R : (i + 1) * R] for l in range(L)]
+            if fused:
+                qkv0 = self.lin["transformer_decoder.layers.0.self_attn.qkv"]
+                K.gemm(x, qkv0.W, rows_i[0], bias=qkv0.b)
+
+            def cross(q, out, l):
                 Kl, Vl, kvw = kvs[l]
                 if xattn_flash:  # the G beams of an image are G query positions of one flash-attention item over its memory
-                    K.mha_fwd(b.q, Kl, Vl, b.o, lse, NI, H, G, M, dh)
+                    K.mha_fwd(q, Kl, Vl, out, lse, NI, H, G, M, dh)
                 else:
-                    K.mha_decode_beam(b.q, Kl, Vl, b.o, R, G, H, dh, M, kimg_stride=M * kvw, vimg_stride=M * kvw)
-                K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
-                K.add_ln_fwd(b.y1, b.s, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), b.y2, mean, rstd, D)
-                K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
-                K.gemm(b.h1, f2.W, b.s, bias=f2.b)
-                K.add_ln_fwd(b.y2, b.s, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), b.y3, mean, rstd, D)
-                x = b.y3
+                    K.mha_decode_beam(q, Kl, Vl, out, R, G, H, dh, M, kimg_stride=M * kvw, vimg_stride=M * kvw)
+
+            for l in range(L):
+                x = self._dec_step_layer(
+                    l, x, rows_i[l], rows_i[l + 1] if l + 1 < L else None, bufs[l],
+                    lambda row, out, l=l: K.mha_decode_beam(row[:, :DP], cache[l][:, DP : 2 * DP], cache[l][:, 2 * DP :], out, R, G, H, dh,
+                                                            i + 1, anc=anc[cur], kpos_stride=pos, vpos_stride=pos),
+                    lambda q, out, l=l: cross(q, out, l), R, mean, rstd, fused)
             self._heads_fwd(ctx, tok[cur], x, scores, R, 1, i, Tmax, E, F, lag=1, group=G)
             K.beam_select(scores, W, cum, ksel, tok[cur], msk[cur], tok[nxt], msk[nxt], anc[cur], anc[nxt], best, result, NI, G, i, Tmax,
                           V, E, self.has_facts, self.end, self.pad, workspace=cand)

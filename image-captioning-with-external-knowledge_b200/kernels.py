@@ -366,3 +366,24 @@ class CudaKernels:
         self._call("ick_beam_select", _p(scores), W, _ld(scores), _p(cum), _p(ksel), _p(tok_in), _p(mask_in), _p(tok_out), _p(mask_out),
                    _p(anc_in), _p(anc_out), _p(best), _p(result), images, group, step, Tmax, V, E, int(has_facts), end_tok, pad_tok,
                    _p(workspace), workspace.numel() * workspace.element_size(), n=2)
+
+    def decode_chain(self, attn_out, x_res, Wo, bo, gamma1, beta1, y, D, ffn=None, proj=None, eps=1e-5):
+        """One launch for the row-wise tail of a decoder layer in the decode loops (include/ickb200.h: ick_decode_chain):
+        y = LN(x_res + attn_out Wo^T + bo); ffn = (W1, b1, W2, b2, gamma2, beta2) adds the feed-forward sublayer;
+        proj = (Wn, bn, out) also writes out = y Wn^T + bn.  bf16 only."""
+        assert attn_out.dtype == torch.bfloat16 and Wo.dtype == torch.bfloat16, "ick_decode_chain is a bf16 kernel"
+        rows, DP = attn_out.shape[0], Wo.shape[1]
+        W1 = b1 = W2 = b2 = g2 = be2 = None
+        FFP = DP
+        if ffn is not None:
+            W1, b1, W2, b2, g2, be2 = ffn
+            FFP = W1.shape[0]
+        Wn = bn = out = None
+        Nn = 0
+        if proj is not None:
+            Wn, bn, out = proj
+            Nn = Wn.shape[0]
+        self._call("ick_decode_chain", _p(attn_out), _ld(attn_out), _p(x_res), _ld(x_res), _p(Wo), _ld(Wo), _p(bo), _p(gamma1), _p(beta1),
+                   _p(W1), _ld(W1) if W1 is not None else 0, _p(b1), _p(W2), _ld(W2) if W2 is not None else 0, _p(b2), _p(g2), _p(be2),
+                   _p(Wn), _ld(Wn) if Wn is not None else 0, _p(bn), _p(y), _ld(y), _p(out), _ld(out) if out is not None else 0, rows, D, DP,
+                   FFP, Nn, eps)

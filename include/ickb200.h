@@ -193,6 +193,17 @@ int ick_greedy_select(const float* scores, int W, int lds, long long* output, in
                       cudaStream_t stream);
 
 
+/* ---- decode loops: the row-wise tail of a decoder layer between two attention kernels in ONE launch (decode_chain.cu) ----------
+ * y = LayerNorm(x_res + attn_out Wo^T + bo) [gamma1, beta1];  if W1: y = LayerNorm(y + relu(y W1^T + b1) W2^T + b2) [gamma2, beta2];
+ * y (rows, ldy) is written;  if Wn: proj (rows, ldproj) = y Wn^T + bn (Nn columns) - the cross-attention query projection or the
+ * next layer's self-attention q|k|v cache row (nn.TransformerDecoderLayer, post-LN, G/models.py:241-242; one position per row).
+ * bf16 activations and K-major packed weights [N, ldw] (the same operand copies the GEMM entry points take), fp32 biases /
+ * LayerNorm parameters, fp32 accumulation.  D real columns in rows of DP (pad columns zero), DP and FFP multiples of 32. */
+int ick_decode_chain(const void* attn_out, int lda, const void* x_res, int ldx, const void* Wo, int ldwo, const float* bo,
+                     const float* gamma1, const float* beta1, const void* W1, int ldw1, const float* b1, const void* W2, int ldw2,
+                     const float* b2, const float* gamma2, const float* beta2, const void* Wn, int ldwn, const float* bn, void* y,
+                     int ldy, void* proj, int ldproj, int rows, int D, int DP, int FFP, int Nn, float eps, cudaStream_t stream);
+
 /* ---- beam-search decoding: EXTENSION, no reference counterpart (the reference's predict() is greedy; BASELINE.json
  * asks for beam-5).  The algorithm is the beam search of the Show-Attend-Tell tutorial the reference's READMEs name as their
  * starting point (G/README.md:37), restated in oracle/decoder_oracle.py:beam_search over the reference-pinned scoring function. -- */

@@ -597,3 +597,30 @@ class HostKernels:
         m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
         s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
         out.copy_(((x - m) / s).to(out.dtype))
+
+    def decode_chain(self, attn_out, x_res, Wo, bo, gamma1, beta1, y, D, ffn=None, proj=None, eps=1e-5):
+        self.calls += 1
+
+        def ln(v, g, b):
+            v = v[:, :D]
+            m = v.mean(1, keepdim=True)
+            var = ((v - m) ** 2).mean(1, keepdim=True)
+            return (v - m) / torch.sqrt(var + eps) * g.float() + b.float()
+
+        def pad(v, width):
+            out = torch.zeros(v.shape[0], width)
+            out[:, : v.shape[1]] = v
+            return out
+
+        DP = Wo.shape[1]
+        s1 = x_res.float() + attn_out.float() @ Wo.float().T + bo.float()
+        yy = pad(ln(s1, gamma1, beta1), DP).to(y.dtype).float()
+        if ffn is not None:
+            W1, b1, W2, b2, g2, be2 = ffn
+            h = torch.relu(yy @ W1.float().T + b1.float()).to(y.dtype).float()
+            s2 = yy + h @ W2.float().T + b2.float()
+            yy = pad(ln(s2, g2, be2), DP).to(y.dtype).float()
+        y.copy_(yy.to(y.dtype))
+        if proj is not None:
+            Wn, bn, out = proj
+            out.copy_((yy @ Wn.float().T + bn.float()).to(out.dtype))

@@ -766,3 +766,47 @@ def test_mha_decode_tma_streaming_path(K, Hk, klen):
     O2 = torch.zeros_like(Og)
     K.mha_decode(qg, wide[:, : H * 32], wide[:, H * 32 : ldkv], O2, B, H, dh, klen * (ldkv + 64), klen * (ldkv + 64), klen)
     assert err(Og, O2) < 1e-2
+
+
+@pytest.mark.parametrize("rows", [625, 37, 16])
+@pytest.mark.parametrize("ffn,proj_n", [(False, 320), (True, 960), (True, 0)])
+def test_decode_chain(K, Hk, rows, ffn, proj_n):
+    """Fused row-wise tail of a decoder layer (out-proj + LN [+ FFN + LN] [+ next projection]) against the host restatement."""
+    D, DP, FFP = 300, 320, 512
+    dtype = torch.bfloat16
+
+    def w(n, k, kreal, seed):
+        m = torch.zeros(n, k)
+        m[:, :kreal] = rnd((n, kreal), torch.float32, seed, 0.08)
+        return m.to(dtype)
+
+    def rows_of(seed, ld=DP):
+        x = torch.zeros(rows, ld)
+        x[:, :D] = rnd((rows, D), torch.float32, seed)
+        return x.to(dtype)
+
+    a = headify(rnd((rows, DP), torch.float32, 1), 10, 30).to(dtype)
+    x = rows_of(2)
+    Wo, bo = w(DP, DP, DP, 3), torch.cat([rnd((D,), torch.float32, 4, 0.1), torch.zeros(DP - D)])
+    Wo[D:] = 0
+    g1, be1 = 1 + rnd((D,), torch.float32, 5, 0.1), rnd((D,), torch.float32, 6, 0.1)
+    f = None
+    if ffn:
+        W1, b1 = w(FFP, DP, D, 7), rnd((FFP,), torch.float32, 8, 0.1)
+        W2, b2 = w(DP, FFP, FFP, 9), torch.cat([rnd((D,), torch.float32, 10, 0.1), torch.zeros(DP - D)])
+        W2[D:] = 0
+        f = (W1, b1, W2, b2, 1 + rnd((D,), torch.float32, 11, 0.1), rnd((D,), torch.float32, 12, 0.1))
+    yr, yg = torch.zeros(rows, DP, dtype=dtype), torch.full((rows, DP), float("nan"), dtype=dtype).to(DEV)
+    pr = pg = None
+    pj_r = pj_g = None
+    if proj_n:
+        Wn, bn = w(proj_n, DP, D, 13), rnd((proj_n,), torch.float32, 14, 0.1)
+        big_r, big_g = torch.zeros(rows, 3 * proj_n, dtype=dtype), torch.zeros(rows, 3 * proj_n, dtype=dtype).to(DEV)
+        pr, pg = big_r[:, proj_n : 2 * proj_n], big_g[:, proj_n : 2 * proj_n]  # strided rows, like a cache slice
+        pj_r, pj_g = (Wn, bn, pr), (cu(Wn), cu(bn), pg)
+    Hk.decode_chain(a, x, Wo, bo, g1, be1, yr, D, ffn=f, proj=pj_r)
+    K.decode_chain(cu(a), cu(x), cu(Wo), cu(bo), cu(g1), cu(be1), yg, D, ffn=tuple(cu(t) for t in f) if f else None, proj=pj_g)
+    assert torch.isfinite(yg.float()).all()
+    assert err(yg, yr) < TOL[dtype] and float(yg[:, D:].float().abs().max()) == 0.0
+    if proj_n:
+        assert err(pg, pr) < TOL[dtype]

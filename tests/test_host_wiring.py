@@ -138,6 +138,39 @@ def test_beam_search_tokens_vs_golden(variant):
         assert np.allclose(score.numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
 
 
+@pytest.mark.parametrize("variant", ["G", "K"])
+def test_fused_decode_chain_orchestration(variant, monkeypatch):
+    """The decode loops with the row-wise layer tails as single ick_decode_chain launches (opt-in on the GPU: ICK_DECODE_CHAIN=1),
+    driven over the host kernels in fp32: greedy tokens and beam captions must equal the golden ones of the unfused orchestration."""
+    import os
+
+    import numpy as np
+
+    from helpers import GOLDEN_DIR
+
+    monkeypatch.setenv("ICK_DECODE_CHAIN", "force")
+    cfg = syn.SMALL_CONFIGS[variant]
+    g = load_golden(variant)
+    dec = build_module(cfg, "cpu").eval()
+    pb = syn.make_batch(cfg, seed=int(g["predict_seed"]))
+    T = int(g["predict_max_len"])
+    calls0 = dec._ensure_engine().K.calls
+    out = dec.predict_batch(pb["encoder_out"], T, pb["entities"], pb.get("facts"))
+    assert out.tolist() == g["predict_tokens"].tolist()
+    fused_calls = dec._ensure_engine().K.calls - calls0
+    monkeypatch.setenv("ICK_DECODE_CHAIN", "0")
+    calls0 = dec._ensure_engine().K.calls
+    dec.predict_batch(pb["encoder_out"], T, pb["entities"], pb.get("facts"))
+    assert fused_calls < dec._ensure_engine().K.calls - calls0  # fewer launches
+    monkeypatch.setenv("ICK_DECODE_CHAIN", "force")
+    gb = dict(np.load(os.path.join(GOLDEN_DIR, f"golden_beam_{variant}.npz")))
+    Tb, k, B = int(gb["max_len"]), int(gb["beam"]), int(gb["batch"])
+    pbb = syn.make_batch(cfg.with_batch(B), seed=int(gb["seed"]))
+    outb = dec.beam_search_batch(pbb["encoder_out"], Tb, pbb["entities"], pbb.get("facts"), beam_size=k)
+    ok = gb["margins_0"] > 1e-4
+    assert outb[ok].tolist() == gb["tokens_0"][ok].tolist()
+
+
 def test_module_pickles_like_reference_checkpoints(tmp_path):
     cfg = syn.SMALL_CONFIGS["G"]
     dec = build_module(cfg, "cpu").eval()

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) image_prep_kernel(const __half* __restric
 //               facts sharing that predicate; FIRST_NONE for the others (the predicate indicator is a SET of predicates).
 __global__ void __launch_bounds__(256) fact_first_mention_kernel(const long long* __restrict__ caps, const long long* __restrict__ facts,
                                                                  int* __restrict__ first_t, int* __restrict__ tmin, int T_, int F,
-                                                                 int V, int E, int group) {
+                                                                 int V, int E, int group, int NP) {
     ick_pdl_entry();
     extern __shared__ int sm[];
     int* sfirst = sm;
@@ -397,6 +397,26 @@ __global__ void __launch_bounds__(256) fact_first_mention_kernel(const long long
         sfirst[f] = first;
         spred[f] = (int)fb[3 * f + 2];
         first_t[(size_t)b * F + f] = first;
+    }
+    if (NP > 0) {  // predicate ids are known to lie in [0, NP): two shared tables replace the O(F^2) duplicate search
+        int* ptm = sm + 2 * F;   // earliest first mention per predicate
+        int* prep = ptm + NP;    // lowest fact index per predicate (its representative)
+        for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+            ptm[p] = FIRST_NONE;
+            prep[p] = 0x7fffffff;
+        }
+        __syncthreads();
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            const int p = min(max(spred[f], 0), NP - 1);
+            atomicMin(&ptm[p], sfirst[f]);
+            atomicMin(&prep[p], f);
+        }
+        __syncthreads();
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            const int p = min(max(spred[f], 0), NP - 1);
+            tmin[(size_t)b * F + f] = prep[p] == f ? ptm[p] : FIRST_NONE;
+        }
+        return;
     }
     __syncthreads();
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -776,11 +796,13 @@ extern "C" int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt,
 }
 
 extern "C" int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F,
-                                      int V, int E, int group, cudaStream_t stream) {
+                                      int V, int E, int group, int NP, cudaStream_t stream) {
     ICK_REQUIRE(F > 0 && F <= 4096, "fact_first_mention: F=%d out of range", F);
     ICK_REQUIRE(group >= 1 && B % group == 0, "fact_first_mention: B=%d is not a multiple of group=%d", B, group);
     if (B == 0) return ICK_OK;
-    ick_launch(fact_first_mention_kernel, B, 256, 2 * F * sizeof(int), stream)(captions, facts, first_t, tmin, T, F, V, E, group);
+    if (NP < 0 || (size_t)(2 * F + 2 * NP) * sizeof(int) > 46 * 1024) NP = 0;  // tables do not fit: pairwise search
+    ick_launch(fact_first_mention_kernel, B, 256, (size_t)(2 * F + 2 * NP) * sizeof(int), stream)(captions, facts, first_t, tmin, T, F, V, E, group,
+                                                                                                 NP);
     return ick_check_launch("fact_first_mention");
 }
 

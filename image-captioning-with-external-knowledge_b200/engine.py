@@ -458,7 +458,7 @@ class DecoderEngine:
         if self.has_facts:
             ctx.first_t = torch.empty(B * F, dtype=torch.int32, device=self.device)
             ctx.tmin = torch.empty(B * F, dtype=torch.int32, device=self.device)
-            K.fact_first_mention(captions, ctx.inp.facts, ctx.first_t, ctx.tmin, B, Tcap, F, V, E, group=group)
+            K.fact_first_mention(captions, ctx.inp.facts, ctx.first_t, ctx.tmin, B, Tcap, F, V, E, group=group, NP=self.NP)
             ctx.gate = self._new(B * Tn, DP)
             ctx.hg = self._new(B * Tn, DP)
             K.pred_gate_fwd(ctx.tmin, ctx.inp.facts, self.WpT, self.param("fc_predicate.bias"), h, ctx.gate, ctx.hg, B, Tn, t0, F, D,

@@ -304,8 +304,8 @@ class CudaKernels:
                    int(channels_last), work=lambda: (raw.numel() * (2 + out.element_size()), 0))
 
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
-    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1):
-        self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E, group)
+    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1, NP=0):
+        self._call("ick_fact_first_mention", _p(captions), _p(facts), _p(first_t), _p(tmin), B, T, F, V, E, group, NP)
 
     def pred_gate_fwd(self, tmin, facts, WpT, bias, h, gate, hg, B, Tn, t0, F, D, NP, lag, group=1):
         self._call("ick_pred_gate_fwd", _p(tmin), _p(facts), _p(WpT), _p(bias), _p(h), _p(gate), _p(hg), dt_of(gate), B, Tn, t0, F, D,

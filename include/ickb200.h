@@ -151,8 +151,10 @@ int ick_image_prep(const void* raw_f16, void* out, int dt, long long N, int C, i
                    int channels_last, cudaStream_t stream);
 
 /* ---- context indicators + predicate gate: get_context_indicators K/models.py:380-418, fc_predicate K/models.py:436-437 ---- */
+/* NP: number of predicates if every predicate id is known to lie in [0, NP) (the duplicate-predicate search then uses two shared
+ * tables instead of comparing all fact pairs), 0 = unknown. */
 int ick_fact_first_mention(const long long* captions, const long long* facts, int* first_t, int* tmin, int B, int T, int F, int V,
-                           int E, int group, cudaStream_t stream);
+                           int E, int group, int NP, cudaStream_t stream);
 int ick_pred_gate_fwd(const int* tmin, const long long* facts, const float* WpT, const float* bias, const void* h, void* gate,
                       void* hg, int dt, int B, int Tn, int t0, int F, int D, int ld, int ldp, int NP, int lag, int group,
                       cudaStream_t stream);

@@ -382,7 +382,7 @@ class HostKernels:
         rows[:, :C] = pooled.permute(0, 2, 3, 1).reshape(B * Hout * Wout, C).to(rows.dtype)
 
     # ---- indicators / gate ------------------------------------------------------------------------------------------------
-    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1):
+    def fact_first_mention(self, captions, facts, first_t, tmin, B, T, F, V, E, group=1, NP=0):
         self.calls += 1
         if group > 1:
             facts = facts.repeat_interleave(group, 0)

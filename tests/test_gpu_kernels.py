@@ -438,12 +438,18 @@ def test_indicators_gate_pointer(K, Hk, dtype, lag, Tn, t0):
     B, E, F, V, D, ld, NP = 4, 23, 17, 61, 300, 320, 3000
     cfg, batch = make_context(1, B, E, F, V, seed=5)
     T = cfg.T
-    caps, facts = batch["captions"], batch["facts"]
+    caps, facts = batch["captions"], batch["facts"].clone()
+    facts[:, 3, 2] = facts[:, 1, 2]  # duplicate predicates: the indicator is a SET of predicates (one representative fact each)
+    facts[:, 9, 2] = facts[:, 1, 2]
+    facts[:, 12, 2] = facts[:, 5, 2]
     ftr, tmr = torch.zeros(B * F, dtype=torch.int32), torch.zeros(B * F, dtype=torch.int32)
     ftg, tmg = ftr.clone().cuda(), tmr.clone().cuda()
     Hk.fact_first_mention(caps, facts, ftr, tmr, B, T, F, V, E)
     K.fact_first_mention(cu(caps), cu(facts), ftg, tmg, B, T, F, V, E)
     assert torch.equal(ftg.cpu(), ftr) and torch.equal(tmg.cpu(), tmr)  # integer work: bit-exact
+    ftg2, tmg2 = torch.zeros_like(ftg), torch.zeros_like(tmg)
+    K.fact_first_mention(cu(caps), cu(facts), ftg2, tmg2, B, T, F, V, E, NP=NP)  # per-predicate tables instead of the pair search
+    assert torch.equal(ftg2.cpu(), ftr) and torch.equal(tmg2.cpu(), tmr)
     assert int((ftr < FIRST_NONE).sum()) > 0
     WpT = torch.zeros(NP, ld)
     WpT[:, :D] = rnd((NP, D), torch.float32, 1, 0.3)

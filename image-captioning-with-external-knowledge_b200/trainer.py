@@ -198,3 +198,46 @@ class Trainer:
         if pending is not None:
             pending[1].synchronize()
             yield pending[0].clone()
+
+
+def generate_sharded(decoder, encoder_out, max_pred_len, entities, facts=None, beam_size: int = 0, process_group=None):
+    """
+    Caption generation over several GPUs: images are independent, so rank r decodes the images i with
+    i % world_size == r - no communication on the data path - and the token ids are gathered on every rank at the end
+    (one all_gather of small int64 tensors) and put back in the original order.  beam_size = 0: greedy predict() semantics
+    (DecoderTransformer.predict_batch); > 0: beam search (extension).  Every rank passes the FULL inputs (or at least its shard's
+    rows at their global positions); returns (N, max_pred_len) int64 on the CPU.  Without an initialised process group this is the
+    single-process call.
+    """
+    import torch.distributed as dist
+
+    n = encoder_out.shape[0]
+    world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(process_group) if world > 1 else 0
+    mine = torch.arange(rank, n, world)
+    args = (encoder_out[mine.to(encoder_out.device)], max_pred_len, entities[mine.to(entities.device)],
+            facts[mine.to(facts.device)] if facts is not None else None)
+    if mine.numel() == 0:
+        out = torch.zeros((0, max_pred_len), dtype=torch.int64)
+    elif beam_size > 0:
+        out = decoder.beam_search_batch(*args, beam_size=beam_size).cpu()
+    else:
+        out = decoder.predict_batch(*args).cpu()
+    if world == 1:
+        return out
+    per_rank = (n + world - 1) // world
+    padded = torch.zeros((per_rank, max_pred_len), dtype=torch.int64)
+    padded[: out.shape[0]] = out
+    if dist.get_backend(process_group) == "nccl":
+        dev = encoder_out.device
+        bufs = [torch.empty_like(padded, device=dev) for _ in range(world)]
+        dist.all_gather(bufs, padded.to(dev), group=process_group)
+        bufs = [b.cpu() for b in bufs]
+    else:
+        bufs = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(bufs, padded, group=process_group)
+    full = torch.zeros((n, max_pred_len), dtype=torch.int64)
+    for r in range(world):
+        idx = torch.arange(r, n, world)
+        full[idx] = bufs[r][: idx.numel()]
+    return full

@@ -105,3 +105,44 @@ def test_two_rank_gloo_equals_single_process():
         n_close += int((d < 2e-5).sum())
         n_all += d.numel()
     assert n_close > 0.999 * n_all  # all but noise-gradient elements agree to fp32 summation order
+
+
+def _gen_worker(rank, world, port, cfg, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from ickb200.trainer import generate_sharded
+
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu").eval()
+    pb = syn.make_batch(cfg, seed=11)
+    greedy = generate_sharded(dec, pb["encoder_out"], 6, pb["entities"], pb.get("facts"))
+    beam = generate_sharded(dec, pb["encoder_out"], 6, pb["entities"], pb.get("facts"), beam_size=3)
+    if rank == 0:
+        q.put((greedy.tolist(), beam.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_generation_two_ranks_equals_single_process():
+    """Inference shards images i % world == rank with no data-path communication: 5 images over 2 gloo ranks
+    (a ragged split) give the single-process captions, greedy and beam."""
+    from ickb200.trainer import generate_sharded
+
+    cfg = syn.SMALL_CONFIGS["K"].with_batch(5)
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu").eval()
+    pb = syn.make_batch(cfg, seed=11)
+    ref_g = generate_sharded(dec, pb["encoder_out"], 6, pb["entities"], pb.get("facts")).tolist()
+    ref_b = generate_sharded(dec, pb["encoder_out"], 6, pb["entities"], pb.get("facts"), beam_size=3).tolist()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gen_worker, args=(r, 2, port, cfg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got_g, got_b = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    assert got_g == ref_g and got_b == ref_b

@@ -375,7 +375,37 @@ class DecoderTransformer(nn.Module):
         cache = self.__dict__.setdefault("_decode_graphs", {})
         key = (id(eng), max_pred_len, tuple(inp.encoder_out.shape), tuple(inp.entities.shape),
                tuple(inp.facts.shape) if inp.facts is not None else None, beam)
-        run = (lambda x: eng.beam_decode(x, max_pred_len, beam)) if beam else (lambda x: eng.greedy_decode(x, max_pred_len))
+        one = (lambda x: eng.beam_decode(x, max_pred_len, beam)) if beam else (lambda x: eng.greedy_decode(x, max_pred_len))
+        # Experiment switch, default 1 = off: images are independent, so the batch can be cut into ICKB200_DECODE_STREAMS chunks whose
+        # loops are captured on parallel branches of the graph (one chunk's small latency-bound GEMMs / LayerNorms could overlap
+        # another chunk's HBM-bound attention).  Measured on a B200: 23.3k captions/s with 1, 22.2k / 21.3k / 19.9k with 2 / 3 / 4
+        # branches - the halves' kernels do not overlap enough to pay for running twice as many of them (profiles/README.md).
+        nstr = max(1, min(int(os.environ.get("ICKB200_DECODE_STREAMS", "1")), inp.encoder_out.shape[0] // 64))
+        side_streams = self.__dict__.setdefault("_decode_streams", [])
+        while len(side_streams) < nstr:
+            side_streams.append(torch.cuda.Stream())
+
+        def run(x):
+            if nstr == 1:
+                return one(x)
+            B = x.encoder_out.shape[0]
+            cuts = [B * i // nstr for i in range(nstr + 1)]
+            cur = torch.cuda.current_stream()
+            outs = []
+            for i in range(nstr):
+                st = side_streams[i]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    sl = slice(cuts[i], cuts[i + 1])
+                    outs.append(one(NS(encoder_out=x.encoder_out[sl], entities=x.entities[sl],
+                                       facts=x.facts[sl] if x.facts is not None else None)))
+            for i in range(nstr):
+                cur.wait_stream(side_streams[i])
+            if beam:
+                return tuple(torch.cat([o[j] for o in outs]) for j in range(2))
+            return torch.cat(outs)
+
+        key = key + (nstr,)
         entry = cache.get(key)
         if entry is None:
             static = NS(encoder_out=inp.encoder_out.clone(), entities=inp.entities.clone(),

@@ -150,6 +150,22 @@ def test_fp32_beam_search_token_identical(variant):
             assert np.allclose(score.cpu().numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
 
 
+def test_fp32_beam_search_edge_cases_vs_oracle():
+    """One image, one step, widths 1 and 8 (the widest supported): the CUDA path against the oracle run live on the host."""
+    cfg = syn.SMALL_CONFIGS["K"]
+    dec = build_module(cfg, "cuda", torch.float32).eval()
+    p = oracle_params(cfg)
+    pb = syn.make_batch(cfg.with_batch(2), seed=5)
+    for T, k in ((1, 1), (1, 8), (5, 8), (4, 2)):
+        out, score = dec.beam_search_batch(pb["encoder_out"][:1].cuda(), T, pb["entities"][:1], pb["facts"][:1].cuda(), beam_size=k,
+                                           return_scores=True)
+        with torch.no_grad():
+            ref, margin = orc.beam_search(spec_for(cfg), p, pb["encoder_out"][:1], T, pb["entities"][:1], pb["facts"][:1], beam_size=k,
+                                          return_margin=True)
+        assert tuple(out.shape) == (1, T) and torch.isfinite(score).all()
+        assert margin < 1e-4 or out[0].cpu().tolist() == ref.tolist(), (T, k)
+
+
 def test_beam_search_properties_at_baseline_size():
     """bf16, knowledge-aware at the BASELINE shapes (E=301, F=51, V=10000), beam 5: size-independent properties."""
     cfg = syn.BASELINE_CONFIGS["knowledge_b128"].with_batch(6)

@@ -208,3 +208,23 @@ def test_dropout_hash_statistics(p):
     # each row / column keeps its own share close to 1-p
     assert float(k.mean(1).std()) < 1.3 * (p * (1 - p) / cols) ** 0.5
     assert float(k.mean(0).std()) < 1.3 * (p * (1 - p) / rows) ** 0.5
+
+
+def test_beam_search_edge_cases():
+    """One image, one step, widths 1 and 8 (the widest supported), and equality with the oracle on each."""
+    from helpers import oracle_params, spec_for
+    from oracle import decoder_oracle as orc
+
+    cfg = syn.SMALL_CONFIGS["K"]
+    dec = build_module(cfg, "cpu").eval()
+    p = oracle_params(cfg)
+    pb = syn.make_batch(cfg.with_batch(2), seed=5)
+    for T, k in ((1, 1), (1, 8), (5, 8), (4, 2)):
+        out, score = dec.beam_search_batch(pb["encoder_out"][:1], T, pb["entities"][:1], pb["facts"][:1], beam_size=k, return_scores=True)
+        with torch.no_grad():
+            ref, margin = orc.beam_search(spec_for(cfg), p, pb["encoder_out"][:1], T, pb["entities"][:1], pb["facts"][:1], beam_size=k,
+                                          return_margin=True)
+        assert tuple(out.shape) == (1, T) and torch.isfinite(score).all()
+        assert margin < 1e-4 or out[0].tolist() == ref.tolist(), (T, k)
+    with pytest.raises(AssertionError):
+        dec.beam_search_batch(pb["encoder_out"][:1], 3, pb["entities"][:1], pb["facts"][:1], beam_size=9)

@@ -700,7 +700,9 @@ class DecoderEngine:
         tok = [torch.full((R, Tmax), self.start, dtype=torch.int64, device=dev) for _ in range(2)]
         msk = [torch.zeros((R, Tmax), dtype=torch.int64, device=dev) for _ in range(2)]
         own = (torch.arange(R, dtype=torch.int32, device=dev) % G).unsqueeze(1).expand(R, Tmax)
-        anc = [own.contiguous() for _ in range(2)]  # anc[r, j]: slot of row r's ancestor at position j (own slot by default)
+        # anc[r, j]: slot of row r's ancestor at position j (own slot by default); two distinct buffers (clone: .contiguous() of
+        # an expanded (R, 1) view is the view itself)
+        anc = [own.clone(memory_format=torch.contiguous_format) for _ in range(2)]
         cum = torch.zeros(R, dtype=torch.float32, device=dev)
         ksel = torch.full((NI,), G, dtype=torch.int32, device=dev)
         best = torch.full((NI,), float("-inf"), dtype=torch.float32, device=dev)

@@ -244,6 +244,7 @@ class DecoderTransformer(nn.Module):
         st = self.__dict__.copy()
         st["_engine"] = None  # ctypes handles and device buffers are rebuilt lazily after unpickling (G/utils.py:32-46)
         st.pop("_decode_graphs", None)
+        st.pop("_decode_streams", None)
         st["_flat"] = None
         st["_packed_version"] = None
         return st

@@ -150,6 +150,22 @@ def test_fp32_beam_search_token_identical(variant):
             assert np.allclose(score.cpu().numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
 
 
+def test_module_pickles_after_graphed_decode(tmp_path):
+    """ut.save_checkpoint pickles whole modules (G/utils.py:32-46): a decoder that has run the graph-captured decode loops (CUDA
+    graphs, side streams and ctypes handles in its __dict__) must still pickle, and the reloaded module must decode the same tokens."""
+    cfg = syn.SMALL_CONFIGS["K"]
+    dec = build_module(cfg, "cuda", torch.float32).eval()
+    pb = syn.make_batch(cfg, seed=9)
+    args = (pb["encoder_out"].cuda(), 6, pb["entities"], pb["facts"].cuda())
+    t0 = dec.predict_batch(*args)
+    b0 = dec.beam_search_batch(*args, beam_size=3)
+    assert dec.__dict__.get("_decode_graphs")
+    path = tmp_path / "ckpt.pth.tar"
+    torch.save({"decoder": dec}, path)
+    dec2 = torch.load(path, weights_only=False)["decoder"]
+    assert torch.equal(dec2.predict_batch(*args), t0) and torch.equal(dec2.beam_search_batch(*args, beam_size=3), b0)
+
+
 def test_fp32_beam_search_edge_cases_vs_oracle():
     """One image, one step, widths 1 and 8 (the widest supported): the CUDA path against the oracle run live on the host."""
     cfg = syn.SMALL_CONFIGS["K"]

@@ -8,10 +8,17 @@ clamp(+-5) + Adam + operand re-pack (G/train.py:263-297) on synthetic inputs.
     python bench.py --impl reference [--steps K] [--warmup W]           reference arm: the CPU port of the reference
                                                                         (oracle/) on all host cores, same workload shape
 
+    python bench.py --workload geo_b32 | news_b8 | geo_e2e_b256          the other BASELINE.json configs (geo_e2e_b256 = configs[4]:
+                                                                        raw fp16 images -> image prep -> ResNet-101 on cuDNN ->
+                                                                        Encoder hand-off -> decoder train step)
+
 Prints ONE JSON line (rank 0).  `value` = whole-job captions/s with inputs resident in HBM; `e2e` = the same through the
 public call with pinned HOST buffers, H2D copies and a D2H read of the loss inside the timed region; `roofline` = the
 dominant kernel family of the step (CUDA-event time per launch, measured live in a separate instrumented pass over the
 same steps) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port timed on this box's host cores (N=1 only).
+Extras on the same line: `greedy_decode` (625 images per GPU through predict_batch, with `roofline_step_attention` = the per-step
+cross-attention kernel timed alone against the HBM peak), `beam5_decode` (beam search, an extension without a reference arm),
+`trimmed_padding` (dynamic padding) and, at N = 1, `encoder_e2e` (configs[4] in short).
 """
 import argparse
 import json

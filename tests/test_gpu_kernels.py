@@ -764,9 +764,11 @@ def test_mha_decode_tma_streaming_path(K, Hk, klen):
     Or = torch.zeros(B, H * 32, dtype=dtype)
     Hk.mha_decode(q, kv[:, : H * 32], kv[:, H * 32 :], Or, B, H, dh, klen * ldkv, klen * ldkv, klen)
     kg, qg = cu(kv), cu(q)
-    Og = torch.zeros(B, H * 32, dtype=dtype, device=DEV)
+    guard = torch.full((B + 2, H * 32 + 16), 7.0, dtype=dtype, device=DEV)  # canary rows / columns around the output
+    Og = guard[1 : B + 1, : H * 32]
     K.mha_decode(qg, kg[:, : H * 32], kg[:, H * 32 :], Og, B, H, dh, klen * ldkv, klen * ldkv, klen)
     assert err(Og, Or) < TOL[dtype]
+    assert bool((guard[0] == 7).all()) and bool((guard[-1] == 7).all()) and bool((guard[:, H * 32 :] == 7).all())
     wide = torch.zeros(B * klen, ldkv + 64, dtype=dtype, device=DEV)  # same rows, padded stride -> the CUDA-core kernel
     wide[:, :ldkv] = kg
     O2 = torch.zeros_like(Og)
@@ -816,3 +818,4 @@ def test_decode_chain(K, Hk, rows, ffn, proj_n):
     assert err(yg, yr) < TOL[dtype] and float(yg[:, D:].float().abs().max()) == 0.0
     if proj_n:
         assert err(pg, pr) < TOL[dtype]
+        assert float(big_g[:, :proj_n].float().abs().max()) == 0.0 and float(big_g[:, 2 * proj_n :].float().abs().max()) == 0.0  # canaries

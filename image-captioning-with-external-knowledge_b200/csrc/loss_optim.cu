@@ -316,6 +316,92 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
     }
 }
 
+// stage 1, register-resident variant for rows of at most TK_NT * TK_NPT columns (every shape of the reference): the whole row sits in
+// registers (all loads independent and in flight at once), the log-sum-exp is two branch-free passes over them, and each of the G
+// selection rounds is a branch-free thread-local argmax + a block argmax; the winning thread blanks its element.  The scan kernel
+// above keeps a sorted top-G list per thread, and with 40 elements per thread some lane of a warp inserts at almost every element:
+// the warp runs the divergent insertion path for the whole row (134 us per launch at 3125 rows x 10352 columns).  Same total order
+// (value descending, column ascending), hence the same candidates.
+constexpr int TK_NT = 512, TK_NPT = 24;
+template <int G>
+__global__ void __launch_bounds__(TK_NT) beam_row_topk_reg_kernel(const float* __restrict__ scores, int W, int lds, const float* __restrict__ cum,
+                                                                  const int* __restrict__ ksel, float* __restrict__ cand_v,
+                                                                  int* __restrict__ cand_i, int step) {
+    ick_pdl_entry();
+    __shared__ float red_a[TK_NT / 32], red_v[TK_NT / 32];
+    __shared__ int red_i[TK_NT / 32];
+    __shared__ float s_bcast;
+    __shared__ int s_win;
+    const int row = blockIdx.x, img = row / G, j = row % G, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = ksel[img];
+    if (k <= 0 || j >= (step == 0 ? 1 : k)) return;  // not a live beam
+    const float* s = scores + (size_t)row * lds;
+    float xs[TK_NPT];
+#pragma unroll
+    for (int u = 0; u < TK_NPT; ++u) {
+        const int c = tid + u * TK_NT;
+        xs[u] = c < W ? s[c] : -INFINITY;
+    }
+    float tm = xs[0];
+#pragma unroll
+    for (int u = 1; u < TK_NPT; ++u) tm = fmaxf(tm, xs[u]);
+    tm = warp_max(tm);
+    if (lane == 0) red_a[wid] = tm;
+    __syncthreads();
+    if (tid == 0) {
+        float M = red_a[0];
+        for (int w = 1; w < TK_NT / 32; ++w) M = fmaxf(M, red_a[w]);
+        s_bcast = M;
+    }
+    __syncthreads();
+    const float M = s_bcast;
+    float ts = 0.f;
+#pragma unroll
+    for (int u = 0; u < TK_NPT; ++u) ts += expf(xs[u] - M);  // exp(-inf) = 0 for the slots past the row
+    ts = warp_sum(ts);
+    __syncthreads();  // everybody has read s_bcast / thread 0 has read red_a
+    if (lane == 0) red_a[wid] = ts;
+    __syncthreads();
+    if (tid == 0) {
+        float L = 0.f;
+        for (int w = 0; w < TK_NT / 32; ++w) L += red_a[w];
+        s_bcast = M + logf(L);
+    }
+    __syncthreads();
+    const float logz = s_bcast, cj = cum[row];
+    for (int r = 0; r < G; ++r) {
+        float bv = xs[0];
+        int bu = 0;
+#pragma unroll
+        for (int u = 1; u < TK_NPT; ++u)
+            if (xs[u] > bv) { bv = xs[u]; bu = u; }
+        const int bi = bv == -INFINITY ? 0x7fffffff : tid + bu * TK_NT;
+        float v = bv;
+        int i = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+        if (lane == 0) { red_v[wid] = v; red_i[wid] = i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < TK_NT / 32; ++w)
+                if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) { v = red_v[w]; i = red_i[w]; }
+            s_win = i;
+            cand_v[(size_t)row * G + r] = i == 0x7fffffff ? -INFINITY : cj + (v - logz);
+            cand_i[(size_t)row * G + r] = i == 0x7fffffff ? i : j * W + i;
+        }
+        __syncthreads();
+        if (bi == s_win && bi != 0x7fffffff) {
+#pragma unroll
+            for (int u = 0; u < TK_NPT; ++u)
+                if (u == bu) xs[u] = -INFINITY;
+        }
+    }
+}
+
 // stage 2, one CTA per image: the k best of the live rows' candidate lists (each sorted), then the beam bookkeeping
 template <int G>
 __global__ void __launch_bounds__(64) beam_select_kernel(const float* __restrict__ cand_v, const int* __restrict__ cand_i, int W,
@@ -513,9 +599,18 @@ extern "C" int ick_beam_select(const float* scores, int W, int lds, float* cum, 
     if (images == 0) return ICK_OK;
     float* cand_v = (float*)workspace;
     int* cand_i = (int*)(cand_v + ncand);
+    static int scan_only = -1;  // ICK_BEAM_TOPK=scan: always the per-thread sorted-list kernel (A/B aid)
+    if (scan_only < 0) {
+        const char* e = getenv("ICK_BEAM_TOPK");
+        scan_only = (e && e[0] == 's') ? 1 : 0;
+    }
+    const bool reg_rows = !scan_only && W <= TK_NT * TK_NPT;
 #define ICK_BEAM_SEL(GG)                                                                                                               \
     case GG:                                                                                                                           \
-        ick_launch(beam_row_topk_kernel<GG>, images * GG, 256, 0, stream)(scores, W, lds, cum, ksel, cand_v, cand_i, step);              \
+        if (reg_rows)                                                                                                                  \
+            ick_launch(beam_row_topk_reg_kernel<GG>, images * GG, TK_NT, 0, stream)(scores, W, lds, cum, ksel, cand_v, cand_i, step);        \
+        else                                                                                                                           \
+            ick_launch(beam_row_topk_kernel<GG>, images * GG, 256, 0, stream)(scores, W, lds, cum, ksel, cand_v, cand_i, step);          \
         ick_launch(beam_select_kernel<GG>, images, 64, 0, stream)(cand_v, cand_i, W, cum, ksel, tok_in, mask_in, tok_out, mask_out, anc_in, \
                                                                    anc_out, best, result, step, Tmax, V, E, has_facts, end_tok, pad_tok); \
         break;

@@ -150,6 +150,21 @@ class Trainer:
     def train_step(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None) -> torch.Tensor:
         return self.step(self.prepare(captions, encoder_out, caption_masks, caption_lengths, entities, facts))
 
+    def validate_step(self, captions, encoder_out, caption_masks, caption_lengths, entities, facts=None) -> torch.Tensor:
+        """validate() of train.py (G/train.py:317-386): eval-mode forward (no dropout) and the packed cross-entropy, no gradient and
+        no update.  Returns a fresh device tensor [loss_sum, kept_tokens] (summed over the ranks under DDP); the reference's
+        `losses.avg` over an epoch is sum(loss_sum) / sum(kept_tokens) weighted the same way (mean over non-<pad> targets)."""
+        inp = self.prepare(captions, encoder_out, caption_masks, caption_lengths, entities, facts)
+        eng = self.eng
+        with torch.no_grad():
+            scores, _ = eng.forward(inp, train=False, seed=None)
+            acc, _ = eng.loss(scores, inp.captions, inp.decode_len, want_grad=False)
+        if self.distributed:
+            import torch.distributed as dist
+
+            dist.all_reduce(acc, group=self.pg)
+        return acc
+
     def run(self, host_batches):
         """
         Steady-state training loop over HOST batches (tuples in train.py's argument order, G/train.py:263-272; pinned memory

@@ -150,6 +150,24 @@ def test_fp32_beam_search_token_identical(variant):
             assert np.allclose(score.cpu().numpy()[ok], g[f"scores_{j}"][ok], atol=1e-3)
 
 
+def test_validate_step_vs_oracle_eval_loss():
+    """Trainer.validate_step (validate() of train.py, G/train.py:317-386): eval-mode loss of the CUDA path, fp32, against the oracle."""
+    from ickb200.trainer import Trainer
+
+    cfg = syn.SMALL_CONFIGS["K"]
+    batch = syn.make_batch(cfg, seed=6, equal_lengths=False)
+    dec = build_module(cfg, "cuda", torch.float32).train()
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0)
+    before = dec._get("fc_vocab.weight").detach().clone()
+    acc = tr.validate_step(*batch_args(cfg, to_dev(cfg, batch))).cpu()
+    p = oracle_params(cfg)
+    with torch.no_grad():
+        scores, caps, dl = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch))
+        ref = orc.caption_loss(scores, caps, dl)
+    assert abs(float(acc[0] / acc[1]) - float(ref)) < 1e-4
+    assert torch.equal(dec._get("fc_vocab.weight").detach(), before)
+
+
 def test_module_pickles_after_graphed_decode(tmp_path):
     """ut.save_checkpoint pickles whole modules (G/utils.py:32-46): a decoder that has run the graph-captured decode loops (CUDA
     graphs, side streams and ctypes handles in its __dict__) must still pickle, and the reloaded module must decode the same tokens."""

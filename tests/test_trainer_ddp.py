@@ -146,3 +146,22 @@ def test_sharded_generation_two_ranks_equals_single_process():
         p.join(timeout=600)
         assert p.exitcode == 0
     assert got_g == ref_g and got_b == ref_b
+
+
+def test_validate_step_is_the_eval_mode_loss():
+    """Trainer.validate_step = train.py's validate() body (G/train.py:317-386): decoder in eval mode, same packed CE, no update."""
+    cfg = syn.SMALL_CONFIGS["K"]
+    batch = syn.make_batch(cfg, seed=6, equal_lengths=False)
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu").train()  # default dropouts 0.5/0.5/0.1: validate_step must not apply them
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0)
+    before = {k: v.detach().clone() for k, v in dec.named_parameters()}
+    acc = tr.validate_step(*batch_args(cfg, batch))
+    p = oracle_params(cfg)
+    with torch.no_grad():
+        scores, caps, dl = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch))
+        ref = orc.caption_loss(scores, caps, dl)
+    assert abs(float(acc[0] / acc[1]) - float(ref)) < 1e-4
+    assert float(acc[1]) == float(sum(1 for b, n in enumerate(dl) for t in range(n) if int(caps[b, t + 1]) != 0))
+    for k, v in dec.named_parameters():
+        assert torch.equal(v.detach(), before[k]), k

@@ -60,7 +60,7 @@ class CaptionBatchSource:
     reference's fp32 tensor bit for bit):
         geo:                  (raw_images, captions, caplens, capmasks, entity_features, entity_names)
         knowledge / news:     (..., facts, fact_names)
-    File parsing (HDF5 / JSON / pickle) is left to the caller: pass the loaded objects.
+    ``from_files`` opens the reference's files by their names (JSON / pickle with the standard library, HDF5 through h5py if installed).
     """
 
     def __init__(self, images, captions, caplens, capmasks, entity_features, entity_names, facts=None, fact_names=None,
@@ -78,6 +78,42 @@ class CaptionBatchSource:
         for t in (self.caplens, self.capmasks, self.entity_features, self.entity_names, self.facts, self.fact_names):
             assert t is None or t.shape[0] == n, "all per-caption arrays must have one row per caption"
         assert len(images) == n, "one image per caption (the reference stores one caption per image row)"
+
+    @classmethod
+    def from_files(cls, data_dir: str, data_name: str, split: str, images=None, pin_memory: bool = True) -> "CaptionBatchSource":
+        """
+        The files CaptionDataset.__init__ opens (G/datasets.py:19-41, K/datasets.py:19-49), same names:
+        ``<split>_CAPTIONS_``, ``_CAPLENS_``, ``_CAPMASKS_<data_name>.json``; ``_ENT_FEATURES_``, ``_ENT_NAMES_`` and, when present,
+        ``_FACTS_``, ``_FACT_NAMES_<data_name>.pkl``; images from ``<split>_IMAGES_<data_name>.hdf5`` (dataset "images") unless an
+        array-like is passed - h5py is imported only then, and its absence is an error, not a silent fallback.
+        """
+        import json
+        import os
+        import pickle
+
+        assert split in {"TRAIN", "VAL", "TEST"}
+
+        def path(kind, ext):
+            return os.path.join(data_dir, f"{split}_{kind}_{data_name}.{ext}")
+
+        def load_json(kind):
+            with open(path(kind, "json"), "r") as f:
+                return json.load(f)
+
+        def load_pkl(kind, required=True):
+            if not required and not os.path.exists(path(kind, "pkl")):
+                return None
+            with open(path(kind, "pkl"), "rb") as f:
+                return pickle.load(f)
+
+        if images is None:
+            try:
+                import h5py
+            except ImportError as e:
+                raise ImportError("CaptionBatchSource.from_files needs h5py to open the image file; pass `images=` otherwise") from e
+            images = h5py.File(path("IMAGES", "hdf5"), "r")["images"]
+        return cls(images, load_json("CAPTIONS"), load_json("CAPLENS"), load_json("CAPMASKS"), load_pkl("ENT_FEATURES"),
+                   load_pkl("ENT_NAMES"), load_pkl("FACTS", required=False), load_pkl("FACT_NAMES", required=False), pin_memory=pin_memory)
 
     def __len__(self) -> int:
         return self.captions.shape[0]

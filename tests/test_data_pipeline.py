@@ -64,3 +64,31 @@ def test_epoch_covers_every_caption_once():
         seen += [tuple(c.tolist()) for c in caps]
     assert sorted(seen) == sorted(tuple(c) for c in st["captions"])
     assert len(list(src.batches(4, shuffle=False, drop_last=True))) == 2
+
+
+def test_from_files_reads_the_reference_file_layout(tmp_path):
+    """The JSON / pickle files CaptionDataset opens (K/datasets.py:19-49), written with the reference's names; images passed in
+    (h5py is not installed here - and without `images=` that must be an ImportError, not a fallback)."""
+    import json
+    import pickle
+
+    import pytest
+
+    cfg, st = make_store(n=6, seed=2)
+    name = "synthetic_5_cap_per_img"
+    for kind, key in (("CAPTIONS", "captions"), ("CAPLENS", "caplens"), ("CAPMASKS", "capmasks")):
+        with open(tmp_path / f"VAL_{kind}_{name}.json", "w") as f:
+            json.dump(st[key], f)
+    for kind, key in (("ENT_FEATURES", "entity_features"), ("ENT_NAMES", "entity_names"), ("FACTS", "facts"), ("FACT_NAMES", "fact_names")):
+        with open(tmp_path / f"VAL_{kind}_{name}.pkl", "wb") as f:
+            pickle.dump(st[key], f)
+    src = CaptionBatchSource.from_files(str(tmp_path), name, "VAL", images=st["imgs"], pin_memory=False)
+    ref = CaptionBatchSource(st["imgs"], st["captions"], st["caplens"], st["capmasks"], st["entity_features"], st["entity_names"],
+                             st["facts"], st["fact_names"], pin_memory=False)
+    for a, b in zip(src.batch([4, 1, 5]), ref.batch([4, 1, 5])):
+        assert torch.equal(a, b)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            CaptionBatchSource.from_files(str(tmp_path), name, "VAL", pin_memory=False)

@@ -68,6 +68,25 @@ class Trainer:
         self._lr *= shrink_factor
         self.lr_dev.fill_(self._lr)
 
+    # ---- checkpoint / resume (the reference pickles the optimizer object next to the modules, G/utils.py:32-46, G/train.py:102-129) ----
+    def state_dict(self) -> dict:
+        """Everything the fused optimizer needs to resume: Adam moments in the decoder's flat parameter order, the step counter
+        (bias corrections, dropout seed offset), learning rate and seed base.  The weights themselves live in the decoder."""
+        return {"m": self.m.detach().cpu().clone(), "v": self.v.detach().cpu().clone(), "step": int(self.step_dev.item()),
+                "lr": float(self._lr), "betas": tuple(self.betas), "eps": float(self.eps), "clip": float(self.clip),
+                "seed_base": int(self.seed_base), "n_params": int(self.n)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if int(sd["n_params"]) != self.n:
+            raise ValueError(f"optimizer state for {sd['n_params']} parameters does not fit a decoder with {self.n}")
+        self.m.copy_(sd["m"].to(self.m.device))
+        self.v.copy_(sd["v"].to(self.v.device))
+        self.step_dev.fill_(int(sd["step"]))
+        self._lr = float(sd["lr"])
+        self.lr_dev.fill_(self._lr)
+        self.betas, self.eps, self.clip = tuple(sd["betas"]), float(sd["eps"]), float(sd["clip"])
+        self.seed_base = int(sd["seed_base"])
+
     def trimmed_width(self, captions) -> int:
         """Width that keeps every non-<pad> token of the batch (multiple of 8, at least 8).  A host tensor costs nothing; a
         device tensor costs one small D2H sync."""

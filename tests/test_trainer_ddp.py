@@ -165,3 +165,32 @@ def test_validate_step_is_the_eval_mode_loss():
     assert float(acc[1]) == float(sum(1 for b, n in enumerate(dl) for t in range(n) if int(caps[b, t + 1]) != 0))
     for k, v in dec.named_parameters():
         assert torch.equal(v.detach(), before[k]), k
+
+
+def test_trainer_state_dict_resumes_exactly(tmp_path):
+    """Checkpoint / resume of the fused optimizer (the reference pickles its optimizer, G/utils.py:32-46, G/train.py:102-129): two
+    steps, save decoder + trainer state, reload into fresh objects, one more step == three uninterrupted steps, bit for bit
+    (train-mode dropout included: the mask stream is a function of seed base + step)."""
+    cfg = syn.SMALL_CONFIGS["G"]
+    batch = syn.make_batch(cfg, seed=8, equal_lengths=False)
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    torch.manual_seed(1234)
+    dec_a = build_module(cfg, "cpu", dropouts=(0.3, 0.3, 0.1)).train()
+    tr_a = Trainer(dec_a, lr=4e-4, grad_clip=5.0)
+    for _ in range(3):
+        acc_a = tr_a.train_step(*batch_args(cfg, batch)).clone()
+    torch.manual_seed(1234)
+    dec_b = build_module(cfg, "cpu", dropouts=(0.3, 0.3, 0.1)).train()
+    tr_b = Trainer(dec_b, lr=4e-4, grad_clip=5.0)
+    for _ in range(2):
+        tr_b.train_step(*batch_args(cfg, batch))
+    path = tmp_path / "ckpt.pth.tar"
+    torch.save({"decoder": dec_b, "trainer": tr_b.state_dict()}, path)
+    ck = torch.load(path, weights_only=False)
+    dec_c = ck["decoder"].train()
+    tr_c = Trainer(dec_c, lr=1.0, grad_clip=None)  # deliberately wrong hyper-parameters: load_state_dict must restore them
+    tr_c.load_state_dict(ck["trainer"])
+    acc_c = tr_c.train_step(*batch_args(cfg, batch)).clone()
+    assert torch.equal(acc_a, acc_c)
+    for (k, pa), (_, pc) in zip(dec_a.named_parameters(), dec_c.named_parameters()):
+        assert torch.equal(pa.detach(), pc.detach()), k

@@ -132,3 +132,72 @@ def test_image_prep_oracle_is_the_reference_host_pipeline():
     norm = T.Compose([T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
     ref = torch.stack([norm(torch.FloatTensor(a[i] / 255.0)) for i in range(a.shape[0])])
     assert torch.equal(orc.prepare_images(a), ref)
+
+
+# ---- BASELINE shapes (E, F, T, V of SURVEY.md §8d, batch 8): fixtures of the unmodified reference, reference-scale weights --------
+def check_scores_against_base_golden(scores, g, V, tol, what=""):
+    """Strided grid over all columns, all pointer columns at every third position (normalised max error), row logsumexp / max
+    (absolute, on the logit scale) of `scores` against the BASELINE-shape fixture."""
+    from helpers import score_views
+
+    v = score_views(scores, V)
+    scale = float(np.abs(g["s_grid"]).max())
+    assert nmax_err(v["s_grid"], g["s_grid"]) < tol, what
+    assert float(np.abs(v["s_ptr"] - g["s_ptr"]).max()) < tol * scale, what
+    assert float(np.abs(v["s_lse"] - g["s_lse"]).max()) < tol * max(scale, 1.0), what
+    assert float(np.abs(v["s_rowmax"] - g["s_rowmax"]).max()) < tol * scale, what
+    return v
+
+
+def check_grads_against_base_golden(named_grads, g, tol):
+    for k, gr in named_grads:
+        gr = gr.detach().cpu().float()
+        ref_norm = float(g[f"gnorm_{k}"])
+        assert abs(float(gr.double().norm()) - ref_norm) <= tol * max(ref_norm, 1e-6), k
+        if f"grad_{k}" in g:
+            assert nmax_err(gr, g[f"grad_{k}"]) < tol or ref_norm < 1e-12, k
+        elif f"gradrows_{k}" in g:
+            rows = gr.reshape(gr.shape[0], -1)[:: max(1, gr.shape[0] // 7)][:, :64]
+            ref = g[f"gradrows_{k}"]
+            assert float((rows.double() - torch.as_tensor(ref).double()).abs().max()) <= tol * max(float(np.abs(ref).max()), 1e-6) + 1e-9, k
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_baseline_shape_forward_loss_grads(variant):
+    from helpers import load_base_golden
+
+    cfg = syn.BASE_PARITY_CONFIGS[variant]
+    g = load_base_golden(variant)
+    p = oracle_params(cfg, requires_grad=True, profile="reference")
+    chk = sum(float(v.detach().double().abs().sum()) for k, v in sorted(p.items()) if not k.endswith("pe"))
+    assert abs(chk - float(g["weights_checksum"])) <= 1e-9 * abs(chk)
+    batch = syn.make_batch(cfg, seed=int(g["seed"]))
+    for k, v in batch.items():
+        assert abs(float(v.double().abs().sum()) - float(g[f"insum_{k}"])) <= 1e-9 * max(1.0, float(g[f"insum_{k}"])), k
+    batch["encoder_out"].requires_grad_(True)
+    scores, caps, dl = orc.forward(spec_for(cfg), p, *batch_args(cfg, batch))
+    assert np.array_equal(caps.numpy(), g["captions_sorted"]) and dl == g["decode_lengths"].tolist()
+    v = check_scores_against_base_golden(scores, g, cfg.V, 1e-4)
+    assert float((v["s_argmax"] == g["s_argmax"]).mean()) > 0.999
+    loss = orc.caption_loss(scores, caps, dl)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    loss.backward()
+    ge = batch["encoder_out"].grad
+    assert nmax_err(ge[:, ::29, ::11], g["grad_encoder_out_rows"]) < 1e-3
+    assert abs(float(ge.double().norm()) - float(g["gnorm_encoder_out"])) <= 1e-3 * float(g["gnorm_encoder_out"])
+    check_grads_against_base_golden(((k, v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()
+                                     if k != "pos_encoder.pe"), g, 1e-3)
+
+
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_baseline_shape_predict_tokens(variant):
+    from helpers import load_base_golden
+
+    cfg = syn.BASE_PARITY_CONFIGS[variant]
+    g = load_base_golden(variant)
+    p = oracle_params(cfg, profile="reference")
+    pb = syn.make_batch(cfg, seed=int(g["predict_seed"]))
+    T = int(g["predict_max_len"])
+    with torch.no_grad():  # one image here (0.4 s of un-cached decoding); the GPU tests cover all four
+        out = orc.predict(spec_for(cfg), p, pb["encoder_out"][:1], T, pb["entities"][:1], pb["facts"][:1] if cfg.has_facts else None)
+    assert out.reshape(-1).tolist() == g["predict_tokens"][0].tolist()

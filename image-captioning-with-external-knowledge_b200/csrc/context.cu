@@ -332,6 +332,51 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
     }
 }
 
+// Backward of pool_rows: d rows (B*Hout*Wout, ldo) -> d x (B, C, Hin, Win) fp32.  An input pixel receives, from every output
+// cell whose window covers it, that cell's gradient divided by the window size (AdaptiveAvgPool2d backward).  One CTA per
+// (64-channel slab, image): the slab of the row gradients is staged in shared memory by coalesced reads along the channel
+// axis, then every (channel, pixel) sums over the (contiguous) range of output rows / columns that cover it.
+template <typename T>
+__global__ void __launch_bounds__(256) pool_rows_bwd_kernel(const T* __restrict__ drows, float* __restrict__ dx, int C, int Hin, int Win,
+                                                            int Hout, int Wout, int ldo) {
+    ick_pdl_entry();
+    extern __shared__ float planes[];  // [nout][PR_C + 1] gradients, then per input row / column: (first cell, last cell) covering it
+    const int b = blockIdx.y, c0 = blockIdx.x * PR_C;
+    const int npix = Hin * Win, nout = Hout * Wout, cst = PR_C + 1;
+    int2* yr = reinterpret_cast<int2*>(planes + ((nout * cst + 1) & ~1));
+    int2* xr = yr + Hin;
+    for (int i = threadIdx.x; i < Hin + Win; i += blockDim.x) {
+        const bool isy = i < Hin;
+        const int v = isy ? i : i - Hin, nin = isy ? Hin : Win, no = isy ? Hout : Wout;
+        int lo = no, hi = -1;
+        for (int o = 0; o < no; ++o) {
+            const int a0 = (o * nin) / no, a1 = ((o + 1) * nin + no - 1) / no;
+            if (a0 <= v && v < a1) { lo = o < lo ? o : lo; hi = o; }
+        }
+        (isy ? yr : xr)[v] = make_int2(lo, hi);
+    }
+    for (int idx = threadIdx.x; idx < nout * PR_C; idx += blockDim.x) {
+        const int o = idx / PR_C, c = idx - o * PR_C;
+        planes[o * cst + c] = c0 + c < C ? to_f(drows[((size_t)b * nout + o) * ldo + c0 + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PR_C * npix; idx += blockDim.x) {
+        const int c = idx / npix, p = idx - c * npix;
+        if (c0 + c >= C) break;
+        const int y = p / Win, x = p - y * Win;
+        const int2 ry = yr[y], rx = xr[x];
+        float acc = 0.f;
+        for (int oy = ry.x; oy <= ry.y; ++oy) {
+            const int hy = ((oy + 1) * Hin + Hout - 1) / Hout - (oy * Hin) / Hout;
+            for (int ox = rx.x; ox <= rx.y; ++ox) {
+                const int wx = ((ox + 1) * Win + Wout - 1) / Wout - (ox * Win) / Wout;
+                acc += planes[(oy * Wout + ox) * cst + c] / (float)(hy * wx);
+            }
+        }
+        dx[((size_t)b * C + c0 + c) * npix + p] = acc;
+    }
+}
+
 // ---- image preparation (the input pipeline's device half) ------------------------------------------------------
 // The HDF5 files hold images as fp16 (N, 3, H, W) with values in [0, 255] (G/create_input_files.py:99-101, :334-337);
 // CaptionDataset.__getitem__ divides by 255 (numpy fp16 array / python float -> fp16 result), converts to fp32
@@ -949,6 +994,23 @@ extern "C" int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int 
     else if (dt == ICK_BF16) ick_launch(pool_rows_kernel<bf16>, grid, 256, smem, stream)(x, (bf16*)rows, C, Hin, Win, Hout, Wout, ldo);
     else ICK_BAD_DT("pool_rows_fwd", dt);
     return ick_check_launch("pool_rows_fwd");
+}
+
+extern "C" int ick_pool_rows_bwd(const void* drows, float* dx, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
+                                 cudaStream_t stream) {
+    ICK_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && ldo >= C, "pool_rows_bwd: bad sizes");
+    const size_t smem = (size_t)((Hout * Wout * (PR_C + 1) + 1) & ~1) * sizeof(float) + (size_t)(Hin + Win) * sizeof(int2);
+    ICK_REQUIRE(smem <= 100 * 1024, "pool_rows_bwd: %d x %d output cells do not fit the staging buffer", Hout, Wout);
+    if (B == 0) return ICK_OK;
+    dim3 grid((C + PR_C - 1) / PR_C, B);
+    if (dt == ICK_F32) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pool_rows_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ick_launch(pool_rows_bwd_kernel<float>, grid, 256, smem, stream)((const float*)drows, dx, C, Hin, Win, Hout, Wout, ldo);
+    } else if (dt == ICK_BF16) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(pool_rows_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ick_launch(pool_rows_bwd_kernel<bf16>, grid, 256, smem, stream)((const bf16*)drows, dx, C, Hin, Win, Hout, Wout, ldo);
+    } else ICK_BAD_DT("pool_rows_bwd", dt);
+    return ick_check_launch("pool_rows_bwd");
 }
 
 extern "C" int ick_image_prep(const void* raw_f16, void* out, int dt, long long N, int C, int HW, const float* mean, const float* stdev,

@@ -292,6 +292,10 @@ class CudaKernels:
         self._call("ick_pool_rows_fwd", _p(x), _p(rows), dt_of(rows), B, C, Hin, Win, Hout, Wout, _ld(rows),
                    work=lambda: (x.numel() * 4 + B * Hout * Wout * C * rows.element_size(), 0))
 
+    def pool_rows_bwd(self, drows, dx, B, C, Hin, Win, Hout, Wout):
+        self._call("ick_pool_rows_bwd", _p(drows), _p(dx), dt_of(drows), B, C, Hin, Win, Hout, Wout, _ld(drows),
+                   work=lambda: (dx.numel() * 4 + B * Hout * Wout * C * drows.element_size(), 0))
+
     def image_prep(self, raw, out, mean, std, channels_last=False):
         """raw (N, 3, H, W) fp16 in [0, 255] (the HDF5 storage format) -> out = ((raw / 255 in fp16) - mean[c]) / std[c], fp32 or bf16,
         NCHW or channels-last memory order (include/ickb200.h: ick_image_prep)."""

@@ -43,13 +43,21 @@ class Encoder(nn.Module):
 
         self.emb_dim = emb_dim
         self.compute_dtype = compute_dtype  # dtype of the hand-off GEMM (None: ICKB200_DTYPE / bf16)
-        resnet = None
         if pretrained:  # the reference always asks for the ImageNet weights (G/models.py:24)
             try:
-                resnet = torchvision.models.resnet101(pretrained=True)
-            except Exception:  # no network / no cached weights: random init, same architecture
-                resnet = None
-        if resnet is None:
+                resnet = torchvision.models.resnet101(weights=torchvision.models.ResNet101_Weights.IMAGENET1K_V1)
+            except Exception as e:  # no network and no cached weights
+                if os.environ.get("ICKB200_ALLOW_RANDOM_TRUNK") != "1":
+                    raise RuntimeError(
+                        "Encoder(pretrained=True): the ImageNet ResNet-101 weights could not be loaded "
+                        f"({type(e).__name__}: {e}).  The reference always starts from them (G/models.py:24); pass "
+                        "pretrained=False (or set ICKB200_ALLOW_RANDOM_TRUNK=1) to build a randomly initialised trunk on purpose."
+                    ) from e
+                import warnings
+
+                warnings.warn(f"Encoder: ImageNet weights unavailable ({e}); RANDOM trunk (ICKB200_ALLOW_RANDOM_TRUNK=1)")
+                resnet = torchvision.models.resnet101(weights=None)
+        else:
             resnet = torchvision.models.resnet101(weights=None)
         self.resnet = nn.Sequential(*list(resnet.children())[:-2])
         self.adaptive_pool = nn.AdaptiveAvgPool2d((encoded_image_size, encoded_image_size))
@@ -62,29 +70,53 @@ class Encoder(nn.Module):
     def head(self, feats):
         """
         Trunk output (B, encoder_dim, h, w) -> (B, emb_dim, 14*14): AdaptiveAvgPool2d + 1x1 conv + view (G/models.py:43-46).
-        On a CUDA device without autograd through ``conv1`` (eval.py, or train.py's frozen encoder under ``torch.no_grad``)
-        this is the B200 hand-off path: one pooling kernel that writes the GEMM's K-major A operand, the 1x1 convolution as a
-        tcgen05 GEMM with the bias in its epilogue, one transpose to the channel-major layout the reference returns.  When
-        ``conv1`` (or the trunk) needs gradients the stock PyTorch ops run, so autograd semantics are unchanged.
+        On a CUDA device this is ALWAYS the B200 hand-off path: one pooling kernel that writes the GEMM's K-major A operand, the
+        1x1 convolution as a tcgen05 GEMM with the bias in its epilogue, one transpose to the channel-major layout the reference
+        returns.  Under autograd - the reference's own call sites run with gradients enabled and conv1.requires_grad = True
+        (G/train.py:269, G/eval.py:77-83, G/models.py:32) - the same kernels run inside one autograd node (_EncoderHeadFn) whose
+        backward is hand-written: conv1's weight / bias gradient on the tensor-core wgrad kernel, and, when the trunk is being
+        fine-tuned, the input gradient (dgrad GEMM + pooling backward).  A CPU tensor takes the stock ops (the trunk itself is
+        stock PyTorch and may legitimately run anywhere; the decoder has no CPU path).
         """
-        needs_grad = torch.is_grad_enabled() and (feats.requires_grad or self.conv1.weight.requires_grad or self.conv1.bias.requires_grad)
-        if not feats.is_cuda or needs_grad:
+        if not feats.is_cuda:
             out = self.conv1(self.adaptive_pool(feats))
             return out.view(out.shape[0], self.emb_dim, -1)
+        needs_grad = torch.is_grad_enabled() and (feats.requires_grad or self.conv1.weight.requires_grad or self.conv1.bias.requires_grad)
+        if needs_grad:
+            return _EncoderHeadFn.apply(self, feats, self.conv1.weight, self.conv1.bias)
+        return self._head_fwd(feats)[0]
+
+    def _kernels_and_dtype(self):
         from .kernels import CudaKernels
 
         K = self.__dict__.get("_kernels")
         if K is None:
             K = self.__dict__["_kernels"] = CudaKernels()
-        dt = getattr(self, "compute_dtype", None) or _default_dtype()
+        return K, (getattr(self, "compute_dtype", None) or _default_dtype())
+
+    def repack(self) -> None:
+        """Drop the packed copy of conv1 (see DecoderTransformer.repack: needed after writes through ``.data``)."""
+        self.__dict__.pop("_wver", None)
+
+    def train(self, mode: bool = True):
+        self.__dict__.pop("_wver", None)
+        return super().train(mode)
+
+    def _head_fwd(self, feats):
+        K, dt = self._kernels_and_dtype()
         B, C, h, w = feats.shape
         ho, wo = self.adaptive_pool.output_size
         P, D = ho * wo, self.emb_dim
         ldo = (D + 7) // 8 * 8
-        # packed copy of the (frozen) 1x1 convolution, refreshed when the parameter changes
-        ver = (self.conv1.weight._version, self.conv1.weight.data_ptr(), dt)
+        # packed copies of the 1x1 convolution (K-major weight, its transpose for the input gradient), refreshed when the
+        # parameter changes
+        ver = (self.conv1.weight._version, self.conv1.weight.data_ptr(), self.conv1.bias._version, dt)
         if self.__dict__.get("_wver") != ver:
-            self.__dict__["_wpack"] = self.conv1.weight.detach().view(D, C).to(dt).contiguous()
+            w2 = self.conv1.weight.detach().view(D, C)
+            self.__dict__["_wpack"] = w2.to(dt).contiguous()
+            wt = torch.zeros(C, ldo, dtype=dt, device=w2.device)
+            wt[:, :D] = w2.t()
+            self.__dict__["_wtpack"] = wt
             self.__dict__["_bpack"] = self.conv1.bias.detach().float().contiguous()
             self.__dict__["_wver"] = ver
         rows = torch.empty(B * P, C, dtype=dt, device=feats.device)
@@ -93,11 +125,43 @@ class Encoder(nn.Module):
         K.gemm(rows, self.__dict__["_wpack"], y[:, :D], bias=self.__dict__["_bpack"])
         out = torch.empty(B, D, P, dtype=torch.float32, device=feats.device)
         K.pixels_bwd(y, out, B, D, P, P)
-        return out
+        return out, rows
+
+    def _head_bwd(self, dout, rows, feat_shape, need_w, need_b, need_x):
+        """dout (B, D, P) fp32 -> (d feats | None, d conv1.weight | None, d conv1.bias | None), all through the C ABI."""
+        K, dt = self._kernels_and_dtype()
+        B, C, h, w = feat_shape
+        ho, wo = self.adaptive_pool.output_size
+        P, D = ho * wo, self.emb_dim
+        ldo = (D + 7) // 8 * 8
+        dev = dout.device
+        dy = torch.zeros(B * P, ldo, dtype=dt, device=dev)
+        K.pixels_fwd(dout.contiguous().float(), dy, B, D, P, P)  # (B, D, P) -> rows (b, p) x D: the transpose of the hand-off
+        dW = dB = dX = None
+        if need_w or need_b:
+            # flat fp32 gradient buffer [weight (D, C) | bias (D)], index maps as the decoder's packing maps
+            key = (D, C, str(dev))
+            if self.__dict__.get("_gmaps_key") != key:
+                self.__dict__["_gmaps"] = (torch.arange(D, dtype=torch.int32, device=dev) * C, torch.arange(C, dtype=torch.int32, device=dev),
+                                           torch.arange(D, dtype=torch.int32, device=dev) + D * C)
+                self.__dict__["_gmaps_key"] = key
+            rowoff, colmap, biasoff = self.__dict__["_gmaps"]
+            g = torch.zeros(D * C + D, dtype=torch.float32, device=dev)
+            K.wgrad(dy[:, :D], rows, g, rowoff, colmap, biasoff)
+            if need_w:
+                dW = g[: D * C].view(D, C, 1, 1)
+            if need_b:
+                dB = g[D * C :]
+        if need_x:
+            drows = torch.empty(B * P, C, dtype=dt, device=dev)
+            K.gemm(dy, self.__dict__["_wtpack"], drows)  # d rows = d y @ W   (W^T stored K-major, pad columns zero)
+            dX = torch.empty(B, C, h, w, dtype=torch.float32, device=dev)
+            K.pool_rows_bwd(drows, dX, B, C, h, w, ho, wo)
+        return dX, dW, dB
 
     def __getstate__(self):  # checkpoints pickle whole modules (G/utils.py:32-46): drop the device-side caches
         d = dict(self.__dict__)
-        for k in ("_kernels", "_wpack", "_bpack", "_wver"):
+        for k in ("_kernels", "_wpack", "_wtpack", "_bpack", "_wver", "_gmaps", "_gmaps_key"):
             d.pop(k, None)
         return d
 
@@ -117,6 +181,23 @@ def _register(root: nn.Module, key: str, param: nn.Parameter) -> None:
             m.add_module(name, nn.Module())
         m = m._modules[name]
     m.register_parameter(parts[-1], param)
+
+
+class _EncoderHeadFn(torch.autograd.Function):
+    """Encoder hand-off under autograd: forward = the pooling / GEMM / transpose kernels, backward hand-written (Encoder._head_bwd)."""
+
+    @staticmethod
+    def forward(ctx, module, feats, weight, bias):
+        out, rows = module._head_fwd(feats)
+        ctx.module, ctx.rows, ctx.shape = module, rows, tuple(feats.shape)
+        ctx.need = (feats.requires_grad, weight.requires_grad, bias.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        need_x, need_w, need_b = ctx.need
+        dX, dW, dB = ctx.module._head_bwd(dout, ctx.rows, ctx.shape, need_w, need_b, need_x)
+        return None, dX, dW, dB
 
 
 class _DecoderFn(torch.autograd.Function):
@@ -191,6 +272,7 @@ class DecoderTransformer(nn.Module):
             self.add_module("pos_encoder", nn.Module())
         self.pos_encoder.register_buffer("pe", pe.unsqueeze(0).transpose(0, 1))
         self._flat = flat
+        self._flat_gen = 0  # bumped whenever the flat parameter buffer is re-gathered (captured graphs bake its addresses)
         self._engine: Optional[DecoderEngine] = None
         self._packed_version = None
         self._step = 0
@@ -240,6 +322,24 @@ class DecoderTransformer(nn.Module):
         """G/models.py:282-289."""
         self._get("word_embedding.weight").requires_grad = fine_tune
 
+    def repack(self) -> None:
+        """
+        Refresh the packed bf16 / transposed operand copies from the fp32 parameters NOW.  The module re-packs by itself when a
+        parameter's autograd version changes (optimizer.step(), copy_, load_state_dict) and on every train() / eval()
+        transition; writes that bypass the version counter - ``p.data.uniform_()`` (the reference's own idiom in init_weights,
+        G/models.py:264-272), EMA or weight surgery through ``.data`` - need this call (or a train()/eval() switch) before the
+        next forward.  Replaced storages (``p.data = ...``, ``load_state_dict(assign=True)``) are detected by address.
+        """
+        self._packed_version = None
+        self._ensure_engine()
+
+    invalidate = repack
+
+    def train(self, mode: bool = True):
+        # a cheap safety net for `.data` writes done between epochs: one re-pack launch per train()/eval() switch
+        self._packed_version = None
+        return super().train(mode)
+
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engine"] = None  # ctypes handles and device buffers are rebuilt lazily after unpickling (G/utils.py:32-46)
@@ -276,7 +376,11 @@ class DecoderTransformer(nn.Module):
                     p.data = flat[off : off + cnt].view(p.shape)
                     off += cnt
             self._flat = flat
+            self._flat_gen = getattr(self, "_flat_gen", 0) + 1
             self._packed_version = None
+            # captured decode loops (and the Trainer's captured steps, keyed on _flat_gen) read fp32 parameters - LayerNorm
+            # weights, fc_entity, the type embedding - at addresses inside the OLD flat buffer
+            self.__dict__.pop("_decode_graphs", None)
             if self._engine is not None and self._engine.device != dev:
                 self._engine = None
         if self._engine is None:

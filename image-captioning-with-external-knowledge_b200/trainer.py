@@ -42,12 +42,23 @@ class Trainer:
         self.distributed = distributed
         self.pg = process_group
         self.seed_base = int(torch.initial_seed()) & 0x7FFFFFFF
+        self.rank = 0
+        if distributed:
+            import torch.distributed as dist
+
+            # Replicas must start identical: rank 0's parameters (and moments) win, whatever each rank seeded.  This first
+            # collective also creates the NCCL communicator outside of any graph capture.  The dropout seed is rank-dependent:
+            # with one seed every rank would draw the SAME masks for its different shard (rows are numbered per rank).
+            self.rank = dist.get_rank(process_group)
+            for t in (self.eng.P, self.m, self.v):
+                dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+            self.eng.repack()
+            self.seed_base = (self.seed_base + self.rank * 0x9E3779B1) & 0x7FFFFFFF
         # device-resident step state: read by the kernels at run time (graph replay needs no new kernel arguments)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=dev)
         self._lr = lr
-        # parameters that the reference would not update (requires_grad False) keep a zero gradient
-        self._frozen = [k for k in decoder._param_names if not decoder._get(k).requires_grad]
+        self._skip_collective = False  # set around the capture warm-up step (see _capture)
         self.use_graph = use_graph
         self._graph = None
         self._static = None
@@ -74,7 +85,7 @@ class Trainer:
         (bias corrections, dropout seed offset), learning rate and seed base.  The weights themselves live in the decoder."""
         return {"m": self.m.detach().cpu().clone(), "v": self.v.detach().cpu().clone(), "step": int(self.step_dev.item()),
                 "lr": float(self._lr), "betas": tuple(self.betas), "eps": float(self.eps), "clip": float(self.clip),
-                "seed_base": int(self.seed_base), "n_params": int(self.n)}
+                "seed_base": int(self.seed_base), "rank": int(self.rank), "n_params": int(self.n)}
 
     def load_state_dict(self, sd: dict) -> None:
         if int(sd["n_params"]) != self.n:
@@ -85,7 +96,18 @@ class Trainer:
         self._lr = float(sd["lr"])
         self.lr_dev.fill_(self._lr)
         self.betas, self.eps, self.clip = tuple(sd["betas"]), float(sd["eps"]), float(sd["clip"])
-        self.seed_base = int(sd["seed_base"])
+        # a checkpoint written by another rank (rank 0 saves) must not hand its rank-mixed seed to this one
+        self.seed_base = (int(sd["seed_base"]) + (self.rank - int(sd.get("rank", 0))) * 0x9E3779B1) & 0x7FFFFFFF
+        self.invalidate_graphs()  # betas / eps / clip / seed_base are by-value kernel arguments of the captured steps
+
+    def invalidate_graphs(self) -> None:
+        """Drop the captured steps (they bake hyper-parameters, the training flag, the frozen set and buffer addresses)."""
+        self._graphs.clear()
+        self._graph = self._static = None
+
+    def _frozen(self):
+        """parameters that the reference would not update (requires_grad False, e.g. fine_tune_embeddings(False)) keep a zero gradient"""
+        return tuple(k for k in self.decoder._param_names if not self.decoder._get(k).requires_grad)
 
     def trimmed_width(self, captions) -> int:
         """Width that keeps every non-<pad> token of the batch (multiple of 8, at least 8).  A host tensor costs nothing; a
@@ -101,6 +123,15 @@ class Trainer:
         (unless trim_padding has to look at captions that already live on the device)."""
         if self.trim_padding:
             Tw = self.trimmed_width(captions)
+            if self.distributed:
+                # The width must be ONE decision for all ranks: graphs are keyed by the caption shape, and a rank that meets a
+                # new width alone would capture while its peers replay.  (Also: equal work per rank.)
+                import torch.distributed as dist
+
+                nccl = dist.get_backend(self.pg) == "nccl"
+                w = torch.tensor([Tw], dtype=torch.int32, device=self.eng.device if nccl else "cpu")
+                dist.all_reduce(w, op=dist.ReduceOp.MAX, group=self.pg)
+                Tw = int(w.item())
             if Tw < captions.shape[1]:
                 captions, caption_masks = captions[:, :Tw], caption_masks[:, :Tw]
                 caption_lengths = caption_lengths.clamp(max=Tw)
@@ -120,9 +151,9 @@ class Trainer:
             eng.backward(ctx, ds, self.g, need_encoder_grad=False)
         finally:
             K.set_seed_source(None)
-        for k in self._frozen:
+        for k in self._frozen():
             eng.param(k, self.g).zero_()
-        if self.distributed:
+        if self.distributed and not self._skip_collective:
             import torch.distributed as dist
 
             dist.all_reduce(self.gbuf, group=self.pg)
@@ -132,10 +163,13 @@ class Trainer:
 
     def step(self, inp) -> torch.Tensor:
         """One optimisation step on a prepared batch.  Returns a device tensor [loss_sum, kept_tokens] (global under DDP)."""
+        self.eng = self.decoder._ensure_engine()  # re-gathers / re-packs if the parameter storages were replaced or invalidated
         if not self.use_graph:
             self._step_impl(inp)
             return self.loss_acc
-        key = tuple(inp.captions.shape)
+        # everything a captured step bakes in: shapes, the training flag (dropout on / off), the frozen set, and the parameter
+        # storage generation (a re-gathered flat buffer moves the fp32 addresses the kernels read)
+        key = (tuple(inp.captions.shape), bool(self.decoder.training), self._frozen(), getattr(self.decoder, "_flat_gen", 0))
         if key not in self._graphs:
             self._capture(inp)
             self._graphs[key] = (self._graph, self._static)
@@ -155,7 +189,13 @@ class Trainer:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._step_impl(self._static)
+            # no collective in the warm-up: a rank that captures a new shape alone (e.g. a ragged last batch) must still issue
+            # exactly ONE all-reduce for this step, like its peers that replay - the warm-up's result is thrown away anyway
+            self._skip_collective = True
+            try:
+                self._step_impl(self._static)
+            finally:
+                self._skip_collective = False
         torch.cuda.current_stream().wait_stream(s)
         for t, c in zip((self.eng.P, self.m, self.v, self.step_dev), snap):
             t.copy_(c)
@@ -263,7 +303,7 @@ def generate_sharded(decoder, encoder_out, max_pred_len, entities, facts=None, b
     padded = torch.zeros((per_rank, max_pred_len), dtype=torch.int64)
     padded[: out.shape[0]] = out
     if dist.get_backend(process_group) == "nccl":
-        dev = encoder_out.device
+        dev = decoder._ensure_engine().device  # the inputs may live on the host (predict_batch moves them itself)
         bufs = [torch.empty_like(padded, device=dev) for _ in range(world)]
         dist.all_gather(bufs, padded.to(dev), group=process_group)
         bufs = [b.cpu() for b in bufs]

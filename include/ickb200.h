@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 8
+#define ICK_ABI_VERSION 9
 
 #ifdef __cplusplus
 extern "C" {
@@ -140,6 +140,11 @@ int ick_pixels_bwd(const void* dmemory, float* d_encoder_out, int dt, int B, int
  * is ick_gemm_tn_* with W = conv1.weight (emb_dim, C); ick_pixels_bwd(M = P) turns the GEMM output into the (B, emb_dim, P)
  * layout Encoder.forward returns (G/models.py:46). */
 int ick_pool_rows_fwd(const float* x, void* rows, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
+                      cudaStream_t stream);
+/* Its backward (the trunk is fine-tuned: Encoder.fine_tune(True), G/models.py:49-60): d rows -> d x (B, C, Hin, Win) fp32, every
+ * input pixel summing grad / window size over the output cells whose window covers it (AdaptiveAvgPool2d backward).  The weight
+ * gradient of conv1 is ick_wgrad_tc / ick_wgrad_simt over (d rows of conv1's output, pooled rows), its input gradient ick_gemm_tn_*. */
+int ick_pool_rows_bwd(const void* drows, float* dx, int dt, int B, int C, int Hin, int Win, int Hout, int Wout, int ldo,
                       cudaStream_t stream);
 
 /* Input pipeline, device half.  raw: the HDF5 storage format of the images - fp16 (N, 3, H, W), values in

@@ -357,10 +357,44 @@ def test_encoder_head_matches_torch_ops(dtype, tol, hw):
     assert got.shape == ref.shape == (5, 300, 196) and got.dtype == torch.float32
     assert nmax_err(got.cpu(), ref) < tol
     assert nmax_err(stock.cpu(), ref) < 2e-2  # and the stock path agrees with the same reference
-    # with autograd through conv1 the stock ops run and gradients flow as in the reference
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("fine_tune", [False, True])
+def test_encoder_head_under_autograd_takes_the_kernel_path(dtype, tol, fine_tune):
+    """The reference's own call sites run the encoder with gradients enabled and conv1.requires_grad = True (G/train.py:269,
+    G/eval.py:77-83, G/models.py:32): the hand-off must stay on the kernels there (one autograd node, hand-written backward: conv1
+    weight / bias gradient on the wgrad kernel; with a fine-tuned trunk also dgrad GEMM + pooling backward) and give the gradients
+    of the stock AdaptiveAvgPool2d + Conv2d ops (float64 on the host)."""
+    from ickb200 import _lib
+    from ickb200.geo_aware import Encoder
+
+    torch.manual_seed(4)
+    enc = Encoder(pretrained=False, compute_dtype=dtype).cuda().train()
+    feats = torch.randn(3, 2048, 8, 8, device="cuda", requires_grad=fine_tune)
+    wgt = torch.randn(3, 300, 196, device="cuda")
+    lib = _lib.get()
+    n0 = lib.launches
     out = enc.head(feats)
-    out.sum().backward()
-    assert enc.conv1.weight.grad is not None
+    assert out.requires_grad and type(out.grad_fn).__name__.startswith("_EncoderHeadFn")
+    n_fwd = lib.launches - n0
+    assert n_fwd == 3  # pool -> GEMM -> transpose, nothing else (no cuDNN convolution)
+    (out * wgt).sum().backward()
+    assert lib.launches - n0 >= n_fwd + (2 if not fine_tune else 4)  # transpose + wgrad [+ dgrad GEMM + pooling backward]
+    f64 = feats.detach().double().cpu().requires_grad_(True)
+    w64 = enc.conv1.weight.detach().double().cpu().requires_grad_(True)
+    b64 = enc.conv1.bias.detach().double().cpu().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.adaptive_avg_pool2d(f64, (14, 14)), w64, b64).view(3, 300, -1)
+    assert nmax_err(out.detach().cpu(), ref.detach()) < tol
+    (ref * wgt.double().cpu()).sum().backward()
+    assert nmax_err(enc.conv1.weight.grad.cpu(), w64.grad) < tol
+    assert nmax_err(enc.conv1.bias.grad.cpu(), b64.grad) < tol
+    if fine_tune:
+        assert nmax_err(feats.grad.cpu(), f64.grad) < tol
+    else:
+        assert feats.grad is None
+    # eval.py's call (module in eval mode, grad still enabled) takes the same path
+    assert type(enc.eval().head(feats.detach()).grad_fn).__name__.startswith("_EncoderHeadFn")
 
 
 @pytest.mark.parametrize("name", ["geo_b32", "news_b8"])

@@ -228,3 +228,25 @@ def test_beam_search_edge_cases():
         assert margin < 1e-4 or out[0].tolist() == ref.tolist(), (T, k)
     with pytest.raises(AssertionError):
         dec.beam_search_batch(pb["encoder_out"][:1], 3, pb["entities"][:1], pb["facts"][:1], beam_size=9)
+
+
+def test_encoder_pretrained_weights_missing_is_loud(monkeypatch):
+    """Encoder() asks for the ImageNet weights like the reference (G/models.py:24); without network or cache that must raise (or,
+    with ICKB200_ALLOW_RANDOM_TRUNK=1, warn) instead of silently training on a random trunk."""
+    import torchvision
+
+    from ickb200.geo_aware import Encoder
+
+    def boom(*a, **k):
+        if k.get("weights") is not None or k.get("pretrained"):
+            raise OSError("no network")
+        return orig(*a, **k)
+
+    orig = torchvision.models.resnet101
+    monkeypatch.setattr(torchvision.models, "resnet101", boom)
+    monkeypatch.delenv("ICKB200_ALLOW_RANDOM_TRUNK", raising=False)
+    with pytest.raises(RuntimeError, match="pretrained=False"):
+        Encoder()
+    monkeypatch.setenv("ICKB200_ALLOW_RANDOM_TRUNK", "1")
+    with pytest.warns(UserWarning, match="RANDOM trunk"):
+        Encoder()

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from helpers import batch_args, build_module, oracle_params, spec_for
+from helpers import batch_args, build_module, nmax_err, oracle_params, spec_for
 from hostsim import HostKernels
 from ickb200 import models as M, synthetic as syn
 from ickb200.trainer import Trainer
@@ -194,3 +194,102 @@ def test_trainer_state_dict_resumes_exactly(tmp_path):
     assert torch.equal(acc_a, acc_c)
     for (k, pa), (_, pc) in zip(dec_a.named_parameters(), dec_c.named_parameters()):
         assert torch.equal(pa.detach(), pc.detach()), k
+
+
+def _trim_worker(rank, world, port, cfg, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    full = _ragged_batch(cfg)
+    n = cfg.B // world
+    shard = {k: v[rank * n : (rank + 1) * n] for k, v in full.items()}
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    torch.manual_seed(100 + rank)  # ranks seeded DIFFERENTLY on purpose: the Trainer must broadcast rank 0's parameters
+    dec = build_module(cfg.with_batch(n), "cpu", dropouts=(0.0, 0.0, 0.0), seed=rank).train()
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=True, trim_padding=True)
+    local_w = tr.trimmed_width(shard["captions"])
+    inp = tr.prepare(*batch_args(cfg.with_batch(n), shard))
+    acc = tr.step(inp).clone()
+    q.put((rank, local_w, int(inp.captions.shape[1]), acc.tolist(), int(tr.seed_base),
+           {k: v.detach().numpy().copy() for k, v in dec.named_parameters()} if rank == 0 else None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _ragged_batch(cfg):
+    full = syn.make_batch(cfg, seed=4)
+    full["captions"][:2, 9:] = 0  # rank 0's shard: short captions (width 16 after rounding) ...
+    full["caption_masks"][:2, 9:] = 0
+    full["captions"][2:, 30:] = 0  # ... rank 1's: long ones (width 32)
+    full["caption_masks"][2:, 30:] = 0
+    return full
+
+
+def test_trim_padding_width_is_a_collective_decision():
+    """with trim_padding under data parallelism the trimmed width must be agreed by all ranks (graphs are
+    keyed by the caption shape; a rank meeting a new width alone would capture - and all-reduce once more - while its peers
+    replay).  Two gloo ranks whose LOCAL widths differ (16 vs 32) must both run at 32, and the update must equal the
+    single-process step on the whole batch.  Ranks are built from different seeds: rank 0's parameters must win."""
+    cfg = syn.Config("K", B=4, T=40, E=13, F=7, V=57, P=20)
+    full = _ragged_batch(cfg)
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec1 = build_module(cfg, "cpu", dropouts=(0.0, 0.0, 0.0), seed=0).train()
+    tr1 = Trainer(dec1, lr=4e-4, grad_clip=5.0, trim_padding=True)
+    acc1 = tr1.train_step(*batch_args(cfg, full)).clone()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_trim_worker, args=(r, 2, port, cfg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    (_, w0, used0, acc_a, seed0, params), (_, w1, used1, acc_b, seed1, _) = res
+    assert (w0, w1) == (16, 32) and used0 == used1 == 32
+    assert acc_a == acc_b and acc_a[1] == float(acc1[1]) and abs(acc_a[0] - float(acc1[0])) < 1e-3 * abs(float(acc1[0]))
+    assert seed0 != seed1  # rank-mixed dropout seeds: the shards must not draw identical masks
+    n_close = n_all = 0
+    for k, prm in dec1.named_parameters():
+        d = (prm.detach() - torch.from_numpy(params[k])).abs()
+        assert float(d.max()) < 1e-3, k
+        n_close += int((d < 2e-5).sum())
+        n_all += d.numel()
+    assert n_close > 0.999 * n_all
+
+
+def test_writes_through_data_need_repack_and_mode_switch_repacks():
+    """`.data` writes (the reference's own init idiom, G/models.py:264-272) do not bump the autograd version; the
+    public repack() - and every train()/eval() switch - refreshes the packed operand copies."""
+    cfg = syn.SMALL_CONFIGS["G"]
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu").eval()
+    batch = syn.make_batch(cfg, seed=1)
+    s0, _, _ = dec(*batch_args(cfg, batch))
+    dec._get("fc_vocab.weight").data.mul_(2.0)
+    dec._get("fc_vocab.bias").data.zero_()
+    dec.repack()
+    s1, _, _ = dec(*batch_args(cfg, batch))
+    V = cfg.V
+    assert nmax_err(s1[..., :V], 2.0 * (s0[..., :V] - syn.det_weights({"fc_vocab.bias": (V,)})["fc_vocab.bias"])) < 1e-5
+    dec._get("fc_vocab.weight").data.mul_(0.5)
+    dec.train().eval()  # a mode switch alone is enough
+    s2, _, _ = dec(*batch_args(cfg, batch))
+    assert nmax_err(s2[..., :V] , s0[..., :V] - syn.det_weights({"fc_vocab.bias": (V,)})["fc_vocab.bias"]) < 1e-5
+
+
+def test_load_state_dict_and_frozen_set_invalidate_captured_steps():
+    cfg = syn.SMALL_CONFIGS["G"]
+    M.DecoderTransformer._test_kernel_factory = HostKernels
+    dec = build_module(cfg, "cpu").train()
+    tr = Trainer(dec, lr=4e-4)
+    tr._graphs[("stale",)] = (object(), object())
+    tr.load_state_dict(tr.state_dict())
+    assert not tr._graphs and tr._graph is None
+    assert "word_embedding.weight" not in tr._frozen()
+    dec.fine_tune_embeddings(False)  # G/models.py:282-289, called after the Trainer was built
+    assert "word_embedding.weight" in tr._frozen()
+    before = dec._get("word_embedding.weight").detach().clone()
+    tr.train_step(*batch_args(cfg, syn.make_batch(cfg, seed=1)))
+    assert torch.equal(dec._get("word_embedding.weight").detach(), before)

@@ -83,6 +83,20 @@ __device__ __forceinline__ uint64_t prow(const AttnDims& d, int b, int h, int i)
     return ((uint64_t)b * d.H + h) * (uint64_t)d.Sq + i;
 }
 
+// Attention-probability dropout (common.cuh: bit-parallel keep words): multiplier of probability (row mix rmix, key j); the keep
+// word of the key's group of 32 is cached across consecutive keys of a row.
+struct KeepCache {
+    uint32_t kg = 0xFFFFFFFFu, word = 0u;
+    __device__ __forceinline__ float mul(const DropCfg& drop, uint32_t rmix, uint32_t key) {
+        if (drop.thr == 0u) return 1.0f;
+        if ((key >> 5) != kg) {
+            kg = key >> 5;
+            word = ick_keepword(rmix, kg, ick_attn_t16(drop.thr));
+        }
+        return ((word >> ick_keybit(key)) & 1u) ? drop.inv_keep : 0.0f;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, const T* __restrict__ K,
@@ -106,6 +120,7 @@ __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, co
     for (int c = 0; c < HD; ++c) q[c] = (c < d.dh) ? q[c] * d.scale_log2 : 0.f;  // pad lanes never contribute
     float m = -INFINITY, l = 0.f;
     const uint32_t rmix = ick_rowmix(drop.seed, drop.site, prow(d, b, h, i));
+    KeepCache kc;
 
     // causal: no key beyond the last query of this CTA is visible
     const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(NT) mha_fwd_kernel(const T* __restrict__ Q, co
             for (int jj = 0; jj < 8; ++jj) {
                 const float p = exp2f(s[jj] - mnew);  // masked -> exp2(-inf) = 0
                 l += p;
-                const float pd = p * ick_drop_mul(drop, rmix, (uint32_t)(k0 + j0 + jj));
+                const float pd = p * kc.mul(drop, rmix, (uint32_t)(k0 + j0 + jj));
                 axpy32(acc, pd, Vs[j0 + jj]);
             }
             m = mnew;
@@ -190,6 +205,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
     }
 
     const uint32_t rmix = ick_rowmix(drop.seed, drop.site, prow(d, b, h, i));
+    KeepCache kc;
     const int kmax = d.causal ? min(d.Sk, (int)(blockIdx.x * NT + NT)) : d.Sk;
     for (int k0 = 0; k0 < kmax; k0 += KT) {
         __syncthreads();
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__(NT) mha_bwd_dq_kernel(const T* __restrict__ Q,
             const int j = k0 + jj;
             if (d.causal && j > i) break;
             const float p = exp2f(dot32(q, Ks[jj]) - lse);
-            const float dp = dot32(go, Vs[jj]) * ick_drop_mul(drop, rmix, (uint32_t)j);
+            const float dp = dot32(go, Vs[jj]) * kc.mul(drop, rmix, (uint32_t)j);
             const float ds = p * (dp - Di);
             axpy32(dq, ds, Ks[jj]);
         }
@@ -265,7 +281,8 @@ __global__ void __launch_bounds__(NT) mha_bwd_dkv_kernel(const T* __restrict__ Q
             const int i = q0 + ii;
             if (d.causal && j > i) continue;
             const float p = exp2f(dot32(k, Qs[ii]) - Ls[ii]);
-            const float mul = ick_drop_mul(drop, ick_rowmix(drop.seed, drop.site, prow(d, b, h, i)), (uint32_t)j);
+            KeepCache kc;  // one key per thread, a new row per query: nothing to cache (fp32 parity path)
+            const float mul = kc.mul(drop, ick_rowmix(drop.seed, drop.site, prow(d, b, h, i)), (uint32_t)j);
             axpy32(dv, p * mul, Gs[ii]);
             const float dp = dot32(v, Gs[ii]) * mul;
             const float ds = p * (dp - Ds[ii]);

@@ -156,6 +156,42 @@ __device__ __forceinline__ float ick_keep(uint32_t thr, float inv_keep, uint32_t
     return ((col & 1u) ? ick_keep_hi(pairhash, thr) : ick_keep_lo(pairhash, thr)) ? inv_keep : 0.0f;
 }
 
+// ---- attention-probability dropout: bit-parallel keep words ---------------------------------------------------------
+// The (query, key) probability matrices are by far the largest dropout sites (116 M elements per entity layer at B = 128), and a
+// hash per element PAIR made the attention kernels instruction-bound.  For these sites the mask is defined per WORD instead:
+// the 32 keys [32*kg, 32*kg + 32) of a probability row (row mix as above) share up to 16 hashed words w_0.. (bit planes,
+// most significant first) of 32 independent 16-bit uniform numbers U_b, one per key; key k keeps its probability iff
+// U_b < t16, t16 = 65536 * (1 - p) = 65536 - 2 * thr, b = ick_keybit(k).  The comparison runs bit-serially on whole words
+// (two logic ops per plane for 32 keys) and stops at the lowest set bit of t16: the reference's p = 0.5 needs ONE hash per 32
+// probabilities.  Key k of a group sits at bit (k >> 1) + 16 * (k & 1) - the two keys of a bf16 pair at bits i and 16 + i,
+// so a shift puts them on the two sign bits that one byte-permute expands into the AND mask of the packed pair.
+__host__ __device__ __forceinline__ uint32_t ick_fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__host__ __device__ __forceinline__ uint32_t ick_keybit(uint32_t key) { return ((key & 31u) >> 1) + ((key & 1u) << 4); }
+// keep word of key group kg of a row; t16 in [2, 65534]
+__host__ __device__ __forceinline__ uint32_t ick_keepword(uint32_t rowmix, uint32_t kg, uint32_t t16) {
+    uint32_t lt = 0u, eq = 0xFFFFFFFFu;
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t rest = t16 & (0xFFFFu >> i);  // bits of t16 from plane i downwards
+        if (rest == 0u) break;                       // U < t16 is decided: equal prefixes are not below
+        const uint32_t w = ick_fmix32(rowmix + (kg * 16u + (uint32_t)i) * 0x9E3779B1u);
+        if ((t16 >> (15 - i)) & 1u) {
+            lt |= eq & ~w;
+            eq &= w;
+        } else {
+            eq &= ~w;
+        }
+    }
+    return lt;
+}
+__host__ __device__ __forceinline__ uint32_t ick_attn_t16(uint32_t thr) { return 65536u - 2u * thr; }
+
 struct DropCfg {
     uint32_t thr;    // floor(p * 32768), 0 = off
     float inv_keep;  // 1 / (1 - p)

@@ -78,7 +78,7 @@ def build_module(cfg, device, dtype=torch.float32, seed=0, dropouts=(0.5, 0.5, 0
 
 def oracle_drop_fn(seed, ps):
     """DropFn for the oracle that reproduces the kernels' masks: site name -> hash-derived multiplier tensor."""
-    from dropout_ref import drop_mul
+    from dropout_ref import attn_drop_mul, drop_mul
 
     def fn(site, shape):
         if site == "pos":
@@ -92,6 +92,7 @@ def oracle_drop_fn(seed, ps):
         rows = 1
         for s in shape[:-1]:
             rows *= s
-        return drop_mul(p, seed, layout.site_id(site), rows, shape[-1]).view(*shape)
+        fn = attn_drop_mul if site.endswith(".attn") else drop_mul  # attention probabilities: bit-parallel keep words
+        return fn(p, seed, layout.site_id(site), rows, shape[-1]).view(*shape)
 
     return fn

@@ -12,7 +12,7 @@ import math
 import numpy as np
 import torch
 
-from dropout_ref import drop_mul
+from dropout_ref import attn_drop_mul, drop_mul
 
 FIRST_NONE = 1 << 29
 HD = 32
@@ -21,7 +21,7 @@ HD = 32
 _SEED_SRC = [None]
 
 
-def _mul(drop, rows, cols):
+def _mul(drop, rows, cols, attn=False):
     if drop is None:
         return None
     p, seed, site = drop
@@ -29,7 +29,7 @@ def _mul(drop, rows, cols):
         return None
     if _SEED_SRC[0] is not None:
         seed = (seed + int(_SEED_SRC[0][0])) & 0xFFFFFFFF
-    return drop_mul(p, seed, site, rows, cols)
+    return (attn_drop_mul if attn else drop_mul)(p, seed, site, rows, cols)
 
 
 def _rows(rowmap, R):
@@ -111,7 +111,7 @@ class HostKernels:
         v = self._heads(V, B, Sk, H)[..., :dh]
         p = torch.softmax(s, dim=-1)
         lse.copy_((torch.logsumexp(s, dim=-1) * 1.4426950408889634).reshape(-1))
-        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1])
+        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1], attn=True)
         pd = p * m.view_as(p) if m is not None else p
         o = pd @ v  # (B,H,Sq,dh)
         out = torch.zeros(B, H, Sq, HD)
@@ -124,7 +124,7 @@ class HostKernels:
         v = self._heads(V, B, Sk, H)[..., :dh]
         go = self._heads(dO, B, Sq, H)[..., :dh]
         p = torch.softmax(s, dim=-1)
-        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1])
+        m = _mul(drop, p.numel() // p.shape[-1], p.shape[-1], attn=True)
         mm = m.view_as(p) if m is not None else torch.ones_like(p)
         dv = (p * mm).transpose(-1, -2) @ go
         dp = (go @ v.transpose(-1, -2)) * mm

@@ -242,6 +242,37 @@ def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
         assert err(a, b) < TOL[dtype] * 2, name
 
 
+@pytest.mark.parametrize("p", [0.0, 0.3, 0.5])
+@pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", [(100, 10, 70, 70, 30, True), (30, 10, 37, 548, 30, False), (16, 10, 301, 301, 30, False),
+                                                 (20, 10, 52, 598, 30, False), (9, 3, 200, 40, 32, False), (160, 10, 51, 51, 30, False)])
+def test_mha_bwd_fused_many_items(K, Hk, p, B, H, Sq, Sk, dh, causal):
+    """The fused bf16 backward (attention_bwd_fused.cu) with several (image, head) items per CTA: operand stages, ring slots and the
+    TMEM dQ slots are re-used (1000 items on 148 CTAs: 6-7 tenants per slot), p = 0.3 needs 14 bit planes per keep word."""
+    dtype = torch.bfloat16
+    q = headify(rnd((B * Sq, H * 32), torch.float32, 1), H, dh).to(dtype)
+    k = headify(rnd((B * Sk, H * 32), torch.float32, 2), H, dh).to(dtype)
+    v = headify(rnd((B * Sk, H * 32), torch.float32, 3), H, dh).to(dtype)
+    drop = (p, 77, 9) if p > 0 else None
+    Or, lr = torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * H * Sq)
+    Hk.mha_fwd(q, k, v, Or, lr, B, H, Sq, Sk, dh, causal, drop)
+    Og, lg = torch.zeros(B * Sq, H * 32, dtype=dtype).cuda(), torch.zeros(B * H * Sq).cuda()
+    K.mha_fwd(cu(q), cu(k), cu(v), Og, lg, B, H, Sq, Sk, dh, causal, drop)
+    assert err(Og, Or) < TOL[dtype]
+    dO = headify(rnd((B * Sq, H * 32), torch.float32, 4), H, dh).to(dtype)
+    outs_r = [torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype)]
+    outs_g = [torch.full_like(o, float("nan")).cuda() for o in outs_r]
+    dsr, dsg = torch.zeros(B * H * Sq), torch.zeros(B * H * Sq).cuda()
+    Hk.mha_bwd(q, k, v, Or, dO, lr, dsr, *outs_r, B, H, Sq, Sk, dh, causal, drop)
+    K.mha_bwd(cu(q), cu(k), cu(v), cu(Or), cu(dO), cu(lr), dsg, *outs_g, B, H, Sq, Sk, dh, causal, drop)
+    for a, b, name in zip(outs_g, outs_r, ["dQ", "dK", "dV"]):
+        assert not torch.isnan(a).any(), name
+        # per (image, head) item: a wrong tenant in a re-used slot would corrupt single items, which a global max norm could hide
+        ai = a.float().cpu().view(B, -1, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
+        bi = b.float().view(B, -1, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
+        rel = (ai - bi).abs().amax(1) / bi.abs().amax(1).clamp_min(1e-6)
+        assert float(rel.max()) < TOL[dtype] * 3, (name, int(rel.argmax()), float(rel.max()))
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_mha_decode(K, Hk, dtype):
     B, H, dh, Tmax, klen = 5, 10, 30, 12, 7

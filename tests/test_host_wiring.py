@@ -185,14 +185,16 @@ def test_module_pickles_like_reference_checkpoints(tmp_path):
     assert torch.equal(s0, s1)
 
 
-@pytest.mark.parametrize("p", [0.1, 0.5])
-def test_dropout_hash_statistics(p):
-    """The counter hash behind every dropout mask (csrc/common.cuh, ported in dropout_ref.py): keep rate within sampling error
-    of 1-p, and no visible correlation between the two columns of a pair, neighbouring pairs, or neighbouring rows."""
-    from dropout_ref import drop_mul
+@pytest.mark.parametrize("kind", ["pair", "attn"])
+@pytest.mark.parametrize("p", [0.1, 0.3, 0.5])
+def test_dropout_hash_statistics(p, kind):
+    """The counter hashes behind every dropout mask (csrc/common.cuh, ported in dropout_ref.py) - the pair hash of the
+    activation sites and the bit-parallel keep words of the attention probabilities: keep rate within sampling error of 1-p, and
+    no visible correlation between the two columns of a pair, neighbouring pairs, neighbouring rows or neighbouring key groups."""
+    from dropout_ref import attn_drop_mul, drop_mul
 
     rows, cols = 2048, 640
-    k = (drop_mul(p, 1234, 7, rows, cols) > 0).double()
+    k = ((drop_mul if kind == "pair" else attn_drop_mul)(p, 1234, 7, rows, cols) > 0).double()
     thr = int(p * 32768)
     assert abs(float(k.mean()) - (1 - thr / 32768)) < 4 * (p * (1 - p) / (rows * cols)) ** 0.5
     kc = k - k.mean()
@@ -205,6 +207,8 @@ def test_dropout_hash_statistics(p):
     assert abs(corr(kc[:, 0:-2:2], kc[:, 2::2])) < lim     # consecutive pairs
     assert abs(corr(kc[:-1], kc[1:])) < lim                # consecutive rows
     assert abs(corr(kc[:, :-8], kc[:, 8:])) < lim          # the stride an MMA fragment lane sees
+    assert abs(corr(kc[:, :-32], kc[:, 32:])) < lim        # the same bit of consecutive keep words
+    assert abs(corr(kc[:, :-1], kc[:, 1:])) < lim          # bits i and 16 + i / i + 1 of one word
     # each row / column keeps its own share close to 1-p
     assert float(k.mean(1).std()) < 1.3 * (p * (1 - p) / cols) ** 0.5
     assert float(k.mean(0).std()) < 1.3 * (p * (1 - p) / rows) ** 0.5

@@ -24,6 +24,7 @@
 // 2-3 keep-word generators, 4-7 dQ epilogue, 8-23 compute.  setmaxnreg moves registers from the helper warpgroups to the
 // compute warpgroups (104 per thread).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "attention_internal.h"
@@ -52,6 +53,7 @@ struct FArgs {
     int ngroups;         // 32-key groups (keep words per query)
     int nstage, ni;      // operand stages, TMEM item slots
     uint32_t stage_bytes, off_do, off_k, off_ls, off_ds, off_mw;
+    int dbg;             // ICK_FB_DEBUG bit mask (bring-up aid): 1 no setmaxnreg, 2 no tcgen05.mma, 4 no tcgen05.ld, 8 no block math
 };
 
 // ---- tcgen05 wrappers --------------------------------------------------------------------------------------------------------------
@@ -115,31 +117,41 @@ struct FSm {
     __device__ __forceinline__ uint8_t* stage_gen(int s) const { return gen + FB_BAR_BYTES + FB_RING + (size_t)s * stage_bytes; }
 };
 
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
 // One 32-query block of the warp's 16-key slab: S^T and dP^T on mma.sync, P^T / dS^T in registers, dV += P^T dO, dK += dS^T Q,
 // and the dS^T block into columns [32*sub, 32*sub + 32) of the warp's current ring slot (MN-major SWIZZLE_128B: key row r at
 // r*128, 16-byte chunk c of the row at chunk c ^ (r & 7)).
-//   ls / ds / mw: per-query LSE (log2 domain), D and keep word of this block's queries (shared memory), already offset by 2*tq.
-template <bool DROP>
+//   ls / ds / mw: SHARED-space addresses of the per-query LSE (log2 domain), D and keep word of this block's queries, already
+//   offset by the lane's 2*tq.  MASK: the block touches the causal diagonal of the slab.
+template <bool DROP, bool MASK>
 __device__ __forceinline__ void fb_block(float (*dk)[4], float (*dv)[4], const uint32_t (*ka)[4], const uint32_t (*va)[4], uint32_t qt,
-                                         uint32_t gt, int sub, int q0, const float* ls, const float* ds, const uint32_t* mw, uint32_t mk0,
-                                         uint32_t mk1, const OwnRows& r, const TileEnv& e, uint32_t slot_lane, int g) {
-    const Dims& d = e.d;
+                                         uint32_t gt, int sub, int q0, uint32_t ls, uint32_t ds, uint32_t mw, uint32_t mk0, uint32_t mk1,
+                                         const OwnRows& r, const TileEnv& e, uint32_t slot_lane, int g) {
     const int tq = e.tq;
-    const bool need_mask = d.causal && r.wrow + 15 > q0;
     float st[4][4], dpt[4][4];
     mma_a_tT<4>(st, ka, qt, 4 * sub, e.lo);
     mma_a_tT<4>(dpt, va, gt, 4 * sub, e.lo);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 l2 = *reinterpret_cast<const float2*>(ls + 8 * j);
-        const float2 d2 = *reinterpret_cast<const float2*>(ds + 8 * j);
+        const float2 l2 = lds_f2(ls + 32 * j);
+        const float2 d2 = lds_f2(ds + 32 * j);
         uint2 w2 = make_uint2(0u, 0u);
-        if (DROP) w2 = *reinterpret_cast<const uint2*>(mw + 8 * j);
+        if (DROP) w2 = lds_u2(mw + 32 * j);
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             const bool odd_q = (x & 1) != 0, hi_k = x >= 2;
             float p = ex2(fmaf(st[j][x], e.c, -(odd_q ? l2.y : l2.x)));
-            if (need_mask && (hi_k ? r.r1 : r.r0) > q0 + 8 * j + 2 * tq + (x & 1)) p = 0.f;
+            if (MASK && (hi_k ? r.r1 : r.r0) > q0 + 8 * j + 2 * tq + (x & 1)) p = 0.f;
             const float nd = -(odd_q ? d2.y : d2.x);
             if (DROP) {
                 const bool keep = ((odd_q ? w2.y : w2.x) & (hi_k ? mk1 : mk0)) != 0u;
@@ -258,7 +270,8 @@ __device__ __forceinline__ void fb_issuer(const FSm& sm, const FArgs& a, int lan
                                                  : make_desc(sm.zero_lo(), slot - sm.zero_lo(), 1024u, 2u);
                 const uint64_t bd = make_desc(sm.stage(s) + a.off_k + (uint32_t)slab * 1024u, 512u, 512u, 4u);
                 const int bit = 1 << (t >> 1);
-                tc_mma_bf16(tmem_base + (uint32_t)((i * a.nq128 + (t >> 1)) * 32), ad, bd, FB_IDESC, (touched[i] & bit) != 0 ? 1u : 0u);
+                if (!(a.dbg & 2))
+                    tc_mma_bf16(tmem_base + (uint32_t)((i * a.nq128 + (t >> 1)) * 32), ad, bd, FB_IDESC, (touched[i] & bit) != 0 ? 1u : 0u);
                 touched[i] |= bit;
                 tc_commit(sm.rempty(src, hs));
                 if (++cnt[i] == per_item) {
@@ -309,7 +322,12 @@ __device__ __forceinline__ void fb_epilogue(const FSm& sm, const FArgs& a, int w
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[16];
-                tc_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((i * a.nq128 + t) * 32 + 16 * c), r);
+                if (!(a.dbg & 4)) {
+                    tc_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((i * a.nq128 + t) * 32 + 16 * c), r);
+                } else {
+#pragma unroll
+                    for (int z = 0; z < 16; ++z) r[z] = 0u;
+                }
                 if (q < d.Sq) {
                     uint4 u0, u1;
                     u0.x = pack2(__uint_as_float(r[0]) * d.scale, __uint_as_float(r[1]) * d.scale);
@@ -354,9 +372,8 @@ __device__ __forceinline__ void fb_compute(const FSm& sm, const FArgs& a, int wa
         const int s = li % a.nstage, b = item / d.H, h = item % d.H;
         const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
         const uint32_t tQ = sm.stage(s), tG = tQ + a.off_do, tK = tQ + a.off_k;
-        const float* Ls = reinterpret_cast<const float*>(sm.stage_gen(s) + a.off_ls);
-        const float* Ds = reinterpret_cast<const float*>(sm.stage_gen(s) + a.off_ds);
-        const uint32_t* Mw = reinterpret_cast<const uint32_t*>(sm.stage_gen(s) + a.off_mw);
+        // shared-space addresses of this lane's first (query pair) scalars: LSE, D, keep words of key group 0
+        const uint32_t ls0 = tQ + a.off_ls + 8u * tq, ds0 = tQ + a.off_ds + 8u * tq, mw0 = tQ + a.off_mw + 8u * tq;
         // every warp passes through every item in order, so no warp can release a stage before the producer has filled it
         mbar_wait(sm.full(s), ph);
         mbar_wait(sm.sfull(s), ph);
@@ -370,7 +387,7 @@ __device__ __forceinline__ void fb_compute(const FSm& sm, const FArgs& a, int wa
             zero16(dk);
             zero16(dv);
             const uint32_t mk0 = 1u << ick_keybit((uint32_t)r.r0), mk1 = mk0 << 4;
-            const uint32_t* mws = Mw + (size_t)(slab >> 1) * nq + 2 * tq;
+            const uint32_t mws = mw0 + (uint32_t)((slab >> 1) * nq) * 4u;
             for (int t = 0; t < a.ntq; ++t) {
                 const uint32_t hsel = nb & 1u;
                 mbar_wait(sm.rempty(cw, (int)hsel), ((nb >> 1) & 1u) ^ 1u);
@@ -378,11 +395,15 @@ __device__ __forceinline__ void fb_compute(const FSm& sm, const FArgs& a, int wa
 #pragma unroll 1
                 for (int sub = 0; sub < 2; ++sub) {
                     const int q0 = t * TK + sub * SUB;
-                    if (d.causal && q0 + SUB - 1 < r.wrow) {
-                        fb_zero_block(sub, slot_lane, g);
+                    const uint32_t qo = 4u * (uint32_t)q0;
+                    if ((d.causal && q0 + SUB - 1 < r.wrow) || (a.dbg & 8)) {
+                        fb_zero_block(sub, slot_lane, g);  // every query precedes every key of the slab
+                    } else if (d.causal && r.wrow + 15 > q0) {
+                        fb_block<DROP, true>(dk, dv, ka, va, tQ + t * TILE_BYTES, tG + t * TILE_BYTES, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r,
+                                             env, slot_lane, g);
                     } else {
-                        fb_block<DROP>(dk, dv, ka, va, tQ + t * TILE_BYTES, tG + t * TILE_BYTES, sub, q0, Ls + q0 + 2 * tq, Ds + q0 + 2 * tq, mws + q0,
-                                       mk0, mk1, r, env, slot_lane, g);
+                        fb_block<DROP, false>(dk, dv, ka, va, tQ + t * TILE_BYTES, tG + t * TILE_BYTES, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r,
+                                              env, slot_lane, g);
                     }
                 }
                 fence_async_smem();  // the block is read by the tensor core (async proxy)
@@ -456,17 +477,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     ick_pdl_wait();  // nothing above touched global memory
 
     // Register re-distribution per warpgroup; each role branch STARTS with its setmaxnreg so that ptxas allocates the branch against
-    // the new limit: helpers 40, epilogue 56, compute 104  ->  4*32*40 + 4*32*56 + 16*32*104 = 65536.
+    // the new limit: helpers 40, epilogue 56, compute 96: 4*32*40 + 4*32*56 + 16*32*96 = 61440 = the 80 x 768 registers the CTA was launched with (setmaxnreg only re-distributes the CTA's own allocation: asking for more blocks forever).
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (!(a.dbg & 1)) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0) fb_producer(sm, a, lane, &tmQ, &tmG, &tmK, p, n_items);
         else if (warp == 1) fb_issuer(sm, a, lane, tmem_base, my_items);
         else if (DROP) fb_maskgen(sm, a, warp, lane, drop, n_items);
     } else if (warp < FB_FIRST_CW) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (!(a.dbg & 1)) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         fb_epilogue(sm, a, warp, lane, tmem_base, p, n_items);
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if (!(a.dbg & 1)) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         fb_compute<DROP>(sm, a, warp, lane, p, drop, n_items);
     }
 
@@ -523,6 +544,10 @@ int ick_mha_bwd_fused(const void* Q, const void* K, const void* V, const void* O
     if (dh > HD || Sq > 640 || Sk > 640 || (lddq % 8) != 0) return ICK_ERR_UNSUPPORTED;
     if ((((uintptr_t)K | (uintptr_t)Q | (uintptr_t)dO | (uintptr_t)O | (uintptr_t)dQ) & 15) != 0) return ICK_ERR_UNSUPPORTED;
     FArgs a;
+    {
+        const char* e = getenv("ICK_FB_DEBUG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     a.d = make_dims(B, H, Sq, Sk, dh, causal);
     a.nslabs = (Sk + 15) / 16;
     a.ntq = (Sq + TK - 1) / TK;

@@ -8,14 +8,15 @@
 //     stay balanced over the launch) and walks the item's queries in blocks of 32: S^T = K Q^T and dP^T = V dO^T on
 //     mma.sync, P^T / dS^T in registers, dV += P^T dO and dK += dS^T Q accumulated in registers (the operands Q, dO and K are
 //     staged once per item by TMA, 64B-swizzled, two or more items in flight);
-//   * dQ needs the sum over ALL key slabs, i.e. over warps.  Each warp drops its dS^T block - [16 keys][64 queries] bf16, written
-//     in the canonical MN-major SWIZZLE_128B layout - into a private double-buffered 2 KiB slot of shared memory, and one
+//   * dQ needs the sum over ALL key slabs, i.e. over warps.  Each warp drops its dS^T block - [16 keys][128 queries] bf16, written
+//     in the canonical MN-major SWIZZLE_128B layout (two 64-query atoms) - into a private 4 KiB slot of shared memory, and one
 //     elected thread of the issuer warp feeds it to the 5th-generation tensor core:
 //         dQ[128 queries x 32] += dS[128 x 16 keys] * K[16 keys x 32]        (tcgen05.mma, M = 128, N = 32, K = 16)
-//     with the A operand = (the slot | a box of zeros) as the two 64-query atoms of the M dimension, the B operand = the 16 key
-//     rows inside the TMA-staged K tile (MN-major, SWIZZLE_64B), and the fp32 accumulator in TENSOR MEMORY, one 32-column
-//     slice per 128 queries of the item; up to four items' dQ live in TMEM at once, so the warps never wait for each other;
-//   * four epilogue warps read an item's dQ out of TMEM (tcgen05.ld) when its last block has been issued, scale and store it;
+//     with the B operand = the 16 key rows inside the TMA-staged K tile (MN-major, SWIZZLE_64B) and the fp32 accumulator in
+//     TENSOR MEMORY, one 32-column slice per 128 queries of the item; up to four items' dQ live in TMEM at once, so the warps
+//     never wait for each other;
+//   * four epilogue warps read an item's dQ out of TMEM (tcgen05.ld) when its last block has been issued, scale and store it,
+//     and clear the accumulator (tcgen05.st) for the slot's next tenant, so that every MMA simply accumulates;
 //   * attention-probability dropout is the bit-parallel keep-word scheme of common.cuh: two helper warps hash the item's
 //     (key group, query) keep words into the stage while the previous item computes - ONE hash per 32 probabilities at the
 //     reference's p = 0.5 - and the compute warps test one bit per probability.
@@ -40,8 +41,8 @@ constexpr int FB_THREADS = 32 * FB_WARPS;  // 768
 constexpr int FB_MAXNI = 4;                // items whose dQ accumulators live in TMEM
 constexpr int FB_MAXSTAGE = 6;
 constexpr int FB_TMEM_COLS = 512;
-constexpr int FB_HALF = 2048;              // one dS^T block: [16 keys][64 queries] bf16
-constexpr int FB_RING = 2 * FB_HALF + FB_NCW * 2 * FB_HALF;  // zero box | slots | zero box
+constexpr int FB_SLOT = 4096;              // one dS^T block: [16 keys][128 queries] bf16 = two 64-query SWIZZLE_128B atoms of 2 KiB
+constexpr int FB_MAXSLOT = 2;              // ring slots per compute warp
 constexpr int FB_BAR_BYTES = 2048;
 constexpr int FB_SMEM_MAX = 232448;
 
@@ -52,8 +53,9 @@ struct FArgs {
     int nq128;           // 128-query accumulator tiles of an item
     int ngroups;         // 32-key groups (keep words per query)
     int nstage, ni;      // operand stages, TMEM item slots
+    int nslot;           // ring slots per compute warp (1 or 2)
     uint32_t stage_bytes, off_do, off_k, off_ls, off_ds, off_mw;
-    int dbg;             // ICK_FB_DEBUG bit mask (bring-up aid): 1 no setmaxnreg, 2 no tcgen05.mma, 4 no tcgen05.ld, 8 no block math
+    int dbg;             // ICK_FB_DEBUG bit mask (bring-up aid): 1 no setmaxnreg, 2 no tcgen05.mma, 4 no tcgen05.ld, 8 no block math, 16 one ring slot
 };
 
 // ---- tcgen05 wrappers --------------------------------------------------------------------------------------------------------------
@@ -80,6 +82,24 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_st16_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// non-blocking probe (mbarrier.try_wait may suspend the thread up to a system time limit: useless for polling many barriers)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48), layout type [61,64)
 // (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).  MN-major operands: LBO = byte distance of the swizzle atoms along M / N, SBO = byte
 // distance of the 8-row groups along K.
@@ -98,23 +118,21 @@ constexpr uint32_t FB_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | 
 struct FSm {
     uint32_t base;  // shared-space address of the 1024-aligned region
     uint8_t* gen;   // generic pointer to the same byte
-    uint32_t stage_bytes;
+    uint32_t stage_bytes, ring_bytes;
+    int nslot;
     __device__ __forceinline__ uint32_t bar(int i) const { return base + 8u * (uint32_t)i; }
     __device__ __forceinline__ uint32_t full(int s) const { return bar(s); }
     __device__ __forceinline__ uint32_t sfull(int s) const { return bar(FB_MAXSTAGE + s); }
     __device__ __forceinline__ uint32_t empty(int s) const { return bar(2 * FB_MAXSTAGE + s); }
-    __device__ __forceinline__ uint32_t rfull(int w, int h) const { return bar(3 * FB_MAXSTAGE + 2 * w + h); }
-    __device__ __forceinline__ uint32_t rempty(int w, int h) const { return bar(3 * FB_MAXSTAGE + 2 * FB_NCW + 2 * w + h); }
-    __device__ __forceinline__ uint32_t dqfull(int i) const { return bar(3 * FB_MAXSTAGE + 4 * FB_NCW + i); }
-    __device__ __forceinline__ uint32_t dqempty(int i) const { return bar(3 * FB_MAXSTAGE + 4 * FB_NCW + FB_MAXNI + i); }
+    __device__ __forceinline__ uint32_t rfull(int w, int k) const { return bar(3 * FB_MAXSTAGE + FB_MAXSLOT * w + k); }
+    __device__ __forceinline__ uint32_t rempty(int w, int k) const { return bar(3 * FB_MAXSTAGE + FB_MAXSLOT * FB_NCW + FB_MAXSLOT * w + k); }
+    __device__ __forceinline__ uint32_t dqfull(int i) const { return bar(3 * FB_MAXSTAGE + 2 * FB_MAXSLOT * FB_NCW + i); }
+    __device__ __forceinline__ uint32_t dqempty(int i) const { return bar(3 * FB_MAXSTAGE + 2 * FB_MAXSLOT * FB_NCW + FB_MAXNI + i); }
     __device__ __forceinline__ uint32_t* tmem_ptr() const { return reinterpret_cast<uint32_t*>(gen + 1024); }
-    __device__ __forceinline__ volatile uint32_t* meta() const { return reinterpret_cast<volatile uint32_t*>(gen + 1040); }
-    __device__ __forceinline__ int* istate() const { return reinterpret_cast<int*>(gen + 1040 + 4 * 2 * FB_NCW); }  // issuer: 3 x FB_MAXNI ints
-    __device__ __forceinline__ uint32_t zero_lo() const { return base + FB_BAR_BYTES; }
-    __device__ __forceinline__ uint32_t slot(int w, int h) const { return base + FB_BAR_BYTES + FB_HALF + (uint32_t)(2 * w + h) * FB_HALF; }
-    __device__ __forceinline__ uint32_t zero_hi() const { return base + FB_BAR_BYTES + FB_HALF + 2 * FB_NCW * FB_HALF; }
-    __device__ __forceinline__ uint32_t stage(int s) const { return base + FB_BAR_BYTES + FB_RING + (uint32_t)s * stage_bytes; }
-    __device__ __forceinline__ uint8_t* stage_gen(int s) const { return gen + FB_BAR_BYTES + FB_RING + (size_t)s * stage_bytes; }
+    __device__ __forceinline__ volatile uint32_t* meta() const { return reinterpret_cast<volatile uint32_t*>(gen + 1040); }  // [warp][slot]
+    __device__ __forceinline__ uint32_t slot(int w, int k) const { return base + FB_BAR_BYTES + (uint32_t)(w * nslot + k) * FB_SLOT; }
+    __device__ __forceinline__ uint32_t stage(int s) const { return base + FB_BAR_BYTES + ring_bytes + (uint32_t)s * stage_bytes; }
+    __device__ __forceinline__ uint8_t* stage_gen(int s) const { return gen + FB_BAR_BYTES + ring_bytes + (size_t)s * stage_bytes; }
 };
 
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
@@ -129,17 +147,23 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
 }
 
 // One 32-query block of the warp's 16-key slab: S^T and dP^T on mma.sync, P^T / dS^T in registers, dV += P^T dO, dK += dS^T Q,
-// and the dS^T block into columns [32*sub, 32*sub + 32) of the warp's current ring slot (MN-major SWIZZLE_128B: key row r at
-// r*128, 16-byte chunk c of the row at chunk c ^ (r & 7)).
+// and the dS^T block into query columns [32*sub4, 32*sub4 + 32) of the warp's current ring slot (MN-major SWIZZLE_128B: 64-query
+// atom sub4 >> 1 at +2048, key row r at r*128, 16-byte chunk c of the row at chunk c ^ (r & 7)).  `sub` = sub4 & 1 is also the
+// half of the 64-row Q / dO tile the block reads.
 //   ls / ds / mw: SHARED-space addresses of the per-query LSE (log2 domain), D and keep word of this block's queries, already
 //   offset by the lane's 2*tq.  MASK: the block touches the causal diagonal of the slab.
 template <bool DROP, bool MASK>
-__device__ __forceinline__ void fb_block(float (*dk)[4], float (*dv)[4], const uint32_t (*ka)[4], const uint32_t (*va)[4], uint32_t qt,
+__device__ __forceinline__ void fb_block(float (*dk)[4], float (*dv)[4], uint32_t kaddr, const uint32_t (*va)[4], uint32_t qt,
                                          uint32_t gt, int sub, int q0, uint32_t ls, uint32_t ds, uint32_t mw, uint32_t mk0, uint32_t mk1,
                                          const OwnRows& r, const TileEnv& e, uint32_t slot_lane, int g) {
     const int tq = e.tq;
     float st[4][4], dpt[4][4];
-    mma_a_tT<4>(st, ka, qt, 4 * sub, e.lo);
+    {   // the slab's K rows as A fragments, re-read from the staged tile every block (8 registers that need not stay live)
+        uint32_t ka[2][4];
+        ldsm_x4(ka[0][0], ka[0][1], ka[0][2], ka[0][3], kaddr);
+        ldsm_x4(ka[1][0], ka[1][1], ka[1][2], ka[1][3], kaddr ^ 32u);
+        mma_a_tT<4>(st, ka, qt, 4 * sub, e.lo);
+    }
     mma_a_tT<4>(dpt, va, gt, 4 * sub, e.lo);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -230,53 +254,56 @@ __device__ __forceinline__ void fb_producer(const FSm& sm, const FArgs& a, int l
     }
 }
 
-// warp 1: tcgen05 issuer: dQ[item, 128-query tile] += dS block * K slab
+// warp 1: tcgen05 issuer, dQ[item, 128-query tile] += dS block * K slab.  Lane w < FB_NCW watches compute warp w's ring slots
+// (non-blocking probes) and prepares the two descriptors of a ready block; lane 0 issues the MMAs one after the other (one thread:
+// MMAs into the same accumulator stay ordered) and commits each block's slot back to its warp.  The accumulators were cleared by
+// the epilogue warps, so every MMA accumulates; the only state is a per-TMEM-slot block count (four 8-bit counters in a register).
 __device__ __forceinline__ void fb_issuer(const FSm& sm, const FArgs& a, int lane, uint32_t tmem_base, int my_items) {
     uint32_t nb = 0;  // lane w < FB_NCW: blocks consumed from compute warp w
-    int* cur_li = sm.istate();
-    int* cnt = cur_li + FB_MAXNI;
-    int* touched = cnt + FB_MAXNI;
-    const int per_item = a.nslabs * a.ntq;
+    const uint32_t per_item = (uint32_t)(a.nslabs * a.nq128);
     const long long total = (long long)my_items * per_item;
     long long done = 0;
+    uint32_t cnt = 0;  // lane 0: blocks issued so far for the tenant of each TMEM slot (8 bits each)
+    const uint32_t ad_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024, version 1, SWIZZLE_128B
+    const uint32_t bd_hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO = 512, version 1, SWIZZLE_64B
     long long spin0 = clock64();
     while (done < total) {
         bool ready = false;
-        if (lane < FB_NCW) ready = mbar_try_wait(sm.rfull(lane, nb & 1u), (nb >> 1) & 1u);
+        uint32_t ad_lo = 0, bd_lo = 0, info = 0;
+        if (lane < FB_NCW) {
+            const uint32_t k = a.nslot == 2 ? (nb & 1u) : 0u, use = a.nslot == 2 ? (nb >> 1) : nb;
+            ready = mbar_test(sm.rfull(lane, (int)k), use & 1u);
+            if (ready) {
+                const uint32_t m = sm.meta()[FB_MAXSLOT * lane + k];
+                const uint32_t mli = m & 0xFFFFu, t = (m >> 16) & 15u, slab = (m >> 20) & 63u;
+                const uint32_t i = mli % (uint32_t)a.ni, st = mli % (uint32_t)a.nstage;
+                ad_lo = ((sm.slot(lane, (int)k) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);  // the two 64-query atoms are 2 KiB apart
+                bd_lo = (((sm.stage((int)st) + a.off_k + slab * 1024u) >> 4) & 0x3FFFu) | ((512u >> 4) << 16);
+                info = ((i * (uint32_t)a.nq128 + t) * 32u) | (i << 16) | (st << 20) | (k << 24);
+            }
+        }
         uint32_t mask = __ballot_sync(0xffffffffu, ready);
         if (mask == 0u) {
             if (clock64() - spin0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
+            __nanosleep(32);
             continue;
         }
+        tc_fence_after();
         while (mask != 0u) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const uint32_t hs = __shfl_sync(0xffffffffu, nb & 1u, src);
+            const uint32_t al = __shfl_sync(0xffffffffu, ad_lo, src), bl = __shfl_sync(0xffffffffu, bd_lo, src);
+            const uint32_t inf = __shfl_sync(0xffffffffu, info, src);
             if (lane == 0) {
-                const uint32_t m = sm.meta()[2 * src + hs];
-                const int mli = (int)(m & 0xFFFFu), t = (int)((m >> 16) & 15u), slab = (int)((m >> 20) & 63u);
-                const int i = mli % a.ni, s = mli % a.nstage;
-                if (cur_li[i] != mli) {
-                    // first block of a new tenant of TMEM slot i: the previous tenant's dQ must have been read out
-                    mbar_wait(sm.dqempty(i), ((uint32_t)(mli / a.ni) & 1u) ^ 1u);
-                    cur_li[i] = mli;
-                    cnt[i] = 0;
-                    touched[i] = 0;
-                }
-                tc_fence_after();
-                const uint32_t slot = sm.slot(src, hs);
-                // M = 128 queries = two 64-query atoms LBO bytes apart: (block | zeros) for the even tile, (zeros | block) for the odd
-                const uint64_t ad = (t & 1) == 0 ? make_desc(slot, sm.zero_hi() - slot, 1024u, 2u)
-                                                 : make_desc(sm.zero_lo(), slot - sm.zero_lo(), 1024u, 2u);
-                const uint64_t bd = make_desc(sm.stage(s) + a.off_k + (uint32_t)slab * 1024u, 512u, 512u, 4u);
-                const int bit = 1 << (t >> 1);
+                const uint32_t i = (inf >> 16) & 15u, st = (inf >> 20) & 15u, k = (inf >> 24) & 1u;
                 if (!(a.dbg & 2))
-                    tc_mma_bf16(tmem_base + (uint32_t)((i * a.nq128 + (t >> 1)) * 32), ad, bd, FB_IDESC, (touched[i] & bit) != 0 ? 1u : 0u);
-                touched[i] |= bit;
-                tc_commit(sm.rempty(src, hs));
-                if (++cnt[i] == per_item) {
-                    tc_commit(sm.dqfull(i));  // every block of the item has been accumulated
-                    tc_commit(sm.empty(s));   // and its K tile is no longer read
+                    tc_mma_bf16(tmem_base + (inf & 0xFFFFu), ((uint64_t)ad_hi << 32) | al, ((uint64_t)bd_hi << 32) | bl, FB_IDESC, 1u);
+                tc_commit(sm.rempty(src, (int)k));
+                cnt += 1u << (8 * i);
+                if (((cnt >> (8 * i)) & 0xFFu) == per_item) {
+                    cnt &= ~(0xFFu << (8 * i));
+                    tc_commit(sm.dqfull((int)i));  // every block of the item has been accumulated
+                    tc_commit(sm.empty((int)st));  // and its K tile is no longer read
                 }
             }
             if (lane == src) ++nb;
@@ -307,10 +334,18 @@ __device__ __forceinline__ void fb_maskgen(const FSm& sm, const FArgs& a, int wa
     }
 }
 
-// warps 4-7: dQ epilogue, TMEM -> registers -> scale -> bf16 rows
+// warps 4-7: dQ epilogue, TMEM -> registers -> scale -> bf16 rows, then clear the accumulator for the slot's next tenant
 __device__ __forceinline__ void fb_epilogue(const FSm& sm, const FArgs& a, int warp, int lane, uint32_t tmem_base, const FPtrs& p, int n_items) {
     const Dims& d = a.d;
     const int qd = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+    // phase 0 of every dqempty barrier: the slots start out cleared
+    for (int c = 0; c < a.ni * a.nq128 * 2; ++c) tc_st16_zero(tlane + 16u * (uint32_t)c);
+    tc_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+        for (int i = 0; i < a.ni; ++i) mbar_arrive(sm.dqempty(i));
     int li = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
         const int i = li % a.ni, b = item / d.H, h = item % d.H;
@@ -322,12 +357,14 @@ __device__ __forceinline__ void fb_epilogue(const FSm& sm, const FArgs& a, int w
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[16];
+                const uint32_t ta = tlane + (uint32_t)((i * a.nq128 + t) * 32 + 16 * c);
                 if (!(a.dbg & 4)) {
-                    tc_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((i * a.nq128 + t) * 32 + 16 * c), r);
+                    tc_ld16(ta, r);
                 } else {
 #pragma unroll
                     for (int z = 0; z < 16; ++z) r[z] = 0u;
                 }
+                tc_st16_zero(ta);
                 if (q < d.Sq) {
                     uint4 u0, u1;
                     u0.x = pack2(__uint_as_float(r[0]) * d.scale, __uint_as_float(r[1]) * d.scale);
@@ -344,6 +381,7 @@ __device__ __forceinline__ void fb_epilogue(const FSm& sm, const FArgs& a, int w
                 }
             }
         }
+        tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.dqempty(i));
@@ -359,11 +397,11 @@ __device__ __forceinline__ void fb_compute(const FSm& sm, const FArgs& a, int wa
     const TileEnv env = make_env(d, drop, lane);
     // ldmatrix (non-trans) addresses of a 16-row A fragment inside a 64B-swizzled tile: matrix m = lane >> 3 holds rows
     // 8*(m & 1) + (lane & 7), 16-byte chunk 2*ks + (m >> 1)
-    uint32_t aoff[2];
+    // (k-step 1 is chunk + 2: the same address with bit 5 flipped)
+    uint32_t aoff0;
     {
         const int m = lane >> 3, row = 8 * (m & 1) + (lane & 7);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) aoff[ks] = (uint32_t)(row * 64 + (((2 * ks + (m >> 1)) ^ ((row >> 1) & 3)) << 4));
+        aoff0 = (uint32_t)(row * 64 + (((m >> 1) ^ ((row >> 1) & 3)) << 4));
     }
     const int nq = a.ntq * TK;
     uint32_t nb = 0;  // blocks this warp has produced (selects the half slot and its phase)
@@ -377,40 +415,49 @@ __device__ __forceinline__ void fb_compute(const FSm& sm, const FArgs& a, int wa
         // every warp passes through every item in order, so no warp can release a stage before the producer has filled it
         mbar_wait(sm.full(s), ph);
         mbar_wait(sm.sfull(s), ph);
+        bool slot_checked = false;
         for (int slab = first_slab<FB_NCW>(li, a.nslabs, cw); slab < a.nslabs; slab += FB_NCW) {
+            if (!slot_checked) {
+                // The item's dQ accumulators must have been read out and cleared since the TMEM slot's previous tenant.  ONLY a warp
+                // that contributes blocks to the item may wait here: the item cannot complete without it, so the barrier is at most
+                // one phase ahead.  (A warp without a slab could arrive after the item has come and gone - two phases later the
+                // parity test reads "not yet" for ever.)
+                mbar_wait(sm.dqempty(li % a.ni), (uint32_t)(li / a.ni) & 1u);
+                slot_checked = true;
+            }
             const OwnRows r = own_rows(16 * slab, g, drop, b, d.H, h, d.Sq, false);
-            uint32_t ka[2][4], va[2][4];
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) ldsm_x4(ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3], tK + (uint32_t)slab * 1024u + aoff[ks]);
+            uint32_t va[2][4];
+            const uint32_t kaddr = tK + (uint32_t)slab * 1024u + aoff0;
             load_own(p.V + (size_t)b * d.Sk * p.ldv + h * HD, p.ldv, r.r0, r.r1, d.Sk, d.dh, tq, va);
             float dk[4][4], dv[4][4];
             zero16(dk);
             zero16(dv);
             const uint32_t mk0 = 1u << ick_keybit((uint32_t)r.r0), mk1 = mk0 << 4;
             const uint32_t mws = mw0 + (uint32_t)((slab >> 1) * nq) * 4u;
-            for (int t = 0; t < a.ntq; ++t) {
-                const uint32_t hsel = nb & 1u;
-                mbar_wait(sm.rempty(cw, (int)hsel), ((nb >> 1) & 1u) ^ 1u);
-                const uint32_t slot_lane = sm.slot(cw, (int)hsel) + (uint32_t)(g * 128 + tq * 4);
+            for (int t = 0; t < a.nq128; ++t) {
+                const uint32_t k = a.nslot == 2 ? (nb & 1u) : 0u, use = a.nslot == 2 ? (nb >> 1) : nb;
+                mbar_wait(sm.rempty(cw, (int)k), (use & 1u) ^ 1u);
+                const uint32_t slot_lane = sm.slot(cw, (int)k) + (uint32_t)(g * 128 + tq * 4);
 #pragma unroll 1
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int q0 = t * TK + sub * SUB;
-                    const uint32_t qo = 4u * (uint32_t)q0;
+                for (int sub4 = 0; sub4 < 4; ++sub4) {
+                    const int q0 = t * 128 + sub4 * SUB;
+                    if (q0 >= d.Sq) break;  // columns of queries that do not exist only feed dQ rows that are never stored
+                    const int sub = sub4 & 1;
+                    const uint32_t qo = 4u * (uint32_t)q0, sl = slot_lane + (uint32_t)(sub4 >> 1) * 2048u;
+                    const uint32_t qt = tQ + (uint32_t)(q0 >> 6) * TILE_BYTES, gt = tG + (uint32_t)(q0 >> 6) * TILE_BYTES;
                     if ((d.causal && q0 + SUB - 1 < r.wrow) || (a.dbg & 8)) {
-                        fb_zero_block(sub, slot_lane, g);  // every query precedes every key of the slab
+                        fb_zero_block(sub, sl, g);  // every query precedes every key of the slab
                     } else if (d.causal && r.wrow + 15 > q0) {
-                        fb_block<DROP, true>(dk, dv, ka, va, tQ + t * TILE_BYTES, tG + t * TILE_BYTES, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r,
-                                             env, slot_lane, g);
+                        fb_block<DROP, true>(dk, dv, kaddr, va, qt, gt, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r, env, sl, g);
                     } else {
-                        fb_block<DROP, false>(dk, dv, ka, va, tQ + t * TILE_BYTES, tG + t * TILE_BYTES, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r,
-                                              env, slot_lane, g);
+                        fb_block<DROP, false>(dk, dv, kaddr, va, qt, gt, sub, q0, ls0 + qo, ds0 + qo, mws + qo, mk0, mk1, r, env, sl, g);
                     }
                 }
                 fence_async_smem();  // the block is read by the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    sm.meta()[2 * cw + hsel] = (uint32_t)(li & 0xFFFF) | ((uint32_t)t << 16) | ((uint32_t)slab << 20);
-                    mbar_arrive(sm.rfull(cw, (int)hsel));
+                    sm.meta()[FB_MAXSLOT * cw + k] = (uint32_t)(li & 0xFFFF) | ((uint32_t)t << 16) | ((uint32_t)slab << 20);
+                    mbar_arrive(sm.rfull(cw, (int)k));
                 }
                 ++nb;
             }
@@ -433,6 +480,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
     sm.gen = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     sm.base = smem_u32(sm.gen);
     sm.stage_bytes = a.stage_bytes;
+    sm.nslot = a.nslot;
+    sm.ring_bytes = (uint32_t)(FB_NCW * a.nslot * FB_SLOT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = d.B * d.H;
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -448,23 +497,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
             mbar_init(sm.empty(s), FB_NCW + 1);
         }
         for (int w = 0; w < FB_NCW; ++w)
-            for (int h = 0; h < 2; ++h) {
-                mbar_init(sm.rfull(w, h), 1);
-                mbar_init(sm.rempty(w, h), 1);
+            for (int k = 0; k < FB_MAXSLOT; ++k) {
+                mbar_init(sm.rfull(w, k), 1);
+                mbar_init(sm.rempty(w, k), 1);
             }
         for (int i = 0; i < FB_MAXNI; ++i) {
             mbar_init(sm.dqfull(i), 1);
             mbar_init(sm.dqempty(i), 4);
         }
-        int* st = sm.istate();
-        for (int i = 0; i < 3 * FB_MAXNI; ++i) st[i] = i < FB_MAXNI ? -1 : 0;  // cur_li = -1, cnt = 0, touched = 0
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    {   // the two boxes of zeros that stand in for the other 64-query atom of a block's M = 128 operand
-        uint32_t* zl = reinterpret_cast<uint32_t*>(sm.gen + FB_BAR_BYTES);
-        uint32_t* zh = reinterpret_cast<uint32_t*>(sm.gen + FB_BAR_BYTES + FB_HALF + 2 * FB_NCW * FB_HALF);
-        for (int i = threadIdx.x; i < FB_HALF / 4; i += FB_THREADS) { zl[i] = 0u; zh[i] = 0u; }
-        fence_async_smem();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_ptr())), "n"(FB_TMEM_COLS) : "memory");
@@ -560,13 +601,19 @@ int ick_mha_bwd_fused(const void* Q, const void* K, const void* V, const void* O
     a.off_ds = a.off_ls + (uint32_t)a.ntq * TK * 4;
     a.off_mw = a.off_ds + (uint32_t)a.ntq * TK * 4;
     a.stage_bytes = (a.off_mw + (uint32_t)a.ngroups * a.ntq * TK * 4 + 1023u) / 1024u * 1024u;
-    const int avail = FB_SMEM_MAX - 1024 /*alignment slack*/ - FB_BAR_BYTES - FB_RING;
-    int ns = avail / (int)a.stage_bytes;
-    if (ns < 2) return ICK_ERR_UNSUPPORTED;
-    a.nstage = ns > FB_MAXSTAGE ? FB_MAXSTAGE : ns;
     a.ni = FB_TMEM_COLS / (a.nq128 * 32);
     if (a.ni > FB_MAXNI) a.ni = FB_MAXNI;
-    if (a.ni < 2) return ICK_ERR_UNSUPPORTED;
+    if (a.ni < 2 || a.nslabs * a.nq128 > 255) return ICK_ERR_UNSUPPORTED;
+    // shared memory: barriers | ring (one or two 4 KiB slots per compute warp) | operand stages.  Two stages are a must (the next
+    // item loads while this one computes); a second ring slot is taken when it still fits.
+    const int avail = FB_SMEM_MAX - 1024 /*alignment slack*/ - FB_BAR_BYTES;
+    a.nslot = (avail - 2 * FB_NCW * FB_SLOT) / (int)a.stage_bytes >= 2 && !(a.dbg & 16) ? 2 : 1;
+    int ns = (avail - a.nslot * FB_NCW * FB_SLOT) / (int)a.stage_bytes;
+    if (ns < 2) return ICK_ERR_UNSUPPORTED;
+    a.nstage = ns > FB_MAXSTAGE ? FB_MAXSTAGE : ns;
+    // A warp can run at most nstage items ahead of the slowest one (it needs a free operand stage), and two items that share a
+    // TMEM slot (li and li + ni) must never be in flight together.  Hence nstage <= ni.
+    if (a.nstage > a.ni) a.nstage = a.ni;
     int rc;
     CUtensorMap tmQ, tmG, tmK;
     if ((rc = make_tmap3(&tmQ, Q, H, Sq, B, ldq))) return rc;
@@ -577,7 +624,7 @@ int ick_mha_bwd_fused(const void* Q, const void* K, const void* V, const void* O
         ick_launch(fb_rowdot_kernel, (int)((n + 255) / 256), 256, 0, stream)((const bf16*)O, (const bf16*)dO, dsum, B, H, Sq, dh, ldo, lddo);
         if ((rc = ick_check_launch("mha_bwd_fused(rowdot)"))) return rc;
     }
-    const int smem = 1024 + FB_BAR_BYTES + FB_RING + a.nstage * (int)a.stage_bytes;
+    const int smem = 1024 + FB_BAR_BYTES + FB_NCW * a.nslot * FB_SLOT + a.nstage * (int)a.stage_bytes;
     const int grid = B * H < fb_num_sms() ? B * H : fb_num_sms();
     static bool attr_done[2] = {false, false};
     const int v = dc.thr != 0u ? 1 : 0;

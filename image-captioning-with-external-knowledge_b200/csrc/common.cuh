@@ -174,13 +174,16 @@ __host__ __device__ __forceinline__ uint32_t ick_fmix32(uint32_t h) {
     return h;
 }
 __host__ __device__ __forceinline__ uint32_t ick_keybit(uint32_t key) { return ((key & 31u) >> 1) + ((key & 1u) << 4); }
-// keep word of key group kg of a row; t16 in [2, 65534]
+// keep word of key group kg of a row; t16 in [2, 65534].  t16 = 0x8000 (p = 0.5, the reference's default) is ONE plane: the
+// complement of a single hash; the general case loops over the planes (never unrolled: it sits inside the attention tile loops).
 __host__ __device__ __forceinline__ uint32_t ick_keepword(uint32_t rowmix, uint32_t kg, uint32_t t16) {
-    uint32_t lt = 0u, eq = 0xFFFFFFFFu;
+    const uint32_t w0 = ick_fmix32(rowmix + (kg * 16u) * 0x9E3779B1u);
+    if (t16 == 0x8000u) return ~w0;
+    uint32_t lt = 0u, eq = 0xFFFFFFFFu, w = w0;
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) {
-        const uint32_t rest = t16 & (0xFFFFu >> i);  // bits of t16 from plane i downwards
-        if (rest == 0u) break;                       // U < t16 is decided: equal prefixes are not below
-        const uint32_t w = ick_fmix32(rowmix + (kg * 16u + (uint32_t)i) * 0x9E3779B1u);
+        if ((t16 & (0xFFFFu >> i)) == 0u) break;  // U < t16 is decided: equal prefixes are not below
+        if (i > 0) w = ick_fmix32(rowmix + (kg * 16u + (uint32_t)i) * 0x9E3779B1u);
         if ((t16 >> (15 - i)) & 1u) {
             lt |= eq & ~w;
             eq &= w;

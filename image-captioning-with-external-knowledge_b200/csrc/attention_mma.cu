@@ -796,14 +796,19 @@ bool use_ds(int Sq, int Sk, int causal) {
     if (v == 2) return !causal && Sq >= 256;
     return v != 0;
 }
-bool use_fused() {  // ICK_ATTN_FUSED=0: the two-kernel backward (dQ and dK/dV each recompute the probabilities)
+// ICK_ATTN_BWD = tc (default: everything on tcgen05 / TMEM, attention_bwd_tc.cu) | hybrid (mma.sync + tcgen05 dQ, attention_bwd_fused.cu) |
+// split (the two-kernel backward: dQ and dK/dV each recompute the probabilities).  Each falls through to the next when a shape does not fit.
+int bwd_mode() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("ICK_ATTN_FUSED");
-        v = (e && e[0] == '0') ? 0 : 1;
+        const char* e = getenv("ICK_ATTN_BWD");
+        v = (e && e[0] == 's') ? 0 : (e && e[0] == 'h') ? 1 : 2;
+        const char* f = getenv("ICK_ATTN_FUSED");
+        if (f && f[0] == '0') v = 0;
     }
-    return v != 0;
+    return v;
 }
+bool use_fused() { return bwd_mode() >= 1; }
 bool use_persistent() {
     static int v = -1;
     if (v < 0) {
@@ -868,6 +873,10 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
                     ((uintptr_t)O & 15) == 0,
                 "mha_bwd: operands must be 16-byte aligned");
     int rc;
+    if (bwd_mode() == 2) {
+        rc = ick_mha_bwd_tc(Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, causal, dc, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     if (use_fused()) {
         rc = ick_mha_bwd_fused(Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, causal, dc, stream);
         if (rc != ICK_ERR_UNSUPPORTED) return rc;

@@ -28,6 +28,29 @@
 #include "attention_internal.h"
 #include "attention_mma.cuh"
 
+#ifdef ICK_TB_TRACE
+// Debug build only (-DICK_TB_TRACE): per-role timeline of CTA 0 of the last launch, read back by tools/attn_trace.py.
+__device__ unsigned long long ick_tb_trace_buf[6 * 4096];
+#define TBT_DECL(role) unsigned int tr_i_ = 0; const unsigned int tr_role_ = (role)
+#define TBT(ev, tile)                                                                                      \
+    do {                                                                                                   \
+        if (blockIdx.x == 0 && tr_i_ < 2047) {                                                             \
+            ick_tb_trace_buf[tr_role_ * 4096 + 2 * tr_i_] = ((unsigned long long)(ev) << 32) | (unsigned)(tile); \
+            ick_tb_trace_buf[tr_role_ * 4096 + 2 * tr_i_ + 1] = clock64();                                 \
+            ++tr_i_;                                                                                       \
+            ick_tb_trace_buf[tr_role_ * 4096 + 2 * tr_i_] = 0xFFFFFFFFFFFFFFFFull;                         \
+        }                                                                                                  \
+    } while (0)
+extern "C" int ick_debug_tb_trace_read(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ick_tb_trace_buf, sizeof(unsigned long long) * 6 * 4096);
+    return 6 * 2048;
+}
+#else
+#define TBT_DECL(role) do {} while (0)
+#define TBT(ev, tile) do {} while (0)
+#endif
+
 namespace {
 using namespace ickattn;
 
@@ -78,6 +101,21 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// descriptors as (lo, hi) words: the hi word (SBO, version, swizzle) is a constant per operand kind, the lo word (start, LBO) base + k * constant
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr uint32_t DH_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512, version 1, SWIZZLE_64B
+constexpr uint32_t DH_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t dlo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
+
 __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -146,10 +184,27 @@ constexpr int TB_FIXED = TB_BAR_BYTES + 2 * TB_ZBOX + 4 * TB_TILE;  // 70656
 // causal: tile (key block kb, query tile qt) contributes nothing when every query precedes every key
 __device__ __forceinline__ bool tile_dead(const Dims& d, int kb, int qt) { return d.causal && qt * TB_QT + TB_QT - 1 < kb * TB_KB; }
 
-// ---- warp 0: TMA producer + per-query scalars ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tb_producer(const TSm& sm, const TArgs& a, int lane, const CUtensorMap* tmQ, const CUtensorMap* tmG,
-                                            const CUtensorMap* tmK, const CUtensorMap* tmV, const TPtrs& p, int n_items) {
+// ---- keep words of a key block, Mw[32-key group g < 4][query]: warp 3 and (after its copies are issued) warp 0, half of the queries each ----
+__device__ __forceinline__ void tb_fill_keepwords(const TSm& sm, const TArgs& a, int half, int lane, const DropCfg& drop, uint32_t t16, int s, int b, int h,
+                                                  int kb) {
     const Dims& d = a.d;
+    const int nq = a.ntq * TK;
+    uint32_t* Mw = reinterpret_cast<uint32_t*>(sm.gen_of(sm.kv(s) + a.off_mw));
+    for (int q = half * 32 + lane; q < nq; q += 64) {
+        const uint32_t rm = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, q));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) Mw[g * nq + q] = q < d.Sq ? ick_keepword(rm, (uint32_t)(4 * kb + g), t16) : 0u;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.kv_sfull(s));
+}
+// ---- warp 0: TMA producer + per-query scalars ------------------------------------------------------------------------------------------
+template <bool DROP>
+__device__ __forceinline__ void tb_producer(const TSm& sm, const TArgs& a, int lane, const CUtensorMap* tmQ, const CUtensorMap* tmG,
+                                            const CUtensorMap* tmK, const CUtensorMap* tmV, const TPtrs& p, DropCfg drop, int n_items) {
+    const Dims& d = a.d;
+    if (DROP) ick_resolve_seed(drop);
+    const uint32_t t16 = ick_attn_t16(drop.thr);
     uint32_t nqg = 0, nkvu = 0;  // ring use counters
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / d.H, h = item % d.H;
@@ -188,135 +243,176 @@ __device__ __forceinline__ void tb_producer(const TSm& sm, const TArgs& a, int l
                     tma_load_3d(st + a.off_v + t * TILE_BYTES, tmV, sm.kv_full(s), h * HD, (2 * kb + t) * TK, b);
                 }
             }
+            if (DROP) tb_fill_keepwords(sm, a, 0, lane, drop, t16, s, b, h, kb);
             ++nkvu;
         }
     }
 }
 
-// ---- warps 2-3: keep words of a key block, Mw[32-key group g < 4][query] -----------------------------------------------------------------
-__device__ __forceinline__ void tb_maskgen(const TSm& sm, const TArgs& a, int warp, int lane, DropCfg drop, int n_items) {
+__device__ __forceinline__ void tb_maskgen(const TSm& sm, const TArgs& a, int lane, DropCfg drop, int n_items) {
     const Dims& d = a.d;
     ick_resolve_seed(drop);
     const uint32_t t16 = ick_attn_t16(drop.thr);
-    const int nq = a.ntq * TK;
     uint32_t nkvu = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / d.H, h = item % d.H;
         for (int kb = 0; kb < a.nkb; ++kb) {
             const int s = (int)(nkvu % (uint32_t)a.nkv);
             mbar_wait(sm.kv_empty(s), ((nkvu / (uint32_t)a.nkv) & 1u) ^ 1u);
-            uint32_t* Mw = reinterpret_cast<uint32_t*>(sm.gen_of(sm.kv(s) + a.off_mw));
-            for (int q = (warp - 2) * 32 + lane; q < nq; q += 64) {
-                const uint32_t rm = ick_rowmix(drop.seed, drop.site, prob_row(b, d.H, h, d.Sq, q));
-#pragma unroll
-                for (int g = 0; g < 4; ++g) Mw[g * nq + q] = q < d.Sq ? ick_keepword(rm, (uint32_t)(4 * kb + g), t16) : 0u;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sm.kv_sfull(s));
+            tb_fill_keepwords(sm, a, 1, lane, drop, t16, s, b, h, kb);
             ++nkvu;
         }
     }
 }
 
-// ---- warp 1: the tcgen05 issuer ------------------------------------------------------------------------------------------------------------
-struct TileRef {  // what the gradient MMAs of a tile need to know
-    uint32_t qg_slot, kv_slot, dkv_buf;
-    int qt, valid;
-    uint32_t first_of_kb, last_of_kb, first_dq, last_of_item;  // flags
+// ---- warps 1 and 2: the two tcgen05 issuer threads --------------------------------------------------------------------------------------
+// Tile sequence of the CTA (items x key blocks x live query tiles), generated incrementally
+struct TileIter {
+    int item, kb, qt, qt_first;
+    uint32_t nqg, nkvu;
+    bool done;
 };
-__device__ __forceinline__ void tb_issue_sp(const TSm& sm, const TArgs& a, uint32_t tmem_base, int w, uint32_t use, uint32_t qg_slot, uint32_t kv_slot, int qt) {
-    // S^T = K_blk Q_t^T, dP^T = V_blk dO_t^T : A = K / V block (128 rows x 64 B, K-major SWIZZLE_64B), B = Q / dO tile (64 rows), K = 32 = 2 steps
-    mbar_wait(sm.sp_empty(w), (use & 1u) ^ 1u);
-    tc_fence_after();
-    const uint32_t kblk = sm.kv((int)kv_slot), vblk = kblk + a.off_v;
-    const uint32_t qtile = sm.qg((int)qg_slot) + (uint32_t)qt * TILE_BYTES, gtile = qtile + a.off_do;
+__device__ __forceinline__ void ti_settle(TileIter& it, const TArgs& a, int n_items) {
+    // skip dead tiles / advance to the next key block / item until (item, kb, qt) is a live tile or the sequence ends
+    while (!it.done) {
+        if (it.qt < a.ntq) {
+            if (!tile_dead(a.d, it.kb, it.qt)) return;
+            ++it.qt;
+            it.qt_first = it.qt;
+            continue;
+        }
+        it.qt = 0;
+        it.qt_first = 0;
+        ++it.nkvu;
+        if (++it.kb == a.nkb) {
+            it.kb = 0;
+            ++it.nqg;
+            it.item += gridDim.x;
+            if (it.item >= n_items) it.done = true;
+        }
+    }
+}
+__device__ __forceinline__ TileIter ti_begin(const TArgs& a, int n_items) {
+    TileIter it;
+    it.item = blockIdx.x; it.kb = 0; it.qt = 0; it.qt_first = 0; it.nqg = 0; it.nkvu = 0; it.done = it.item >= n_items;
+    ti_settle(it, a, n_items);
+    return it;
+}
+
+// warp 1: S^T = K_blk Q_t^T and dP^T = V_blk dO_t^T of every tile, as soon as the tile's warpgroup has read its previous tile out of
+// TMEM.  A = K / V block (128 rows x 64 B, K-major SWIZZLE_64B), B = Q / dO tile (64 rows), K = 32 = two steps of 32 bytes.
+__device__ __forceinline__ void tb_issuer_sp(const TSm& sm, const TArgs& a, uint32_t tmem_base, int n_items) {
+    TileIter it = ti_begin(a, n_items);
+    TBT_DECL(0);
     constexpr uint32_t ID = idesc(TB_QT, 0, 0);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        tc_mma(tmem_base + TC_S0 + (uint32_t)w * TC_SETSTRIDE, sdesc(kblk + 32u * k, 16u, 512u, 4u), sdesc(qtile + 32u * k, 16u, 512u, 4u), ID, (uint32_t)k);
-        tc_mma(tmem_base + TC_DP0 + (uint32_t)w * TC_SETSTRIDE, sdesc(vblk + 32u * k, 16u, 512u, 4u), sdesc(gtile + 32u * k, 16u, 512u, 4u), ID, (uint32_t)k);
+    uint32_t n = 0, seen_qg = 0xFFFFFFFFu, seen_kv = 0xFFFFFFFFu;
+    uint32_t klo = 0, vlo = 0, qbase = 0;
+    while (!it.done) {
+        const uint32_t qs = it.nqg & 1u, ks = it.nkvu % (uint32_t)a.nkv;
+        if (seen_qg != it.nqg) {
+            mbar_wait(sm.qg_full((int)qs), (it.nqg >> 1) & 1u);
+            seen_qg = it.nqg;
+            qbase = sm.qg((int)qs);
+        }
+        if (seen_kv != it.nkvu) {
+            mbar_wait(sm.kv_full((int)ks), (it.nkvu / (uint32_t)a.nkv) & 1u);
+            seen_kv = it.nkvu;
+            klo = dlo(sm.kv((int)ks), 16u);
+            vlo = dlo(sm.kv((int)ks) + a.off_v, 16u);
+        }
+        const int w = (int)(n & 1u);
+        TBT(1, n);
+        mbar_wait(sm.sp_empty(w), ((n >> 1) & 1u) ^ 1u);
+        TBT(2, n);
+        tc_fence_after();
+        const uint32_t qlo = dlo(qbase + (uint32_t)it.qt * TILE_BYTES, 16u), glo = dlo(qbase + a.off_do + (uint32_t)it.qt * TILE_BYTES, 16u);
+        const uint32_t ts = tmem_base + TC_S0 + (uint32_t)w * TC_SETSTRIDE, tp = tmem_base + TC_DP0 + (uint32_t)w * TC_SETSTRIDE;
+        tc_mma2(ts, klo, DH_SW64, qlo, DH_SW64, ID, 0u);
+        tc_mma2(tp, vlo, DH_SW64, glo, DH_SW64, ID, 0u);
+        tc_mma2(ts, klo + 2u, DH_SW64, qlo + 2u, DH_SW64, ID, 1u);  // + 32 bytes along K
+        tc_mma2(tp, vlo + 2u, DH_SW64, glo + 2u, DH_SW64, ID, 1u);
+        tc_commit(sm.sp_full(w));
+        TBT(3, n);
+        const bool last_of_kb = it.qt == a.ntq - 1, last_of_item = last_of_kb && it.kb == a.nkb - 1;
+        if (last_of_kb) tc_commit(sm.kv_empty((int)ks));     // this thread's reads of the K / V block are done when these MMAs are
+        if (last_of_item) tc_commit(sm.qg_empty((int)qs));
+        ++n;
+        ++it.qt;
+        ti_settle(it, a, n_items);
     }
-    tc_commit(sm.sp_full(w));
 }
-__device__ __forceinline__ void tb_issue_grad(const TSm& sm, const TArgs& a, uint32_t tmem_base, int w, uint32_t use, const TileRef& t,
-                                              uint32_t& dkv_use, uint32_t& dq_use) {
-    mbar_wait(sm.ps_full(w), use & 1u);
-    if (t.first_of_kb) mbar_wait(sm.dkv_empty((int)t.dkv_buf), ((dkv_use >> 1) & 1u) ^ 1u);  // dkv_use counts key blocks: buffer = use & 1
-    if (t.first_dq) mbar_wait(sm.dq_empty(), (dq_use & 1u) ^ 1u);
-    tc_fence_after();
-    const uint32_t pt = sm.ptile(w), dst = sm.dstile(w);
-    const uint32_t qtile = sm.qg((int)t.qg_slot) + (uint32_t)t.qt * TILE_BYTES, gtile = qtile + a.off_do;
-    const uint32_t kblk = sm.kv((int)t.kv_slot);
+
+// warp 2: the gradient MMAs of every tile once its P^T / dS^T rows are written.
+//   dV += P^T dO_t, dK += dS^T Q_t : A = tile rows (keys) x 64 queries, K-major SWIZZLE_128B; B = dO / Q tile, MN-major SWIZZLE_64B (16 rows per step)
+//   dQ_grp += dS K_blk             : A = the dS^T tile read MN-major (its 64 queries are one atom of M = 128, the other atom a box of zeros
+//                                    LBO bytes away), B = K block MN-major; K = 128 keys = 8 steps of 16 rows
+__device__ __forceinline__ void tb_issuer_grad(const TSm& sm, const TArgs& a, uint32_t tmem_base, int n_items) {
+    TileIter it = ti_begin(a, n_items);
+    TBT_DECL(1);
     constexpr uint32_t ID_KV = idesc(32, 0, 1), ID_Q = idesc(32, 1, 1);
-    const uint32_t tdk = tmem_base + TC_DK0 + t.dkv_buf * TC_DKVSTRIDE, tdv = tmem_base + TC_DV0 + t.dkv_buf * TC_DKVSTRIDE;
-    if (!(a.dbg & 2)) {
-        // dV += P^T dO_t, dK += dS^T Q_t : A = tile rows (keys) x 64 queries, K-major SWIZZLE_128B; B = dO / Q tile, MN-major SWIZZLE_64B
-#pragma unroll
-        for (int k = 0; k < TB_QT / 16; ++k) {
-            const uint32_t acc = (t.first_of_kb && k == 0) ? 0u : 1u;
-            tc_mma(tdv, sdesc(pt + 32u * k, 16u, 1024u, 2u), sdesc(gtile + 1024u * k, 512u, 512u, 4u), ID_KV, acc);
-            tc_mma(tdk, sdesc(dst + 32u * k, 16u, 1024u, 2u), sdesc(qtile + 1024u * k, 512u, 512u, 4u), ID_KV, acc);
+    uint32_t n = 0, dkv_use = 0, dq_use = 0, seen_qg = 0xFFFFFFFFu, seen_kv = 0xFFFFFFFFu;
+    uint32_t klo = 0, qbase = 0;
+    const uint32_t zl4 = sm.zero_lo() >> 4, zh4 = sm.zero_hi() >> 4;
+    while (!it.done) {
+        const uint32_t qs = it.nqg & 1u, ks = it.nkvu % (uint32_t)a.nkv;
+        if (seen_qg != it.nqg) {
+            mbar_wait(sm.qg_full((int)qs), (it.nqg >> 1) & 1u);
+            seen_qg = it.nqg;
+            qbase = sm.qg((int)qs);
         }
-    }
-    if (!(a.dbg & 4)) {
-        // dQ_grp += dS K_blk : A = the dS^T tile read MN-major (its 64 queries are one atom of M = 128, the other atom is a box of
-        // zeros LBO bytes away), B = K block MN-major; K = 128 keys = 8 steps of 16 rows
-        const uint32_t tdq = tmem_base + TC_DQ + 32u * (uint32_t)(t.qt >> 1);
-#pragma unroll
-        for (int k = 0; k < TB_KB / 16; ++k) {
-            const uint32_t rows = dst + 2048u * k;
-            const uint64_t ad = (t.qt & 1) == 0 ? sdesc(rows, sm.zero_hi() - rows, 1024u, 2u) : sdesc(sm.zero_lo(), rows - sm.zero_lo(), 1024u, 2u);
-            tc_mma(tdq, ad, sdesc(kblk + 1024u * k, 512u, 512u, 4u), ID_Q, (t.first_dq && k == 0) ? 0u : 1u);
+        if (seen_kv != it.nkvu) {
+            mbar_wait(sm.kv_full((int)ks), (it.nkvu / (uint32_t)a.nkv) & 1u);
+            seen_kv = it.nkvu;
+            klo = dlo(sm.kv((int)ks), 512u);
         }
-    }
-    tc_commit(sm.ps_empty(w));
-    if (t.last_of_kb) {
-        tc_commit(sm.dkv_full((int)t.dkv_buf));
-        tc_commit(sm.kv_empty((int)t.kv_slot));
-        ++dkv_use;
-    }
-    if (t.last_of_item) {
-        tc_commit(sm.dq_full());
-        tc_commit(sm.qg_empty((int)t.qg_slot));
-        ++dq_use;
-    }
-}
-__device__ __forceinline__ void tb_issuer(const TSm& sm, const TArgs& a, uint32_t tmem_base, int n_items) {
-    const Dims& d = a.d;
-    uint32_t n = 0;        // tiles issued (S^T / dP^T)
-    uint32_t nqg = 0, nkvu = 0, dkv_use = 0, dq_use = 0;
-    TileRef pend;
-    pend.valid = 0;
-    uint32_t pend_n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t qs = nqg & 1u;
-        mbar_wait(sm.qg_full((int)qs), (nqg >> 1) & 1u);
-        for (int kb = 0; kb < a.nkb; ++kb) {
-            const uint32_t ks = nkvu % (uint32_t)a.nkv;
-            mbar_wait(sm.kv_full((int)ks), (nkvu / (uint32_t)a.nkv) & 1u);
-            // tiles of this key block: queries that can see at least one of its keys
-            int qt_first = 0;
-            while (qt_first < a.ntq && tile_dead(d, kb, qt_first)) ++qt_first;
-            for (int qt = qt_first; qt < a.ntq; ++qt) {
-                tb_issue_sp(sm, a, tmem_base, (int)(n & 1u), n >> 1, qs, ks, qt);
-                if (pend.valid) tb_issue_grad(sm, a, tmem_base, (int)(pend_n & 1u), pend_n >> 1, pend, dkv_use, dq_use);
-                pend.valid = 1;
-                pend.qg_slot = qs;
-                pend.kv_slot = ks;
-                pend.dkv_buf = dkv_use & 1u;  // (after the previous tile's gradient MMAs: a finished key block has bumped the counter)
-                pend.qt = qt;
-                pend.first_of_kb = qt == qt_first;
-                pend.last_of_kb = qt == a.ntq - 1;
-                pend.first_dq = kb == 0 && (qt & 1) == 0;
-                pend.last_of_item = kb == a.nkb - 1 && qt == a.ntq - 1;
-                pend_n = n;
-                ++n;
+        const int w = (int)(n & 1u);
+        const bool first_of_kb = it.qt == it.qt_first, last_of_kb = it.qt == a.ntq - 1;
+        const bool first_dq = it.kb == 0 && (it.qt & 1) == 0, last_of_item = last_of_kb && it.kb == a.nkb - 1;
+        const uint32_t buf = dkv_use & 1u;
+        TBT(4, n);
+        mbar_wait(sm.ps_full(w), (n >> 1) & 1u);
+        TBT(5, n);
+        if (first_of_kb) mbar_wait(sm.dkv_empty((int)buf), ((dkv_use >> 1) & 1u) ^ 1u);
+        if (first_dq) mbar_wait(sm.dq_empty(), (dq_use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t plo = dlo(sm.ptile(w), 16u), slo = dlo(sm.dstile(w), 16u);
+        const uint32_t qlo = dlo(qbase + (uint32_t)it.qt * TILE_BYTES, 512u), glo = dlo(qbase + a.off_do + (uint32_t)it.qt * TILE_BYTES, 512u);
+        const uint32_t tdk = tmem_base + TC_DK0 + buf * TC_DKVSTRIDE, tdv = tmem_base + TC_DV0 + buf * TC_DKVSTRIDE;
+        if (!(a.dbg & 2)) {
+            const uint32_t acc0 = first_of_kb ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < TB_QT / 16; ++k) {  // A: + 32 bytes along K; B: + 16 rows x 64 bytes
+                tc_mma2(tdv, plo + 2u * k, DH_SW128, glo + 64u * k, DH_SW64, ID_KV, k == 0 ? acc0 : 1u);
+                tc_mma2(tdk, slo + 2u * k, DH_SW128, qlo + 64u * k, DH_SW64, ID_KV, k == 0 ? acc0 : 1u);
             }
-            ++nkvu;
         }
-        ++nqg;
+        if (!(a.dbg & 4)) {
+            const uint32_t tdq = tmem_base + TC_DQ + 32u * (uint32_t)(it.qt >> 1);
+            const uint32_t d4 = sm.dstile(w) >> 4;
+            // even tile: (rows | zeros): start = rows, LBO = zero_hi - rows;  odd tile: (zeros | rows): start = zero_lo, LBO = rows - zero_lo;
+            // rows advance by 16 x 128 bytes = 128 descriptor units per step
+            uint32_t alo = (it.qt & 1) == 0 ? (d4 | ((zh4 - d4) << 16)) : (zl4 | ((d4 - zl4) << 16));
+            const uint32_t astep = (it.qt & 1) == 0 ? (128u - (128u << 16)) : (128u << 16);
+            const uint32_t acc0 = first_dq ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < TB_KB / 16; ++k) tc_mma2(tdq, alo + astep * (uint32_t)k, DH_SW128, klo + 64u * k, DH_SW64, ID_Q, k == 0 ? acc0 : 1u);
+        }
+        tc_commit(sm.ps_empty(w));
+        TBT(6, n);
+        if (last_of_kb) {
+            tc_commit(sm.dkv_full((int)buf));
+            tc_commit(sm.kv_empty((int)ks));
+            ++dkv_use;
+        }
+        if (last_of_item) {
+            tc_commit(sm.dq_full());
+            tc_commit(sm.qg_empty((int)qs));
+            ++dq_use;
+        }
+        ++n;
+        ++it.qt;
+        ti_settle(it, a, n_items);
     }
-    if (pend.valid) tb_issue_grad(sm, a, tmem_base, (int)(pend_n & 1u), pend_n >> 1, pend, dkv_use, dq_use);
 }
 
 // ---- warps 4-7: epilogue ------------------------------------------------------------------------------------------------------------------
@@ -430,6 +526,10 @@ __device__ __forceinline__ void tb_softmax(const TSm& sm, const TArgs& a, int wa
     const uint32_t sw = (uint32_t)(row & 7);
     const int nq = a.ntq * TK;
     uint32_t n = 0, nqg = 0, nkvu = 0;
+#ifdef ICK_TB_TRACE
+    unsigned int tr_i_ = 0;
+    const unsigned int tr_role_ = (lane == 0 && qd == 0) ? 2 + w : 5;  // role 5: everybody else (never read)
+#endif
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t qs = nqg & 1u;
         // every warp passes every ring slot in order (also one it has no tile in): nobody can run ahead of the rings' phases
@@ -449,7 +549,9 @@ __device__ __forceinline__ void tb_softmax(const TSm& sm, const TArgs& a, int wa
             for (int qt = qt_first; qt < a.ntq; ++qt, ++n) {
                 if ((int)(n & 1u) != w) continue;
                 const uint32_t use = n >> 1;
+                TBT(7, n);
                 mbar_wait(sm.sp_full(w), use & 1u);
+                TBT(8, n);
                 tc_fence_after();
                 const bool diag = d.causal && kb * TB_KB + TB_KB - 1 > qt * TB_QT;  // some (key, query) pairs of the tile are masked
 #pragma unroll 1
@@ -461,27 +563,38 @@ __device__ __forceinline__ void tb_softmax(const TSm& sm, const TArgs& a, int wa
                         tc_ld16_nowait(tl + TC_S0 + 16u * ch, s);
                         tc_ld16_nowait(tl + TC_DP0 + 16u * ch, dp);
                         tc_wait_ld();
+                        if (ch == TB_QT / 16 - 1) {  // S^T / dP^T of this set have been read: the issuer may overwrite them (next tile)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sm.sp_empty(w));
+                        }
                         const uint32_t qo = 4u * (uint32_t)q0;
                         if (diag) tb_chunk<DROP, true>(s, dp, ls0 + qo, ds0 + qo, mw0 + qo, mk, c, ik, key, q0, pp, pd);
                         else tb_chunk<DROP, false>(s, dp, ls0 + qo, ds0 + qo, mw0 + qo, mk, c, ik, key, q0, pp, pd);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) pp[i] = pd[i] = 0u;
+                        if (ch == TB_QT / 16 - 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(sm.sp_empty(w));
+                        }
                     }
-                    if (ch == 0) mbar_wait(sm.ps_empty(w), (use & 1u) ^ 1u);  // the gradient MMAs of this warpgroup's previous tile are done
+                    if (ch == 0) {
+                        TBT(9, n);
+                        mbar_wait(sm.ps_empty(w), (use & 1u) ^ 1u);  // the gradient MMAs of this warpgroup's previous tile are done
+                        TBT(10, n);
+                    }
                     const uint32_t c0 = ((uint32_t)(2 * ch) ^ sw) << 4, c1 = ((uint32_t)(2 * ch + 1) ^ sw) << 4;
                     sts_u4(prow + c0, pp[0], pp[1], pp[2], pp[3]);
                     sts_u4(prow + c1, pp[4], pp[5], pp[6], pp[7]);
                     sts_u4(drow + c0, pd[0], pd[1], pd[2], pd[3]);
                     sts_u4(drow + c1, pd[4], pd[5], pd[6], pd[7]);
                 }
-                tc_fence_before();
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(sm.sp_empty(w));  // S^T / dP^T of this set have been read
-                    mbar_arrive(sm.ps_full(w));   // P^T / dS^T rows of this warp are in place
-                }
+                if (lane == 0) mbar_arrive(sm.ps_full(w));  // P^T / dS^T rows of this warp are in place
+                TBT(11, n);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(sm.kv_empty((int)ks));
@@ -514,12 +627,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1)
         for (int s = 0; s < 2; ++s) {
             mbar_init(sm.qg_full(s), 1);
             mbar_init(sm.qg_sfull(s), 1);
-            mbar_init(sm.qg_empty(s), 1 + 8);  // issuer commit + the 8 softmax warps
+            mbar_init(sm.qg_empty(s), 2 + 8);  // the two issuer threads' commits + the 8 softmax warps
         }
         for (int s = 0; s < TB_MAXKV; ++s) {
             mbar_init(sm.kv_full(s), 1);
             mbar_init(sm.kv_sfull(s), 2);
-            mbar_init(sm.kv_empty(s), 1 + 8);
+            mbar_init(sm.kv_empty(s), 2 + 8);
         }
         for (int w = 0; w < 2; ++w) {
             mbar_init(sm.sp_full(w), 1);
@@ -550,11 +663,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1)
     ick_pdl_wait();
 
     if (warp == 0) {
-        tb_producer(sm, a, lane, &tmQ, &tmG, &tmK, &tmV, p, n_items);
+        tb_producer<DROP>(sm, a, lane, &tmQ, &tmG, &tmK, &tmV, p, drop, n_items);
     } else if (warp == 1) {
-        if (lane == 0) tb_issuer(sm, a, tmem_base, n_items);
-    } else if (warp < 4) {
-        if (DROP) tb_maskgen(sm, a, warp, lane, drop, n_items);
+        if (lane == 0) tb_issuer_sp(sm, a, tmem_base, n_items);
+    } else if (warp == 2) {
+        if (lane == 0) tb_issuer_grad(sm, a, tmem_base, n_items);
+    } else if (warp == 3) {
+        if (DROP) tb_maskgen(sm, a, lane, drop, n_items);
     } else if (warp < 8) {
         tb_epilogue(sm, a, warp, lane, tmem_base, p, drop.inv_keep, n_items);
     } else {

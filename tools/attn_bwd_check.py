@@ -38,4 +38,5 @@ torch.cuda.synchronize()
 for a, b, name in zip(out, ref, ["dQ", "dK", "dV"]):
     a = a.float().cpu()
     e = float((a - b.float()).abs().max() / b.float().abs().max())
-    print(name, "nan", int(torch.isnan(a).sum()), "err", e)
+    fro = float((a - b.float()).norm() / b.float().norm())
+    print(name, "nan", int(torch.isnan(a).sum()), "max err", round(e, 5), "fro err", round(fro, 5), "norm ratio", round(float(a.norm() / b.float().norm()), 5))

@@ -121,13 +121,10 @@ def args_of(cfg, b):
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(cfg, B_cpu, steps, warmup, budget_s=None):
-    """Train steps of the CPU port of the reference (oracle) with all host threads; returns (captions/s, steps run, cores)."""
+def _cpu_port_step_fn(c):
+    """One train step of the oracle port (oracle/decoder_oracle.py), train-mode dropout from torch's RNG."""
     from oracle import decoder_oracle as orc
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    c = cfg.with_batch(B_cpu)
     shapes = layout.param_shapes(c.variant, c.V, c.D, c.L, c.ff, c.ff)
     p = syn.det_weights(shapes)
     p["pos_encoder.pe"] = orc.positional_table(5000, c.D).unsqueeze(1)
@@ -155,6 +152,57 @@ def cpu_reference_steps(cfg, B_cpu, steps, warmup, budget_s=None):
         opt.step()
         return float(loss.detach())
 
+    return one
+
+
+def _cpu_reference_step_fn(c):
+    """One train step of the UNMODIFIED reference module (oracle/_ref, see oracle/make_ref.py) with train.py's recipe
+    (G/train.py:270-292): decoder forward, pack_padded_sequence, CrossEntropyLoss(ignore_index=<pad>), backward, clip_gradient(5),
+    Adam(lr 4e-4) - on the host cores, in train mode with the constructor's default dropouts, as the reference runs it."""
+    from torch import nn
+    from torch.nn.utils.rnn import pack_padded_sequence
+
+    from oracle import ref_loader
+
+    torch.manual_seed(0)
+    dec = ref_loader.build_decoder(c.variant, syn.make_word_map(c.V), c.D, c.ff, c.H, c.L).train()
+    params = [p for p in dec.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params=params, lr=4e-4)
+    crit = nn.CrossEntropyLoss(ignore_index=0)
+    batch = syn.make_batch(c, seed=0)
+
+    def one():
+        scores, caps_sorted, decode_lengths = dec(*args_of(c, batch))
+        targets = caps_sorted[:, 1:]
+        ps = pack_padded_sequence(scores, decode_lengths, batch_first=True).data
+        pt = pack_padded_sequence(targets, decode_lengths, batch_first=True).data
+        loss = crit(ps, pt)
+        opt.zero_grad()
+        loss.backward()
+        for group in opt.param_groups:  # ut.clip_gradient, G/utils.py:75-85
+            for prm in group["params"]:
+                if prm.grad is not None:
+                    prm.grad.data.clamp_(-5.0, 5.0)
+        opt.step()
+        return float(loss.detach())
+
+    return one
+
+
+def cpu_reference_kind():
+    from oracle import ref_loader
+
+    return "reference" if ref_loader.available() else "port"
+
+
+def cpu_reference_steps(cfg, B_cpu, steps, warmup, budget_s=None):
+    """Train steps of the reference's CPU path with all host threads: the unmodified reference modules when oracle/_ref is there
+    (kind "reference"), else the oracle port.  Returns (captions/s, steps run, cores, s/step, kind)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = cfg.with_batch(B_cpu)
+    kind = cpu_reference_kind()
+    one = _cpu_reference_step_fn(c) if kind == "reference" else _cpu_port_step_fn(c)
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
@@ -165,23 +213,70 @@ def cpu_reference_steps(cfg, B_cpu, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s and n >= 2:
             break
     dt = time.perf_counter() - t0
-    return B_cpu * n / dt, n, cores, dt / n
+    return B_cpu * n / dt, n, cores, dt / n, kind
+
+
+def cpu_reference_predict(cfg, n_captions, t_max, budget_s=10.0):
+    """Greedy caption generation on the host cores: the reference's own batch-1 predict() (G/models.py:363-443) when oracle/_ref is
+    there, else the oracle port.  Returns (captions/s, captions run, cores, kind)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = cfg.with_batch(max(1, n_captions))
+    pb = syn.make_batch(c, seed=100)
+    kind = cpu_reference_kind()
+    if kind == "reference":
+        from oracle import ref_loader
+
+        torch.manual_seed(0)
+        dec = ref_loader.build_decoder(c.variant, syn.make_word_map(c.V), c.D, c.ff, c.H, c.L).eval()
+
+        def one(i):
+            a = [pb["encoder_out"][i:i + 1], t_max, pb["entities"][i:i + 1]]
+            if c.has_facts:
+                a.append(pb["facts"][i:i + 1])
+            with torch.no_grad():
+                return dec.predict(*a)
+    else:
+        from oracle import decoder_oracle as orc
+
+        shapes = layout.param_shapes(c.variant, c.V, c.D, c.L, c.ff, c.ff)
+        p = syn.det_weights(shapes)
+        p["pos_encoder.pe"] = orc.positional_table(5000, c.D).unsqueeze(1)
+        spec = orc.Spec(c.variant, c.V, c.D, c.H, c.L, pad=0, start=c.V - 2, end=c.V - 1)
+
+        def one(i):
+            with torch.no_grad():
+                return orc.predict(spec, p, pb["encoder_out"][i:i + 1], t_max, pb["entities"][i:i + 1], pb["facts"][i:i + 1] if c.has_facts else None)
+    one(0)
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(n_captions):
+        one(i % c.B)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return n / (time.perf_counter() - t0), n, cores, kind
 
 
 def run_reference(a):
+    """Reference arm: the reference's OWN CPU implementation of the path (the unmodified model files of oracle/_ref driven by
+    train.py's recipe; the oracle port only if oracle/_ref is missing) on all host cores, same workload shape, a bounded sample
+    per step (4 captions) so that the whole run ends within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = syn.BASELINE_CONFIGS[a.workload]
-    B_cpu = 8
-    v, n, cores, spb = cpu_reference_steps(cfg, B_cpu, a.steps, a.warmup)
+    cfg = syn.BASELINE_CONFIGS["geo_b32" if a.workload == "geo_e2e_b256" else a.workload]
+    B_cpu = 4
+    v, n, cores, spb, kind = cpu_reference_steps(cfg, B_cpu, a.steps, a.warmup, budget_s=240.0)
+    what = ("the UNMODIFIED reference models.py (oracle/_ref, copied by oracle/make_ref.py) driven by train.py's step recipe" if kind == "reference"
+            else "oracle/decoder_oracle.py (CPU port of the reference: oracle/_ref is missing)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": n, "warmup": a.warmup,
         "ms_per_step": spb * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(cfg, "fp32 on CPU"), "sample": f"each step = {B_cpu} captions of the same shapes"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} steps x {B_cpu} captions, oracle/decoder_oracle.py (CPU port of the reference; the Python "
-                                   f"reference itself cannot travel to the GPU box), torch {torch.__version__}, {cores} threads"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n} steps x {B_cpu} captions, {what}, train mode (dropout 0.5/0.5/0.1), torch {torch.__version__}, "
+                                   f"{cores} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -602,9 +697,34 @@ def run_ours(a):
                 beam = {"error": f"{type(e).__name__}: {e}"}
             dec.train()
 
-    # ---- geo-aware end to end with the ResNet-101 trunk (BASELINE configs[4]), N = 1 only; `--workload geo_e2e_b256` runs it at any N ----
+    # ---- the other BASELINE.json train configs in short (configs[0]: geo-aware batch 32; configs[2]: news-knowledge-aware, global batch 64
+    # over 8 GPUs = 8 captions per GPU), same fused step, CUDA-graph replay, per-GPU batch as named - at every N ------------------------
+    configs = None
+    if a.workload == CFG_NAME and not a.no_config_extras:
+        configs = {}
+        for name in ("geo_b32", "news_b8"):
+            try:
+                c2 = syn.BASELINE_CONFIGS[name]
+                dec2 = build_decoder(c2, dev, dtype)
+                tr3 = Trainer(dec2, lr=4e-4, grad_clip=5.0, distributed=distributed, use_graph=tr.use_graph)
+                inp3 = tr3.prepare(*args_of(c2, host_batch(c2, seed=rank, pin=False)))
+                for _ in range(4):
+                    tr3.step(inp3)
+                nst = 30
+                ms3 = timed(lambda: tr3.step(inp3), nst)
+                la3 = tr3.loss_acc.clone()
+                configs[name] = {"value": c2.B * world * nst / (ms3 / 1e3), "unit": UNIT, "ms_per_step": ms3 / nst, "per_gpu_batch": c2.B,
+                                 "global_batch": c2.B * world, "workload": workload_desc(c2, a.dtype), "loss": float(la3[0] / la3[1].clamp_min(1))}
+                tr3._graph = None
+                tr3._graphs = {}
+                del tr3, inp3, dec2
+            except Exception as e:
+                configs[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+
+    # ---- geo-aware end to end with the ResNet-101 trunk (BASELINE configs[4]) in short, at every N ----------------------------------------
     enc_extra = None
-    if world == 1 and not a.no_encoder_extra and a.workload == CFG_NAME:
+    if not a.no_encoder_extra and a.workload == CFG_NAME:
         try:
             enc_extra = run_encoder_e2e(a, steps=10, warmup=3, quiet=True)
             for k in ("steps", "warmup", "higher_is_better", "scaling", "vs_baseline", "data", "clocks", "n_gpus"):
@@ -616,9 +736,20 @@ def run_ours(a):
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, n, cores, spb = cpu_reference_steps(cfg, 8, steps=50, warmup=1, budget_s=15.0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} train steps x 8 captions of the same shapes ({spb:.2f} s/step), oracle/decoder_oracle.py, fp32, train-mode dropout"}
+        v, n, cores, spb, kind = cpu_reference_steps(cfg, 8, steps=50, warmup=1, budget_s=15.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{n} train steps x 8 captions of the same shapes ({spb:.2f} s/step), "
+                         + ("unmodified reference models.py (oracle/_ref) + train.py's recipe" if kind == "reference" else "oracle/decoder_oracle.py")
+                         + ", fp32, train-mode dropout"}
+        if decode is not None and "error" not in decode:
+            try:
+                dv, dn, _, dkind = cpu_reference_predict(cfg, 6, decode["max_len"], budget_s=8.0)
+                decode["cpu_baseline"] = {"value": dv, "unit": "captions/s", "cores": cores, "kind": dkind,
+                                          "sample": f"{dn} captions, batch-1 greedy predict() of "
+                                                    + ("the unmodified reference (oracle/_ref)" if dkind == "reference" else "the oracle port")
+                                                    + f", max_len {decode['max_len']}, no KV cache (as the reference decodes)"}
+            except Exception as e:
+                decode["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -626,6 +757,8 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": workload_desc(cfg, a.dtype), "global_batch": cfg.B * world, "parallelism": f"dp{world}",
                        "cuda_graph": graph,
+                       "inputs": "`value`: one resident batch re-fed every step (throughput of the step itself); `e2e`: every step copies "
+                                 "its batch from pinned host memory and reads its loss back",
                        "l2": "no explicit flush: each step streams > 4 GB of activations/gradients, far beyond the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8},
@@ -636,6 +769,7 @@ def run_ours(a):
             "greedy_decode": decode,
             "beam5_decode": beam,
             "encoder_e2e": enc_extra,
+            "configs": configs,
             "trimmed_padding": trimmed,
             "kept_tokens": float(loss_acc[1]),
             "loss": float(loss_acc[0] / loss_acc[1].clamp_min(1)),
@@ -666,6 +800,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy-decode extra")
     ap.add_argument("--no-trim-extra", action="store_true", help="skip the dynamic-padding extra")
     ap.add_argument("--no-encoder-extra", action="store_true", help="skip the end-to-end-with-ResNet-101 extra (N = 1 only)")
+    ap.add_argument("--no-config-extras", action="store_true", help="skip the short geo_b32 / news_b8 train-step extras")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--graph", action="store_true", help="(default since the N = 2 and N = 8 runs of profiles/) capture the step, incl. the NCCL all-reduce")
     a = ap.parse_args()

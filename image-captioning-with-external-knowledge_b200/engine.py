@@ -238,7 +238,7 @@ class DecoderEngine:
             saves.append(sv)
         return saves
 
-    def _enc_dual_bwd(self, saves, dmem, B, E, F, P, M, gflat, p, seed):
+    def _enc_dual_bwd(self, saves, dmem, B, E, F, P, M, gflat, p, seed, done=lambda region: None):
         """dmem: gradient of the memory buffer.  Returns the gradient of the concatenated stack input (entity rows | pad | fact rows)."""
         K, DP, D, H, dh, L = self.K, self.DP, self.D, self.H, self.dh, self.L
         stacks, off, Re, Rc = self._dual_slices(B, E, F, P)
@@ -285,6 +285,7 @@ class DecoderEngine:
                 self._wg(wg, dq, sv.x[sl], qkv_l[i])
             K.gemm_dual(dqkv, qkv_l[0].WT, qkv_l[1].WT, dC, off, Re, accumulate=True)
             K.wgrad_group(wg, gflat)
+            done(f"enc{l}")
             d = dC
         return d
 
@@ -486,11 +487,48 @@ class DecoderEngine:
         return loss_acc, ds
 
     # ---- backward --------------------------------------------------------------------------------------------------------------------
-    def backward(self, ctx, dscores, gflat, need_encoder_grad: bool = False):
+    def grad_regions(self):
+        """Contiguous slices (lo, hi) of the flat gradient buffer in the order the backward pass COMPLETES them - what a data-parallel
+        trainer can all-reduce while the rest of the backward still runs (see backward(on_done=...)):
+          "heads"     fc_vocab .. fc_predicate (the tail of the buffer)          done after the score heads
+          "decoder"   the three decoder layers                                   done after the decoder stack
+          "word"      word_embedding                                             done after the caption embedder (G, K; N: at the end)
+          "enc{l}"    layer l of the entity / fact encoder stacks (two slices)   done after that lock-step layer
+          "rest"      the remaining embeddings (N: word_embedding too)           done at the end"""
+        off, n = self.plan.offsets, self.plan.n_params
+        names = list(self.plan.shapes.keys())
+
+        def span(pred):
+            ks = [k for k in names if pred(k)]
+            lo = min(off[k] for k in ks)
+            hi = max(off[k] + int(math.prod(self.plan.shapes[k])) for k in ks)
+            return (lo, hi)
+
+        reg = {"heads": [span(lambda k: k.startswith("fc_"))], "decoder": [span(lambda k: k.startswith("transformer_decoder."))]}
+        word = span(lambda k: k == "word_embedding.weight")
+        rest = span(lambda k: k in ("entity_encoder.type_embedding.weight", "predicate_embedding.weight"))
+        if self.variant == "N":
+            rest = (min(word[0], rest[0]), max(word[1], rest[1]))
+        else:
+            reg["word"] = [word]
+        reg["rest"] = [rest]
+        for l in range(self.L):
+            sl = [span(lambda k, l=l: k.startswith(f"transformer_encoder_entities.layers.{l}."))]
+            if self.has_facts:
+                sl.append(span(lambda k, l=l: k.startswith(f"transformer_encoder_facts.layers.{l}.")))
+            reg[f"enc{l}"] = sl
+        covered = sorted(s for v in reg.values() for s in v)
+        assert covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:])), covered
+        return reg
+
+    def backward(self, ctx, dscores, gflat, need_encoder_grad: bool = False, on_done=None):
         """
         dscores: (B*T, ld>=W) in the activation dtype (pad columns ignored).  Accumulates every parameter gradient into
         gflat (flat fp32, reference parameter order) and returns d encoder_out (B,D,P) fp32 or None.
+        on_done(region): called on the launching thread as soon as every kernel that writes the gradient region (grad_regions())
+        has been LAUNCHED - the hook where a data-parallel trainer starts that region's all-reduce on a side stream.
         """
+        done = on_done if on_done is not None else (lambda region: None)
         K, D, DP, L, V = self.K, self.D, self.DP, self.L, self.V
         B, T, E, F, P, M = ctx.B, ctx.T, ctx.E, ctx.F, ctx.P, ctx.M
         inp, seed = ctx.inp, ctx.seed
@@ -516,16 +554,20 @@ class DecoderEngine:
         if self.has_facts:
             K.pointer_bwd(dscores, ctx.h, ctx.fact_enc, self.param("fc_fact.weight"), ctx.first_t, dFact, dh, gflat,
                           self.off("fc_fact.weight"), self.off("fc_fact.bias"), B, T, F, D, V + E, 0)
+        done("heads")
         # decoder layers
         kv_l = self.lin["transformer_decoder.kv_all"]
         dkv = self._new(B * M, kv_l.lin.Np)
         dx = dh
         for l in reversed(range(L)):
             dx = self._dec_layer_bwd(l, ctx.dec_saves[l], dx, dkv, B, T, M, gflat, ctx.p_dec, seed)
+        # memory K/V projections (all layers at once): parameters of the decoder layers (multihead_attn.in_proj rows 300..899)
+        K.wgrad(dkv, ctx.mem, gflat, kv_l.rowoff, kv_l.colmap, kv_l.biasoff)
+        done("decoder")
         K.caption_embed_bwd(dx, inp.captions, inp.caption_masks, dEnt, dFact, gflat, self.off("word_embedding.weight"), B, T, V, E, F, D,
                             self.pad, math.sqrt(D), drop=self._drop(ctx.p_pos, seed, "pos"))
-        # memory K/V projections (all layers at once)
-        K.wgrad(dkv, ctx.mem, gflat, kv_l.rowoff, kv_l.colmap, kv_l.biasoff)
+        if self.variant != "N":
+            done("word")  # (N: the entity encoder adds name-word gradients at the very end)
         dmem = self._new(B * M, DP)
         K.gemm(dkv, kv_l.WT, dmem)
         d_enc = None
@@ -535,7 +577,7 @@ class DecoderEngine:
         # context encoders; the fact encodings' input gradient also flows into the entity encodings (FactEncoder gathers them)
         if self.has_facts:
             Re, Rf, off, Rc = self._dual_geometry(B, E, F)
-            dcat = self._enc_dual_bwd(ctx.enc_saves["dual"], dmem, B, E, F, P, M, gflat, ctx.p_enc, seed)
+            dcat = self._enc_dual_bwd(ctx.enc_saves["dual"], dmem, B, E, F, P, M, gflat, ctx.p_enc, seed, done)
             K.accum_f32(dcat[off : off + Rf], dFact)
             K.fact_encode_bwd(dFact, inp.facts, dEnt, gflat, self.off("predicate_embedding.weight"), B, E, F, D, self.NP)
             d = dcat[:Re]
@@ -546,11 +588,13 @@ class DecoderEngine:
                 d = self._enc_layer_bwd("transformer_encoder_entities", l, ctx.enc_saves["transformer_encoder_entities"][l], d, rowmap, B,
                                         E, gflat, ctx.p_enc, seed)
                 rowmap = (0, 0, 0)
+                done(f"enc{l}")
         K.accum_f32(d, dEnt)
         K.entity_encode_bwd(dEnt, inp.entities, inp.facts, self.param("entity_encoder.type_embedding.weight"),
                             self.wemb if self.variant == "N" else None, gflat, self.off("entity_encoder.type_embedding.weight"),
                             self.off("word_embedding.weight"), 0 if self.dtype == torch.float32 else 1, VARIANT_CODE[self.variant], B, E, F,
                             D, self.plan.shapes["entity_encoder.type_embedding.weight"][0], self.V)
+        done("rest")
         return d_enc
 
     def _memory_kv(self, mem, rows):

@@ -59,6 +59,8 @@ class Trainer:
         self.lr_dev = torch.full((1,), lr, dtype=torch.float32, device=dev)
         self._lr = lr
         self._skip_collective = False  # set around the capture warm-up step (see _capture)
+        self._regions = None           # engine.grad_regions(), built on first use
+        self._comm_stream = None       # side stream of the overlapped gradient all-reduce
         self.use_graph = use_graph
         self._graph = None
         self._static = None
@@ -145,21 +147,52 @@ class Trainer:
         self.step_dev.add_(1)
         self.gbuf.zero_()
         K.set_seed_source(self.step_dev)  # effective dropout seed = seed_base + step (read on the device)
+        reduce = self.distributed and not self._skip_collective
         try:
             scores, ctx = eng.forward(inp, train=self.decoder.training, seed=self.seed_base)
             _, ds = eng.loss(scores, inp.captions, inp.decode_len, loss_acc=self.loss_acc)
-            eng.backward(ctx, ds, self.g, need_encoder_grad=False)
+            eng.backward(ctx, ds, self.g, need_encoder_grad=False, on_done=self._reduce_region if reduce else None)
         finally:
             K.set_seed_source(None)
+        if reduce:
+            self._reduce_join()
         for k in self._frozen():
             eng.param(k, self.g).zero_()
-        if self.distributed and not self._skip_collective:
-            import torch.distributed as dist
-
-            dist.all_reduce(self.gbuf, group=self.pg)
         b1, b2 = self.betas
         K.adam_step(eng.P, self.g, self.m, self.v, self._lr, b1, b2, self.eps, 1.0, 1.0, self.clip, self.loss_acc[1:], 1.0, eng.dstA,
                     eng.dstB, eng.dstC, eng.packT, eng.packF, update=True, step_dev=self.step_dev, lr_dev=self.lr_dev)
+
+    # ---- gradient all-reduce overlapped with the backward pass ------------------------------------------------------------------------
+    # The flat buffer is reduced region by region, in the order the backward completes them (engine.grad_regions): the score heads'
+    # weights (+ the loss sum / token count behind them) while the decoder stack is still being differentiated, the decoder layers
+    # and the word embedding under the encoder stacks, each encoder layer under the next one; only the last encoder layer and the
+    # small embeddings are exposed.  On CUDA the collectives run on a side stream forked / joined with events (inside a captured
+    # step they become a parallel branch of the graph); sums are independent per element, so the result equals one big all-reduce.
+    def _reduce_region(self, region: str) -> None:
+        import torch.distributed as dist
+
+        if self._regions is None:
+            self._regions = self.eng.grad_regions()
+        slices = list(self._regions[region])
+        if region == "heads":  # the tail of the buffer carries [loss_sum, kept_tokens] right behind the last parameter
+            slices[-1] = (slices[-1][0], self.n + 2)
+        if self.gbuf.device.type != "cuda":
+            for lo, hi in slices:
+                dist.all_reduce(self.gbuf[lo:hi], group=self.pg)
+            return
+        main = torch.cuda.current_stream(self.gbuf.device)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.gbuf.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            for lo, hi in slices:
+                dist.all_reduce(self.gbuf[lo:hi], group=self.pg)
+
+    def _reduce_join(self) -> None:
+        if self.gbuf.device.type == "cuda" and self._comm_stream is not None:
+            torch.cuda.current_stream(self.gbuf.device).wait_stream(self._comm_stream)
 
     def step(self, inp) -> torch.Tensor:
         """One optimisation step on a prepared batch.  Returns a device tensor [loss_sum, kept_tokens] (global under DDP)."""

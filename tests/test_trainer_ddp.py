@@ -18,10 +18,10 @@ from ickb200.trainer import Trainer
 from oracle import decoder_oracle as orc
 
 
-def _trainer_step(cfg, batch, steps=2, distributed=False, pg=None):
+def _trainer_step(cfg, batch, steps=2, distributed=False, pg=None, overlap=False):
     M.DecoderTransformer._test_kernel_factory = HostKernels
     dec = build_module(cfg, "cpu", dropouts=(0.0, 0.0, 0.0)).train()
-    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, process_group=pg)
+    tr = Trainer(dec, lr=4e-4, grad_clip=5.0, distributed=distributed, process_group=pg, overlap_allreduce=overlap)
     accs = []
     for _ in range(steps):
         accs.append(tr.train_step(*batch_args(cfg, batch)).clone())
@@ -76,8 +76,11 @@ def _worker(rank, world, port, cfg, q):
     n = cfg.B // world
     shard = {k: v[rank * n : (rank + 1) * n] for k, v in full.items()}
     dec, accs, _ = _trainer_step(cfg.with_batch(n), shard, steps=2, distributed=True)
+    dec_o, accs_o, _ = _trainer_step(cfg.with_batch(n), shard, steps=2, distributed=True, overlap=True)  # region-wise all-reduce
+    same = all(torch.equal(a, b) for a, b in zip(accs, accs_o)) and all(
+        torch.allclose(p1.detach(), p2.detach(), atol=1e-7) for (_, p1), (_, p2) in zip(dec.named_parameters(), dec_o.named_parameters()))
     if rank == 0:
-        q.put(({k: v.detach().numpy().copy() for k, v in dec.named_parameters()}, [a.tolist() for a in accs]))
+        q.put(({k: v.detach().numpy().copy() for k, v in dec.named_parameters()}, [a.tolist() for a in accs], same))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -92,7 +95,8 @@ def test_two_rank_gloo_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, q)) for r in range(2)]
     for p in procs:
         p.start()
-    params2, accs2 = q.get(timeout=600)
+    params2, accs2, overlap_same = q.get(timeout=600)
+    assert overlap_same  # the region-wise (overlapped) all-reduce gives the update of the single collective
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0

@@ -14,6 +14,10 @@ int ick_mha_bwd_mma(const void* Q, const void* K, const void* V, const void* O, 
 int ick_mha_bwd_fused(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
                       void* dK, void* dV, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk,
                       int lddv, int causal, DropCfg dc, cudaStream_t stream);
+// attention_fwd_tc.cu: the forward on tcgen05 / TMEM (S = Q K^T and O += P V as UMMA tiles, softmax warps on tcgen05.ld, lazily
+// rescaled accumulator).  ICK_ERR_UNSUPPORTED (nothing launched) when an item's Q, K, V do not fit two shared-memory stages.
+int ick_mha_fwd_tc(const void* Q, const void* K, const void* V, void* O, float* lse, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv,
+                   int ldo, int causal, DropCfg dc, cudaStream_t stream);
 // attention_bwd_tc.cu: the backward entirely on tcgen05 / TMEM (S^T, dP^T, dV, dK, dQ as UMMA tiles, softmax warps on tcgen05.ld).
 // ICK_ERR_UNSUPPORTED (nothing launched) for more than 512 queries or when the operand rings do not fit.
 int ick_mha_bwd_tc(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ, void* dK,

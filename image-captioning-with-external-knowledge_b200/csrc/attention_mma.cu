@@ -809,6 +809,14 @@ int bwd_mode() {
     return v;
 }
 bool use_fused() { return bwd_mode() >= 1; }
+bool fwd_tc() {  // ICK_ATTN_FWD=mma: the mma.sync forward kernels of this file instead of attention_fwd_tc.cu
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_ATTN_FWD");
+        v = (e && e[0] == 'm') ? 0 : 1;
+    }
+    return v != 0;
+}
 bool use_persistent() {
     static int v = -1;
     if (v < 0) {
@@ -838,6 +846,10 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
                     int ldv, int ldo, int causal, DropCfg dc, cudaStream_t stream) {
     ICK_REQUIRE(((uintptr_t)K & 15) == 0 && ((uintptr_t)V & 15) == 0 && ((uintptr_t)Q & 3) == 0, "mha_fwd: operands must be 16-byte aligned");
     int rc;
+    if (fwd_tc()) {
+        rc = ick_mha_fwd_tc(Q, K, V, O, lse, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, causal, dc, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     Dims d = make_dims(B, H, Sq, Sk, dh, causal);
     CUtensorMap tmK, tmV;
     if ((rc = make_tmap3(&tmK, K, H, Sk, B, ldk))) return rc;

@@ -242,6 +242,35 @@ def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
         assert err(a, b) < TOL[dtype] * 2, name
 
 
+@pytest.mark.parametrize("qscale", [4.0, 10.0])
+@pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", [(3, 10, 301, 301, 30, False), (4, 10, 102, 548, 30, False), (5, 4, 130, 130, 30, True)])
+def test_mha_fwd_sharp_scores_rescaled_accumulator(K, Hk, qscale, B, H, Sq, Sk, dh, causal):
+    """Large score magnitudes: row maxima that grow by more than 2^8 from one key tile to the next force the tcgen05 forward to
+    rescale its TMEM accumulator (the lazy running maximum), and tiles far below the row maximum underflow to exact zeros."""
+    dtype = torch.bfloat16
+    q = (headify(rnd((B * Sq, H * 32), torch.float32, 1), H, dh) * qscale).to(dtype)
+    k = headify(rnd((B * Sk, H * 32), torch.float32, 2), H, dh).to(dtype)
+    v = headify(rnd((B * Sk, H * 32), torch.float32, 3), H, dh).to(dtype)
+    drop = (0.5, 11, 3)
+    Or, lr = torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * H * Sq)
+    Hk.mha_fwd(q, k, v, Or, lr, B, H, Sq, Sk, dh, causal, drop)
+    Og, lg = torch.full((B * Sq, H * 32), float("nan"), dtype=dtype).cuda(), torch.zeros(B * H * Sq).cuda()
+    K.mha_fwd(cu(q), cu(k), cu(v), Og, lg, B, H, Sq, Sk, dh, causal, drop)
+    assert not torch.isnan(Og).any()
+    assert err(Og, Or) < TOL[dtype]
+    assert float((lg.cpu() - lr).abs().max()) < 5e-2
+    # and the backward on top of it (the probabilities are recomputed from the saved LSE)
+    dO = headify(rnd((B * Sq, H * 32), torch.float32, 4), H, dh).to(dtype)
+    outs_r = [torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype), torch.zeros(B * Sk, H * 32, dtype=dtype)]
+    outs_g = [torch.full_like(o, float("nan")).cuda() for o in outs_r]
+    dsr, dsg = torch.zeros(B * H * Sq), torch.zeros(B * H * Sq).cuda()
+    Hk.mha_bwd(q, k, v, Or, dO, lr, dsr, *outs_r, B, H, Sq, Sk, dh, causal, drop)
+    K.mha_bwd(cu(q), cu(k), cu(v), cu(Or), cu(dO), cu(lr), dsg, *outs_g, B, H, Sq, Sk, dh, causal, drop)
+    for a, b, name in zip(outs_g, outs_r, ["dQ", "dK", "dV"]):
+        assert not torch.isnan(a).any(), name
+        assert err(a, b) < TOL[dtype] * 2, name
+
+
 @pytest.mark.parametrize("p", [0.0, 0.3, 0.5])
 @pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", [(100, 10, 70, 70, 30, True), (30, 10, 37, 548, 30, False), (16, 10, 301, 301, 30, False),
                                                  (20, 10, 52, 598, 30, False), (9, 3, 200, 40, 32, False), (160, 10, 51, 51, 30, False)])

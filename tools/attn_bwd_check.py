@@ -25,9 +25,17 @@ def heads(rows):
 
 
 q, k, v, do = heads(B * Sq), heads(B * Sk), heads(B * Sk), heads(B * Sq)
+if len(sys.argv) > 7:  # sharper score distributions (exercises the lazily rescaled accumulator of the tcgen05 forward)
+    q = (q.float() * float(sys.argv[7])).to(bf)
 drop = (p, 7, 9) if p > 0 else None
 o, lse = torch.zeros(B * Sq, H * 32, dtype=bf), torch.zeros(B * H * Sq)
 Hk.mha_fwd(q, k, v, o, lse, B, H, Sq, Sk, dh, causal, drop)
+og, lg = torch.full((B * Sq, H * 32), float("nan"), dtype=bf).cuda(), torch.zeros(B * H * Sq).cuda()
+K.mha_fwd(q.cuda(), k.cuda(), v.cuda(), og, lg, B, H, Sq, Sk, dh, causal, drop)
+torch.cuda.synchronize()
+of = og.float().cpu()
+print("O  nan", int(torch.isnan(of).sum()), "max err", round(float((of - o.float()).abs().max() / o.float().abs().max()), 5), "fro err",
+      round(float((of - o.float()).norm() / o.float().norm()), 5), "| lse max abs err", round(float((lg.cpu() - lse).abs().max()), 5))
 ref = [torch.zeros(B * Sq, H * 32, dtype=bf), torch.zeros(B * Sk, H * 32, dtype=bf), torch.zeros(B * Sk, H * 32, dtype=bf)]
 ds = torch.zeros(B * H * Sq)
 Hk.mha_bwd(q, k, v, o, do, lse, ds, *ref, B, H, Sq, Sk, dh, causal, drop)

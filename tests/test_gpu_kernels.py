@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 DTYPES = [torch.float32, torch.bfloat16]
+BIG_SEED = 1234003703  # a 31-bit seed as Trainer / the module derive them (initial_seed * 1000003 + step): the toy seeds hide wrap-around bugs
 
 
 DRYRUN = os.environ.get("ICK_DRYRUN") == "1"  # debugging aid for the test code itself on a GPU-less box
@@ -90,7 +91,7 @@ def test_gemm_epilogues(K, Hk, tc, dtype):
         pytest.skip("tensor-core path is bf16")
     M, N, K_ = 333, 512, 320
     A, W, bias = rnd((M, K_), dtype, 1), rnd((N, K_), dtype, 2, 0.1), rnd((N,), torch.float32, 3)
-    drop = (0.3, 1234, 77)
+    drop = (0.3, BIG_SEED, 77)
     # relu + dropout
     Cr, Cg = torch.zeros(M, N, dtype=dtype), torch.zeros(M, N, dtype=dtype).cuda()
     Hk.gemm(A, W, Cr, bias=bias, epi=1, drop=drop)
@@ -222,7 +223,7 @@ def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
     Qbuf = torch.zeros(B * Sq, ld, dtype=dtype)
     Qbuf[:, : H * 32] = qkv_q
     Q = Qbuf[:, : H * 32]
-    drop = (p, 99, 5) if p > 0 else None
+    drop = (p, BIG_SEED + 99, 5) if p > 0 else None
     Or, lr = torch.zeros(B * Sq, H * 32, dtype=dtype), torch.zeros(B * H * Sq)
     Og, lg = torch.zeros(B * Sq, H * 32, dtype=dtype).cuda(), torch.zeros(B * H * Sq).cuda()
     Hk.mha_fwd(Q, qkv_k, qkv_v, Or, lr, B, H, Sq, Sk, dh, causal, drop)
@@ -324,7 +325,7 @@ def test_add_ln_fwd_bwd(K, Hk, dtype, p, rows, rowmap, yrows):
     d, ld = 300, 320
     x, sub = rnd((rows, ld), dtype, 1), rnd((rows, ld), dtype, 2)
     gamma, beta = 1 + 0.1 * rnd((d,), torch.float32, 3), rnd((d,), torch.float32, 4)
-    drop = (p, 7, 3) if p > 0 else None
+    drop = (p, BIG_SEED, 3) if p > 0 else None
     yr, yg = torch.zeros(yrows, ld, dtype=dtype), torch.full((yrows, ld), 7.0, dtype=dtype).cuda()
     sr, sg = sub.clone(), sub.clone().cuda()
     mr, rr, mg, rg = torch.zeros(rows), torch.zeros(rows), torch.zeros(rows).cuda(), torch.zeros(rows).cuda()
@@ -460,13 +461,13 @@ def test_entity_fact_caption_kernels(K, Hk, dtype, variant):
     caps[1, 2], masks[1, 2] = V + 2, 0           # pointer id with mask 0 -> <pad> word row
     pe = rnd((T + 3, D), torch.float32, 6)
     for (t0, Tn), p in (((0, T), 0.0), ((0, T), 0.2), ((5, 1), 0.0)):
-        drop = (p, 3, 9) if p > 0 else None
+        drop = (p, BIG_SEED + 3, 9) if p > 0 else None
         xr, xg = torch.zeros(B * Tn, ld, dtype=dtype), torch.full((B * Tn, ld), float("nan"), dtype=dtype).cuda()
         Hk.caption_embed_fwd(caps, masks, wemb, outr, fact_r, pe, xr, B, T, t0, Tn, V, E, F, D, 0, math.sqrt(D), drop)
         K.caption_embed_fwd(cu(caps), cu(masks), cu(wemb), cu(outr), cu(fact_r), cu(pe), xg, B, T, t0, Tn, V, E, F, D, 0, math.sqrt(D), drop)
         assert err(xg, xr) < TOL[dtype]
     dX = rnd((B * T, ld), dtype, 7)
-    drop = (0.2, 3, 9)
+    drop = (0.2, BIG_SEED + 3, 9)
     dEr, dEg = torch.zeros(B * E, ld), torch.zeros(B * E, ld).cuda()
     dFr = torch.zeros(B * F, ld) if F else None
     dFg = cu(dFr.clone()) if F else None

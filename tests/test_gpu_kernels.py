@@ -211,10 +211,24 @@ ATT_CASES = [(2, 10, 301, 301, 30, False), (3, 10, 102, 102, 30, True), (2, 10, 
              (1, 2, 70, 700, 30, False), (1, 2, 700, 700, 30, True)]
 
 
+# bf16 attention implementations behind ick_mha_fwd / ick_mha_bwd (csrc/attention_mma.cu dispatch): the defaults (mma.sync forward,
+# tcgen05 backward) and the alternatives kept as switches
+ATT_MODES = [("mma", "tc"), ("tc", "tc"), ("mma", "hybrid"), ("mma", "split")]
+
+
+@pytest.fixture(params=ATT_MODES, ids=lambda m: f"fwd-{m[0]}_bwd-{m[1]}")
+def att_mode(request, monkeypatch):
+    monkeypatch.setenv("ICK_ATTN_FWD", request.param[0])
+    monkeypatch.setenv("ICK_ATTN_BWD", request.param[1])
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("p", [0.0, 0.5])
 @pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", ATT_CASES)
-def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
+def test_mha_fwd_bwd(K, Hk, att_mode, dtype, p, B, H, Sq, Sk, dh, causal):
+    if dtype == torch.float32 and att_mode != ATT_MODES[0]:
+        pytest.skip("the fp32 CUDA-core kernels have one implementation")
     ld = 3 * H * 32 + 8
     qkv_q = headify(rnd((B * Sq, H * 32), torch.float32, 1), H, dh).to(dtype)
     qkv_k = headify(rnd((B * Sk, H * 32), torch.float32, 2), H, dh).to(dtype)
@@ -245,7 +259,7 @@ def test_mha_fwd_bwd(K, Hk, dtype, p, B, H, Sq, Sk, dh, causal):
 
 @pytest.mark.parametrize("qscale", [4.0, 10.0])
 @pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", [(3, 10, 301, 301, 30, False), (4, 10, 102, 548, 30, False), (5, 4, 130, 130, 30, True)])
-def test_mha_fwd_sharp_scores_rescaled_accumulator(K, Hk, qscale, B, H, Sq, Sk, dh, causal):
+def test_mha_fwd_sharp_scores_rescaled_accumulator(K, Hk, att_mode, qscale, B, H, Sq, Sk, dh, causal):
     """Large score magnitudes: row maxima that grow by more than 2^8 from one key tile to the next force the tcgen05 forward to
     rescale its TMEM accumulator (the lazy running maximum), and tiles far below the row maximum underflow to exact zeros."""
     dtype = torch.bfloat16
@@ -275,7 +289,9 @@ def test_mha_fwd_sharp_scores_rescaled_accumulator(K, Hk, qscale, B, H, Sq, Sk, 
 @pytest.mark.parametrize("p", [0.0, 0.3, 0.5])
 @pytest.mark.parametrize("B,H,Sq,Sk,dh,causal", [(100, 10, 70, 70, 30, True), (30, 10, 37, 548, 30, False), (16, 10, 301, 301, 30, False),
                                                  (20, 10, 52, 598, 30, False), (9, 3, 200, 40, 32, False), (160, 10, 51, 51, 30, False)])
-def test_mha_bwd_fused_many_items(K, Hk, p, B, H, Sq, Sk, dh, causal):
+def test_mha_bwd_fused_many_items(K, Hk, att_mode, p, B, H, Sq, Sk, dh, causal):
+    if att_mode[1] == "split" or (p == 0.3 and att_mode != ATT_MODES[1]):
+        pytest.skip("many-item slot re-use concerns the persistent fused kernels; the 14-plane keep words are checked once")
     """The fused bf16 backward (attention_bwd_fused.cu) with several (image, head) items per CTA: operand stages, ring slots and the
     TMEM dQ slots are re-used (1000 items on 148 CTAs: 6-7 tenants per slot), p = 0.3 needs 14 bit planes per keep word."""
     dtype = torch.bfloat16

@@ -40,8 +40,9 @@ if "--all" in sys.argv:
 # A call of ick_mha_bwd is one dK/dV launch plus either a recomputing dQ launch or rowdot + dQ-from-dS; a call of
 # ick_wgrad_group_tc one grouped wgrad + one reduce, ...  (counting kernel, kernels of the family, entry points that share them)
 FAMILY = {
-    "ick_mha_bwd": ("bwd_dkv_pkernel", ["bwd_dq_pkernel", "bwd_dkv_pkernel", "bwd_dq_ds_kernel", "rowdot_kernel", "bwd_dq_kernel", "bwd_dkv_kernel"], []),
-    "ick_mha_fwd": ("fwd_pkernel", ["fwd_pkernel", "fwd_kernel"], []),
+    "ick_mha_bwd": ("bwd_tc_kernel", ["bwd_tc_kernel", "tb_rowdot_kernel", "bwd_fused_kernel", "fb_rowdot_kernel", "bwd_dq_pkernel", "bwd_dkv_pkernel",
+                                       "bwd_dq_ds_kernel", "rowdot_kernel", "bwd_dq_kernel", "bwd_dkv_kernel"], []),
+    "ick_mha_fwd": ("fwd_pkernel", ["fwd_pkernel", "fwd_kernel", "fwd_tc_kernel"], []),
     "ick_gemm_tn_tc": ("gemm_tn_tc_kernel", ["gemm_tn_tc_kernel"], ["ick_gemm_tn_tc_dual"]),
     "ick_wgrad_group_tc": ("wgrad_group_tc_kernel", ["wgrad_group_tc_kernel", "wgrad_group_reduce_kernel"], []),
     "ick_wgrad_tc": ("wgrad_tc_kernel", ["wgrad_tc_kernel", "wgrad_reduce_kernel", "bias_grad_kernel"], []),

@@ -104,14 +104,9 @@ def test_bf16_logits_and_loss_vs_reference_golden(variant):
             assert cos > 0.995, (k, cos)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("variant", ["G", "K", "N"])
-def test_train_mode_dropout_at_baseline_shapes_vs_oracle_with_same_masks(variant, dtype):
-    """Train mode at full size: the oracle is given the kernels' own dropout masks (hash of seed, site, element), so the
-    forward and every gradient are compared exactly, not statistically."""
-    cfg = syn.BASE_PARITY_CONFIGS[variant].with_batch(4)
-    ps = dict(dec=0.5, enc=0.5, pos=0.1)  # the reference's defaults (G/models.py:219)
-    torch.manual_seed(1234)  # the dropout seed derives from torch.initial_seed(): pin the mask draw whatever ran before
+def _train_mode_grads(cfg, dtype, ps, torch_seed):
+    """One train-mode forward + backward of the CUDA module and of the oracle fed the kernels' own dropout masks."""
+    torch.manual_seed(torch_seed)  # the dropout seed derives from torch.initial_seed(): pin the mask draw whatever ran before
     dec = build_module(cfg, "cuda", dtype, dropouts=(ps["dec"], ps["enc"], ps["pos"]), profile="reference").train()
     batch_cpu = syn.make_batch(cfg, seed=23)
     scores, caps, dl = dec(*batch_args(cfg, to_dev(batch_cpu)))
@@ -122,25 +117,56 @@ def test_train_mode_dropout_at_baseline_shapes_vs_oracle_with_same_masks(variant
     assert nmax_err(scores.detach().cpu(), ref_scores.detach()) < tol
     orc.caption_loss(scores, caps, dl).backward()
     orc.caption_loss(ref_scores, caps.cpu(), dl).backward()
+    out = []
     for k, prm in dec.named_parameters():
         ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
         got = (prm.grad if prm.grad is not None else torch.zeros_like(prm)).float().cpu()
-        if dtype == torch.float32:
-            # 2e-3 of the gradient's magnitude, element by element - except for a ReLU unit whose pre-activation is within fp32
-            # rounding of zero: kernel and oracle may then disagree on ReLU'(0) for that one unit (about 0.6 million FFN
-            # pre-activations per pass, so roughly every other mask draw has one), which changes ONE row of linear1.weight / one
-            # element of linear1.bias (and, through the input gradient, little else).  Up to 0.25 % outlying elements are let pass.
-            bad = (got - ref).abs() > 2e-3 * max(float(ref.abs().max()), 1e-6) + 1e-7
-            assert int(bad.sum()) <= max(1, int(0.0025 * bad.numel())), (k, int(bad.sum()), float((got - ref).abs().max()))
-        else:
-            # bf16 activations under p = 0.5 dropout (kept values doubled) through three layers: single parameters land 2-6 % off
-            # in norm depending on the mask draw (measured on B200); the direction is the sharper test
-            rn = float(ref.double().norm())
-            if rn > 1e-7:
-                assert abs(float(got.double().norm()) - rn) <= 8e-2 * rn, k
-                if ref.numel() >= 300:
-                    cos = float((got.double() * ref.double()).sum() / (got.double().norm() * ref.double().norm()))
-                    assert cos > 0.99, (k, cos)
+        out.append((k, got, ref))
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", ["G", "K", "N"])
+def test_train_mode_dropout_at_baseline_shapes_vs_oracle_with_same_masks(variant, dtype):
+    """Train mode at full size: the oracle is given the kernels' own dropout masks (hash of seed, site, element), so the
+    forward and every gradient are compared exactly, not statistically."""
+    cfg = syn.BASE_PARITY_CONFIGS[variant].with_batch(4)
+    ps = dict(dec=0.5, enc=0.5, pos=0.1)  # the reference's defaults (G/models.py:219)
+    if dtype == torch.float32:
+        # EVERY element of EVERY gradient within 2e-3 of the gradient's magnitude.  One effect is not a kernel error and is
+        # handled explicitly: a ReLU unit whose pre-activation is within fp32 rounding of zero (0.2-0.6 million FFN pre-activations
+        # per layer and pass, kept values doubled by the p = 0.5 dropout in front) may get ReLU'(0) = 0 from one side and 1 from
+        # the other.  That toggles ONE (token, unit) term: a whole row of that layer's linear1.weight moves by a few per cent and
+        # everything upstream of the token by ~0.4 % in l2 (tools/grad_err.py, gpurun_out/r02d: mask draw 1234 of K has exactly one
+        # such unit in decoder layer 2; draw 7 agrees to 1e-6 everywhere).  So: up to three mask draws, at least one must be
+        # clean in the strict sense, and a draw that is not clean must look like a flip (every parameter within 1 % in l2).
+        clean = False
+        report = []
+        for torch_seed in (1234, 7, 99):
+            worst = None
+            for k, got, ref in _train_mode_grads(cfg, dtype, ps, torch_seed):
+                lim = 2e-3 * max(float(ref.abs().max()), 1e-6) + 1e-7
+                nbad = int(((got - ref).abs() > lim).sum())
+                if nbad:
+                    rel = float((got - ref).double().norm() / max(float(ref.double().norm()), 1e-12))
+                    assert rel < 1e-2, (torch_seed, k, nbad, rel)  # larger than one ReLU'(0) flip can explain
+                    if worst is None or rel > worst[2]:
+                        worst = (k, nbad, rel)
+            report.append((torch_seed, worst))
+            if worst is None:
+                clean = True
+                break
+        assert clean, report
+        return
+    for k, got, ref in _train_mode_grads(cfg, dtype, ps, 1234):
+        # bf16 activations under p = 0.5 dropout (kept values doubled) through three layers: single parameters land 2-6 % off
+        # in norm depending on the mask draw (measured on B200); the direction is the sharper test
+        rn = float(ref.double().norm())
+        if rn > 1e-7:
+            assert abs(float(got.double().norm()) - rn) <= 8e-2 * rn, k
+            if ref.numel() >= 300:
+                cos = float((got.double() * ref.double()).sum() / (got.double().norm() * ref.double().norm()))
+                assert cos > 0.99, (k, cos)
 
 
 def _oracle_recipe(cfg, batch, steps, profile, lr=4e-4):

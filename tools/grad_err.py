@@ -26,3 +26,11 @@ for sd in (1234, 7):
         errs.append((float((got-ref).abs().max())/max(float(ref.abs().max()),1e-9), k))
     errs.sort(reverse=True)
     print("   worst:", [(round(e,5),k) for e,k in errs[:4]])
+    # where do the out-of-tolerance elements of the worst parameters sit?
+    for e, k in errs[:3]:
+        prm = dict(dec.named_parameters())[k]
+        ref = p[k].grad; got = prm.grad.float().cpu()
+        d = (got - ref).abs(); tol = 2e-3 * float(ref.abs().max()) + 1e-7
+        bad = d > tol
+        print("   ", k, tuple(ref.shape), "bad", int(bad.sum()), "of", bad.numel(), "max", float(d.max()), "tol", tol,
+              "rel-l2", float((got - ref).norm() / ref.norm()))

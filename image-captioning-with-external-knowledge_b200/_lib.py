@@ -71,11 +71,16 @@ class Library:
         m = re.search(r"#define\s+ICK_ABI_VERSION\s+(\d+)", open(HEADER).read())
         if m and int(m.group(1)) != ver:
             raise ImportError(f"ickb200: ABI version mismatch: header {m.group(1)} vs library {ver}; rebuild")
-        self.launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+    @property
+    def launches(self) -> int:
+        """Kernels the library has launched in this process (counted at every cudaLaunchKernelEx of csrc/, bench.py's gpu_launches)."""
+        n = ctypes.c_longlong(0)
+        self.fn["ick_launch_count"](ctypes.addressof(n))
+        return int(n.value)
 
     def call(self, name: str, *args) -> None:
         rc = self.fn[name](*args)
-        self.launches += 1
         if rc != 0:
             raise RuntimeError(f"{name} failed (rc={rc}): {self.fn['ick_last_error']().decode()}")
 

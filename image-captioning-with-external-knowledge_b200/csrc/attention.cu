@@ -613,7 +613,8 @@ extern "C" int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O,
 extern "C" int ick_mha_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse,
                            float* dsum, void* dQ, void* dK, void* dV, int dt, int B, int H, int Sq, int Sk, int dh, int ldq,
                            int ldk, int ldv, int ldo, int lddo, int lddq, int lddk, int lddv, int causal, float drop_p,
-                           unsigned seed, unsigned site, void* workspace, long long workspace_bytes, cudaStream_t stream) {
+                           unsigned seed, unsigned site, void* workspace, long long workspace_bytes, int dsum_ready,
+                           cudaStream_t stream) {
     int rc = check_dims("mha_bwd", B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo);
     if (rc) return rc;
     ICK_REQUIRE(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "mha_bwd: grad leading dims must be multiples of 8");
@@ -623,7 +624,7 @@ extern "C" int ick_mha_bwd(const void* Q, const void* K, const void* V, const vo
     dim3 gq((Sq + NT - 1) / NT, H, B), gk((Sk + NT - 1) / NT, H, B);
     if (dt == ICK_BF16 && use_mma())
         return ick_mha_bwd_mma(Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, causal, dc,
-                               workspace, workspace_bytes, stream);
+                               workspace, workspace_bytes, dsum_ready, stream);
     if (dt == ICK_F32) {
         ick_launch(mha_bwd_dq_kernel<float>, gq, NT, 0, stream)((const float*)Q, (const float*)K, (const float*)V, (const float*)O,
                                                         (const float*)dO, lse, dsum, (float*)dQ, d, lddo, lddq, dc);

@@ -724,7 +724,7 @@ int tb_num_sms() {
 // memory budget (more than 512 queries, or operand rings that do not fit) - the caller then takes the mma.sync hybrid.
 int ick_mha_bwd_tc(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ, void* dK,
                    void* dV, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo, int lddq, int lddk, int lddv,
-                   int causal, DropCfg dc, cudaStream_t stream) {
+                   int causal, DropCfg dc, int dsum_ready, cudaStream_t stream) {
     if (dh > HD || Sq > 512 || (lddq % 8) != 0 || (lddk % 8) != 0 || (lddv % 8) != 0) return ICK_ERR_UNSUPPORTED;
     if ((((uintptr_t)K | (uintptr_t)V | (uintptr_t)Q | (uintptr_t)dO | (uintptr_t)O | (uintptr_t)dQ | (uintptr_t)dK | (uintptr_t)dV) & 15) != 0)
         return ICK_ERR_UNSUPPORTED;
@@ -755,7 +755,7 @@ int ick_mha_bwd_tc(const void* Q, const void* K, const void* V, const void* O, c
     if ((rc = make_tmap3(&tmG, dO, H, Sq, B, lddo))) return rc;
     if ((rc = make_tmap3(&tmK, K, H, Sk, B, ldk))) return rc;
     if ((rc = make_tmap3(&tmV, V, H, Sk, B, ldv))) return rc;
-    {
+    if (!dsum_ready) {
         const long long n = (long long)B * Sq * H;
         ick_launch(tb_rowdot_kernel, (int)((n + 255) / 256), 256, 0, stream)((const bf16*)O, (const bf16*)dO, dsum, B, H, Sq, dh, ldo, lddo);
         if ((rc = ick_check_launch("mha_bwd_tc(rowdot)"))) return rc;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void ick_pdl_entry() {
     ick_pdl_wait();
 }
 bool ick_pdl_enabled();  // loss_optim.cu
+extern long long ick_launch_counter;  // loss_optim.cu: kernels launched by this library (ick_launch_count, bench.py's gpu_launches)
 
 template <typename... KArgs>
 struct IckLauncher {
@@ -58,6 +59,7 @@ struct IckLauncher {
         attr[0].val.programmaticStreamSerializationAllowed = ick_pdl_enabled() ? 1 : 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        ++ick_launch_counter;
         cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through ick_check_launch()
     }
 };

@@ -132,6 +132,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -264,6 +276,13 @@ struct TnParams {
     int split_tile;
     const float* bias2;
     uint32_t site2;
+    // epi 3 (out-projection dgrad of an attention block): C = dO as usual, and the epilogue also writes the backward's row term
+    // dsum[(b*H + h)*S + i] = sum_d dO[b*S+i, 32h+d] * O[b*S+i, 32h+d] (aux = O; a 32-column chunk is exactly one head), which
+    // saves the separate row-dot kernel and its re-read of dO and O.  Second row group (dual launch): dsum2 / rd_S2, rows
+    // counted from the split; rows in [rd_rows0, split) are padding.
+    float* dsum;
+    float* dsum2;
+    int rd_S, rd_S2, rd_rows0, rd_H;
     DropCfg drop;
 };
 // Work of a CTA.  Streaming mode: tiles blockIdx.x, +gridDim.x, ... over the (m, n) grid, n fastest.  W-stationary mode:
@@ -448,6 +467,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                     ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = t[j] != 0.f ? v[j] * p.drop.inv_keep : 0.f;
+                } else if (p.epi == 3 && live) {
+                    float t[32];
+                    ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc = fmaf(t[j], __bfloat162float(__float2bfloat16_rn(v[j])), acc);  // dO as stored (bf16)
+                    const int h = col0 >> 5;
+                    if (h < p.rd_H) {
+                        if (!second) {
+                            if (row < p.rd_rows0) p.dsum[((size_t)(row / p.rd_S) * p.rd_H + h) * p.rd_S + row % p.rd_S] = acc;
+                        } else {
+                            const int r2 = row - p.split_tile * BM;
+                            p.dsum2[((size_t)(r2 / p.rd_S2) * p.rd_H + h) * p.rd_S2 + r2 % p.rd_S2] = acc;
+                        }
+                    }
                 }
                 if (p.tma_store) {
                     const uint32_t box = stg + (uint32_t)sb * sbox;
@@ -902,6 +936,205 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Linear + residual + dropout + LayerNorm in ONE kernel (the post-LN sublayer tail of every Transformer layer, G/models.py:241-244:
+// x = norm(x + dropout(sublayer(x))) with the sublayer ending in out_proj / linear2):
+//     s = x + dropout(A W^T + bias)        (s is stored: the LayerNorm backward needs it)
+//     y = LN(s) * gamma + beta             (+ mean, rstd per row for the backward)
+// A LayerNorm row is the full d_model width, so a work item is a 128-row x 320-column tile: two N = 160 tcgen05.mma per k-step
+// into ONE 320-column TMEM accumulator (2 x 320 does not fit the 512 columns: single accumulator stage).  The epilogue makes two
+// sweeps over the accumulator: sweep 1 forms s in registers (bias, hash dropout, residual), accumulates the row's sum and sum of
+// squares, writes s back INTO TENSOR MEMORY in place (tcgen05.st) and to global (bf16, bulk stores); the two warps that share a
+// lane quadrant exchange their half-row statistics through shared memory; sweep 2 re-reads s from TMEM, normalises and stores y.
+// Against GEMM + add_ln_fwd this drops one launch and one write + one read of the (rows x 320) sublayer output per LayerNorm.
+constexpr int LN_W = 320;                       // padded d_model = tile width
+constexpr int LN_HALF = 160;                    // columns per tcgen05.mma
+constexpr int LN_STAGE = A_STAGE + LN_W * BK * 2;  // 16 KiB of A + 40 KiB of W per k-block
+constexpr int LN_NSBOX = 3;                     // staging boxes per epilogue warp
+constexpr int LN_RED_BYTES = 2 * BM * 8;        // (sum, sumsq) per row and half
+struct LnParams {
+    const bf16* X;  // residual rows (nullptr: none)
+    float* mean;
+    float* rstd;
+    const float* bias; const float* bias2;
+    const float* gamma; const float* gamma2;
+    const float* beta; const float* beta2;
+    int M, D, ldx, nkb, stages, m_tiles, split_tile;
+    float eps, inv_d;
+    uint32_t site2;
+    DropCfg drop;
+};
+
+__device__ __forceinline__ void ln_stage_store(uint32_t box, int lane, const float* v, const CUtensorMap* tm, int col0, int row0) {
+    if (lane == 0) bulk_wait_read<LN_NSBOX - 1>();  // the bulk store that last read this box is done with it
+    __syncwarp();
+    const uint32_t rowa = box + (uint32_t)lane * 64u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), t1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), t3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4)),
+                     "r"(*reinterpret_cast<uint32_t*>(&t0)), "r"(*reinterpret_cast<uint32_t*>(&t1)), "r"(*reinterpret_cast<uint32_t*>(&t2)),
+                     "r"(*reinterpret_cast<uint32_t*>(&t3))
+                     : "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(tm, box, col0, row0);  // rows >= M are clipped by the tensor map
+        bulk_commit();
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmS,
+                                                                  const __grid_constant__ CUtensorMap tmY, LnParams p) {
+    ick_pdl_launch();
+    extern __shared__ uint8_t smem_raw[];
+    const Smem s = carve(smem_raw, LN_STAGE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    setup(s, warp, lane, &tmA, &tmW);
+    const uint32_t tmem_base = *s.tmem_ptr;
+    ick_pdl_wait();
+    ick_resolve_seed(p.drop);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+                const CUtensorMap* tw = mt >= p.split_tile ? &tmW2 : &tmW;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(s.empty(stage), phase ^ 1);
+                    mbar_expect_tx(s.full(stage), (uint32_t)LN_STAGE);
+                    tma_load_2d(s.a(stage), &tmA, s.full(stage), kb * BK, mt * BM);
+                    tma_load_2d(s.b(stage), tw, s.full(stage), kb * BK, 0);
+                    tma_load_2d(s.b(stage) + LN_HALF * BK * 2, tw, s.full(stage), kb * BK, LN_HALF);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(LN_HALF, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+                mbar_wait(s.tempty(0), acc_phase ^ 1);  // single accumulator: the epilogue must have drained the previous tile
+                tc_fence_after();
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(s.full(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = s.a(stage), b0 = s.b(stage);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = make_desc(a0 + k * UMMA_K * 2, 16, 1024);
+                        tc_mma_bf16(tmem_base, ad, make_desc(b0 + k * UMMA_K * 2, 16, 1024), idesc, (kb | k) != 0);
+                        tc_mma_bf16(tmem_base + LN_HALF, ad, make_desc(b0 + LN_HALF * BK * 2 + k * UMMA_K * 2, 16, 1024), idesc, (kb | k) != 0);
+                    }
+                    tc_commit(s.empty(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(s.tfull(0));
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint32_t acc_phase = 0;
+        const uint32_t stg = s.a(0) + (uint32_t)p.stages * s.stage_bytes + (uint32_t)(warp - 2) * LN_NSBOX * 2048u;
+        uint8_t* gen_base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+        float2* red = reinterpret_cast<float2*>(gen_base + BAR_BYTES + (size_t)p.stages * LN_STAGE + NEPI * LN_NSBOX * 2048);
+        int sb = 0;
+        const bool x_al = p.X != nullptr && (p.ldx % 8 == 0) && ((((uintptr_t)p.X) & 15) == 0);
+        // gamma / beta are views into the flat fp32 parameter buffer: any 4-byte offset
+        const bool gb_al = ((((uintptr_t)p.gamma) | ((uintptr_t)p.gamma2) | ((uintptr_t)p.beta) | ((uintptr_t)p.beta2)) & 15) == 0;
+        const bool dropping = p.drop.thr != 0u;
+        for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+            const int m_idx = mt * BM;
+            const int row = m_idx + q * 32 + lane;
+            const bool live = row < p.M;
+            const bool second = mt >= p.split_tile;
+            const float* bias_p = second ? p.bias2 : p.bias;
+            const float* gamma_p = second ? p.gamma2 : p.gamma;
+            const float* beta_p = second ? p.beta2 : p.beta;
+            const uint32_t rmix = second ? ick_rowmix(p.drop.seed, p.site2, (uint64_t)(row - p.split_tile * BM))
+                                         : ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            mbar_wait(s.tfull(0), acc_phase);
+            tc_fence_after();
+            float sum = 0.f, sq = 0.f;
+            // ---- sweep 1: s = x + dropout(acc + bias) -> TMEM (in place) + global; row statistics ----
+            for (int c0 = half * 32; c0 < LN_W; c0 += 64) {
+                float bv[32], xv[32];
+                if (bias_p != nullptr) ld32_f32(bias_p + c0, true, 32, bv);  // packed biases are LN_W wide, zero padded
+                if (p.X != nullptr && live) ld32_bf16(p.X + (size_t)row * p.ldx + c0, x_al, 32, xv);
+                uint32_t r[32];
+                tc_ld32(trow + c0, r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = bias_p != nullptr ? __uint_as_float(r[j]) + bv[j] : __uint_as_float(r[j]);
+                if (dropping) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const uint32_t hsh = ick_pairhash(rmix, (uint32_t)(c0 + j));
+                        v[j] *= ick_keep_lo(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
+                        v[j + 1] *= ick_keep_hi(hsh, p.drop.thr) ? p.drop.inv_keep : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (p.X != nullptr && live) v[j] += xv[j];
+                    if (c0 + j >= p.D) v[j] = 0.f;  // pad columns [D, LN_W) stay exactly zero
+                    sum += v[j];
+                    sq = fmaf(v[j], v[j], sq);
+                    r[j] = __float_as_uint(v[j]);
+                }
+                tc_st32(trow + c0, r);
+                ln_stage_store(stg + (uint32_t)sb * 2048u, lane, v, &tmS, c0, m_idx + q * 32);
+                sb = sb + 1 == LN_NSBOX ? 0 : sb + 1;
+            }
+            tc_wait_st();
+            red[half * BM + q * 32 + lane] = make_float2(sum, sq);
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            {
+                const float2 o = red[(half ^ 1) * BM + q * 32 + lane];
+                sum += o.x;
+                sq += o.y;
+            }
+            const float mean = sum * p.inv_d;
+            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sq * p.inv_d), 0.f) + p.eps);
+            const float nmr = -mean * rstd;
+            if (half == 0 && live) {
+                p.mean[row] = mean;
+                p.rstd[row] = rstd;
+            }
+            // ---- sweep 2: y = LN(s) * gamma + beta ----
+            for (int c0 = half * 32; c0 < LN_W; c0 += 64) {
+                float gv[32], tv[32];
+                const int nv = min(32, p.D - c0);  // gamma / beta hold D entries
+                ld32_f32(gamma_p + c0, nv == 32 && gb_al, nv, gv);
+                ld32_f32(beta_p + c0, nv == 32 && gb_al, nv, tv);
+                uint32_t r[32];
+                tc_ld32(trow + c0, r);
+                if (c0 + 64 >= LN_W) {  // this warp's last chunk is in registers: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s.tempty(0));
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = j < nv ? fmaf(fmaf(__uint_as_float(r[j]), rstd, nmr), gv[j], tv[j]) : 0.f;
+                ln_stage_store(stg + (uint32_t)sb * 2048u, lane, v, &tmY, c0, m_idx + q * 32);
+                sb = sb + 1 == LN_NSBOX ? 0 : sb + 1;
+            }
+            acc_phase ^= 1;
+        }
+        if (lane == 0) bulk_wait_read<0>();  // staging boxes must outlive their stores
+    }
+    teardown(warp, tmem_base);
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1045,9 +1278,14 @@ int set_smem(K kernel) {
 
 }  // namespace
 
+struct RowDot {  // epi 3 arguments (see TnParams)
+    float* dsum;
+    float* dsum2;
+    int S, S2, rows0, H;
+};
 static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C, int c_dt, const float* bias, const float* bias2,
                            const void* aux, int M, int M_split, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi, int accumulate,
-                           float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream) {
+                           float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream, const RowDot* rd = nullptr) {
     ICK_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_tn_tc: bad sizes M=%d N=%d K=%d", M, N, K);
     if (W2 != nullptr) {
         ICK_REQUIRE(M_split > 0 && M_split % BM == 0 && M_split <= M, "gemm_tn_tc_dual: M_split=%d must be a positive multiple of %d <= M", M_split,
@@ -1057,7 +1295,8 @@ static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C
     ICK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm_tn_tc: lda/ldw must be multiples of 8 (16-byte TMA strides)");
     ICK_REQUIRE((((uintptr_t)A) & 15) == 0 && (((uintptr_t)W) & 15) == 0, "gemm_tn_tc: operands must be 16-byte aligned");
     ICK_REQUIRE(c_dt == ICK_F32 || c_dt == ICK_BF16, "gemm_tn_tc: bad output dtype %d", c_dt);
-    ICK_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || (aux != nullptr && c_dt == ICK_BF16)), "gemm_tn_tc: bad epilogue");
+    ICK_REQUIRE(epi >= 0 && epi <= 3 && (epi < 2 || (aux != nullptr && c_dt == ICK_BF16)) && ((epi == 3) == (rd != nullptr)),
+                "gemm_tn_tc: bad epilogue");
     if (M == 0) return ICK_OK;
     int rc = set_smem(gemm_tn_tc_kernel);
     if (rc) return rc;
@@ -1083,6 +1322,13 @@ static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C
     p.n_tiles_n = (N + p.BN - 1) / p.BN;
     p.n_tiles = p.m_tiles * p.n_tiles_n;
     p.drop = make_drop(drop_p, seed, site);
+    p.dsum = p.dsum2 = nullptr;
+    p.rd_S = p.rd_S2 = 1;
+    p.rd_rows0 = p.rd_H = 0;
+    if (rd != nullptr) {
+        p.dsum = rd->dsum; p.dsum2 = rd->dsum2;
+        p.rd_S = rd->S; p.rd_S2 = rd->S2 > 0 ? rd->S2 : 1; p.rd_rows0 = rd->rows0; p.rd_H = rd->H;
+    }
     CUtensorMap tmA, tmW, tmW2, tmC;
     if ((rc = make_tmap(&tmA, A, K, M, lda, BM))) return rc;
     if ((rc = make_tmap(&tmW, W, K, N, ldw, p.BN))) return rc;
@@ -1120,6 +1366,65 @@ extern "C" int ick_gemm_tn_tc_dual(const void* A, const void* W, const void* W2,
     ICK_REQUIRE(W2 != nullptr, "gemm_tn_tc_dual: W2 is required");
     return gemm_tn_tc_impl(A, W, W2, C, c_dt, bias, bias2, aux, M, M_split, N, K, lda, ldw, ldc, ldaux, epi, accumulate, drop_p, seed, site, site2,
                            stream);
+}
+
+extern "C" int ick_gemm_tn_tc_rowdot(const void* A, const void* W, const void* W2, void* C, const void* O, float* dsum, float* dsum2, int M,
+                                     int M_split, int rows0, int N, int K, int lda, int ldw, int ldc, int ldo, int S, int S2, int H,
+                                     cudaStream_t stream) {
+    ICK_REQUIRE(O != nullptr && dsum != nullptr && S > 0 && H > 0 && H * 32 <= N, "gemm_tn_tc_rowdot: bad row-dot arguments");
+    ICK_REQUIRE(W2 == nullptr || (dsum2 != nullptr && S2 > 0 && rows0 > 0 && rows0 <= M_split), "gemm_tn_tc_rowdot: bad second row group");
+    ICK_REQUIRE(rows0 % S == 0 && (W2 == nullptr ? rows0 == M : (M - M_split) % S2 == 0), "gemm_tn_tc_rowdot: rows are not whole sequences");
+    RowDot rd{dsum, dsum2, S, S2, rows0, H};
+    return gemm_tn_tc_impl(A, W, W2, C, ICK_BF16, nullptr, nullptr, O, M, M_split, N, K, lda, ldw, ldc, ldo, 3, 0, 0.f, 0u, 0u, 0u, stream, &rd);
+}
+
+extern "C" int ick_gemm_add_ln_tc(const void* A, const void* W, const void* W2, const float* bias, const float* bias2, const void* X, void* S,
+                                  void* Y, float* mean, float* rstd, const float* gamma, const float* beta, const float* gamma2,
+                                  const float* beta2, int M, int M_split, int K, int d, int lda, int ldw, int ldx, int lds, int ldy, float eps,
+                                  float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream) {
+    ICK_REQUIRE(M >= 0 && K > 0 && d > 0 && d <= LN_W && d % 2 == 0, "gemm_add_ln_tc: bad sizes M=%d K=%d d=%d", M, K, d);
+    ICK_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lds % 8 == 0 && ldy % 8 == 0 && lds >= LN_W && ldy >= LN_W,
+                "gemm_add_ln_tc: leading dims must be multiples of 8 and s / y rows at least %d wide", LN_W);
+    ICK_REQUIRE(((((uintptr_t)A) | ((uintptr_t)W) | ((uintptr_t)S) | ((uintptr_t)Y)) & 15) == 0, "gemm_add_ln_tc: operands must be 16-byte aligned");
+    ICK_REQUIRE(mean != nullptr && rstd != nullptr && gamma != nullptr && beta != nullptr, "gemm_add_ln_tc: mean / rstd / gamma / beta are required");
+    ICK_REQUIRE(bias == nullptr || (((uintptr_t)bias) & 15) == 0, "gemm_add_ln_tc: bias must be 16-byte aligned (and %d wide)", LN_W);
+    if (W2 != nullptr) {
+        ICK_REQUIRE(M_split > 0 && M_split % BM == 0 && M_split <= M, "gemm_add_ln_tc: M_split=%d must be a positive multiple of %d <= M", M_split, BM);
+        ICK_REQUIRE((((uintptr_t)W2) & 15) == 0 && (bias == nullptr) == (bias2 == nullptr) && gamma2 != nullptr && beta2 != nullptr &&
+                        (bias2 == nullptr || (((uintptr_t)bias2) & 15) == 0),
+                    "gemm_add_ln_tc: bad second weight / bias / LayerNorm parameters");
+    }
+    if (M == 0) return ICK_OK;
+    int rc = set_smem(gemm_ln_tc_kernel);
+    if (rc) return rc;
+    LnParams p;
+    p.X = (const bf16*)X; p.mean = mean; p.rstd = rstd;
+    p.bias = bias; p.bias2 = W2 != nullptr ? bias2 : bias;
+    p.gamma = gamma; p.gamma2 = W2 != nullptr ? gamma2 : gamma;
+    p.beta = beta; p.beta2 = W2 != nullptr ? beta2 : beta;
+    p.M = M; p.D = d; p.ldx = ldx;
+    p.nkb = (K + BK - 1) / BK;
+    p.m_tiles = (M + BM - 1) / BM;
+    p.split_tile = W2 != nullptr ? M_split / BM : 0x7FFFFFFF;
+    p.eps = eps; p.inv_d = 1.0f / (float)d;
+    p.site2 = site2;
+    p.drop = make_drop(drop_p, seed, site);
+    p.stages = (SMEM_DATA - NEPI * LN_NSBOX * 2048 - LN_RED_BYTES) / LN_STAGE;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    ICK_REQUIRE(p.stages >= 2, "gemm_add_ln_tc: stages do not fit");
+    CUtensorMap tmA, tmW, tmW2, tmS, tmY;
+    if ((rc = make_tmap(&tmA, A, K, M, lda, BM))) return rc;
+    if ((rc = make_tmap(&tmW, W, K, LN_W, ldw, LN_HALF))) return rc;
+    if (W2 != nullptr) {
+        if ((rc = make_tmap(&tmW2, W2, K, LN_W, ldw, LN_HALF))) return rc;
+    } else {
+        tmW2 = tmW;
+    }
+    if ((rc = make_tmap_out(&tmS, S, 0, LN_W, M, lds))) return rc;
+    if ((rc = make_tmap_out(&tmY, Y, 0, LN_W, M, ldy))) return rc;
+    const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+    ick_launch(gemm_ln_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmW2, tmS, tmY, p);
+    return ick_check_launch("gemm_add_ln_tc");
 }
 
 extern "C" int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M,

@@ -105,6 +105,72 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
+// Same update, four consecutive parameters per thread: 16-byte loads / stores of p, g, m, v and of the three index arrays (all
+// buffers 16-byte aligned, checked by the launcher), every load of a thread's group issued before the first use.  The scalar
+// kernel ran at 3.4 TB/s of DRAM traffic on 15.2 M parameters (profiles/r02c_launches.csv).
+template <typename T>
+__global__ void __launch_bounds__(256) adam_kernel_v4(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                      float* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
+                                                      float bc1, float bc2_sqrt, float clip, const float* __restrict__ count,
+                                                      float grad_scale, const int* __restrict__ dstA, const int* __restrict__ dstB,
+                                                      const int* __restrict__ dstC, T* __restrict__ packT, float* __restrict__ packF,
+                                                      int update, const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
+    ick_pdl_entry();
+    float gs = grad_scale;
+    if (count) gs /= fmaxf(count[0], 1.f);
+    if (step_dev) {
+        const float t = (float)step_dev[0];
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
+    if (lr_dev) lr = lr_dev[0];
+    const float step = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pv4 = reinterpret_cast<const float4*>(p)[i];
+        int4 a4 = make_int4(-1, -1, -1, -1), b4 = a4, c4 = a4;
+        if (dstA) a4 = __ldg(reinterpret_cast<const int4*>(dstA) + i);
+        if (dstB) b4 = __ldg(reinterpret_cast<const int4*>(dstB) + i);
+        if (dstC) c4 = __ldg(reinterpret_cast<const int4*>(dstC) + i);
+        float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+        if (update) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+            const float4 m4 = reinterpret_cast<const float4*>(m)[i];
+            const float4 v4 = reinterpret_cast<const float4*>(v)[i];
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+            float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float gv = gg[j] * gs;
+                if (clip > 0.f) gv = fminf(fmaxf(gv, -clip), clip);
+                mm[j] = b1 * mm[j] + (1.f - b1) * gv;
+                vv[j] = b2 * vv[j] + (1.f - b2) * gv * gv;
+                pv[j] -= step * mm[j] / (sqrtf(vv[j]) / bc2_sqrt + eps);
+            }
+            reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            reinterpret_cast<float4*>(p)[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        }
+        const int aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+        // a parameter row is contiguous in the K-major copy: four consecutive destinations, 8-byte aligned, become one store
+        if (aa[0] >= 0 && (aa[0] & 3) == 0 && aa[1] == aa[0] + 1 && aa[2] == aa[0] + 2 && aa[3] == aa[0] + 3 && sizeof(T) == 2) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo);
+            u.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(packT + aa[0]) = u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (aa[j] >= 0) packT[aa[j]] = from_f<T>(pv[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (bb[j] >= 0) packT[bb[j]] = from_f<T>(pv[j]);
+            if (cc[j] >= 0) packF[cc[j]] = pv[j];
+        }
+    }
+}
+
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) cast2d_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long rows, int cols, int lds,
                                                      int ldd) {
@@ -520,6 +586,31 @@ extern "C" int ick_adam_step(float* p, const float* g, float* m, float* v, long 
     ICK_REQUIRE(!dstC || packF, "adam: packF missing");
     if (n == 0) return ICK_OK;
     const float bc2s = sqrtf(bias_corr2);
+    const uintptr_t al = (uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)dstA | (uintptr_t)dstB | (uintptr_t)dstC | (uintptr_t)packT;
+    if ((al & 15) == 0 && n >= 4 && (dt == ICK_F32 || dt == ICK_BF16)) {
+        const long long n4 = n / 4, tail = n - 4 * n4;
+        if (dt == ICK_F32)
+            ick_launch(adam_kernel_v4<float>, ew_grid(n4), 256, 0, stream)(p, g, m, v, n4, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count,
+                                                                        grad_scale, dstA, dstB, dstC, (float*)packT, packF, update, step_dev, lr_dev);
+        else
+            ick_launch(adam_kernel_v4<bf16>, ew_grid(n4), 256, 0, stream)(p, g, m, v, n4, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count,
+                                                                       grad_scale, dstA, dstB, dstC, (bf16*)packT, packF, update, step_dev, lr_dev);
+        if (tail > 0) {  // the last 1-3 parameters through the scalar kernel
+            const long long o = 4 * n4;
+            const int* a = dstA ? dstA + o : nullptr;
+            const int* b = dstB ? dstB + o : nullptr;
+            const int* c = dstC ? dstC + o : nullptr;
+            if (dt == ICK_F32)
+                ick_launch(adam_kernel<float>, 1, 32, 0, stream)(p + o, g ? g + o : g, m ? m + o : m, v ? v + o : v, tail, lr, beta1, beta2, eps,
+                                                                 bias_corr1, bc2s, clip, count, grad_scale, a, b, c, (float*)packT, packF, update,
+                                                                 step_dev, lr_dev);
+            else
+                ick_launch(adam_kernel<bf16>, 1, 32, 0, stream)(p + o, g ? g + o : g, m ? m + o : m, v ? v + o : v, tail, lr, beta1, beta2, eps,
+                                                                bias_corr1, bc2s, clip, count, grad_scale, a, b, c, (bf16*)packT, packF, update,
+                                                                step_dev, lr_dev);
+        }
+        return ick_check_launch("adam_step");
+    }
     if (dt == ICK_F32)
         ick_launch(adam_kernel<float>, ew_grid(n), 256, 0, stream)(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bc2s, clip, count, grad_scale,
                                                            dstA, dstB, dstC, (float*)packT, packF, update, step_dev, lr_dev);
@@ -663,3 +754,10 @@ extern "C" int ick_set_seed_source(const unsigned* seed_dev) {
     return ICK_OK;
 }
 extern "C" int ick_abi_version(void) { return ICK_ABI_VERSION; }
+
+long long ick_launch_counter = 0;
+extern "C" int ick_launch_count(long long* out) {
+    ICK_REQUIRE(out != nullptr, "launch_count: null output");
+    *out = ick_launch_counter;
+    return ICK_OK;
+}

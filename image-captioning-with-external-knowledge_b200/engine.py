@@ -111,19 +111,23 @@ class DecoderEngine:
         K.mha_fwd(sv.qkv[:, :DP], sv.qkv[:, DP : 2 * DP], sv.qkv[:, 2 * DP :], sv.o, sv.lse, B, H, S, S, dh, causal=False,
                   drop=self._drop(p, seed, site + ".sa.attn"))
         sv.s1 = self._new(R, DP)
-        K.gemm(sv.o, out_l.W, sv.s1, bias=out_l.b)
         sv.y1 = self._new(R, DP)
         sv.mean1, sv.rstd1 = self._newf(R), self._newf(R)
-        K.add_ln_fwd(x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1, sv.rstd1, D,
-                     drop=self._drop(p, seed, site + ".d1"))
+        # out-projection + residual + dropout + LayerNorm: one launch (kernels.gemm_add_ln)
+        K.gemm_add_ln(sv.o, out_l.W, out_l.b, x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1,
+                      sv.rstd1, D, drop=self._drop(p, seed, site + ".d1"))
         sv.h1 = self._new(R, f1.lin.Np)
         K.gemm(sv.y1, f1.W, sv.h1, bias=f1.b, epi=1, drop=self._drop(p, seed, site + ".ffn"))
         sv.s2 = self._new(R, DP)
-        K.gemm(sv.h1, f2.W, sv.s2, bias=f2.b)
         y2 = out if out is not None else self._new(R, DP)
         sv.mean2, sv.rstd2 = self._newf(R), self._newf(R)
-        K.add_ln_fwd(sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), y2, sv.mean2, sv.rstd2, D,
-                     rowmap=rowmap, drop=self._drop(p, seed, site + ".d2"))
+        if rowmap[0] == 0:
+            K.gemm_add_ln(sv.h1, f2.W, f2.b, sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), y2, sv.mean2,
+                          sv.rstd2, D, drop=self._drop(p, seed, site + ".d2"))
+        else:  # row-mapped output (the last layer writes into the memory buffer): separate LayerNorm kernel
+            K.gemm(sv.h1, f2.W, sv.s2, bias=f2.b)
+            K.add_ln_fwd(sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), y2, sv.mean2, sv.rstd2, D,
+                         rowmap=rowmap, drop=self._drop(p, seed, site + ".d2"))
         return y2, sv
 
     # The weight gradients of a layer do not feed its input gradient, so the backward helpers only RECORD them
@@ -149,11 +153,12 @@ class DecoderEngine:
         R = B * S
         self._wg(wg, dB, sv_o, out_l)
         dO = self._new(R, DP)
-        K.gemm(dB, out_l.WT, dO)
         dqkv = self._new(R, 3 * DP)
         dsum = self._newf(B * H * S)
+        ready = K.gemm_rowdot(dB, out_l.WT, dO, sv_o, dsum, S, H)  # dO and rowsum(dO * O) from one launch
         K.mha_bwd(sv_qkv[:, :DP], sv_qkv[:, DP : 2 * DP], sv_qkv[:, 2 * DP :], sv_o, dO, sv_lse, dsum, dqkv[:, :DP],
-                  dqkv[:, DP : 2 * DP], dqkv[:, 2 * DP :], B, H, S, S, dh, causal=causal, drop=self._drop(p, seed, site + ".sa.attn"))
+                  dqkv[:, DP : 2 * DP], dqkv[:, 2 * DP :], B, H, S, S, dh, causal=causal, drop=self._drop(p, seed, site + ".sa.attn"),
+                  dsum_ready=ready)
         self._wg(wg, dqkv, x_in, qkv_l)
         K.gemm(dqkv, qkv_l.WT, dC, accumulate=True)
 
@@ -217,23 +222,30 @@ class DecoderEngine:
                           drop=self._drop(p, seed, site[i] + ".sa.attn"))
                 sv.lse.append(lse)
             sv.s1 = self._new(Rc, DP)
-            K.gemm_dual(sv.o, out_l[0].W, out_l[1].W, sv.s1, off, Re, out_l[0].b, out_l[1].b)
             sv.y1 = self._new(Rc, DP)
             sv.mean1, sv.rstd1, sv.mean2, sv.rstd2 = (self._newf(Rc) for _ in range(4))
             Rf = stacks[1][2]
             par = lambda n: (self.param(pre[0] + n), self.param(pre[1] + n))  # noqa: E731
-            K.add_ln_fwd_dual(x, sv.s1, sv.y1, sv.mean1, sv.rstd1, D, Re, Rf, off, par("norm1.weight"), par("norm1.bias"),
-                              drops=(self._drop(p, seed, site[0] + ".d1"), self._drop(p, seed, site[1] + ".d1")))
+            # out-projection + residual + dropout + LayerNorm of both stacks: one launch
+            K.gemm_add_ln_dual(sv.o, out_l[0].W, out_l[1].W, out_l[0].b, out_l[1].b, x, sv.s1, sv.y1, sv.mean1, sv.rstd1, D, off, Re,
+                               par("norm1.weight"), par("norm1.bias"),
+                               drops=(self._drop(p, seed, site[0] + ".d1"), self._drop(p, seed, site[1] + ".d1")))
             sv.h1 = self._new(Rc, f1[0].lin.Np)
             K.gemm_dual(sv.y1, f1[0].W, f1[1].W, sv.h1, off, Re, f1[0].b, f1[1].b, epi=1, drop0=self._drop(p, seed, site[0] + ".ffn"),
                         drop1=self._drop(p, seed, site[1] + ".ffn"))
             sv.s2 = self._new(Rc, DP)
-            K.gemm_dual(sv.h1, f2[0].W, f2[1].W, sv.s2, off, Re, f2[0].b, f2[1].b)
             y2 = None if last else self._new(Rc, DP)
-            # the last layer writes straight into the decoder's memory rows (the reference concatenates, K/models.py:497-499)
-            maps = tuple((S, M, m0) if last else (0, 0, 0) for (_, S, _, _, m0) in stacks)
-            K.add_ln_fwd_dual(sv.y1, sv.s2, mem if last else y2, sv.mean2, sv.rstd2, D, Re, Rf, off, par("norm2.weight"), par("norm2.bias"),
-                              rowmaps=maps, drops=(self._drop(p, seed, site[0] + ".d2"), self._drop(p, seed, site[1] + ".d2")))
+            drops2 = (self._drop(p, seed, site[0] + ".d2"), self._drop(p, seed, site[1] + ".d2"))
+            if not last:
+                K.gemm_add_ln_dual(sv.h1, f2[0].W, f2[1].W, f2[0].b, f2[1].b, sv.y1, sv.s2, y2, sv.mean2, sv.rstd2, D, off, Re,
+                                   par("norm2.weight"), par("norm2.bias"), drops=drops2)
+            else:
+                # the last layer writes straight into the decoder's memory rows (the reference concatenates, K/models.py:497-499):
+                # a row-mapped output, which the separate LayerNorm kernel provides
+                K.gemm_dual(sv.h1, f2[0].W, f2[1].W, sv.s2, off, Re, f2[0].b, f2[1].b)
+                maps = tuple((S, M, m0) for (_, S, _, _, m0) in stacks)
+                K.add_ln_fwd_dual(sv.y1, sv.s2, mem, sv.mean2, sv.rstd2, D, Re, Rf, off, par("norm2.weight"), par("norm2.bias"),
+                                  rowmaps=maps, drops=drops2)
             x = y2
             saves.append(sv)
         return saves
@@ -274,14 +286,16 @@ class DecoderEngine:
                 self._wg(wg, dh1[sl], sv.y1[sl], f1[i])
                 self._wg(wg, dB1[sl], sv.o[sl], out_l[i])
             dO = self._new(Rc, DP)
-            K.gemm_dual(dB1, out_l[0].WT, out_l[1].WT, dO, off, Re)
+            dsums = [self._newf(B * H * S) for (_, S, _, _, _) in stacks]
+            # dO of both stacks and their rowsum(dO * O) terms from one launch
+            ready = K.gemm_rowdot(dB1, out_l[0].WT, dO, sv.o, dsums[0], stacks[0][1], H, W1=out_l[1].WT, m_split=off, rows0=Re,
+                                  dsum1=dsums[1], S1=stacks[1][1])
             dqkv = self._new(Rc, 3 * DP)
             for i, (_, S, R, r0, _) in enumerate(stacks):
                 sl = slice(r0, r0 + R)
                 q, dq = sv.qkv[sl], dqkv[sl]
-                dsum = self._newf(B * H * S)
-                K.mha_bwd(q[:, :DP], q[:, DP : 2 * DP], q[:, 2 * DP :], sv.o[sl], dO[sl], sv.lse[i], dsum, dq[:, :DP], dq[:, DP : 2 * DP],
-                          dq[:, 2 * DP :], B, H, S, S, dh, causal=False, drop=self._drop(p, seed, site[i] + ".sa.attn"))
+                K.mha_bwd(q[:, :DP], q[:, DP : 2 * DP], q[:, 2 * DP :], sv.o[sl], dO[sl], sv.lse[i], dsums[i], dq[:, :DP], dq[:, DP : 2 * DP],
+                          dq[:, 2 * DP :], B, H, S, S, dh, causal=False, drop=self._drop(p, seed, site[i] + ".sa.attn"), dsum_ready=ready)
                 self._wg(wg, dq, sv.x[sl], qkv_l[i])
             K.gemm_dual(dqkv, qkv_l[0].WT, qkv_l[1].WT, dC, off, Re, accumulate=True)
             K.wgrad_group(wg, gflat)
@@ -307,11 +321,10 @@ class DecoderEngine:
         K.mha_fwd(sv.qkv[:, :DP], sv.qkv[:, DP : 2 * DP], sv.qkv[:, 2 * DP :], sv.o, sv.lse, B, H, T, T, dh, causal=True,
                   drop=self._drop(p, seed, site + ".sa.attn"))
         sv.s1 = self._new(R, DP)
-        K.gemm(sv.o, out_l.W, sv.s1, bias=out_l.b)
         sv.y1 = self._new(R, DP)
         sv.mean1, sv.rstd1 = self._newf(R), self._newf(R)
-        K.add_ln_fwd(x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1, sv.rstd1, D,
-                     drop=self._drop(p, seed, site + ".d1"))
+        K.gemm_add_ln(sv.o, out_l.W, out_l.b, x, sv.s1, self.param(pre + "norm1.weight"), self.param(pre + "norm1.bias"), sv.y1, sv.mean1,
+                      sv.rstd1, D, drop=self._drop(p, seed, site + ".d1"))
         # cross-attention over the memory (its K/V projections were computed for all layers at once)
         sv.q = self._new(R, DP)
         K.gemm(sv.y1, q_l.W, sv.q, bias=q_l.b)
@@ -321,20 +334,18 @@ class DecoderEngine:
         sv.lse2 = self._newf(B * H * T)
         K.mha_fwd(sv.q, sv.k, sv.v, sv.o2, sv.lse2, B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"))
         sv.s2 = self._new(R, DP)
-        K.gemm(sv.o2, out2_l.W, sv.s2, bias=out2_l.b)
         sv.y2 = self._new(R, DP)
         sv.mean2, sv.rstd2 = self._newf(R), self._newf(R)
-        K.add_ln_fwd(sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), sv.y2, sv.mean2, sv.rstd2, D,
-                     drop=self._drop(p, seed, site + ".d2"))
+        K.gemm_add_ln(sv.o2, out2_l.W, out2_l.b, sv.y1, sv.s2, self.param(pre + "norm2.weight"), self.param(pre + "norm2.bias"), sv.y2,
+                      sv.mean2, sv.rstd2, D, drop=self._drop(p, seed, site + ".d2"))
         # feed-forward
         sv.h1 = self._new(R, f1.lin.Np)
         K.gemm(sv.y2, f1.W, sv.h1, bias=f1.b, epi=1, drop=self._drop(p, seed, site + ".ffn"))
         sv.s3 = self._new(R, DP)
-        K.gemm(sv.h1, f2.W, sv.s3, bias=f2.b)
         y3 = self._new(R, DP)
         sv.mean3, sv.rstd3 = self._newf(R), self._newf(R)
-        K.add_ln_fwd(sv.y2, sv.s3, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), y3, sv.mean3, sv.rstd3, D,
-                     drop=self._drop(p, seed, site + ".d3"))
+        K.gemm_add_ln(sv.h1, f2.W, f2.b, sv.y2, sv.s3, self.param(pre + "norm3.weight"), self.param(pre + "norm3.bias"), y3, sv.mean3,
+                      sv.rstd3, D, drop=self._drop(p, seed, site + ".d3"))
         return y3, sv
 
     def _dec_layer_bwd(self, l, sv, dy, dkv, B, T, M, gflat, p, seed):
@@ -358,11 +369,12 @@ class DecoderEngine:
         # cross-attention backward
         self._wg(wg, dB2, sv.o2, out2_l)
         dO2 = self._new(R, DP)
-        K.gemm(dB2, out2_l.WT, dO2)
         dq = self._new(R, DP)
         dsum = self._newf(B * H * T)
+        ready = K.gemm_rowdot(dB2, out2_l.WT, dO2, sv.o2, dsum, T, H)
         K.mha_bwd(sv.q, sv.k, sv.v, sv.o2, dO2, sv.lse2, dsum, dq, dkv[:, l * 2 * DP : l * 2 * DP + DP],
-                  dkv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"))
+                  dkv[:, l * 2 * DP + DP : (l + 1) * 2 * DP], B, H, T, M, dh, causal=False, drop=self._drop(p, seed, site + ".ca.attn"),
+                  dsum_ready=ready)
         self._wg(wg, dq, sv.y1, q_l)
         K.gemm(dq, q_l.WT, dC, accumulate=True)
         dE, dB1 = self._new(R, DP), self._new(R, DP)
@@ -631,15 +643,12 @@ class DecoderEngine:
         if not fused:
             K.gemm(x, qkv_l.W, row, bias=qkv_l.b)
             attn_self(row, b.o)
-            K.gemm(b.o, out_l.W, b.s, bias=out_l.b)
-            K.add_ln_fwd(x, b.s, n1[0], n1[1], b.y1, mean, rstd, D)
+            K.gemm_add_ln(b.o, out_l.W, out_l.b, x, b.s, n1[0], n1[1], b.y1, mean, rstd, D)
             K.gemm(b.y1, q_l.W, b.q, bias=q_l.b)
             attn_cross(b.q, b.o)
-            K.gemm(b.o, out2_l.W, b.s, bias=out2_l.b)
-            K.add_ln_fwd(b.y1, b.s, n2[0], n2[1], b.y2, mean, rstd, D)
+            K.gemm_add_ln(b.o, out2_l.W, out2_l.b, b.y1, b.s, n2[0], n2[1], b.y2, mean, rstd, D)
             K.gemm(b.y2, f1.W, b.h1, bias=f1.b, epi=1)
-            K.gemm(b.h1, f2.W, b.s, bias=f2.b)
-            K.add_ln_fwd(b.y2, b.s, n3[0], n3[1], b.y3, mean, rstd, D)
+            K.gemm_add_ln(b.h1, f2.W, f2.b, b.y2, b.s, n3[0], n3[1], b.y3, mean, rstd, D)
             return b.y3
         attn_self(row, b.o)
         K.decode_chain(b.o, x, out_l.W, out_l.b, n1[0], n1[1], b.y1, D, proj=(q_l.W, q_l.b, b.q))

@@ -72,7 +72,6 @@ class CudaKernels:
             self.lib.call(name, *args, self._s())
             e1.record()
             self.prof.append((name, e0, e1, work() if work is not None else (0, 0)))
-        self.lib.launches += n - 1
 
     # ---- dense ---------------------------------------------------------------------------------------------------
     def gemm(self, A, W, C, bias=None, aux=None, epi=0, accumulate=False, drop: Drop = None, force_simt=False):
@@ -116,6 +115,74 @@ class CudaKernels:
         work = lambda: ((rows * K) * 2 + 2 * (N * K) * 2 + rows * N * C.element_size() * (2 if accumulate else 1), 2 * rows * N * K)  # noqa: E731
         self._call("ick_gemm_tn_tc_dual", _p(A), _p(W0), _p(W1), _p(C), dt_of(C), _p(bias0), _p(bias1), _p(aux), M, m_split, N, K, _ld(A),
                    _ld(W0), _ld(C), _ld(aux) if aux is not None else 0, epi, int(accumulate), max(p, p1), seed or seed1, site0, site1, work=work)
+
+    def gemm_rowdot(self, A, W, C, O, dsum, S, H, W1=None, m_split=0, rows0=None, dsum1=None, S1=0) -> bool:
+        """
+        C = A @ W^T (the out-projection input gradient dO of an attention block) with the attention backward's row term
+        dsum[(b*H + h)*S + i] = sum_d dO * O written by the GEMM epilogue (include/ickb200.h: ick_gemm_tn_tc_rowdot).  W1 given:
+        two row groups as in gemm_dual (rows [m_split, M) use W1, dsum1, S1).  Returns True when dsum was written (tensor-core
+        bf16 path) - the caller then passes dsum_ready=True to mha_bwd - and False after a plain GEMM (dsum untouched).
+        """
+        M, K = A.shape
+        N = W.shape[0]
+        rows0 = M if rows0 is None else rows0
+        tc = (self.use_tc and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and C.dtype == torch.bfloat16 and O.dtype == torch.bfloat16
+              and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0 and N >= H * 32 and _ld(O) % 8 == 0 and O.data_ptr() % 16 == 0
+              and (W1 is None or (W1.data_ptr() % 16 == 0 and m_split % 128 == 0 and 0 < m_split < M)))
+        if not tc:
+            if W1 is None:
+                self.gemm(A, W, C)
+            else:
+                self.gemm_dual(A, W, W1, C, m_split, rows0)
+            return False
+        rows = rows0 + ((M - m_split) if W1 is not None else 0)
+        work = lambda: ((rows * K) * 2 + (1 if W1 is None else 2) * (N * K) * 2 + 2 * rows * N * 2 + rows * H // 8 * 4, 2 * rows * N * K)  # noqa: E731
+        self._call("ick_gemm_tn_tc_rowdot", _p(A), _p(W), _p(W1), _p(C), _p(O), _p(dsum), _p(dsum1), M, m_split, rows0, N, K, _ld(A), _ld(W),
+                   _ld(C), _ld(O), S, S1, H, work=work)
+        return True
+
+    def gemm_add_ln(self, A, W, bias, x, s, gamma, beta, y, mean, rstd, d, eps=1e-5, drop: Drop = None):
+        """s = x + dropout(A @ W^T + bias); y = LN(s) * gamma + beta; mean / rstd per row (the post-LN sublayer tail with its last
+        Linear folded in).  bf16 rows of 320 elements run as ONE tcgen05 launch (ick_gemm_add_ln_tc); anything else as
+        gemm + add_ln_fwd."""
+        M, K = A.shape
+        if self._ln_fusable(A, W, x, s, y, d):
+            p, seed, site = _drop(drop)
+            self._call("ick_gemm_add_ln_tc", _p(A), _p(W), None, _p(bias), None, _p(x), _p(s), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                       None, None, M, 0, K, d, _ld(A), _ld(W), _ld(x) if x is not None else 0, _ld(s), _ld(y), eps, p, seed, site, 0,
+                       work=lambda: ((M * K) * 2 + 320 * K * 2 + M * d * 2 * (3 if x is not None else 2), 2 * M * 320 * K))
+            return
+        self.gemm(A, W, s, bias=bias)
+        self.add_ln_fwd(x, s, gamma, beta, y, mean, rstd, d, eps, drop=drop)
+
+    def gemm_add_ln_dual(self, A, W0, W1, bias0, bias1, x, s, y, mean, rstd, d, m_split, rows0, gammas, betas, drops=(None, None), eps=1e-5):
+        """gemm_add_ln for two row groups with their own weights / LayerNorm parameters / dropout sites (rows [0, rows0) and
+        [m_split, M); the lockstep entity / fact encoder stacks)."""
+        M, K = A.shape
+        (p, seed, site0), (p1, seed1, site1) = _drop(drops[0]), _drop(drops[1])
+        if (self._ln_fusable(A, W0, x, s, y, d) and W1.data_ptr() % 16 == 0 and W0.stride(0) == W1.stride(0) and m_split % 128 == 0
+                and 0 < m_split < M and (p, seed) == (p1, seed1)):
+            rows = rows0 + (M - m_split)
+            self._call("ick_gemm_add_ln_tc", _p(A), _p(W0), _p(W1), _p(bias0), _p(bias1), _p(x), _p(s), _p(y), _p(mean), _p(rstd),
+                       _p(gammas[0]), _p(betas[0]), _p(gammas[1]), _p(betas[1]), M, m_split, K, d, _ld(A), _ld(W0), _ld(x), _ld(s), _ld(y),
+                       eps, p, seed, site0, site1,
+                       work=lambda: ((rows * K) * 2 + 2 * 320 * K * 2 + rows * d * 2 * 3, 2 * rows * 320 * K))
+            return
+        self.gemm_dual(A, W0, W1, s, m_split, rows0, bias0, bias1)
+        self.add_ln_fwd_dual(x, s, y, mean, rstd, d, rows0, M - m_split, m_split, gammas, betas, drops=drops, eps=eps)
+
+    def _ln_fusable(self, A, W, x, s, y, d) -> bool:
+        # OPT-IN (ICK_FUSE_LN=1).  Measured on a B200 (profiles/README.md, r02e): the K train step takes 5.72 ms with the fused
+        # kernel against 5.62 ms with GEMM + LayerNorm launches, and the 625-image greedy decode drops from 23.5k to 20.6k
+        # captions/s: a 128 x 320 tile per CTA leaves 102 of 148 SMs busy on the decoder rows (5 at decode sizes), the single
+        # 320-column TMEM accumulator cannot overlap the epilogue with the next tile's main loop, and the two-sweep row-per-lane
+        # epilogue is latency-bound where the stand-alone LayerNorm kernel has a warp per row.
+        import os
+
+        return (self.use_tc and os.environ.get("ICK_FUSE_LN", "0") == "1" and A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+                and s.dtype == torch.bfloat16 and y.dtype == torch.bfloat16 and (x is None or x.dtype == torch.bfloat16)
+                and W.shape[0] == 320 and d <= 320 and d % 2 == 0 and s.shape[1] == 320 and y.shape[1] == 320
+                and all(t.data_ptr() % 16 == 0 and _ld(t) % 8 == 0 for t in (A, W, s, y)))
 
     def wgrad(self, dY, X, gflat, rowoff, colmap=None, biasoff=None, force_simt=False):
         """gflat[rowoff[n] + colmap[k]] += sum_m dY[m,n] X[m,k];  gflat[biasoff[n]] += sum_m dY[m,n]."""
@@ -183,7 +250,7 @@ class CudaKernels:
                    int(causal), p, seed, site,
                    work=lambda: (B * H * dh * (2 * Sq + 2 * Sk) * Q.element_size() + B * H * Sq * 4, int(4 * B * H * Sq * Sk * dh * c)))
 
-    def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop: Drop = None):
+    def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop: Drop = None, dsum_ready=False):
         p, seed, site = _drop(drop)
         ws = None
         if Q.dtype == torch.bfloat16:
@@ -194,7 +261,7 @@ class CudaKernels:
             ws = self._ds_ws
         self._call("ick_mha_bwd", _p(Q), _p(K), _p(V), _p(O), _p(dO), _p(lse), _p(dsum), _p(dQ), _p(dK), _p(dV), dt_of(Q), B, H, Sq,
                    Sk, dh, _ld(Q), _ld(K), _ld(V), _ld(O), _ld(dO), _ld(dQ), _ld(dK), _ld(dV), int(causal), p, seed, site, _p(ws),
-                   ws.numel() if ws is not None else 0, n=3 if ws is not None else 2,
+                   ws.numel() if ws is not None else 0, int(dsum_ready),
                    work=lambda: (B * H * dh * (4 * Sq + 4 * Sk) * Q.element_size() + 2 * B * H * Sq * 4,
                                  int(10 * B * H * Sq * Sk * dh * (0.5 if causal else 1.0))))
 

@@ -24,7 +24,7 @@
 
 #include <cuda_runtime_api.h>
 
-#define ICK_ABI_VERSION 9
+#define ICK_ABI_VERSION 10
 
 #ifdef __cplusplus
 extern "C" {
@@ -32,6 +32,9 @@ extern "C" {
 
 const char* ick_last_error(void);
 int ick_abi_version(void);
+/* number of kernels this library has launched so far in the process (every launch, whichever entry point issued it; replays of a
+ * captured CUDA graph are not launches of the library and are not counted) */
+int ick_launch_count(long long* out);
 
 /* ---- dense projections: nn.Linear inside nn.MultiheadAttention / Transformer*Layer, fc_vocab --------------------- */
 /* C[M,N] (+)= A[M,K] * W[N,K]^T + bias.  epi: 0 none, 1 ReLU+dropout (linear1 -> activation -> dropout),
@@ -58,6 +61,25 @@ int ick_gemm_tn_tc(const void* A, const void* W, void* C, int c_dt, const float*
 int ick_gemm_tn_tc_dual(const void* A, const void* W, const void* W2, void* C, int c_dt, const float* bias, const float* bias2,
                         const void* aux, int M, int M_split, int N, int K, int lda, int ldw, int ldc, int ldaux, int epi,
                         int accumulate, float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream);
+/* The out-projection input gradient of an attention block, dO = dB W (W = out_proj.weight^T packed K-major), which ALSO writes
+ * the attention backward's row term dsum[(b*H + h)*S + i] = sum_d dO[b*S+i, 32h+d] * O[b*S+i, 32h+d] from the epilogue (dO rounded
+ * to bf16 first, as stored) - pass dsum_ready = 1 to ick_mha_bwd afterwards.  W2 != NULL: two row groups as in ick_gemm_tn_tc_dual
+ * (rows [0, rows0) -> dsum with S tokens per sequence, rows [M_split, M) -> dsum2 with S2); W2 == NULL: rows0 = M.  N = H*32 = ldo
+ * columns of head layout.  Replaces the out_proj half of F.multi_head_attention_forward's autograd (G/models.py:241-244). */
+int ick_gemm_tn_tc_rowdot(const void* A, const void* W, const void* W2, void* C, const void* O, float* dsum, float* dsum2, int M,
+                          int M_split, int rows0, int N, int K, int lda, int ldw, int ldc, int ldo, int S, int S2, int H,
+                          cudaStream_t stream);
+/* Linear + residual + dropout + LayerNorm, the post-LN sublayer tail x = norm(x + dropout(sublayer(x))) of
+ * nn.TransformerEncoderLayer / nn.TransformerDecoderLayer (constructed G/models.py:241-244) with the sublayer's last Linear
+ * (out_proj / linear2) folded in:  S = X + dropout(A W^T + bias);  Y = LN(S) * gamma + beta;  mean / rstd per row are kept for
+ * ick_add_ln_bwd.  W: [320, K] bf16 (d_model padded to 320 rows, pad rows zero), bias: 320 floats (pad zero, 16-byte aligned),
+ * d = 300 logical columns, S / Y rows of lds / ldy >= 320 elements (pad columns written as zeros).  W2 != NULL: rows
+ * [M_split, M) use (W2, bias2, gamma2, beta2, site2; dropout rows counted from M_split), M_split % 128 == 0.  One tcgen05 launch
+ * instead of ick_gemm_tn_tc + ick_add_ln_fwd: the sublayer output never leaves tensor memory before the normalisation. */
+int ick_gemm_add_ln_tc(const void* A, const void* W, const void* W2, const float* bias, const float* bias2, const void* X, void* S,
+                       void* Y, float* mean, float* rstd, const float* gamma, const float* beta, const float* gamma2,
+                       const float* beta2, int M, int M_split, int K, int d, int lda, int ldw, int ldx, int lds, int ldy, float eps,
+                       float drop_p, unsigned seed, unsigned site, unsigned site2, cudaStream_t stream);
 /* workspace (optional, fp32, >= splits*N*ceil32(K)*4 bytes): row-slice partial tiles are stored there and reduced by a
  * second kernel; without it the partials are added with fp32 atomics. */
 int ick_wgrad_tc(const void* dY, const void* X, float* gflat, const int* rowoff, const int* colmap, const int* biasoff, int M, int N,
@@ -79,7 +101,9 @@ int ick_mha_fwd(const void* Q, const void* K, const void* V, void* O, float* lse
 int ick_mha_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse, float* dsum, void* dQ,
                 void* dK, void* dV, int dt, int B, int H, int Sq, int Sk, int dh, int ldq, int ldk, int ldv, int ldo, int lddo,
                 int lddq, int lddk, int lddv, int causal, float drop_p, unsigned seed, unsigned site, void* workspace,
-                long long workspace_bytes, cudaStream_t stream);
+                long long workspace_bytes, int dsum_ready, cudaStream_t stream);
+/* dsum_ready != 0: dsum already holds rowsum(dO * O) (written by ick_gemm_tn_tc_rowdot); implementations that would launch a
+ * row-dot kernel skip it, the others recompute it. */
 /* workspace (optional, bf16 path): B*H*ceil(Sk/16)*2*ceil(Sq/64) KiB.  With it the backward runs as rowsum(dO*O) -> dK/dV (which
  * also stores dS^T) -> dQ = dS K as a GEMM over the stored dS; without it dS is recomputed by a separate dQ kernel. */
 /* one query per (batch, head) against klen cached keys/values (KV-cached greedy decode; predict() re-decodes instead) */

@@ -92,6 +92,29 @@ class HostKernels:
         for dY, X, rowoff, colmap, biasoff in probs:
             self.wgrad(dY, X, gflat, rowoff, colmap, biasoff)
 
+    def gemm_rowdot(self, A, W, C, O, dsum, S, H, W1=None, m_split=0, rows0=None, dsum1=None, S1=0) -> bool:
+        """ick_gemm_tn_tc_rowdot: C = A W^T and dsum[(b*H + h)*S + i] = sum_d C[b*S+i, 32h+d] * O[b*S+i, 32h+d] (C as stored)."""
+        M = A.shape[0]
+        if W1 is None:
+            self.gemm(A, W, C)
+            groups = ((0, M, S, dsum),)
+        else:
+            self.gemm_dual(A, W, W1, C, m_split, rows0)
+            groups = ((0, rows0, S, dsum), (m_split, M - m_split, S1, dsum1))
+        for r0, n, Sg, out in groups:
+            prod = (C[r0:r0 + n, :H * HD].float() * O[r0:r0 + n, :H * HD].float()).view(n // Sg, Sg, H, HD).sum(-1)  # (b, i, h)
+            out.copy_(prod.permute(0, 2, 1).reshape(-1))
+        return True
+
+    def gemm_add_ln(self, A, W, bias, x, s, gamma, beta, y, mean, rstd, d, eps=1e-5, drop=None):
+        """ick_gemm_add_ln_tc as its two-kernel equivalent"""
+        self.gemm(A, W, s, bias=bias)
+        self.add_ln_fwd(x, s, gamma, beta, y, mean, rstd, d, eps, drop=drop)
+
+    def gemm_add_ln_dual(self, A, W0, W1, bias0, bias1, x, s, y, mean, rstd, d, m_split, rows0, gammas, betas, drops=(None, None), eps=1e-5):
+        self.gemm_dual(A, W0, W1, s, m_split, rows0, bias0, bias1)
+        self.add_ln_fwd_dual(x, s, y, mean, rstd, d, rows0, A.shape[0] - m_split, m_split, gammas, betas, drops=drops, eps=eps)
+
     # ---- attention -------------------------------------------------------------------------------------------------
     @staticmethod
     def _heads(X, B, S, H):
@@ -118,8 +141,9 @@ class HostKernels:
         out[..., :dh] = o
         O.copy_(out.permute(0, 2, 1, 3).reshape(B * Sq, H * HD).to(O.dtype))
 
-    def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop=None):
+    def mha_bwd(self, Q, K, V, O, dO, lse, dsum, dQ, dK, dV, B, H, Sq, Sk, dh, causal=False, drop=None, dsum_ready=False):
         self.calls += 2
+        given = dsum.clone() if dsum_ready else None
         q, k, s = self._probs(Q, K, B, H, Sq, Sk, dh, causal)
         v = self._heads(V, B, Sk, H)[..., :dh]
         go = self._heads(dO, B, Sq, H)[..., :dh]
@@ -129,6 +153,9 @@ class HostKernels:
         dv = (p * mm).transpose(-1, -2) @ go
         dp = (go @ v.transpose(-1, -2)) * mm
         D = (dp * p).sum(-1, keepdim=True)
+        if given is not None:  # the row term handed over by gemm_rowdot must be the one this backward would compute itself
+            tol = 1e-4 if O.dtype == torch.float32 else 3e-2
+            assert float((given - D.reshape(-1)).abs().max()) <= tol * max(1.0, float(D.abs().max())), "dsum_ready: stale / wrong row term"
         dsum.copy_(D.reshape(-1))
         ds = p * (dp - D)
         dq = ds @ k / math.sqrt(dh)

@@ -319,6 +319,31 @@ def test_mha_bwd_fused_many_items(K, Hk, att_mode, p, B, H, Sq, Sk, dh, causal):
         assert float(rel.max()) < TOL[dtype] * 3, (name, int(rel.argmax()), float(rel.max()))
 
 
+@pytest.mark.parametrize("split", ["1", "0"])
+@pytest.mark.parametrize("B,H,Sq,Sk,dh", [(40, 10, 5, 548, 30), (7, 10, 5, 598, 30), (33, 10, 3, 300, 30), (9, 10, 16, 548, 30), (400, 10, 1, 257, 30)])
+def test_mha_fwd_few_queries_split_keys(K, Hk, monkeypatch, split, B, H, Sq, Sk, dh):
+    """One 16-row slab of queries per (image, head) item - the beam-search decode step's cross-attention (Sq = beam width) - runs on
+    the split-key kernel (fwd_split_pkernel: the item's key tiles dealt to a group of warps, partial softmaxes merged in shared
+    memory); ICK_ATTN_SPLIT=0 is the one-warp-per-item path it replaces.  More items than CTAs: stages and scratch are re-used."""
+    monkeypatch.setenv("ICK_ATTN_SPLIT", split)
+    monkeypatch.setenv("ICK_ATTN_FWD", "mma")
+    dtype = torch.bfloat16
+    q = headify(rnd((B * Sq, H * 32), torch.float32, 1, 2.0), H, dh).to(dtype)
+    k = headify(rnd((B * Sk, H * 32), torch.float32, 2, 2.0), H, dh).to(dtype)
+    v = headify(rnd((B * Sk, H * 32), torch.float32, 3), H, dh).to(dtype)
+    Or, Og = torch.zeros(B * Sq, H * 32, dtype=dtype), torch.full((B * Sq, H * 32), float("nan"), dtype=dtype).cuda()
+    lr, lg = torch.zeros(B * H * Sq), torch.zeros(B * H * Sq).cuda()
+    Hk.mha_fwd(q, k, v, Or, lr, B, H, Sq, Sk, dh, False, None)
+    K.mha_fwd(cu(q), cu(k), cu(v), Og, lg, B, H, Sq, Sk, dh, False, None)
+    assert not torch.isnan(Og).any()
+    # per item, so that a wrong tenant of a re-used stage / scratch slot cannot hide behind a global norm
+    ai = Og.float().cpu().view(B, Sq, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
+    bi = Or.float().view(B, Sq, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
+    rel = (ai - bi).abs().amax(1) / bi.abs().amax(1).clamp_min(1e-6)
+    assert float(rel.max()) < TOL[dtype], (int(rel.argmax()), float(rel.max()))
+    assert err(lg, lr) < 1e-3
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_mha_decode(K, Hk, dtype):
     B, H, dh, Tmax, klen = 5, 10, 30, 12, 7
@@ -407,6 +432,107 @@ def test_add_ln_dual(K, Hk, dtype, p, mapped):
         assert err(dsub_g[real], dsub_r[real]) < TOL[dtype] * 2
         for i in range(2):
             assert err(dgg[i], dgr[i]) < 1e-3 and err(dbg[i], dbr[i]) < 1e-3
+
+
+def _fused_launched(K, name):
+    """the fused entry point really ran (a silent fall-back to the two-kernel path would make these tests vacuous)"""
+    return DRYRUN or any(n == name for n, *_ in K.prof)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+@pytest.mark.parametrize("M,K_,has_x", [(301 * 3, 320, True), (128, 512, True), (1000, 512, True), (77, 320, False), (13056, 320, True)])
+def test_gemm_add_ln_fused(K, Hk, monkeypatch, p, M, K_, has_x):
+    """Linear + residual + dropout + LayerNorm in one tcgen05 launch (ick_gemm_add_ln_tc) against GEMM -> add_ln on the host."""
+    monkeypatch.setenv("ICK_FUSE_LN", "1")  # the fused kernel is opt-in (kernels._ln_fusable)
+    dtype, d, ld = torch.bfloat16, 300, 320
+    A = rnd((M, K_), dtype, 1)
+    W = rnd((ld, K_), dtype, 2, 0.06)
+    W[d:] = 0  # d_model padded to 320 rows: pad rows of the packed weight are zero
+    bias = torch.cat([rnd((d,), torch.float32, 3), torch.zeros(ld - d)])
+    x = rnd((M, ld), dtype, 4) if has_x else None
+    if x is not None:
+        x[:, d:] = 0
+    gamma, beta = 1 + 0.1 * rnd((d,), torch.float32, 5), rnd((d,), torch.float32, 6)
+    drop = (p, BIG_SEED, 11) if p > 0 else None
+    sr, yr, mr, rr = torch.zeros(M, ld, dtype=dtype), torch.zeros(M, ld, dtype=dtype), torch.zeros(M), torch.zeros(M)
+    Hk.gemm_add_ln(A, W, bias, x, sr, gamma, beta, yr, mr, rr, d, drop=drop)
+    sg, yg = torch.full((M + 3, ld), 7.0, dtype=dtype).cuda(), torch.full((M + 3, ld), 7.0, dtype=dtype).cuda()  # 3 canary rows
+    mg, rg = torch.zeros(M).cuda(), torch.zeros(M).cuda()
+    K.prof = []
+    K.gemm_add_ln(cu(A), cu(W), cu(bias), cu(x), sg[:M], cu(gamma), cu(beta), yg[:M], mg, rg, d, drop=drop)
+    torch.cuda.synchronize() if not DRYRUN else None
+    assert _fused_launched(K, "ick_gemm_add_ln_tc")
+    K.prof = None
+    # the fused kernel normalises the fp32 accumulator, the host reference the bf16-rounded GEMM output: bf16 tolerance
+    assert err(sg[:M, :d], sr[:, :d]) < 2e-2 and err(yg[:M, :d], yr[:, :d]) < 2e-2
+    assert float(yg[:M, d:].abs().max()) == 0.0 and float(sg[:M, d:].abs().max()) == 0.0  # pad columns are exact zeros
+    assert float((sg[M:] - 7.0).abs().max()) == 0.0 and float((yg[M:] - 7.0).abs().max()) == 0.0  # rows behind M untouched
+    assert err(mg, mr) < 2e-2 and err(rg, rr) < 2e-2
+    # self-consistency at fp32 level: y is LayerNorm of the s the kernel stored (up to the bf16 rounding of s), with its mean / rstd
+    sf = sg[:M, :d].float()
+    mu, var = sf.mean(-1), sf.var(-1, unbiased=False)
+    assert float((mg - mu).abs().max()) < 2e-2 and err(rg, torch.rsqrt(var + 1e-5)) < 2e-2
+    y2 = (sf - mg[:, None]) * rg[:, None] * cu(gamma) + cu(beta)
+    assert err(yg[:M, :d], y2) < 2e-2
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_gemm_add_ln_fused_dual(K, Hk, monkeypatch, p):
+    """two row groups (entity rows | pad | fact rows) with their own weights, LayerNorm parameters and dropout sites"""
+    monkeypatch.setenv("ICK_FUSE_LN", "1")
+    dtype, d, ld, K_ = torch.bfloat16, 300, 320, 320
+    rows0, rows1 = 301 * 2, 51 * 2
+    m_split = (rows0 + 127) // 128 * 128
+    M = m_split + rows1
+    A = rnd((M, K_), dtype, 1)
+    Ws = [rnd((ld, K_), dtype, 2 + i, 0.06) for i in range(2)]
+    for W in Ws:
+        W[d:] = 0
+    bs = [torch.cat([rnd((d,), torch.float32, 4 + i), torch.zeros(ld - d)]) for i in range(2)]
+    x = rnd((M, ld), dtype, 6)
+    x[:, d:] = 0
+    gam = [1 + 0.1 * rnd((d,), torch.float32, 7 + i) for i in range(2)]
+    bet = [rnd((d,), torch.float32, 9 + i) for i in range(2)]
+    drops = ((p, BIG_SEED, 3), (p, BIG_SEED, 4)) if p > 0 else (None, None)
+    sr, yr, mr, rr = torch.zeros(M, ld, dtype=dtype), torch.zeros(M, ld, dtype=dtype), torch.zeros(M), torch.zeros(M)
+    Hk.gemm_add_ln_dual(A, Ws[0], Ws[1], bs[0], bs[1], x, sr, yr, mr, rr, d, m_split, rows0, gam, bet, drops)
+    sg, yg, mg, rg = torch.zeros(M, ld, dtype=dtype).cuda(), torch.zeros(M, ld, dtype=dtype).cuda(), torch.zeros(M).cuda(), torch.zeros(M).cuda()
+    K.prof = []
+    K.gemm_add_ln_dual(cu(A), cu(Ws[0]), cu(Ws[1]), cu(bs[0]), cu(bs[1]), cu(x), sg, yg, mg, rg, d, m_split, rows0, [cu(t) for t in gam],
+                       [cu(t) for t in bet], drops)
+    torch.cuda.synchronize() if not DRYRUN else None
+    assert _fused_launched(K, "ick_gemm_add_ln_tc")
+    K.prof = None
+    real = torch.cat([torch.arange(rows0), torch.arange(m_split, M)])
+    assert err(sg[real][:, :d], sr[real][:, :d]) < 2e-2 and err(yg[real][:, :d], yr[real][:, :d]) < 2e-2
+    assert err(mg[real], mr[real]) < 2e-2 and err(rg[real], rr[real]) < 2e-2
+    assert float(yg[real][:, d:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dual", [False, True])
+def test_gemm_rowdot_epilogue(K, Hk, dual):
+    """dO = dB W and the attention backward's row term rowsum(dO * O) from the GEMM epilogue (ick_gemm_tn_tc_rowdot)"""
+    dtype, H, ld, K_ = torch.bfloat16, 10, 320, 320
+    S0, S1, B = 301, 51, 3
+    rows0, rows1 = B * S0, B * S1
+    m_split = (rows0 + 127) // 128 * 128 if dual else 0
+    M = m_split + rows1 if dual else rows0
+    A, O = rnd((M, K_), dtype, 1), rnd((M, ld), dtype, 2)
+    Ws = [rnd((ld, K_), dtype, 3 + i, 0.06) for i in range(2)]
+    Cr, Cg = torch.zeros(M, ld, dtype=dtype), torch.zeros(M, ld, dtype=dtype).cuda()
+    dr = [torch.zeros(B * H * S0), torch.zeros(B * H * S1)]
+    dg = [torch.full((B * H * S0,), 9.0).cuda(), torch.full((B * H * S1,), 9.0).cuda()]
+    kw = dict(W1=Ws[1], m_split=m_split, rows0=rows0, dsum1=dr[1], S1=S1) if dual else {}
+    assert Hk.gemm_rowdot(A, Ws[0], Cr, O, dr[0], S0, H, **kw)
+    kw = dict(W1=cu(Ws[1]), m_split=m_split, rows0=rows0, dsum1=dg[1], S1=S1) if dual else {}
+    assert K.gemm_rowdot(cu(A), cu(Ws[0]), Cg, cu(O), dg[0], S0, H, **kw)
+    real = torch.cat([torch.arange(rows0), torch.arange(m_split, M)]) if dual else torch.arange(M)
+    assert err(Cg[real], Cr[real]) < 2e-2
+    for i in range(2 if dual else 1):
+        assert err(dg[i], dr[i]) < 2e-2
+    # exact agreement with the standalone row-dot over the dO the kernel itself stored (same bf16 inputs, same summation order)
+    prod = (Cg[:rows0].float() * cu(O)[:rows0].float()).view(B, S0, H, 32).sum(-1).permute(0, 2, 1).reshape(-1)
+    assert float((dg[0] - prod).abs().max()) <= 1e-5 * max(1.0, float(prod.abs().max()))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

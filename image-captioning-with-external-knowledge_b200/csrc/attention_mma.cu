@@ -504,106 +504,6 @@ __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     }
 }
 
-// Few queries per item (one 16-row slab: the beam-search decode step, Sq = beam width rows of an image against its 548-slot memory).
-// In fwd_pkernel such an item is ONE warp's work, so a CTA has `nstage` warps computing and the rest idle: the launch is bound by
-// the latency of a single warp walking all key tiles (112 us per layer against 76 us for the TMA-streamed greedy kernel, which is
-// HBM-bound).  Here the compute warps form one group of PNW_S / nstage warps per pipeline stage; the key tiles of the stage's item are
-// dealt round-robin to the warps of its group (flash-decoding split over keys inside the CTA), every warp keeps its own online
-// softmax, and warp 0 of the group merges the partial (max, sum, accumulator) triples through shared memory - the fragment layout is
-// the same in every warp, so lane i merges with lane i - and stores O / LSE.  While one group computes, the other stage's copy is in
-// flight: the kernel streams the memory K/V at HBM speed.
-constexpr int PNW_S = 18;       // compute warps of the split kernel
-constexpr int SPLIT_STAGES = 2;
-constexpr int SPLIT_REC = 20;   // floats per lane of a partial: m0, m1, l0, l1, o[4][4]
-__global__ void __launch_bounds__(32 * (PNW_S + 1), 1)
-    fwd_split_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
-                      bf16* __restrict__ O, float* __restrict__ LSE, PArgs a, int ldq, int ldo) {
-    ick_pdl_entry();
-    extern __shared__ uint8_t smem_raw[];
-    const Dims& d = a.d;
-    const Pipe pp = make_pipe<PNW_S>(smem_raw, a.ntc, a.nstage, a.stage_bytes, &tmK, &tmV);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
-    const int n_items = d.B * d.H;
-    if (warp == PNW_S) {
-        if (lane == 0) {
-            int li = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-                const int s = li % a.nstage;
-                mbar_wait(pp.empty(s), ((uint32_t)(li / a.nstage) & 1u) ^ 1u);
-                produce_item(pp, s, &tmK, &tmV, item % d.H, item / d.H);
-            }
-        }
-        return;
-    }
-    DropCfg drop;
-    drop.thr = 0u; drop.inv_keep = 1.f; drop.seed = 0u; drop.site = 0u; drop.seed_dev = nullptr;
-    const TileEnv env = make_env(d, drop, lane);
-    const int W = PNW_S / a.nstage;             // warps per group
-    const int grp = warp / W, gw = warp % W;    // this warp's group (= the stage it serves) and its rank in the group
-    float* scratch = reinterpret_cast<float*>(pp.gen + (size_t)a.nstage * a.stage_bytes);  // [nstage][W][SPLIT_REC][32]
-    int li = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
-        const int s = li % a.nstage, b = item / d.H, h = item % d.H;
-        const uint32_t ph = (uint32_t)(li / a.nstage) & 1u;
-        if (grp == s) {
-            const OwnRows r = own_rows(0, g, drop, b, d.H, h, d.Sq, true);
-            uint32_t qa[2][4];
-            load_own(Q + (size_t)b * d.Sq * ldq + h * HD, ldq, r.r0, r.r1, d.Sq, d.dh, tq, qa);
-            FwdAcc acc;
-            fwd_init(acc);
-            for (int t = gw; t < a.ntc; t += W) {
-                mbar_wait(pp.full(s, t), ph);
-                fwd_tile(acc, qa, pp.t0(s) + t * TILE_BYTES, pp.t1(s) + t * TILE_BYTES, t * TK, r, env);
-            }
-            float* grp_sc = scratch + (size_t)s * W * SPLIT_REC * 32;
-            if (gw != 0) {
-                float* mine = grp_sc + (size_t)gw * SPLIT_REC * 32 + lane;
-                mine[0] = acc.m0; mine[32] = acc.m1; mine[64] = acc.l0; mine[96] = acc.l1;
-#pragma unroll
-                for (int n = 0; n < 4; ++n)
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) mine[(4 + 4 * n + x) * 32] = acc.o[n][x];
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(W * 32) : "memory");
-            if (gw == 0) {
-                float M0 = acc.m0, M1 = acc.m1;
-                for (int w = 1; w < W; ++w) {
-                    const float* o = grp_sc + (size_t)w * SPLIT_REC * 32 + lane;
-                    M0 = fmaxf(M0, o[0]);
-                    M1 = fmaxf(M1, o[32]);
-                }
-                // the lanes of a quad hold different keys' maxima only through fwd_tile's quad reduction: m is already row-uniform
-                const float e0 = M0 == -INFINITY ? 0.f : M0 * env.c, e1 = M1 == -INFINITY ? 0.f : M1 * env.c;
-                const float f0 = ex2(acc.m0 * env.c - e0), f1 = ex2(acc.m1 * env.c - e1);
-                acc.l0 *= f0; acc.l1 *= f1;
-#pragma unroll
-                for (int n = 0; n < 4; ++n) { acc.o[n][0] *= f0; acc.o[n][1] *= f0; acc.o[n][2] *= f1; acc.o[n][3] *= f1; }
-                for (int w = 1; w < W; ++w) {
-                    const float* o = grp_sc + (size_t)w * SPLIT_REC * 32 + lane;
-                    const float g0 = ex2(o[0] * env.c - e0), g1 = ex2(o[32] * env.c - e1);
-                    acc.l0 = fmaf(o[64], g0, acc.l0);
-                    acc.l1 = fmaf(o[96], g1, acc.l1);
-#pragma unroll
-                    for (int n = 0; n < 4; ++n) {
-                        acc.o[n][0] = fmaf(o[(4 + 4 * n) * 32], g0, acc.o[n][0]);
-                        acc.o[n][1] = fmaf(o[(5 + 4 * n) * 32], g0, acc.o[n][1]);
-                        acc.o[n][2] = fmaf(o[(6 + 4 * n) * 32], g1, acc.o[n][2]);
-                        acc.o[n][3] = fmaf(o[(7 + 4 * n) * 32], g1, acc.o[n][3]);
-                    }
-                }
-                acc.m0 = M0;
-                acc.m1 = M1;
-                fwd_finish(acc, O + (size_t)b * d.Sq * ldo + h * HD, ldo, LSE + ((size_t)b * d.H + h) * d.Sq, r, env);
-            }
-        }
-        // every warp passes through every item in order (see fwd_pkernel).  The group's scratch is safe: its next item can only be
-        // produced after ALL compute warps - the merging warp included - have released this one.
-        mbar_wait(pp.full(s, 0), ph);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pp.empty(s));
-    }
-}
-
 template <int PNW>
 __global__ void __launch_bounds__(32 * (PNW + 1), 1)
     bwd_dq_pkernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const bf16* __restrict__ Q,
@@ -876,14 +776,6 @@ int num_sms() {
     }
     return n;
 }
-bool split_keys() {  // ICK_ATTN_SPLIT=0: few-query items stay on fwd_pkernel (A/B aid)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("ICK_ATTN_SPLIT");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
 bool wide_q() {  // ICK_ATTN_QWARPS=19 selects the 19-warp forward / dQ kernels (96 registers per thread; measured 1.4% slower per step than 15 warps x 128 registers)
     static int v = -1;
     if (v < 0) {
@@ -963,18 +855,6 @@ int ick_mha_fwd_mma(const void* Q, const void* K, const void* V, void* O, float*
     pa.d = d;
     pa.nslabs = (Sq + 15) / 16;
     plan_pipe(nt, false, &pa);
-    if (pa.nstage >= SPLIT_STAGES && use_persistent() && pa.nslabs == 1 && !causal && nt >= 4 && dc.thr == 0u && split_keys()) {
-        // one slab of queries per item (beam-search decode): split the item's key tiles over a group of warps
-        pa.nstage = SPLIT_STAGES;
-        const int smem = pipe_smem(pa) + SPLIT_STAGES * (PNW_S / SPLIT_STAGES) * SPLIT_REC * 32 * 4;
-        if (smem <= SMEM_MAX) {
-            const int grid = B * H < num_sms() ? B * H : num_sms();
-            if ((rc = set_smem(fwd_split_pkernel, true))) return rc;
-            ick_launch(fwd_split_pkernel, grid, 32 * (PNW_S + 1), smem, stream)(tmK, tmV, (const bf16*)Q, (bf16*)O, lse, pa, ldq, ldo);
-            return ick_check_launch("mha_fwd_mma(split keys)");
-        }
-        plan_pipe(nt, false, &pa);
-    }
     if (pa.nstage && use_persistent()) {
         const int grid = B * H < num_sms() ? B * H : num_sms();
         if (wide_q()) {

@@ -883,19 +883,23 @@ __global__ void __launch_bounds__(256) wgrad_group_reduce_kernel(const __grid_co
     if (ro < 0 || k >= p.K) return;
     const float* src = p.ws + (size_t)n * p.Kws + k;
     const size_t stride = (size_t)p.N * p.Kws;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     int sp = 0;
-    for (; sp + 1 < p.splits; sp += 2) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride);
+    for (; sp + 3 < p.splits; sp += 4) {  // four partial tiles in flight per thread (the kernel is latency-bound: ~1 TB/s with two)
+        const float4 v0 = *(reinterpret_cast<const float4*>(src + (size_t)sp * stride));
+        const float4 v1 = *(reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride));
+        const float4 v2 = *(reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * stride));
+        const float4 v3 = *(reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * stride));
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
     }
-    if (sp < p.splits) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+    for (; sp < p.splits; ++sp) {
+        const float4 v0 = *(reinterpret_cast<const float4*>(src + (size_t)sp * stride));
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
     }
-    const float r[4] = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w};
+    const float r[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w)};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (k + j >= p.K) break;

@@ -383,21 +383,23 @@ __global__ void __launch_bounds__(256) beam_row_topk_kernel(const float* __restr
 }
 
 // stage 1, register-resident variant for rows of at most TK_NT * TK_NPT columns (every shape of the reference): the whole row sits in
-// registers (all loads independent and in flight at once), the log-sum-exp is two branch-free passes over them, and each of the G
-// selection rounds is a branch-free thread-local argmax + a block argmax; the winning thread blanks its element.  The scan kernel
-// above keeps a sorted top-G list per thread, and with 40 elements per thread some lane of a warp inserts at almost every element:
-// the warp runs the divergent insertion path for the whole row (134 us per launch at 3125 rows x 10352 columns).  Same total order
-// (value descending, column ascending), hence the same candidates.
+// registers (all loads independent and in flight at once).  Every warp reduces its own columns: (max, sum of exponentials at that max)
+// and its G best columns by G rounds of a branch-free thread-local argmax + a warp argmax (the winning lane blanks its element) - no
+// block barrier inside the rounds; after ONE barrier warp 0 folds the per-warp pairs into log Z and takes the G best of the
+// NW * G warp candidates.  (The first version ran the G rounds block-wide: 14 barriers with serial thread-0 folds per row, 100 us
+// per launch at 3125 rows x 10352 columns = 1.3 TB/s.)  The scan kernel above keeps a sorted top-G list per thread, and with 40
+// elements per thread some lane of a warp inserts at almost every element: the warp runs the divergent insertion path for the whole
+// row (134 us per launch).  Same total order (value descending, column ascending), hence the same candidates.
 constexpr int TK_NT = 512, TK_NPT = 24;
 template <int G>
 __global__ void __launch_bounds__(TK_NT) beam_row_topk_reg_kernel(const float* __restrict__ scores, int W, int lds, const float* __restrict__ cum,
                                                                   const int* __restrict__ ksel, float* __restrict__ cand_v,
                                                                   int* __restrict__ cand_i, int step) {
     ick_pdl_entry();
-    __shared__ float red_a[TK_NT / 32], red_v[TK_NT / 32];
-    __shared__ int red_i[TK_NT / 32];
-    __shared__ float s_bcast;
-    __shared__ int s_win;
+    constexpr int NW = TK_NT / 32;
+    __shared__ float red_m[NW], red_l[NW];
+    __shared__ float wv[NW * G];
+    __shared__ int wi[NW * G];
     const int row = blockIdx.x, img = row / G, j = row % G, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = ksel[img];
     if (k <= 0 || j >= (step == 0 ? 1 : k)) return;  // not a live beam
@@ -408,33 +410,20 @@ __global__ void __launch_bounds__(TK_NT) beam_row_topk_reg_kernel(const float* _
         const int c = tid + u * TK_NT;
         xs[u] = c < W ? s[c] : -INFINITY;
     }
+    // log-sum-exp: per-warp (max, sum at that max), one barrier, then every warp folds the NW pairs itself (no serial thread-0 loop)
     float tm = xs[0];
 #pragma unroll
     for (int u = 1; u < TK_NPT; ++u) tm = fmaxf(tm, xs[u]);
     tm = warp_max(tm);
-    if (lane == 0) red_a[wid] = tm;
-    __syncthreads();
-    if (tid == 0) {
-        float M = red_a[0];
-        for (int w = 1; w < TK_NT / 32; ++w) M = fmaxf(M, red_a[w]);
-        s_bcast = M;
-    }
-    __syncthreads();
-    const float M = s_bcast;
     float ts = 0.f;
+    if (tm != -INFINITY) {
 #pragma unroll
-    for (int u = 0; u < TK_NPT; ++u) ts += expf(xs[u] - M);  // exp(-inf) = 0 for the slots past the row
-    ts = warp_sum(ts);
-    __syncthreads();  // everybody has read s_bcast / thread 0 has read red_a
-    if (lane == 0) red_a[wid] = ts;
-    __syncthreads();
-    if (tid == 0) {
-        float L = 0.f;
-        for (int w = 0; w < TK_NT / 32; ++w) L += red_a[w];
-        s_bcast = M + logf(L);
+        for (int u = 0; u < TK_NPT; ++u) ts += __expf(xs[u] - tm);  // ex2.approx (the kernel is issue-bound); exp(-inf) = 0 past the row
     }
-    __syncthreads();
-    const float logz = s_bcast, cj = cum[row];
+    ts = warp_sum(ts);
+    if (lane == 0) { red_m[wid] = tm; red_l[wid] = ts; }
+    // the G best of this warp's columns, in order (value descending, column ascending): thread-local argmax + warp argmax per round,
+    // the winning lane blanks its element.  No block barrier inside the rounds.
     for (int r = 0; r < G; ++r) {
         float bv = xs[0];
         int bu = 0;
@@ -450,21 +439,49 @@ __global__ void __launch_bounds__(TK_NT) beam_row_topk_reg_kernel(const float* _
             const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
             if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
         }
-        if (lane == 0) { red_v[wid] = v; red_i[wid] = i; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < TK_NT / 32; ++w)
-                if (red_v[w] > v || (red_v[w] == v && red_i[w] < i)) { v = red_v[w]; i = red_i[w]; }
-            s_win = i;
-            cand_v[(size_t)row * G + r] = i == 0x7fffffff ? -INFINITY : cj + (v - logz);
-            cand_i[(size_t)row * G + r] = i == 0x7fffffff ? i : j * W + i;
-        }
-        __syncthreads();
-        if (bi == s_win && bi != 0x7fffffff) {
+        if (lane == 0) { wv[wid * G + r] = v; wi[wid * G + r] = i; }
+        if (bi == i && bi != 0x7fffffff) {
 #pragma unroll
             for (int u = 0; u < TK_NPT; ++u)
                 if (u == bu) xs[u] = -INFINITY;
         }
+    }
+    __syncthreads();
+    if (wid != 0) return;
+    // warp 0: log Z from the NW pairs, then the G best of the NW * G warp candidates (every global winner is among them)
+    float m = lane < NW ? red_m[lane] : -INFINITY;
+    const float M = warp_max(m);
+    float l = (lane < NW && m != -INFINITY) ? red_l[lane] * expf(m - M) : 0.f;
+    l = warp_sum(l);
+    const float logz = M + logf(l), cj = cum[row];
+    constexpr int CPL = (NW * G + 31) / 32;  // candidates per lane
+    float cv[CPL];
+    int ci[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+        const int idx = lane + 32 * q;
+        cv[q] = idx < NW * G ? wv[idx] : -INFINITY;
+        ci[q] = idx < NW * G ? wi[idx] : 0x7fffffff;
+    }
+    for (int r = 0; r < G; ++r) {
+        float v = cv[0];
+        int i = ci[0];
+#pragma unroll
+        for (int q = 1; q < CPL; ++q)
+            if (cv[q] > v || (cv[q] == v && ci[q] < i)) { v = cv[q]; i = ci[q]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+        if (lane == 0) {
+            cand_v[(size_t)row * G + r] = i == 0x7fffffff ? -INFINITY : cj + (v - logz);
+            cand_i[(size_t)row * G + r] = i == 0x7fffffff ? i : j * W + i;
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            if (ci[q] == i && i != 0x7fffffff) { cv[q] = -INFINITY; ci[q] = 0x7fffffff; }
     }
 }
 

@@ -6,6 +6,8 @@
 // mask(t,s) = first_t[b,s] < t + lag for the fact head (the indicator multiplies fc_fact's INPUT, so the bias survives), 1 for
 // the entity head.  Operand tiles are staged in shared memory with row strides that are odd multiples of 16 bytes, which makes
 // every ldmatrix conflict-free; (mask*dS)^T is never materialised - its A fragments come from ldmatrix.trans of the dS tile.
+#include <stdlib.h>
+
 #include "mma.cuh"
 #include "pointer_internal.h"
 
@@ -301,10 +303,117 @@ int set_smem(K kernel) {
     return ICK_OK;
 }
 
+// Single greedy decode step (one row per image): scores[b, col0 + s] = bias + mask * sum_d (h[b, d] w[d]) ctx[b, s, d].  Per step every
+// image re-reads all of its context rows (120 MB for 625 images x 301 entities) against two FLOPs per element, so this is a
+// streaming matrix-vector product: 8 lanes share a 640-byte ctx row (consecutive lanes read consecutive 16-byte chunks), a thread
+// requests all ten of its chunks (two rows) before the first use, the query vector h * w sits in shared memory in fp32, and an
+// 8-lane shuffle tree finishes each row's dot product.  The tensor-core kernel above stages 64 rows through shared memory behind a
+// barrier for a 16 x 64 x 320 product of which one row is real (2 TB/s, 36 us per launch); this one is +2.9 % on the whole greedy
+// decode (24.0k vs 23.3k captions/s, profiles/README.md r02h).  For the G = 5 beam rows of an image the staged tensor-core kernel
+// is the faster one (38 vs 63 us per launch), so beam search keeps it; the template parameter stays for that measurement.
+constexpr int PS_W = 320;    // row width in elements (d_model padded): 40 chunks of 8
+constexpr int PS_ROWS = 64;  // ctx rows per CTA: 8 warps x 4 rows x 2 passes
+template <int G>
+__global__ void __launch_bounds__(NT, 3) pointer_step_kernel(const bf16* __restrict__ h, const bf16* __restrict__ ctx, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const int* __restrict__ first_t,
+                                                          float* __restrict__ scores, int t0, int S, int D, int lds, int col0, int lag,
+                                                          int beams) {
+    ick_pdl_entry();
+    __shared__ __align__(16) float hw[G][PS_W];
+    const int b = blockIdx.y, s0 = blockIdx.x * PS_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l8 = lane & 7, rq = lane >> 3;
+    // this thread's ctx chunks first: they are independent of hw and by far the longest latency
+    uint4 v[2][5];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sr = s0 + pass * 32 + warp * 4 + rq;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[pass][i] = sr < S ? __ldg(reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + sr) * PS_W) + l8 + 8 * i) : zero4();
+    }
+    for (int idx = threadIdx.x; idx < G * PS_W; idx += NT) {
+        const int g = idx / PS_W, c = idx % PS_W;
+        hw[g][c] = c < D ? __bfloat162float(h[((size_t)b * G + g) * PS_W + c]) * __ldg(w + c) : 0.f;
+    }
+    __syncthreads();
+    const float bv = bias[0];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int sr = s0 + pass * 32 + warp * 4 + rq;
+        float acc[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&v[pass][i]);
+            float x[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(pr[k]);
+                x[2 * k] = f.x;
+                x[2 * k + 1] = f.y;
+            }
+            const int c0 = (l8 + 8 * i) * 8;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 a = *reinterpret_cast<const float4*>(&hw[g][c0]);
+                const float4 c = *reinterpret_cast<const float4*>(&hw[g][c0 + 4]);
+                acc[g] = fmaf(x[0], a.x, acc[g]); acc[g] = fmaf(x[1], a.y, acc[g]); acc[g] = fmaf(x[2], a.z, acc[g]); acc[g] = fmaf(x[3], a.w, acc[g]);
+                acc[g] = fmaf(x[4], c.x, acc[g]); acc[g] = fmaf(x[5], c.y, acc[g]); acc[g] = fmaf(x[6], c.z, acc[g]); acc[g] = fmaf(x[7], c.w, acc[g]);
+                // keeps the compiler from hoisting all 2 * 5 * G shared-memory loads of a pass above the arithmetic (254 registers,
+                // one CTA per SM: too few bytes in flight); the ctx chunks in v[][] are registers and are not affected
+                asm volatile("" ::: "memory");
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 1);
+            acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 2);
+            acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 4);
+        }
+        if (l8 == 0 && sr < S) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const bool on = first_t == nullptr || (beams ? first_t[((size_t)b * G + g) * S + sr] < t0 + lag : first_t[(size_t)b * S + sr] < t0 + g + lag);
+                scores[((size_t)b * G + g) * lds + col0 + sr] = (on ? acc[g] : 0.f) + bv;
+            }
+        }
+    }
+}
+
+bool ptr_step() {  // ICK_PTR_STEP=0: single-step pointer heads stay on the staged tensor-core kernel (A/B aid)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ICK_PTR_STEP");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 }  // namespace
 
 int ick_pointer_fwd_mma(const void* h, const void* ctx, const float* w, const float* bias, const int* first_t, float* scores, int B, int Tn,
                         int t0, int S, int D, int ld, int ldscores, int col0, int lag, int beams, cudaStream_t stream) {
+    static const bool step_beams = getenv("ICK_PTR_STEP_BEAMS") != nullptr;  // A/B aid: the streaming kernel for beam rows too
+    if (Tn <= 8 && (Tn == 1 || (beams && step_beams)) && ld == PS_W && D <= PS_W && ptr_step() && (((uintptr_t)h | (uintptr_t)ctx) & 15) == 0) {
+        dim3 gs((S + PS_ROWS - 1) / PS_ROWS, B);
+#define ICK_PS_CASE(GG)                                                                                                                 \
+    case GG:                                                                                                                            \
+        ick_launch(pointer_step_kernel<GG>, gs, NT, 0, stream)((const bf16*)h, (const bf16*)ctx, w, bias, first_t, scores, t0, S, D, ldscores, col0, \
+                                                               lag, beams);                                                             \
+        break;
+        switch (Tn) {
+            ICK_PS_CASE(1)
+            ICK_PS_CASE(2)
+            ICK_PS_CASE(3)
+            ICK_PS_CASE(4)
+            ICK_PS_CASE(5)
+            ICK_PS_CASE(6)
+            ICK_PS_CASE(7)
+            ICK_PS_CASE(8)
+        }
+#undef ICK_PS_CASE
+        return ick_check_launch("pointer_fwd(step)");
+    }
     const int Tp = (Tn + 15) / 16 * 16, KP = (D + 15) / 16 * 16;
     const size_t smem = (size_t)(Tp + CW) * (KP + 8) * 2;
     if (KP > ld || ld % 8 != 0 || smem > SMEM_MAX || (((uintptr_t)h | (uintptr_t)ctx) & 15) != 0) return ICK_ERR_UNSUPPORTED;

@@ -319,13 +319,10 @@ def test_mha_bwd_fused_many_items(K, Hk, att_mode, p, B, H, Sq, Sk, dh, causal):
         assert float(rel.max()) < TOL[dtype] * 3, (name, int(rel.argmax()), float(rel.max()))
 
 
-@pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("B,H,Sq,Sk,dh", [(40, 10, 5, 548, 30), (7, 10, 5, 598, 30), (33, 10, 3, 300, 30), (9, 10, 16, 548, 30), (400, 10, 1, 257, 30)])
-def test_mha_fwd_few_queries_split_keys(K, Hk, monkeypatch, split, B, H, Sq, Sk, dh):
-    """One 16-row slab of queries per (image, head) item - the beam-search decode step's cross-attention (Sq = beam width) - runs on
-    the split-key kernel (fwd_split_pkernel: the item's key tiles dealt to a group of warps, partial softmaxes merged in shared
-    memory); ICK_ATTN_SPLIT=0 is the one-warp-per-item path it replaces.  More items than CTAs: stages and scratch are re-used."""
-    monkeypatch.setenv("ICK_ATTN_SPLIT", split)
+def test_mha_fwd_few_queries_many_items(K, Hk, monkeypatch, B, H, Sq, Sk, dh):
+    """One 16-row slab of queries per (image, head) item - the beam-search decode step's cross-attention (Sq = beam width) - with more
+    items than CTAs, so that pipeline stages are re-used; checked per item."""
     monkeypatch.setenv("ICK_ATTN_FWD", "mma")
     dtype = torch.bfloat16
     q = headify(rnd((B * Sq, H * 32), torch.float32, 1, 2.0), H, dh).to(dtype)
@@ -336,7 +333,6 @@ def test_mha_fwd_few_queries_split_keys(K, Hk, monkeypatch, split, B, H, Sq, Sk,
     Hk.mha_fwd(q, k, v, Or, lr, B, H, Sq, Sk, dh, False, None)
     K.mha_fwd(cu(q), cu(k), cu(v), Og, lg, B, H, Sq, Sk, dh, False, None)
     assert not torch.isnan(Og).any()
-    # per item, so that a wrong tenant of a re-used stage / scratch slot cannot hide behind a global norm
     ai = Og.float().cpu().view(B, Sq, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
     bi = Or.float().view(B, Sq, H, 32).permute(0, 2, 1, 3).reshape(B * H, -1)
     rel = (ai - bi).abs().amax(1) / bi.abs().amax(1).clamp_min(1e-6)

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-R=${R:-r02c}
+R=${R:-r02i}
 (timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 600 2>&1 | tail -n 40) > gpurun_out/${R}_tests.log
 (timeout 600 python bench.py --steps 50 --warmup 3 2> gpurun_out/${R}_bench.err | tail -n 1) > gpurun_out/${R}_bench.json
 (timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> gpurun_out/${R}_bench.err | tail -n 1) > gpurun_out/${R}_bench_reference_arm.json

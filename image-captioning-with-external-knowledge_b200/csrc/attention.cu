@@ -687,6 +687,11 @@ extern "C" int ick_mha_decode_beam(const void* Q, const void* K, const void* V, 
     ICK_REQUIRE(anc == nullptr || anc_ld >= klen, "mha_decode_beam: ancestor table narrower than klen");
     const uintptr_t al = dt == ICK_F32 ? 31 : 15;
     ICK_REQUIRE(((((uintptr_t)Q) | ((uintptr_t)K) | ((uintptr_t)V) | ((uintptr_t)O)) & al) == 0, "mha_decode_beam: misaligned operand");
+    if (dt == ICK_BF16 && anc == nullptr && (const bf16*)V == (const bf16*)K + H * HD && ldk == ldv && kimg_stride == vimg_stride) {
+        // shared keys with contiguous K|V rows (the cross-attention over the memory): tensor-core kernel fed by whole-row TMA copies
+        const int rc = ick_mha_decode_tma_mma(Q, K, O, rows / group, group, H, dh, ldq, ldk, ldo, kimg_stride, klen, stream);
+        if (rc != ICK_ERR_UNSUPPORTED) return rc;
+    }
     if (dt == ICK_F32)
         return launch_decode_beam((const float*)Q, (const float*)K, (const float*)V, (float*)O, rows, group, H, dh, ldq, ldk, ldv, ldo,
                                   kimg_stride, vimg_stride, klen, anc, anc_ld, kpos_stride, vpos_stride, stream);

@@ -26,3 +26,6 @@ int ick_mha_bwd_tc(const void* Q, const void* K, const void* V, const void* O, c
 // attention_decode_tma.cu: TMA-staged per-step cross-attention of the decode loop (contiguous K|V rows only; else ICK_ERR_UNSUPPORTED)
 int ick_mha_decode_tma(const void* Q, const void* KV, void* O, int B, int H, int dh, int ldq, int ldkv, int ldo, long long batch_stride,
                        int klen, cudaStream_t stream);
+// the G <= 8 beams of an image against its memory K|V on the tensor cores, whole rows streamed by TMA (same contiguity rule)
+int ick_mha_decode_tma_mma(const void* Q, const void* KV, void* O, int images, int G, int H, int dh, int ldq, int ldkv, int ldo,
+                           long long img_stride, int klen, cudaStream_t stream);

@@ -64,11 +64,20 @@ __global__ void __launch_bounds__(NT) pointer_fwd_mma_kernel(const bf16* __restr
         }
         *reinterpret_cast<uint4*>(hw + (size_t)t * PLD + c) = out;
     }
-    for (int idx = threadIdx.x; idx < CW * kc; idx += NT) {
-        const int s = idx / kc, c = (idx % kc) * 8;
-        uint4 v = zero4();
-        if (s0 + s < S) v = *reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s0 + s) * ld + c);
-        *reinterpret_cast<uint4*>(cs + (size_t)s * PLD + c) = v;
+    // ctx rows of the slot tile: four 16-byte chunks per thread requested before the first shared-memory store (one load per trip
+    // left the staging latency-bound: 2 TB/s on the 64-row tiles of a decode step)
+    for (int idx0 = threadIdx.x; idx0 < CW * kc; idx0 += 4 * NT) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * NT, s = idx / kc, c = (idx % kc) * 8;
+            v[u] = (idx < CW * kc && s0 + s < S) ? __ldg(reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s0 + s) * ld + c)) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * NT, s = idx / kc, c = (idx % kc) * 8;
+            if (idx < CW * kc) *reinterpret_cast<uint4*>(cs + (size_t)s * PLD + c) = v[u];
+        }
     }
     __syncthreads();
     const float bv = bias[0];

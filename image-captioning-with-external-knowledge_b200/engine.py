@@ -767,7 +767,10 @@ class DecoderEngine:
         x0 = self._new(R, DP)
         bufs = [NS(o=self._new(R, DP), s=self._new(R, DP), y1=self._new(R, DP), q=self._new(R, DP), y2=self._new(R, DP),
                    h1=self._new(R, self.lin[f"transformer_decoder.layers.{l}.ffn1"].lin.Np), y3=self._new(R, DP)) for l in range(L)]
-        xattn_flash = os.environ.get("ICK_BEAM_XATTN", "flash") == "flash" and self.dtype != torch.float32
+        # cross-attention of the G beams of an image: "tma" (default) = ick_mha_decode_beam, which runs shared contiguous K|V rows on the
+        # TMA-streamed tensor-core kernel (csrc/attention_decode_tma.cu); "flash" = the G beams as G query positions of one
+        # flash-attention item per (image, head) (the round-1 path: per-head TMA boxes, 4 TB/s)
+        xattn_flash = os.environ.get("ICK_BEAM_XATTN", "tma") == "flash" and self.dtype != torch.float32
         lse = self._newf(NI * H * G)
         cand = self._newf(R * G * 2)  # per-row candidate lists of beam_select
         fused = self._decode_fused()

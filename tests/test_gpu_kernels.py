@@ -975,6 +975,39 @@ def test_mha_decode_tma_streaming_path(K, Hk, klen):
     assert err(Og, O2) < 1e-2
 
 
+@pytest.mark.parametrize("G", [5, 1, 3, 8])
+@pytest.mark.parametrize("klen,NI", [(548, 37), (598, 9), (65, 330), (80, 5), (257, 64)])
+def test_mha_decode_beam_tma_tensor_core_path(K, Hk, G, klen, NI):
+    """Beam-search step cross-attention: the G beams of an image against its contiguous memory K|V rows run on the TMA-streamed
+    tensor-core kernel (mha_decode_tma_mma_kernel: bf16, more than 64 cached positions).  Against the host restatement, per row (a
+    wrong stage tenant or a broken fragment layout corrupts single rows / heads), with canaries around the output, and against the
+    CUDA-core kernel on a copy with a padded stride."""
+    H, dh = 10, 30
+    R = NI * G
+    ldkv = 2 * H * 32
+    dtype = torch.bfloat16
+    kv = headify(rnd((NI * klen, ldkv), torch.float32, 21, 1.5), 2 * H, dh).to(dtype)
+    q = headify(rnd((R, H * 32), torch.float32, 22, 1.5), H, dh).to(dtype)
+    Or = torch.zeros(R, H * 32, dtype=dtype)
+    Hk.mha_decode_beam(q, kv[:, : H * 32], kv[:, H * 32 :], Or, R, G, H, dh, klen, kimg_stride=klen * ldkv, vimg_stride=klen * ldkv)
+    kg, qg = cu(kv), cu(q)
+    guard = torch.full((R + 2, H * 32 + 16), 7.0, dtype=dtype, device=DEV)
+    Og = guard[1 : R + 1, : H * 32]
+    K.mha_decode_beam(qg, kg[:, : H * 32], kg[:, H * 32 :], Og, R, G, H, dh, klen, kimg_stride=klen * ldkv, vimg_stride=klen * ldkv)
+    assert not torch.isnan(Og.float()).any()
+    ai, bi = Og.float().cpu().view(R * H, 32), Or.float().view(R * H, 32)
+    rel = (ai - bi).abs().amax(1) / bi.abs().amax(1).clamp_min(1e-6)
+    assert float(rel.max()) < TOL[dtype], (int(rel.argmax()), float(rel.max()))
+    assert float(Og.float().view(R, H, 32)[:, :, dh:].abs().max()) == 0.0  # pad lanes of every head stay zero
+    assert bool((guard[0] == 7).all()) and bool((guard[-1] == 7).all()) and bool((guard[:, H * 32 :] == 7).all())
+    wide = torch.zeros(NI * klen, ldkv + 64, dtype=dtype, device=DEV)  # same rows, padded stride -> the CUDA-core kernel
+    wide[:, :ldkv] = kg
+    O2 = torch.zeros(R, H * 32, dtype=dtype, device=DEV)
+    K.mha_decode_beam(qg, wide[:, : H * 32], wide[:, H * 32 : ldkv], O2, R, G, H, dh, klen, kimg_stride=klen * (ldkv + 64),
+                      vimg_stride=klen * (ldkv + 64))
+    assert err(Og, O2) < 1e-2
+
+
 @pytest.mark.parametrize("rows", [625, 37, 16])
 @pytest.mark.parametrize("ffn,proj_n", [(False, 320), (True, 960), (True, 0)])
 def test_decode_chain(K, Hk, rows, ffn, proj_n):

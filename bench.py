@@ -695,6 +695,36 @@ def run_ours(a):
                     "note": "extension without a reference counterpart (SURVEY.md §0): Show-Attend-Tell tutorial beam search over the "
                             "KV-cached decoder, device-resident; parity against oracle/decoder_oracle.py:beam_search and captions "
                             "scored by the unmodified reference modules (tests/golden/golden_beam_*.npz)"}
+            # the beam step's cross-attention kernel alone (5 query rows per image against the image's memory K|V of one layer)
+            try:
+                eng = dec._ensure_engine()
+                Md, DPd, Hd, Gb = dcfg.M, eng.DP, eng.H, 5
+                kvb = torch.randn(n_img * Md, 2 * DPd, device=dev).to(torch.bfloat16)
+                qb = torch.randn(n_img * Gb, DPd, device=dev).to(torch.bfloat16)
+                ob = torch.empty_like(qb)
+                call = lambda: eng.K.mha_decode_beam(qb, kvb[:, :DPd], kvb[:, DPd:], ob, n_img * Gb, Gb, Hd, eng.dh, Md,  # noqa: E731
+                                                     kimg_stride=Md * 2 * DPd, vimg_stride=Md * 2 * DPd)
+                for _ in range(3):
+                    call()
+                nrep = 20
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ea.record()
+                for _ in range(nrep):
+                    call()
+                eb.record()
+                torch.cuda.synchronize()
+                t_ms = ea.elapsed_time(eb) / nrep
+                abytes = kvb.numel() * 2 + 2 * qb.numel() * 2
+                pkd = peaks()
+                beam["roofline_step_attention"] = {
+                    "kernel": "ick_mha_decode_beam (TMA-streamed whole K|V rows, one warp per head on mma.sync, 5 beams per image)",
+                    "bound": "hbm", "achieved": abytes / (t_ms / 1e3) / 1e9, "peak": pkd["hbm"], "unit": "GB/s",
+                    "frac": abytes / (t_ms / 1e3) / 1e9 / pkd["hbm"], "avg_launch_ms": t_ms, "algorithmic_bytes_per_launch": abytes,
+                    "peak_source": pkd["src"], "launches_per_step": eng.L, "note": "timed alone, back to back, inputs larger than L2"}
+                del kvb, qb, ob
+            except Exception as e:
+                beam["roofline_step_attention"] = {"error": f"{type(e).__name__}: {e}"}
             dec.train()
         except Exception as e:  # the decode figures are extras; never lose the train line over them
             if decode is None:

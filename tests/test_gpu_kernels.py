@@ -926,6 +926,41 @@ def test_beam_select_state_machine(K, Hk, G):
     assert int((state["r"]["ksel"] < G).sum()) > 0 and torch.isfinite(state["r"]["best"]).all()
 
 
+@pytest.mark.parametrize("kind", ["normal", "quantised", "constant", "short"])
+def test_beam_row_topk_candidates_at_full_width(K, kind):
+    """Stage 1 of beam_select at the reference's score width (10 352 columns, the register-resident kernel): the per-row candidate
+    lists (value = cum + log_softmax, column) must be the row's G best in the order (value descending, column ascending).  "quantised"
+    and "constant" rows are full of ties: the per-warp threshold lists overflow and the kernel must take its full-rounds path."""
+    if DRYRUN:
+        pytest.skip("reads the kernel's workspace layout")
+    G, NI, Tmax, V, E = 5, 6, 4, 10000, 301
+    Wd = 10352 if kind != "short" else 700
+    R = NI * G
+    sc = rnd((R, Wd), torch.float32, 77, 3.0)
+    if kind == "quantised":
+        sc = torch.round(sc * 2) / 2
+    elif kind == "constant":
+        sc = torch.full((R, Wd), 1.25)
+        sc[3, 77] = 1.5
+    cum = rnd((R,), torch.float32, 78)
+    own = (torch.arange(R, dtype=torch.int32) % G).unsqueeze(1).expand(R, Tmax).contiguous()
+    tok = [torch.full((R, Tmax), 28, dtype=torch.int64, device=DEV) for _ in range(2)]
+    msk = [torch.zeros(R, Tmax, dtype=torch.int64, device=DEV) for _ in range(2)]
+    anc = [own.clone().to(DEV) for _ in range(2)]
+    ws = torch.zeros(R * G * 2, dtype=torch.float32, device=DEV)
+    K.beam_select(cu(sc), Wd, cu(cum).clone(), torch.full((NI,), G, dtype=torch.int32, device=DEV), tok[0], msk[0], tok[1], msk[1], anc[0], anc[1],
+                  torch.full((NI,), float("-inf"), device=DEV), torch.zeros(NI, Tmax, dtype=torch.int64, device=DEV), NI, G, 1, Tmax, V, E, True,
+                  V - 1, 0, workspace=ws)
+    cand_v = ws[: R * G].cpu().view(R, G)
+    cand_i = ws[R * G :].cpu().view(torch.int32).view(R, G)
+    lp = torch.log_softmax(sc.double(), dim=1)
+    order = torch.sort(-sc, dim=1, stable=True).indices[:, :G]  # value descending, ties by ascending column
+    want_i = order + (torch.arange(R) % G).unsqueeze(1) * Wd
+    want_v = (cum.double().unsqueeze(1) + lp.gather(1, order)).float()
+    assert torch.equal(cand_i.long(), want_i), kind
+    assert torch.allclose(cand_v, want_v, atol=2e-5, rtol=1e-6)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_image_prep_matches_the_reference_host_pipeline(K, dtype, channels_last):

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-R=${R:-r02m}
+R=${R:-r02n}
 (timeout 400 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -x --timeout 300 -k "beam" 2>&1 | tail -n 15) > gpurun_out/${R}_kernels.log
 tail -n 8 gpurun_out/${R}_kernels.log
 (timeout 600 python -m pytest tests/test_gpu_model.py -m gpu -q --tb=short -x --timeout 500 -k "beam" 2>&1 | tail -n 15) > gpurun_out/${R}_model.log

@@ -17,12 +17,14 @@ bf = torch.bfloat16
 A = torch.randn(M, Kd, device="cuda").to(bf)
 W = (torch.randn(N, Kd, device="cuda") * 0.05).to(bf)
 C = torch.empty(M, N, device="cuda", dtype=bf)
-bias = torch.randn(N, device="cuda")
+bias = None if "nobias" in sys.argv else torch.randn(N, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+NOFLUSH = "noflush" in sys.argv  # keep L2 warm (operands and bias resident, as inside the step)
 buf = (ctypes.c_ulonglong * 8192)()
 zero = torch.zeros(1)
 for it in range(4):
-    flush.zero_()
+    if not NOFLUSH:
+        flush.zero_()
     torch.cuda.synchronize()
     K.gemm(A, W, C, bias=bias)
     torch.cuda.synchronize()

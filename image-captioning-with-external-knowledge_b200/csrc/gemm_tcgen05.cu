@@ -317,6 +317,10 @@ struct TileIter {
     }
 };
 
+// KIND >= 0: the epilogue switches are compile-time constants - bits 0-1 epilogue kind, bit 2 accumulate, bit 3 fp32 output, bulk
+// stores through the staging boxes; the per-role timeline showed ~200 of an epilogue chunk's ~1 150 cycles in uniform branches over
+// the kinds that do not apply.  KIND = -1: everything read from the parameter block (unaligned outputs, rare combinations).
+template <int KIND>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW,
                                                                   const __grid_constant__ CUtensorMap tmW2,
@@ -397,14 +401,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
         const int half = (warp - 2) >> 2;  // which of the two warps of the quadrant: even / odd 32-column chunks
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool c_al = (p.ldc % (p.c_f32 ? 4 : 8) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+        const int k_epi = KIND >= 0 ? (KIND & 3) : p.epi;
+        const bool k_acc = KIND >= 0 ? ((KIND >> 2) & 1) != 0 : p.accumulate != 0;
+        const bool k_f32 = KIND >= 0 ? ((KIND >> 3) & 1) != 0 : p.c_f32 != 0;
+        const bool k_tma = KIND >= 0 ? true : p.tma_store != 0;
+        const bool c_al = (p.ldc % (k_f32 ? 4 : 8) == 0) && ((((uintptr_t)p.C) & 15) == 0);
         const bool aux_al = p.aux != nullptr && (p.ldaux % 8 == 0) && ((((uintptr_t)p.aux) & 15) == 0);
         const bool bias_al = p.bias != nullptr && ((((uintptr_t)p.bias) & 15) == 0) && ((((uintptr_t)p.bias2) & 15) == 0);
         // Bulk-store path: each warp owns NSBOX staging boxes of [32 rows x 32 columns] behind the operand stages (64-byte rows
         // swizzled 64B for bf16, 128-byte rows swizzled 128B for fp32; lane r writes row r, so each 16-byte chunk column is
         // bank-conflict free); one lane issues the TMA store of a finished box and the warp goes on with its next chunk.  Stores
         // issued by the warps themselves (row per lane, or transposed through shared memory) measured 35-40% slower.
-        const uint32_t sbox = p.c_f32 ? 4096u : 2048u;
+        const uint32_t sbox = k_f32 ? 4096u : 2048u;
         const uint32_t stg = s.a(0) + (uint32_t)p.stages * s.stage_bytes + (uint32_t)(warp - 2) * NSBOX * sbox;
         int sb = 0;
         ICK_TR_DECL(2);
@@ -441,14 +449,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = bias_p ? __uint_as_float(r[j]) + bv[j] : __uint_as_float(r[j]);
-                if (p.accumulate && live) {
+                if (k_acc && live) {
                     float t[32];
-                    if (p.c_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
+                    if (k_f32) ld32_f32((const float*)p.C + (size_t)row * p.ldc + col0, false, nv, t);
                     else ld32_bf16((const bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += t[j];
                 }
-                if (p.epi == 1) {
+                if (k_epi == 1) {
                     const uint32_t rmix = second ? ick_rowmix(p.drop.seed, p.site2, (uint64_t)(row - p.split_tile * BM))
                                                  : ick_rowmix(p.drop.seed, p.drop.site, (uint64_t)row);
 #pragma unroll
@@ -462,12 +470,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                         v[j] = fmaxf(v[j], 0.f) * k0;
                         v[j + 1] = fmaxf(v[j + 1], 0.f) * k1;
                     }
-                } else if (p.epi == 2 && live) {
+                } else if (k_epi == 2 && live) {
                     float t[32];
                     ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = t[j] != 0.f ? v[j] * p.drop.inv_keep : 0.f;
-                } else if (p.epi == 3 && live) {
+                } else if (k_epi == 3 && live) {
                     float t[32];
                     ld32_bf16((const bf16*)p.aux + (size_t)row * p.ldaux + col0, full && aux_al, nv, t);
                     float acc = 0.f;
@@ -483,11 +491,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                         }
                     }
                 }
-                if (p.tma_store) {
+                if (k_tma) {
                     const uint32_t box = stg + (uint32_t)sb * sbox;
                     if (lane == 0) bulk_wait_read<NSBOX - 1>();  // the bulk store that last read this box is done with it
                     __syncwarp();
-                    if (p.c_f32) {
+                    if (k_f32) {
                         const uint32_t rowa = box + (uint32_t)lane * 128u;
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
                     sb = sb + 1 == NSBOX ? 0 : sb + 1;
                     if (warp == 2 && lane == 0) ICK_TR(8, ti.m_tile * 100 + c0 / 32);
                 } else if (live) {
-                    if (p.c_f32) st32_f32((float*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
+                    if (k_f32) st32_f32((float*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
                     else st32_bf16((bf16*)p.C + (size_t)row * p.ldc + col0, full && c_al, nv, v);
                 }
             }
@@ -526,7 +534,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const __grid_co
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.tma_store && lane == 0) bulk_wait_read<0>();  // staging boxes must outlive their stores
+        if (k_tma && lane == 0) bulk_wait_read<0>();  // staging boxes must outlive their stores
         if (warp == 2 && lane == 0) ICK_TR(9, 0);
     }
     teardown(warp, tmem_base);
@@ -1302,8 +1310,7 @@ static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C
     ICK_REQUIRE(epi >= 0 && epi <= 3 && (epi < 2 || (aux != nullptr && c_dt == ICK_BF16)) && ((epi == 3) == (rd != nullptr)),
                 "gemm_tn_tc: bad epilogue");
     if (M == 0) return ICK_OK;
-    int rc = set_smem(gemm_tn_tc_kernel);
-    if (rc) return rc;
+    int rc;
     TnParams p;
     p.C = C; p.bias = bias; p.aux = aux;
     p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.ldaux = ldaux; p.epi = epi; p.accumulate = accumulate;
@@ -1353,7 +1360,36 @@ static int gemm_tn_tc_impl(const void* A, const void* W, const void* W2, void* C
         if (cpp > p.m_tiles) cpp = p.m_tiles;
         grid = cpp * p.n_tiles_n;
     }
-    ick_launch(gemm_tn_tc_kernel, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmW2, tmC, p);
+    // specialised epilogues for the combinations the step uses (bulk-store path only); everything else reads its switches at run time
+    const int kind = p.tma_store ? (epi | (accumulate ? 4 : 0) | (p.c_f32 ? 8 : 0)) : -1;
+    // (set_smem keeps one flag per function TYPE, and all instances share theirs: a flag per kind here)
+    static bool smem_set[17] = {};
+#define ICK_TN_SMEM(KK)                                                                                                      \
+    if (!smem_set[(KK) + 1]) {                                                                                               \
+        if (cudaFuncSetAttribute(gemm_tn_tc_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { \
+            ick_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed", SMEM_BYTES);                      \
+            return ICK_ERR_CUDA;                                                                                             \
+        }                                                                                                                    \
+        smem_set[(KK) + 1] = true;                                                                                           \
+    }
+#define ICK_TN_CASE(KK)                                                                                   \
+    case KK:                                                                                              \
+        ICK_TN_SMEM(KK)                                                                                   \
+        ick_launch(gemm_tn_tc_kernel<KK>, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmW2, tmC, p);    \
+        break;
+    switch (kind) {
+        ICK_TN_CASE(0)   // bias / plain, bf16
+        ICK_TN_CASE(1)   // ReLU + dropout
+        ICK_TN_CASE(2)   // ReLU / dropout backward
+        ICK_TN_CASE(3)   // attention row term
+        ICK_TN_CASE(4)   // accumulate into bf16
+        ICK_TN_CASE(8)   // fp32 output (vocabulary scores)
+        default:
+            ICK_TN_SMEM(-1)
+            ick_launch(gemm_tn_tc_kernel<-1>, grid, NTHREADS, SMEM_BYTES, stream)(tmA, tmW, tmW2, tmC, p);
+    }
+#undef ICK_TN_CASE
+#undef ICK_TN_SMEM
     return ick_check_launch("gemm_tn_tc");
 }
 

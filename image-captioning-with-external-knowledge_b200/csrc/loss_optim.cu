@@ -70,6 +70,78 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ score
     }
 }
 
+// Register-resident variant for rows of at most CE_NT * 2 * CE_NPP columns with even W / lds / ldd (the K and N score widths): a thread
+// owns CE_NPP column PAIRS (8-byte loads, all in flight at once), the row maximum and the sum of exponentials are two passes over
+// registers with one block barrier each, and the gradient row is written from the same registers as bf16x2 / float2 - no second read
+// of the scores.  The scalar kernel above runs a dependent online-softmax chain per element (two exponentials each) and re-reads the
+// row for the gradient: 148 us for 13 056 x 10 352 scores, 17 instructions per element (ncu: issue slots 47 %, DRAM 32 %).
+constexpr int CE_NT = 512, CE_NPP = 11;
+template <typename TD>
+__global__ void __launch_bounds__(CE_NT) ce_reg_kernel(const float* __restrict__ scores, const long long* __restrict__ caps,
+                                                       const int* __restrict__ decode_len, float* __restrict__ loss_acc, TD* __restrict__ dS,
+                                                       int T_, int W, int lds, int ldd, int pad) {
+    ick_pdl_entry();
+    constexpr int NW = CE_NT / 32;
+    __shared__ float red[NW];
+    __shared__ float s_bc;
+    const int row = blockIdx.x, b = row / T_, t = row % T_, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* s = scores + (size_t)row * lds;
+    TD* d = dS ? dS + (size_t)row * ldd : nullptr;
+    long long target = pad;
+    if (t < decode_len[b] && t + 1 < T_) target = caps[(size_t)b * T_ + t + 1];
+    const bool valid = target != pad && target >= 0 && target < W;
+    if (!valid) {
+        if (d)
+            for (int c = 2 * tid; c < ldd; c += 2 * CE_NT) st2(d + c, 0.f, 0.f);
+        return;
+    }
+    float2 x[CE_NPP];
+#pragma unroll
+    for (int u = 0; u < CE_NPP; ++u) {
+        const int c = 2 * (tid + u * CE_NT);
+        x[u] = c < W ? __ldg(reinterpret_cast<const float2*>(s + c)) : make_float2(-INFINITY, -INFINITY);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < CE_NPP; ++u) m = fmaxf(m, fmaxf(x[u].x, x[u].y));
+    m = warp_max(m);
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    m = lane < NW ? red[lane] : -INFINITY;
+    m = warp_max(m);  // every warp folds the NW maxima itself
+    float l = 0.f;
+#pragma unroll
+    for (int u = 0; u < CE_NPP; ++u) {
+        x[u].x = __expf(x[u].x - m);  // exp(-inf) = 0 for the slots past the row
+        x[u].y = __expf(x[u].y - m);
+        l += x[u].x + x[u].y;
+    }
+    l = warp_sum(l);
+    __syncthreads();  // everybody has read red[]
+    if (lane == 0) red[wid] = l;
+    __syncthreads();
+    l = lane < NW ? red[lane] : 0.f;
+    l = warp_sum(l);
+    if (tid == 0) {
+        atomicAdd(loss_acc, (m + logf(l)) - s[target]);
+        atomicAdd(loss_acc + 1, 1.f);
+    }
+    if (d) {
+        const float inv = 1.f / l;
+        const int tg = (int)target;
+#pragma unroll
+        for (int u = 0; u < CE_NPP; ++u) {
+            const int c = 2 * (tid + u * CE_NT);
+            if (c < ldd) {
+                float g0 = c < W ? x[u].x * inv : 0.f, g1 = c + 1 < W ? x[u].y * inv : 0.f;
+                if (c == tg) g0 -= 1.f;
+                if (c + 1 == tg) g1 -= 1.f;
+                st2(d + c, g0, g1);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
@@ -582,7 +654,13 @@ extern "C" int ick_ce_fwd_bwd(const float* scores, const long long* captions_sor
     ICK_REQUIRE(B >= 0 && T > 0 && W > 0 && lds >= W, "ce: bad sizes");
     ICK_REQUIRE(dscores == nullptr || ldd >= W, "ce: ldd < W");
     if (B == 0) return ICK_OK;
-    if (dscores == nullptr || dt == ICK_F32)
+    const bool reg_rows = W <= CE_NT * 2 * CE_NPP && ldd <= CE_NT * 2 * CE_NPP && ((W | lds | ldd) & 1) == 0 && (((uintptr_t)scores) & 7) == 0 &&
+                          (dscores == nullptr || (((uintptr_t)dscores) & 7) == 0);
+    if (reg_rows && (dscores == nullptr || dt == ICK_F32))
+        ick_launch(ce_reg_kernel<float>, B * T, CE_NT, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (float*)dscores, T, W, lds, ldd, pad);
+    else if (reg_rows && dt == ICK_BF16)
+        ick_launch(ce_reg_kernel<bf16>, B * T, CE_NT, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (bf16*)dscores, T, W, lds, ldd, pad);
+    else if (dscores == nullptr || dt == ICK_F32)
         ick_launch(ce_kernel<float>, B * T, 256, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (float*)dscores, T, W, lds, ldd, pad);
     else if (dt == ICK_BF16)
         ick_launch(ce_kernel<bf16>, B * T, 256, 0, stream)(scores, captions_sorted, decode_len, loss_acc, (bf16*)dscores, T, W, lds, ldd, pad);

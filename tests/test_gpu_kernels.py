@@ -733,6 +733,33 @@ def test_pointer_tensor_core_path(K, Hk, S, col0, masked):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Wd", [10352, 10301, 1038, 2])
+def test_ce_row_kernels(K, Hk, dtype, Wd):
+    """Packed cross-entropy + its gradient at the reference's score widths: even widths (K / N: 10 352) run the register-resident
+    kernel, odd ones (G: 10 301) the scalar one; targets in the first and the last column, pad targets, rows behind the decode length."""
+    B, T = 4, 7
+    scores = rnd((B * T, Wd), torch.float32, 1, 3.0)
+    caps = torch.randint(1, Wd, (B, T), generator=g(2))
+    caps[0, 1] = Wd - 1  # last column
+    caps[0, 2] = 1
+    caps[1, 3:] = 0  # pad targets inside the decode length are ignored
+    dl = torch.tensor([6, 6, 4, 0], dtype=torch.int32)
+    ldd = (Wd + 7) // 8 * 8
+    accr, accg = torch.zeros(2), torch.zeros(2).cuda()
+    dr, dg = torch.zeros(B * T, ldd, dtype=dtype), torch.full((B * T, ldd), float("nan"), dtype=dtype).cuda()
+    Hk.ce(scores, caps, dl, accr, dr, B, T, Wd, 0)
+    K.ce(cu(scores), cu(caps), cu(dl), accg, dg, B, T, Wd, 0)
+    assert float(accg[1]) == float(accr[1]) and abs(float(accg[0]) - float(accr[0])) < 1e-4 * float(accr[0])
+    assert not torch.isnan(dg.float()).any()
+    assert err(dg, dr) < TOL[dtype]
+    # the gradient rows sum to zero (softmax - onehot) on valid rows and are exactly zero elsewhere
+    rs = dg.float().sum(1).cpu()
+    valid = (dr.float().abs().sum(1) > 0)
+    assert float(rs[valid].abs().max()) < (1e-4 if dtype == torch.float32 else 5e-2)
+    assert float(dg.float().cpu()[~valid].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_ce_adam_misc(K, Hk, dtype):
     B, T, Wd = 5, 9, 1037
     scores = rnd((B * T, Wd), torch.float32, 1, 3.0)

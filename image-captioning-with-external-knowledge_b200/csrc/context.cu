@@ -258,20 +258,24 @@ __global__ void __launch_bounds__(256) caption_embed_bwd_kernel(const T* __restr
 }
 
 // ---- pixels: (B, D, P) fp32 channel-major  <->  memory rows (b*M + p, c) ------------------------------------------------
+// 64 channels x 32 pixels per CTA: a warp reads 32 consecutive pixels of a channel (128 bytes) and writes 64 consecutive channels of a
+// pixel as element pairs (128 bytes in bf16; the 32 x 32 version wrote 64-byte rows of single elements); ld must be even.
 template <typename T>
 __global__ void __launch_bounds__(256) pixels_fwd_kernel(const float* __restrict__ enc, T* __restrict__ mem, int D, int P, int M, int ld) {
     ick_pdl_entry();
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    __shared__ float tile[64][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int i = ty; i < 32; i += 8) {
+#pragma unroll
+    for (int i = ty; i < 64; i += 8) {
         const int c = c0 + i, p = p0 + tx;
-        tile[i][tx] = (c < D && p < P) ? enc[((size_t)b * D + c) * P + p] : 0.f;
+        tile[i][tx] = (c < D && p < P) ? __ldg(enc + ((size_t)b * D + c) * P + p) : 0.f;
     }
     __syncthreads();
+#pragma unroll
     for (int i = ty; i < 32; i += 8) {
-        const int p = p0 + i, c = c0 + tx;
-        if (p < P && c < ld) mem[((size_t)b * M + p) * ld + c] = from_f<T>(c < D ? tile[tx][i] : 0.f);
+        const int p = p0 + i, c = c0 + 2 * tx;
+        if (p < P && c < ld) st2(mem + ((size_t)b * M + p) * ld + c, c < D ? tile[2 * tx][i] : 0.f, c + 1 < D ? tile[2 * tx + 1][i] : 0.f);
     }
 }
 
@@ -823,7 +827,8 @@ extern "C" int ick_caption_embed_bwd(const void* dX, const long long* captions, 
 extern "C" int ick_pixels_fwd(const float* encoder_out, void* memory, int dt, int B, int D, int P, int M, int ld, cudaStream_t stream) {
     ICK_REQUIRE(P <= M && D <= ld, "pixels_fwd: bad sizes");
     if (B * P == 0) return ICK_OK;
-    dim3 grid((P + 31) / 32, (ld + 31) / 32, B);
+    ICK_REQUIRE(ld % 2 == 0, "pixels_fwd: ld must be even");
+    dim3 grid((P + 31) / 32, (ld + 63) / 64, B);
     if (dt == ICK_F32) ick_launch(pixels_fwd_kernel<float>, grid, 256, 0, stream)(encoder_out, (float*)memory, D, P, M, ld);
     else if (dt == ICK_BF16) ick_launch(pixels_fwd_kernel<bf16>, grid, 256, 0, stream)(encoder_out, (bf16*)memory, D, P, M, ld);
     else ICK_BAD_DT("pixels_fwd", dt);

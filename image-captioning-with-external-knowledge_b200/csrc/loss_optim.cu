@@ -261,6 +261,19 @@ __global__ void __launch_bounds__(256) accum_f32_kernel(const T* __restrict__ sr
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] += to_f(src[i]);
 }
+// eight elements per thread (16-byte source loads for bf16, two 16-byte read-modify-writes of the fp32 destination)
+template <typename T>
+__global__ void __launch_bounds__(256) accum_f32_v8_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n8) {
+    ick_pdl_entry();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        ld8(src + 8 * i, a);
+        ld8(dst + 8 * i, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] += a[j];
+        st8(dst + 8 * i, b);
+    }
+}
 
 // out[c] += sum_r x[r, c]; grid-stride over row blocks, columns across threads
 template <typename T>
@@ -269,9 +282,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
     ick_pdl_entry();
     const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
     for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float s = 0.f;
-        for (long long r = r0; r < r1; ++r) s += to_f(x[r * ld + c]);
-        atomicAdd(out + c, s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four rows in flight (one dependent add chain per column was latency-bound)
+        long long r = r0;
+        for (; r + 3 < r1; r += 4) {
+            s0 += to_f(x[r * ld + c]);
+            s1 += to_f(x[(r + 1) * ld + c]);
+            s2 += to_f(x[(r + 2) * ld + c]);
+            s3 += to_f(x[(r + 3) * ld + c]);
+        }
+        for (; r < r1; ++r) s0 += to_f(x[r * ld + c]);
+        atomicAdd(out + c, (s0 + s1) + (s2 + s3));
     }
 }
 
@@ -741,6 +761,11 @@ extern "C" int ick_cast2d(const void* src, int src_dt, void* dst, int dst_dt, lo
 
 extern "C" int ick_accum_f32(const void* src, int dt, float* dst, long long n, cudaStream_t stream) {
     if (n == 0) return ICK_OK;
+    if (n % 8 == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 31) == 0 && (dt == ICK_F32 || dt == ICK_BF16)) {
+        if (dt == ICK_F32) ick_launch(accum_f32_v8_kernel<float>, ew_grid(n / 8), 256, 0, stream)((const float*)src, dst, n / 8);
+        else ick_launch(accum_f32_v8_kernel<bf16>, ew_grid(n / 8), 256, 0, stream)((const bf16*)src, dst, n / 8);
+        return ick_check_launch("accum_f32");
+    }
     if (dt == ICK_F32) ick_launch(accum_f32_kernel<float>, ew_grid(n), 256, 0, stream)((const float*)src, dst, n);
     else if (dt == ICK_BF16) ick_launch(accum_f32_kernel<bf16>, ew_grid(n), 256, 0, stream)((const bf16*)src, dst, n);
     else {
@@ -752,7 +777,7 @@ extern "C" int ick_accum_f32(const void* src, int dt, float* dst, long long n, c
 
 extern "C" int ick_colsum(const void* x, int dt, float* out, long long rows, int cols, int ld, cudaStream_t stream) {
     if (rows == 0 || cols == 0) return ICK_OK;
-    const int rpb = 64;
+    const int rpb = 32;  // 13 056 rows -> 408 blocks
     const int grid = (int)((rows + rpb - 1) / rpb);
     if (dt == ICK_F32) ick_launch(colsum_kernel<float>, grid, 256, 0, stream)((const float*)x, out, rows, cols, ld, rpb);
     else if (dt == ICK_BF16) ick_launch(colsum_kernel<bf16>, grid, 256, 0, stream)((const bf16*)x, out, rows, cols, ld, rpb);

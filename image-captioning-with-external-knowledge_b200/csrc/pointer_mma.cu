@@ -126,17 +126,32 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     const int d0 = blockIdx.x * CWB, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     for (int s = threadIdx.x; s < Sp; s += NT) ft[s] = (first_t != nullptr && s < S) ? first_t[(size_t)b * S + s] : -0x40000000;
-    for (int idx = threadIdx.x; idx < Sp * (CWB / 8); idx += NT) {
-        const int s = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
-        uint4 v = zero4();
-        if (s < S && d0 + c < ld) v = *reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s) * ld + d0 + c);
-        *reinterpret_cast<uint4*>(cs + (size_t)s * CLD + c) = v;
+    // ctx / h column slices: up to four 16-byte loads requested per thread before the first shared-memory store
+    for (int idx0 = threadIdx.x; idx0 < Sp * (CWB / 8); idx0 += 4 * NT) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * NT, s = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
+            v[u] = (idx < Sp * (CWB / 8) && s < S && d0 + c < ld) ? __ldg(reinterpret_cast<const uint4*>(ctx + ((size_t)b * S + s) * ld + d0 + c)) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * NT, s = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
+            if (idx < Sp * (CWB / 8)) *reinterpret_cast<uint4*>(cs + (size_t)s * CLD + c) = v[u];
+        }
     }
-    for (int idx = threadIdx.x; idx < Tp * (CWB / 8); idx += NT) {
-        const int t = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
-        uint4 v = zero4();
-        if (t < T && d0 + c < ld) v = *reinterpret_cast<const uint4*>(h + ((size_t)b * T + t) * ld + d0 + c);
-        *reinterpret_cast<uint4*>(hs + (size_t)t * CLD + c) = v;
+    for (int idx0 = threadIdx.x; idx0 < Tp * (CWB / 8); idx0 += 2 * NT) {
+        uint4 v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = idx0 + u * NT, t = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
+            v[u] = (idx < Tp * (CWB / 8) && t < T && d0 + c < ld) ? __ldg(reinterpret_cast<const uint4*>(h + ((size_t)b * T + t) * ld + d0 + c)) : zero4();
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = idx0 + u * NT, t = idx / (CWB / 8), c = (idx % (CWB / 8)) * 8;
+            if (idx < Tp * (CWB / 8)) *reinterpret_cast<uint4*>(hs + (size_t)t * CLD + c) = v[u];
+        }
     }
     __syncthreads();  // ft visible
     // dS tile (+ mask); the slice may start at an odd column (col0 = V + E), so pairs are used only when 4-byte aligned
@@ -147,24 +162,34 @@ __global__ void __launch_bounds__(NT) pointer_bwd_mma_kernel(const bf16* __restr
     // flight per thread.  The tail chunk is cut at S (the columns behind it belong to the next head).
     const bool vec_ok = first_t == nullptr && ((col0 | ldds) & 7) == 0 && ((reinterpret_cast<uintptr_t>(dS) & 15) == 0);
     if (vec_ok) {
+        // EIGHT 16-byte loads requested per thread before the first is used (ncu source view, profiles/README.md r03b: a third of the
+        // kernel's stall samples sat on the first use of each single load of this loop); the bias-gradient sum only where it is used
         const int sp8 = Sp / 8;
-#pragma unroll 4
-        for (int idx = threadIdx.x; idx < Tp * sp8; idx += NT) {
-            const int t = idx / sp8, s8 = (idx % sp8) * 8;
-            uint4 v = zero4();
-            if (t < T && s8 < S) {
-                v = *reinterpret_cast<const uint4*>(dS + ((size_t)b * T + t) * ldds + col0 + s8);
-                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&v);
+        const bool want_bsum = blockIdx.x == 0;
+        for (int idx0 = threadIdx.x; idx0 < Tp * sp8; idx0 += 8 * NT) {
+            uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float2 f = __bfloat1622float2(hp[i]);
-                    if (s8 + 2 * i >= S) f.x = 0.f;
-                    if (s8 + 2 * i + 1 >= S) f.y = 0.f;
-                    if (s8 + 8 > S) hp[i] = __floats2bfloat162_rn(f.x, f.y);
-                    bsum += f.x + f.y;
-                }
+            for (int u = 0; u < 8; ++u) {
+                const int idx = idx0 + u * NT, t = idx / sp8, s8 = (idx % sp8) * 8;
+                v[u] = (idx < Tp * sp8 && t < T && s8 < S) ? __ldg(reinterpret_cast<const uint4*>(dS + ((size_t)b * T + t) * ldds + col0 + s8)) : zero4();
             }
-            *reinterpret_cast<uint4*>(ds + (size_t)t * DLD + s8) = v;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = idx0 + u * NT, t = idx / sp8, s8 = (idx % sp8) * 8;
+                if (idx >= Tp * sp8) break;
+                if (s8 + 8 > S || want_bsum) {  // ragged tail chunk of a row (the columns behind S belong to the next head), or the sum
+                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&v[u]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float2 f = __bfloat1622float2(hp[i]);
+                        if (s8 + 2 * i >= S) f.x = 0.f;
+                        if (s8 + 2 * i + 1 >= S) f.y = 0.f;
+                        if (s8 + 8 > S) hp[i] = __floats2bfloat162_rn(f.x, f.y);
+                        bsum += f.x + f.y;
+                    }
+                }
+                *reinterpret_cast<uint4*>(ds + (size_t)t * DLD + s8) = v[u];
+            }
         }
     } else
     for (int idx = threadIdx.x; idx < Tp * sp2; idx += NT) {

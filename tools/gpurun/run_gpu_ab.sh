@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-R=${R:-r03d}
-(timeout 400 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -x --timeout 300 -k "pixels or ce_ or pool or indicators" 2>&1 | tail -n 15) > gpurun_out/${R}_kernels.log
+R=${R:-r03f}
+(timeout 400 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short -x --timeout 300 -k "pointer or indicators or grouped" 2>&1 | tail -n 15) > gpurun_out/${R}_kernels.log
 tail -n 6 gpurun_out/${R}_kernels.log
 (timeout 600 python -m pytest tests/test_gpu_model.py tests/test_gpu_baseline_parity.py -m gpu -q --tb=short -x --timeout 500 2>&1 | tail -n 8) > gpurun_out/${R}_model.log
 tail -n 4 gpurun_out/${R}_model.log

@@ -1,7 +1,10 @@
 mkdir -p gpurun_out
-R=r87
-N=${1:-8}
-(timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 50 --warmup 3 --workload news_b8 --no-decode --no-trim-extra --no-cpu-baseline 2> gpurun_out/${R}_bench${N}_news.err | tail -n 1) > gpurun_out/${R}_bench${N}_news.json; echo "rc=$?"
-cut -c1-300 gpurun_out/${R}_bench${N}_news.json; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/${R}_bench${N}_news.err | tail -n 4 | cut -c1-300
-python -c "
-import json; d=json.loads(open('gpurun_out/${R}_bench${N}_news.json').read()); print(d['value'], d['e2e'], d['config']['cuda_graph'], d['config']['global_batch'])"
+R=${R:-r03h}
+N=8
+(timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 3 2> gpurun_out/${R}_bench${N}.err | tail -n 1) > gpurun_out/${R}_bench${N}.json; echo "default rc=$?"
+cut -c1-260 gpurun_out/${R}_bench${N}.json
+grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/${R}_bench${N}.err | tail -n 4 | cut -c1-300
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/${R}_bench${N}.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['greedy_decode']['value'], d['beam5_decode']['value'], {k:v['value'] for k,v in d['configs'].items()})
+PY

@@ -5,8 +5,10 @@ the reference's effective defaults, G/train.py:71-78), one step = forward + mask
 clamp(+-5) + Adam + operand re-pack (G/train.py:263-297) on synthetic inputs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 our arm   (torchrun for N > 1)
-    python bench.py --impl reference [--steps K] [--warmup W]           reference arm: the CPU port of the reference
-                                                                        (oracle/) on all host cores, same workload shape
+    python bench.py --impl reference [--steps K] [--warmup W]           reference arm: the UNMODIFIED reference models.py
+                                                                        (oracle/_ref, copied by oracle/make_ref.py; the oracle
+                                                                        port only if that is absent) + train.py's step recipe
+                                                                        on all host cores, same workload shape, bounded sample
 
     python bench.py --workload geo_b32 | news_b8 | geo_e2e_b256          the other BASELINE.json configs (geo_e2e_b256 = configs[4]:
                                                                         raw fp16 images -> image prep -> ResNet-101 on cuDNN ->
@@ -15,9 +17,11 @@ clamp(+-5) + Adam + operand re-pack (G/train.py:263-297) on synthetic inputs.
 Prints ONE JSON line (rank 0).  `value` = whole-job captions/s with inputs resident in HBM; `e2e` = the same through the
 public call with pinned HOST buffers, H2D copies and a D2H read of the loss inside the timed region; `roofline` = the
 dominant kernel family of the step (CUDA-event time per launch, measured live in a separate instrumented pass over the
-same steps) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port timed on this box's host cores (N=1 only).
+same steps, each queued behind a GPU spin so that the events bracket kernels that run back to back) against MEASURED_PEAKS.json;
+`cpu_baseline` = the reference's CPU path (oracle/_ref, else the oracle port) timed on this box's host cores (N=1 only).
 Extras on the same line: `greedy_decode` (625 images per GPU through predict_batch, with `roofline_step_attention` = the per-step
-cross-attention kernel timed alone against the HBM peak), `beam5_decode` (beam search, an extension without a reference arm),
+cross-attention kernel timed alone against the HBM peak), `beam5_decode` (beam search, an extension without a reference arm; same
+roofline entry for its 5-beam cross-attention kernel),
 `trimmed_padding` (dynamic padding) and, at N = 1, `encoder_e2e` (configs[4] in short).
 """
 import argparse
